@@ -1,0 +1,948 @@
+"""CPU oracle for the VBN batched posterior-inference hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in ``vectorizedbayesiannetwork_b200/`` may import
+this module; only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs use it, and only as the checker or the
+timed CPU baseline -- never as the product path.
+
+It is a functional torch-CPU restatement of the reference algorithm (the reference
+itself is pure Python + torch, so torch on the host IS the reference's arithmetic;
+SURVEY.md section 8c).  Every function cites the reference ``file:line`` it follows
+(paths relative to /root/reference).  The model is a plain ``spec`` dict of tensors
+(see ``spec_from_reference``), not ``nn.Module`` objects.
+
+Parity pinning: ``tests/test_oracle_pin.py`` checks (in the build container, where
+/root/reference exists) that this oracle reproduces the unmodified reference
+BIT-FOR-BIT under the same ``torch.manual_seed`` for every CPD kind and every
+inference method on the path, and ``tests/golden/*.pt`` holds input/noise/output
+vectors recorded from the reference itself (generator: ``tests/golden/make_golden.py``)
+that travel to the GPU box.
+
+Randomness is routed through a *noise source* so the same draw can be
+  * taken from torch's global generator exactly like the reference does (``TorchNoise``),
+  * recorded (``RecordingNoise``) and
+  * replayed / injected (``ReplayNoise``) -- the CUDA path accepts the same tensors.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+LOG_2PI = math.log(2 * math.pi)
+
+# --------------------------------------------------------------------------------------
+# noise sources
+# --------------------------------------------------------------------------------------
+
+
+class TorchNoise:
+    """Draws from torch's global generator with the same calls the reference makes
+    (SURVEY.md Appendix B), so a run under ``torch.manual_seed(k)`` consumes the stream
+    identically to the reference."""
+
+    def normal(self, key, like: torch.Tensor) -> torch.Tensor:
+        # torch.randn_like(scale)  (linear_gaussian.py:195, gaussian_nn.py:260, mdn.py:234, kde.py:180)
+        return torch.randn_like(like)
+
+    def normal_shape(self, key, shape, like: torch.Tensor) -> torch.Tensor:
+        # Normal(loc, scale).sample((b, S)) == loc + scale * randn(shape)  (gaussian_nn.py:254)
+        return torch.randn(shape, dtype=like.dtype, device=like.device)
+
+    def uniform(self, key, like: torch.Tensor) -> torch.Tensor:
+        # torch.rand_like(center)  (softmax_nn.py:666, 669)
+        return torch.rand_like(like)
+
+    def categorical_probs(self, key, probs: torch.Tensor) -> torch.Tensor:
+        # Categorical(probs=...).sample()  (mdn.py:229)
+        return torch.distributions.Categorical(probs=probs).sample()
+
+    def categorical_logits(self, key, logits: torch.Tensor) -> torch.Tensor:
+        # Categorical(logits=...).sample()  (softmax_nn.py:651-652)
+        return torch.distributions.Categorical(logits=logits).sample()
+
+    def multinomial(self, key, weights: torch.Tensor) -> torch.Tensor:
+        # torch.multinomial(weights, 1).squeeze(-1)  (kde.py:178)
+        return torch.multinomial(weights, num_samples=1).squeeze(-1)
+
+    def randint(self, key, n: int, count: int, device) -> torch.Tensor:
+        # torch.randint(0, n, (count,))  (kde.py:170)
+        return torch.randint(0, n, (count,), device=device)
+
+
+class RecordingNoise(TorchNoise):
+    """TorchNoise that also stores every draw under its key (list per key, call order)."""
+
+    def __init__(self) -> None:
+        self.log: Dict[Tuple, List[torch.Tensor]] = {}
+
+    def _rec(self, key, value):
+        self.log.setdefault(tuple(key), []).append(value.clone())
+        return value
+
+    def normal(self, key, like):
+        return self._rec(key + ("eps",), super().normal(key, like))
+
+    def normal_shape(self, key, shape, like):
+        return self._rec(key + ("eps",), super().normal_shape(key, shape, like))
+
+    def uniform(self, key, like):
+        return self._rec(key + ("u",), super().uniform(key, like))
+
+    def categorical_probs(self, key, probs):
+        return self._rec(key + ("idx",), super().categorical_probs(key, probs))
+
+    def categorical_logits(self, key, logits):
+        return self._rec(key + ("idx",), super().categorical_logits(key, logits))
+
+    def multinomial(self, key, weights):
+        return self._rec(key + ("idx",), super().multinomial(key, weights))
+
+    def randint(self, key, n, count, device):
+        return self._rec(key + ("idx",), super().randint(key, n, count, device))
+
+
+class ReplayNoise:
+    """Replays a ``RecordingNoise.log`` (or a hand-built dict) in call order."""
+
+    def __init__(self, log: Dict[Tuple, Sequence[torch.Tensor]]) -> None:
+        self.log = {tuple(k): list(v) for k, v in log.items()}
+        self.pos: Dict[Tuple, int] = {}
+
+    def _next(self, key):
+        key = tuple(key)
+        i = self.pos.get(key, 0)
+        self.pos[key] = i + 1
+        return self.log[key][i]
+
+    def normal(self, key, like):
+        return self._next(key + ("eps",)).to(like.dtype).reshape(like.shape)
+
+    def normal_shape(self, key, shape, like):
+        return self._next(key + ("eps",)).to(like.dtype).reshape(shape)
+
+    def uniform(self, key, like):
+        return self._next(key + ("u",)).to(like.dtype).reshape(like.shape)
+
+    def categorical_probs(self, key, probs):
+        return self._next(key + ("idx",)).reshape(probs.shape[:-1])
+
+    def categorical_logits(self, key, logits):
+        return self._next(key + ("idx",)).reshape(logits.shape[:-1])
+
+    def multinomial(self, key, weights):
+        return self._next(key + ("idx",)).reshape(weights.shape[:-1])
+
+    def randint(self, key, n, count, device):
+        return self._next(key + ("idx",)).reshape(count)
+
+
+# --------------------------------------------------------------------------------------
+# shape helpers (vbn/core/utils.py:56-82)
+# --------------------------------------------------------------------------------------
+
+
+def ensure_2d(x: torch.Tensor) -> torch.Tensor:
+    if x.dim() == 1:
+        return x.unsqueeze(-1)
+    if x.dim() == 2:
+        return x
+    raise ValueError(f"Expected 1D or 2D tensor, got shape {tuple(x.shape)}")
+
+
+def broadcast_samples(x: torch.Tensor, n: int) -> torch.Tensor:
+    if x.dim() == 2:
+        return x.unsqueeze(1).expand(-1, n, -1)
+    if x.dim() == 3:
+        return x
+    raise ValueError(f"Expected 2D or 3D tensor, got shape {tuple(x.shape)}")
+
+
+def _x3(x: torch.Tensor) -> torch.Tensor:
+    if x.dim() <= 2:
+        x = ensure_2d(x)
+    if x.dim() == 2:
+        x = x.unsqueeze(1)
+    return x
+
+
+_ACT = {"relu": F.relu, "tanh": torch.tanh, "gelu": F.gelu, "elu": F.elu}
+
+
+def mlp_forward(layers, activation: str, x: torch.Tensor) -> torch.Tensor:
+    """nn.Sequential(Linear, act, ..., Linear)  (gaussian_nn.py:16-34 ``_build_mlp``)."""
+    act = _ACT[activation]
+    last = len(layers) - 1
+    for i, (w, b) in enumerate(layers):
+        x = F.linear(x, w, b)
+        if i != last:
+            x = act(x)
+    return x
+
+
+def softplus_min(x: torch.Tensor, min_val: float) -> torch.Tensor:
+    """safe_softplus (vbn/cpds/utils.py:6-7): F.softplus (beta=1, threshold=20) + min."""
+    return F.softplus(x) + float(min_val)
+
+
+def gaussian_logpdf_sum(x, loc, scale):
+    """-0.5*sum_d[(x-loc)^2/scale^2 + 2 ln scale + ln 2pi]  (linear_gaussian.py:214-217)."""
+    var = scale**2
+    return -0.5 * (((x - loc) ** 2) / var + 2 * torch.log(scale) + LOG_2PI).sum(dim=-1)
+
+
+# --------------------------------------------------------------------------------------
+# linear_gaussian  (vbn/cpds/linear_gaussian.py:163-217)
+# --------------------------------------------------------------------------------------
+
+
+def lg_scale(c) -> torch.Tensor:
+    return torch.sqrt(c["var"].clamp(min=float(c["min_scale"]) ** 2))  # :163-165
+
+
+def lg_params(c, parents: Optional[torch.Tensor]):
+    if c["input_dim"] == 0:
+        return c["bias"], lg_scale(c)
+    if parents.dim() == 2:
+        parents = parents.unsqueeze(1)
+    b, s, dp = parents.shape
+    mu = parents.reshape(b * s, dp) @ c["weight"] + c["bias"]  # :180
+    loc = mu.reshape(b, s, c["output_dim"])
+    scale = lg_scale(c).view(1, 1, -1).expand(b, s, -1)
+    return loc, scale
+
+
+def lg_sample(c, parents, n, noise, key):
+    if c["input_dim"] == 0:
+        b = 1 if parents is None else parents.shape[0]  # :187
+        loc = c["bias"].view(1, 1, -1).expand(b, n, -1)
+        scale = lg_scale(c).view(1, 1, -1).expand(b, n, -1)
+    else:
+        if parents is None:
+            raise ValueError("parents cannot be None when input_dim > 0")
+        loc, scale = lg_params(c, broadcast_samples(parents, n))
+    eps = noise.normal(key, scale)  # :195
+    return loc + eps * scale
+
+
+def lg_log_prob(c, x, parents):
+    x = _x3(x)
+    if c["input_dim"] == 0:
+        b, s, _ = x.shape
+        loc = c["bias"].view(1, 1, -1).expand(b, s, -1)
+        scale = lg_scale(c).view(1, 1, -1).expand(b, s, -1)
+    else:
+        if parents is None:
+            raise ValueError("parents cannot be None when input_dim > 0")
+        loc, scale = lg_params(c, broadcast_samples(parents, x.shape[1]))
+    return gaussian_logpdf_sum(x, loc, scale)
+
+
+# --------------------------------------------------------------------------------------
+# gaussian_nn  (vbn/cpds/gaussian_nn.py:105-119, 215-288)
+# --------------------------------------------------------------------------------------
+
+
+def gnn_params(c, parents: Optional[torch.Tensor]):
+    d = c["output_dim"]
+    mean_y = c["mean_y"].view(1, 1, -1)
+    std_y = c["std_y"].view(1, 1, -1)
+    if c["input_dim"] == 0:
+        loc = c["loc"].view(1, 1, -1)
+        scale = softplus_min(c["log_scale"], c["min_scale"]).view(1, 1, -1)
+        return loc * std_y + mean_y, scale * std_y  # :114-119
+    if parents.dim() == 2:
+        parents = parents.unsqueeze(1)
+    z = (parents - c["mean_x"].view(1, 1, -1)) / c["std_x"].view(1, 1, -1)  # :105-112
+    b, s, dp = z.shape
+    out = mlp_forward(c["layers"], c["activation"], z.reshape(b * s, dp)).reshape(b, s, 2 * d)
+    loc = out[..., :d]
+    scale = softplus_min(out[..., d:], c["min_scale"])
+    return loc * std_y + mean_y, scale * std_y
+
+
+def gnn_sample(c, parents, n, noise, key):
+    if c["input_dim"] == 0:
+        b = 1 if parents is None else parents.shape[0]
+        loc, scale = gnn_params(c, None)
+        loc, scale = loc.squeeze(0).squeeze(0), scale.squeeze(0).squeeze(0)
+        # Normal(loc, scale).sample((b, n))  (:244-254)
+        eps = noise.normal_shape(key, (b, n) + tuple(loc.shape), loc)
+        return loc + eps * scale
+    if parents is None:
+        raise ValueError("parents cannot be None when input_dim > 0")
+    loc, scale = gnn_params(c, broadcast_samples(parents, n))
+    eps = noise.normal(key, scale)  # :260
+    return loc + eps * scale
+
+
+def gnn_log_prob(c, x, parents):
+    x = _x3(x)
+    if c["input_dim"] == 0:
+        loc, scale = gnn_params(c, None)
+        loc, scale = loc.squeeze(0).squeeze(0), scale.squeeze(0).squeeze(0)
+        # torch.distributions.Normal.log_prob  (:263-278)
+        var = scale**2
+        lp = -((x - loc) ** 2) / (2 * var) - scale.log() - math.log(math.sqrt(2 * math.pi))
+        return lp.sum(dim=-1)
+    if parents is None:
+        raise ValueError("parents cannot be None when input_dim > 0")
+    loc, scale = gnn_params(c, broadcast_samples(parents, x.shape[1]))
+    return gaussian_logpdf_sum(x, loc, scale)
+
+
+# --------------------------------------------------------------------------------------
+# mdn  (vbn/cpds/mdn.py:185-272)
+# --------------------------------------------------------------------------------------
+
+
+def mdn_params(c, parents: Optional[torch.Tensor]):
+    k, d = c["n_components"], c["output_dim"]
+    if c["input_dim"] == 0:
+        return c["logits"], c["loc"], softplus_min(c["log_scale"], c["min_scale"])
+    if parents.dim() == 2:
+        parents = parents.unsqueeze(1)
+    b, s, dp = parents.shape
+    out = mlp_forward(c["layers"], c["activation"], parents.reshape(b * s, dp)).reshape(b, s, -1)
+    logits = out[..., :k]
+    rest = out[..., k:].reshape(b, s, k, 2 * d)  # :200-203
+    loc = rest[..., :d]
+    scale = softplus_min(rest[..., d:], c["min_scale"])
+    return logits, loc, scale
+
+
+def mdn_mixture_weights(logits):
+    pi = torch.softmax(logits, dim=-1).clamp_min(1e-5)  # :227 / :269
+    return pi / pi.sum(dim=-1, keepdim=True).clamp_min(1e-12)
+
+
+def mdn_sample(c, parents, n, noise, key):
+    k, d = c["n_components"], c["output_dim"]
+    if c["input_dim"] == 0:
+        b = 1 if parents is None else parents.shape[0]
+        logits = c["logits"].view(1, 1, -1).expand(b, n, -1)
+        loc = c["loc"].view(1, 1, k, d).expand(b, n, -1, -1)
+        scale = softplus_min(c["log_scale"], c["min_scale"]).view(1, 1, k, d).expand(b, n, -1, -1)
+    else:
+        if parents is None:
+            raise ValueError("parents cannot be None when input_dim > 0")
+        logits, loc, scale = mdn_params(c, broadcast_samples(parents, n))
+    b, s, _ = logits.shape
+    pi = mdn_mixture_weights(logits)
+    comps = noise.categorical_probs(key, pi.reshape(b * s, -1)).reshape(b, s)  # :229
+    idx = comps.unsqueeze(-1).unsqueeze(-1).expand(-1, -1, 1, d)
+    loc = loc.gather(dim=2, index=idx).squeeze(2)
+    scale = scale.gather(dim=2, index=idx).squeeze(2)
+    eps = noise.normal(key, loc)  # :234
+    return loc + eps * scale
+
+
+def mdn_log_prob(c, x, parents):
+    k, d = c["n_components"], c["output_dim"]
+    x = _x3(x)
+    if c["input_dim"] == 0:
+        b, s, _ = x.shape
+        logits = c["logits"].view(1, 1, -1).expand(b, s, -1)
+        loc = c["loc"].view(1, 1, k, d).expand(b, s, -1, -1)
+        scale = softplus_min(c["log_scale"], c["min_scale"])
+        log_scale = torch.log(scale.view(1, 1, k, d).expand(b, s, -1, -1))
+    else:
+        if parents is None:
+            raise ValueError("parents cannot be None when input_dim > 0")
+        logits, loc, scale = mdn_params(c, broadcast_samples(parents, x.shape[1]))
+        log_scale = torch.log(scale)
+    x_exp = x.unsqueeze(2).expand(-1, -1, k, -1)
+    var = torch.exp(2 * log_scale)  # :265
+    log_comp = -0.5 * (((x_exp - loc) ** 2) / var + 2 * log_scale + LOG_2PI).sum(dim=-1)
+    log_pi = torch.log(mdn_mixture_weights(logits))
+    return torch.logsumexp(log_pi + log_comp, dim=-1)  # :272
+
+
+# --------------------------------------------------------------------------------------
+# softmax_nn  (vbn/cpds/softmax_nn.py:581-759)
+# --------------------------------------------------------------------------------------
+
+
+def snn_logits(c, parents: Optional[torch.Tensor], b: int, s: int) -> torch.Tensor:
+    d, k = c["output_dim"], c["n_classes"]
+    t = float(c.get("temperature", 1.0))
+    if c["input_dim"] == 0:
+        if c["root_ready"]:  # :636-641
+            logits = c["root_log_probs"].view(1, 1, d, k).expand(b, s, -1, -1)
+            return torch.log_softmax(logits / t, dim=-1)
+        return c["logits"].view(1, 1, d, k).expand(b, s, -1, -1) / t
+    if parents.dim() == 2:
+        parents = parents.unsqueeze(1)
+    pb, ps, dp = parents.shape
+    out = mlp_forward(c["layers"], c["activation"], parents.reshape(pb * ps, dp))
+    return out.reshape(pb, ps, d, k) / t  # :581-587
+
+
+def snn_gather_bin_edges(c, indices: torch.Tensor):
+    """(:589-610)"""
+    d, k = c["output_dim"], c["n_classes"]
+    edges = c["bin_edges"]
+    if indices.dim() == 3:
+        d_idx = torch.arange(d).view(1, 1, -1).expand(indices.shape[0], indices.shape[1], -1)
+    else:
+        d_idx = torch.arange(d).view(1, -1).expand(indices.shape[0], -1)
+    idx = indices.clamp(min=0, max=k - 1)
+    left = edges[d_idx, idx]
+    right = edges[d_idx, (idx + 1).clamp(max=k)]
+    width = torch.clamp(right - left, min=float(c["min_bin_width"]))
+    center = 0.5 * (left + right)
+    return left, right, width, center
+
+
+def snn_x_to_bin(c, x: torch.Tensor) -> torch.Tensor:
+    """(:612-630)"""
+    if not c["bins_ready"]:
+        raise RuntimeError("Bins not initialized. Call fit(...) before sampling.")
+    k = c["n_classes"]
+    edges = c["bin_edges"].to(dtype=x.dtype)
+    flat = x.reshape(-1, x.shape[-1])
+    cont = (flat.unsqueeze(-1) >= edges.unsqueeze(0)).sum(dim=-1) - 1
+    cont = cont.clamp(min=0, max=k - 1)
+    is_disc = c["is_discrete"]
+    if bool(is_disc.any()):
+        cv = c["class_values"].to(dtype=x.dtype)
+        match = flat.unsqueeze(-1) == cv.unsqueeze(0)
+        disc = match.long().argmax(dim=-1)
+        missing = (~match.any(dim=-1)) & is_disc.unsqueeze(0)
+        if bool(missing.any()):
+            raise ValueError("Found values outside discrete class set.")
+        bins = torch.where(is_disc.unsqueeze(0), disc, cont)
+    else:
+        bins = cont
+    return bins.reshape(*x.shape)
+
+
+def snn_sample(c, parents, n, noise, key):
+    if not c["bins_ready"]:
+        raise RuntimeError("Bins not initialized. Call fit(...) before sampling.")
+    d, k = c["output_dim"], c["n_classes"]
+    if c["input_dim"] == 0:
+        b = 1 if parents is None else parents.shape[0]
+        logits = snn_logits(c, None, b, n)
+    else:
+        if parents is None:
+            raise ValueError("parents cannot be None when input_dim > 0")
+        logits = snn_logits(c, broadcast_samples(parents, n), 0, 0)
+    indices = noise.categorical_logits(key, logits)  # :651-652
+    values = c["sample_values"].to(dtype=logits.dtype).view(1, 1, d, k)
+    values = values.expand(indices.shape[0], indices.shape[1], -1, -1)
+    disc_values = values.gather(-1, indices.unsqueeze(-1)).squeeze(-1)
+    left, right, width, center = snn_gather_bin_edges(c, indices)
+    wb = c["within_bin"]
+    if wb == "uniform":
+        u = noise.uniform(key, center)
+        cont = left + u * width
+    elif wb == "triangular":
+        u = noise.uniform(key, center)
+        lv = left + width * torch.sqrt(torch.clamp(u * 0.5, min=0.0))
+        rv = right - width * torch.sqrt(torch.clamp((1.0 - u) * 0.5, min=0.0))
+        cont = torch.where(u < 0.5, lv, rv)
+    elif wb == "gaussian":
+        sigma = torch.clamp(float(c["within_bin_scale"]) * width, min=float(c["min_bin_width"]))
+        cont = center + noise.normal(key, center) * sigma
+    else:
+        raise ValueError(f"Unknown within_bin '{wb}'")
+    if c["within_bin_clip"]:
+        cont = cont.clamp(min=left, max=right)
+    is_disc = c["is_discrete"]
+    if bool(is_disc.any()):
+        return torch.where(is_disc.view(1, 1, -1), disc_values, cont)
+    return cont
+
+
+def snn_log_prob(c, x, parents):
+    x = _x3(x)
+    if c["input_dim"] == 0:
+        b, s, _ = x.shape
+        logits = snn_logits(c, None, b, s)
+    else:
+        if parents is None:
+            raise ValueError("parents cannot be None when input_dim > 0")
+        logits = snn_logits(c, broadcast_samples(parents, x.shape[1]), 0, 0)
+    bins = snn_x_to_bin(c, x).long()
+    log_probs = torch.log_softmax(logits, dim=-1)
+    log_bin = log_probs.gather(-1, bins.unsqueeze(-1)).squeeze(-1)
+    left, right, width, center = snn_gather_bin_edges(c, bins)
+    clip = bool(c["within_bin_clip"])
+    x_use = x.clamp(min=left, max=right) if clip else x
+    wb = c["within_bin"]
+    mbw = float(c["min_bin_width"])
+    neg_inf = float("-inf")
+    if wb == "uniform":
+        log_within = -torch.log(width)
+        if not clip:
+            inside = (x >= left) & (x <= right)
+            log_within = torch.where(inside, log_within, torch.full_like(log_within, neg_inf))
+    elif wb == "triangular":
+        denom_l = torch.clamp(width * (center - left), min=mbw**2)
+        denom_r = torch.clamp(width * (right - center), min=mbw**2)
+        left_pdf = 2.0 * (x_use - left) / denom_l
+        right_pdf = 2.0 * (right - x_use) / denom_r
+        pdf = torch.clamp(torch.where(x_use <= center, left_pdf, right_pdf), min=0.0)
+        log_within = torch.log(torch.clamp(pdf, min=1e-12))
+        if not clip:
+            inside = (x >= left) & (x <= right)
+            log_within = torch.where(inside, log_within, torch.full_like(log_within, neg_inf))
+    elif wb == "gaussian":
+        sigma = torch.clamp(float(c["within_bin_scale"]) * width, min=mbw)
+        var = sigma**2
+        log_within = -((x_use - center) ** 2) / (2 * var) - sigma.log() - math.log(math.sqrt(2 * math.pi))
+    else:
+        raise ValueError(f"Unknown within_bin '{wb}'")
+    is_disc = c["is_discrete"]
+    if bool(is_disc.any()):
+        mask = (~is_disc).view(1, 1, -1)
+        log_within = torch.where(mask, log_within, torch.zeros_like(log_within))
+    return (log_bin + log_within).sum(dim=-1)
+
+
+# --------------------------------------------------------------------------------------
+# kde  (vbn/cpds/kde.py:105-182)
+# --------------------------------------------------------------------------------------
+
+
+def kde_kernel_log(c, diff: torch.Tensor, bandwidth: float) -> torch.Tensor:
+    scale = max(float(bandwidth), 1e-3) + float(c["min_scale"])  # :105-109
+    return -0.5 * ((diff / scale) ** 2 + LOG_2PI + 2 * math.log(scale))
+
+
+def kde_log_prob(c, x, parents, chunk: int = 512):
+    if c.get("targets") is None:
+        raise RuntimeError("KDECPD is not fitted yet.")
+    x = _x3(x)
+    targets = c["targets"]
+    b, s, dx = x.shape
+    n = targets.shape[0]
+    flat_x = x.reshape(b * s, dx)
+    flat_p = None
+    if c["input_dim"] != 0:
+        if parents is None:
+            raise ValueError("parents cannot be None when input_dim > 0")
+        flat_p = broadcast_samples(parents, s).reshape(b * s, c["input_dim"])
+    out = []
+    for start in range(0, flat_x.shape[0], chunk):
+        end = min(start + chunk, flat_x.shape[0])
+        diff_y = flat_x[start:end].unsqueeze(1) - targets.unsqueeze(0)
+        log_ky = kde_kernel_log(c, diff_y, c["bandwidth"]).sum(dim=-1)
+        if c["input_dim"] == 0:
+            out.append(torch.logsumexp(log_ky, dim=1) - math.log(float(n)))
+        else:
+            diff_p = flat_p[start:end].unsqueeze(1) - c["parents"].unsqueeze(0)
+            log_kp = kde_kernel_log(c, diff_p, c["parent_bandwidth"]).sum(dim=-1)
+            out.append(torch.logsumexp(log_kp + log_ky, dim=1) - torch.logsumexp(log_kp, dim=1))
+    return torch.cat(out, dim=0).reshape(b, s)
+
+
+def kde_sample(c, parents, n_samples, noise, key, chunk: int = 512):
+    if c.get("targets") is None:
+        raise RuntimeError("KDECPD is not fitted yet.")
+    targets = c["targets"]
+    n = targets.shape[0]
+    b = 1 if parents is None else parents.shape[0]
+    flat_out = torch.empty(b * n_samples, c["output_dim"], dtype=targets.dtype)
+    flat_p = None
+    if c["input_dim"] != 0:
+        if parents is None:
+            raise ValueError("parents cannot be None when input_dim > 0")
+        flat_p = broadcast_samples(parents, n_samples).reshape(b * n_samples, c["input_dim"])
+    bw = max(float(c["bandwidth"]), 1e-3)
+    for start in range(0, flat_out.shape[0], chunk):
+        end = min(start + chunk, flat_out.shape[0])
+        if c["input_dim"] == 0:
+            idx = noise.randint(key, n, end - start, targets.device)  # :170
+        else:
+            diff_p = flat_p[start:end].unsqueeze(1) - c["parents"].unsqueeze(0)
+            log_kp = kde_kernel_log(c, diff_p, c["parent_bandwidth"]).sum(dim=-1)
+            idx = noise.multinomial(key, torch.softmax(log_kp, dim=-1))  # :177-178
+        selected = targets[idx]
+        flat_out[start:end] = selected + noise.normal(key, selected) * (bw + float(c["min_scale"]))
+    return flat_out.reshape(b, n_samples, c["output_dim"])
+
+
+# --------------------------------------------------------------------------------------
+# CPD dispatch (BaseCPD.sample / log_prob / forward, vbn/core/base.py:28-59)
+# --------------------------------------------------------------------------------------
+
+_SAMPLE = {
+    "linear_gaussian": lg_sample,
+    "gaussian_nn": gnn_sample,
+    "mdn": mdn_sample,
+    "softmax_nn": snn_sample,
+    "kde": kde_sample,
+}
+_LOG_PROB = {
+    "linear_gaussian": lg_log_prob,
+    "gaussian_nn": gnn_log_prob,
+    "mdn": mdn_log_prob,
+    "softmax_nn": snn_log_prob,
+    "kde": kde_log_prob,
+}
+
+
+def cpd_sample(c, parents, n_samples: int, noise=None, key=("cpd",)):
+    return _SAMPLE[c["kind"]](c, parents, int(n_samples), noise or TorchNoise(), tuple(key))
+
+
+def cpd_log_prob(c, x, parents):
+    return _LOG_PROB[c["kind"]](c, x, parents)
+
+
+def cpd_forward(c, parents, n_samples: int, noise=None, key=("cpd",)):
+    samples = cpd_sample(c, parents, n_samples, noise, key)
+    lp = cpd_log_prob(c, samples, parents)
+    return samples, lp, torch.exp(lp)
+
+
+# --------------------------------------------------------------------------------------
+# inference state (vbn/inference/_core.py:57-135, vbn/utils/__init__.py:46-61)
+# --------------------------------------------------------------------------------------
+
+
+def infer_batch_size(evidence, do) -> int:
+    evidence = evidence or {}
+    do = do or {}
+    if evidence:
+        batch = int(next(iter(evidence.values())).shape[0])
+        if do and int(next(iter(do.values())).shape[0]) != batch:
+            raise ValueError("Evidence and do batch sizes must match.")
+        return batch
+    if do:
+        return int(next(iter(do.values())).shape[0])
+    return 1
+
+
+def clamp_evidence(x: torch.Tensor) -> torch.Tensor:
+    x = torch.nan_to_num(x, nan=0.0, posinf=1e6, neginf=-1e6)  # _core.py:112-114
+    return x.clamp(min=-1e6, max=1e6)
+
+
+class _State:
+    def __init__(self, spec, query):
+        topo = list(spec["topo"])
+        self.topo = topo
+        n2i = {n: i for i, n in enumerate(topo)}
+        self.node_to_idx = n2i
+        self.parent_idx = [tuple(n2i[p] for p in spec["parents"][n]) for n in topo]
+        self.evidence_mask = [n in query["evidence"] for n in topo]
+        self.do_mask = [n in query.get("do", {}) for n in topo]
+        self.target_idx = n2i[query["target"]]
+        self.slices = []
+        off = 0
+        for n in topo:
+            d = int(spec["cpds"][n]["output_dim"])
+            self.slices.append(slice(off, off + d))
+            off += d
+        self.total_dim = off
+
+
+def _fixed_values(query, st: _State, dtype, clamp_obs: bool):
+    vals: List[Optional[torch.Tensor]] = [None] * len(st.topo)
+    for node, v in (query.get("do") or {}).items():  # _core.py:117-135: do first, then evidence
+        vals[st.node_to_idx[node]] = ensure_2d(v).to(dtype)
+    for node, v in query["evidence"].items():
+        v = ensure_2d(v).to(dtype)
+        vals[st.node_to_idx[node]] = clamp_evidence(v) if clamp_obs else v
+    return vals
+
+
+def _gather_parents(samples, st: _State, idx: int):
+    pidx = st.parent_idx[idx]
+    if not pidx:
+        return None
+    return torch.cat([samples[..., st.slices[p]] for p in pidx], dim=-1)
+
+
+def _norm_query(query):
+    return {
+        "target": query["target"],
+        "evidence": dict(query.get("evidence") or {}),
+        "do": dict(query.get("do") or {}),
+    }
+
+
+# --------------------------------------------------------------------------------------
+# likelihood weighting (vbn/inference/likelihood_weighting.py:24-82)
+# --------------------------------------------------------------------------------------
+
+
+def likelihood_weighting(spec, query, n_samples: int, noise=None, scope="lw", normalize=True,
+                         eps: float = 1e-12, return_all: bool = False):
+    query = _norm_query(query)
+    noise = noise or TorchNoise()
+    b = infer_batch_size(query["evidence"], query["do"])
+    st = _State(spec, query)
+    dtype = torch.float32
+    samples = torch.zeros(b, n_samples, st.total_dim, dtype=dtype)
+    logw = torch.zeros(b, n_samples, dtype=dtype)
+    fixed = _fixed_values(query, st, dtype, clamp_obs=True)
+    for idx, node in enumerate(st.topo):
+        c = spec["cpds"][node]
+        if fixed[idx] is not None:
+            value = fixed[idx].unsqueeze(1).expand(b, n_samples, -1)
+            samples[..., st.slices[idx]] = value
+            if st.evidence_mask[idx]:
+                logw = logw + cpd_log_prob(c, value, _gather_parents(samples, st, idx))
+            continue
+        samples[..., st.slices[idx]] = cpd_sample(
+            c, _gather_parents(samples, st, idx), n_samples, noise, (scope, node)
+        )
+    target = samples[..., st.slices[st.target_idx]]
+    if normalize:
+        w = torch.softmax(logw, dim=1)
+    else:
+        lw = logw - logw.max(dim=-1, keepdim=True).values
+        w = torch.exp(lw).clamp_min(eps)
+    if return_all:
+        return w, target, samples, logw
+    return w, target
+
+
+# --------------------------------------------------------------------------------------
+# importance sampling (vbn/inference/importance_sampling.py:24-93)
+# --------------------------------------------------------------------------------------
+
+
+def importance_sampling(spec, query, n_samples: int, noise=None, ess_threshold: float = 0.1,
+                        return_info: bool = False):
+    query = _norm_query(query)
+    noise = noise or TorchNoise()
+    b = infer_batch_size(query["evidence"], query["do"])
+    st = _State(spec, query)
+    dtype = torch.float32
+    samples = torch.zeros(b, n_samples, st.total_dim, dtype=dtype)
+    logw = torch.zeros(b, n_samples, dtype=dtype)
+    fixed = _fixed_values(query, st, dtype, clamp_obs=False)
+
+    def sample_node(c, node, parent_tensor):
+        if b <= 1:
+            return cpd_sample(c, parent_tensor, n_samples, noise, ("is", node))
+        rows = []  # per-query-row independent draws (:37-54)
+        for bi in range(b):
+            p_i = None if parent_tensor is None else parent_tensor[bi : bi + 1]
+            rows.append(cpd_sample(c, p_i, n_samples, noise, ("is", node)))
+        return torch.cat(rows, dim=0)
+
+    for idx, node in enumerate(st.topo):
+        c = spec["cpds"][node]
+        if fixed[idx] is not None:
+            value = fixed[idx].unsqueeze(1).expand(b, n_samples, -1)
+            samples[..., st.slices[idx]] = value
+            if st.evidence_mask[idx]:
+                logw = logw + cpd_log_prob(c, value, _gather_parents(samples, st, idx))
+            continue
+        samples[..., st.slices[idx]] = sample_node(c, node, _gather_parents(samples, st, idx))
+
+    w = torch.softmax(logw, dim=1)
+    ess = 1.0 / (w**2).sum(dim=1)  # :82-84
+    threshold = max(1.0, ess_threshold * float(n_samples))
+    fallback = bool(torch.any(ess < threshold))
+    if fallback:
+        w, target = likelihood_weighting(spec, query, n_samples, noise, scope="lw")  # :85-88
+    else:
+        target = samples[..., st.slices[st.target_idx]]
+    if return_info:
+        return w, target, {"ess": ess, "fallback": fallback, "logw": logw, "samples": samples}
+    return w, target
+
+
+# --------------------------------------------------------------------------------------
+# ancestral sampling (vbn/sampling/ancestral.py:13-65)
+# --------------------------------------------------------------------------------------
+
+
+def ancestral_sample_tensor(spec, query, n_samples: int, noise=None, scope="anc"):
+    query = _norm_query(query)
+    noise = noise or TorchNoise()
+    b = infer_batch_size(query["evidence"], query["do"])
+    st = _State(spec, query) if query["target"] else None
+    if st is None:
+        q2 = dict(query)
+        q2["target"] = spec["topo"][0]
+        st = _State(spec, q2)
+    samples = torch.zeros(b, n_samples, st.total_dim, dtype=torch.float32)
+    fixed = _fixed_values(query, st, torch.float32, clamp_obs=False)
+    for idx, node in enumerate(st.topo):
+        if fixed[idx] is not None:
+            samples[..., st.slices[idx]] = fixed[idx].unsqueeze(1).expand(b, n_samples, -1)
+            continue
+        samples[..., st.slices[idx]] = cpd_sample(
+            spec["cpds"][node], _gather_parents(samples, st, idx), n_samples, noise, (scope, node)
+        )
+    return samples, st
+
+
+def ancestral_sample(spec, query, n_samples: int, noise=None):
+    samples, st = ancestral_sample_tensor(spec, query, n_samples, noise)
+    out = {n: samples[..., st.slices[i]] for i, n in enumerate(st.topo)}
+    return out[query["target"]] if query.get("target") else out
+
+
+# --------------------------------------------------------------------------------------
+# monte-carlo marginalisation (vbn/inference/monte_carlo_marginalization.py:18-92)
+# --------------------------------------------------------------------------------------
+
+
+def monte_carlo_marginalization(spec, query, n_samples: int, noise=None):
+    query = _norm_query(query)
+    noise = noise or TorchNoise()
+    b = infer_batch_size(query["evidence"], query["do"])
+    st = _State(spec, query)
+    dtype = torch.float32
+    fixed = _fixed_values(query, st, dtype, clamp_obs=False)
+    t = st.target_idx
+    target_node = st.topo[t]
+    c_t = spec["cpds"][target_node]
+    pidx = st.parent_idx[t]
+
+    if target_node in query["do"]:  # :33-37
+        tv = fixed[t].unsqueeze(1).expand(b, n_samples, -1)
+        return torch.ones(b, n_samples, dtype=dtype), tv
+
+    if all(fixed[p] is not None for p in pidx):  # :39-58
+        if pidx:
+            ptensor = torch.cat(
+                [fixed[p].unsqueeze(1).expand(b, n_samples, -1) for p in pidx], dim=-1
+            )
+        else:
+            ptensor = None
+        if fixed[t] is not None:
+            ts = fixed[t].unsqueeze(1).expand(b, n_samples, -1)
+        else:
+            ts = cpd_sample(c_t, ptensor, n_samples, noise, ("mcm", target_node))
+        return torch.exp(cpd_log_prob(c_t, ts, ptensor)), ts
+
+    samples = torch.zeros(b, n_samples, st.total_dim, dtype=dtype)
+    for idx, node in enumerate(st.topo):  # :60-78
+        if fixed[idx] is not None:
+            samples[..., st.slices[idx]] = fixed[idx].unsqueeze(1).expand(b, n_samples, -1)
+            continue
+        samples[..., st.slices[idx]] = cpd_sample(
+            spec["cpds"][node], _gather_parents(samples, st, idx), n_samples, noise, ("mcm", node)
+        )
+    ts = samples[..., st.slices[t]]
+    lp = cpd_log_prob(c_t, ts, _gather_parents(samples, st, t))  # :80-92
+    return torch.exp(lp), ts
+
+
+# --------------------------------------------------------------------------------------
+# closed-form linear-Gaussian posterior (builder-supplied check)
+# --------------------------------------------------------------------------------------
+
+
+def lg_exact_posterior(spec, target: str, evidence: Dict[str, torch.Tensor],
+                       do: Optional[Dict[str, torch.Tensor]] = None):
+    """Exact N(mean, var) of ``target`` given evidence for an all-linear_gaussian DAG with
+    scalar nodes.  float64.  Returns (mean[B], var[B])."""
+    do = do or {}
+    topo = list(spec["topo"])
+    n = len(topo)
+    n2i = {k: i for i, k in enumerate(topo)}
+    b = infer_batch_size(evidence, do)
+    A = torch.zeros(n, n, dtype=torch.float64)
+    bias = torch.zeros(b, n, dtype=torch.float64)
+    d = torch.zeros(n, dtype=torch.float64)
+    for node in topo:
+        c = spec["cpds"][node]
+        assert c["kind"] == "linear_gaussian" and c["output_dim"] == 1
+        i = n2i[node]
+        if node in do:
+            bias[:, i] = ensure_2d(do[node]).double()[:, 0]
+            continue
+        for j, p in enumerate(spec["parents"][node]):
+            A[i, n2i[p]] = c["weight"][j, 0].double()
+        bias[:, i] = c["bias"][0].double()
+        d[i] = c["var"][0].double().clamp(min=float(c["min_scale"]) ** 2)
+    M = torch.linalg.inv(torch.eye(n, dtype=torch.float64) - A)
+    mu = bias @ M.T
+    Sigma = M @ torch.diag(d) @ M.T
+    t = n2i[target]
+    e_idx = [n2i[k] for k in evidence]
+    if not e_idx:
+        return mu[:, t], Sigma[t, t].expand(b)
+    e_val = torch.cat([ensure_2d(evidence[k]).double() for k in evidence], dim=1)
+    S_ee = Sigma[e_idx][:, e_idx]
+    S_te = Sigma[t, e_idx]
+    gain = torch.linalg.solve(S_ee, S_te)
+    mean = mu[:, t] + (e_val - mu[:, e_idx]) @ gain
+    var = Sigma[t, t] - S_te @ gain
+    return mean, var.expand(b)
+
+
+# --------------------------------------------------------------------------------------
+# spec extraction from a live reference model (used only where /root/reference exists)
+# --------------------------------------------------------------------------------------
+
+
+def _layers_of(net) -> List[Tuple[torch.Tensor, torch.Tensor]]:
+    return [
+        (m.weight.detach().clone(), m.bias.detach().clone())
+        for m in net
+        if hasattr(m, "weight") and hasattr(m, "bias")
+    ]
+
+
+def cpd_spec_from_reference(cpd) -> dict:
+    """Read a reference CPD object's parameters/buffers into the oracle's spec dict."""
+    name = type(cpd).__name__
+    base = {"input_dim": int(cpd.input_dim), "output_dim": int(cpd.output_dim)}
+    g = lambda t: t.detach().clone()
+    if name == "LinearGaussianCPD":
+        return {**base, "kind": "linear_gaussian", "min_scale": float(cpd.min_scale),
+                "weight": g(cpd._weight), "bias": g(cpd._bias), "var": g(cpd._var)}
+    if name == "GaussianNNCPD":
+        out = {**base, "kind": "gaussian_nn", "min_scale": float(cpd.min_scale),
+               "activation": cpd.activation, "mean_x": g(cpd.mean_x), "std_x": g(cpd.std_x),
+               "mean_y": g(cpd.mean_y), "std_y": g(cpd.std_y)}
+        if cpd.input_dim == 0:
+            out.update(loc=g(cpd._loc), log_scale=g(cpd._log_scale))
+        else:
+            out["layers"] = _layers_of(cpd.net)
+        return out
+    if name == "MDNCPD":
+        out = {**base, "kind": "mdn", "min_scale": float(cpd.min_scale),
+               "activation": cpd.activation, "n_components": int(cpd.n_components)}
+        if cpd.input_dim == 0:
+            out.update(logits=g(cpd._logits), loc=g(cpd._loc), log_scale=g(cpd._log_scale))
+        else:
+            out["layers"] = _layers_of(cpd.net)
+        return out
+    if name == "SoftmaxNNCPD":
+        out = {**base, "kind": "softmax_nn", "n_classes": int(cpd.n_classes),
+               "activation": cpd.activation, "temperature": float(cpd.temperature),
+               "min_bin_width": float(cpd.min_bin_width), "within_bin": cpd.within_bin,
+               "within_bin_scale": float(cpd.within_bin_scale),
+               "within_bin_clip": bool(cpd.within_bin_clip),
+               "bin_edges": g(cpd._bin_edges), "class_values": g(cpd._class_values),
+               "sample_values": g(cpd._sample_values), "is_discrete": g(cpd._is_discrete),
+               "bins_ready": bool(cpd._bins_ready.item()),
+               "root_ready": bool(cpd._root_ready.item()),
+               "root_log_probs": g(cpd._root_log_probs)}
+        if cpd.input_dim == 0:
+            out["logits"] = g(cpd._logits)
+        else:
+            out["layers"] = _layers_of(cpd.net)
+        return out
+    if name == "KDECPD":
+        return {**base, "kind": "kde", "bandwidth": float(cpd.bandwidth),
+                "parent_bandwidth": float(cpd.parent_bandwidth), "min_scale": float(cpd.min_scale),
+                "parents": None if cpd._parents is None else g(cpd._parents),
+                "targets": None if cpd._targets is None else g(cpd._targets)}
+    raise ValueError(f"CPD type '{name}' is outside the hot-path scope")
+
+
+def spec_from_reference(vbn) -> dict:
+    """Model spec of a fitted reference ``VBN`` (vbn/vbn.py:184; dags.py:24-45)."""
+    nodes = list(vbn.dag.nodes())
+    return {
+        "nodes": nodes,
+        "parents": {n: list(vbn.dag.parents(n)) for n in nodes},
+        "topo": list(vbn.dag.topological_order()),
+        "cpds": {n: cpd_spec_from_reference(vbn.nodes[n]) for n in nodes},
+    }

@@ -1,0 +1,168 @@
+"""Builders of small fitted *reference* models (only usable where /root/reference exists,
+i.e. the build container).  Used by the oracle pin tests and by tests/golden/make_golden.py.
+Nothing here runs on the GPU box."""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+REF_ROOT = os.environ.get("VBN_REFERENCE_ROOT", "/root/reference")
+
+
+def have_reference() -> bool:
+    return os.path.isdir(os.path.join(REF_ROOT, "vbn"))
+
+
+def import_reference():
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    import vbn  # noqa: F401
+
+    return vbn
+
+
+def _fit(g, nodes_cpds, data, seed=0):
+    vbn = import_reference()
+    model = vbn.VBN(g, seed=seed, device="cpu")
+    model.set_learning_method("node_wise", nodes_cpds=nodes_cpds)
+    model.fit(data, verbosity=0)
+    return model
+
+
+def readme_model(n=1000, epochs=20):
+    """README minimal example (README.md:88-127): gaussian_nn x2 -> mdn(K=3)."""
+    import networkx as nx
+
+    gen = torch.Generator().manual_seed(0)
+    x0 = torch.randn(n, generator=gen)
+    x1 = torch.randn(n, generator=gen)
+    x2 = 0.5 * x0 - 0.2 * x1 + 0.1 * torch.randn(n, generator=gen)
+    g = nx.DiGraph()
+    g.add_edges_from([("feature_0", "feature_2"), ("feature_1", "feature_2")])
+    fit = {"epochs": epochs, "batch_size": 256}
+    cpds = {
+        "feature_0": {"cpd": "gaussian_nn", "fit": fit},
+        "feature_1": {"cpd": "gaussian_nn", "fit": fit},
+        "feature_2": {"cpd": "mdn", "n_components": 3, "fit": fit},
+    }
+    data = {"feature_0": x0[:, None], "feature_1": x1[:, None], "feature_2": x2[:, None]}
+    return _fit(g, cpds, data)
+
+
+def lg_chain_model(n_nodes=6, rows=2048, slope=1.0, seed=0):
+    import networkx as nx
+
+    gen = torch.Generator().manual_seed(seed)
+    g = nx.DiGraph()
+    names = [f"x{i}" for i in range(n_nodes)]
+    g.add_nodes_from(names)
+    for a, b in zip(names[:-1], names[1:]):
+        g.add_edge(a, b)
+    data = {}
+    x = torch.randn(rows, generator=gen)
+    data[names[0]] = x[:, None]
+    for nm in names[1:]:
+        x = slope * x + 0.1 + 0.5 * torch.randn(rows, generator=gen)
+        data[nm] = x[:, None]
+    cpds = {nm: {"cpd": "linear_gaussian"} for nm in names}
+    return _fit(g, cpds, data)
+
+
+def mixed_model(rows=512, epochs=3, seed=0, activation="relu", dims=None):
+    """Diamond-ish DAG mixing every CPD kind on the path, incl. a 2-D node.
+
+        a(lg root) -> c(mdn) -> e(gaussian_nn) -> g(lg, D=2)
+        b(gnn root) -> c ; b -> d(lg) ; d -> e ; c -> f(softmax_nn binned) ; f -> g
+        r(mdn root) -> h(kde) ; a -> h
+    """
+    import networkx as nx
+
+    gen = torch.Generator().manual_seed(seed)
+    g = nx.DiGraph()
+    g.add_edges_from(
+        [("a", "c"), ("b", "c"), ("b", "d"), ("c", "e"), ("d", "e"), ("c", "f"), ("e", "g"),
+         ("f", "g"), ("r", "h"), ("a", "h")]
+    )
+    rn = lambda *s: torch.randn(*s, generator=gen)
+    a = rn(rows, 1)
+    b = 0.5 + 1.5 * rn(rows, 1)
+    r = torch.where(torch.rand(rows, 1, generator=gen) < 0.4, -2 + 0.3 * rn(rows, 1), 1 + 0.5 * rn(rows, 1))
+    c = torch.tanh(a - 0.5 * b) + 0.3 * rn(rows, 1)
+    d = 0.8 * b - 0.2 + 0.4 * rn(rows, 1)
+    e = torch.sin(c) + 0.5 * d + 0.2 * rn(rows, 1)
+    f = c**2 + 0.3 * rn(rows, 1)
+    gg = torch.cat([e + 0.5 * f, e - f], dim=1) + 0.3 * rn(rows, 2)
+    h = torch.sin(r) + 0.3 * a + 0.2 * rn(rows, 1)
+    fit = {"epochs": epochs, "batch_size": 128}
+    cpds = {
+        "a": {"cpd": "linear_gaussian"},
+        "b": {"cpd": "gaussian_nn", "fit": fit},
+        "r": {"cpd": "mdn", "n_components": 2, "fit": fit},
+        "c": {"cpd": "mdn", "n_components": 3, "activation": activation, "fit": fit},
+        "d": {"cpd": "linear_gaussian"},
+        "e": {"cpd": "gaussian_nn", "activation": activation, "fit": fit},
+        "f": {"cpd": "softmax_nn", "n_classes": 5, "binning": "quantile",
+              "within_bin": "triangular", "activation": activation, "fit": fit},
+        "g": {"cpd": "linear_gaussian"},
+        "h": {"cpd": "kde", "bandwidth": 0.4, "parent_bandwidth": 0.6, "max_points": 64},
+    }
+    data = {"a": a, "b": b, "r": r, "c": c, "d": d, "e": e, "f": f, "g": gg, "h": h}
+    return _fit(g, cpds, data)
+
+
+def discrete_model(rows=600, epochs=5, seed=0):
+    """Small discrete BN with softmax_nn in discrete mode (like examples/06 and cfg3):
+    rain(2) -> wet(3) <- sprinkler(2);  wet -> slip(2)."""
+    import networkx as nx
+
+    gen = torch.Generator().manual_seed(seed)
+    g = nx.DiGraph()
+    g.add_edges_from([("rain", "wet"), ("sprinkler", "wet"), ("wet", "slip")])
+    u = lambda: torch.rand(rows, generator=gen)
+    rain = (u() < 0.3).float()
+    spr = (u() < 0.5).float()
+    wet = torch.clamp(rain + spr + (u() < 0.2).float() - (u() < 0.2).float(), 0, 2)
+    slip = ((wet > 0) & (u() < 0.6)).float()
+    fit = {"epochs": epochs, "batch_size": 128}
+    cpds = {
+        "rain": {"cpd": "softmax_nn", "n_classes": 2, "fit": fit},
+        "sprinkler": {"cpd": "softmax_nn", "n_classes": 2, "fit": fit},
+        "wet": {"cpd": "softmax_nn", "n_classes": 3, "fit": fit},
+        "slip": {"cpd": "softmax_nn", "n_classes": 2, "fit": fit},
+    }
+    data = {"rain": rain[:, None], "sprinkler": spr[:, None], "wet": wet[:, None], "slip": slip[:, None]}
+    return _fit(g, cpds, data)
+
+
+def binned_model(within_bin="uniform", clip=False, rows=400, epochs=3, seed=0, dim=2):
+    """softmax_nn in binned-continuous mode, root + child, D=dim."""
+    import networkx as nx
+
+    gen = torch.Generator().manual_seed(seed)
+    g = nx.DiGraph()
+    g.add_edge("p", "q")
+    p = torch.randn(rows, dim, generator=gen)
+    q = torch.tanh(p) + 0.3 * torch.randn(rows, dim, generator=gen)
+    fit = {"epochs": epochs, "batch_size": 128}
+    conf = {"cpd": "softmax_nn", "n_classes": 6, "binning": "uniform", "within_bin": within_bin,
+            "within_bin_clip": clip, "fit": fit}
+    return _fit(g, {"p": dict(conf), "q": dict(conf)}, {"p": p, "q": q})
+
+
+def kde_model(rows=300, seed=0, max_points=128):
+    import networkx as nx
+
+    gen = torch.Generator().manual_seed(seed)
+    g = nx.DiGraph()
+    g.add_edges_from([("p", "y"), ("p2", "y")])
+    p = torch.randn(rows, 1, generator=gen)
+    p2 = torch.randn(rows, 1, generator=gen)
+    y = torch.sin(p) + 0.2 * p2 + 0.1 * torch.randn(rows, 1, generator=gen)
+    cpds = {
+        "p": {"cpd": "kde", "bandwidth": 0.3, "max_points": max_points},
+        "p2": {"cpd": "linear_gaussian"},
+        "y": {"cpd": "kde", "bandwidth": 0.5, "parent_bandwidth": 0.4, "max_points": max_points},
+    }
+    return _fit(g, cpds, {"p": p, "p2": p2, "y": y})

@@ -1,0 +1,160 @@
+"""Pins the oracle (oracle/vbn_oracle.py) to the UNMODIFIED reference, bit for bit, under the
+same torch seed.  Runs only where /root/reference exists (the build container)."""
+import pytest
+import torch
+
+import refmodels
+from oracle import vbn_oracle as O
+
+pytestmark = [
+    pytest.mark.reference,
+    pytest.mark.skipif(not refmodels.have_reference(), reason="/root/reference not present"),
+]
+
+
+def _eq(a, b):
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert torch.equal(torch.nan_to_num(a, nan=123.0), torch.nan_to_num(b, nan=123.0)), (
+        (a - b).abs().max()
+    )
+
+
+def _run_methods(model, spec, query, S, methods=("lw", "is", "mcm", "anc")):
+    tq = {"target": query["target"], "evidence": query.get("evidence", {}), "do": query.get("do", {})}
+    if "lw" in methods:
+        model.set_inference_method("likelihood_weighting", n_samples=S)
+        torch.manual_seed(11)
+        rw, rs = model.infer_posterior(tq)
+        torch.manual_seed(11)
+        ow, os_ = O.likelihood_weighting(spec, tq, S)
+        _eq(rw, ow), _eq(rs, os_)
+    if "is" in methods:
+        model.set_inference_method("importance_sampling", n_samples=S)
+        torch.manual_seed(12)
+        rw, rs = model.infer_posterior(tq)
+        torch.manual_seed(12)
+        ow, os_, info = O.importance_sampling(spec, tq, S, return_info=True)
+        _eq(rw, ow), _eq(rs, os_)
+        assert info["fallback"] == model._inference._last_fallback
+        _eq(info["ess"], model._inference._last_ess)
+    if "mcm" in methods:
+        model.set_inference_method("monte_carlo_marginalization", n_samples=S)
+        torch.manual_seed(13)
+        rw, rs = model.infer_posterior(tq)
+        torch.manual_seed(13)
+        ow, os_ = O.monte_carlo_marginalization(spec, tq, S)
+        _eq(rw, ow), _eq(rs, os_)
+    if "anc" in methods:
+        model.set_sampling_method("ancestral")
+        torch.manual_seed(14)
+        rs = model.sample(tq, n_samples=S)
+        torch.manual_seed(14)
+        os_ = O.ancestral_sample(spec, tq, S)
+        _eq(rs, os_)
+
+
+def test_readme_minimal_example():
+    model = refmodels.readme_model(epochs=5)
+    spec = O.spec_from_reference(model)
+    q = {"target": "feature_2",
+         "evidence": {"feature_0": torch.tensor([[0.3]]), "feature_1": torch.tensor([[-0.2]])}}
+    _run_methods(model, spec, q, 200)
+    q2 = {"target": "feature_2", "evidence": {"feature_0": torch.randn(5, 1)}}
+    _run_methods(model, spec, q2, 64)
+    q3 = {"target": "feature_0", "evidence": {"feature_2": torch.randn(3, 1)}}
+    _run_methods(model, spec, q3, 64)
+
+
+def test_lg_chain_all_methods_and_exact_posterior():
+    model = refmodels.lg_chain_model(n_nodes=6)
+    spec = O.spec_from_reference(model)
+    ev = torch.tensor([[0.2], [1.0], [-0.7]])
+    q = {"target": "x2", "evidence": {"x5": ev}}
+    _run_methods(model, spec, q, 128)
+    q = {"target": "x4", "evidence": {"x5": ev}, "do": {"x1": torch.tensor([[0.5], [0.5], [-1.0]])}}
+    _run_methods(model, spec, q, 128)
+    # closed form vs a large LW run of the reference itself
+    model.set_inference_method("likelihood_weighting", n_samples=200_000)
+    torch.manual_seed(0)
+    w, s = model.infer_posterior({"target": "x2", "evidence": {"x5": ev}})
+    mean = (w * s[..., 0]).sum(1)
+    var = (w * (s[..., 0] - mean[:, None]) ** 2).sum(1)
+    em, evar = O.lg_exact_posterior(spec, "x2", {"x5": ev})
+    assert torch.allclose(mean.double(), em, atol=0.03)
+    assert torch.allclose(var.double(), evar, rtol=0.05)
+
+
+@pytest.mark.parametrize("activation", ["relu", "tanh", "gelu", "elu"])
+def test_mixed_dag_all_cpd_kinds(activation):
+    model = refmodels.mixed_model(activation=activation, epochs=2)
+    spec = O.spec_from_reference(model)
+    B = 3
+    q = {"target": "e", "evidence": {"g": torch.randn(B, 2), "h": torch.randn(B, 1)}}
+    _run_methods(model, spec, q, 32)
+    q = {"target": "a", "evidence": {"f": torch.randn(B, 1) ** 2, "c": torch.randn(B, 1)},
+         "do": {"d": torch.randn(B, 1)}}
+    _run_methods(model, spec, q, 32)
+    q = {"target": "h", "evidence": {}}
+    _run_methods(model, spec, q, 32)
+
+
+def test_discrete_softmax_model():
+    model = refmodels.discrete_model()
+    spec = O.spec_from_reference(model)
+    q = {"target": "rain", "evidence": {"slip": torch.tensor([[1.0], [0.0]]),
+                                        "wet": torch.tensor([[2.0], [1.0]])}}
+    _run_methods(model, spec, q, 64)
+    q = {"target": "slip", "evidence": {"rain": torch.tensor([[1.0], [0.0], [1.0]])}}
+    _run_methods(model, spec, q, 64)
+    with pytest.raises(ValueError):
+        O.likelihood_weighting(spec, {"target": "rain", "evidence": {"wet": torch.tensor([[0.5]])}}, 8)
+
+
+@pytest.mark.parametrize("within_bin,clip", [("uniform", False), ("triangular", False),
+                                             ("gaussian", False), ("uniform", True),
+                                             ("triangular", True)])
+def test_binned_softmax_model(within_bin, clip):
+    model = refmodels.binned_model(within_bin=within_bin, clip=clip)
+    spec = O.spec_from_reference(model)
+    q = {"target": "p", "evidence": {"q": torch.randn(4, 2) * 0.5}}
+    _run_methods(model, spec, q, 32)
+    q = {"target": "q", "evidence": {"p": torch.randn(4, 2) * 3.0}}  # some outside the bins
+    _run_methods(model, spec, q, 32)
+
+
+def test_kde_model():
+    model = refmodels.kde_model()
+    spec = O.spec_from_reference(model)
+    q = {"target": "p", "evidence": {"y": torch.randn(3, 1)}}
+    _run_methods(model, spec, q, 40)
+    q = {"target": "y", "evidence": {"p2": torch.randn(3, 1)}}
+    _run_methods(model, spec, q, 40)
+
+
+def test_cpd_level_sample_log_prob_forward():
+    model = refmodels.mixed_model(epochs=2)
+    spec = O.spec_from_reference(model)
+    for node, cpd in model.nodes.items():
+        c = spec["cpds"][node]
+        dp = c["input_dim"]
+        for parents in ([None] if dp == 0 else [torch.randn(4, dp), torch.randn(4, 7, dp)]):
+            torch.manual_seed(3)
+            rs = cpd.sample(parents, 7)
+            torch.manual_seed(3)
+            os_ = O.cpd_sample(c, parents, 7)
+            _eq(rs.detach(), os_)
+            _eq(cpd.log_prob(rs, parents).detach(), O.cpd_log_prob(c, os_, parents))
+            x2 = rs[:, 0]
+            _eq(cpd.log_prob(x2, parents if parents is None or parents.dim() == 2 else parents[:, :1]).detach(),
+                O.cpd_log_prob(c, x2, parents if parents is None or parents.dim() == 2 else parents[:, :1]))
+
+
+def test_record_replay_roundtrip():
+    model = refmodels.mixed_model(epochs=2)
+    spec = O.spec_from_reference(model)
+    q = {"target": "e", "evidence": {"g": torch.randn(3, 2), "h": torch.randn(3, 1)}}
+    rec = O.RecordingNoise()
+    torch.manual_seed(5)
+    w1, s1 = O.importance_sampling(spec, q, 16, noise=rec)
+    w2, s2 = O.importance_sampling(spec, q, 16, noise=O.ReplayNoise(rec.log))
+    _eq(w1, w2), _eq(s1, s2)
