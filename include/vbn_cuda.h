@@ -1,0 +1,204 @@
+/*
+ * vbn_cuda.h -- C ABI of libvbn_cuda.so, the B200 (sm_100a) backend for VBN's batched
+ * posterior-inference hot path.
+ *
+ * The reference (Giovannibriglia/VectorizedBayesianNetwork, package `vbn` 0.3.0) is pure
+ * Python/PyTorch and has no FFI; each entry point below names the reference code it
+ * replaces (paths relative to the reference root).  INTEGRATION.md shows the ctypes stub a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative VBN_E_* code otherwise; the message
+ *     is available from vbn_cuda_last_error() (thread local).  Nothing throws.
+ *   - all `*_dev` / device-side pointers are CUDA device pointers owned by the CALLER
+ *     (PyTorch tensors); the library allocates no device memory and keeps no global state.
+ *   - every launch goes to the cudaStream_t passed as `stream` (a void* here so the header
+ *     needs no CUDA include); no implicit synchronisation.
+ *   - all floating point is IEEE fp32; categorical indices are int32.
+ *   - row r of a run is (query b, sample s) with r = b*S + s, b in [0,B), s in [0,S).
+ */
+#ifndef VBN_CUDA_H_
+#define VBN_CUDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VBN_CUDA_ABI_VERSION 1
+
+/* error codes */
+#define VBN_OK 0
+#define VBN_E_INVALID (-1)   /* bad argument / malformed program */
+#define VBN_E_CUDA (-2)      /* CUDA runtime error, see last_error */
+#define VBN_E_CAPACITY (-3)  /* program needs more on-chip slots than one CTA can hold */
+
+/* ---- op kinds: one per CPD family on the path --------------------------------------- */
+#define VBN_OP_NONE 0   /* value only (do-node, or parent supplied by the caller)          */
+#define VBN_OP_LG 1     /* vbn/cpds/linear_gaussian.py:163-217 (also gaussian_nn roots)    */
+#define VBN_OP_GNN 2    /* vbn/cpds/gaussian_nn.py:105-119,215-288                         */
+#define VBN_OP_MDN 3    /* vbn/cpds/mdn.py:185-272                                         */
+#define VBN_OP_SNN 4    /* vbn/cpds/softmax_nn.py:581-759                                  */
+#define VBN_OP_KDE 5    /* vbn/cpds/kde.py:105-182                                         */
+
+/* ---- op flags ------------------------------------------------------------------------ */
+#define VBN_SRC_MASK 0x3
+#define VBN_SRC_SAMPLE 0x0     /* draw x ~ p(x | parents)                                    */
+#define VBN_SRC_FIXED_Q 0x1    /* x = fixed[fixed_col + d][b]   (evidence / do, per query)   */
+#define VBN_SRC_FIXED_ROW 0x2  /* x = inputs[fixed_col] element (r, d)  (per row, CPD API)   */
+#define VBN_F_ADD_LOGW 0x4     /* logw[r] += log p(x | parents)  (evidence node)             */
+#define VBN_F_OUT_LOGP 0x8     /* logp[r]  = log p(x | parents)  (MCM target, CPD.log_prob)  */
+#define VBN_F_SHARED 0x10      /* draw is shared by all queries: noise keyed by s, not (b,s) */
+
+/* activations of the MLP CPDs (gaussian_nn.py:16-34) */
+#define VBN_ACT_RELU 0
+#define VBN_ACT_TANH 1
+#define VBN_ACT_GELU 2
+#define VBN_ACT_ELU 3
+
+/* softmax_nn within-bin laws (softmax_nn.py:664-679) */
+#define VBN_WB_UNIFORM 0
+#define VBN_WB_TRIANGULAR 1
+#define VBN_WB_GAUSSIAN 2
+
+#define VBN_MAX_LAYERS 8
+
+/*
+ * One node of the schedule.  The host-side plan compiler
+ * (vectorizedbayesiannetwork_b200/plan.py) emits these in topological order; it replaces
+ * InferenceState / get_inference_state / prepare_fixed_values (vbn/inference/_core.py:13-135)
+ * and the per-node Python loop bodies of likelihood_weighting.py:42-71,
+ * importance_sampling.py:56-80, monte_carlo_marginalization.py:39-92, ancestral.py:27-41.
+ * 128 bytes, 16-byte aligned so the kernel fetches it with eight 128-bit loads.
+ */
+typedef struct VbnOp {
+  int32_t kind;       /* VBN_OP_*                                                          */
+  int32_t flags;      /* VBN_SRC_* | VBN_F_*                                               */
+  int32_t dim;        /* D: output dims of the node                                        */
+  int32_t n_par;      /* Dp: total parent dims                                             */
+  int32_t out_slot;   /* first of D consecutive value slots, -1 if the value is never read */
+  int32_t par_off;    /* offset into par_slots[] of the Dp parent slot ids                 */
+  int32_t param_off;  /* float offset of this node's block in the parameter blob           */
+  int32_t fixed_col;  /* FIXED_Q: first row of fixed[][B]; FIXED_ROW: index into inputs[]  */
+  int32_t store_idx;  /* index into stores[] where x is written, -1 none                   */
+  int32_t noise_idx;  /* index into noise[] (injected draws), -1 = Philox                  */
+  int32_t n_off;      /* first index in the per-row normal stream used by this op          */
+  int32_t u_off;      /* first index in the per-row uniform stream used by this op         */
+  int32_t n_layers;   /* MLP: number of Linear layers; 0 = outputs are constants (root)    */
+  int32_t act;        /* VBN_ACT_*                                                         */
+  int32_t n_out;      /* MLP output width O                                                */
+  int32_t k;          /* MDN: components K; SNN: classes C; KDE: stored points N           */
+  int32_t layer_dim[VBN_MAX_LAYERS]; /* widths after each Linear layer (last == n_out)      */
+  int32_t aux[4];     /* SNN: {within_bin, clip, any_discrete, 0}                          */
+  int32_t reserved[4];
+} VbnOp;
+
+/* strided view of caller memory: element (r, d) lives at base[r*row_stride + d*dim_stride] */
+typedef struct VbnView {
+  float* base;
+  int64_t row_stride;
+  int64_t dim_stride;
+} VbnView;
+
+/* injected draws for one node (record/replay parity).  Layout of each
+ * array is [Bn, S, D] row-major with Bn = 1 when the op has VBN_F_SHARED, else B.
+ * eps: normals; u: uniforms; idx: categorical picks (MDN [Bn,S]; SNN [Bn,S,D]; KDE [Bn,S]). */
+typedef struct VbnNoise {
+  const float* eps;
+  const float* u;
+  const int32_t* idx;
+} VbnNoise;
+
+/* A compiled schedule.  All pointers are DEVICE pointers that must outlive the plan. */
+typedef struct VbnProgramDesc {
+  const VbnOp* ops_dev;
+  int32_t n_ops;
+  const int32_t* par_slots_dev;
+  int32_t n_par_slots;
+  const float* params_dev;
+  int64_t n_params;
+  int32_t n_slots;    /* value slots a row needs at once (after liveness analysis)         */
+  int32_t n_scratch;  /* per-row scratch floats (max MLP output width over the program)    */
+  int32_t heavy;      /* 1 if the program contains MLP / KDE ops (picks the launch shape)  */
+  int32_t reserved;
+} VbnProgramDesc;
+
+typedef struct VbnPlan VbnPlan;
+
+/* One execution of a plan over B*S rows. */
+typedef struct VbnRunDesc {
+  int64_t n_queries;       /* B (local)                                                    */
+  int64_t n_samples;       /* S (local)                                                    */
+  int64_t query_offset;    /* global index of local query 0   (multi-GPU sharding)         */
+  int64_t sample_offset;   /* global index of local sample 0                               */
+  uint64_t seed;           /* Philox key                                                   */
+  uint64_t call_offset;    /* Philox counter word 3: caller bumps it per call              */
+  const float* fixed_dev;  /* [n_fixed_cols][B] evidence / do values, may be NULL          */
+  const VbnView* inputs_dev; /* per-row inputs referenced by FIXED_ROW ops                 */
+  const VbnView* stores_dev; /* outputs referenced by store_idx                            */
+  const VbnNoise* noise_dev; /* injected draws referenced by noise_idx, may be NULL        */
+  float* logw_dev;         /* [B*S] log-weights, required if any op has VBN_F_ADD_LOGW      */
+  float* logp_dev;         /* [B*S] log-density, required if any op has VBN_F_OUT_LOGP      */
+  int32_t logp_as_pdf;     /* 1: write exp(logp) (MCM pdf, monte_carlo_marginalization.py:57,91) */
+  int32_t reserved;
+  int32_t* error_flag_dev; /* set to 1 when a softmax_nn discrete value has no class
+                              (softmax_nn.py:620-625 raises ValueError); may be NULL       */
+} VbnRunDesc;
+
+int32_t vbn_cuda_abi_version(void);
+const char* vbn_cuda_last_error(void);
+int32_t vbn_cuda_device_count(int32_t* out_count);
+
+/* Validates the program and records launch geometry for the current device. */
+int32_t vbn_plan_create(const VbnProgramDesc* desc, VbnPlan** out_plan);
+int32_t vbn_plan_destroy(VbnPlan* plan);
+
+/* Replaces the whole per-node loop of LW / IS / MCM / ancestral and CPD.sample/log_prob:
+ * one launch runs every op of the schedule for every row. */
+int32_t vbn_run_forward(const VbnPlan* plan, const VbnRunDesc* run, void* stream);
+/* number of kernel launches vbn_run_forward issues (for bench accounting) */
+int32_t vbn_run_forward_launches(const VbnPlan* plan);
+
+/*
+ * Weight reduction: torch.softmax(log_weights, dim=1), ess = 1/sum(w^2)
+ * (importance_sampling.py:82-84, likelihood_weighting.py:75-80).
+ *   partials_dev : [B][n_split][3] workspace (m, l = sum exp(x-m), q = sum exp(2(x-m)))
+ *   stats_dev    : [B][3] merged (m, l, q); ess = l*l/q
+ * vbn_lse_partials + vbn_lse_merge compute stats; a multi-GPU caller all-gathers stats
+ * across ranks and calls vbn_lse_merge again on the gathered [B][n_ranks][3] array.
+ * vbn_weights_normalize then writes w = exp(x-m)/l (normalize=1) or
+ * max(exp(x-m), eps) (normalize=0) and, if ess_dev != NULL, ess[b].
+ */
+int32_t vbn_lse_partials(const float* logw_dev, int64_t n_queries, int64_t n_samples,
+                         int32_t n_split, float* partials_dev, void* stream);
+int32_t vbn_lse_merge(const float* partials_dev, int64_t n_queries, int32_t n_split,
+                      float* stats_dev, void* stream);
+int32_t vbn_weights_normalize(const float* logw_dev, const float* stats_dev, int64_t n_queries,
+                              int64_t n_samples, int32_t normalize, float eps, float* w_dev,
+                              float* ess_dev, void* stream);
+/* any(ess < threshold) -> *flag_dev (int32), the IS->LW fallback test
+ * (importance_sampling.py:85-88) */
+int32_t vbn_ess_below(const float* stats_dev, int64_t n_queries, float threshold,
+                      int32_t* flag_dev, void* stream);
+
+/*
+ * KDE conditional log-density over M query rows against N stored points
+ * (vbn/cpds/kde.py:111-149): out[m] = LSE_n(log_kp + log_ky) - LSE_n(log_kp)
+ * (root, dp == 0: LSE_n(log_ky) - ln N).  Stored points / queries are row-major
+ * [N,dp],[N,dx],[M,dp],[M,dx].
+ */
+int32_t vbn_kde_log_prob(const float* train_p_dev, const float* train_y_dev, int64_t n_points,
+                         int32_t dp, int32_t dx, const float* query_p_dev,
+                         const float* query_x_dev, int64_t n_rows, float bandwidth,
+                         float parent_bandwidth, float min_scale, float* out_dev, void* stream);
+
+/* Philox4x32-10 known-answer hook: out[i] = philox(ctr[i], key) for n counters (uint32 x4). */
+int32_t vbn_philox_fill(const uint32_t* ctr_dev, int64_t n, uint32_t key0, uint32_t key1,
+                        uint32_t* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VBN_CUDA_H_ */

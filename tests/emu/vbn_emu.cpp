@@ -1,0 +1,124 @@
+// TEST INFRASTRUCTURE ONLY -- host emulation of libvbn_cuda.so's C ABI (see cuda_shim.h).
+// The schedule kernel is the real device code compiled for the host; reductions / KDE use the
+// thread-independent generic code paths or plain loops.  Pointers are HOST pointers.
+#include "cuda_shim.h"
+
+thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
+namespace vbn { float smem[256 * 1024]; }
+
+#include "vbn_cuda.h"
+#include "vbn_schedule.cuh"
+
+#include <cstdio>
+#include <vector>
+
+struct VbnPlan { VbnProgramDesc desc; };
+
+namespace {
+template <int RPT, int NT, bool HEAVY>
+void run_kernel(const vbn::ScheduleArgs& a) {
+  const int64_t rows = static_cast<int64_t>(RPT) * NT;
+  const int64_t n_tiles = (a.n_rows + rows - 1) / rows;
+  gridDim.x = static_cast<unsigned>(n_tiles);
+  blockDim.x = NT;
+  for (unsigned b = 0; b < gridDim.x; ++b) {
+    blockIdx.x = b;
+    for (unsigned t = 0; t < NT; ++t) {
+      threadIdx.x = t;
+      vbn::schedule_kernel<RPT, NT, HEAVY, 1>(a);
+    }
+  }
+}
+}  // namespace
+
+extern "C" {
+int32_t vbn_cuda_abi_version(void) { return VBN_CUDA_ABI_VERSION; }
+const char* vbn_cuda_last_error(void) { return "emu"; }
+int32_t vbn_cuda_device_count(int32_t* n) { *n = 0; return 0; }
+int32_t vbn_plan_create(const VbnProgramDesc* d, VbnPlan** out) { *out = new VbnPlan{*d}; return 0; }
+int32_t vbn_plan_destroy(VbnPlan* p) { delete p; return 0; }
+int32_t vbn_run_forward_launches(const VbnPlan*) { return 1; }
+
+int32_t vbn_run_forward(const VbnPlan* plan, const VbnRunDesc* run, void*) {
+  vbn::ScheduleArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.ops = plan->desc.ops_dev; a.par_slots = plan->desc.par_slots_dev; a.params = plan->desc.params_dev;
+  a.n_ops = plan->desc.n_ops; a.n_slots = plan->desc.n_slots; a.n_scratch = plan->desc.n_scratch;
+  a.logp_as_pdf = run->logp_as_pdf; a.n_queries = run->n_queries; a.n_samples = run->n_samples;
+  a.n_rows = run->n_queries * run->n_samples;
+  a.query_offset = (uint32_t)run->query_offset; a.sample_offset = (uint32_t)run->sample_offset;
+  a.key0 = (uint32_t)run->seed; a.key1 = (uint32_t)(run->seed >> 32); a.call_offset = (uint32_t)run->call_offset;
+  a.fixed = run->fixed_dev; a.inputs = run->inputs_dev; a.stores = run->stores_dev; a.noise = run->noise_dev;
+  a.logw = run->logw_dev; a.logp = run->logp_dev; a.error_flag = run->error_flag_dev;
+  if ((size_t)(a.n_slots + a.n_scratch) * 2 * 32 > sizeof(vbn::smem) / sizeof(float)) return VBN_E_CAPACITY;
+  if (plan->desc.heavy) run_kernel<2, 32, true>(a); else run_kernel<2, 32, false>(a);
+  return 0;
+}
+
+int32_t vbn_lse_partials(const float* x, int64_t B, int64_t S, int32_t n_split, float* part, void*) {
+  const int64_t chunk = (S + n_split - 1) / n_split;
+  for (int64_t b = 0; b < B; ++b)
+    for (int sp = 0; sp < n_split; ++sp) {
+      const int64_t lo = sp * chunk, hi = std::min<int64_t>(lo + chunk, S);
+      float m = -CUDART_INF_F; double l = 0, q = 0;
+      for (int64_t i = lo; i < hi; ++i) m = std::max(m, x[b * S + i]);
+      for (int64_t i = lo; i < hi; ++i) { const double e = std::exp((double)x[b * S + i] - m); l += e; q += e * e; }
+      float* o = part + (b * n_split + sp) * 3; o[0] = m; o[1] = (float)l; o[2] = (float)q;
+    }
+  return 0;
+}
+int32_t vbn_lse_merge(const float* part, int64_t B, int32_t n, float* st, void*) {
+  for (int64_t b = 0; b < B; ++b) {
+    float m = -CUDART_INF_F;
+    for (int i = 0; i < n; ++i) m = std::max(m, part[(b * n + i) * 3]);
+    double l = 0, q = 0;
+    for (int i = 0; i < n; ++i) {
+      const float* p = part + (b * n + i) * 3;
+      if (p[0] == -CUDART_INF_F) continue;
+      const double e = std::exp((double)p[0] - m); l += p[1] * e; q += p[2] * e * e;
+    }
+    st[b * 3] = m; st[b * 3 + 1] = (float)l; st[b * 3 + 2] = (float)q;
+  }
+  return 0;
+}
+int32_t vbn_weights_normalize(const float* x, const float* st, int64_t B, int64_t S, int32_t norm, float eps,
+                              float* w, float* ess, void*) {
+  for (int64_t b = 0; b < B; ++b) {
+    const float m = st[b * 3], l = st[b * 3 + 1], q = st[b * 3 + 2];
+    for (int64_t i = 0; i < S; ++i) {
+      const float e = std::exp(x[b * S + i] - m);
+      w[b * S + i] = norm ? e / l : std::max(e, eps);
+    }
+    if (ess) ess[b] = l * l / q;
+  }
+  return 0;
+}
+int32_t vbn_ess_below(const float* st, int64_t B, float thr, int32_t* flag, void*) {
+  for (int64_t b = 0; b < B; ++b) if (st[b * 3 + 1] * st[b * 3 + 1] / st[b * 3 + 2] < thr) *flag |= 1;
+  return 0;
+}
+int32_t vbn_kde_log_prob(const float* tp, const float* ty, int64_t N, int32_t dp, int32_t dx, const float* qp,
+                         const float* qx, int64_t M, float bw, float pbw, float ms, float* out, void*) {
+  const double sy = std::max((double)bw, 1e-3) + ms, sp = std::max((double)pbw, 1e-3) + ms;
+  const float hy = (float)(0.5 / (sy * sy)), hp = (float)(0.5 / (sp * sp));
+  const float cy = (float)(-0.5 * dx * (1.8378770664093453 + 2.0 * std::log(sy))), ln = (float)std::log((double)N);
+  for (int64_t r = 0; r < M; ++r) {
+    vbn::Lse num, den; num.init(); den.init();
+    for (int64_t n = 0; n < N; ++n) {
+      float q1 = 0, q2 = 0;
+      for (int d = 0; d < dp; ++d) { const float df = qp[r * dp + d] - tp[n * dp + d]; q1 += df * df; }
+      for (int d = 0; d < dx; ++d) { const float df = qx[r * dx + d] - ty[n * dx + d]; q2 += df * df; }
+      den.push(-hp * q1); num.push(-hp * q1 - hy * q2);
+    }
+    out[r] = dp > 0 ? num.value() - den.value() + cy : num.value() + cy - ln;
+  }
+  return 0;
+}
+int32_t vbn_philox_fill(const uint32_t* ctr, int64_t n, uint32_t k0, uint32_t k1, uint32_t* out, void*) {
+  for (int64_t i = 0; i < n; ++i) {
+    const uint4 r = vbn::philox4x32_10(make_uint4(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3]), make_uint2(k0, k1));
+    out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+  }
+  return 0;
+}
+}

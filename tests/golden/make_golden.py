@@ -1,0 +1,158 @@
+"""Generates tests/golden/*.pt from the UNMODIFIED reference (needs /root/reference; run in the
+build container):  python tests/golden/make_golden.py
+
+Each case stores: the fitted model as a spec dict (parameters read from the reference objects),
+the query, the draws the reference consumed (recorded through the oracle, which is bit-identical
+to the reference under the same seed -- asserted here per case) and the REFERENCE outputs.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import refmodels  # noqa: E402
+from noise_util import log_to_strkeys  # noqa: E402
+from oracle import vbn_oracle as O  # noqa: E402
+
+METHODS = {
+    "lw": ("likelihood_weighting", O.likelihood_weighting),
+    "is": ("importance_sampling", O.importance_sampling),
+    "mcm": ("monte_carlo_marginalization", O.monte_carlo_marginalization),
+}
+
+
+def _same(a, b):
+    return a.shape == b.shape and torch.equal(torch.nan_to_num(a, nan=7.0), torch.nan_to_num(b, nan=7.0))
+
+
+def run_case(model, spec, query, S, method, seed):
+    q = {"target": query["target"], "evidence": query.get("evidence", {}), "do": query.get("do", {})}
+    rec = O.RecordingNoise()
+    info = {}
+    if method == "anc":
+        model.set_sampling_method("ancestral")
+        torch.manual_seed(seed)
+        ref_s = model.sample(q, n_samples=S)
+        torch.manual_seed(seed)
+        ora_s = O.ancestral_sample(spec, q, S, noise=rec)
+        assert _same(ref_s, ora_s)
+        expect = {"samples": ref_s}
+    else:
+        name, fn = METHODS[method]
+        model.set_inference_method(name, n_samples=S)
+        torch.manual_seed(seed)
+        ref_w, ref_s = model.infer_posterior(q)
+        torch.manual_seed(seed)
+        if method == "is":
+            ora_w, ora_s, inf = fn(spec, q, S, noise=rec, return_info=True)
+            info = {"fallback": bool(inf["fallback"]), "ess": inf["ess"]}
+            assert info["fallback"] == model._inference._last_fallback
+        else:
+            ora_w, ora_s = fn(spec, q, S, noise=rec)
+        assert _same(ref_w, ora_w) and _same(ref_s, ora_s), (method, query["target"])
+        expect = {"pdf": ref_w, "samples": ref_s}
+    return {"query": q, "S": S, "method": method, "noise": log_to_strkeys(rec.log), "expect": expect, "info": info}
+
+
+def cpd_cases(model, spec, S=9, seed=3):
+    out = []
+    for node, cpd in model.nodes.items():
+        c = spec["cpds"][node]
+        dp = c["input_dim"]
+        variants = [None] if dp == 0 else [torch.randn(4, dp), torch.randn(4, S, dp)]
+        for parents in variants:
+            rec = O.RecordingNoise()
+            torch.manual_seed(seed)
+            ref = cpd.sample(parents, S).detach()
+            torch.manual_seed(seed)
+            ora = O.cpd_sample(c, parents, S, noise=rec, key=("cpd", node))
+            assert _same(ref, ora)
+            lp = cpd.log_prob(ref, parents).detach()
+            lp2 = cpd.log_prob(ref[:, 0], parents if parents is None or parents.dim() == 2 else parents[:, :1]).detach()
+            out.append({"node": node, "parents": parents, "S": S, "noise": log_to_strkeys(rec.log),
+                        "samples": ref, "log_prob": lp, "log_prob_2d": lp2})
+    return out
+
+
+def main():
+    torch.manual_seed(1234)
+    files = {}
+
+    m = refmodels.readme_model(epochs=20)
+    spec = O.spec_from_reference(m)
+    q_readme = {"target": "feature_2", "evidence": {"feature_0": torch.tensor([[0.3]]), "feature_1": torch.tensor([[-0.2]])}}
+    cases = [run_case(m, spec, q_readme, 200, "mcm", 0)]
+    q2 = {"target": "feature_2", "evidence": {"feature_0": torch.randn(5, 1)}}
+    q3 = {"target": "feature_0", "evidence": {"feature_2": torch.randn(3, 1)}}
+    for q in (q_readme, q2, q3):
+        for meth in ("lw", "is", "mcm", "anc"):
+            cases.append(run_case(m, spec, q, 48, meth, 5))
+    files["readme"] = {"spec": spec, "cases": cases, "cpd_cases": cpd_cases(m, spec)}
+
+    m = refmodels.lg_chain_model(n_nodes=6)
+    spec = O.spec_from_reference(m)
+    ev = torch.tensor([[0.2], [1.0], [-0.7]])
+    qs = [{"target": "x2", "evidence": {"x5": ev}},
+          {"target": "x0", "evidence": {"x5": ev}},
+          {"target": "x4", "evidence": {"x5": ev}, "do": {"x1": torch.tensor([[0.5], [0.5], [-1.0]])}},
+          {"target": "x3", "evidence": {}},
+          {"target": "x3", "evidence": {"x2": ev, "x5": torch.tensor([[float("nan")], [float("inf")], [1.0]])}}]
+    cases = [run_case(m, spec, q, 64, meth, 7) for q in qs for meth in ("lw", "is", "mcm", "anc")]
+    files["lg_chain"] = {"spec": spec, "cases": cases, "cpd_cases": cpd_cases(m, spec)}
+
+    for act in ("relu", "tanh", "gelu", "elu"):
+        m = refmodels.mixed_model(activation=act, epochs=2)
+        spec = O.spec_from_reference(m)
+        B = 3
+        qs = [{"target": "e", "evidence": {"g": torch.randn(B, 2), "h": torch.randn(B, 1)}},
+              {"target": "a", "evidence": {"f": torch.randn(B, 1) ** 2, "c": torch.randn(B, 1)}, "do": {"d": torch.randn(B, 1)}},
+              {"target": "h", "evidence": {}},
+              {"target": "g", "evidence": {"e": torch.randn(B, 1), "f": torch.rand(B, 1)}}]
+        meths = ("lw", "is", "mcm", "anc") if act == "relu" else ("lw",)
+        cases = [run_case(m, spec, q, 32, meth, 9) for q in qs for meth in meths]
+        files[f"mixed_{act}"] = {"spec": spec, "cases": cases,
+                                 "cpd_cases": cpd_cases(m, spec) if act in ("relu", "gelu") else []}
+
+    m = refmodels.discrete_model()
+    spec = O.spec_from_reference(m)
+    qs = [{"target": "rain", "evidence": {"slip": torch.tensor([[1.0], [0.0]]), "wet": torch.tensor([[2.0], [1.0]])}},
+          {"target": "slip", "evidence": {"rain": torch.tensor([[1.0], [0.0], [1.0]])}},
+          {"target": "wet", "evidence": {"slip": torch.tensor([[1.0]])}}]
+    cases = [run_case(m, spec, q, 64, meth, 11) for q in qs for meth in ("lw", "is", "mcm", "anc")]
+    files["discrete"] = {"spec": spec, "cases": cases, "cpd_cases": cpd_cases(m, spec)}
+
+    for wb, clip in (("uniform", False), ("triangular", False), ("gaussian", False), ("uniform", True), ("triangular", True)):
+        m = refmodels.binned_model(within_bin=wb, clip=clip)
+        spec = O.spec_from_reference(m)
+        qs = [{"target": "p", "evidence": {"q": torch.randn(4, 2) * 0.5}},
+              {"target": "q", "evidence": {"p": torch.randn(4, 2) * 3.0}}]
+        cases = [run_case(m, spec, q, 32, meth, 13) for q in qs for meth in ("lw", "is", "mcm")]
+        files[f"binned_{wb}{'_clip' if clip else ''}"] = {"spec": spec, "cases": cases, "cpd_cases": cpd_cases(m, spec)}
+
+    m = refmodels.kde_model()
+    spec = O.spec_from_reference(m)
+    qs = [{"target": "p", "evidence": {"y": torch.randn(3, 1)}},
+          {"target": "y", "evidence": {"p2": torch.randn(3, 1)}},
+          {"target": "y", "evidence": {"p": torch.randn(2, 1), "p2": torch.randn(2, 1)}}]
+    cases = [run_case(m, spec, q, 40, meth, 15) for q in qs for meth in ("lw", "is", "mcm", "anc")]
+    files["kde"] = {"spec": spec, "cases": cases, "cpd_cases": cpd_cases(m, spec)}
+
+    total = 0
+    for name, blob in files.items():
+        path = os.path.join(HERE, f"{name}.pt")
+        torch.save(blob, path)
+        total += os.path.getsize(path)
+        print(f"{name}: {len(blob['cases'])} cases, {len(blob['cpd_cases'])} cpd cases, {os.path.getsize(path)/1024:.0f} KiB")
+    print(f"total {total/1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,524 @@
+"""Host-side mirror of the reference CPD classes on the hot path (vbn/cpds/{linear_gaussian,
+gaussian_nn,mdn,softmax_nn,kde}.py).  These objects only HOLD parameters and know how to pack
+them for the CUDA schedule kernel; ``sample`` / ``log_prob`` / ``forward`` run on the GPU through
+libvbn_cuda.so (see engine.py) -- there is no CPU implementation here.  Fitting is out of scope:
+parameters come from a fitted reference model (``from_reference``), from a spec dict
+(``from_spec``, the format of tests/golden) or from the caller.
+"""
+from __future__ import annotations
+
+import itertools
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _lib as L
+
+LOG_2PI = math.log(2.0 * math.pi)
+_UID = itertools.count(1)  # object ids can be recycled by CPython; cache keys use these instead
+
+
+def _pad4(n: int) -> int:
+    return (n + 3) & ~3
+
+
+def _f32(t) -> torch.Tensor:
+    return torch.as_tensor(t).detach().to(device="cpu", dtype=torch.float32).contiguous()
+
+
+def _np(t: torch.Tensor) -> np.ndarray:
+    return t.detach().cpu().numpy().astype(np.float32, copy=False).reshape(-1)
+
+
+def _padded(a: np.ndarray, n: int) -> np.ndarray:
+    out = np.zeros(n, dtype=np.float32)
+    out[: a.size] = a.reshape(-1)
+    return out
+
+
+@dataclass
+class Packed:
+    """What the plan compiler needs to know about one CPD."""
+
+    kind: int
+    dim: int
+    n_par: int
+    params: np.ndarray
+    n_layers: int = 0
+    act: int = 0
+    n_out: int = 0
+    k: int = 0
+    layer_dim: List[int] = field(default_factory=list)
+    aux: List[int] = field(default_factory=lambda: [0, 0, 0, 0])
+    n_normals: int = 0   # per-row normals consumed by one sample()
+    n_uniforms: int = 0  # per-row uniforms consumed by one sample()
+    scratch: int = 0     # per-row scratch floats
+    heavy: bool = False
+
+
+def pack_mlp(layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], input_dim: int) -> Tuple[np.ndarray, List[int]]:
+    """Layout documented in csrc/vbn_schedule.cuh: hidden layers transposed [in][pad4(out)], the
+    last layer in nn.Linear layout [out][pad4(in)], every bias padded to a multiple of 4."""
+    if len(layers) > L.MAX_LAYERS:
+        raise ValueError(f"MLP deeper than {L.MAX_LAYERS} Linear layers is not supported")
+    chunks: List[np.ndarray] = []
+    dims: List[int] = []
+    last = len(layers) - 1
+    cur_in = int(input_dim)
+    for i, (w, b) in enumerate(layers):
+        w, b = _f32(w), _f32(b)
+        out_dim, in_dim = int(w.shape[0]), int(w.shape[1])
+        if in_dim != cur_in:
+            raise ValueError(f"layer {i} expects {in_dim} inputs, got {cur_in}")
+        if i != last:
+            buf = np.zeros((in_dim, _pad4(out_dim)), dtype=np.float32)
+            buf[:, :out_dim] = w.numpy().T
+        else:
+            buf = np.zeros((out_dim, _pad4(in_dim)), dtype=np.float32)
+            buf[:, :in_dim] = w.numpy()
+        chunks.append(buf.reshape(-1))
+        chunks.append(_padded(b.numpy(), _pad4(out_dim)))
+        dims.append(out_dim)
+        cur_in = out_dim
+    fast = len(layers) == 3 and dims[0] == 32 and dims[1] == 32
+    if not fast:
+        widest = max([int(input_dim)] + dims[:-1]) if layers else 0
+        if widest > L.MAX_GENERIC_WIDTH:
+            raise ValueError(
+                f"MLP width {widest} exceeds the generic device path limit {L.MAX_GENERIC_WIDTH}"
+            )
+    return np.concatenate(chunks) if chunks else np.zeros(0, np.float32), dims
+
+
+def _layers_from_module(net) -> List[Tuple[torch.Tensor, torch.Tensor]]:
+    return [(m.weight, m.bias) for m in net if hasattr(m, "weight") and hasattr(m, "bias")]
+
+
+class BaseCPD:
+    """Signature mirror of vbn/core/base.py:28-81 (sample / log_prob / forward)."""
+
+    kind = "base"
+
+    def __init__(self, input_dim: int, output_dim: int, device=None) -> None:
+        self.input_dim = int(input_dim)
+        self.output_dim = int(output_dim)
+        self.device = torch.device(device) if device is not None else torch.device("cuda")
+        self._packed: Optional[Packed] = None
+        self._version = 0
+        self._uid = next(_UID)
+
+    # --- packing -----------------------------------------------------------------------
+    def pack(self) -> Packed:
+        if self._packed is None:
+            self._packed = self._pack()
+        return self._packed
+
+    def _pack(self) -> Packed:  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    def invalidate(self) -> None:
+        """Call after changing parameters in place: drops the packed blob and cached plans."""
+        self._packed = None
+        self._version += 1
+
+    # --- public CPD API (GPU) ------------------------------------------------------------
+    def sample(self, parents: Optional[torch.Tensor], n_samples: int, *, noise=None, seed=None) -> torch.Tensor:
+        from .engine import cpd_sample
+
+        return cpd_sample(self, parents, int(n_samples), noise=noise, seed=seed)
+
+    def log_prob(self, x: torch.Tensor, parents: Optional[torch.Tensor]) -> torch.Tensor:
+        from .engine import cpd_log_prob
+
+        return cpd_log_prob(self, x, parents)
+
+    def forward(self, parents: Optional[torch.Tensor], n_samples: int):
+        from .core import CPDOutput
+
+        samples = self.sample(parents, n_samples)
+        log_prob = self.log_prob(samples, parents)
+        return CPDOutput(samples=samples, log_prob=log_prob, pdf=torch.exp(log_prob))
+
+    __call__ = forward
+
+    def to_spec(self) -> dict:  # pragma: no cover - abstract
+        raise NotImplementedError
+
+
+# ------------------------------------------------------------------------------------------
+class LinearGaussianCPD(BaseCPD):
+    """vbn/cpds/linear_gaussian.py:14-217 (buffers _weight[Dp,D], _bias[D], _var[D])."""
+
+    kind = "linear_gaussian"
+
+    def __init__(self, input_dim, output_dim, weight, bias, var, min_scale: float = 1e-3, device=None):
+        super().__init__(input_dim, output_dim, device)
+        self._weight = _f32(weight).reshape(self.input_dim, self.output_dim)
+        self._bias = _f32(bias).reshape(self.output_dim)
+        self._var = _f32(var).reshape(self.output_dim)
+        self.min_scale = float(min_scale)
+
+    def _scale(self) -> torch.Tensor:
+        return torch.sqrt(self._var.clamp(min=self.min_scale**2))  # linear_gaussian.py:163-165
+
+    def _pack(self) -> Packed:
+        scale = self._scale()
+        params = np.concatenate(
+            [_np(self._weight), _np(self._bias), _np(scale), _np(2 * torch.log(scale)), _np(scale**2)]
+        )
+        return Packed(kind=L.OP_LG, dim=self.output_dim, n_par=self.input_dim, params=params,
+                      n_normals=self.output_dim)
+
+    @classmethod
+    def from_spec(cls, c, device=None):
+        return cls(c["input_dim"], c["output_dim"], c["weight"], c["bias"], c["var"], c["min_scale"], device)
+
+    @classmethod
+    def from_reference(cls, cpd, device=None):
+        return cls(cpd.input_dim, cpd.output_dim, cpd._weight, cpd._bias, cpd._var, cpd.min_scale, device)
+
+    def to_spec(self):
+        return {"kind": self.kind, "input_dim": self.input_dim, "output_dim": self.output_dim,
+                "min_scale": self.min_scale, "weight": self._weight, "bias": self._bias, "var": self._var}
+
+
+# ------------------------------------------------------------------------------------------
+class GaussianNNCPD(BaseCPD):
+    """vbn/cpds/gaussian_nn.py:37-288."""
+
+    kind = "gaussian_nn"
+
+    def __init__(self, input_dim, output_dim, *, layers=None, loc=None, log_scale=None,
+                 mean_x=None, std_x=None, mean_y=None, std_y=None, activation="relu",
+                 min_scale: float = 1e-3, device=None):
+        super().__init__(input_dim, output_dim, device)
+        d, dp = self.output_dim, self.input_dim
+        self.activation = str(activation)
+        self.min_scale = float(min_scale)
+        self.mean_x = _f32(mean_x if mean_x is not None else torch.zeros(dp)).reshape(dp)
+        self.std_x = _f32(std_x if std_x is not None else torch.ones(dp)).reshape(dp)
+        self.mean_y = _f32(mean_y if mean_y is not None else torch.zeros(d)).reshape(d)
+        self.std_y = _f32(std_y if std_y is not None else torch.ones(d)).reshape(d)
+        if dp == 0:
+            self._loc = _f32(loc).reshape(d)
+            self._log_scale = _f32(log_scale).reshape(d)
+            self.layers = None
+        else:
+            self.layers = [(_f32(w), _f32(b)) for w, b in layers]
+
+    def _pack(self) -> Packed:
+        d, dp = self.output_dim, self.input_dim
+        if dp == 0:
+            # root: fixed Normal(loc*std_y+mean_y, (softplus(log_scale)+min)*std_y)
+            # (gaussian_nn.py:244-254); same density family as linear_gaussian with Dp = 0
+            loc = self._loc * self.std_y + self.mean_y
+            scale = (F.softplus(self._log_scale) + self.min_scale) * self.std_y
+            params = np.concatenate([_np(loc), _np(scale), _np(2 * torch.log(scale)), _np(scale**2)])
+            return Packed(kind=L.OP_LG, dim=d, n_par=0, params=params, n_normals=d)
+        head = np.concatenate([_np(self.mean_x), _np(self.std_x), _np(self.mean_y), _np(self.std_y),
+                               np.array([self.min_scale], np.float32)])
+        mlp, dims = pack_mlp(self.layers, dp)
+        if dims[-1] != 2 * d:
+            raise ValueError("gaussian_nn net must output 2*output_dim values")
+        params = np.concatenate([_padded(head, _pad4(2 * dp + 2 * d + 1)), mlp])
+        return Packed(kind=L.OP_GNN, dim=d, n_par=dp, params=params, n_layers=len(dims),
+                      act=L.ACT[self.activation], n_out=2 * d, layer_dim=dims, n_normals=d,
+                      scratch=2 * d, heavy=True)
+
+    @classmethod
+    def from_spec(cls, c, device=None):
+        return cls(c["input_dim"], c["output_dim"], layers=c.get("layers"), loc=c.get("loc"),
+                   log_scale=c.get("log_scale"), mean_x=c["mean_x"], std_x=c["std_x"],
+                   mean_y=c["mean_y"], std_y=c["std_y"], activation=c["activation"],
+                   min_scale=c["min_scale"], device=device)
+
+    @classmethod
+    def from_reference(cls, cpd, device=None):
+        root = cpd.input_dim == 0
+        return cls(cpd.input_dim, cpd.output_dim,
+                   layers=None if root else _layers_from_module(cpd.net),
+                   loc=cpd._loc if root else None, log_scale=cpd._log_scale if root else None,
+                   mean_x=cpd.mean_x, std_x=cpd.std_x, mean_y=cpd.mean_y, std_y=cpd.std_y,
+                   activation=cpd.activation, min_scale=cpd.min_scale, device=device)
+
+    def to_spec(self):
+        out = {"kind": self.kind, "input_dim": self.input_dim, "output_dim": self.output_dim,
+               "min_scale": self.min_scale, "activation": self.activation, "mean_x": self.mean_x,
+               "std_x": self.std_x, "mean_y": self.mean_y, "std_y": self.std_y}
+        if self.input_dim == 0:
+            out.update(loc=self._loc, log_scale=self._log_scale)
+        else:
+            out["layers"] = self.layers
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+class MDNCPD(BaseCPD):
+    """vbn/cpds/mdn.py:37-272."""
+
+    kind = "mdn"
+
+    def __init__(self, input_dim, output_dim, n_components, *, layers=None, logits=None, loc=None,
+                 log_scale=None, activation="relu", min_scale: float = 1e-3, device=None):
+        super().__init__(input_dim, output_dim, device)
+        self.n_components = int(n_components)
+        self.activation = str(activation)
+        self.min_scale = float(min_scale)
+        k, d = self.n_components, self.output_dim
+        if self.input_dim == 0:
+            self._logits = _f32(logits).reshape(k)
+            self._loc = _f32(loc).reshape(k, d)
+            self._log_scale = _f32(log_scale).reshape(k, d)
+            self.layers = None
+        else:
+            self.layers = [(_f32(w), _f32(b)) for w, b in layers]
+
+    def _pack(self) -> Packed:
+        k, d, dp = self.n_components, self.output_dim, self.input_dim
+        n_out = k + 2 * k * d
+        head = _padded(np.array([self.min_scale], np.float32), 4)
+        if dp == 0:
+            rest = torch.cat([self._loc, self._log_scale], dim=1).reshape(-1)  # per k: loc[D], raw[D]
+            consts = np.concatenate([_np(self._logits), _np(rest)])
+            params = np.concatenate([head, _padded(consts, _pad4(n_out))])
+            return Packed(kind=L.OP_MDN, dim=d, n_par=0, params=params, n_layers=0, n_out=n_out, k=k,
+                          n_normals=d, n_uniforms=1, scratch=n_out, heavy=True)
+        mlp, dims = pack_mlp(self.layers, dp)
+        if dims[-1] != n_out:
+            raise ValueError("mdn net must output K*(2D+1) values")
+        return Packed(kind=L.OP_MDN, dim=d, n_par=dp, params=np.concatenate([head, mlp]),
+                      n_layers=len(dims), act=L.ACT[self.activation], n_out=n_out, k=k,
+                      layer_dim=dims, n_normals=d, n_uniforms=1, scratch=n_out, heavy=True)
+
+    @classmethod
+    def from_spec(cls, c, device=None):
+        return cls(c["input_dim"], c["output_dim"], c["n_components"], layers=c.get("layers"),
+                   logits=c.get("logits"), loc=c.get("loc"), log_scale=c.get("log_scale"),
+                   activation=c["activation"], min_scale=c["min_scale"], device=device)
+
+    @classmethod
+    def from_reference(cls, cpd, device=None):
+        root = cpd.input_dim == 0
+        return cls(cpd.input_dim, cpd.output_dim, cpd.n_components,
+                   layers=None if root else _layers_from_module(cpd.net),
+                   logits=cpd._logits if root else None, loc=cpd._loc if root else None,
+                   log_scale=cpd._log_scale if root else None, activation=cpd.activation,
+                   min_scale=cpd.min_scale, device=device)
+
+    def to_spec(self):
+        out = {"kind": self.kind, "input_dim": self.input_dim, "output_dim": self.output_dim,
+               "min_scale": self.min_scale, "activation": self.activation,
+               "n_components": self.n_components}
+        if self.input_dim == 0:
+            out.update(logits=self._logits, loc=self._loc, log_scale=self._log_scale)
+        else:
+            out["layers"] = self.layers
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+class SoftmaxNNCPD(BaseCPD):
+    """vbn/cpds/softmax_nn.py:40-759 (inference-time state only)."""
+
+    kind = "softmax_nn"
+
+    def __init__(self, input_dim, output_dim, n_classes, *, layers=None, logits=None,
+                 root_log_probs=None, root_ready=False, bin_edges=None, class_values=None,
+                 sample_values=None, is_discrete=None, bins_ready=True, activation="relu",
+                 temperature: float = 1.0, min_bin_width: float = 1e-12, within_bin="uniform",
+                 within_bin_scale: float = 0.25, within_bin_clip: bool = False, device=None):
+        super().__init__(input_dim, output_dim, device)
+        d, k = self.output_dim, int(n_classes)
+        self.n_classes = k
+        self.activation = str(activation)
+        self.temperature = float(temperature)
+        self.min_bin_width = float(min_bin_width)
+        self.within_bin = str(within_bin)
+        if self.within_bin not in L.WITHIN_BIN:
+            raise ValueError(f"Unknown within_bin '{within_bin}'")
+        self.within_bin_scale = float(within_bin_scale)
+        self.within_bin_clip = bool(within_bin_clip)
+        self._bin_edges = _f32(bin_edges).reshape(d, k + 1)
+        self._class_values = _f32(class_values).reshape(d, k)
+        self._sample_values = _f32(sample_values).reshape(d, k)
+        self._is_discrete = torch.as_tensor(is_discrete).detach().cpu().bool().reshape(d)
+        self._bins_ready = bool(bins_ready)
+        self._root_ready = bool(root_ready)
+        self._root_log_probs = _f32(root_log_probs if root_log_probs is not None else torch.zeros(d, k)).reshape(d, k)
+        if self.input_dim == 0:
+            self._logits = _f32(logits if logits is not None else torch.zeros(d, k)).reshape(d, k)
+            self.layers = None
+        else:
+            self.layers = [(_f32(w), _f32(b)) for w, b in layers]
+
+    def _ensure_bins_ready(self) -> None:
+        if not self._bins_ready:  # softmax_nn.py:178-180
+            raise RuntimeError("Bins not initialized. Call fit(...) before sampling.")
+
+    def _pack(self) -> Packed:
+        self._ensure_bins_ready()
+        d, k, dp = self.output_dim, self.n_classes, self.input_dim
+        head = np.concatenate([
+            np.array([self.min_bin_width, self.within_bin_scale, self.temperature, 0.0], np.float32),
+            _np(self._bin_edges), _np(self._class_values), _np(self._sample_values),
+            _np(self._is_discrete.float()),
+        ])
+        head = _padded(head, _pad4(4 + d * (k + 1) + 2 * d * k + d))
+        aux = [L.WITHIN_BIN[self.within_bin], int(self.within_bin_clip), int(bool(self._is_discrete.any())), 0]
+        gaussian = self.within_bin == "gaussian"
+        common = dict(kind=L.OP_SNN, dim=d, k=k, n_out=d * k, aux=aux, scratch=d * k, heavy=True,
+                      n_normals=d if gaussian else 0, n_uniforms=d if gaussian else 2 * d)
+        if dp == 0:
+            t = self.temperature
+            if self._root_ready:  # softmax_nn.py:636-641
+                logits = torch.log_softmax(self._root_log_probs / t, dim=-1)
+            else:
+                logits = self._logits / t
+            params = np.concatenate([head, _padded(_np(logits), _pad4(d * k))])
+            return Packed(n_par=0, params=params, n_layers=0, **common)
+        mlp, dims = pack_mlp(self.layers, dp)
+        if dims[-1] != d * k:
+            raise ValueError("softmax_nn net must output D*C logits")
+        return Packed(n_par=dp, params=np.concatenate([head, mlp]), n_layers=len(dims),
+                      act=L.ACT[self.activation], layer_dim=dims, **common)
+
+    @classmethod
+    def from_spec(cls, c, device=None):
+        return cls(c["input_dim"], c["output_dim"], c["n_classes"], layers=c.get("layers"),
+                   logits=c.get("logits"), root_log_probs=c.get("root_log_probs"),
+                   root_ready=c.get("root_ready", False), bin_edges=c["bin_edges"],
+                   class_values=c["class_values"], sample_values=c["sample_values"],
+                   is_discrete=c["is_discrete"], bins_ready=c.get("bins_ready", True),
+                   activation=c["activation"], temperature=c.get("temperature", 1.0),
+                   min_bin_width=c["min_bin_width"], within_bin=c["within_bin"],
+                   within_bin_scale=c["within_bin_scale"], within_bin_clip=c["within_bin_clip"],
+                   device=device)
+
+    @classmethod
+    def from_reference(cls, cpd, device=None):
+        root = cpd.input_dim == 0
+        return cls(cpd.input_dim, cpd.output_dim, cpd.n_classes,
+                   layers=None if root else _layers_from_module(cpd.net),
+                   logits=cpd._logits if root else None, root_log_probs=cpd._root_log_probs,
+                   root_ready=bool(cpd._root_ready.item()), bin_edges=cpd._bin_edges,
+                   class_values=cpd._class_values, sample_values=cpd._sample_values,
+                   is_discrete=cpd._is_discrete, bins_ready=bool(cpd._bins_ready.item()),
+                   activation=cpd.activation, temperature=cpd.temperature,
+                   min_bin_width=cpd.min_bin_width, within_bin=cpd.within_bin,
+                   within_bin_scale=cpd.within_bin_scale, within_bin_clip=cpd.within_bin_clip,
+                   device=device)
+
+    def to_spec(self):
+        out = {"kind": self.kind, "input_dim": self.input_dim, "output_dim": self.output_dim,
+               "n_classes": self.n_classes, "activation": self.activation,
+               "temperature": self.temperature, "min_bin_width": self.min_bin_width,
+               "within_bin": self.within_bin, "within_bin_scale": self.within_bin_scale,
+               "within_bin_clip": self.within_bin_clip, "bin_edges": self._bin_edges,
+               "class_values": self._class_values, "sample_values": self._sample_values,
+               "is_discrete": self._is_discrete, "bins_ready": self._bins_ready,
+               "root_ready": self._root_ready, "root_log_probs": self._root_log_probs}
+        if self.input_dim == 0:
+            out["logits"] = self._logits
+        else:
+            out["layers"] = self.layers
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+class KDECPD(BaseCPD):
+    """vbn/cpds/kde.py:13-182 (stored points _parents[N,Dp], _targets[N,Dx])."""
+
+    kind = "kde"
+
+    def __init__(self, input_dim, output_dim, *, parents=None, targets=None, bandwidth: float = 1.0,
+                 parent_bandwidth: Optional[float] = None, min_scale: float = 1e-3, device=None):
+        super().__init__(input_dim, output_dim, device)
+        self.bandwidth = float(bandwidth)
+        self.parent_bandwidth = float(parent_bandwidth) if parent_bandwidth is not None else float(bandwidth)
+        self.min_scale = float(min_scale)
+        self._targets = None if targets is None else _f32(targets).reshape(-1, self.output_dim)
+        n = 0 if self._targets is None else self._targets.shape[0]
+        if parents is None or self.input_dim == 0:
+            self._parents = torch.zeros(n, 0)
+        else:
+            self._parents = _f32(parents).reshape(n, self.input_dim)
+        self._dev_points = None  # (parents, targets) on the device for the stand-alone kernel
+
+    def _check_fitted(self) -> None:
+        if self._targets is None:  # kde.py:64-66
+            raise RuntimeError("KDECPD is not fitted yet.")
+
+    def scales(self) -> Tuple[float, float]:
+        sy = max(self.bandwidth, 1e-3) + self.min_scale  # kde.py:105-109
+        sp = max(self.parent_bandwidth, 1e-3) + self.min_scale
+        return sy, sp
+
+    def _pack(self) -> Packed:
+        self._check_fitted()
+        d, dp = self.output_dim, self.input_dim
+        n = int(self._targets.shape[0])
+        sy, sp = self.scales()
+        head = np.array([0.5 / (sy * sy), 0.5 / (sp * sp), -0.5 * d * (LOG_2PI + 2.0 * math.log(sy)),
+                         max(self.bandwidth, 1e-3) + self.min_scale, math.log(float(n)), 0, 0, 0], np.float32)
+        params = np.concatenate([head, _padded(_np(self._parents), _pad4(n * dp)),
+                                 _padded(_np(self._targets), _pad4(n * d))])
+        return Packed(kind=L.OP_KDE, dim=d, n_par=dp, params=params, k=n, n_normals=d, n_uniforms=1,
+                      heavy=True)
+
+    @classmethod
+    def from_spec(cls, c, device=None):
+        return cls(c["input_dim"], c["output_dim"], parents=c.get("parents"), targets=c.get("targets"),
+                   bandwidth=c["bandwidth"], parent_bandwidth=c["parent_bandwidth"],
+                   min_scale=c["min_scale"], device=device)
+
+    @classmethod
+    def from_reference(cls, cpd, device=None):
+        return cls(cpd.input_dim, cpd.output_dim, parents=cpd._parents, targets=cpd._targets,
+                   bandwidth=cpd.bandwidth, parent_bandwidth=cpd.parent_bandwidth,
+                   min_scale=cpd.min_scale, device=device)
+
+    def to_spec(self):
+        return {"kind": self.kind, "input_dim": self.input_dim, "output_dim": self.output_dim,
+                "bandwidth": self.bandwidth, "parent_bandwidth": self.parent_bandwidth,
+                "min_scale": self.min_scale, "parents": self._parents, "targets": self._targets}
+
+
+CPD_CLASSES = {
+    "linear_gaussian": LinearGaussianCPD,
+    "gaussian_nn": GaussianNNCPD,
+    "mdn": MDNCPD,
+    "softmax_nn": SoftmaxNNCPD,
+    "kde": KDECPD,
+}
+
+_REFERENCE_CLASS_NAMES = {
+    "LinearGaussianCPD": LinearGaussianCPD,
+    "GaussianNNCPD": GaussianNNCPD,
+    "MDNCPD": MDNCPD,
+    "SoftmaxNNCPD": SoftmaxNNCPD,
+    "KDECPD": KDECPD,
+}
+
+
+def cpd_from_spec(c: dict, device=None) -> BaseCPD:
+    kind = c["kind"]
+    if kind not in CPD_CLASSES:
+        raise ValueError(f"CPD kind '{kind}' is outside the accelerated path")
+    return CPD_CLASSES[kind].from_spec(c, device)
+
+
+def wrap_cpd(obj, device=None) -> BaseCPD:
+    """Accepts one of our CPDs or a reference ``vbn.cpds.*`` module and returns ours."""
+    if isinstance(obj, BaseCPD):
+        return obj
+    name = type(obj).__name__
+    if name in _REFERENCE_CLASS_NAMES and hasattr(obj, "input_dim"):
+        return _REFERENCE_CLASS_NAMES[name].from_reference(obj, device)
+    raise TypeError(
+        f"CPD type '{name}' has no CUDA implementation (supported: {sorted(CPD_CLASSES)}); "
+        "there is no CPU fallback"
+    )

@@ -1,0 +1,246 @@
+// libvbn_cuda.so -- C ABI + host launch code.  See include/vbn_cuda.h for the contract.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "vbn_cuda.h"
+#include "vbn_kde.cuh"
+#include "vbn_reduce.cuh"
+#include "vbn_schedule.cuh"
+
+static_assert(sizeof(VbnOp) == 128, "VbnOp must be 128 bytes");
+static_assert(sizeof(VbnView) == 24, "VbnView layout");
+static_assert(sizeof(VbnNoise) == 24, "VbnNoise layout");
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t e__ = (expr);                                                           \
+    if (e__ != cudaSuccess)                                                             \
+      return fail(VBN_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                  __FILE__, __LINE__);                                                  \
+  } while (0)
+
+// ---- launch shapes of the schedule kernel -------------------------------------------------
+struct Shape {
+  int rpt, nt, heavy, min_blocks;
+  const void* fn;
+};
+
+template <int RPT, int NT, bool HEAVY, int MB>
+constexpr Shape make_shape() {
+  return Shape{RPT, NT, HEAVY ? 1 : 0, MB,
+               reinterpret_cast<const void*>(&vbn::schedule_kernel<RPT, NT, HEAVY, MB>)};
+}
+
+// preferred first; later entries hold fewer rows per CTA (capacity fallbacks)
+const Shape kShapes[] = {
+    make_shape<2, 128, true, 3>(),
+    make_shape<1, 128, true, 3>(),
+    make_shape<1, 64, true, 1>(),
+    make_shape<2, 256, false, 2>(),
+    make_shape<1, 128, false, 4>(),
+    make_shape<1, 64, false, 1>(),
+};
+
+}  // namespace
+
+struct VbnPlan {
+  VbnProgramDesc desc;
+  int device;
+  int num_sms;
+  int shape;       // index into kShapes
+  int blocks_per_sm;
+  size_t smem_bytes;
+};
+
+extern "C" {
+
+int32_t vbn_cuda_abi_version(void) { return VBN_CUDA_ABI_VERSION; }
+
+const char* vbn_cuda_last_error(void) { return g_err; }
+
+int32_t vbn_cuda_device_count(int32_t* out_count) {
+  if (!out_count) return fail(VBN_E_INVALID, "out_count is NULL");
+  int n = 0;
+  CUDA_TRY(cudaGetDeviceCount(&n));
+  *out_count = n;
+  return VBN_OK;
+}
+
+int32_t vbn_plan_create(const VbnProgramDesc* desc, VbnPlan** out_plan) {
+  if (!desc || !out_plan) return fail(VBN_E_INVALID, "NULL argument");
+  if (desc->n_ops <= 0 || !desc->ops_dev) return fail(VBN_E_INVALID, "empty program");
+  if (desc->n_slots <= 0 || desc->n_scratch < 0) return fail(VBN_E_INVALID, "bad slot counts");
+  VbnPlan* p = new (std::nothrow) VbnPlan();
+  if (!p) return fail(VBN_E_INVALID, "out of host memory");
+  p->desc = *desc;
+  CUDA_TRY(cudaGetDevice(&p->device));
+  CUDA_TRY(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, p->device));
+  int max_smem = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
+  p->shape = -1;
+  const size_t per_row = static_cast<size_t>(desc->n_slots + desc->n_scratch) * sizeof(float);
+  for (int i = 0; i < static_cast<int>(sizeof(kShapes) / sizeof(kShapes[0])); ++i) {
+    const Shape& s = kShapes[i];
+    if (s.heavy != (desc->heavy ? 1 : 0)) continue;
+    const size_t bytes = per_row * s.rpt * s.nt;
+    if (bytes > static_cast<size_t>(max_smem)) continue;
+    CUDA_TRY(cudaFuncSetAttribute(s.fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(bytes)));
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s.fn, s.nt, bytes));
+    if (occ < 1) continue;
+    p->shape = i;
+    p->blocks_per_sm = occ;
+    p->smem_bytes = bytes;
+    break;
+  }
+  if (p->shape < 0) {
+    delete p;
+    return fail(VBN_E_CAPACITY,
+                "schedule needs %d value slots + %d scratch floats per row: exceeds %d bytes of "
+                "shared memory even at 64 rows per CTA",
+                desc->n_slots, desc->n_scratch, max_smem);
+  }
+  *out_plan = p;
+  return VBN_OK;
+}
+
+int32_t vbn_plan_destroy(VbnPlan* plan) {
+  delete plan;
+  return VBN_OK;
+}
+
+int32_t vbn_run_forward_launches(const VbnPlan* plan) { return plan ? 1 : 0; }
+
+int32_t vbn_run_forward(const VbnPlan* plan, const VbnRunDesc* run, void* stream) {
+  if (!plan || !run) return fail(VBN_E_INVALID, "NULL argument");
+  if (run->n_queries <= 0 || run->n_samples <= 0) return fail(VBN_E_INVALID, "empty run");
+  const Shape& s = kShapes[plan->shape];
+  vbn::ScheduleArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.ops = plan->desc.ops_dev;
+  a.par_slots = plan->desc.par_slots_dev;
+  a.params = plan->desc.params_dev;
+  a.n_ops = plan->desc.n_ops;
+  a.n_slots = plan->desc.n_slots;
+  a.n_scratch = plan->desc.n_scratch;
+  a.logp_as_pdf = run->logp_as_pdf;
+  a.n_queries = run->n_queries;
+  a.n_samples = run->n_samples;
+  a.n_rows = run->n_queries * run->n_samples;
+  a.query_offset = static_cast<uint32_t>(run->query_offset);
+  a.sample_offset = static_cast<uint32_t>(run->sample_offset);
+  a.key0 = static_cast<uint32_t>(run->seed);
+  a.key1 = static_cast<uint32_t>(run->seed >> 32);
+  a.call_offset = static_cast<uint32_t>(run->call_offset);
+  a.fixed = run->fixed_dev;
+  a.inputs = run->inputs_dev;
+  a.stores = run->stores_dev;
+  a.noise = run->noise_dev;
+  a.logw = run->logw_dev;
+  a.logp = run->logp_dev;
+  a.error_flag = run->error_flag_dev;
+  const int64_t rows_per_cta = static_cast<int64_t>(s.rpt) * s.nt;
+  const int64_t n_tiles = (a.n_rows + rows_per_cta - 1) / rows_per_cta;
+  const int64_t resident = static_cast<int64_t>(plan->num_sms) * plan->blocks_per_sm;
+  const unsigned grid = static_cast<unsigned>(n_tiles < resident ? n_tiles : resident);
+  void* args[] = {&a};
+  CUDA_TRY(cudaLaunchKernel(s.fn, dim3(grid), dim3(s.nt), args, plan->smem_bytes,
+                            static_cast<cudaStream_t>(stream)));
+  return VBN_OK;
+}
+
+int32_t vbn_lse_partials(const float* logw_dev, int64_t n_queries, int64_t n_samples,
+                         int32_t n_split, float* partials_dev, void* stream) {
+  if (!logw_dev || !partials_dev || n_queries <= 0 || n_samples <= 0 || n_split <= 0)
+    return fail(VBN_E_INVALID, "bad argument to vbn_lse_partials");
+  vbn::lse_partials_kernel<<<dim3(static_cast<unsigned>(n_queries), n_split), 256, 0,
+                             static_cast<cudaStream_t>(stream)>>>(logw_dev, n_samples, n_split,
+                                                                  partials_dev);
+  CUDA_TRY(cudaGetLastError());
+  return VBN_OK;
+}
+
+int32_t vbn_lse_merge(const float* partials_dev, int64_t n_queries, int32_t n_split,
+                      float* stats_dev, void* stream) {
+  if (!partials_dev || !stats_dev || n_queries <= 0 || n_split <= 0)
+    return fail(VBN_E_INVALID, "bad argument to vbn_lse_merge");
+  const unsigned grid = static_cast<unsigned>((n_queries + 127) / 128);
+  vbn::lse_merge_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      partials_dev, n_queries, n_split, stats_dev);
+  CUDA_TRY(cudaGetLastError());
+  return VBN_OK;
+}
+
+int32_t vbn_weights_normalize(const float* logw_dev, const float* stats_dev, int64_t n_queries,
+                              int64_t n_samples, int32_t normalize, float eps, float* w_dev,
+                              float* ess_dev, void* stream) {
+  if (!logw_dev || !stats_dev || !w_dev || n_queries <= 0 || n_samples <= 0)
+    return fail(VBN_E_INVALID, "bad argument to vbn_weights_normalize");
+  int dev = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t total = n_queries * n_samples;
+  int64_t want = (total + 256 * 4 - 1) / (256 * 4);
+  const int64_t cap = static_cast<int64_t>(sms) * 8;
+  const unsigned grid = static_cast<unsigned>(want < cap ? (want > 0 ? want : 1) : cap);
+  vbn::weights_normalize_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      logw_dev, stats_dev, n_queries, n_samples, normalize, eps, w_dev, ess_dev);
+  CUDA_TRY(cudaGetLastError());
+  return VBN_OK;
+}
+
+int32_t vbn_ess_below(const float* stats_dev, int64_t n_queries, float threshold,
+                      int32_t* flag_dev, void* stream) {
+  if (!stats_dev || !flag_dev || n_queries <= 0) return fail(VBN_E_INVALID, "bad argument");
+  const unsigned grid = static_cast<unsigned>((n_queries + 255) / 256);
+  vbn::ess_below_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(stats_dev, n_queries,
+                                                                           threshold, flag_dev);
+  CUDA_TRY(cudaGetLastError());
+  return VBN_OK;
+}
+
+int32_t vbn_kde_log_prob(const float* train_p_dev, const float* train_y_dev, int64_t n_points,
+                         int32_t dp, int32_t dx, const float* query_p_dev,
+                         const float* query_x_dev, int64_t n_rows, float bandwidth,
+                         float parent_bandwidth, float min_scale, float* out_dev, void* stream) {
+  if (!train_y_dev || !query_x_dev || !out_dev || n_points <= 0 || n_rows <= 0 || dx <= 0 || dp < 0)
+    return fail(VBN_E_INVALID, "bad argument to vbn_kde_log_prob");
+  if (dp > 0 && (!train_p_dev || !query_p_dev))
+    return fail(VBN_E_INVALID, "parent arrays required when dp > 0");
+  return vbn::launch_kde_log_prob(train_p_dev, train_y_dev, n_points, dp, dx, query_p_dev,
+                                  query_x_dev, n_rows, bandwidth, parent_bandwidth, min_scale,
+                                  out_dev, static_cast<cudaStream_t>(stream)) == cudaSuccess
+             ? VBN_OK
+             : fail(VBN_E_CUDA, "kde launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+}
+
+int32_t vbn_philox_fill(const uint32_t* ctr_dev, int64_t n, uint32_t key0, uint32_t key1,
+                        uint32_t* out_dev, void* stream) {
+  if (!ctr_dev || !out_dev || n <= 0) return fail(VBN_E_INVALID, "bad argument");
+  const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+  vbn::philox_fill_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(ctr_dev, n, key0, key1,
+                                                                             out_dev);
+  CUDA_TRY(cudaGetLastError());
+  return VBN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,104 @@
+// Device-side building blocks shared by the schedule kernel and the stand-alone kernels.
+// sm_100a only.  No host code here.
+#pragma once
+#ifndef VBN_HOST_EMU  // tests/emu/cuda_shim.h supplies these for the host-emulation test build
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#endif
+#include <stdint.h>
+
+#include "vbn_cuda.h"
+
+namespace vbn {
+
+constexpr float kLog2Pi = 1.8378770664093453f;      // ln(2*pi)
+constexpr float kHalfLog2Pi = 0.9189385332046727f;  // ln(sqrt(2*pi))
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 counter RNG (Salmon et al., SC'11).  Counter layout used by the schedule
+// kernel: (c0, c1, c2, c3) = (global sample s, global query b | 0xFFFFFFFF when the draw is
+// shared by all queries, stream block index | stream tag << 30, call offset).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  constexpr uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += W0;
+    k.y += W1;
+  }
+  return c;
+}
+
+// uint32 -> float in (0,1): 24 random bits, centred, never 0 or 1.
+__device__ __forceinline__ float u01(uint32_t x) {
+  return (static_cast<float>(x >> 8) + 0.5f) * 5.9604644775390625e-8f;  // 2^-24
+}
+
+// Two uniforms -> two standard normals (Box-Muller).  Fast intrinsics: these only shape the
+// generated noise (no parity requirement on generated bits, only on the law).
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  const float u1 = u01(a);
+  const float u2 = u01(b) - 0.5f;  // angle in (-pi, pi): best range for sin/cos.approx
+  const float r = sqrtf(-2.0f * __logf(u1));
+  float s, c;
+  __sincosf(6.283185307179586f * u2, &s, &c);
+  return make_float2(r * c, r * s);
+}
+
+__device__ __forceinline__ float4 normal4(uint4 w) {
+  const float2 a = box_muller(w.x, w.y);
+  const float2 b = box_muller(w.z, w.w);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+__device__ __forceinline__ float4 uniform4(uint4 w) {
+  return make_float4(u01(w.x), u01(w.y), u01(w.z), u01(w.w));
+}
+
+__device__ __forceinline__ float lane4(const float4& v, int lane) {
+  return lane == 0 ? v.x : (lane == 1 ? v.y : (lane == 2 ? v.z : v.w));
+}
+
+// ---------------------------------------------------------------------------------------
+// scalar math that mirrors the torch ops the reference uses
+// ---------------------------------------------------------------------------------------
+// F.softplus(x) (beta=1, threshold=20)  -- vbn/cpds/utils.py:6-7
+__device__ __forceinline__ float softplus20(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
+
+__device__ __forceinline__ float activate(float x, int act) {
+  switch (act) {
+    case VBN_ACT_RELU: return fmaxf(x, 0.0f);
+    case VBN_ACT_TANH: return tanhf(x);
+    case VBN_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));  // nn.GELU (erf)
+    default: return x > 0.0f ? x : expm1f(x);                                      // nn.ELU(alpha=1)
+  }
+}
+
+// -0.5*((x-loc)^2/var + 2 ln sigma + ln 2pi) for one dim (linear_gaussian.py:214-217)
+__device__ __forceinline__ float gauss_term(float x, float loc, float var, float two_log_scale) {
+  const float d = x - loc;
+  return __fdiv_rn(d * d, var) + two_log_scale + kLog2Pi;
+}
+
+// streaming logsumexp state
+struct Lse {
+  float m, l;
+  __device__ __forceinline__ void init() { m = -CUDART_INF_F; l = 0.0f; }
+  __device__ __forceinline__ void push(float x) {
+    if (x > m) {
+      l = l * __expf(m - x) + 1.0f;
+      m = x;
+    } else {
+      l += __expf(x - m);
+    }
+  }
+  __device__ __forceinline__ float value() const { return m + logf(l); }
+};
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+}  // namespace vbn

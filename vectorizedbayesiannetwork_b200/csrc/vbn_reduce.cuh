@@ -1,0 +1,146 @@
+// Weight reduction kernels: per-query softmax over the S log-weights, ESS, fallback flag.
+// Replaces torch.softmax(log_weights, dim=1); ess = 1/(w**2).sum(1); torch.any(ess < thr)
+// (vbn/inference/importance_sampling.py:82-86, likelihood_weighting.py:75-80).
+// HBM-bound: logw is read twice (4+4 B/row) and w written once (4 B/row).
+#pragma once
+#include "vbn_device.cuh"
+
+namespace vbn {
+
+// (m, l, q) triple: m = max x, l = sum exp(x-m), q = sum exp(2(x-m)).  Merge is associative.
+struct Mlq {
+  float m, l, q;
+};
+
+__device__ __forceinline__ Mlq mlq_merge(Mlq a, Mlq b) {
+  if (b.m == -CUDART_INF_F) return a;
+  if (a.m == -CUDART_INF_F) return b;
+  const float m = fmaxf(a.m, b.m);
+  const float ea = __expf(a.m - m), eb = __expf(b.m - m);
+  return Mlq{m, a.l * ea + b.l * eb, a.q * ea * ea + b.q * eb * eb};
+}
+
+__device__ __forceinline__ void mlq_push(Mlq& s, float x) {
+  if (x > s.m) {
+    const float e = __expf(s.m - x);  // exp(-inf)=0 on the first element
+    s.l = s.l * e + 1.0f;
+    s.q = s.q * e * e + 1.0f;
+    s.m = x;
+  } else {
+    const float e = __expf(x - s.m);
+    s.l += e;
+    s.q += e * e;
+  }
+}
+
+__device__ __forceinline__ Mlq mlq_warp(Mlq s) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Mlq t;
+    t.m = __shfl_xor_sync(0xffffffffu, s.m, o);
+    t.l = __shfl_xor_sync(0xffffffffu, s.l, o);
+    t.q = __shfl_xor_sync(0xffffffffu, s.q, o);
+    s = mlq_merge(s, t);
+  }
+  return s;
+}
+
+// grid (B, n_split), 256 threads: block (b, sp) reduces samples [sp*chunk, (sp+1)*chunk) of query b
+__global__ void __launch_bounds__(256) lse_partials_kernel(const float* __restrict__ logw,
+                                                            int64_t n_samples, int n_split,
+                                                            float* __restrict__ partials) {
+  const int64_t b = blockIdx.x;
+  const int sp = blockIdx.y;
+  const int64_t chunk = (n_samples + n_split - 1) / n_split;
+  const int64_t lo = sp * chunk;
+  const int64_t hi = lo + chunk < n_samples ? lo + chunk : n_samples;
+  const float* x = logw + b * n_samples;
+  Mlq s{-CUDART_INF_F, 0.0f, 0.0f};
+  // 128-bit loads when the query row is 16-byte aligned
+  const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((lo & 3) == 0);
+  if (vec) {
+    const int64_t n4 = (hi - lo) >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x + lo);
+    for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 v = __ldg(x4 + i);
+      mlq_push(s, v.x);
+      mlq_push(s, v.y);
+      mlq_push(s, v.z);
+      mlq_push(s, v.w);
+    }
+    for (int64_t i = lo + (n4 << 2) + threadIdx.x; i < hi; i += blockDim.x) mlq_push(s, __ldg(x + i));
+  } else {
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) mlq_push(s, __ldg(x + i));
+  }
+  s = mlq_warp(s);
+  __shared__ Mlq sh[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) sh[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    s = lane < 8 ? sh[lane] : Mlq{-CUDART_INF_F, 0.0f, 0.0f};
+    s = mlq_warp(s);
+    if (lane == 0) {
+      float* o = partials + (b * n_split + sp) * 3;
+      o[0] = s.m;
+      o[1] = s.l;
+      o[2] = s.q;
+    }
+  }
+}
+
+// one thread per query: merge n_split partial triples.  Also used for the cross-GPU merge
+// (partials = all-gathered per-rank stats).
+__global__ void lse_merge_kernel(const float* __restrict__ partials, int64_t n_queries, int n_split,
+                                 float* __restrict__ stats) {
+  const int64_t b = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (b >= n_queries) return;
+  Mlq s{-CUDART_INF_F, 0.0f, 0.0f};
+  for (int i = 0; i < n_split; ++i) {
+    const float* p = partials + (b * n_split + i) * 3;
+    s = mlq_merge(s, Mlq{p[0], p[1], p[2]});
+  }
+  stats[b * 3 + 0] = s.m;
+  stats[b * 3 + 1] = s.l;
+  stats[b * 3 + 2] = s.q;
+}
+
+__global__ void __launch_bounds__(256) weights_normalize_kernel(
+    const float* __restrict__ logw, const float* __restrict__ stats, int64_t n_queries,
+    int64_t n_samples, int normalize, float eps, float* __restrict__ w, float* __restrict__ ess) {
+  const int64_t total = n_queries * n_samples;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; r < total; r += stride) {
+    const int64_t b = r / n_samples;
+    const float m = __ldg(stats + b * 3), l = __ldg(stats + b * 3 + 1);
+    const float e = expf(__ldg(logw + r) - m);
+    w[r] = normalize ? __fdiv_rn(e, l) : fmaxf(e, eps);
+    if (ess != nullptr && r == b * n_samples) {
+      const float q = __ldg(stats + b * 3 + 2);
+      ess[b] = __fdiv_rn(l * l, q);  // 1/sum(w^2) with w = e/l
+    }
+  }
+}
+
+__global__ void ess_below_kernel(const float* __restrict__ stats, int64_t n_queries, float threshold,
+                                 int32_t* __restrict__ flag) {
+  const int64_t b = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (b >= n_queries) return;
+  const float l = stats[b * 3 + 1], q = stats[b * 3 + 2];
+  const float ess = __fdiv_rn(l * l, q);
+  if (ess < threshold) atomicOr(flag, 1);
+}
+
+__global__ void philox_fill_kernel(const uint32_t* __restrict__ ctr, int64_t n, uint32_t k0,
+                                   uint32_t k1, uint32_t* __restrict__ out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const uint4 c = make_uint4(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3]);
+  const uint4 r = philox4x32_10(c, make_uint2(k0, k1));
+  out[4 * i] = r.x;
+  out[4 * i + 1] = r.y;
+  out[4 * i + 2] = r.z;
+  out[4 * i + 3] = r.w;
+}
+
+}  // namespace vbn

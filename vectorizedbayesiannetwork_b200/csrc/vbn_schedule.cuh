@@ -1,0 +1,861 @@
+// The fused schedule kernel: one launch walks every op (node) of a compiled schedule for a
+// tile of rows; node values live in shared-memory slots, never in HBM unless the caller
+// asked for the column.  sm_100a only.
+//
+// Replaces, per row, the Python per-node loops of the reference:
+//   vbn/inference/likelihood_weighting.py:42-71, importance_sampling.py:56-80,
+//   monte_carlo_marginalization.py:39-92, vbn/sampling/ancestral.py:27-41
+// and the CPD bodies they call (cited at each op below).
+#pragma once
+#include "vbn_device.cuh"
+
+namespace vbn {
+
+struct ScheduleArgs {
+  const VbnOp* ops;
+  const int32_t* par_slots;
+  const float* params;
+  int32_t n_ops;
+  int32_t n_slots;
+  int32_t n_scratch;
+  int32_t logp_as_pdf;
+  int64_t n_queries;  // B (local)
+  int64_t n_samples;  // S (local)
+  int64_t n_rows;     // B*S
+  uint32_t query_offset;
+  uint32_t sample_offset;
+  uint32_t key0, key1;
+  uint32_t call_offset;
+  const float* fixed;
+  const VbnView* inputs;
+  const VbnView* stores;
+  const VbnNoise* noise;
+  float* logw;
+  float* logp;
+  int32_t* error_flag;
+};
+
+constexpr int kMaxGenericWidth = 128;  // widest layer the generic MLP path accepts
+
+__host__ __device__ __forceinline__ int pad4(int x) { return (x + 3) & ~3; }
+
+// Per-thread state for RPT rows handled together (row j of the thread is tile row j*NT+tid).
+template <int RPT>
+struct Rows {
+  int64_t r[RPT];   // local row index, clamped into range
+  int64_t lb[RPT];  // local query index
+  int64_t ls[RPT];  // local sample index
+  uint32_t gb[RPT], gs[RPT];  // global query / sample index (RNG counter words)
+  bool valid[RPT];
+  float logw[RPT];
+  float logp[RPT];
+  // Philox stream caches (per-row keyed streams): block index + 4 values per row
+  int cur_nq, cur_uq;
+  float4 ncache[RPT], ucache[RPT];
+};
+
+template <int RPT, int NT>
+struct Ctx {
+  const ScheduleArgs& a;
+  float* slots;    // [n_slots][ROWS]
+  float* scratch;  // [n_scratch][ROWS]
+  int tid;
+  Rows<RPT> rows;
+  static constexpr int ROWS = RPT * NT;
+
+  __device__ __forceinline__ Ctx(const ScheduleArgs& args, float* smem, int t)
+      : a(args), slots(smem), scratch(smem + static_cast<size_t>(args.n_slots) * ROWS), tid(t) {}
+
+  __device__ __forceinline__ float& slot(int s, int j) { return slots[s * ROWS + j * NT + tid]; }
+  __device__ __forceinline__ float& scr(int s, int j) { return scratch[s * ROWS + j * NT + tid]; }
+
+  // ---- random draws ---------------------------------------------------------------------
+  // stream tags in counter word c2 (top 2 bits): 0 normal/row, 1 uniform/row, 2 normal/shared,
+  // 3 uniform/shared
+  __device__ __forceinline__ uint4 philox(int j, uint32_t block, uint32_t tag, bool shared) const {
+    const uint4 c = make_uint4(rows.gs[j], shared ? 0xFFFFFFFFu : rows.gb[j], block | (tag << 30),
+                               a.call_offset);
+    return philox4x32_10(c, make_uint2(a.key0, a.key1));
+  }
+
+  // normal number `index` of the op's stream, for all RPT rows
+  __device__ __forceinline__ void draw_normal(const VbnOp& op, int index, int d, float (&out)[RPT]) {
+    const bool shared = (op.flags & VBN_F_SHARED) != 0;
+    if (op.noise_idx >= 0) {
+      const float* eps = a.noise[op.noise_idx].eps;
+#pragma unroll
+      for (int j = 0; j < RPT; ++j)
+        out[j] = __ldg(eps + (shared ? rows.ls[j] : rows.r[j]) * op.dim + d);
+      return;
+    }
+    const int q = index >> 2, lane = index & 3;
+    if (shared) {
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) out[j] = lane4(normal4(philox(j, q, 2u, true)), lane);
+      return;
+    }
+    if (q != rows.cur_nq) {
+      rows.cur_nq = q;
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) rows.ncache[j] = normal4(philox(j, q, 0u, false));
+    }
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) out[j] = lane4(rows.ncache[j], lane);
+  }
+
+  // uniform number `index`; `slot_in_noise` selects which injected array element to use
+  __device__ __forceinline__ void draw_uniform(const VbnOp& op, int index, int d, float (&out)[RPT]) {
+    const bool shared = (op.flags & VBN_F_SHARED) != 0;
+    if (op.noise_idx >= 0 && a.noise[op.noise_idx].u != nullptr) {
+      const float* u = a.noise[op.noise_idx].u;
+#pragma unroll
+      for (int j = 0; j < RPT; ++j)
+        out[j] = __ldg(u + (shared ? rows.ls[j] : rows.r[j]) * op.dim + d);
+      return;
+    }
+    const int q = index >> 2, lane = index & 3;
+    if (shared) {
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) out[j] = lane4(uniform4(philox(j, q, 3u, true)), lane);
+      return;
+    }
+    if (q != rows.cur_uq) {
+      rows.cur_uq = q;
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) rows.ucache[j] = uniform4(philox(j, q, 1u, false));
+    }
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) out[j] = lane4(rows.ucache[j], lane);
+  }
+
+  // injected categorical pick (per row, per dim `d` of `width` dims); returns false if absent
+  __device__ __forceinline__ bool injected_index(const VbnOp& op, int d, int width, int (&out)[RPT]) {
+    if (op.noise_idx < 0) return false;
+    const int32_t* idx = a.noise[op.noise_idx].idx;
+    if (idx == nullptr) return false;
+    const bool shared = (op.flags & VBN_F_SHARED) != 0;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j)
+      out[j] = __ldg(idx + (shared ? rows.ls[j] : rows.r[j]) * width + d);
+    return true;
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// MLP forward (gaussian_nn.py:16-34 _build_mlp; mdn.py:199; softmax_nn.py:585).
+// Parameter block layout (floats, every array padded to a multiple of 4):
+//   n_layers == 0 : out[n_out] constants (root CPDs)
+//   hidden layer l: WT[in][pad4(out)] (transposed), bias[pad4(out)]
+//   last layer    : W[out][pad4(in)] (nn.Linear layout), bias[pad4(out)]
+// Result lands in scratch rows 0..n_out-1.
+// `norm` (gaussian_nn only): mean_x[Dp], std_x[Dp] -> z = (pa - mean_x)/std_x (gaussian_nn.py:105-112)
+// ---------------------------------------------------------------------------------------
+template <int RPT, int NT>
+__device__ __noinline__ void mlp_generic(Ctx<RPT, NT>& c, const VbnOp& op, const float* P,
+                                         const float* norm, const int32_t* par) {
+  float bufA[kMaxGenericWidth], bufB[kMaxGenericWidth];
+  for (int j = 0; j < RPT; ++j) {
+    for (int p = 0; p < op.n_par; ++p) {
+      float z = c.slot(__ldg(par + p), j);
+      if (norm) z = __fdiv_rn(z - __ldg(norm + p), __ldg(norm + op.n_par + p));
+      bufA[p] = z;
+    }
+    float* cur = bufA;
+    float* nxt = bufB;
+    int in = op.n_par;
+    const float* W = P;
+    for (int l = 0; l + 1 < op.n_layers; ++l) {
+      const int out = op.layer_dim[l], outp = pad4(out);
+      const float* bias = W + static_cast<size_t>(in) * outp;
+      for (int o = 0; o < out; ++o) {
+        float acc = __ldg(bias + o);
+        for (int i = 0; i < in; ++i) acc = fmaf(__ldg(W + i * outp + o), cur[i], acc);
+        nxt[o] = activate(acc, op.act);
+      }
+      W = bias + outp;
+      float* t = cur;
+      cur = nxt;
+      nxt = t;
+      in = out;
+    }
+    const int out = op.n_out, inp = pad4(in);
+    const float* bias = W + static_cast<size_t>(out) * inp;
+    for (int o = 0; o < out; ++o) {
+      float acc = __ldg(bias + o);
+      for (int i = 0; i < in; ++i) acc = fmaf(__ldg(W + o * inp + i), cur[i], acc);
+      c.scr(o, j) = acc;
+    }
+  }
+}
+
+// Fast path for the reference's default hidden_dims [32, 32]: h1 lives in registers, the
+// 32x32 layer is register-tiled 8 outputs at a time with 128-bit uniform weight loads (L1
+// broadcast), and the output layer is accumulated chunk by chunk into scratch.
+template <int RPT, int NT>
+__device__ __forceinline__ void mlp_fast32(Ctx<RPT, NT>& c, const VbnOp& op, const float* P,
+                                           const float* norm, const int32_t* par) {
+  constexpr int H = 32;
+  const int dp = op.n_par;
+  const float* W1 = P;               // [dp][32]
+  const float* b1 = W1 + dp * H;     // [32]
+  const float* W2 = b1 + H;          // [32][32] transposed: W2[k][j]
+  const float* b2 = W2 + H * H;      // [32]
+  const float* W3 = b2 + H;          // [O][32]
+  const int O = op.n_out;
+  const float* b3 = W3 + O * H;      // [pad4(O)]
+  const int act = op.act;
+
+  float h1[RPT][H];
+#pragma unroll
+  for (int q = 0; q < H / 4; ++q) {
+    const float4 b = ldg4(b1 + 4 * q);
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      h1[j][4 * q + 0] = b.x;
+      h1[j][4 * q + 1] = b.y;
+      h1[j][4 * q + 2] = b.z;
+      h1[j][4 * q + 3] = b.w;
+    }
+  }
+  for (int p = 0; p < dp; ++p) {
+    float z[RPT];
+    const int ps = __ldg(par + p);
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) z[j] = c.slot(ps, j);
+    if (norm) {
+      const float mu = __ldg(norm + p), sd = __ldg(norm + dp + p);
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) z[j] = __fdiv_rn(z[j] - mu, sd);
+    }
+#pragma unroll
+    for (int q = 0; q < H / 4; ++q) {
+      const float4 w = ldg4(W1 + p * H + 4 * q);
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        h1[j][4 * q + 0] = fmaf(w.x, z[j], h1[j][4 * q + 0]);
+        h1[j][4 * q + 1] = fmaf(w.y, z[j], h1[j][4 * q + 1]);
+        h1[j][4 * q + 2] = fmaf(w.z, z[j], h1[j][4 * q + 2]);
+        h1[j][4 * q + 3] = fmaf(w.w, z[j], h1[j][4 * q + 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < H; ++k)
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) h1[j][k] = activate(h1[j][k], act);
+
+  for (int o = 0; o < O; ++o) {
+    const float b = __ldg(b3 + o);
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) c.scr(o, j) = b;
+  }
+
+#pragma unroll 1
+  for (int jc = 0; jc < H / 8; ++jc) {
+    float acc[RPT][8];
+    {
+      const float4 ba = ldg4(b2 + 8 * jc), bb = ldg4(b2 + 8 * jc + 4);
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        acc[j][0] = ba.x; acc[j][1] = ba.y; acc[j][2] = ba.z; acc[j][3] = ba.w;
+        acc[j][4] = bb.x; acc[j][5] = bb.y; acc[j][6] = bb.z; acc[j][7] = bb.w;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+      const float4 wa = ldg4(W2 + k * H + 8 * jc), wb = ldg4(W2 + k * H + 8 * jc + 4);
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        const float h = h1[j][k];
+        acc[j][0] = fmaf(wa.x, h, acc[j][0]);
+        acc[j][1] = fmaf(wa.y, h, acc[j][1]);
+        acc[j][2] = fmaf(wa.z, h, acc[j][2]);
+        acc[j][3] = fmaf(wa.w, h, acc[j][3]);
+        acc[j][4] = fmaf(wb.x, h, acc[j][4]);
+        acc[j][5] = fmaf(wb.y, h, acc[j][5]);
+        acc[j][6] = fmaf(wb.z, h, acc[j][6]);
+        acc[j][7] = fmaf(wb.w, h, acc[j][7]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < RPT; ++j)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[j][q] = activate(acc[j][q], act);
+    for (int o = 0; o < O; ++o) {
+      const float4 wa = ldg4(W3 + o * H + 8 * jc), wb = ldg4(W3 + o * H + 8 * jc + 4);
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        float t = c.scr(o, j);
+        t = fmaf(wa.x, acc[j][0], t);
+        t = fmaf(wa.y, acc[j][1], t);
+        t = fmaf(wa.z, acc[j][2], t);
+        t = fmaf(wa.w, acc[j][3], t);
+        t = fmaf(wb.x, acc[j][4], t);
+        t = fmaf(wb.y, acc[j][5], t);
+        t = fmaf(wb.z, acc[j][6], t);
+        t = fmaf(wb.w, acc[j][7], t);
+        c.scr(o, j) = t;
+      }
+    }
+  }
+}
+
+template <int RPT, int NT>
+__device__ __forceinline__ void mlp_eval(Ctx<RPT, NT>& c, const VbnOp& op, const float* P,
+                                         const float* norm, const int32_t* par) {
+  if (op.n_layers == 0) {
+    for (int o = 0; o < op.n_out; ++o) {
+      const float v = __ldg(P + o);
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) c.scr(o, j) = v;
+    }
+  } else if (op.n_layers == 3 && op.layer_dim[0] == 32 && op.layer_dim[1] == 32) {
+    mlp_fast32<RPT, NT>(c, op, P, norm, par);
+  } else {
+    mlp_generic<RPT, NT>(c, op, P, norm, par);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// value sources / sinks common to all ops
+// ---------------------------------------------------------------------------------------
+template <int RPT, int NT>
+__device__ __forceinline__ void load_fixed(Ctx<RPT, NT>& c, const VbnOp& op) {
+  const int src = op.flags & VBN_SRC_MASK;
+  if (src == VBN_SRC_FIXED_Q) {
+    for (int d = 0; d < op.dim; ++d)
+#pragma unroll
+      for (int j = 0; j < RPT; ++j)
+        c.slot(op.out_slot + d, j) =
+            __ldg(c.a.fixed + static_cast<int64_t>(op.fixed_col + d) * c.a.n_queries + c.rows.lb[j]);
+  } else if (src == VBN_SRC_FIXED_ROW) {
+    const VbnView v = c.a.inputs[op.fixed_col];
+    for (int d = 0; d < op.dim; ++d)
+#pragma unroll
+      for (int j = 0; j < RPT; ++j)
+        c.slot(op.out_slot + d, j) = __ldg(v.base + c.rows.r[j] * v.row_stride + d * v.dim_stride);
+  }
+}
+
+template <int RPT, int NT>
+__device__ __forceinline__ void store_value(Ctx<RPT, NT>& c, const VbnOp& op) {
+  if (op.store_idx < 0) return;
+  const VbnView v = c.a.stores[op.store_idx];
+  for (int d = 0; d < op.dim; ++d)
+#pragma unroll
+    for (int j = 0; j < RPT; ++j)
+      if (c.rows.valid[j]) v.base[c.rows.r[j] * v.row_stride + d * v.dim_stride] = c.slot(op.out_slot + d, j);
+}
+
+template <int RPT, int NT>
+__device__ __forceinline__ void commit_logp(Ctx<RPT, NT>& c, const VbnOp& op, const float (&lp)[RPT]) {
+  if (op.flags & VBN_F_ADD_LOGW) {
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) c.rows.logw[j] += lp[j];
+  }
+  if (op.flags & VBN_F_OUT_LOGP) {
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) c.rows.logp[j] = lp[j];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// VBN_OP_LG: linear_gaussian.py:163-217 (and gaussian_nn roots, gaussian_nn.py:244-254).
+// params: W[Dp][D], bias[D], scale[D], two_log_scale[D], var[D]
+// ---------------------------------------------------------------------------------------
+template <int RPT, int NT>
+__device__ __forceinline__ void op_lg(Ctx<RPT, NT>& c, const VbnOp& op) {
+  const float* P = c.a.params + op.param_off;
+  const int D = op.dim, Dp = op.n_par;
+  const float* W = P;
+  const float* bias = W + Dp * D;
+  const float* scale = bias + D;
+  const float* tls = scale + D;
+  const float* var = tls + D;
+  const int32_t* par = c.a.par_slots + op.par_off;
+  const bool sample = (op.flags & VBN_SRC_MASK) == VBN_SRC_SAMPLE;
+  const bool want_lp = (op.flags & (VBN_F_ADD_LOGW | VBN_F_OUT_LOGP)) != 0;
+  float acc[RPT];
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) acc[j] = 0.0f;
+  for (int d = 0; d < D; ++d) {
+    float loc[RPT];
+    const float b = __ldg(bias + d);
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) loc[j] = 0.0f;
+    for (int p = 0; p < Dp; ++p) {
+      const float w = __ldg(W + p * D + d);
+      const int ps = __ldg(par + p);
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) loc[j] = fmaf(c.slot(ps, j), w, loc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) loc[j] += b;  // flat @ W + bias (linear_gaussian.py:180)
+    if (sample) {
+      float eps[RPT];
+      c.draw_normal(op, op.n_off + d, d, eps);
+      const float sc = __ldg(scale + d);
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) c.slot(op.out_slot + d, j) = fmaf(eps[j], sc, loc[j]);
+    }
+    if (want_lp) {
+      const float v = __ldg(var + d), t = __ldg(tls + d);
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) acc[j] += gauss_term(c.slot(op.out_slot + d, j), loc[j], v, t);
+    }
+  }
+  if (want_lp) {
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) acc[j] *= -0.5f;
+    commit_logp(c, op, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// VBN_OP_GNN: gaussian_nn.py:215-288.
+// params: mean_x[Dp], std_x[Dp], mean_y[D], std_y[D], min_scale, pad4 ; then MLP block
+// ---------------------------------------------------------------------------------------
+template <int RPT, int NT>
+__device__ __forceinline__ void op_gnn(Ctx<RPT, NT>& c, const VbnOp& op) {
+  const float* P = c.a.params + op.param_off;
+  const int D = op.dim, Dp = op.n_par;
+  const float* norm = P;
+  const float* mean_y = P + 2 * Dp;
+  const float* std_y = mean_y + D;
+  const float min_scale = __ldg(std_y + D);
+  const float* mlp = P + pad4(2 * Dp + 2 * D + 1);
+  const int32_t* par = c.a.par_slots + op.par_off;
+  mlp_eval<RPT, NT>(c, op, mlp, norm, par);
+  const bool sample = (op.flags & VBN_SRC_MASK) == VBN_SRC_SAMPLE;
+  const bool want_lp = (op.flags & (VBN_F_ADD_LOGW | VBN_F_OUT_LOGP)) != 0;
+  float acc[RPT];
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) acc[j] = 0.0f;
+  for (int d = 0; d < D; ++d) {
+    const float my = __ldg(mean_y + d), sy = __ldg(std_y + d);
+    float loc[RPT], sc[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      loc[j] = fmaf(c.scr(d, j), sy, my);                          // loc*std_y + mean_y
+      sc[j] = (softplus20(c.scr(D + d, j)) + min_scale) * sy;      // (softplus+min)*std_y
+    }
+    if (sample) {
+      float eps[RPT];
+      c.draw_normal(op, op.n_off + d, d, eps);
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) c.slot(op.out_slot + d, j) = fmaf(eps[j], sc[j], loc[j]);
+    }
+    if (want_lp) {
+#pragma unroll
+      for (int j = 0; j < RPT; ++j)
+        acc[j] += gauss_term(c.slot(op.out_slot + d, j), loc[j], sc[j] * sc[j], 2.0f * logf(sc[j]));
+    }
+  }
+  if (want_lp) {
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) acc[j] *= -0.5f;
+    commit_logp(c, op, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// VBN_OP_MDN: mdn.py:185-272.  params: min_scale, pad4 ; MLP block.
+// MLP outputs: logits[K], then per component k: loc[D], raw_scale[D].
+// ---------------------------------------------------------------------------------------
+template <int RPT, int NT>
+__device__ __forceinline__ void op_mdn(Ctx<RPT, NT>& c, const VbnOp& op) {
+  const float* P = c.a.params + op.param_off;
+  const int D = op.dim, K = op.k;
+  const float min_scale = __ldg(P);
+  const int32_t* par = c.a.par_slots + op.par_off;
+  mlp_eval<RPT, NT>(c, op, P + 4, nullptr, par);
+  const bool sample = (op.flags & VBN_SRC_MASK) == VBN_SRC_SAMPLE;
+  const bool want_lp = (op.flags & (VBN_F_ADD_LOGW | VBN_F_OUT_LOGP)) != 0;
+
+  // pi = softmax(logits).clamp_min(1e-5); pi /= pi.sum().clamp_min(1e-12)   (mdn.py:227-228)
+  float mx[RPT], se[RPT], tot[RPT];
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) mx[j] = -CUDART_INF_F;
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) mx[j] = fmaxf(mx[j], c.scr(k, j));
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) se[j] = 0.0f;
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) se[j] += expf(c.scr(k, j) - mx[j]);
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) tot[j] = 0.0f;
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) tot[j] += fmaxf(__fdiv_rn(expf(c.scr(k, j) - mx[j]), se[j]), 1e-5f);
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) tot[j] = fmaxf(tot[j], 1e-12f);
+
+  if (sample) {
+    int pick[RPT];
+    if (!c.injected_index(op, 0, 1, pick)) {
+      float u[RPT];
+      c.draw_uniform(op, op.u_off, 0, u);
+      float cum[RPT];
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) { cum[j] = 0.0f; pick[j] = K - 1; }
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+          const float pk = __fdiv_rn(fmaxf(__fdiv_rn(expf(c.scr(k, j) - mx[j]), se[j]), 1e-5f), tot[j]);
+          const float before = cum[j];
+          cum[j] += pk;
+          if (u[j] >= before && u[j] < cum[j]) pick[j] = k;
+        }
+    }
+    for (int d = 0; d < D; ++d) {
+      float eps[RPT];
+      c.draw_normal(op, op.n_off + d, d, eps);
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        const int kk = min(max(pick[j], 0), K - 1);
+        const float loc = c.scr(K + kk * 2 * D + d, j);
+        const float sc = softplus20(c.scr(K + kk * 2 * D + D + d, j)) + min_scale;
+        c.slot(op.out_slot + d, j) = fmaf(eps[j], sc, loc);
+      }
+    }
+  }
+  if (want_lp) {
+    // t_k = log pi_k + log_comp_k, then logsumexp over k (mdn.py:264-272); t_k overwrites logit k
+    float tmax[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) tmax[j] = -CUDART_INF_F;
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        const float pk = __fdiv_rn(fmaxf(__fdiv_rn(expf(c.scr(k, j) - mx[j]), se[j]), 1e-5f), tot[j]);
+        float q = 0.0f;
+        for (int d = 0; d < D; ++d) {
+          const float loc = c.scr(K + k * 2 * D + d, j);
+          const float ls = logf(softplus20(c.scr(K + k * 2 * D + D + d, j)) + min_scale);
+          const float var = expf(2.0f * ls);  // mdn.py:265
+          q += gauss_term(c.slot(op.out_slot + d, j), loc, var, 2.0f * ls);
+        }
+        const float t = logf(pk) + (-0.5f * q);
+        c.scr(k, j) = t;
+        tmax[j] = fmaxf(tmax[j], t);
+      }
+    }
+    float lp[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) lp[j] = 0.0f;
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) lp[j] += expf(c.scr(k, j) - tmax[j]);
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) lp[j] = (tmax[j] == -CUDART_INF_F) ? -CUDART_INF_F : tmax[j] + logf(lp[j]);
+    commit_logp(c, op, lp);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// VBN_OP_SNN: softmax_nn.py:581-759.
+// params: {min_bin_width, within_bin_scale, temperature, 0}, bin_edges[D][C+1],
+//         class_values[D][C], sample_values[D][C], is_discrete[D], pad4 ; MLP block
+// MLP outputs: logits[D][C]
+// ---------------------------------------------------------------------------------------
+template <int RPT, int NT>
+__device__ __forceinline__ void op_snn(Ctx<RPT, NT>& c, const VbnOp& op) {
+  const float* P = c.a.params + op.param_off;
+  const int D = op.dim, C = op.k;
+  const float min_bw = __ldg(P), wb_scale = __ldg(P + 1), temperature = __ldg(P + 2);
+  const float* edges = P + 4;
+  const float* class_values = edges + D * (C + 1);
+  const float* sample_values = class_values + D * C;
+  const float* is_disc = sample_values + D * C;
+  const float* mlp = P + pad4(4 + D * (C + 1) + 2 * D * C + D);
+  const int32_t* par = c.a.par_slots + op.par_off;
+  const int within = op.aux[0];
+  const bool clip = op.aux[1] != 0;
+  mlp_eval<RPT, NT>(c, op, mlp, nullptr, par);
+  if (op.n_layers > 0 && temperature != 1.0f) {
+    for (int o = 0; o < D * C; ++o)
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) c.scr(o, j) = __fdiv_rn(c.scr(o, j), temperature);
+  }
+  const bool sample = (op.flags & VBN_SRC_MASK) == VBN_SRC_SAMPLE;
+  const bool want_lp = (op.flags & (VBN_F_ADD_LOGW | VBN_F_OUT_LOGP)) != 0;
+  float lp[RPT];
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) lp[j] = 0.0f;
+
+  for (int d = 0; d < D; ++d) {
+    const bool disc = __ldg(is_disc + d) != 0.0f;
+    const float* e = edges + d * (C + 1);
+    float mx[RPT], se[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) mx[j] = -CUDART_INF_F;
+    for (int k = 0; k < C; ++k)
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) mx[j] = fmaxf(mx[j], c.scr(d * C + k, j));
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) se[j] = 0.0f;
+    for (int k = 0; k < C; ++k)
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) se[j] += expf(c.scr(d * C + k, j) - mx[j]);
+
+    if (sample) {
+      int pick[RPT];
+      if (!c.injected_index(op, d, D, pick)) {  // Categorical(logits).sample() (softmax_nn.py:651)
+        float u[RPT], cum[RPT];
+        c.draw_uniform(op, op.u_off + d, d, u);
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) { cum[j] = 0.0f; pick[j] = C - 1; u[j] *= se[j]; }
+        for (int k = 0; k < C; ++k)
+#pragma unroll
+          for (int j = 0; j < RPT; ++j) {
+            const float before = cum[j];
+            cum[j] += expf(c.scr(d * C + k, j) - mx[j]);
+            if (u[j] >= before && u[j] < cum[j]) pick[j] = k;
+          }
+      }
+      float val[RPT];
+      if (disc) {
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) val[j] = __ldg(sample_values + d * C + min(max(pick[j], 0), C - 1));
+      }
+      // the reference draws the within-bin variate for every dim, discrete or not
+      // (softmax_nn.py:664-679); the stream index is consumed either way.
+      float w[RPT];
+      if (within == VBN_WB_GAUSSIAN) {
+        c.draw_normal(op, op.n_off + d, d, w);
+      } else {
+        // injected u for within-bin shares the [Bn,S,D] layout of noise.u
+        c.draw_uniform(op, op.u_off + D + d, d, w);
+      }
+      if (!disc) {
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+          const int kk = min(max(pick[j], 0), C - 1);
+          const float left = __ldg(e + kk), right = __ldg(e + min(kk + 1, C));
+          const float width = fmaxf(right - left, min_bw);
+          float v;
+          if (within == VBN_WB_UNIFORM) {
+            v = fmaf(w[j], width, left);
+          } else if (within == VBN_WB_TRIANGULAR) {
+            const float lv = fmaf(width, sqrtf(fmaxf(w[j] * 0.5f, 0.0f)), left);
+            const float rv = right - width * sqrtf(fmaxf((1.0f - w[j]) * 0.5f, 0.0f));
+            v = w[j] < 0.5f ? lv : rv;
+          } else {
+            const float center = 0.5f * (left + right);
+            v = fmaf(w[j], fmaxf(wb_scale * width, min_bw), center);
+          }
+          if (clip) v = fminf(fmaxf(v, left), right);
+          val[j] = v;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) c.slot(op.out_slot + d, j) = val[j];
+    }
+
+    if (want_lp) {
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        const float x = c.slot(op.out_slot + d, j);
+        int bin;
+        if (disc) {  // exact class match (softmax_nn.py:618-627)
+          bin = -1;
+          for (int k = C - 1; k >= 0; --k)
+            if (x == __ldg(class_values + d * C + k)) bin = k;
+          if (bin < 0) {
+            if (c.rows.valid[j] && c.a.error_flag) atomicOr(c.a.error_flag, 1);
+            bin = 0;
+          }
+        } else {     // (x >= edges).sum() - 1, clamped (softmax_nn.py:615-616)
+          int cnt = 0;
+          for (int k = 0; k <= C; ++k) cnt += (x >= __ldg(e + k)) ? 1 : 0;
+          bin = min(max(cnt - 1, 0), C - 1);
+        }
+        const float log_bin = (c.scr(d * C + bin, j) - mx[j]) - logf(se[j]);  // log_softmax
+        float log_within = 0.0f;
+        if (!disc) {
+          const float left = __ldg(e + bin), right = __ldg(e + min(bin + 1, C));
+          const float width = fmaxf(right - left, min_bw);
+          const float center = 0.5f * (left + right);
+          const float xu = clip ? fminf(fmaxf(x, left), right) : x;
+          const bool inside = (x >= left) && (x <= right);
+          if (within == VBN_WB_UNIFORM) {
+            log_within = -logf(width);
+            if (!clip && !inside) log_within = -CUDART_INF_F;
+          } else if (within == VBN_WB_TRIANGULAR) {
+            const float dl = fmaxf(width * (center - left), min_bw * min_bw);
+            const float dr = fmaxf(width * (right - center), min_bw * min_bw);
+            const float lpdf = __fdiv_rn(2.0f * (xu - left), dl);
+            const float rpdf = __fdiv_rn(2.0f * (right - xu), dr);
+            const float pdf = fmaxf(xu <= center ? lpdf : rpdf, 0.0f);
+            log_within = logf(fmaxf(pdf, 1e-12f));
+            if (!clip && !inside) log_within = -CUDART_INF_F;
+          } else {
+            const float sigma = fmaxf(wb_scale * width, min_bw);
+            const float dd = xu - center;
+            log_within = -__fdiv_rn(dd * dd, 2.0f * sigma * sigma) - logf(sigma) - kHalfLog2Pi;
+          }
+        }
+        lp[j] += log_bin + log_within;
+      }
+    }
+  }
+  if (want_lp) commit_logp(c, op, lp);
+}
+
+// ---------------------------------------------------------------------------------------
+// VBN_OP_KDE: kde.py:105-182.
+// params: {hy, hp, const_y, noise_scale, log_n, 0,0,0}, parents[N][Dp] (pad4), targets[N][D]
+//   hy = 0.5/s_y^2, hp = 0.5/s_p^2  ->  log_k = -h*diff^2 + const
+// ---------------------------------------------------------------------------------------
+template <int RPT, int NT>
+__device__ __noinline__ void op_kde(Ctx<RPT, NT>& c, const VbnOp& op) {
+  const float* P = c.a.params + op.param_off;
+  const int D = op.dim, Dp = op.n_par, N = op.k;
+  const float hy = __ldg(P), hp = __ldg(P + 1), const_y = __ldg(P + 2), noise_scale = __ldg(P + 3);
+  const float log_n = __ldg(P + 4);
+  const float* tp = P + 8;
+  const float* ty = tp + pad4(N * Dp);
+  const int32_t* par = c.a.par_slots + op.par_off;
+  const bool sample = (op.flags & VBN_SRC_MASK) == VBN_SRC_SAMPLE;
+  const bool want_lp = (op.flags & (VBN_F_ADD_LOGW | VBN_F_OUT_LOGP)) != 0;
+
+  if (sample) {
+    int pick[RPT];
+    if (!c.injected_index(op, 0, 1, pick)) {
+      float u[RPT];
+      c.draw_uniform(op, op.u_off, 0, u);
+      if (Dp == 0) {  // torch.randint(0, N) (kde.py:170)
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) pick[j] = min(static_cast<int>(u[j] * N), N - 1);
+      } else {        // multinomial(softmax(log_kp)) (kde.py:172-178): two passes, inverse CDF
+        Lse acc[RPT];
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) acc[j].init();
+        for (int n = 0; n < N; ++n)
+#pragma unroll
+          for (int j = 0; j < RPT; ++j) {
+            float q = 0.0f;
+            for (int p = 0; p < Dp; ++p) {
+              const float df = c.slot(__ldg(par + p), j) - __ldg(tp + n * Dp + p);
+              q = fmaf(df, df, q);
+            }
+            acc[j].push(-hp * q);
+          }
+        float cum[RPT];
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) { cum[j] = 0.0f; pick[j] = N - 1; u[j] *= acc[j].l; }
+        for (int n = 0; n < N; ++n)
+#pragma unroll
+          for (int j = 0; j < RPT; ++j) {
+            float q = 0.0f;
+            for (int p = 0; p < Dp; ++p) {
+              const float df = c.slot(__ldg(par + p), j) - __ldg(tp + n * Dp + p);
+              q = fmaf(df, df, q);
+            }
+            const float before = cum[j];
+            cum[j] += __expf(-hp * q - acc[j].m);
+            if (u[j] >= before && u[j] < cum[j]) pick[j] = n;
+          }
+      }
+    }
+    for (int d = 0; d < D; ++d) {
+      float eps[RPT];
+      c.draw_normal(op, op.n_off + d, d, eps);
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        const int nn = min(max(pick[j], 0), N - 1);
+        c.slot(op.out_slot + d, j) = fmaf(eps[j], noise_scale, __ldg(ty + nn * D + d));
+      }
+    }
+  }
+  if (want_lp) {
+    Lse num[RPT], den[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) { num[j].init(); den[j].init(); }
+    for (int n = 0; n < N; ++n)
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        float qp = 0.0f, qy = 0.0f;
+        for (int p = 0; p < Dp; ++p) {
+          const float df = c.slot(__ldg(par + p), j) - __ldg(tp + n * Dp + p);
+          qp = fmaf(df, df, qp);
+        }
+        for (int d = 0; d < D; ++d) {
+          const float df = c.slot(op.out_slot + d, j) - __ldg(ty + n * D + d);
+          qy = fmaf(df, df, qy);
+        }
+        const float a = -hp * qp;
+        den[j].push(a);
+        num[j].push(fmaf(-hy, qy, a));
+      }
+    float lp[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j)
+      lp[j] = (Dp == 0) ? (num[j].value() + const_y - log_n) : (num[j].value() - den[j].value() + const_y);
+    commit_logp(c, op, lp);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------
+template <int RPT, int NT, bool HEAVY, int MIN_BLOCKS>
+__global__ void __launch_bounds__(NT, MIN_BLOCKS) schedule_kernel(const ScheduleArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int ROWS = RPT * NT;
+  Ctx<RPT, NT> c(a, smem, threadIdx.x);
+  const int64_t n_tiles = (a.n_rows + ROWS - 1) / ROWS;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t base = tile * ROWS;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int64_t r = base + j * NT + threadIdx.x;
+      c.rows.valid[j] = r < a.n_rows;
+      const int64_t rc = c.rows.valid[j] ? r : a.n_rows - 1;
+      c.rows.r[j] = rc;
+      const int64_t b = rc / a.n_samples;
+      c.rows.lb[j] = b;
+      c.rows.ls[j] = rc - b * a.n_samples;
+      c.rows.gb[j] = a.query_offset + static_cast<uint32_t>(b);
+      c.rows.gs[j] = a.sample_offset + static_cast<uint32_t>(c.rows.ls[j]);
+      c.rows.logw[j] = 0.0f;
+      c.rows.logp[j] = 0.0f;
+    }
+    c.rows.cur_nq = -1;
+    c.rows.cur_uq = -1;
+
+    for (int i = 0; i < a.n_ops; ++i) {
+      VbnOp op;
+      {
+        const int4* src = reinterpret_cast<const int4*>(a.ops + i);
+        int4* dst = reinterpret_cast<int4*>(&op);
+#pragma unroll
+        for (int q = 0; q < static_cast<int>(sizeof(VbnOp) / sizeof(int4)); ++q) dst[q] = __ldg(src + q);
+      }
+      load_fixed(c, op);
+      switch (op.kind) {
+        case VBN_OP_LG: op_lg(c, op); break;
+        case VBN_OP_GNN: if (HEAVY) op_gnn(c, op); break;
+        case VBN_OP_MDN: if (HEAVY) op_mdn(c, op); break;
+        case VBN_OP_SNN: if (HEAVY) op_snn(c, op); break;
+        case VBN_OP_KDE: if (HEAVY) op_kde(c, op); break;
+        default: break;
+      }
+      store_value(c, op);
+    }
+    if (a.logw) {
+#pragma unroll
+      for (int j = 0; j < RPT; ++j)
+        if (c.rows.valid[j]) a.logw[c.rows.r[j]] = c.rows.logw[j];
+    }
+    if (a.logp) {
+#pragma unroll
+      for (int j = 0; j < RPT; ++j)
+        if (c.rows.valid[j]) a.logp[c.rows.r[j]] = a.logp_as_pdf ? expf(c.rows.logp[j]) : c.rows.logp[j];
+    }
+  }
+}
+
+}  // namespace vbn

@@ -1,0 +1,85 @@
+"""Multi-GPU sharding of the posterior path: one process per GPU, torch.distributed (NCCL over
+NVLink) only as plumbing.  Rows (query b, sample s) are independent through the whole schedule,
+so the only cross-rank step is the per-query logsumexp merge when SAMPLES are sharded
+(SURVEY.md section 8e); sharding QUERIES needs no data-path collective at all (only the
+batch-global IS->LW fallback flag, 4 bytes).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+
+def block_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Balanced contiguous partition of range(n): returns (count, offset) of ``rank``."""
+    base, extra = divmod(int(n), int(world))
+    count = base + (1 if rank < extra else 0)
+    offset = rank * base + min(rank, extra)
+    return count, offset
+
+
+@dataclass
+class Shard:
+    kind: str            # "queries" | "samples"
+    rank: int
+    world: int
+    group: Optional[object] = None
+
+    def __post_init__(self):
+        if self.kind not in ("queries", "samples"):
+            raise ValueError("Shard.kind must be 'queries' or 'samples'")
+        if not (0 <= self.rank < self.world):
+            raise ValueError("bad rank/world")
+
+    def local_queries(self, b: int) -> Tuple[int, int]:
+        if self.kind != "queries":
+            return int(b), 0
+        cnt, off = block_bounds(b, self.rank, self.world)
+        if cnt == 0:
+            raise ValueError(f"rank {self.rank} got no queries (B={b} < world={self.world}); shard samples instead")
+        return cnt, off
+
+    def local_samples(self, s: int) -> Tuple[int, int]:
+        if self.kind != "samples":
+            return int(s), 0
+        cnt, off = block_bounds(s, self.rank, self.world)
+        if cnt == 0:
+            raise ValueError(f"rank {self.rank} got no samples (S={s} < world={self.world})")
+        return cnt, off
+
+    def slice_queries(self, v: torch.Tensor) -> torch.Tensor:
+        if self.kind != "queries":
+            return v
+        cnt, off = block_bounds(v.shape[0], self.rank, self.world)
+        return v[off : off + cnt]
+
+    def any_flag(self, flag: torch.Tensor) -> torch.Tensor:
+        """Logical OR of a per-rank int flag over all ranks."""
+        if self.world == 1:
+            return flag
+        import torch.distributed as dist
+
+        out = flag.clone()
+        dist.all_reduce(out, op=dist.ReduceOp.MAX, group=self.group)
+        return out
+
+
+def gather_stats(stats: torch.Tensor, shard: Shard) -> torch.Tensor:
+    """All-gather per-rank (m, l, q) triples: [B,3] -> [B, world, 3].  Payload is B*12 bytes per
+    rank -- latency bound on NVLink; the merge itself is the CUDA kernel vbn_lse_merge."""
+    if shard.world == 1:
+        return stats.unsqueeze(1)
+    import torch.distributed as dist
+
+    parts = [torch.empty_like(stats) for _ in range(shard.world)]
+    dist.all_gather(parts, stats.contiguous(), group=shard.group)
+    return torch.stack(parts, dim=1).contiguous()
+
+
+def auto_shard(n_queries: int, rank: int, world: int, group=None) -> Optional[Shard]:
+    """Queries when there are enough of them (no collective), else samples."""
+    if world <= 1:
+        return None
+    return Shard("queries" if n_queries >= world else "samples", rank, world, group)

@@ -1,0 +1,272 @@
+"""CUDA drop-ins for the reference's sampling-based inference methods, registered under the same
+keys (vbn/inference/{likelihood_weighting,importance_sampling,monte_carlo_marginalization}.py)
+and the ancestral sampler (vbn/sampling/ancestral.py).  Constructors, ``infer_posterior`` /
+``sample`` signatures, return shapes and the attributes tests read (``n_samples``,
+``ess_threshold``, ``_last_ess``, ``_last_fallback``, ``_cache``) follow the reference.
+
+Extra keyword arguments understood by every method (all optional):
+  noise : {node: {"eps"|"u"|"idx": tensor}} -- inject the draws instead of Philox (parity tests);
+          importance_sampling takes {"is": {...}, "lw": {...}} for its two passes
+  seed  : int Philox key (default: one draw from torch's global CPU generator per pass)
+  shard : dist.Shard -- this rank's slice of the queries or samples (multi-GPU)
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import engine as E
+from .core import (Query, infer_batch_size, model_cpds, register_inference, register_sampling)
+from .dist import Shard, gather_stats
+from .plan import Role, compile_schedule
+
+
+def _check_model(vbn) -> torch.device:
+    dev = E.require_cuda(getattr(vbn, "device", None))
+    return dev
+
+
+def _topology(vbn):
+    topo = list(vbn.dag.topological_order())
+    parents = {n: list(vbn.dag.parents(n)) for n in topo}
+    return topo, parents
+
+
+def clamp_evidence(x: torch.Tensor) -> torch.Tensor:
+    """vbn/inference/_core.py:112-114."""
+    x = torch.nan_to_num(x, nan=0.0, posinf=1e6, neginf=-1e6)
+    return x.clamp(min=-1e6, max=1e6)
+
+
+class _ScheduleRunner:
+    """Shared by all methods: builds (and caches) the schedule for a query signature and runs it."""
+
+    def __init__(self) -> None:
+        self._cache: Dict[tuple, E.DevicePlan] = {}
+
+    def plan_for(self, vbn, query: Query, mode: str, *, inject=frozenset(), store_all=False,
+                 only=None) -> E.DevicePlan:
+        cpds = model_cpds(vbn)
+        fp = tuple((c._uid, c._version) for c in cpds.values())
+        key = (fp, mode, query.target, tuple(sorted(query.evidence)), tuple(sorted(query.do)),
+               tuple(sorted(inject)), bool(store_all), None if only is None else tuple(only), str(vbn.device))
+        plan = self._cache.get(key)
+        if plan is not None:
+            return plan
+        topo, parents = _topology(vbn)
+        roles: Dict[str, Role] = {}
+        for n in topo:
+            if only is not None and n not in only:
+                continue
+            if n in query.do:
+                r = Role(src="fixed_q", density=False)
+            elif n in query.evidence:
+                if mode in ("lw", "is"):
+                    r = Role(src="fixed_q", add_logw=True)
+                else:
+                    r = Role(src="fixed_q", density=False)
+            else:
+                shared = mode != "is" and len(parents[n]) == 0 and mode != "mcm_fast"
+                r = Role(src="sample", shared=shared, inject=n in inject)
+            if n == query.target or store_all:
+                r.store = True
+            roles[n] = r
+        if mode in ("mcm", "mcm_fast"):
+            t = roles[query.target]
+            t.out_logp = True
+            t.density = True
+        prog = compile_schedule(topo, parents, cpds, roles)
+        plan = E.DevicePlan(prog, vbn.device)
+        if len(self._cache) > 64:
+            self._cache.clear()
+        self._cache[key] = plan
+        return plan
+
+    @staticmethod
+    def fixed_table(plan: E.DevicePlan, query: Query, b: int, *, clamp_obs: bool, shard: Optional[Shard]):
+        prog = plan.program
+        if not prog.n_fixed_cols:
+            return None
+        cols = []
+        for n in prog.fixed_cols:  # insertion order == op order
+            v = query.do[n] if n in query.do else query.evidence[n]
+            v = v.to(device=plan.device, dtype=torch.float32)
+            if clamp_obs and n in query.evidence:
+                v = clamp_evidence(v)
+            if shard is not None:
+                v = shard.slice_queries(v)
+            if v.shape[0] != b:
+                raise ValueError("Evidence and do batch sizes must match.")
+            cols.append(v.t())
+        return torch.cat(cols, dim=0).contiguous()
+
+    def forward(self, vbn, query: Query, n_samples: int, mode: str, *, noise=None, seed=None,
+                shard: Optional[Shard] = None, clamp_obs: bool = False, store_all: bool = False,
+                only=None, n_queries: Optional[int] = None):
+        """Runs one pass.  Returns dict(logw, logp, stores={node: [B,S,D]}, plan, b, s)."""
+        dev = _check_model(vbn)
+        noise = noise or {}
+        plan = self.plan_for(vbn, query, mode, inject=frozenset(noise), store_all=store_all, only=only)
+        prog = plan.program
+        b_full = infer_batch_size(query.evidence, query.do) if n_queries is None else n_queries
+        b, s, q_off, s_off = b_full, int(n_samples), 0, 0
+        if shard is not None:
+            b, q_off = shard.local_queries(b_full)
+            s, s_off = shard.local_samples(s)
+        with torch.cuda.device(dev):
+            fixed = self.fixed_table(plan, query, b, clamp_obs=clamp_obs, shard=shard)
+            stores = {n: torch.empty(b, s, prog.dims[n], device=dev, dtype=torch.float32) for n in prog.stores}
+            logw = torch.empty(b, s, device=dev, dtype=torch.float32) if prog.needs_logw else None
+            logp = torch.empty(b, s, device=dev, dtype=torch.float32) if prog.needs_logp else None
+            flag = torch.zeros(1, device=dev, dtype=torch.int32)
+            plan.run(b, s, fixed=fixed, stores=[stores[n] for n in prog.stores],
+                     noise=[noise[n] for n in prog.noise], logw=logw, logp=logp,
+                     logp_as_pdf=mode in ("mcm", "mcm_fast"),
+                     seed=E.draw_seed() if seed is None else seed,
+                     query_offset=q_off, sample_offset=s_off, error_flag=flag)
+        return {"logw": logw, "logp": logp, "stores": stores, "plan": plan, "b": b, "s": s, "flag": flag}
+
+
+def _raise_if_flagged(vbn, out) -> None:
+    cpds = model_cpds(vbn)
+    if any(c.kind == "softmax_nn" and bool(c._is_discrete.any()) for c in cpds.values()):
+        if int(out["flag"].item()) != 0:
+            raise ValueError("Found values outside discrete class set.")  # softmax_nn.py:623-625
+
+
+def _weights(out, *, normalize=True, eps=1e-12, shard: Optional[Shard] = None):
+    """softmax over samples (+ESS) from a pass's log-weights; merges across ranks when the
+    samples are sharded."""
+    b, s = out["b"], out["s"]
+    logw = out["logw"]
+    if logw is None:  # no evidence with a density: uniform weights, like softmax of zeros
+        dev = next(iter(out["stores"].values())).device
+        logw = torch.zeros(b, s, device=dev, dtype=torch.float32)
+    stats = E.lse_stats(logw)
+    if shard is not None and shard.kind == "samples" and shard.world > 1:
+        stats = E.merge_stats(gather_stats(stats, shard))
+    w, ess = E.normalize_weights(logw, stats, normalize=normalize, eps=eps)
+    return w, ess, stats
+
+
+@register_inference("likelihood_weighting")
+class LikelihoodWeighting:
+    """vbn/inference/likelihood_weighting.py:11-82."""
+
+    def __init__(self, n_samples: int = 512, eps: float = 1e-12, normalize: bool = True, **kwargs) -> None:
+        self.n_samples = int(n_samples)
+        self.eps = float(eps)
+        self.normalize = bool(normalize)
+        self._runner = _ScheduleRunner()
+        self._cache = self._runner._cache
+
+    def infer_posterior(self, vbn, query: Query, **kwargs):
+        n_samples = int(kwargs.get("n_samples", self.n_samples))
+        normalize = bool(kwargs.get("normalize", self.normalize))
+        eps = float(kwargs.get("eps", self.eps))
+        shard = kwargs.get("shard")
+        out = self._runner.forward(vbn, query, n_samples, "lw", noise=kwargs.get("noise"),
+                                   seed=kwargs.get("seed"), shard=shard, clamp_obs=True)
+        _raise_if_flagged(vbn, out)
+        w, _, _ = _weights(out, normalize=normalize, eps=eps, shard=shard)
+        return w, out["stores"][query.target]
+
+
+@register_inference("importance_sampling")
+class ImportanceSampling:
+    """vbn/inference/importance_sampling.py:14-93: per-query independent root draws, ESS test,
+    whole-batch fallback to likelihood weighting."""
+
+    def __init__(self, n_samples: int = 200, **kwargs) -> None:
+        self.n_samples = int(n_samples)
+        self.ess_threshold = 0.1
+        self._runner = _ScheduleRunner()
+        self._cache = self._runner._cache
+        self._lw = LikelihoodWeighting(n_samples=self.n_samples)
+        self._last_fallback = False
+        self._last_ess: Optional[torch.Tensor] = None
+
+    def infer_posterior(self, vbn, query: Query, **kwargs):
+        n_samples = int(kwargs.get("n_samples", self.n_samples))
+        shard = kwargs.get("shard")
+        noise = kwargs.get("noise") or {}
+        seed = kwargs.get("seed")
+        out = self._runner.forward(vbn, query, n_samples, "is", noise=noise.get("is"), seed=seed, shard=shard)
+        _raise_if_flagged(vbn, out)
+        w, ess, stats = _weights(out, shard=shard)
+        self._last_ess = ess
+        threshold = max(1.0, self.ess_threshold * float(n_samples))
+        flag = E.ess_below(stats, threshold)
+        if shard is not None and shard.kind == "queries" and shard.world > 1:
+            flag = shard.any_flag(flag)  # the fallback is batch-global (importance_sampling.py:85-88)
+        if int(flag.item()) != 0:
+            self._last_fallback = True
+            lw_kwargs = {"n_samples": n_samples, "shard": shard, "noise": noise.get("lw")}
+            if seed is not None:
+                lw_kwargs["seed"] = seed + 1
+            return self._lw.infer_posterior(vbn, query, **lw_kwargs)
+        self._last_fallback = False
+        return w, out["stores"][query.target]
+
+
+@register_inference("monte_carlo_marginalization")
+class MonteCarloMarginalization:
+    """vbn/inference/monte_carlo_marginalization.py:12-92 (three paths)."""
+
+    def __init__(self, n_samples: int = 200, **kwargs) -> None:
+        self.n_samples = int(n_samples)
+        self._runner = _ScheduleRunner()
+        self._cache = self._runner._cache
+
+    def infer_posterior(self, vbn, query: Query, **kwargs):
+        n_samples = int(kwargs.get("n_samples", self.n_samples))
+        shard = kwargs.get("shard")
+        dev = _check_model(vbn)
+        b = infer_batch_size(query.evidence, query.do)
+        target = query.target
+        fixed = set(query.evidence) | set(query.do)
+        tparents = list(vbn.dag.parents(target))
+
+        if target in query.do:  # :33-37
+            v = query.do[target].to(device=dev, dtype=torch.float32)
+            if shard is not None:
+                v = shard.slice_queries(v)
+            return (torch.ones(v.shape[0], n_samples, device=dev, dtype=torch.float32),
+                    v.unsqueeze(1).expand(v.shape[0], n_samples, -1))
+
+        if all(p in fixed for p in tparents):  # :39-58 -- only the target CPD is evaluated
+            only = tparents + [target]
+            # a parentless, unobserved target is drawn with parents=None -> batch of 1 (:49-56)
+            nq = 1 if (not tparents and target not in fixed) else b
+            sub = Query(target=target,
+                        evidence={k: v for k, v in query.evidence.items() if k in only},
+                        do={k: v for k, v in query.do.items() if k in only})
+            run_shard = shard if nq == b else None
+            out = self._runner.forward(vbn, sub, n_samples, "mcm_fast", noise=kwargs.get("noise"),
+                                       seed=kwargs.get("seed"), shard=run_shard, only=only, n_queries=nq)
+            _raise_if_flagged(vbn, out)
+            return out["logp"], out["stores"][target]
+
+        out = self._runner.forward(vbn, query, n_samples, "mcm", noise=kwargs.get("noise"),
+                                   seed=kwargs.get("seed"), shard=shard)  # :60-92
+        _raise_if_flagged(vbn, out)
+        return out["logp"], out["stores"][target]
+
+
+@register_sampling("ancestral")
+class AncestralSampler:
+    """vbn/sampling/ancestral.py:57-65."""
+
+    def __init__(self, n_samples: int = 200, **kwargs) -> None:
+        self.n_samples = int(n_samples)
+        self._runner = _ScheduleRunner()
+
+    def sample(self, vbn, query: Query, n_samples: Optional[int] = None, **kwargs):
+        n_samples = int(n_samples or self.n_samples)
+        joint = not query.target
+        q = query if not joint else Query(target=vbn.dag.topological_order()[0],
+                                          evidence=query.evidence, do=query.do)
+        out = self._runner.forward(vbn, q, n_samples, "anc", noise=kwargs.get("noise"),
+                                   seed=kwargs.get("seed"), shard=kwargs.get("shard"), store_all=joint)
+        return out["stores"] if joint else out["stores"][query.target]

@@ -1,0 +1,33 @@
+"""Drop-in installation into a live reference ``vbn`` package: replaces the registry entries of the
+hot-path methods (vbn/core/registry.py:7-11) with the CUDA classes, so
+``vbn.VBN(...).set_inference_method("importance_sampling")`` transparently runs on the B200 path.
+The registry decorator refuses duplicate keys (registry.py:18-20), hence plain dict assignment."""
+from __future__ import annotations
+
+from .inference import (AncestralSampler, ImportanceSampling, LikelihoodWeighting,
+                        MonteCarloMarginalization)
+
+_ORIGINAL = {}
+
+
+def install(vbn_module=None) -> None:
+    if vbn_module is None:
+        import vbn as vbn_module  # the reference package must be importable
+    reg = vbn_module.core.registry
+    for key, cls in (("likelihood_weighting", LikelihoodWeighting),
+                     ("importance_sampling", ImportanceSampling),
+                     ("monte_carlo_marginalization", MonteCarloMarginalization)):
+        _ORIGINAL.setdefault(("inference", key), reg.INFERENCE_REGISTRY.get(key))
+        reg.INFERENCE_REGISTRY[key] = cls
+    _ORIGINAL.setdefault(("sampling", "ancestral"), reg.SAMPLING_REGISTRY.get("ancestral"))
+    reg.SAMPLING_REGISTRY["ancestral"] = AncestralSampler
+
+
+def uninstall(vbn_module=None) -> None:
+    if vbn_module is None:
+        import vbn as vbn_module
+    reg = vbn_module.core.registry
+    for (cat, key), cls in _ORIGINAL.items():
+        if cls is not None:
+            (reg.INFERENCE_REGISTRY if cat == "inference" else reg.SAMPLING_REGISTRY)[key] = cls
+    _ORIGINAL.clear()

@@ -1,0 +1,212 @@
+"""Plan compiler: (DAG, CPDs, query roles) -> flat schedule for the CUDA kernel.
+
+Replaces the reference's per-call bookkeeping -- InferenceState / get_inference_state /
+prepare_fixed_values (vbn/inference/_core.py:13-135) -- and decides, per node, what the fused
+kernel does with it: draw it, clamp it to a per-query value, score it into the log-weight, or
+evaluate its density.  Node values live in shared-memory *slots*; a liveness pass reuses a slot as
+soon as the last reader of a node has run, so the on-chip footprint is the widest live set of the
+DAG, not the node count (a 1000-node DAG with parents drawn from the previous 20 nodes needs ~25).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+from .cpds import BaseCPD, Packed
+
+
+@dataclass
+class Role:
+    """What the schedule does with one node."""
+
+    src: str = "sample"      # "sample" | "fixed_q" (per-query value) | "fixed_row" (per-row input)
+    add_logw: bool = False   # evidence: logw += log p(value | parents)
+    out_logp: bool = False   # write log p(value | parents) to the logp output
+    shared: bool = False     # one draw shared by all queries (root drawn with parents=None)
+    store: bool = False      # write the value to an output column
+    inject: bool = False     # draws come from caller-supplied noise instead of Philox
+    density: bool = True     # False: the node's CPD is never evaluated (do / plain clamp)
+
+
+@dataclass
+class Program:
+    ops: np.ndarray
+    par_slots: np.ndarray
+    params: np.ndarray
+    n_slots: int
+    n_scratch: int
+    heavy: bool
+    nodes: List[str]                       # emitted nodes, op order
+    fixed_cols: Dict[str, int]             # node -> first row of the fixed[][B] table
+    n_fixed_cols: int
+    inputs: List[str]                      # node order of inputs[]
+    stores: List[str]                      # node order of stores[]
+    noise: List[str]                       # node order of noise[]
+    needs_logw: bool
+    needs_logp: bool
+    dims: Dict[str, int] = field(default_factory=dict)
+
+
+def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpds: Dict[str, BaseCPD],
+                     roles: Dict[str, Role]) -> Program:
+    """``topo``: nodes to emit, in topological order (nodes absent from ``roles`` are skipped)."""
+    order = [n for n in topo if n in roles]
+    index = {n: i for i, n in enumerate(order)}
+    packed: Dict[str, Optional[Packed]] = {}
+    dims: Dict[str, int] = {}
+    for n in order:
+        r = roles[n]
+        evaluates = r.density and (r.src == "sample" or r.add_logw or r.out_logp)
+        packed[n] = cpds[n].pack() if evaluates else None
+        dims[n] = int(cpds[n].output_dim)
+
+    # ---- liveness: last op that reads each node's value -------------------------------------
+    last_use = {n: index[n] for n in order}
+    for n in order:
+        if packed[n] is None:
+            continue
+        for p in parents.get(n, ()):
+            if p not in index:
+                raise ValueError(f"node '{n}' is evaluated but its parent '{p}' is not in the schedule")
+            last_use[p] = max(last_use[p], index[n])
+
+    # ---- slot allocation (first fit, D consecutive slots per node) --------------------------
+    occupied: List[bool] = []
+    slot_of: Dict[str, int] = {}
+    expiring: Dict[int, List[str]] = {}
+    for n, lu in last_use.items():
+        expiring.setdefault(lu, []).append(n)
+
+    def alloc(d: int) -> int:
+        run = 0
+        for i, busy in enumerate(occupied):
+            run = 0 if busy else run + 1
+            if run == d:
+                start = i - d + 1
+                for j in range(start, start + d):
+                    occupied[j] = True
+                return start
+        start = len(occupied) - run  # extend the free tail
+        occupied.extend([True] * (d - run))
+        for j in range(start, start + d):
+            occupied[j] = True
+        return start
+
+    # ---- parameter blob ------------------------------------------------------------------------
+    blob: List[np.ndarray] = []
+    blob_len = 0
+    param_off: Dict[int, int] = {}
+
+    ops = np.zeros(len(order), dtype=L.OP_DTYPE)
+    par_slots: List[int] = []
+    fixed_cols: Dict[str, int] = {}
+    n_fixed = 0
+    inputs: List[str] = []
+    stores: List[str] = []
+    noise: List[str] = []
+    n_off = 0
+    u_off = 0
+    n_scratch = 0
+    heavy = False
+    needs_logw = False
+    needs_logp = False
+
+    for i, n in enumerate(order):
+        r = roles[n]
+        pk = packed[n]
+        d = dims[n]
+        slot_of[n] = alloc(d)
+        op = ops[i]
+        op["dim"] = d
+        op["out_slot"] = slot_of[n]
+        flags = {"sample": L.SRC_SAMPLE, "fixed_q": L.SRC_FIXED_Q, "fixed_row": L.SRC_FIXED_ROW}[r.src]
+        op["fixed_col"] = -1
+        if r.src == "fixed_q":
+            fixed_cols[n] = n_fixed
+            op["fixed_col"] = n_fixed
+            n_fixed += d
+        elif r.src == "fixed_row":
+            op["fixed_col"] = len(inputs)
+            inputs.append(n)
+        op["store_idx"] = -1
+        if r.store:
+            op["store_idx"] = len(stores)
+            stores.append(n)
+        op["noise_idx"] = -1
+        if pk is None:
+            op["kind"] = L.OP_NONE
+            op["flags"] = flags
+        else:
+            plist = list(parents.get(n, ()))
+            pdim = sum(dims[p] for p in plist)
+            if pdim != pk.n_par:
+                raise ValueError(f"node '{n}': CPD expects {pk.n_par} parent dims, DAG provides {pdim}")
+            op["kind"] = pk.kind
+            op["n_par"] = pk.n_par
+            op["par_off"] = len(par_slots)
+            for p in plist:
+                par_slots.extend(range(slot_of[p], slot_of[p] + dims[p]))
+            key = id(pk)
+            if key not in param_off:
+                pad = (-blob_len) % 4
+                if pad:
+                    blob.append(np.zeros(pad, np.float32))
+                    blob_len += pad
+                param_off[key] = blob_len
+                blob.append(pk.params.astype(np.float32, copy=False))
+                blob_len += pk.params.size
+            op["param_off"] = param_off[key]
+            op["n_layers"] = pk.n_layers
+            op["act"] = pk.act
+            op["n_out"] = pk.n_out
+            op["k"] = pk.k
+            ld = list(pk.layer_dim)[: L.MAX_LAYERS]
+            op["layer_dim"][: len(ld)] = ld
+            op["aux"][:] = pk.aux
+            if r.add_logw:
+                flags |= L.F_ADD_LOGW
+                needs_logw = True
+            if r.out_logp:
+                flags |= L.F_OUT_LOGP
+                needs_logp = True
+            if r.src == "sample":
+                if r.shared:
+                    flags |= L.F_SHARED
+                op["n_off"] = n_off
+                op["u_off"] = u_off
+                n_off += pk.n_normals
+                u_off += pk.n_uniforms
+                if r.inject:
+                    op["noise_idx"] = len(noise)
+                    noise.append(n)
+            op["flags"] = flags
+            n_scratch = max(n_scratch, pk.scratch)
+            heavy = heavy or pk.heavy
+        for gone in expiring.get(i, ()):  # release slots whose last reader was this op
+            s = slot_of[gone]
+            for j in range(s, s + dims[gone]):
+                occupied[j] = False
+
+    params = np.concatenate(blob) if blob else np.zeros(4, np.float32)
+    if params.size == 0:
+        params = np.zeros(4, np.float32)
+    return Program(
+        ops=ops,
+        par_slots=np.asarray(par_slots if par_slots else [0], dtype=np.int32),
+        params=params,
+        n_slots=max(len(occupied), 1),
+        n_scratch=int(n_scratch),
+        heavy=bool(heavy),
+        nodes=order,
+        fixed_cols=fixed_cols,
+        n_fixed_cols=n_fixed,
+        inputs=inputs,
+        stores=stores,
+        noise=noise,
+        needs_logw=needs_logw,
+        needs_logp=needs_logp,
+        dims=dims,
+    )
