@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""Benchmark of the posterior-inference hot path (BASELINE.json metric: posterior samples/sec).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg5|cfg2|cfg3] [--impl reference]
+
+A *step* is one ``infer_posterior`` call (importance sampling, with its likelihood-weighting
+fallback when ESS is low -- exactly the reference semantics) over one batch of synthetic queries.
+Default workload = BASELINE config 5 (1000-node random DAG, linear_gaussian + mdn CPDs,
+10 000 queries x 4096 samples sharded over 8 GPUs): every rank owns 1250 queries x 4096 samples,
+so the job at N GPUs is 1250*N queries ("weak" scaling; N=8 is the configuration as stated).
+
+One JSON line is printed by rank 0.  ``value`` = device-timed throughput with the evidence already
+resident in HBM; ``e2e`` = the same metric through the public API with HOST evidence buffers and
+the (weights, samples) result copied back to pinned host memory inside the timed region.
+``--impl reference`` times the CPU restatement of the reference (oracle/, pinned bit-for-bit to
+the reference in tests/test_oracle_pin.py) on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (description, per-rank queries, samples, method)
+    "cfg5": ("cfg5: 1000-node random DAG, even=linear_gaussian odd=mdn(K=3,[32,32]), importance_sampling, "
+             "evidence on last 5 nodes, target n500", 1250, 4096, "importance_sampling"),
+    "cfg2": ("cfg2: 50-node linear_gaussian chain, importance_sampling, evidence x49, target x25",
+             64, 1_000_000, "importance_sampling"),
+    "cfg3": ("cfg3: ALARM (37 nodes) softmax_nn discrete CPDs, likelihood_weighting, 4 evidence nodes, "
+             "target LVFAILURE", 4096, 16384, "likelihood_weighting"),
+}
+
+
+def build_workload(name: str, n_queries_total: int):
+    from vectorizedbayesiannetwork_b200 import synthetic as S
+
+    g = torch.Generator().manual_seed(1)
+    if name == "cfg5":
+        spec = S.random_dag_lg_mdn(1000, seed=0)
+        ev_nodes = spec["nodes"][-5:]
+        evidence = {n: 0.3 * torch.randn(n_queries_total, 1, generator=g) for n in ev_nodes}
+        target = "n500"
+    elif name == "cfg2":
+        spec = S.lg_chain(50)
+        # x49 marginal: mean 4.9, var 1 + 49*0.25; evidence within +-1.5 sigma
+        sd = (1 + 49 * 0.25) ** 0.5
+        evidence = {"x49": 4.9 + sd * (torch.rand(n_queries_total, 1, generator=g) * 3 - 1.5)}
+        target = "x25"
+    elif name == "cfg3":
+        spec = S.alarm_softmax(seed=0)
+        evidence = {}
+        for n in ("HRBP", "BP", "EXPCO2", "PRESS"):
+            card = S.ALARM[n][0]
+            evidence[n] = torch.randint(0, card, (n_queries_total, 1), generator=g).float()
+        target = "LVFAILURE"
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    return spec, target, evidence
+
+
+def algorithmic_work(program) -> dict:
+    """Per-row algorithmic flops (2*MAC of every affine map the schedule evaluates) and the
+    SURVEY 8(d) per-level byte count (what a one-launch-per-level SoA design would move)."""
+    from vectorizedbayesiannetwork_b200 import _lib as L
+
+    flops = 0
+    level_bytes = 8  # final reduction: read logw + write weight
+    for op in program.ops:
+        kind, dim, dp = int(op["kind"]), int(op["dim"]), int(op["n_par"])
+        if kind == L.OP_NONE:
+            continue
+        sampled = (int(op["flags"]) & 3) == L.SRC_SAMPLE
+        if kind == L.OP_LG:
+            flops += 2 * dp * dim
+        elif kind in (L.OP_GNN, L.OP_MDN, L.OP_SNN) and int(op["n_layers"]) > 0:
+            dims = [dp] + [int(x) for x in op["layer_dim"][: int(op["n_layers"])]]
+            flops += sum(2 * a * b for a, b in zip(dims[:-1], dims[1:]))
+        level_bytes += 4 * (dp + dim) if sampled else 4 * dp + 8
+    return {"flops_per_row": flops, "level_bytes_per_row": level_bytes}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measure_fma_peak(dev) -> dict:
+    """Measured FP32 FMA peak (TFLOP/s) of this GPU with our probe kernel: scalar FFMA and FFMA2."""
+    from vectorizedbayesiannetwork_b200 import _lib as L
+
+    lib = L.load()
+    out = {}
+    with torch.cuda.device(dev):
+        scratch = torch.zeros(4, device=dev)
+        blocks = 148 * 8
+        for mode, name in ((0, "ffma"), (1, "ffma2")):
+            iters = 20000
+            lib.vbn_fma_peak(mode, 100, blocks, scratch.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            best = 0.0
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                lib.vbn_fma_peak(mode, iters, blocks, scratch.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+                best = max(best, 2.0 * 16 * iters * 256 * blocks / (ms * 1e-3) / 1e12)
+            out[name] = round(best, 2)
+    return out
+
+
+def run_reference(args, rank: int, world: int) -> None:
+    """CPU arm: the oracle port of the reference on the host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import vbn_oracle as O
+
+    desc, b_rank, s, method = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_q = {"cfg5": 4, "cfg2": 2, "cfg3": 64}[args.workload]
+    sample_s = {"cfg5": 4096, "cfg2": 65536, "cfg3": 4096}[args.workload]
+    spec, target, evidence = build_workload(args.workload, sample_q)
+    q = {"target": target, "evidence": evidence, "do": {}}
+    fn = O.importance_sampling if method == "importance_sampling" else O.likelihood_weighting
+    torch.manual_seed(0)
+    for _ in range(max(args.warmup, 1)):
+        fn(spec, q, sample_s)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn(spec, q, sample_s)
+    dt = time.perf_counter() - t0
+    value = sample_q * sample_s * args.steps / dt
+    sample = f"{sample_q} queries x {sample_s} samples per step (bounded sample of the workload; cost is linear in rows)"
+    line = {
+        "impl": "reference", "metric": "posterior_samples_per_sec", "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1),
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "method": method, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "queries_per_sec": sample_q * args.steps / dt,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--queries-per-gpu", type=int, default=None)
+    ap.add_argument("--samples", type=int, default=None)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+
+    import vectorizedbayesiannetwork_b200 as V
+    from vectorizedbayesiannetwork_b200 import _lib as L
+    from vectorizedbayesiannetwork_b200 import engine as E
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    args.warmup = max(args.warmup, 3)
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L.load()
+
+    desc, b_rank, s, method = WORKLOADS[args.workload]
+    if args.queries_per_gpu:
+        b_rank = args.queries_per_gpu
+    if args.samples:
+        s = args.samples
+    b_total = b_rank * world
+    spec, target, evidence_host = build_workload(args.workload, b_total)
+    shard = V.Shard("queries", rank, world) if world > 1 else None
+    model = V.VBN.from_spec(spec, device=dev)
+    model.set_inference_method(method, n_samples=s)
+    evidence_dev = {k: v.to(dev) for k, v in evidence_host.items()}
+    evidence_pinned = {k: v.pin_memory() for k, v in evidence_host.items()}
+    q_dev = {"target": target, "evidence": evidence_dev}
+    kw = {"shard": shard} if shard is not None else {}
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- warm-up (also compiles / uploads the schedule) ------------------------------------
+    for _ in range(args.warmup):
+        model.infer_posterior(q_dev, **kw)
+    torch.cuda.synchronize()
+
+    # ---- device-resident timed region ------------------------------------------------------
+    E.KERNEL_EVENTS = []
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = L.launch_count()
+    barrier()
+    step_events = []
+    fallbacks = 0
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        w, smp = model.infer_posterior(q_dev, **kw)
+        e1.record()
+        step_events.append((e0, e1))
+        fallbacks += int(bool(getattr(model._inference, "_last_fallback", False)))
+    barrier()
+    launches = L.launch_count() - launches0
+    clock_info = clocks.stop() if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in step_events]
+    total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_s = float(total_ms.item()) * 1e-3
+    kernel_ms = [a.elapsed_time(b) for a, b in E.KERNEL_EVENTS]
+    E.KERNEL_EVENTS = None
+    value = b_total * s * args.steps / total_s
+
+    # ---- end-to-end: host evidence in, host (weights, samples) out --------------------------
+    out_w = torch.empty(b_rank, s, dtype=torch.float32).pin_memory()
+    out_s = torch.empty(b_rank, s, 1, dtype=torch.float32).pin_memory()
+    h2d = sum(v.numel() * 4 for v in evidence_pinned.values())
+    d2h = out_w.numel() * 4 + out_s.numel() * 4
+
+    def e2e_step():
+        ev = {k: v.to(dev, non_blocking=True) for k, v in evidence_pinned.items()}
+        w_, s_ = model.infer_posterior({"target": target, "evidence": ev}, **kw)
+        out_w.copy_(w_, non_blocking=True)
+        out_s.copy_(s_, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    e2e_events = []
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e2e_step()
+        e1.record()
+        e2e_events.append((e0, e1))
+    barrier()
+    e2e_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in e2e_events)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = b_total * s * args.steps / (float(e2e_ms.item()) * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the fused schedule kernel) -------------------------
+    plan = next(iter(model._inference._runner._cache.values()))
+    work = algorithmic_work(plan.program)
+    rows = b_rank * s
+    k_avg_ms = sum(kernel_ms) / max(len(kernel_ms), 1)
+    peaks = measure_fma_peak(dev)
+    measured = {}
+    try:
+        measured = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = measured.get("hbm_gbs", 6650.0)
+    heavy = plan.program.heavy
+    if heavy:
+        achieved = work["flops_per_row"] * rows / (k_avg_ms * 1e-3) / 1e12
+        peak = max(peaks.values())
+        roofline = {"bound": "fp32_fma", "achieved": round(achieved, 3), "peak": peak, "unit": "TFLOP/s",
+                    "frac": round(achieved / peak, 4), "traffic": None,
+                    "peak_source": "FFMA/FFMA2 probe kernel measured in this run (MEASURED_PEAKS.json has no fp32 "
+                                   "figure; SURVEY 8d: FFMA path -> measured FP32 FMA peak)",
+                    "fma_peaks_tflops": peaks}
+    else:
+        achieved = work["level_bytes_per_row"] * rows / (k_avg_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
+                    "frac": round(achieved / hbm_peak, 4), "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if measured else "fallback 6650",
+                    "note": "algorithmic bytes = SURVEY 8(d) per-level SoA formula; the fused kernel keeps node "
+                            "columns in shared memory, so real DRAM traffic is only the stored columns"}
+    roofline.update({"kernel": "vbn::schedule_kernel", "kernel_ms_avg": round(k_avg_ms, 4),
+                     "kernel_launches_timed": len(kernel_ms), "rows_per_launch": rows,
+                     "flops_per_row": work["flops_per_row"], "level_bytes_per_row": work["level_bytes_per_row"],
+                     "kernel_share_of_step": round(sum(kernel_ms) / sum(step_ms), 4)})
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            proc = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload",
+                                   args.workload, "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
+                                  timeout=900, env={k: v for k, v in os.environ.items()
+                                                    if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+            cpu = json.loads(proc.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception as exc:  # keep the bench line even if the CPU leg fails
+            cpu = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
+
+    line = {
+        "metric": "posterior_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_s / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "method": method, "queries_per_gpu": b_rank, "queries_total": b_total,
+                   "samples_per_query": s, "sharding": "queries" if world > 1 else "none",
+                   "l2": "256 MB buffer rewritten between timed steps (L2 flush)",
+                   "is_fallback_steps": fallbacks, "weights": "random-init (nn.Linear default), seeded"},
+        "queries_per_sec": b_total * args.steps / total_s,
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches, "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

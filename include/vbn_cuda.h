@@ -198,6 +198,11 @@ int32_t vbn_kde_log_prob(const float* train_p_dev, const float* train_y_dev, int
 int32_t vbn_philox_fill(const uint32_t* ctr_dev, int64_t n, uint32_t key0, uint32_t key1,
                         uint32_t* out_dev, void* stream);
 
+/* Bench-only probe of the FP32 FMA pipe (the MLP layers' roofline denominator): n_blocks x 256
+ * threads each run 16*iters FMAs.  mode 0 = scalar FFMA, 1 = packed fma.rn.f32x2.
+ * flops = 2 * 16 * iters * 256 * n_blocks.  scratch_dev: >= 1 float. */
+int32_t vbn_fma_peak(int32_t mode, int32_t iters, int32_t n_blocks, float* scratch_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

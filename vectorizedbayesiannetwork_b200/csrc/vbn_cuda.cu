@@ -243,4 +243,11 @@ int32_t vbn_philox_fill(const uint32_t* ctr_dev, int64_t n, uint32_t key0, uint3
   return VBN_OK;
 }
 
+int32_t vbn_fma_peak(int32_t mode, int32_t iters, int32_t n_blocks, float* scratch_dev, void* stream) {
+  if (!scratch_dev || iters <= 0 || n_blocks <= 0) return fail(VBN_E_INVALID, "bad argument");
+  vbn::fma_peak_kernel<<<n_blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(mode, iters, scratch_dev);
+  CUDA_TRY(cudaGetLastError());
+  return VBN_OK;
+}
+
 }  // extern "C"

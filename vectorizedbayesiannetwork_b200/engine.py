@@ -13,6 +13,9 @@ from .cpds import BaseCPD, KDECPD
 from .plan import Program, Role, compile_schedule
 
 
+KERNEL_EVENTS = None  # set to a list by bench.py to time every schedule-kernel launch
+
+
 def require_cuda(device=None) -> torch.device:
     if not torch.cuda.is_available():
         raise L.VbnCudaError("no CUDA device: vectorizedbayesiannetwork_b200 has no CPU fallback")
@@ -133,7 +136,14 @@ class DevicePlan:
                 logp_as_pdf=1 if logp_as_pdf else 0, reserved=0,
                 error_flag_dev=error_flag.data_ptr() if error_flag is not None else None,
             )
+            events = KERNEL_EVENTS
+            if events is not None:  # bench.py: CUDA events on the launching stream around the kernel
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             L.check(self.lib.vbn_run_forward(self.handle, C.byref(run), _stream_ptr(self.device)))
+            if events is not None:
+                e1.record()
+                events.append((e0, e1))
             L.count_launch(1)
         # `table` / `keep` are stream-ordered torch allocations: safe to drop after the launch
 
