@@ -1,0 +1,141 @@
+"""CPU-only checks of the host side: the C-ABI library exports every symbol the header declares,
+struct layouts match, the plan compiler's liveness/slot allocation, query validation, registry."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import vectorizedbayesiannetwork_b200 as V
+from vectorizedbayesiannetwork_b200 import _lib as L
+from vectorizedbayesiannetwork_b200 import synthetic as S
+from vectorizedbayesiannetwork_b200.plan import Role, compile_schedule
+from oracle.philox import KAT, philox4x32_10
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    header = open(os.path.join(ROOT, "include", "vbn_cuda.h")).read()
+    declared = set(re.findall(r"\b(vbn_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = L.load()  # loads without a GPU
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/vbn_cuda.h but not exported"
+    assert declared == set(L.EXPORTS), (declared ^ set(L.EXPORTS))
+    assert lib.vbn_cuda_abi_version() == L.ABI_VERSION
+
+
+def test_struct_layouts_match_header():
+    assert L.OP_DTYPE.itemsize == 128
+    assert C.sizeof(L.ProgramDesc) == 64
+    assert C.sizeof(L.RunDesc) == 112
+    assert L.RunDesc.logw_dev.offset == 80 and L.RunDesc.error_flag_dev.offset == 104
+
+
+def test_product_refuses_to_run_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(L.VbnCudaError):
+        V.VBN.from_spec(S.lg_chain(3))
+    cpd = V.cpd_from_spec(S.lg_chain(3)["cpds"]["x1"], device="cpu")
+    with pytest.raises(L.VbnCudaError):
+        cpd.sample(torch.zeros(2, 1), 4)
+
+
+def _compile(spec, roles):
+    cpds = {n: V.cpd_from_spec(c, device="cpu") for n, c in spec["cpds"].items()}
+    return compile_schedule(spec["topo"], spec["parents"], cpds, roles)
+
+
+def test_chain_needs_two_slots_regardless_of_length():
+    spec = S.lg_chain(50)
+    roles = {n: Role() for n in spec["topo"]}
+    roles["x25"].store = True
+    prog = _compile(spec, roles)
+    assert len(prog.ops) == 50 and prog.n_slots == 2 and not prog.heavy
+    assert prog.stores == ["x25"] and prog.n_fixed_cols == 0
+
+
+def test_cfg5_live_set_is_small_and_slots_never_alias_live_values():
+    spec = S.random_dag_lg_mdn(300, seed=0)
+    roles = {n: Role() for n in spec["topo"]}
+    for n in spec["topo"][-5:]:
+        roles[n] = Role(src="fixed_q", add_logw=True)
+    prog = _compile(spec, roles)
+    assert prog.heavy and prog.needs_logw and prog.n_fixed_cols == 5
+    assert prog.n_slots <= 40, prog.n_slots
+    # replay the schedule symbolically: every parent slot must still hold that parent's value
+    owner = {}
+    slot_of = {n: int(op["out_slot"]) for n, op in zip(prog.nodes, prog.ops)}
+    for n, op in zip(prog.nodes, prog.ops):
+        if int(op["kind"]) != L.OP_NONE:
+            got = list(prog.par_slots[int(op["par_off"]): int(op["par_off"]) + int(op["n_par"])])
+            want = [slot_of[p] for p in spec["parents"][n]]
+            assert got == want
+            for p in spec["parents"][n]:
+                assert owner[slot_of[p]] == p, f"{n}: parent {p} was overwritten"
+        owner[int(op["out_slot"])] = n
+
+
+def test_param_blocks_are_16_byte_aligned_and_shared():
+    spec = S.random_dag_lg_mdn(40, seed=1)
+    prog = _compile(spec, {n: Role() for n in spec["topo"]})
+    assert all(int(op["param_off"]) % 4 == 0 for op in prog.ops)
+    assert prog.params.dtype == np.float32
+
+
+def test_mlp_packing_layout():
+    g = torch.Generator().manual_seed(0)
+    layers = S.mlp_layers(g, 3, (32, 32), 9)
+    from vectorizedbayesiannetwork_b200.cpds import pack_mlp
+
+    blob, dims = pack_mlp(layers, 3)
+    assert dims == [32, 32, 9]
+    w1, b1 = layers[0]
+    np.testing.assert_array_equal(blob[: 3 * 32].reshape(3, 32), w1.numpy().T)
+    np.testing.assert_array_equal(blob[96:128], b1.numpy())
+    off = 128 + 32 * 32 + 32
+    np.testing.assert_array_equal(blob[off: off + 9 * 32].reshape(9, 32), layers[2][0].numpy())
+    assert blob.size == off + 9 * 32 + 12
+    with pytest.raises(ValueError):
+        pack_mlp(S.mlp_layers(g, 3, (200, 8), 2), 3)  # wider than the generic device path
+
+
+def test_registry_and_resolution_mirror_reference():
+    assert set(V.INFERENCE_REGISTRY) == {"likelihood_weighting", "importance_sampling", "monte_carlo_marginalization"}
+    assert set(V.SAMPLING_REGISTRY) == {"ancestral"}
+    from vectorizedbayesiannetwork_b200.core import register_inference
+
+    with pytest.raises(ValueError):
+        register_inference("importance_sampling")(object)  # duplicate key, registry.py:18-20
+    inf = V.INFERENCE_REGISTRY["importance_sampling"](n_samples=12, unknown_kwarg=1)
+    assert inf.n_samples == 12 and inf.ess_threshold == 0.1 and inf._last_fallback is False
+    lw = V.INFERENCE_REGISTRY["likelihood_weighting"]()
+    assert (lw.n_samples, lw.eps, lw.normalize) == (512, 1e-12, True)
+    assert V.INFERENCE_REGISTRY["monte_carlo_marginalization"]().n_samples == 200
+    assert V.SAMPLING_REGISTRY["ancestral"]().n_samples == 200
+
+
+def test_philox_oracle_known_answers():
+    for ctr, key, want in KAT:
+        got = philox4x32_10(np.array([ctr], dtype=np.uint32), key[0], key[1])[0]
+        assert [int(x) for x in got] == list(want)
+
+
+def test_block_bounds_partition():
+    from vectorizedbayesiannetwork_b200.dist import Shard, block_bounds
+
+    for n, w in ((10, 3), (8, 8), (4096, 7), (5, 2)):
+        parts = [block_bounds(n, r, w) for r in range(w)]
+        assert sum(c for c, _ in parts) == n
+        off = 0
+        for c, o in parts:
+            assert o == off
+            off += c
+    with pytest.raises(ValueError):
+        Shard("queries", 3, 4).local_queries(2)
+    assert Shard("samples", 1, 4).local_queries(2) == (2, 0)
+    assert Shard("samples", 1, 4).local_samples(10) == (3, 3)

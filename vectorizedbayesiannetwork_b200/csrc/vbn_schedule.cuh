@@ -57,6 +57,7 @@ struct Rows {
 template <int RPT, int NT>
 struct Ctx {
   const ScheduleArgs& a;
+  const VbnOp* gop = nullptr;  // the op being executed, in global memory (for dynamic field access)
   float* slots;    // [n_slots][ROWS]
   float* scratch;  // [n_scratch][ROWS]
   int tid;
@@ -151,7 +152,7 @@ struct Ctx {
 // `norm` (gaussian_nn only): mean_x[Dp], std_x[Dp] -> z = (pa - mean_x)/std_x (gaussian_nn.py:105-112)
 // ---------------------------------------------------------------------------------------
 template <int RPT, int NT>
-__device__ __noinline__ void mlp_generic(Ctx<RPT, NT>& c, const VbnOp& op, const float* P,
+__device__ __forceinline__ void mlp_generic(Ctx<RPT, NT>& c, const VbnOp& op, const float* P,
                                          const float* norm, const int32_t* par) {
   float bufA[kMaxGenericWidth], bufB[kMaxGenericWidth];
   for (int j = 0; j < RPT; ++j) {
@@ -165,7 +166,7 @@ __device__ __noinline__ void mlp_generic(Ctx<RPT, NT>& c, const VbnOp& op, const
     int in = op.n_par;
     const float* W = P;
     for (int l = 0; l + 1 < op.n_layers; ++l) {
-      const int out = op.layer_dim[l], outp = pad4(out);
+      const int out = __ldg(&c.gop->layer_dim[l]), outp = pad4(out);
       const float* bias = W + static_cast<size_t>(in) * outp;
       for (int o = 0; o < out; ++o) {
         float acc = __ldg(bias + o);
@@ -710,7 +711,7 @@ __device__ __forceinline__ void op_snn(Ctx<RPT, NT>& c, const VbnOp& op) {
 //   hy = 0.5/s_y^2, hp = 0.5/s_p^2  ->  log_k = -h*diff^2 + const
 // ---------------------------------------------------------------------------------------
 template <int RPT, int NT>
-__device__ __noinline__ void op_kde(Ctx<RPT, NT>& c, const VbnOp& op) {
+__device__ __forceinline__ void op_kde(Ctx<RPT, NT>& c, const VbnOp& op) {
   const float* P = c.a.params + op.param_off;
   const int D = op.dim, Dp = op.n_par, N = op.k;
   const float hy = __ldg(P), hp = __ldg(P + 1), const_y = __ldg(P + 2), noise_scale = __ldg(P + 3);
@@ -834,6 +835,7 @@ __global__ void __launch_bounds__(NT, MIN_BLOCKS) schedule_kernel(const Schedule
 #pragma unroll
         for (int q = 0; q < static_cast<int>(sizeof(VbnOp) / sizeof(int4)); ++q) dst[q] = __ldg(src + q);
       }
+      c.gop = a.ops + i;
       load_fixed(c, op);
       switch (op.kind) {
         case VBN_OP_LG: op_lg(c, op); break;
