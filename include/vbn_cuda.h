@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define VBN_CUDA_ABI_VERSION 1
+#define VBN_CUDA_ABI_VERSION 2
 
 /* error codes */
 #define VBN_OK 0
@@ -92,7 +92,10 @@ typedef struct VbnOp {
   int32_t k;          /* MDN: components K; SNN: classes C; KDE: stored points N           */
   int32_t layer_dim[VBN_MAX_LAYERS]; /* widths after each Linear layer (last == n_out)      */
   int32_t aux[4];     /* SNN: {within_bin, clip, any_discrete, 0}                          */
-  int32_t reserved[4];
+  int32_t tc[4];      /* tensor-core MLP image (hidden dims [32,32], Dp <= 32, O <= 32), written by
+                         the plan compiler: {1 if present, float offset of the image in the
+                         parameter blob (16-byte aligned), K1 = Dp padded to 8, N3 = O padded to 16};
+                         image layout: see csrc/vbn_schedule_tc.cuh and cpds.py pack_mlp_tc        */
 } VbnOp;
 
 /* strided view of caller memory: element (r, d) lives at base[r*row_stride + d*dim_stride] */
@@ -122,7 +125,7 @@ typedef struct VbnProgramDesc {
   int32_t n_slots;    /* value slots a row needs at once (after liveness analysis)         */
   int32_t n_scratch;  /* per-row scratch floats (max MLP output width over the program)    */
   int32_t heavy;      /* 1 if the program contains MLP / KDE ops (picks the launch shape)  */
-  int32_t reserved;
+  int32_t tc;         /* 1: run the tcgen05 kernel (ops carry tensor-core MLP images)      */
 } VbnProgramDesc;
 
 typedef struct VbnPlan VbnPlan;

@@ -1,0 +1,88 @@
+"""The tcgen05 (tensor-core) schedule kernel against the FFMA schedule kernel on identical Philox
+streams: same schedule, same draws, so every output must agree to fp32 parity tolerance (the
+3xTF32 split keeps ~2^-21 per product).  The FFMA kernel itself is pinned to the reference by
+tests/test_parity_golden.py (which also runs through the tensor-core kernel on the GPU, because the
+golden models use the reference's default hidden_dims [32, 32])."""
+import numpy as np
+import pytest
+import torch
+
+import vectorizedbayesiannetwork_b200 as V
+from vectorizedbayesiannetwork_b200 import synthetic as S
+from vectorizedbayesiannetwork_b200.cpds import _core_matrix_image, _split_tf32, pack_mlp_tc
+from vectorizedbayesiannetwork_b200.plan import Role, compile_schedule
+
+
+def test_tf32_split_is_exact_and_representable():
+    rng = np.random.default_rng(0)
+    w = (rng.standard_normal(4096) * np.exp(rng.uniform(-20, 20, 4096))).astype(np.float32)
+    hi, lo = _split_tf32(w)
+    assert np.all((hi.view(np.uint32) & 0x1FFF) == 0) and np.all((lo.view(np.uint32) & 0x1FFF) == 0)
+    # hi is the nearest tf32; the two-term split captures w to ~2^-22
+    assert np.all(np.abs(w - hi) <= np.abs(w) * 2.0**-11 * 1.0001)
+    assert np.all(np.abs(w - (hi.astype(np.float64) + lo)) <= np.abs(w) * 2.0**-21)
+
+
+def test_core_matrix_image_layout():
+    n, k = 16, 8
+    w = np.arange(n * k, dtype=np.float32).reshape(n, k)
+    img = _core_matrix_image(w)
+    for r in range(n):
+        for c in range(k):
+            off = ((r // 8) * (k // 4) + c // 4) * 32 + (r % 8) * 4 + c % 4  # floats
+            assert img[off] == w[r, c]
+
+
+def test_pack_mlp_tc_eligibility_and_size():
+    g = torch.Generator().manual_seed(0)
+    ok = pack_mlp_tc(S.mlp_layers(g, 3, (32, 32), 9), 3)
+    assert ok is not None
+    blob, k1, n3 = ok
+    assert (k1, n3) == (8, 16) and blob.size * 4 == 4 * (2 * 32 * 8 + 2 * 32 * 32 + 2 * 16 * 32 + 64 + 16)
+    assert pack_mlp_tc(S.mlp_layers(g, 3, (16, 16), 9), 3) is None       # other hidden sizes: FFMA path
+    assert pack_mlp_tc(S.mlp_layers(g, 40, (32, 32), 9), 40) is None     # too many parent dims
+    assert pack_mlp_tc(S.mlp_layers(g, 3, (32, 32), 40), 3) is None      # too many outputs
+
+
+def test_plan_marks_tensor_core_ops(monkeypatch):
+    spec = S.random_dag_lg_mdn(12, seed=3)
+    cpds = {n: V.cpd_from_spec(c, device="cpu") for n, c in spec["cpds"].items()}
+    roles = {n: Role() for n in spec["topo"]}
+    prog = compile_schedule(spec["topo"], spec["parents"], cpds, roles, use_tc=True)
+    assert prog.tc
+    for op, n in zip(prog.ops, prog.nodes):
+        want = spec["cpds"][n]["kind"] == "mdn" and spec["cpds"][n]["input_dim"] > 0
+        assert bool(op["tc"][0]) == want
+        if want:
+            assert op["tc"][1] % 4 == 0 and op["tc"][2] == 8 and op["tc"][3] == 16
+    assert not compile_schedule(spec["topo"], spec["parents"], cpds, roles, use_tc=False).tc
+
+
+def _run(spec, q, method, n_samples, seed, device):
+    model = V.VBN.from_spec(spec, device=device)
+    model.set_inference_method(method, n_samples=n_samples)
+    w, s = model.infer_posterior(q, seed=seed)
+    plan = next(iter(model._inference._runner._cache.values()))
+    torch.cuda.synchronize()
+    return w.cpu(), s.cpu(), plan.program.tc
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_queries,n_samples", [(1, 200), (8, 2048), (3, 1000)])
+def test_tensor_core_kernel_matches_ffma_kernel(monkeypatch, n_queries, n_samples):
+    dev = torch.device("cuda", 0)
+    spec = S.random_dag_lg_mdn(60, seed=1)
+    g = torch.Generator().manual_seed(5)
+    q = {"target": "n30", "evidence": {n: 0.3 * torch.randn(n_queries, 1, generator=g) for n in spec["nodes"][-3:]}}
+    monkeypatch.setenv("VBN_TC", "0")
+    w0, s0, tc0 = _run(spec, q, "likelihood_weighting", n_samples, 1234, dev)
+    monkeypatch.setenv("VBN_TC", "1")
+    w1, s1, tc1 = _run(spec, q, "likelihood_weighting", n_samples, 1234, dev)
+    assert not tc0 and tc1
+    assert torch.isfinite(s1).all() and torch.isfinite(w1).all()
+    # a component pick can flip when u sits within rounding of a CDF edge: allow a vanishing fraction
+    bad = ((s1 - s0).abs() > 1e-5 + 1e-5 * s0.abs()).float().mean().item()
+    assert bad < 1e-4, f"fraction of mismatching samples {bad}"
+    torch.testing.assert_close(w1.sum(1), torch.ones(n_queries), rtol=1e-4, atol=1e-4)
+    badw = ((w1 - w0).abs() > 1e-7 + 2e-4 * w0.abs()).float().mean().item()
+    assert badw < 1e-3, f"fraction of mismatching weights {badw}"

@@ -10,7 +10,7 @@ import numpy as np
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libvbn_cuda.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # op kinds / flags (keep in sync with include/vbn_cuda.h)
 OP_NONE, OP_LG, OP_GNN, OP_MDN, OP_SNN, OP_KDE = 0, 1, 2, 3, 4, 5
@@ -27,7 +27,7 @@ OP_DTYPE = np.dtype(
         ("out_slot", "<i4"), ("par_off", "<i4"), ("param_off", "<i4"), ("fixed_col", "<i4"),
         ("store_idx", "<i4"), ("noise_idx", "<i4"), ("n_off", "<i4"), ("u_off", "<i4"),
         ("n_layers", "<i4"), ("act", "<i4"), ("n_out", "<i4"), ("k", "<i4"),
-        ("layer_dim", "<i4", (MAX_LAYERS,)), ("aux", "<i4", (4,)), ("reserved", "<i4", (4,)),
+        ("layer_dim", "<i4", (MAX_LAYERS,)), ("aux", "<i4", (4,)), ("tc", "<i4", (4,)),
     ]
 )
 assert OP_DTYPE.itemsize == 128
@@ -39,7 +39,7 @@ class ProgramDesc(C.Structure):
         ("par_slots_dev", C.c_void_p), ("n_par_slots", C.c_int32),
         ("params_dev", C.c_void_p), ("n_params", C.c_int64),
         ("n_slots", C.c_int32), ("n_scratch", C.c_int32),
-        ("heavy", C.c_int32), ("reserved", C.c_int32),
+        ("heavy", C.c_int32), ("tc", C.c_int32),
     ]
 
 

@@ -58,6 +58,9 @@ class Packed:
     n_uniforms: int = 0  # per-row uniforms consumed by one sample()
     scratch: int = 0     # per-row scratch floats
     heavy: bool = False
+    tc_blob: Optional[np.ndarray] = None  # tensor-core weight image (pack_mlp_tc), if eligible
+    tc_k1: int = 0
+    tc_n3: int = 0
 
 
 def pack_mlp(layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], input_dim: int) -> Tuple[np.ndarray, List[int]]:
@@ -94,8 +97,58 @@ def pack_mlp(layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], input_dim: int
     return np.concatenate(chunks) if chunks else np.zeros(0, np.float32), dims
 
 
+def _split_tf32(w: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """w = hi + lo with hi, lo representable in tf32 (10 explicit mantissa bits), round to nearest."""
+    def rn(x):
+        bits = x.astype(np.float32).view(np.uint32)
+        return ((bits + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+    hi = rn(w)
+    lo = rn(w.astype(np.float32) - hi)
+    return hi, lo
+
+
+def _core_matrix_image(w: np.ndarray) -> np.ndarray:
+    """[N][K] (K-major) -> the no-swizzle UMMA shared-memory image: core matrices of 8 rows x 16 bytes
+    (4 floats), K-adjacent core matrices 128 B apart, 8-row groups K*32 B apart
+    (csrc/vbn_schedule_tc.cuh make_b_desc)."""
+    n, k = w.shape
+    assert n % 8 == 0 and k % 4 == 0
+    return np.ascontiguousarray(w.reshape(n // 8, 8, k // 4, 4).transpose(0, 2, 1, 3)).reshape(-1)
+
+
+def pack_mlp_tc(layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], input_dim: int):
+    """Weight image for the tcgen05 kernel, or None when the MLP is not [Dp<=32 -> 32 -> 32 -> O<=32].
+    Layout (floats): W1hi, W1lo [32][K1]; W2hi, W2lo [32][32]; W3hi, W3lo [N3][32] (all core-matrix
+    images of nn.Linear's [out][in] = [N][K] K-major weight); b1[32], b2[32], b3[N3]."""
+    if len(layers) != 3:
+        return None
+    (w1, b1), (w2, b2), (w3, b3) = [(_f32(w).numpy(), _f32(b).numpy()) for w, b in layers]
+    dp, n_out = int(input_dim), int(w3.shape[0])
+    if w1.shape != (32, dp) or w2.shape != (32, 32) or w3.shape[1] != 32 or not (1 <= dp <= 32) or not (1 <= n_out <= 32):
+        return None
+    k1 = (dp + 7) & ~7
+    n3 = (n_out + 15) & ~15
+    w1p = np.zeros((32, k1), np.float32)
+    w1p[:, :dp] = w1
+    w3p = np.zeros((n3, 32), np.float32)
+    w3p[:n_out] = w3
+    chunks = []
+    for w in (w1p, w2, w3p):
+        hi, lo = _split_tf32(w)
+        chunks += [_core_matrix_image(hi), _core_matrix_image(lo)]
+    chunks += [b1.astype(np.float32), b2.astype(np.float32), _padded(b3, n3)]
+    return np.concatenate(chunks), k1, n3
+
+
 def _layers_from_module(net) -> List[Tuple[torch.Tensor, torch.Tensor]]:
     return [(m.weight, m.bias) for m in net if hasattr(m, "weight") and hasattr(m, "bias")]
+
+
+def _with_tc(pk: Packed, layers, input_dim: int) -> Packed:
+    img = pack_mlp_tc(layers, input_dim)
+    if img is not None:
+        pk.tc_blob, pk.tc_k1, pk.tc_n3 = img
+    return pk
 
 
 class BaseCPD:
@@ -225,9 +278,9 @@ class GaussianNNCPD(BaseCPD):
         if dims[-1] != 2 * d:
             raise ValueError("gaussian_nn net must output 2*output_dim values")
         params = np.concatenate([_padded(head, _pad4(2 * dp + 2 * d + 1)), mlp])
-        return Packed(kind=L.OP_GNN, dim=d, n_par=dp, params=params, n_layers=len(dims),
-                      act=L.ACT[self.activation], n_out=2 * d, layer_dim=dims, n_normals=d,
-                      scratch=2 * d, heavy=True)
+        return _with_tc(Packed(kind=L.OP_GNN, dim=d, n_par=dp, params=params, n_layers=len(dims),
+                               act=L.ACT[self.activation], n_out=2 * d, layer_dim=dims, n_normals=d,
+                               scratch=2 * d, heavy=True), self.layers, dp)
 
     @classmethod
     def from_spec(cls, c, device=None):
@@ -290,9 +343,10 @@ class MDNCPD(BaseCPD):
         mlp, dims = pack_mlp(self.layers, dp)
         if dims[-1] != n_out:
             raise ValueError("mdn net must output K*(2D+1) values")
-        return Packed(kind=L.OP_MDN, dim=d, n_par=dp, params=np.concatenate([head, mlp]),
-                      n_layers=len(dims), act=L.ACT[self.activation], n_out=n_out, k=k,
-                      layer_dim=dims, n_normals=d, n_uniforms=1, scratch=n_out, heavy=True)
+        return _with_tc(Packed(kind=L.OP_MDN, dim=d, n_par=dp, params=np.concatenate([head, mlp]),
+                               n_layers=len(dims), act=L.ACT[self.activation], n_out=n_out, k=k,
+                               layer_dim=dims, n_normals=d, n_uniforms=1, scratch=n_out, heavy=True),
+                        self.layers, dp)
 
     @classmethod
     def from_spec(cls, c, device=None):
@@ -383,8 +437,8 @@ class SoftmaxNNCPD(BaseCPD):
         mlp, dims = pack_mlp(self.layers, dp)
         if dims[-1] != d * k:
             raise ValueError("softmax_nn net must output D*C logits")
-        return Packed(n_par=dp, params=np.concatenate([head, mlp]), n_layers=len(dims),
-                      act=L.ACT[self.activation], layer_dim=dims, **common)
+        return _with_tc(Packed(n_par=dp, params=np.concatenate([head, mlp]), n_layers=len(dims),
+                               act=L.ACT[self.activation], layer_dim=dims, **common), self.layers, dp)
 
     @classmethod
     def from_spec(cls, c, device=None):

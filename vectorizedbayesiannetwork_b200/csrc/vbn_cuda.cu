@@ -12,6 +12,7 @@
 #include "vbn_kde.cuh"
 #include "vbn_reduce.cuh"
 #include "vbn_schedule.cuh"
+#include "vbn_schedule_tc.cuh"
 
 static_assert(sizeof(VbnOp) == 128, "VbnOp must be 128 bytes");
 static_assert(sizeof(VbnView) == 24, "VbnView layout");
@@ -68,6 +69,8 @@ struct VbnPlan {
   int shape;       // index into kShapes
   int blocks_per_sm;
   size_t smem_bytes;
+  int tc;          // 1: launch vbn::tc::schedule_tc_kernel
+  int tc_nbuf;     // weight-ring depth of the tensor-core kernel
 };
 
 extern "C" {
@@ -96,7 +99,31 @@ int32_t vbn_plan_create(const VbnProgramDesc* desc, VbnPlan** out_plan) {
   int max_smem = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
   p->shape = -1;
+  p->tc = 0;
+  p->tc_nbuf = 0;
   const size_t per_row = static_cast<size_t>(desc->n_slots + desc->n_scratch) * sizeof(float);
+  if (desc->tc) {
+    // tensor-core kernel: 512 rows per CTA, one CTA per SM, deepest weight ring that fits
+    const void* fn = reinterpret_cast<const void*>(&vbn::tc::schedule_tc_kernel);
+    for (int nbuf = vbn::tc::kMaxBufs; nbuf >= 2 && !p->tc; --nbuf) {
+      const size_t bytes = vbn::tc::kCtrlBytes + static_cast<size_t>(nbuf) * vbn::tc::kWbufBytes +
+                           per_row * vbn::tc::kConsumerThreads;
+      if (bytes > static_cast<size_t>(max_smem)) continue;
+      CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+      int occ = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, vbn::tc::kThreads, bytes));
+      if (occ < 1) continue;
+      p->tc = 1;
+      p->tc_nbuf = nbuf;
+      p->blocks_per_sm = 1;
+      p->smem_bytes = bytes;
+    }
+    if (p->tc) {
+      *out_plan = p;
+      return VBN_OK;
+    }
+    // does not fit: fall through to the FFMA shapes (the ops keep their FFMA parameter blocks)
+  }
   for (int i = 0; i < static_cast<int>(sizeof(kShapes) / sizeof(kShapes[0])); ++i) {
     const Shape& s = kShapes[i];
     if (s.heavy != (desc->heavy ? 1 : 0)) continue;
@@ -133,7 +160,7 @@ int32_t vbn_run_forward_launches(const VbnPlan* plan) { return plan ? 1 : 0; }
 int32_t vbn_run_forward(const VbnPlan* plan, const VbnRunDesc* run, void* stream) {
   if (!plan || !run) return fail(VBN_E_INVALID, "NULL argument");
   if (run->n_queries <= 0 || run->n_samples <= 0) return fail(VBN_E_INVALID, "empty run");
-  const Shape& s = kShapes[plan->shape];
+  const Shape& s = kShapes[plan->shape < 0 ? 0 : plan->shape];
   vbn::ScheduleArgs a;
   std::memset(&a, 0, sizeof(a));
   a.ops = plan->desc.ops_dev;
@@ -158,6 +185,16 @@ int32_t vbn_run_forward(const VbnPlan* plan, const VbnRunDesc* run, void* stream
   a.logw = run->logw_dev;
   a.logp = run->logp_dev;
   a.error_flag = run->error_flag_dev;
+  if (plan->tc) {
+    const int64_t n_tiles = (a.n_rows + vbn::tc::kConsumerThreads - 1) / vbn::tc::kConsumerThreads;
+    const unsigned grid = static_cast<unsigned>(n_tiles < plan->num_sms ? n_tiles : plan->num_sms);
+    int nbuf = plan->tc_nbuf;
+    void* targs[] = {&a, &nbuf};
+    CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(&vbn::tc::schedule_tc_kernel), dim3(grid),
+                              dim3(vbn::tc::kThreads), targs, plan->smem_bytes,
+                              static_cast<cudaStream_t>(stream)));
+    return VBN_OK;
+  }
   const int64_t rows_per_cta = static_cast<int64_t>(s.rpt) * s.nt;
   const int64_t n_tiles = (a.n_rows + rows_per_cta - 1) / rows_per_cta;
   const int64_t resident = static_cast<int64_t>(plan->num_sms) * plan->blocks_per_sm;

@@ -54,13 +54,19 @@ struct Rows {
   float4 ncache[RPT], ucache[RPT];
 };
 
-template <int RPT, int NT>
+// Tensor-core hook: the tcgen05 kernel (vbn_schedule_tc.cuh) plugs its MLP evaluator in here.
+struct NoTc {
+  static constexpr bool kEnabled = false;
+};
+
+template <int RPT, int NT, class TC = NoTc>
 struct Ctx {
   const ScheduleArgs& a;
   const VbnOp* gop = nullptr;  // the op being executed, in global memory (for dynamic field access)
   float* slots;    // [n_slots][ROWS]
   float* scratch;  // [n_scratch][ROWS]
   int tid;
+  TC tc;
   Rows<RPT> rows;
   static constexpr int ROWS = RPT * NT;
 
@@ -151,8 +157,8 @@ struct Ctx {
 // Result lands in scratch rows 0..n_out-1.
 // `norm` (gaussian_nn only): mean_x[Dp], std_x[Dp] -> z = (pa - mean_x)/std_x (gaussian_nn.py:105-112)
 // ---------------------------------------------------------------------------------------
-template <int RPT, int NT>
-__device__ __forceinline__ void mlp_generic(Ctx<RPT, NT>& c, const VbnOp& op, const float* P,
+template <int RPT, int NT, class TC>
+__device__ __forceinline__ void mlp_generic(Ctx<RPT, NT, TC>& c, const VbnOp& op, const float* P,
                                          const float* norm, const int32_t* par) {
   float bufA[kMaxGenericWidth], bufB[kMaxGenericWidth];
   for (int j = 0; j < RPT; ++j) {
@@ -192,8 +198,8 @@ __device__ __forceinline__ void mlp_generic(Ctx<RPT, NT>& c, const VbnOp& op, co
 // Fast path for the reference's default hidden_dims [32, 32]: h1 lives in registers, the
 // 32x32 layer is register-tiled 8 outputs at a time with 128-bit uniform weight loads (L1
 // broadcast), and the output layer is accumulated chunk by chunk into scratch.
-template <int RPT, int NT>
-__device__ __forceinline__ void mlp_fast32(Ctx<RPT, NT>& c, const VbnOp& op, const float* P,
+template <int RPT, int NT, class TC>
+__device__ __forceinline__ void mlp_fast32(Ctx<RPT, NT, TC>& c, const VbnOp& op, const float* P,
                                            const float* norm, const int32_t* par) {
   constexpr int H = 32;
   const int dp = op.n_par;
@@ -301,9 +307,15 @@ __device__ __forceinline__ void mlp_fast32(Ctx<RPT, NT>& c, const VbnOp& op, con
   }
 }
 
-template <int RPT, int NT>
-__device__ __forceinline__ void mlp_eval(Ctx<RPT, NT>& c, const VbnOp& op, const float* P,
+template <int RPT, int NT, class TC>
+__device__ __forceinline__ void mlp_eval(Ctx<RPT, NT, TC>& c, const VbnOp& op, const float* P,
                                          const float* norm, const int32_t* par) {
+  if constexpr (TC::kEnabled) {
+    if (op.tc[0] != 0) {  // tensor-core eligible MLP (plan.py sets the tc fields)
+      c.tc.mlp(c, op, norm, par);
+      return;
+    }
+  }
   if (op.n_layers == 0) {
     for (int o = 0; o < op.n_out; ++o) {
       const float v = __ldg(P + o);
@@ -311,17 +323,17 @@ __device__ __forceinline__ void mlp_eval(Ctx<RPT, NT>& c, const VbnOp& op, const
       for (int j = 0; j < RPT; ++j) c.scr(o, j) = v;
     }
   } else if (op.n_layers == 3 && op.layer_dim[0] == 32 && op.layer_dim[1] == 32) {
-    mlp_fast32<RPT, NT>(c, op, P, norm, par);
+    mlp_fast32(c, op, P, norm, par);
   } else {
-    mlp_generic<RPT, NT>(c, op, P, norm, par);
+    mlp_generic(c, op, P, norm, par);
   }
 }
 
 // ---------------------------------------------------------------------------------------
 // value sources / sinks common to all ops
 // ---------------------------------------------------------------------------------------
-template <int RPT, int NT>
-__device__ __forceinline__ void load_fixed(Ctx<RPT, NT>& c, const VbnOp& op) {
+template <int RPT, int NT, class TC>
+__device__ __forceinline__ void load_fixed(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
   const int src = op.flags & VBN_SRC_MASK;
   if (src == VBN_SRC_FIXED_Q) {
     for (int d = 0; d < op.dim; ++d)
@@ -338,8 +350,8 @@ __device__ __forceinline__ void load_fixed(Ctx<RPT, NT>& c, const VbnOp& op) {
   }
 }
 
-template <int RPT, int NT>
-__device__ __forceinline__ void store_value(Ctx<RPT, NT>& c, const VbnOp& op) {
+template <int RPT, int NT, class TC>
+__device__ __forceinline__ void store_value(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
   if (op.store_idx < 0) return;
   const VbnView v = c.a.stores[op.store_idx];
   for (int d = 0; d < op.dim; ++d)
@@ -348,8 +360,8 @@ __device__ __forceinline__ void store_value(Ctx<RPT, NT>& c, const VbnOp& op) {
       if (c.rows.valid[j]) v.base[c.rows.r[j] * v.row_stride + d * v.dim_stride] = c.slot(op.out_slot + d, j);
 }
 
-template <int RPT, int NT>
-__device__ __forceinline__ void commit_logp(Ctx<RPT, NT>& c, const VbnOp& op, const float (&lp)[RPT]) {
+template <int RPT, int NT, class TC>
+__device__ __forceinline__ void commit_logp(Ctx<RPT, NT, TC>& c, const VbnOp& op, const float (&lp)[RPT]) {
   if (op.flags & VBN_F_ADD_LOGW) {
 #pragma unroll
     for (int j = 0; j < RPT; ++j) c.rows.logw[j] += lp[j];
@@ -364,8 +376,8 @@ __device__ __forceinline__ void commit_logp(Ctx<RPT, NT>& c, const VbnOp& op, co
 // VBN_OP_LG: linear_gaussian.py:163-217 (and gaussian_nn roots, gaussian_nn.py:244-254).
 // params: W[Dp][D], bias[D], scale[D], two_log_scale[D], var[D]
 // ---------------------------------------------------------------------------------------
-template <int RPT, int NT>
-__device__ __forceinline__ void op_lg(Ctx<RPT, NT>& c, const VbnOp& op) {
+template <int RPT, int NT, class TC>
+__device__ __forceinline__ void op_lg(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
   const float* P = c.a.params + op.param_off;
   const int D = op.dim, Dp = op.n_par;
   const float* W = P;
@@ -416,8 +428,8 @@ __device__ __forceinline__ void op_lg(Ctx<RPT, NT>& c, const VbnOp& op) {
 // VBN_OP_GNN: gaussian_nn.py:215-288.
 // params: mean_x[Dp], std_x[Dp], mean_y[D], std_y[D], min_scale, pad4 ; then MLP block
 // ---------------------------------------------------------------------------------------
-template <int RPT, int NT>
-__device__ __forceinline__ void op_gnn(Ctx<RPT, NT>& c, const VbnOp& op) {
+template <int RPT, int NT, class TC>
+__device__ __forceinline__ void op_gnn(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
   const float* P = c.a.params + op.param_off;
   const int D = op.dim, Dp = op.n_par;
   const float* norm = P;
@@ -426,7 +438,7 @@ __device__ __forceinline__ void op_gnn(Ctx<RPT, NT>& c, const VbnOp& op) {
   const float min_scale = __ldg(std_y + D);
   const float* mlp = P + pad4(2 * Dp + 2 * D + 1);
   const int32_t* par = c.a.par_slots + op.par_off;
-  mlp_eval<RPT, NT>(c, op, mlp, norm, par);
+  mlp_eval(c, op, mlp, norm, par);
   const bool sample = (op.flags & VBN_SRC_MASK) == VBN_SRC_SAMPLE;
   const bool want_lp = (op.flags & (VBN_F_ADD_LOGW | VBN_F_OUT_LOGP)) != 0;
   float acc[RPT];
@@ -463,13 +475,13 @@ __device__ __forceinline__ void op_gnn(Ctx<RPT, NT>& c, const VbnOp& op) {
 // VBN_OP_MDN: mdn.py:185-272.  params: min_scale, pad4 ; MLP block.
 // MLP outputs: logits[K], then per component k: loc[D], raw_scale[D].
 // ---------------------------------------------------------------------------------------
-template <int RPT, int NT>
-__device__ __forceinline__ void op_mdn(Ctx<RPT, NT>& c, const VbnOp& op) {
+template <int RPT, int NT, class TC>
+__device__ __forceinline__ void op_mdn(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
   const float* P = c.a.params + op.param_off;
   const int D = op.dim, K = op.k;
   const float min_scale = __ldg(P);
   const int32_t* par = c.a.par_slots + op.par_off;
-  mlp_eval<RPT, NT>(c, op, P + 4, nullptr, par);
+  mlp_eval(c, op, P + 4, nullptr, par);
   const bool sample = (op.flags & VBN_SRC_MASK) == VBN_SRC_SAMPLE;
   const bool want_lp = (op.flags & (VBN_F_ADD_LOGW | VBN_F_OUT_LOGP)) != 0;
 
@@ -561,8 +573,8 @@ __device__ __forceinline__ void op_mdn(Ctx<RPT, NT>& c, const VbnOp& op) {
 //         class_values[D][C], sample_values[D][C], is_discrete[D], pad4 ; MLP block
 // MLP outputs: logits[D][C]
 // ---------------------------------------------------------------------------------------
-template <int RPT, int NT>
-__device__ __forceinline__ void op_snn(Ctx<RPT, NT>& c, const VbnOp& op) {
+template <int RPT, int NT, class TC>
+__device__ __forceinline__ void op_snn(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
   const float* P = c.a.params + op.param_off;
   const int D = op.dim, C = op.k;
   const float min_bw = __ldg(P), wb_scale = __ldg(P + 1), temperature = __ldg(P + 2);
@@ -574,7 +586,7 @@ __device__ __forceinline__ void op_snn(Ctx<RPT, NT>& c, const VbnOp& op) {
   const int32_t* par = c.a.par_slots + op.par_off;
   const int within = op.aux[0];
   const bool clip = op.aux[1] != 0;
-  mlp_eval<RPT, NT>(c, op, mlp, nullptr, par);
+  mlp_eval(c, op, mlp, nullptr, par);
   if (op.n_layers > 0 && temperature != 1.0f) {
     for (int o = 0; o < D * C; ++o)
 #pragma unroll
@@ -710,8 +722,8 @@ __device__ __forceinline__ void op_snn(Ctx<RPT, NT>& c, const VbnOp& op) {
 // params: {hy, hp, const_y, noise_scale, log_n, 0,0,0}, parents[N][Dp] (pad4), targets[N][D]
 //   hy = 0.5/s_y^2, hp = 0.5/s_p^2  ->  log_k = -h*diff^2 + const
 // ---------------------------------------------------------------------------------------
-template <int RPT, int NT>
-__device__ __forceinline__ void op_kde(Ctx<RPT, NT>& c, const VbnOp& op) {
+template <int RPT, int NT, class TC>
+__device__ __forceinline__ void op_kde(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
   const float* P = c.a.params + op.param_off;
   const int D = op.dim, Dp = op.n_par, N = op.k;
   const float hy = __ldg(P), hp = __ldg(P + 1), const_y = __ldg(P + 2), noise_scale = __ldg(P + 3);
@@ -800,8 +812,62 @@ __device__ __forceinline__ void op_kde(Ctx<RPT, NT>& c, const VbnOp& op) {
 }
 
 // ---------------------------------------------------------------------------------------
-// the kernel
+// the kernels' shared body
 // ---------------------------------------------------------------------------------------
+// binds row j of the thread to local row index r (clamped into range; `valid` masks the stores)
+template <class C>
+__device__ __forceinline__ void bind_row(C& c, int j, int64_t r) {
+  const ScheduleArgs& a = c.a;
+  c.rows.valid[j] = r < a.n_rows;
+  const int64_t rc = c.rows.valid[j] ? r : a.n_rows - 1;
+  c.rows.r[j] = rc;
+  const int64_t b = rc / a.n_samples;
+  c.rows.lb[j] = b;
+  c.rows.ls[j] = rc - b * a.n_samples;
+  c.rows.gb[j] = a.query_offset + static_cast<uint32_t>(b);
+  c.rows.gs[j] = a.sample_offset + static_cast<uint32_t>(c.rows.ls[j]);
+  c.rows.logw[j] = 0.0f;
+  c.rows.logp[j] = 0.0f;
+}
+
+// walks every op of the schedule for the rows bound to this thread, then writes logw / logp
+template <bool HEAVY, int RPT, int NT, class TC>
+__device__ __forceinline__ void run_ops(Ctx<RPT, NT, TC>& c) {
+  const ScheduleArgs& a = c.a;
+  c.rows.cur_nq = -1;
+  c.rows.cur_uq = -1;
+  for (int i = 0; i < a.n_ops; ++i) {
+    VbnOp op;
+    {
+      const int4* src = reinterpret_cast<const int4*>(a.ops + i);
+      int4* dst = reinterpret_cast<int4*>(&op);
+#pragma unroll
+      for (int q = 0; q < static_cast<int>(sizeof(VbnOp) / sizeof(int4)); ++q) dst[q] = __ldg(src + q);
+    }
+    c.gop = a.ops + i;
+    load_fixed(c, op);
+    switch (op.kind) {
+      case VBN_OP_LG: op_lg(c, op); break;
+      case VBN_OP_GNN: if (HEAVY) op_gnn(c, op); break;
+      case VBN_OP_MDN: if (HEAVY) op_mdn(c, op); break;
+      case VBN_OP_SNN: if (HEAVY) op_snn(c, op); break;
+      case VBN_OP_KDE: if (HEAVY) op_kde(c, op); break;
+      default: break;
+    }
+    store_value(c, op);
+  }
+  if (a.logw) {
+#pragma unroll
+    for (int j = 0; j < RPT; ++j)
+      if (c.rows.valid[j]) a.logw[c.rows.r[j]] = c.rows.logw[j];
+  }
+  if (a.logp) {
+#pragma unroll
+    for (int j = 0; j < RPT; ++j)
+      if (c.rows.valid[j]) a.logp[c.rows.r[j]] = a.logp_as_pdf ? expf(c.rows.logp[j]) : c.rows.logp[j];
+  }
+}
+
 template <int RPT, int NT, bool HEAVY, int MIN_BLOCKS>
 __global__ void __launch_bounds__(NT, MIN_BLOCKS) schedule_kernel(const ScheduleArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -811,52 +877,8 @@ __global__ void __launch_bounds__(NT, MIN_BLOCKS) schedule_kernel(const Schedule
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t base = tile * ROWS;
 #pragma unroll
-    for (int j = 0; j < RPT; ++j) {
-      const int64_t r = base + j * NT + threadIdx.x;
-      c.rows.valid[j] = r < a.n_rows;
-      const int64_t rc = c.rows.valid[j] ? r : a.n_rows - 1;
-      c.rows.r[j] = rc;
-      const int64_t b = rc / a.n_samples;
-      c.rows.lb[j] = b;
-      c.rows.ls[j] = rc - b * a.n_samples;
-      c.rows.gb[j] = a.query_offset + static_cast<uint32_t>(b);
-      c.rows.gs[j] = a.sample_offset + static_cast<uint32_t>(c.rows.ls[j]);
-      c.rows.logw[j] = 0.0f;
-      c.rows.logp[j] = 0.0f;
-    }
-    c.rows.cur_nq = -1;
-    c.rows.cur_uq = -1;
-
-    for (int i = 0; i < a.n_ops; ++i) {
-      VbnOp op;
-      {
-        const int4* src = reinterpret_cast<const int4*>(a.ops + i);
-        int4* dst = reinterpret_cast<int4*>(&op);
-#pragma unroll
-        for (int q = 0; q < static_cast<int>(sizeof(VbnOp) / sizeof(int4)); ++q) dst[q] = __ldg(src + q);
-      }
-      c.gop = a.ops + i;
-      load_fixed(c, op);
-      switch (op.kind) {
-        case VBN_OP_LG: op_lg(c, op); break;
-        case VBN_OP_GNN: if (HEAVY) op_gnn(c, op); break;
-        case VBN_OP_MDN: if (HEAVY) op_mdn(c, op); break;
-        case VBN_OP_SNN: if (HEAVY) op_snn(c, op); break;
-        case VBN_OP_KDE: if (HEAVY) op_kde(c, op); break;
-        default: break;
-      }
-      store_value(c, op);
-    }
-    if (a.logw) {
-#pragma unroll
-      for (int j = 0; j < RPT; ++j)
-        if (c.rows.valid[j]) a.logw[c.rows.r[j]] = c.rows.logw[j];
-    }
-    if (a.logp) {
-#pragma unroll
-      for (int j = 0; j < RPT; ++j)
-        if (c.rows.valid[j]) a.logp[c.rows.r[j]] = a.logp_as_pdf ? expf(c.rows.logp[j]) : c.rows.logp[j];
-    }
+    for (int j = 0; j < RPT; ++j) bind_row(c, j, base + j * NT + threadIdx.x);
+    run_ops<HEAVY>(c);
   }
 }
 

@@ -1,0 +1,379 @@
+// Tensor-core variant of the fused schedule kernel (sm_100a: tcgen05 + TMEM + bulk async copy).
+//
+// Same schedule walk as schedule_kernel (vbn_schedule.cuh), but the three dense contractions of
+// every [Dp -> 32 -> 32 -> O] MLP CPD (gaussian_nn.py:16-34 _build_mlp, evaluated at
+// gaussian_nn.py:235, mdn.py:199, softmax_nn.py:585) run on the 5th-gen tensor cores:
+//
+//   * one CTA = 4 consumer warpgroups (4 x 128 rows) + 1 producer warp, one CTA per SM;
+//   * a row is a TMEM lane: thread t of a warpgroup owns row t of its 128-row tile for the whole
+//     DAG walk, so MLP inputs/outputs move registers <-> TMEM with tcgen05.st / tcgen05.ld
+//     (32x32b shapes) and never touch shared memory or HBM;
+//   * activations are the A operand, read by tcgen05.mma straight from TMEM; the weights are the
+//     B operand, K-major core-matrix images prepacked by the host (cpds.py pack_mlp_tc) and
+//     streamed L2 -> shared memory by the producer warp with cp.async.bulk through a ring of
+//     mbarrier-guarded buffers, running ahead of the consumers;
+//   * fp32 parity (1e-5) rules out plain TF32, so every product is the error-compensated
+//     3xTF32 split  a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  (hi = RN-to-tf32, lo = exact
+//     remainder), accumulated in fp32 in TMEM: ~2^-21 relative per product;
+//   * each warpgroup issues its own MMAs (one elected thread) and waits on its own mbarrier
+//     (tcgen05.commit), so the four row tiles of a CTA drift freely and hide each other's
+//     MMA / TMEM latency; the only CTA-wide coupling is the weight ring.
+//
+// TMEM map (512 columns, 128 per warpgroup): D fp32 accumulator [0,32) | A_hi [32,64) |
+// A_lo [64,96).
+#pragma once
+#include "vbn_schedule.cuh"
+
+namespace vbn {
+namespace tc {
+
+constexpr int kWgThreads = 128;
+constexpr int kNumWg = 4;
+constexpr int kConsumerThreads = kWgThreads * kNumWg;
+constexpr int kThreads = kConsumerThreads + 32;  // + producer warp
+constexpr int kTmemCols = 512;
+constexpr int kColsPerWg = 128;
+constexpr int kColD = 0, kColAhi = 32, kColAlo = 64;
+constexpr int kHidden = 32;
+constexpr int kWbufBytes = 25088;  // >= largest weight image (K1 = 32, N3 = 32: 24960 B)
+constexpr int kMaxBufs = 4;
+constexpr int kCtrlBytes = 128;    // tmem address + 12 mbarriers
+
+// bytes of one weight image: W1 hi/lo [32][K1], W2 hi/lo [32][32], W3 hi/lo [N3][32], b1, b2, b3
+__host__ __device__ __forceinline__ int blob_bytes(int k1, int n3) {
+  return 4 * (2 * kHidden * k1 + 2 * kHidden * kHidden + 2 * n3 * kHidden + 2 * kHidden + n3);
+}
+
+// ---- PTX wrappers -----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(addr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(addr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+      "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr),
+               "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem descriptor], kind::tf32, issued by ONE thread
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+
+// Shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B (128 B
+// contiguous); LBO = bytes between the two K-adjacent core matrices of one MMA (K = 8 tf32),
+// SBO = bytes between 8-row groups.  Bits: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
+// version=1 [46,48) | layout_type=0 (SWIZZLE_NONE) [61,64).
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu) |
+         (static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         (static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// Instruction descriptor, kind::tf32, fp32 accumulate, A and B K-major, M = 128.
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// x = hi + lo with hi = x rounded to nearest tf32 (10 explicit mantissa bits), lo exact
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+// 3xTF32 layer: D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi over K (multiple of 8), N columns.
+// B images are [N][K] K-major core-matrix layouts (see pack_mlp_tc): LBO = 128, SBO = K*32.
+__device__ __forceinline__ void issue_layer(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                            uint32_t b_lo, int k, int n) {
+  const uint32_t idesc = make_idesc(n);
+  const uint32_t sbo = static_cast<uint32_t>(k) * 32u;
+  const uint64_t dhi = make_b_desc(b_hi, 128u, sbo), dlo = make_b_desc(b_lo, 128u, sbo);
+  const int ks = k >> 3;
+  uint32_t acc = 0;
+  for (int s = 0; s < ks; ++s) {  // one K = 8 step covers two core matrices = 256 B = 16 desc units
+    mma_tf32_ts(d, a_lo + 8 * s, dhi + 16 * s, idesc, acc);
+    acc = 1;
+  }
+  for (int s = 0; s < ks; ++s) mma_tf32_ts(d, a_hi + 8 * s, dlo + 16 * s, idesc, 1);
+  for (int s = 0; s < ks; ++s) mma_tf32_ts(d, a_hi + 8 * s, dhi + 16 * s, idesc, 1);
+}
+
+// Per-thread tensor-core state, plugged into Ctx as the TC policy.
+struct TcMlp {
+  static constexpr bool kEnabled = true;
+  uint32_t t_d, t_ahi, t_alo;  // TMEM addresses for this thread's warp (lane base folded in)
+  uint32_t m_d, m_ahi, m_alo;  // same columns, lane 0: operands of the MMA
+  uint32_t wbuf;               // shared-space address of weight buffer 0
+  const unsigned char* wbuf_ptr;
+  uint32_t full_bar, empty_bar, mma_bar;  // full/empty: arrays of nbuf; mma_bar: this warpgroup's
+  uint32_t w_iter;     // tensor-core MLPs consumed so far (ring position)
+  uint32_t mma_phase;  // parity of the next completion of mma_bar
+  int nbuf;
+  int wg, warp_in_wg, lane;
+
+  __device__ __forceinline__ void wg_sync() const { named_bar_sync(1 + wg, kWgThreads); }
+
+  // all 128 threads of the warpgroup: publish TMEM writes, elect, issue, wait for completion
+  __device__ __forceinline__ void run_layer(uint32_t b_hi, uint32_t b_lo, int k, int n) {
+    tc_fence_before();
+    wg_sync();
+    tc_fence_after();
+    if (warp_in_wg == 0) {
+      if (lane == 0) {
+        issue_layer(m_d, m_ahi, m_alo, b_hi, b_lo, k, n);
+        mma_commit(mma_bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait(mma_bar, mma_phase);
+    mma_phase ^= 1u;
+    tc_fence_after();
+  }
+
+  // D (32 fp32 columns) -> bias + activation -> 3xTF32 split -> A_hi / A_lo
+  __device__ __forceinline__ void hidden_epilogue(const float* bias, int act) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t v[16], hi[16], lo[16];
+      tmem_ld16(t_d + 16 * half, v);
+      tmem_wait_ld();
+      if (act == VBN_ACT_RELU) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 b = *reinterpret_cast<const float4*>(bias + 16 * half + 4 * q);
+          split_tf32(fmaxf(__uint_as_float(v[4 * q + 0]) + b.x, 0.0f), hi[4 * q + 0], lo[4 * q + 0]);
+          split_tf32(fmaxf(__uint_as_float(v[4 * q + 1]) + b.y, 0.0f), hi[4 * q + 1], lo[4 * q + 1]);
+          split_tf32(fmaxf(__uint_as_float(v[4 * q + 2]) + b.z, 0.0f), hi[4 * q + 2], lo[4 * q + 2]);
+          split_tf32(fmaxf(__uint_as_float(v[4 * q + 3]) + b.w, 0.0f), hi[4 * q + 3], lo[4 * q + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          split_tf32(activate(__uint_as_float(v[q]) + bias[16 * half + q], act), hi[q], lo[q]);
+      }
+      tmem_st16(t_ahi + 16 * half, hi);
+      tmem_st16(t_alo + 16 * half, lo);
+    }
+    tmem_wait_st();
+  }
+
+  // Evaluates the op's MLP for this thread's row; outputs land in scratch rows 0..n_out-1 like
+  // the FFMA paths (mlp_fast32 / mlp_generic).
+  template <class C>
+  __device__ __forceinline__ void mlp(C& c, const VbnOp& op, const float* norm, const int32_t* par) {
+    const int k1 = op.tc[2], n3 = op.tc[3];
+    const int dp = op.n_par;
+    const uint32_t buf = w_iter % static_cast<uint32_t>(nbuf);
+    const uint32_t ph = (w_iter / static_cast<uint32_t>(nbuf)) & 1u;
+    const uint32_t w1hi = wbuf + buf * kWbufBytes;
+    const uint32_t w1lo = w1hi + kHidden * k1 * 4;
+    const uint32_t w2hi = w1lo + kHidden * k1 * 4;
+    const uint32_t w2lo = w2hi + kHidden * kHidden * 4;
+    const uint32_t w3hi = w2lo + kHidden * kHidden * 4;
+    const uint32_t w3lo = w3hi + n3 * kHidden * 4;
+    const float* bias = reinterpret_cast<const float*>(wbuf_ptr + (w3lo + n3 * kHidden * 4 - wbuf));
+
+    // ---- inputs -> A (K1 columns, zero padded); gaussian_nn standardises them first
+    for (int k0 = 0; k0 < k1; k0 += 8) {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int p = k0 + q;
+        float z = 0.0f;
+        if (p < dp) {
+          z = c.slot(__ldg(par + p), 0);
+          if (norm) z = __fdiv_rn(z - __ldg(norm + p), __ldg(norm + dp + p));
+        }
+        split_tf32(z, hi[q], lo[q]);
+      }
+      tmem_st8(t_ahi + k0, hi);
+      tmem_st8(t_alo + k0, lo);
+    }
+    tmem_wait_st();
+    mbar_wait(full_bar + 8 * buf, ph);  // weights + biases of this op have landed
+
+    run_layer(w1hi, w1lo, k1, kHidden);
+    hidden_epilogue(bias, op.act);
+    run_layer(w2hi, w2lo, kHidden, kHidden);
+    hidden_epilogue(bias + kHidden, op.act);
+    run_layer(w3hi, w3lo, kHidden, n3);
+
+    // ---- outputs -> scratch
+    const float* b3 = bias + 2 * kHidden;
+    const int n_out = op.n_out;
+    for (int o0 = 0; o0 < n3; o0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(t_d + o0, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        if (o0 + q < n_out) c.scr(o0 + q, 0) = __uint_as_float(v[q]) + b3[o0 + q];
+    }
+    // this warp is done with the weight buffer (its MMAs completed, biases read)
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar + 8 * buf);
+    ++w_iter;
+  }
+};
+
+// The kernel.  grid <= #SMs (one CTA per SM), kThreads threads.
+// dynamic smem: [ctrl 128 B][nbuf weight buffers][slots + scratch: (n_slots+n_scratch) x 512 floats]
+__global__ void __launch_bounds__(kThreads, 1) schedule_tc_kernel(const ScheduleArgs a, const int nbuf) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t smem_base = smem_u32(smem_raw);
+  const uint32_t full_bar = smem_base + 16;
+  const uint32_t empty_bar = full_bar + 8 * kMaxBufs;
+  const uint32_t mma_bar0 = empty_bar + 8 * kMaxBufs;
+  const uint32_t wbuf = smem_base + kCtrlBytes;
+  float* slots = reinterpret_cast<float*>(smem_raw + kCtrlBytes + static_cast<size_t>(nbuf) * kWbufBytes);
+
+  if (tid == 0) {
+    for (int i = 0; i < kMaxBufs; ++i) {
+      mbar_init(full_bar + 8 * i, 1);                        // producer's arrive.expect_tx
+      mbar_init(empty_bar + 8 * i, kConsumerThreads / 32);   // one arrive per consumer warp
+    }
+    for (int g = 0; g < kNumWg; ++g) mbar_init(mma_bar0 + 8 * g, 1);  // tcgen05.commit
+    fence_mbar_init();
+  }
+  if (warp == kConsumerThreads / 32) tmem_alloc(smem_base, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw);
+
+  const int64_t n_tiles = (a.n_rows + kWgThreads - 1) / kWgThreads;
+  const int64_t per_round = static_cast<int64_t>(gridDim.x) * kNumWg;
+  const int64_t n_iter = (n_tiles + per_round - 1) / per_round;  // same for every warpgroup: the ring needs it
+
+  if (warp == kConsumerThreads / 32) {
+    // ===== producer warp: stream the weight image of every tensor-core MLP, in schedule order
+    if (lane == 0) {
+      uint32_t w_iter = 0;
+      for (int64_t it = 0; it < n_iter; ++it) {
+        for (int i = 0; i < a.n_ops; ++i) {
+          const int4 t = __ldg(reinterpret_cast<const int4*>(&a.ops[i].tc[0]));
+          if (t.x == 0) continue;
+          const uint32_t buf = w_iter % static_cast<uint32_t>(nbuf);
+          const uint32_t ph = (w_iter / static_cast<uint32_t>(nbuf)) & 1u;
+          mbar_wait(empty_bar + 8 * buf, ph ^ 1u);
+          const uint32_t bytes = static_cast<uint32_t>(blob_bytes(t.z, t.w));
+          mbar_expect_tx(full_bar + 8 * buf, bytes);
+          bulk_g2s(wbuf + buf * kWbufBytes, a.params + t.y, bytes, full_bar + 8 * buf);
+          ++w_iter;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== consumer warpgroups
+    Ctx<1, kConsumerThreads, TcMlp> c(a, slots, tid);
+    const int wg = tid / kWgThreads;
+    const uint32_t col = tmem_base + static_cast<uint32_t>(wg * kColsPerWg);
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    c.tc.m_d = col + kColD;
+    c.tc.m_ahi = col + kColAhi;
+    c.tc.m_alo = col + kColAlo;
+    c.tc.t_d = c.tc.m_d + lane_base;
+    c.tc.t_ahi = c.tc.m_ahi + lane_base;
+    c.tc.t_alo = c.tc.m_alo + lane_base;
+    c.tc.wbuf = wbuf;
+    c.tc.wbuf_ptr = smem_raw + kCtrlBytes;
+    c.tc.full_bar = full_bar;
+    c.tc.empty_bar = empty_bar;
+    c.tc.mma_bar = mma_bar0 + 8 * wg;
+    c.tc.w_iter = 0;
+    c.tc.mma_phase = 0;
+    c.tc.nbuf = nbuf;
+    c.tc.wg = wg;
+    c.tc.warp_in_wg = warp & 3;
+    c.tc.lane = lane;
+    for (int64_t it = 0; it < n_iter; ++it) {
+      const int64_t tile = (it * gridDim.x + blockIdx.x) * kNumWg + wg;
+      bind_row(c, 0, tile * kWgThreads + (tid & (kWgThreads - 1)));
+      run_ops<true>(c);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kConsumerThreads / 32) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace tc
+}  // namespace vbn

@@ -55,7 +55,7 @@ class DevicePlan:
                 par_slots_dev=self.par_slots.data_ptr(), n_par_slots=int(self.par_slots.numel()),
                 params_dev=self.params.data_ptr(), n_params=int(self.params.numel()),
                 n_slots=program.n_slots, n_scratch=program.n_scratch,
-                heavy=1 if program.heavy else 0, reserved=0,
+                heavy=1 if program.heavy else 0, tc=1 if program.tc else 0,
             )
             handle = C.c_void_p()
             L.check(self.lib.vbn_plan_create(C.byref(desc), C.byref(handle)))

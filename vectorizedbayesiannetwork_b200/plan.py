@@ -10,6 +10,7 @@ DAG, not the node count (a 1000-node DAG with parents drawn from the previous 20
 from __future__ import annotations
 
 from dataclasses import dataclass, field
+import os
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -48,11 +49,20 @@ class Program:
     needs_logw: bool
     needs_logp: bool
     dims: Dict[str, int] = field(default_factory=dict)
+    tc: bool = False                       # ops carry tensor-core MLP images -> tcgen05 kernel
+
+
+def tensor_cores_enabled() -> bool:
+    """VBN_TC=0 keeps every MLP on the FFMA path (A/B measurements); default on."""
+    return os.environ.get("VBN_TC", "1") != "0"
 
 
 def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpds: Dict[str, BaseCPD],
-                     roles: Dict[str, Role]) -> Program:
+                     roles: Dict[str, Role], use_tc: Optional[bool] = None) -> Program:
     """``topo``: nodes to emit, in topological order (nodes absent from ``roles`` are skipped)."""
+    if use_tc is None:
+        use_tc = tensor_cores_enabled()
+    any_tc = False
     order = [n for n in topo if n in roles]
     index = {n: i for i, n in enumerate(order)}
     packed: Dict[str, Optional[Packed]] = {}
@@ -98,7 +108,7 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
     # ---- parameter blob ------------------------------------------------------------------------
     blob: List[np.ndarray] = []
     blob_len = 0
-    param_off: Dict[int, int] = {}
+    param_off: Dict[object, int] = {}
 
     ops = np.zeros(len(order), dtype=L.OP_DTYPE)
     par_slots: List[int] = []
@@ -159,6 +169,18 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
                 blob.append(pk.params.astype(np.float32, copy=False))
                 blob_len += pk.params.size
             op["param_off"] = param_off[key]
+            if use_tc and pk.tc_blob is not None:
+                tkey = ("tc", id(pk))
+                if tkey not in param_off:
+                    pad = (-blob_len) % 4  # the bulk copy needs a 16-byte aligned source
+                    if pad:
+                        blob.append(np.zeros(pad, np.float32))
+                        blob_len += pad
+                    param_off[tkey] = blob_len
+                    blob.append(pk.tc_blob.astype(np.float32, copy=False))
+                    blob_len += pk.tc_blob.size
+                op["tc"][:] = [1, param_off[tkey], pk.tc_k1, pk.tc_n3]
+                any_tc = True
             op["n_layers"] = pk.n_layers
             op["act"] = pk.act
             op["n_out"] = pk.n_out
@@ -209,4 +231,5 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
         needs_logw=needs_logw,
         needs_logp=needs_logp,
         dims=dims,
+        tc=any_tc,
     )
