@@ -17,7 +17,7 @@ for ln in dis:
     m = re.search(r'//## File "([^"]+)", line (\d+)(.*)', ln)
     if m:
         cur = (m.group(1).split("/")[-1], int(m.group(2))); continue
-    if re.match(r"\s+/\*[0-9a-f]{4}\*/", ln):
+    if re.match(r"\s+/\*[0-9a-f]{4,6}\*/", ln):
         lines.append(cur)
 print("ncu instrs", len(inst), "nvdisasm instrs", len(lines))
 agg = collections.defaultdict(lambda: [0, 0, 0])

@@ -59,6 +59,11 @@ __device__ __forceinline__ float4 uniform4(uint4 w) {
   return make_float4(u01(w.x), u01(w.y), u01(w.z), u01(w.w));
 }
 
+// Out-of-line Philox + transform: the schedule kernels call these from many op bodies; keeping one
+// copy keeps the hot loop inside the instruction cache.
+__device__ __noinline__ float4 philox_normal4(uint4 c, uint2 k) { return normal4(philox4x32_10(c, k)); }
+__device__ __noinline__ float4 philox_uniform4(uint4 c, uint2 k) { return uniform4(philox4x32_10(c, k)); }
+
 __device__ __forceinline__ float lane4(const float4& v, int lane) {
   return lane == 0 ? v.x : (lane == 1 ? v.y : (lane == 2 ? v.z : v.w));
 }
@@ -69,13 +74,15 @@ __device__ __forceinline__ float lane4(const float4& v, int lane) {
 // F.softplus(x) (beta=1, threshold=20)  -- vbn/cpds/utils.py:6-7
 __device__ __forceinline__ float softplus20(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
 
-__device__ __forceinline__ float activate(float x, int act) {
+__device__ __noinline__ float activate_slow(float x, int act) {
   switch (act) {
-    case VBN_ACT_RELU: return fmaxf(x, 0.0f);
     case VBN_ACT_TANH: return tanhf(x);
     case VBN_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));  // nn.GELU (erf)
     default: return x > 0.0f ? x : expm1f(x);                                      // nn.ELU(alpha=1)
   }
+}
+__device__ __forceinline__ float activate(float x, int act) {
+  return act == VBN_ACT_RELU ? fmaxf(x, 0.0f) : activate_slow(x, act);
 }
 
 // -0.5*((x-loc)^2/var + 2 ln sigma + ln 2pi) for one dim (linear_gaussian.py:214-217)

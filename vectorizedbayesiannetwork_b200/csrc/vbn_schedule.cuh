@@ -79,10 +79,14 @@ struct Ctx {
   // ---- random draws ---------------------------------------------------------------------
   // stream tags in counter word c2 (top 2 bits): 0 normal/row, 1 uniform/row, 2 normal/shared,
   // 3 uniform/shared
-  __device__ __forceinline__ uint4 philox(int j, uint32_t block, uint32_t tag, bool shared) const {
-    const uint4 c = make_uint4(rows.gs[j], shared ? 0xFFFFFFFFu : rows.gb[j], block | (tag << 30),
-                               a.call_offset);
-    return philox4x32_10(c, make_uint2(a.key0, a.key1));
+  __device__ __forceinline__ uint4 counter(int j, uint32_t block, uint32_t tag, bool shared) const {
+    return make_uint4(rows.gs[j], shared ? 0xFFFFFFFFu : rows.gb[j], block | (tag << 30), a.call_offset);
+  }
+  __device__ __forceinline__ float4 normals(int j, uint32_t block, uint32_t tag, bool shared) const {
+    return philox_normal4(counter(j, block, tag, shared), make_uint2(a.key0, a.key1));
+  }
+  __device__ __forceinline__ float4 uniforms(int j, uint32_t block, uint32_t tag, bool shared) const {
+    return philox_uniform4(counter(j, block, tag, shared), make_uint2(a.key0, a.key1));
   }
 
   // normal number `index` of the op's stream, for all RPT rows
@@ -98,13 +102,13 @@ struct Ctx {
     const int q = index >> 2, lane = index & 3;
     if (shared) {
 #pragma unroll
-      for (int j = 0; j < RPT; ++j) out[j] = lane4(normal4(philox(j, q, 2u, true)), lane);
+      for (int j = 0; j < RPT; ++j) out[j] = lane4(normals(j, q, 2u, true), lane);
       return;
     }
     if (q != rows.cur_nq) {
       rows.cur_nq = q;
 #pragma unroll
-      for (int j = 0; j < RPT; ++j) rows.ncache[j] = normal4(philox(j, q, 0u, false));
+      for (int j = 0; j < RPT; ++j) rows.ncache[j] = normals(j, q, 0u, false);
     }
 #pragma unroll
     for (int j = 0; j < RPT; ++j) out[j] = lane4(rows.ncache[j], lane);
@@ -123,13 +127,13 @@ struct Ctx {
     const int q = index >> 2, lane = index & 3;
     if (shared) {
 #pragma unroll
-      for (int j = 0; j < RPT; ++j) out[j] = lane4(uniform4(philox(j, q, 3u, true)), lane);
+      for (int j = 0; j < RPT; ++j) out[j] = lane4(uniforms(j, q, 3u, true), lane);
       return;
     }
     if (q != rows.cur_uq) {
       rows.cur_uq = q;
 #pragma unroll
-      for (int j = 0; j < RPT; ++j) rows.ucache[j] = uniform4(philox(j, q, 1u, false));
+      for (int j = 0; j < RPT; ++j) rows.ucache[j] = uniforms(j, q, 1u, false);
     }
 #pragma unroll
     for (int j = 0; j < RPT; ++j) out[j] = lane4(rows.ucache[j], lane);
@@ -322,7 +326,7 @@ __device__ __forceinline__ void mlp_eval(Ctx<RPT, NT, TC>& c, const VbnOp& op, c
 #pragma unroll
       for (int j = 0; j < RPT; ++j) c.scr(o, j) = v;
     }
-  } else if (op.n_layers == 3 && op.layer_dim[0] == 32 && op.layer_dim[1] == 32) {
+  } else if (op.flags & VBN_F_FAST32) {  // n_layers == 3, hidden dims [32, 32]
     mlp_fast32(c, op, P, norm, par);
   } else {
     mlp_generic(c, op, P, norm, par);
@@ -485,40 +489,53 @@ __device__ __forceinline__ void op_mdn(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
   const bool sample = (op.flags & VBN_SRC_MASK) == VBN_SRC_SAMPLE;
   const bool want_lp = (op.flags & (VBN_F_ADD_LOGW | VBN_F_OUT_LOGP)) != 0;
 
-  // pi = softmax(logits).clamp_min(1e-5); pi /= pi.sum().clamp_min(1e-12)   (mdn.py:227-228)
-  float mx[RPT], se[RPT], tot[RPT];
+  // pi = softmax(logits).clamp_min(1e-5); pi /= pi.sum().clamp_min(1e-12)   (mdn.py:227-228).
+  // The clamped probabilities q_k = max(softmax_k, 1e-5) overwrite the logits in scratch;
+  // pi_k = q_k / tot is formed where it is consumed.
+  float tot[RPT];
+  {
+    float mx[RPT], se[RPT];
 #pragma unroll
-  for (int j = 0; j < RPT; ++j) mx[j] = -CUDART_INF_F;
-  for (int k = 0; k < K; ++k)
+    for (int j = 0; j < RPT; ++j) mx[j] = -CUDART_INF_F;
+    for (int k = 0; k < K; ++k)
 #pragma unroll
-    for (int j = 0; j < RPT; ++j) mx[j] = fmaxf(mx[j], c.scr(k, j));
+      for (int j = 0; j < RPT; ++j) mx[j] = fmaxf(mx[j], c.scr(k, j));
 #pragma unroll
-  for (int j = 0; j < RPT; ++j) se[j] = 0.0f;
-  for (int k = 0; k < K; ++k)
+    for (int j = 0; j < RPT; ++j) se[j] = 0.0f;
+    for (int k = 0; k < K; ++k)
 #pragma unroll
-    for (int j = 0; j < RPT; ++j) se[j] += expf(c.scr(k, j) - mx[j]);
+      for (int j = 0; j < RPT; ++j) {
+        const float e = expf(c.scr(k, j) - mx[j]);
+        c.scr(k, j) = e;
+        se[j] += e;
+      }
 #pragma unroll
-  for (int j = 0; j < RPT; ++j) tot[j] = 0.0f;
-  for (int k = 0; k < K; ++k)
+    for (int j = 0; j < RPT; ++j) tot[j] = 0.0f;
+    for (int k = 0; k < K; ++k)
 #pragma unroll
-    for (int j = 0; j < RPT; ++j) tot[j] += fmaxf(__fdiv_rn(expf(c.scr(k, j) - mx[j]), se[j]), 1e-5f);
+      for (int j = 0; j < RPT; ++j) {
+        const float q = fmaxf(__fdiv_rn(c.scr(k, j), se[j]), 1e-5f);
+        c.scr(k, j) = q;
+        tot[j] += q;
+      }
 #pragma unroll
-  for (int j = 0; j < RPT; ++j) tot[j] = fmaxf(tot[j], 1e-12f);
+    for (int j = 0; j < RPT; ++j) tot[j] = fmaxf(tot[j], 1e-12f);
+  }
 
   if (sample) {
     int pick[RPT];
     if (!c.injected_index(op, 0, 1, pick)) {
+      // k ~ Categorical(pi): inverse CDF on the un-normalised q_k with u scaled by tot
       float u[RPT];
       c.draw_uniform(op, op.u_off, 0, u);
       float cum[RPT];
 #pragma unroll
-      for (int j = 0; j < RPT; ++j) { cum[j] = 0.0f; pick[j] = K - 1; }
+      for (int j = 0; j < RPT; ++j) { cum[j] = 0.0f; pick[j] = K - 1; u[j] *= tot[j]; }
       for (int k = 0; k < K; ++k)
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
-          const float pk = __fdiv_rn(fmaxf(__fdiv_rn(expf(c.scr(k, j) - mx[j]), se[j]), 1e-5f), tot[j]);
           const float before = cum[j];
-          cum[j] += pk;
+          cum[j] += c.scr(k, j);
           if (u[j] >= before && u[j] < cum[j]) pick[j] = k;
         }
     }
@@ -535,14 +552,14 @@ __device__ __forceinline__ void op_mdn(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
     }
   }
   if (want_lp) {
-    // t_k = log pi_k + log_comp_k, then logsumexp over k (mdn.py:264-272); t_k overwrites logit k
+    // t_k = log pi_k + log_comp_k, then logsumexp over k (mdn.py:264-272); t_k overwrites q_k
     float tmax[RPT];
 #pragma unroll
     for (int j = 0; j < RPT; ++j) tmax[j] = -CUDART_INF_F;
     for (int k = 0; k < K; ++k) {
 #pragma unroll
       for (int j = 0; j < RPT; ++j) {
-        const float pk = __fdiv_rn(fmaxf(__fdiv_rn(expf(c.scr(k, j) - mx[j]), se[j]), 1e-5f), tot[j]);
+        const float pk = __fdiv_rn(c.scr(k, j), tot[j]);
         float q = 0.0f;
         for (int d = 0; d < D; ++d) {
           const float loc = c.scr(K + k * 2 * D + d, j);
@@ -837,12 +854,18 @@ __device__ __forceinline__ void run_ops(Ctx<RPT, NT, TC>& c) {
   c.rows.cur_nq = -1;
   c.rows.cur_uq = -1;
   for (int i = 0; i < a.n_ops; ++i) {
-    VbnOp op;
+    VbnOp op;  // only the 16-byte quads this op kind reads are fetched (layer_dim: via c.gop)
     {
       const int4* src = reinterpret_cast<const int4*>(a.ops + i);
       int4* dst = reinterpret_cast<int4*>(&op);
-#pragma unroll
-      for (int q = 0; q < static_cast<int>(sizeof(VbnOp) / sizeof(int4)); ++q) dst[q] = __ldg(src + q);
+      dst[0] = __ldg(src + 0);  // kind, flags, dim, n_par
+      dst[1] = __ldg(src + 1);  // out_slot, par_off, param_off, fixed_col
+      dst[2] = __ldg(src + 2);  // store_idx, noise_idx, n_off, u_off
+      if (HEAVY && op.kind >= VBN_OP_GNN) {
+        dst[3] = __ldg(src + 3);  // n_layers, act, n_out, k
+        dst[6] = __ldg(src + 6);  // aux
+        dst[7] = __ldg(src + 7);  // tc
+      }
     }
     c.gop = a.ops + i;
     load_fixed(c, op);

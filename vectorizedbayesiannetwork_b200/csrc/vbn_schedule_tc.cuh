@@ -59,11 +59,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t"
-      "}" ::"r"(bar), "r"(parity)
+      "}" ::"r"(bar), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware, do not spin
       : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -151,27 +151,42 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
-// x = hi + lo with hi = x rounded to nearest tf32 (10 explicit mantissa bits), lo exact
+// x = hi + lo with hi = x rounded to nearest tf32 (10 explicit mantissa bits), lo the exact
+// remainder (the tensor core reads the top 19 bits of lo: residual <= 2^-21 |x|).  Truncating hi
+// instead saves one instruction per element but its one-sided 2^-20 residual fails the 2e-5
+// log_prob parity of narrow fitted MDN components (readme golden), so round.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 // 3xTF32 layer: D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi over K (multiple of 8), N columns.
 // B images are [N][K] K-major core-matrix layouts (see pack_mlp_tc): LBO = 128, SBO = K*32.
+// KS = number of K = 8 steps (compile time so the issue sequence is straight-line code on the
+// uniform datapath); one step covers two core matrices = 256 B = 16 descriptor units.
+template <int KS>
 __device__ __forceinline__ void issue_layer(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
-                                            uint32_t b_lo, int k, int n) {
+                                            uint32_t b_lo, int n) {
   const uint32_t idesc = make_idesc(n);
-  const uint32_t sbo = static_cast<uint32_t>(k) * 32u;
+  const uint32_t sbo = static_cast<uint32_t>(KS) * 256u;
   const uint64_t dhi = make_b_desc(b_hi, 128u, sbo), dlo = make_b_desc(b_lo, 128u, sbo);
-  const int ks = k >> 3;
-  uint32_t acc = 0;
-  for (int s = 0; s < ks; ++s) {  // one K = 8 step covers two core matrices = 256 B = 16 desc units
-    mma_tf32_ts(d, a_lo + 8 * s, dhi + 16 * s, idesc, acc);
-    acc = 1;
-  }
-  for (int s = 0; s < ks; ++s) mma_tf32_ts(d, a_hi + 8 * s, dlo + 16 * s, idesc, 1);
-  for (int s = 0; s < ks; ++s) mma_tf32_ts(d, a_hi + 8 * s, dhi + 16 * s, idesc, 1);
+#pragma unroll
+  for (int s = 0; s < KS; ++s) mma_tf32_ts(d, a_lo + 8 * s, dhi + 16 * s, idesc, s > 0 ? 1u : 0u);
+#pragma unroll
+  for (int s = 0; s < KS; ++s) mma_tf32_ts(d, a_hi + 8 * s, dlo + 16 * s, idesc, 1u);
+#pragma unroll
+  for (int s = 0; s < KS; ++s) mma_tf32_ts(d, a_hi + 8 * s, dhi + 16 * s, idesc, 1u);
 }
 
 // Per-thread tensor-core state, plugged into Ctx as the TC policy.
@@ -194,9 +209,14 @@ struct TcMlp {
     tc_fence_before();
     wg_sync();
     tc_fence_after();
-    if (warp_in_wg == 0) {
-      if (lane == 0) {
-        issue_layer(m_d, m_ahi, m_alo, b_hi, b_lo, k, n);
+    if (warp_in_wg == 0) {  // warp-uniform: operands stay on the uniform datapath
+      if (elect_one()) {
+        switch (k) {
+          case 8: issue_layer<1>(m_d, m_ahi, m_alo, b_hi, b_lo, n); break;
+          case 16: issue_layer<2>(m_d, m_ahi, m_alo, b_hi, b_lo, n); break;
+          case 24: issue_layer<3>(m_d, m_ahi, m_alo, b_hi, b_lo, n); break;
+          default: issue_layer<4>(m_d, m_ahi, m_alo, b_hi, b_lo, n); break;
+        }
         mma_commit(mma_bar);
       }
       __syncwarp();
@@ -296,7 +316,8 @@ struct TcMlp {
 // dynamic smem: [ctrl 128 B][nbuf weight buffers][slots + scratch: (n_slots+n_scratch) x 512 floats]
 __global__ void __launch_bounds__(kThreads, 1) schedule_tc_kernel(const ScheduleArgs a, const int nbuf) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform for the compiler
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t full_bar = smem_base + 16;
   const uint32_t empty_bar = full_bar + 8 * kMaxBufs;
@@ -316,7 +337,7 @@ __global__ void __launch_bounds__(kThreads, 1) schedule_tc_kernel(const Schedule
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw);
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem_raw), 0);
 
   const int64_t n_tiles = (a.n_rows + kWgThreads - 1) / kWgThreads;
   const int64_t per_round = static_cast<int64_t>(gridDim.x) * kNumWg;
@@ -344,7 +365,7 @@ __global__ void __launch_bounds__(kThreads, 1) schedule_tc_kernel(const Schedule
   } else {
     // ===== consumer warpgroups
     Ctx<1, kConsumerThreads, TcMlp> c(a, slots, tid);
-    const int wg = tid / kWgThreads;
+    const int wg = warp >> 2;
     const uint32_t col = tmem_base + static_cast<uint32_t>(wg * kColsPerWg);
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     c.tc.m_d = col + kColD;

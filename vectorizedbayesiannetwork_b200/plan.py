@@ -188,6 +188,8 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
             ld = list(pk.layer_dim)[: L.MAX_LAYERS]
             op["layer_dim"][: len(ld)] = ld
             op["aux"][:] = pk.aux
+            if pk.n_layers == 3 and list(pk.layer_dim[:2]) == [32, 32]:
+                flags |= L.F_FAST32
             if r.add_logw:
                 flags |= L.F_ADD_LOGW
                 needs_logw = True
