@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define VBN_CUDA_ABI_VERSION 2
+#define VBN_CUDA_ABI_VERSION 3
 
 /* error codes */
 #define VBN_OK 0
@@ -126,7 +126,12 @@ typedef struct VbnProgramDesc {
   int32_t n_slots;    /* value slots a row needs at once (after liveness analysis)         */
   int32_t n_scratch;  /* per-row scratch floats (max MLP output width over the program)    */
   int32_t heavy;      /* 1 if the program contains MLP / KDE ops (picks the launch shape)  */
-  int32_t tc;         /* 1: run the tcgen05 kernel (ops carry tensor-core MLP images)      */
+  int32_t tc;         /* 0: FP32-pipe kernel; 4 or 5: tcgen05 kernel with that many 128-row
+                         warpgroups per CTA (ops carry tensor-core MLP images)              */
+  const int32_t* tc_list_dev; /* [n_tc][2] {image float offset, image bytes} of every op with
+                         tc[0] != 0, in schedule order (the weight ring's fetch list)       */
+  int32_t n_tc;
+  int32_t reserved;
 } VbnProgramDesc;
 
 typedef struct VbnPlan VbnPlan;

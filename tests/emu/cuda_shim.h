@@ -22,6 +22,7 @@
 
 struct uint2 { uint32_t x, y; };
 struct uint4 { uint32_t x, y, z, w; };
+struct int2 { int32_t x, y; };
 struct int4 { int32_t x, y, z, w; };
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };

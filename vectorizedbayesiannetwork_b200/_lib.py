@@ -10,7 +10,7 @@ import numpy as np
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libvbn_cuda.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # op kinds / flags (keep in sync with include/vbn_cuda.h)
 OP_NONE, OP_LG, OP_GNN, OP_MDN, OP_SNN, OP_KDE = 0, 1, 2, 3, 4, 5
@@ -40,6 +40,7 @@ class ProgramDesc(C.Structure):
         ("params_dev", C.c_void_p), ("n_params", C.c_int64),
         ("n_slots", C.c_int32), ("n_scratch", C.c_int32),
         ("heavy", C.c_int32), ("tc", C.c_int32),
+        ("tc_list_dev", C.c_void_p), ("n_tc", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -60,6 +60,11 @@ const Shape kShapes[] = {
     make_shape<1, 64, false, 1>(),
 };
 
+const void* tc_kernel(int nwg) {
+  return nwg == 5 ? reinterpret_cast<const void*>(&vbn::tc::schedule_tc_kernel<5>)
+                  : reinterpret_cast<const void*>(&vbn::tc::schedule_tc_kernel<4>);
+}
+
 }  // namespace
 
 struct VbnPlan {
@@ -69,7 +74,7 @@ struct VbnPlan {
   int shape;       // index into kShapes
   int blocks_per_sm;
   size_t smem_bytes;
-  int tc;          // 1: launch vbn::tc::schedule_tc_kernel
+  int tc;          // 0, or warpgroups per CTA of vbn::tc::schedule_tc_kernel<NWG>
   int tc_nbuf;     // weight-ring depth of the tensor-core kernel
 };
 
@@ -104,16 +109,22 @@ int32_t vbn_plan_create(const VbnProgramDesc* desc, VbnPlan** out_plan) {
   const size_t per_row = static_cast<size_t>(desc->n_slots + desc->n_scratch) * sizeof(float);
   if (desc->tc) {
     // tensor-core kernel: 512 rows per CTA, one CTA per SM, deepest weight ring that fits
-    const void* fn = reinterpret_cast<const void*>(&vbn::tc::schedule_tc_kernel);
+    if (!desc->tc_list_dev || desc->n_tc <= 0) {
+      delete p;
+      return fail(VBN_E_INVALID, "tc program without a tc_list");
+    }
+    const int nwg = desc->tc == 5 ? 5 : 4;
+    const void* fn = tc_kernel(nwg);
+    const int threads = nwg * vbn::tc::kWgThreads;
     for (int nbuf = vbn::tc::kMaxBufs; nbuf >= 2 && !p->tc; --nbuf) {
       const size_t bytes = vbn::tc::kCtrlBytes + static_cast<size_t>(nbuf) * vbn::tc::kWbufBytes +
-                           per_row * vbn::tc::kConsumerThreads;
+                           per_row * threads;
       if (bytes > static_cast<size_t>(max_smem)) continue;
       CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
       int occ = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, vbn::tc::kThreads, bytes));
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, bytes));
       if (occ < 1) continue;
-      p->tc = 1;
+      p->tc = nwg;
       p->tc_nbuf = nbuf;
       p->blocks_per_sm = 1;
       p->smem_bytes = bytes;
@@ -186,12 +197,14 @@ int32_t vbn_run_forward(const VbnPlan* plan, const VbnRunDesc* run, void* stream
   a.logp = run->logp_dev;
   a.error_flag = run->error_flag_dev;
   if (plan->tc) {
-    const int64_t n_tiles = (a.n_rows + vbn::tc::kConsumerThreads - 1) / vbn::tc::kConsumerThreads;
+    const int threads = plan->tc * vbn::tc::kWgThreads;
+    const int64_t n_tiles = (a.n_rows + threads - 1) / threads;
     const unsigned grid = static_cast<unsigned>(n_tiles < plan->num_sms ? n_tiles : plan->num_sms);
     int nbuf = plan->tc_nbuf;
+    a.tc_list = reinterpret_cast<const int2*>(plan->desc.tc_list_dev);
+    a.n_tc = plan->desc.n_tc;
     void* targs[] = {&a, &nbuf};
-    CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(&vbn::tc::schedule_tc_kernel), dim3(grid),
-                              dim3(vbn::tc::kThreads), targs, plan->smem_bytes,
+    CUDA_TRY(cudaLaunchKernel(tc_kernel(plan->tc), dim3(grid), dim3(threads), targs, plan->smem_bytes,
                               static_cast<cudaStream_t>(stream)));
     return VBN_OK;
   }

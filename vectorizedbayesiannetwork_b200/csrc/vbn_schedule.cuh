@@ -33,6 +33,8 @@ struct ScheduleArgs {
   float* logw;
   float* logp;
   int32_t* error_flag;
+  const int2* tc_list;  // tensor-core kernel only: per tc op {image float offset, image bytes}
+  int32_t n_tc;
 };
 
 constexpr int kMaxGenericWidth = 128;  // widest layer the generic MLP path accepts

@@ -4,14 +4,15 @@
 // every [Dp -> 32 -> 32 -> O] MLP CPD (gaussian_nn.py:16-34 _build_mlp, evaluated at
 // gaussian_nn.py:235, mdn.py:199, softmax_nn.py:585) run on the 5th-gen tensor cores:
 //
-//   * one CTA = 4 consumer warpgroups (4 x 128 rows) + 1 producer warp, one CTA per SM;
+//   * one CTA = NWG warpgroups (NWG x 128 rows; NWG = 4 or 5), one CTA per SM, persistent;
 //   * a row is a TMEM lane: thread t of a warpgroup owns row t of its 128-row tile for the whole
 //     DAG walk, so MLP inputs/outputs move registers <-> TMEM with tcgen05.st / tcgen05.ld
 //     (32x32b shapes) and never touch shared memory or HBM;
 //   * activations are the A operand, read by tcgen05.mma straight from TMEM; the weights are the
 //     B operand, K-major core-matrix images prepacked by the host (cpds.py pack_mlp_tc) and
-//     streamed L2 -> shared memory by the producer warp with cp.async.bulk through a ring of
-//     mbarrier-guarded buffers, running ahead of the consumers;
+//     streamed L2 -> shared memory with cp.async.bulk through a ring of mbarrier-guarded buffers;
+//     one elected lane of warp 0 tops the ring up (non-blocking look-ahead) each time it enters an
+//     MLP, so no warp -- and no register allocation -- is spent on a dedicated producer;
 //   * fp32 parity (1e-5) rules out plain TF32, so every product is the error-compensated
 //     3xTF32 split  a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  (hi = RN-to-tf32, lo = exact
 //     remainder), accumulated in fp32 in TMEM: ~2^-21 relative per product;
@@ -19,7 +20,7 @@
 //     (tcgen05.commit), so the four row tiles of a CTA drift freely and hide each other's
 //     MMA / TMEM latency; the only CTA-wide coupling is the weight ring.
 //
-// TMEM map (512 columns, 128 per warpgroup): D fp32 accumulator [0,32) | A_hi [32,64) |
+// TMEM map (512 columns allocated, 96 per warpgroup): D fp32 accumulator [0,32) | A_hi [32,64) |
 // A_lo [64,96).
 #pragma once
 #include "vbn_schedule.cuh"
@@ -28,16 +29,14 @@ namespace vbn {
 namespace tc {
 
 constexpr int kWgThreads = 128;
-constexpr int kNumWg = 4;
-constexpr int kConsumerThreads = kWgThreads * kNumWg;
-constexpr int kThreads = kConsumerThreads + 32;  // + producer warp
+constexpr int kMaxWg = 5;
 constexpr int kTmemCols = 512;
-constexpr int kColsPerWg = 128;
+constexpr int kColsPerWg = 96;
 constexpr int kColD = 0, kColAhi = 32, kColAlo = 64;
 constexpr int kHidden = 32;
 constexpr int kWbufBytes = 25088;  // >= largest weight image (K1 = 32, N3 = 32: 24960 B)
 constexpr int kMaxBufs = 4;
-constexpr int kCtrlBytes = 128;    // tmem address + 12 mbarriers
+constexpr int kCtrlBytes = 128;    // tmem address + up to 13 mbarriers
 
 // bytes of one weight image: W1 hi/lo [32][K1], W2 hi/lo [32][32], W3 hi/lo [N3][32], b1, b2, b3
 __host__ __device__ __forceinline__ int blob_bytes(int k1, int n3) {
@@ -65,6 +64,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE_%=:\n\t"
       "}" ::"r"(bar), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware, do not spin
       : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -201,6 +213,32 @@ struct TcMlp {
   uint32_t mma_phase;  // parity of the next completion of mma_bar
   int nbuf;
   int wg, warp_in_wg, lane;
+  // weight-ring producer (warp 0 only)
+  bool producer;
+  uint32_t p_iter;     // weight images issued so far
+  uint32_t p_total;    // images this CTA will consume in total (n_iter * n_tc)
+  const int2* tc_list; // per tensor-core op: {float offset of its image in params, bytes}
+  const float* params;
+  uint32_t n_tc;
+
+  // Issues every image whose ring slot is free, up to nbuf ahead of this warp; blocks only for the
+  // image of the op this warp is about to run (its slot frees once the slowest warp has left op
+  // w_iter - nbuf, which never depends on this warp).  One elected lane.
+  __device__ __forceinline__ void produce() {
+    while (p_iter < p_total && p_iter < w_iter + static_cast<uint32_t>(nbuf)) {
+      const uint32_t buf = p_iter % static_cast<uint32_t>(nbuf);
+      const uint32_t ph = ((p_iter / static_cast<uint32_t>(nbuf)) & 1u) ^ 1u;
+      if (p_iter > w_iter) {
+        if (!mbar_test(empty_bar + 8 * buf, ph)) break;
+      } else {
+        mbar_wait(empty_bar + 8 * buf, ph);
+      }
+      const int2 e = __ldg(tc_list + (p_iter % n_tc));
+      mbar_expect_tx(full_bar + 8 * buf, static_cast<uint32_t>(e.y));
+      bulk_g2s(wbuf + buf * kWbufBytes, params + e.x, static_cast<uint32_t>(e.y), full_bar + 8 * buf);
+      ++p_iter;
+    }
+  }
 
   __device__ __forceinline__ void wg_sync() const { named_bar_sync(1 + wg, kWgThreads); }
 
@@ -259,6 +297,10 @@ struct TcMlp {
   __device__ __forceinline__ void mlp(C& c, const VbnOp& op, const float* norm, const int32_t* par) {
     const int k1 = op.tc[2], n3 = op.tc[3];
     const int dp = op.n_par;
+    if (producer) {  // warp-uniform
+      if (elect_one()) produce();
+      __syncwarp();
+    }
     const uint32_t buf = w_iter % static_cast<uint32_t>(nbuf);
     const uint32_t ph = (w_iter / static_cast<uint32_t>(nbuf)) & 1u;
     const uint32_t w1hi = wbuf + buf * kWbufBytes;
@@ -312,9 +354,12 @@ struct TcMlp {
   }
 };
 
-// The kernel.  grid <= #SMs (one CTA per SM), kThreads threads.
-// dynamic smem: [ctrl 128 B][nbuf weight buffers][slots + scratch: (n_slots+n_scratch) x 512 floats]
-__global__ void __launch_bounds__(kThreads, 1) schedule_tc_kernel(const ScheduleArgs a, const int nbuf) {
+// The kernel.  grid <= #SMs (one CTA per SM), NWG * 128 threads.
+// dynamic smem: [ctrl 128 B][nbuf weight buffers][slots + scratch: (n_slots+n_scratch) x ROWS floats]
+template <int NWG>
+__global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const ScheduleArgs a, const int nbuf) {
+  constexpr int kThreads = NWG * kWgThreads;
+  static_assert(NWG <= kMaxWg && NWG * kColsPerWg <= kTmemCols, "TMEM budget");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform for the compiler
@@ -327,73 +372,57 @@ __global__ void __launch_bounds__(kThreads, 1) schedule_tc_kernel(const Schedule
 
   if (tid == 0) {
     for (int i = 0; i < kMaxBufs; ++i) {
-      mbar_init(full_bar + 8 * i, 1);                        // producer's arrive.expect_tx
-      mbar_init(empty_bar + 8 * i, kConsumerThreads / 32);   // one arrive per consumer warp
+      mbar_init(full_bar + 8 * i, 1);               // the producer lane's arrive.expect_tx
+      mbar_init(empty_bar + 8 * i, kThreads / 32);  // one arrive per warp
     }
-    for (int g = 0; g < kNumWg; ++g) mbar_init(mma_bar0 + 8 * g, 1);  // tcgen05.commit
+    for (int g = 0; g < NWG; ++g) mbar_init(mma_bar0 + 8 * g, 1);  // tcgen05.commit
     fence_mbar_init();
   }
-  if (warp == kConsumerThreads / 32) tmem_alloc(smem_base, kTmemCols);
+  if (warp == 0) tmem_alloc(smem_base, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem_raw), 0);
 
   const int64_t n_tiles = (a.n_rows + kWgThreads - 1) / kWgThreads;
-  const int64_t per_round = static_cast<int64_t>(gridDim.x) * kNumWg;
+  const int64_t per_round = static_cast<int64_t>(gridDim.x) * NWG;
   const int64_t n_iter = (n_tiles + per_round - 1) / per_round;  // same for every warpgroup: the ring needs it
 
-  if (warp == kConsumerThreads / 32) {
-    // ===== producer warp: stream the weight image of every tensor-core MLP, in schedule order
-    if (lane == 0) {
-      uint32_t w_iter = 0;
-      for (int64_t it = 0; it < n_iter; ++it) {
-        for (int i = 0; i < a.n_ops; ++i) {
-          const int4 t = __ldg(reinterpret_cast<const int4*>(&a.ops[i].tc[0]));
-          if (t.x == 0) continue;
-          const uint32_t buf = w_iter % static_cast<uint32_t>(nbuf);
-          const uint32_t ph = (w_iter / static_cast<uint32_t>(nbuf)) & 1u;
-          mbar_wait(empty_bar + 8 * buf, ph ^ 1u);
-          const uint32_t bytes = static_cast<uint32_t>(blob_bytes(t.z, t.w));
-          mbar_expect_tx(full_bar + 8 * buf, bytes);
-          bulk_g2s(wbuf + buf * kWbufBytes, a.params + t.y, bytes, full_bar + 8 * buf);
-          ++w_iter;
-        }
-      }
-    }
-    __syncwarp();
-  } else {
-    // ===== consumer warpgroups
-    Ctx<1, kConsumerThreads, TcMlp> c(a, slots, tid);
-    const int wg = warp >> 2;
-    const uint32_t col = tmem_base + static_cast<uint32_t>(wg * kColsPerWg);
-    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    c.tc.m_d = col + kColD;
-    c.tc.m_ahi = col + kColAhi;
-    c.tc.m_alo = col + kColAlo;
-    c.tc.t_d = c.tc.m_d + lane_base;
-    c.tc.t_ahi = c.tc.m_ahi + lane_base;
-    c.tc.t_alo = c.tc.m_alo + lane_base;
-    c.tc.wbuf = wbuf;
-    c.tc.wbuf_ptr = smem_raw + kCtrlBytes;
-    c.tc.full_bar = full_bar;
-    c.tc.empty_bar = empty_bar;
-    c.tc.mma_bar = mma_bar0 + 8 * wg;
-    c.tc.w_iter = 0;
-    c.tc.mma_phase = 0;
-    c.tc.nbuf = nbuf;
-    c.tc.wg = wg;
-    c.tc.warp_in_wg = warp & 3;
-    c.tc.lane = lane;
-    for (int64_t it = 0; it < n_iter; ++it) {
-      const int64_t tile = (it * gridDim.x + blockIdx.x) * kNumWg + wg;
-      bind_row(c, 0, tile * kWgThreads + (tid & (kWgThreads - 1)));
-      run_ops<true>(c);
-    }
+  Ctx<1, kThreads, TcMlp> c(a, slots, tid);
+  const int wg = warp >> 2;
+  const uint32_t col = tmem_base + static_cast<uint32_t>(wg * kColsPerWg);
+  const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  c.tc.m_d = col + kColD;
+  c.tc.m_ahi = col + kColAhi;
+  c.tc.m_alo = col + kColAlo;
+  c.tc.t_d = c.tc.m_d + lane_base;
+  c.tc.t_ahi = c.tc.m_ahi + lane_base;
+  c.tc.t_alo = c.tc.m_alo + lane_base;
+  c.tc.wbuf = wbuf;
+  c.tc.wbuf_ptr = smem_raw + kCtrlBytes;
+  c.tc.full_bar = full_bar;
+  c.tc.empty_bar = empty_bar;
+  c.tc.mma_bar = mma_bar0 + 8 * wg;
+  c.tc.w_iter = 0;
+  c.tc.mma_phase = 0;
+  c.tc.nbuf = nbuf;
+  c.tc.wg = wg;
+  c.tc.warp_in_wg = warp & 3;
+  c.tc.lane = lane;
+  c.tc.producer = warp == 0;
+  c.tc.p_iter = 0;
+  c.tc.p_total = static_cast<uint32_t>(n_iter) * static_cast<uint32_t>(a.n_tc);
+  c.tc.tc_list = a.tc_list;
+  c.tc.params = a.params;
+  c.tc.n_tc = static_cast<uint32_t>(a.n_tc);
+  for (int64_t it = 0; it < n_iter; ++it) {
+    const int64_t tile = (it * gridDim.x + blockIdx.x) * NWG + wg;
+    bind_row(c, 0, tile * kWgThreads + (tid & (kWgThreads - 1)));
+    run_ops<true>(c);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kConsumerThreads / 32) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 }  // namespace tc

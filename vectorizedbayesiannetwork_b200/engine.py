@@ -3,6 +3,7 @@ device memory and the current stream; every kernel is ours (libvbn_cuda.so)."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -14,6 +15,12 @@ from .plan import Program, Role, compile_schedule
 
 
 KERNEL_EVENTS = None  # set to a list by bench.py to time every schedule-kernel launch
+
+
+def tc_warpgroups() -> int:
+    """128-row warpgroups per CTA of the tensor-core kernel (VBN_TC_WG=4|5)."""
+    n = int(os.environ.get("VBN_TC_WG", "4"))
+    return n if n in (4, 5) else 4
 
 
 def require_cuda(device=None) -> torch.device:
@@ -50,12 +57,16 @@ class DevicePlan:
             self.ops = torch.from_numpy(ops_i32.copy()).to(self.device)
             self.par_slots = torch.from_numpy(program.par_slots.copy()).to(self.device)
             self.params = torch.from_numpy(program.params.copy()).to(self.device)
+            self.tc_list = (torch.from_numpy(program.tc_list.copy()).to(self.device)
+                            if program.tc else None)
             desc = L.ProgramDesc(
                 ops_dev=self.ops.data_ptr(), n_ops=len(program.ops),
                 par_slots_dev=self.par_slots.data_ptr(), n_par_slots=int(self.par_slots.numel()),
                 params_dev=self.params.data_ptr(), n_params=int(self.params.numel()),
                 n_slots=program.n_slots, n_scratch=program.n_scratch,
-                heavy=1 if program.heavy else 0, tc=1 if program.tc else 0,
+                heavy=1 if program.heavy else 0, tc=tc_warpgroups() if program.tc else 0,
+                tc_list_dev=self.tc_list.data_ptr() if program.tc else None,
+                n_tc=int(program.tc_list.shape[0]) if program.tc else 0, reserved=0,
             )
             handle = C.c_void_p()
             L.check(self.lib.vbn_plan_create(C.byref(desc), C.byref(handle)))

@@ -50,6 +50,7 @@ class Program:
     needs_logp: bool
     dims: Dict[str, int] = field(default_factory=dict)
     tc: bool = False                       # ops carry tensor-core MLP images -> tcgen05 kernel
+    tc_list: Optional[np.ndarray] = None   # [n_tc, 2] int32 {image float offset, image bytes}, op order
 
 
 def tensor_cores_enabled() -> bool:
@@ -63,6 +64,7 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
     if use_tc is None:
         use_tc = tensor_cores_enabled()
     any_tc = False
+    tc_list: List[tuple] = []
     order = [n for n in topo if n in roles]
     index = {n: i for i, n in enumerate(order)}
     packed: Dict[str, Optional[Packed]] = {}
@@ -180,6 +182,7 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
                     blob.append(pk.tc_blob.astype(np.float32, copy=False))
                     blob_len += pk.tc_blob.size
                 op["tc"][:] = [1, param_off[tkey], pk.tc_k1, pk.tc_n3]
+                tc_list.append((param_off[tkey], 4 * int(pk.tc_blob.size)))
                 any_tc = True
             op["n_layers"] = pk.n_layers
             op["act"] = pk.act
@@ -234,4 +237,5 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
         needs_logp=needs_logp,
         dims=dims,
         tc=any_tc,
+        tc_list=np.asarray(tc_list, dtype=np.int32).reshape(-1, 2) if any_tc else None,
     )
