@@ -52,6 +52,8 @@ extern "C" {
 #define VBN_F_OUT_LOGP 0x8     /* logp[r]  = log p(x | parents)  (MCM target, CPD.log_prob)  */
 #define VBN_F_SHARED 0x10      /* draw is shared by all queries: noise keyed by s, not (b,s) */
 #define VBN_F_FAST32 0x20      /* MLP has exactly 3 Linear layers with hidden dims [32, 32]    */
+#define VBN_F_LGFAST 0x40      /* LG op with D = 1, Dp <= 4: layer_dim[] holds the float bits of
+                                  {bias, scale, 2 ln scale, var, w0..w3}, aux[] the parent slots  */
 
 /* activations of the MLP CPDs (gaussian_nn.py:16-34) */
 #define VBN_ACT_RELU 0

@@ -46,3 +46,4 @@ inline float fmaf_(float a, float b, float c) { return std::fma(a, b, c); }
 inline int atomicOr(int32_t* p, int v) { int o = *p; *p |= v; return o; }
 using std::min;
 using std::max;
+inline float __int_as_float(int32_t v) { float f; std::memcpy(&f, &v, 4); return f; }

@@ -430,6 +430,45 @@ __device__ __forceinline__ void op_lg(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
   }
 }
 
+// VBN_OP_LG with VBN_F_LGFAST (D = 1, Dp <= 4): parameters and parent slots ride in the op itself
+// (layer_dim[] as float bits: bias, scale, 2 ln scale, var, w0..w3; aux[] = parent slots), so the
+// op costs one round of independent 128-bit loads and no dependent parameter fetches.
+template <int RPT, int NT, class TC>
+__device__ __forceinline__ void op_lg_fast(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
+  const int Dp = op.n_par;
+  const bool sample = (op.flags & VBN_SRC_MASK) == VBN_SRC_SAMPLE;
+  const bool want_lp = (op.flags & (VBN_F_ADD_LOGW | VBN_F_OUT_LOGP)) != 0;
+  float loc[RPT];
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) loc[j] = 0.0f;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    if (p < Dp) {
+      const float w = __int_as_float(op.layer_dim[4 + p]);
+      const int ps = op.aux[p];
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) loc[j] = fmaf(c.slot(ps, j), w, loc[j]);
+    }
+  }
+  const float b = __int_as_float(op.layer_dim[0]);
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) loc[j] += b;  // flat @ W + bias (linear_gaussian.py:180)
+  if (sample) {
+    float eps[RPT];
+    c.draw_normal(op, op.n_off, 0, eps);
+    const float sc = __int_as_float(op.layer_dim[1]);
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) c.slot(op.out_slot, j) = fmaf(eps[j], sc, loc[j]);
+  }
+  if (want_lp) {
+    const float t = __int_as_float(op.layer_dim[2]), v = __int_as_float(op.layer_dim[3]);
+    float acc[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) acc[j] = -0.5f * gauss_term(c.slot(op.out_slot, j), loc[j], v, t);
+    commit_logp(c, op, acc);
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // VBN_OP_GNN: gaussian_nn.py:215-288.
 // params: mean_x[Dp], std_x[Dp], mean_y[D], std_y[D], min_scale, pad4 ; then MLP block
@@ -863,7 +902,13 @@ __device__ __forceinline__ void run_ops(Ctx<RPT, NT, TC>& c) {
       dst[0] = __ldg(src + 0);  // kind, flags, dim, n_par
       dst[1] = __ldg(src + 1);  // out_slot, par_off, param_off, fixed_col
       dst[2] = __ldg(src + 2);  // store_idx, noise_idx, n_off, u_off
-      if (HEAVY && op.kind >= VBN_OP_GNN) {
+      if (op.kind == VBN_OP_LG) {
+        if (op.flags & VBN_F_LGFAST) {
+          dst[4] = __ldg(src + 4);  // bias, scale, 2 ln scale, var
+          dst[5] = __ldg(src + 5);  // w0..w3
+          dst[6] = __ldg(src + 6);  // parent slots
+        }
+      } else if (HEAVY && op.kind >= VBN_OP_GNN) {
         dst[3] = __ldg(src + 3);  // n_layers, act, n_out, k
         dst[6] = __ldg(src + 6);  // aux
         dst[7] = __ldg(src + 7);  // tc
@@ -872,7 +917,9 @@ __device__ __forceinline__ void run_ops(Ctx<RPT, NT, TC>& c) {
     c.gop = a.ops + i;
     load_fixed(c, op);
     switch (op.kind) {
-      case VBN_OP_LG: op_lg(c, op); break;
+      case VBN_OP_LG:
+        if (op.flags & VBN_F_LGFAST) op_lg_fast(c, op); else op_lg(c, op);
+        break;
       case VBN_OP_GNN: if (HEAVY) op_gnn(c, op); break;
       case VBN_OP_MDN: if (HEAVY) op_mdn(c, op); break;
       case VBN_OP_SNN: if (HEAVY) op_snn(c, op); break;

@@ -193,6 +193,16 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
             op["aux"][:] = pk.aux
             if pk.n_layers == 3 and list(pk.layer_dim[:2]) == [32, 32]:
                 flags |= L.F_FAST32
+            if pk.kind == L.OP_LG and d == 1 and pk.n_par <= 4:
+                # params = W[Dp], bias, scale, 2 ln scale, var  (cpds.LinearGaussianCPD._pack)
+                flags |= L.F_LGFAST
+                pv = pk.params.astype(np.float32)
+                emb = np.zeros(8, np.float32)
+                emb[0:4] = pv[pk.n_par : pk.n_par + 4]
+                emb[4 : 4 + pk.n_par] = pv[: pk.n_par]
+                op["layer_dim"][:] = emb.view(np.int32)
+                slots_here = par_slots[len(par_slots) - pk.n_par :] if pk.n_par else []
+                op["aux"][:] = list(slots_here) + [0] * (4 - pk.n_par)
             if r.add_logw:
                 flags |= L.F_ADD_LOGW
                 needs_logw = True
