@@ -53,7 +53,10 @@ extern "C" {
 #define VBN_F_SHARED 0x10      /* draw is shared by all queries: noise keyed by s, not (b,s) */
 #define VBN_F_FAST32 0x20      /* MLP has exactly 3 Linear layers with hidden dims [32, 32]    */
 #define VBN_F_LGFAST 0x40      /* LG op with D = 1, Dp <= 4: layer_dim[] holds the float bits of
-                                  {bias, scale, 2 ln scale, var, w0..w3}, aux[] the parent slots  */
+                                  {bias, scale, 2 ln scale, var, w0..w3}, aux[] =
+                                  {parent slots 0|1<<16, 2|3<<16, out_slot, n_off}               */
+#define VBN_F_LGPLAIN 0x80     /* LGFAST op that is only drawn: Philox, per-row stream, no store,
+                                  no density -- the kernel reads nothing but quads 0,4,5,6      */
 
 /* activations of the MLP CPDs (gaussian_nn.py:16-34) */
 #define VBN_ACT_RELU 0

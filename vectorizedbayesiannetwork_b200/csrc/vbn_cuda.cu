@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -55,7 +56,11 @@ const Shape kShapes[] = {
     make_shape<2, 128, true, 3>(),
     make_shape<1, 128, true, 3>(),
     make_shape<1, 64, true, 1>(),
+    make_shape<2, 256, false, 4>(),
+    make_shape<2, 256, false, 3>(),
     make_shape<2, 256, false, 2>(),
+    make_shape<1, 256, false, 4>(),
+    make_shape<1, 256, false, 6>(),
     make_shape<1, 128, false, 4>(),
     make_shape<1, 64, false, 1>(),
 };
@@ -135,9 +140,11 @@ int32_t vbn_plan_create(const VbnProgramDesc* desc, VbnPlan** out_plan) {
     }
     // does not fit: fall through to the FFMA shapes (the ops keep their FFMA parameter blocks)
   }
+  const char* force = std::getenv("VBN_SHAPE");  // dev knob: force one launch shape by index
   for (int i = 0; i < static_cast<int>(sizeof(kShapes) / sizeof(kShapes[0])); ++i) {
     const Shape& s = kShapes[i];
     if (s.heavy != (desc->heavy ? 1 : 0)) continue;
+    if (force && std::atoi(force) != i) continue;
     const size_t bytes = per_row * s.rpt * s.nt;
     if (bytes > static_cast<size_t>(max_smem)) continue;
     CUDA_TRY(cudaFuncSetAttribute(s.fn, cudaFuncAttributeMaxDynamicSharedMemorySize,

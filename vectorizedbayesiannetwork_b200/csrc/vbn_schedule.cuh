@@ -445,7 +445,7 @@ __device__ __forceinline__ void op_lg_fast(Ctx<RPT, NT, TC>& c, const VbnOp& op)
   for (int p = 0; p < 4; ++p) {
     if (p < Dp) {
       const float w = __int_as_float(op.layer_dim[4 + p]);
-      const int ps = op.aux[p];
+      const int ps = (op.aux[p >> 1] >> (16 * (p & 1))) & 0xFFFF;
 #pragma unroll
       for (int j = 0; j < RPT; ++j) loc[j] = fmaf(c.slot(ps, j), w, loc[j]);
     }
@@ -467,6 +467,35 @@ __device__ __forceinline__ void op_lg_fast(Ctx<RPT, NT, TC>& c, const VbnOp& op)
     for (int j = 0; j < RPT; ++j) acc[j] = -0.5f * gauss_term(c.slot(op.out_slot, j), loc[j], v, t);
     commit_logp(c, op, acc);
   }
+}
+
+// VBN_F_LGPLAIN: an LGFAST op that is simply drawn (Philox, per-row stream, no store, no density).
+// Everything it needs is in quads 0, 4, 5, 6: aux[] = {parent slots 0|1<<16, 2|3<<16, out_slot, n_off}.
+// This is the inner loop of linear-Gaussian chains (BASELINE cfg2) and of the LG half of cfg5.
+template <int RPT, int NT, class TC>
+__device__ __forceinline__ void op_lg_plain(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
+  const int Dp = op.n_par;
+  float loc[RPT];
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) loc[j] = 0.0f;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    if (p < Dp) {
+      const float w = __int_as_float(op.layer_dim[4 + p]);
+      const int ps = (op.aux[p >> 1] >> (16 * (p & 1))) & 0xFFFF;
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) loc[j] = fmaf(c.slot(ps, j), w, loc[j]);
+    }
+  }
+  const float b = __int_as_float(op.layer_dim[0]), sc = __int_as_float(op.layer_dim[1]);
+  const int n_off = op.aux[3], q = n_off >> 2, lane = n_off & 3;
+  if (q != c.rows.cur_nq) {
+    c.rows.cur_nq = q;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) c.rows.ncache[j] = c.normals(j, q, 0u, false);
+  }
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) c.slot(op.aux[2], j) = fmaf(lane4(c.rows.ncache[j], lane), sc, loc[j] + b);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -900,6 +929,14 @@ __device__ __forceinline__ void run_ops(Ctx<RPT, NT, TC>& c) {
       const int4* src = reinterpret_cast<const int4*>(a.ops + i);
       int4* dst = reinterpret_cast<int4*>(&op);
       dst[0] = __ldg(src + 0);  // kind, flags, dim, n_par
+      if (op.flags & VBN_F_LGPLAIN) {
+        dst[4] = __ldg(src + 4);  // bias, scale, 2 ln scale, var
+        dst[5] = __ldg(src + 5);  // w0..w3
+        dst[6] = __ldg(src + 6);  // packed parent slots, out_slot, n_off
+        c.gop = a.ops + i;
+        op_lg_plain(c, op);
+        continue;
+      }
       dst[1] = __ldg(src + 1);  // out_slot, par_off, param_off, fixed_col
       dst[2] = __ldg(src + 2);  // store_idx, noise_idx, n_off, u_off
       if (op.kind == VBN_OP_LG) {

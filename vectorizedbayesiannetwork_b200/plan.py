@@ -64,6 +64,7 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
     if use_tc is None:
         use_tc = tensor_cores_enabled()
     any_tc = False
+    lg_fast_ops: List[int] = []
     tc_list: List[tuple] = []
     order = [n for n in topo if n in roles]
     index = {n: i for i, n in enumerate(order)}
@@ -201,8 +202,12 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
                 emb[0:4] = pv[pk.n_par : pk.n_par + 4]
                 emb[4 : 4 + pk.n_par] = pv[: pk.n_par]
                 op["layer_dim"][:] = emb.view(np.int32)
-                slots_here = par_slots[len(par_slots) - pk.n_par :] if pk.n_par else []
-                op["aux"][:] = list(slots_here) + [0] * (4 - pk.n_par)
+                sl = list(par_slots[len(par_slots) - pk.n_par :] if pk.n_par else []) + [0] * (4 - pk.n_par)
+                if max(sl + [slot_of[n]]) < 65536:
+                    op["aux"][:] = [sl[0] | (sl[1] << 16), sl[2] | (sl[3] << 16), slot_of[n], 0]
+                    lg_fast_ops.append(i)
+                else:
+                    flags &= ~L.F_LGFAST
             if r.add_logw:
                 flags |= L.F_ADD_LOGW
                 needs_logw = True
@@ -219,6 +224,11 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
                 if r.inject:
                     op["noise_idx"] = len(noise)
                     noise.append(n)
+            if flags & L.F_LGFAST:
+                op["aux"][3] = op["n_off"]
+                if (r.src == "sample" and not r.shared and not r.inject and not r.store
+                        and not r.add_logw and not r.out_logp):
+                    flags |= L.F_LGPLAIN
             op["flags"] = flags
             n_scratch = max(n_scratch, pk.scratch)
             heavy = heavy or pk.heavy
