@@ -38,6 +38,8 @@ WORKLOADS = {
              "evidence on last 5 nodes, target n500", 1250, 4096, "importance_sampling"),
     "cfg2": ("cfg2: 50-node linear_gaussian chain, importance_sampling, evidence x49, target x25",
              64, 1_000_000, "importance_sampling"),
+    "cfg4": ("cfg4: kde CPD p->y with 200k stored points, CPDHandle.log_prob over 1M query rows", 1_000_000, 1,
+             "kde_log_prob"),
     "cfg3": ("cfg3: ALARM (37 nodes) softmax_nn discrete CPDs, likelihood_weighting, 4 evidence nodes, "
              "target LVFAILURE", 4096, 16384, "likelihood_weighting"),
 }
@@ -163,11 +165,169 @@ def measure_fma_peak(dev) -> dict:
     return out
 
 
+def measure_tf32_peak(dev) -> float:
+    """Measured dense tcgen05 kind::tf32 peak (TFLOP/s) with our probe kernel (one CTA per SM)."""
+    from vectorizedbayesiannetwork_b200 import _lib as L
+
+    lib = L.load()
+    with torch.cuda.device(dev):
+        scratch = torch.zeros(4, device=dev)
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        st = torch.cuda.current_stream().cuda_stream
+        L.check(lib.vbn_tf32_peak(256, sms, scratch.data_ptr(), st))
+        best = 0.0
+        iters = 20000
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            L.check(lib.vbn_tf32_peak(iters, sms, scratch.data_ptr(), st))
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, 2.0 * 128 * 256 * 8 * iters * sms / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return round(best, 1)
+
+
+def kde_inputs(n_rows: int):
+    g = torch.Generator().manual_seed(1)
+    return torch.randn(n_rows, 1, generator=g), torch.randn(n_rows, 1, generator=g)
+
+
+def run_kde(args, rank: int, local_rank: int, world: int) -> None:
+    """cfg4: conditional KDE density over query rows (rows sharded across ranks, no collective)."""
+    import torch.distributed as dist
+
+    import vectorizedbayesiannetwork_b200 as V
+    from vectorizedbayesiannetwork_b200 import _lib as L
+    from vectorizedbayesiannetwork_b200 import synthetic as S
+
+    desc, rows_rank, _, method = WORKLOADS["cfg4"]
+    if args.queries_per_gpu:
+        rows_rank = args.queries_per_gpu
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n_points = args.samples or 200_000
+    spec = S.kde_pair(n_points)
+    model = V.VBN.from_spec(spec, device=dev)
+    handle = model.get_cpd("y")
+    x_h, p_h = kde_inputs(rows_rank * world)
+    x_h, p_h = x_h[rank * rows_rank:(rank + 1) * rows_rank], p_h[rank * rows_rank:(rank + 1) * rows_rank]
+    x_d, p_d = x_h.to(dev), p_h.to(dev)
+    x_p, p_p = x_h.pin_memory(), p_h.pin_memory()
+    out_h = torch.empty(rows_rank, 1).pin_memory()
+    args.warmup = max(args.warmup, 3)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        handle.log_prob(x_d, p_d)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = L.launch_count()
+    barrier()
+    ev = []
+    for _ in range(args.steps):  # inputs (8 MB) + stored points (1.6 MB) are L2-sized; the kernel is MUFU bound
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        handle.log_prob(x_d, p_d)
+        e1.record()
+        ev.append((e0, e1))
+    barrier()
+    launches = L.launch_count() - l0
+    clock_info = clocks.stop() if rank == 0 else None
+    tot = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], device=dev, dtype=torch.float64)
+    ev2 = []
+    for _ in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lp = handle.log_prob(x_p.to(dev, non_blocking=True), p_p.to(dev, non_blocking=True))
+        out_h.copy_(lp, non_blocking=True)
+        e1.record()
+        ev2.append((e0, e1))
+    barrier()
+    tot2 = torch.tensor([sum(a.elapsed_time(b) for a, b in ev2)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot2, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    sec = float(tot.item()) * 1e-3
+    rows_total = rows_rank * world
+    value = rows_total * args.steps / sec
+    pairs_per_s = rows_rank * n_points * args.steps / sec  # per GPU
+    sm_mhz = (clock_info or {}).get("sm_mhz") or 1965.0
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    mufu_peak = 16 * sms * sm_mhz * 1e6  # ex2/s
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = kde_cpu_baseline(n_points)
+    line = {
+        "metric": "density_rows_per_sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "method": method, "rows_per_gpu": rows_rank, "rows_total": rows_total,
+                   "stored_points": n_points, "sharding": "rows" if world > 1 else "none",
+                   "l2": "working set (9.6 MB) is L2 resident by nature; kernel is MUFU bound, no flush needed"},
+        "pair_evals_per_sec_per_gpu": pairs_per_s,
+        "e2e": {"value": rows_total * args.steps / (float(tot2.item()) * 1e-3), "unit": "rows/s",
+                "h2d_bytes_per_step": 8 * rows_rank, "d2h_bytes_per_step": 4 * rows_rank},
+        "gpu_launches": launches, "clocks": clock_info,
+        "roofline": {"bound": "mufu", "achieved": round(2 * pairs_per_s / 1e12, 4), "peak": round(mufu_peak / 1e12, 4),
+                     "unit": "Tex2/s", "frac": round(2 * pairs_per_s / mufu_peak, 4), "traffic": None,
+                     "peak_source": "16 MUFU/clk/SM x SMs x median SM clock during the run (SURVEY 8d: KDE is "
+                                    "exp-limited at small dims; 2 ex2 per (row, point) pair)",
+                     "kernel": "vbn::kde_log_prob_kernel<1,1>"},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kde_cpu_baseline(n_points: int, rows: int = 2048) -> dict:
+    from oracle import vbn_oracle as O
+    from vectorizedbayesiannetwork_b200 import synthetic as S
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    c = S.kde_pair(n_points)["cpds"]["y"]
+    x, p = kde_inputs(rows)
+    O.kde_log_prob(c, x[:512], p[:512])
+    t0 = time.perf_counter()
+    O.kde_log_prob(c, x, p)
+    dt = time.perf_counter() - t0
+    return {"value": rows / dt, "unit": "rows/s", "cores": cores, "kind": "port",
+            "sample": f"{rows} query rows x {n_points} stored points (cost is linear in rows)"}
+
+
 def run_reference(args, rank: int, world: int) -> None:
     """CPU arm: the oracle port of the reference on the host cores, bounded sample per step."""
     if rank != 0:
         return
     from oracle import vbn_oracle as O
+
+    if args.workload == "cfg4":
+        n_points = args.samples or 200_000
+        rows = 2048
+        best = None
+        for _ in range(max(args.steps, 1)):
+            b = kde_cpu_baseline(n_points, rows)
+            best = b if best is None or b["value"] > best["value"] else best
+        line = {"impl": "reference", "metric": "density_rows_per_sec", "value": best["value"], "unit": "rows/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": 1, "ms_per_step": rows / best["value"] * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOADS["cfg4"][0], "sample": best["sample"]}, "cpu_baseline": best,
+                "e2e": {"value": best["value"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
 
     desc, b_rank, s, method = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
@@ -217,6 +377,10 @@ def main() -> None:
 
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "cfg4":
+        assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+        run_kde(args, rank, local_rank, world)
         return
 
     import torch.distributed as dist
@@ -336,22 +500,42 @@ def main() -> None:
         pass
     hbm_peak = measured.get("hbm_gbs", 6650.0)
     heavy = plan.program.heavy
-    if heavy:
+    traffic = None
+    try:  # DRAM bytes of the dominant kernel from the committed ncu capture, scaled to this launch's rows
+        cap = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload)
+        if cap:
+            traffic = {"bytes_per_launch": round(cap["dram_bytes"] * rows / cap["rows"]),
+                       "source": f"ncu --set full capture at {cap['rows']} rows ({cap['file']}), scaled by rows"}
+    except Exception:
+        pass
+    if plan.program.tc:
+        achieved = work["flops_per_row"] * rows / (k_avg_ms * 1e-3) / 1e12
+        tf32_peak = measure_tf32_peak(dev)
+        roofline = {"bound": "tensor", "achieved": round(achieved, 3), "peak": tf32_peak, "unit": "TFLOP/s",
+                    "frac": round(achieved / tf32_peak, 4), "traffic": traffic,
+                    "peak_source": "tcgen05 kind::tf32 probe kernel measured in this run (MEASURED_PEAKS.json has "
+                                   "only the bf16 figure; the MLP layers run as 3xTF32 for fp32 parity)",
+                    "note": "achieved = ALGORITHMIC flops (2*MAC of every affine map); the tensor pipe executes 3x "
+                            "that (3xTF32 split) on padded tiles (K>=8, N>=16). MMA tiles are 128x32x8, so the kernel "
+                            "is bound by the per-row epilogue instruction issue, not by the tensor pipe",
+                    "fp32_fma_peak_tflops": max(peaks.values()),
+                    "frac_of_fp32_fma_peak": round(achieved / max(peaks.values()), 4)}
+    elif heavy:
         achieved = work["flops_per_row"] * rows / (k_avg_ms * 1e-3) / 1e12
         peak = max(peaks.values())
         roofline = {"bound": "fp32_fma", "achieved": round(achieved, 3), "peak": peak, "unit": "TFLOP/s",
-                    "frac": round(achieved / peak, 4), "traffic": None,
+                    "frac": round(achieved / peak, 4), "traffic": traffic,
                     "peak_source": "FFMA/FFMA2 probe kernel measured in this run (MEASURED_PEAKS.json has no fp32 "
                                    "figure; SURVEY 8d: FFMA path -> measured FP32 FMA peak)",
                     "fma_peaks_tflops": peaks}
     else:
         achieved = work["level_bytes_per_row"] * rows / (k_avg_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
-                    "frac": round(achieved / hbm_peak, 4), "traffic": None,
+                    "frac": round(achieved / hbm_peak, 4), "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if measured else "fallback 6650",
                     "note": "algorithmic bytes = SURVEY 8(d) per-level SoA formula; the fused kernel keeps node "
                             "columns in shared memory, so real DRAM traffic is only the stored columns"}
-    roofline.update({"kernel": "vbn::schedule_kernel", "kernel_ms_avg": round(k_avg_ms, 4),
+    roofline.update({"kernel": "vbn::tc::schedule_tc_kernel" if plan.program.tc else "vbn::schedule_kernel", "kernel_ms_avg": round(k_avg_ms, 4),
                      "kernel_launches_timed": len(kernel_ms), "rows_per_launch": rows,
                      "flops_per_row": work["flops_per_row"], "level_bytes_per_row": work["level_bytes_per_row"],
                      "kernel_share_of_step": round(sum(kernel_ms) / sum(step_ms), 4)})

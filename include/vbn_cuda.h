@@ -217,6 +217,11 @@ int32_t vbn_philox_fill(const uint32_t* ctr_dev, int64_t n, uint32_t key0, uint3
  * flops = 2 * 16 * iters * 256 * n_blocks.  scratch_dev: >= 1 float. */
 int32_t vbn_fma_peak(int32_t mode, int32_t iters, int32_t n_blocks, float* scratch_dev, void* stream);
 
+/* Bench-only probe of the tensor pipe in the mode the MLP layers use (tcgen05.mma kind::tf32, A in
+ * TMEM): n_blocks CTAs (one per SM) each issue `iters` M=128 N=256 K=8 MMAs.
+ * flops = 2 * 128 * 256 * 8 * iters * n_blocks.  scratch_dev: >= 1 float. */
+int32_t vbn_tf32_peak(int32_t iters, int32_t n_blocks, float* scratch_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -115,6 +115,7 @@ int32_t vbn_kde_log_prob(const float* tp, const float* ty, int64_t N, int32_t dp
   return 0;
 }
 int32_t vbn_fma_peak(int32_t, int32_t, int32_t, float*, void*) { return 0; }
+int32_t vbn_tf32_peak(int32_t, int32_t, float*, void*) { return 0; }
 int32_t vbn_philox_fill(const uint32_t* ctr, int64_t n, uint32_t k0, uint32_t k1, uint32_t* out, void*) {
   for (int64_t i = 0; i < n; ++i) {
     const uint4 r = vbn::philox4x32_10(make_uint4(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3]), make_uint2(k0, k1));

@@ -74,6 +74,7 @@ EXPORTS = {
                                      C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float,
                                      C.c_float, C.c_void_p, C.c_void_p]),
     "vbn_fma_peak": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "vbn_tf32_peak": (C.c_int32, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "vbn_philox_fill": (C.c_int32, [C.c_void_p, C.c_int64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
 }
 

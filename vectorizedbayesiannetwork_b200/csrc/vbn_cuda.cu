@@ -307,4 +307,11 @@ int32_t vbn_fma_peak(int32_t mode, int32_t iters, int32_t n_blocks, float* scrat
   return VBN_OK;
 }
 
+int32_t vbn_tf32_peak(int32_t iters, int32_t n_blocks, float* scratch_dev, void* stream) {
+  if (!scratch_dev || iters <= 0 || n_blocks <= 0) return fail(VBN_E_INVALID, "bad argument");
+  vbn::tc::tf32_peak_kernel<<<n_blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(iters, scratch_dev);
+  CUDA_TRY(cudaGetLastError());
+  return VBN_OK;
+}
+
 }  // extern "C"
