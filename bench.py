@@ -94,50 +94,67 @@ def algorithmic_work(program) -> dict:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
-
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md) through NVML in a
+    background thread (an `nvidia-smi -lms` child process perturbs short steps: its polling stalled
+    launches by tens of ms); falls back to one nvidia-smi query if NVML is unavailable."""
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
-        self.proc = None
+        self.sm, self.reasons = [], set()
+        self.sm_max = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml as N
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            N.nvmlInit()
+            self._nvml = N
+            # honour CUDA_VISIBLE_DEVICES-less boxes: device index == NVML index here (one box, all GPUs visible)
+            self._h = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = float(N.nvmlDeviceGetMaxClockInfo(self._h, N.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        except Exception:
+            self._nvml = None
+
+    def _loop(self):
+        N = self._nvml
+        names = {
+            getattr(N, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(N, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(N, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(N, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(N.nvmlDeviceGetClockInfo(self._h, N.NVML_CLOCK_SM)))
+                try:
+                    mask = N.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    mask = N.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, nm in names.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
-            parts = [p.strip() for p in r.split(",")]
-            if len(parts) < 8:
-                continue
+        if self._nvml is None:
             try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, parts[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=20).stdout
+                a, b = [float(x) for x in out.strip().split(",")]
+                return {"sm_mhz": a, "sm_max_mhz": b, "reasons": [], "samples": 1, "source": "nvidia-smi after the run"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        self._stop.set()
+        self._thread.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "NVML, 50 ms period"}
 
 
 def measure_fma_peak(dev) -> dict:
@@ -369,6 +386,9 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--queries-per-gpu", type=int, default=None)
     ap.add_argument("--samples", type=int, default=None)
+    ap.add_argument("--shard", default="queries", choices=["queries", "samples"],
+                    help="multi-GPU split: queries (weak scaling, no data-path collective) or samples "
+                         "(strong scaling of a fixed B x S job; per-query (m,l,q) all-gather over NCCL)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -403,9 +423,10 @@ def main() -> None:
         b_rank = args.queries_per_gpu
     if args.samples:
         s = args.samples
-    b_total = b_rank * world
+    by_samples = args.shard == "samples" and world > 1
+    b_total = b_rank if by_samples else b_rank * world
     spec, target, evidence_host = build_workload(args.workload, b_total)
-    shard = V.Shard("queries", rank, world) if world > 1 else None
+    shard = V.Shard(args.shard, rank, world) if world > 1 else None
     model = V.VBN.from_spec(spec, device=dev)
     model.set_inference_method(method, n_samples=s)
     evidence_dev = {k: v.to(dev) for k, v in evidence_host.items()}
@@ -455,8 +476,9 @@ def main() -> None:
     value = b_total * s * args.steps / total_s
 
     # ---- end-to-end: host evidence in, host (weights, samples) out --------------------------
-    out_w = torch.empty(b_rank, s, dtype=torch.float32).pin_memory()
-    out_s = torch.empty(b_rank, s, 1, dtype=torch.float32).pin_memory()
+    s_rank = shard.local_samples(s)[0] if by_samples else s
+    out_w = torch.empty(b_rank, s_rank, dtype=torch.float32).pin_memory()
+    out_s = torch.empty(b_rank, s_rank, 1, dtype=torch.float32).pin_memory()
     h2d = sum(v.numel() * 4 for v in evidence_pinned.values())
     d2h = out_w.numel() * 4 + out_s.numel() * 4
 
@@ -490,7 +512,7 @@ def main() -> None:
     # ---- roofline of the dominant kernel (the fused schedule kernel) -------------------------
     plan = next(iter(model._inference._runner._cache.values()))
     work = algorithmic_work(plan.program)
-    rows = b_rank * s
+    rows = b_rank * s_rank
     k_avg_ms = sum(kernel_ms) / max(len(kernel_ms), 1)
     peaks = measure_fma_peak(dev)
     measured = {}
@@ -554,9 +576,10 @@ def main() -> None:
     line = {
         "metric": "posterior_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_s / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if by_samples else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "method": method, "queries_per_gpu": b_rank, "queries_total": b_total,
-                   "samples_per_query": s, "sharding": "queries" if world > 1 else "none",
+                   "samples_per_query": s, "sharding": args.shard if world > 1 else "none",
                    "l2": "256 MB buffer rewritten between timed steps (L2 flush)",
                    "is_fallback_steps": fallbacks, "weights": "random-init (nn.Linear default), seeded"},
         "queries_per_sec": b_total * args.steps / total_s,
