@@ -55,6 +55,12 @@ extern "C" {
 #define VBN_F_LGFAST 0x40      /* LG op with D = 1, Dp <= 4: layer_dim[] holds the float bits of
                                   {bias, scale, 2 ln scale, var, w0..w3}, aux[] =
                                   {parent slots 0|1<<16, 2|3<<16, out_slot, n_off}               */
+#define VBN_F_PAR4 0x100       /* GNN / MDN op with <= 4 parent dims: aux[1] = slots 0|1<<16,
+                                  aux[2] = slots 2|3<<16 (no par_slots[] lookup); aux[0] = float
+                                  bits of min_scale                                            */
+#define VBN_F_MDNPLAIN 0x200   /* MDN op, D = 1, 2 <= K <= 5, PAR4, tensor-core MLP, that is only
+                                  drawn (Philox, per-row stream, no density): register-resident
+                                  tail in the tcgen05 kernel; ignored by the FP32-pipe kernel   */
 #define VBN_F_LGPLAIN 0x80     /* LGFAST op that is only drawn: Philox, per-row stream, no store,
                                   no density -- the kernel reads nothing but quads 0,4,5,6      */
 

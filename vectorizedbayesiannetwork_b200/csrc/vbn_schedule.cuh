@@ -551,6 +551,12 @@ __device__ __forceinline__ void op_gnn(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
 // ---------------------------------------------------------------------------------------
 template <int RPT, int NT, class TC>
 __device__ __forceinline__ void op_mdn(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
+  if constexpr (TC::kEnabled) {
+    if (op.flags & VBN_F_MDNPLAIN) {  // drawn-only node with a tensor-core MLP: register-resident tail
+      c.tc.mdn_plain(c, op);
+      return;
+    }
+  }
   const float* P = c.a.params + op.param_off;
   const int D = op.dim, K = op.k;
   const float min_scale = __ldg(P);

@@ -194,7 +194,7 @@ __device__ __forceinline__ void issue_layer(uint32_t d, uint32_t a_hi, uint32_t 
   const uint32_t sbo = static_cast<uint32_t>(KS) * 256u;
   const uint64_t dhi = make_b_desc(b_hi, 128u, sbo), dlo = make_b_desc(b_lo, 128u, sbo);
 #pragma unroll
-  for (int s = 0; s < KS; ++s) mma_tf32_ts(d, a_lo + 8 * s, dhi + 16 * s, idesc, s > 0 ? 1u : 0u);
+  for (int s = 0; s < KS; ++s) mma_tf32_ts(d, a_lo + 8 * s, dhi + 16 * s, idesc, 1u);  // D holds the bias
 #pragma unroll
   for (int s = 0; s < KS; ++s) mma_tf32_ts(d, a_hi + 8 * s, dlo + 16 * s, idesc, 1u);
 #pragma unroll
@@ -264,8 +264,26 @@ struct TcMlp {
     tc_fence_after();
   }
 
-  // D (32 fp32 columns) -> bias + activation -> 3xTF32 split -> A_hi / A_lo
-  __device__ __forceinline__ void hidden_epilogue(const float* bias, int act) {
+  // D <- bias (identical for every row).  Every MMA of the layer then accumulates, so the
+  // epilogues carry no bias add.  Completion is covered by the tmem_wait_st() before the barrier.
+  __device__ __forceinline__ void preload_bias(const float* bias, int n) {
+    for (int o0 = 0; o0 < n; o0 += 16) {
+      uint32_t b[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(bias + o0 + 4 * q);
+        b[4 * q + 0] = __float_as_uint(t.x);
+        b[4 * q + 1] = __float_as_uint(t.y);
+        b[4 * q + 2] = __float_as_uint(t.z);
+        b[4 * q + 3] = __float_as_uint(t.w);
+      }
+      tmem_st16(t_d + o0, b);
+    }
+  }
+
+  // D (32 fp32 columns, bias included) -> activation -> 3xTF32 split -> A_hi / A_lo; then D <- the
+  // next layer's bias
+  __device__ __forceinline__ void hidden_epilogue(int act, const float* next_bias, int next_n) {
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       uint32_t v[16], hi[16], lo[16];
@@ -273,28 +291,22 @@ struct TcMlp {
       tmem_wait_ld();
       if (act == VBN_ACT_RELU) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 b = *reinterpret_cast<const float4*>(bias + 16 * half + 4 * q);
-          split_tf32(fmaxf(__uint_as_float(v[4 * q + 0]) + b.x, 0.0f), hi[4 * q + 0], lo[4 * q + 0]);
-          split_tf32(fmaxf(__uint_as_float(v[4 * q + 1]) + b.y, 0.0f), hi[4 * q + 1], lo[4 * q + 1]);
-          split_tf32(fmaxf(__uint_as_float(v[4 * q + 2]) + b.z, 0.0f), hi[4 * q + 2], lo[4 * q + 2]);
-          split_tf32(fmaxf(__uint_as_float(v[4 * q + 3]) + b.w, 0.0f), hi[4 * q + 3], lo[4 * q + 3]);
-        }
+        for (int q = 0; q < 16; ++q) split_tf32(fmaxf(__uint_as_float(v[q]), 0.0f), hi[q], lo[q]);
       } else {
 #pragma unroll
-        for (int q = 0; q < 16; ++q)
-          split_tf32(activate(__uint_as_float(v[q]) + bias[16 * half + q], act), hi[q], lo[q]);
+        for (int q = 0; q < 16; ++q) split_tf32(activate_slow(__uint_as_float(v[q]), act), hi[q], lo[q]);
       }
       tmem_st16(t_ahi + 16 * half, hi);
       tmem_st16(t_alo + 16 * half, lo);
     }
+    preload_bias(next_bias, next_n);
     tmem_wait_st();
   }
 
-  // Evaluates the op's MLP for this thread's row; outputs land in scratch rows 0..n_out-1 like
-  // the FFMA paths (mlp_fast32 / mlp_generic).
+  // The three layers of the op's MLP for this thread's row.  On return D holds the N3 outputs
+  // (bias included) and the weight buffer has been released.
   template <class C>
-  __device__ __forceinline__ void mlp(C& c, const VbnOp& op, const float* norm, const int32_t* par) {
+  __device__ __forceinline__ void layers(C& c, const VbnOp& op, const float* norm, const int32_t* par) {
     const int k1 = op.tc[2], n3 = op.tc[3];
     const int dp = op.n_par;
     if (producer) {  // warp-uniform
@@ -312,45 +324,133 @@ struct TcMlp {
     const float* bias = reinterpret_cast<const float*>(wbuf_ptr + (w3lo + n3 * kHidden * 4 - wbuf));
 
     // ---- inputs -> A (K1 columns, zero padded); gaussian_nn standardises them first
-    for (int k0 = 0; k0 < k1; k0 += 8) {
+    if (op.flags & VBN_F_PAR4) {  // <= 4 parent dims, slots packed in aux[1..2]: K1 == 8
       uint32_t hi[8], lo[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int p = k0 + q;
+      for (int q = 0; q < 4; ++q) {
         float z = 0.0f;
-        if (p < dp) {
-          z = c.slot(__ldg(par + p), 0);
-          if (norm) z = __fdiv_rn(z - __ldg(norm + p), __ldg(norm + dp + p));
+        if (q < dp) {
+          z = c.slot((op.aux[1 + (q >> 1)] >> (16 * (q & 1))) & 0xFFFF, 0);
+          if (norm) z = __fdiv_rn(z - __ldg(norm + q), __ldg(norm + dp + q));
         }
         split_tf32(z, hi[q], lo[q]);
       }
-      tmem_st8(t_ahi + k0, hi);
-      tmem_st8(t_alo + k0, lo);
+#pragma unroll
+      for (int q = 4; q < 8; ++q) hi[q] = lo[q] = 0u;
+      tmem_st8(t_ahi, hi);
+      tmem_st8(t_alo, lo);
+    } else {
+      for (int k0 = 0; k0 < k1; k0 += 8) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int p = k0 + q;
+          float z = 0.0f;
+          if (p < dp) {
+            z = c.slot(__ldg(par + p), 0);
+            if (norm) z = __fdiv_rn(z - __ldg(norm + p), __ldg(norm + dp + p));
+          }
+          split_tf32(z, hi[q], lo[q]);
+        }
+        tmem_st8(t_ahi + k0, hi);
+        tmem_st8(t_alo + k0, lo);
+      }
     }
-    tmem_wait_st();
     mbar_wait(full_bar + 8 * buf, ph);  // weights + biases of this op have landed
+    preload_bias(bias, kHidden);
+    tmem_wait_st();
 
     run_layer(w1hi, w1lo, k1, kHidden);
-    hidden_epilogue(bias, op.act);
+    hidden_epilogue(op.act, bias + kHidden, kHidden);
     run_layer(w2hi, w2lo, kHidden, kHidden);
-    hidden_epilogue(bias + kHidden, op.act);
+    hidden_epilogue(op.act, bias + 2 * kHidden, n3);
     run_layer(w3hi, w3lo, kHidden, n3);
 
-    // ---- outputs -> scratch
-    const float* b3 = bias + 2 * kHidden;
-    const int n_out = op.n_out;
+    // this warp is done with the weight buffer (its MMAs completed, biases consumed)
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar + 8 * buf);
+    ++w_iter;
+  }
+
+  // Generic consumer: outputs land in scratch rows 0..n_out-1 like the FFMA paths
+  // (mlp_fast32 / mlp_generic), for op_gnn / op_mdn / op_snn to pick up.
+  template <class C>
+  __device__ __forceinline__ void mlp(C& c, const VbnOp& op, const float* norm, const int32_t* par) {
+    layers(c, op, norm, par);
+    const int n3 = op.tc[3], n_out = op.n_out;
     for (int o0 = 0; o0 < n3; o0 += 16) {
       uint32_t v[16];
       tmem_ld16(t_d + o0, v);
       tmem_wait_ld();
 #pragma unroll
       for (int q = 0; q < 16; ++q)
-        if (o0 + q < n_out) c.scr(o0 + q, 0) = __uint_as_float(v[q]) + b3[o0 + q];
+        if (o0 + q < n_out) c.scr(o0 + q, 0) = __uint_as_float(v[q]);
     }
-    // this warp is done with the weight buffer (its MMAs completed, biases read)
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty_bar + 8 * buf);
-    ++w_iter;
+  }
+
+  // VBN_F_MDNPLAIN: an MDN node (D = 1, K <= 5 components, <= 4 parent dims) that is only drawn
+  // (mdn.py:209-235).  MLP outputs stay in registers: logits[K], then per component (loc, raw scale).
+  template <int K, class C>
+  __device__ __forceinline__ void mdn_tail(C& c, const VbnOp& op, const uint32_t (&v)[16]) {
+    float q[K];
+    float mx = __uint_as_float(v[0]);
+#pragma unroll
+    for (int k = 1; k < K; ++k) mx = fmaxf(mx, __uint_as_float(v[k]));
+    float se = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      q[k] = expf(__uint_as_float(v[k]) - mx);
+      se += q[k];
+    }
+    // pi = softmax.clamp_min(1e-5) / sum (mdn.py:227-228); k ~ Categorical(pi) by inverse CDF on
+    // the un-normalised clamped weights with u scaled by their sum
+    const float inv = __frcp_rn(se);
+    float tot = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      q[k] = fmaxf(q[k] * inv, 1e-5f);
+      tot += q[k];
+    }
+    tot = fmaxf(tot, 1e-12f);
+    const int uq = op.u_off >> 2;
+    if (uq != c.rows.cur_uq) {
+      c.rows.cur_uq = uq;
+      c.rows.ucache[0] = c.uniforms(0, uq, 1u, false);
+    }
+    const float u = lane4(c.rows.ucache[0], op.u_off & 3) * tot;
+    float cum = 0.0f;
+    float loc = __uint_as_float(v[K + 2 * (K - 1)]), raw = __uint_as_float(v[K + 2 * (K - 1) + 1]);
+#pragma unroll
+    for (int k = 0; k < K - 1; ++k) {
+      const float before = cum;
+      cum += q[k];
+      if (u >= before && u < cum) {
+        loc = __uint_as_float(v[K + 2 * k]);
+        raw = __uint_as_float(v[K + 2 * k + 1]);
+      }
+    }
+    const int nq = op.n_off >> 2;
+    if (nq != c.rows.cur_nq) {
+      c.rows.cur_nq = nq;
+      c.rows.ncache[0] = c.normals(0, nq, 0u, false);
+    }
+    const float eps = lane4(c.rows.ncache[0], op.n_off & 3);
+    const float sc = softplus20(raw) + __int_as_float(op.aux[0]);
+    c.slot(op.out_slot, 0) = fmaf(eps, sc, loc);
+  }
+
+  template <class C>
+  __device__ __forceinline__ void mdn_plain(C& c, const VbnOp& op) {
+    layers(c, op, nullptr, nullptr);
+    uint32_t v[16];
+    tmem_ld16(t_d, v);
+    tmem_wait_ld();
+    switch (op.k) {
+      case 2: mdn_tail<2>(c, op, v); break;
+      case 3: mdn_tail<3>(c, op, v); break;
+      case 4: mdn_tail<4>(c, op, v); break;
+      default: mdn_tail<5>(c, op, v); break;
+    }
   }
 };
 

@@ -224,6 +224,16 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
                 if r.inject:
                     op["noise_idx"] = len(noise)
                     noise.append(n)
+            if pk.kind in (L.OP_GNN, L.OP_MDN) and 0 < pk.n_par <= 4 and pk.n_layers > 0:
+                sl = list(par_slots[len(par_slots) - pk.n_par :]) + [0] * (4 - pk.n_par)
+                if max(sl) < 65536:
+                    flags |= L.F_PAR4
+                    op["aux"][:] = [int(np.float32(cpds[n].min_scale).view(np.int32)),
+                                    sl[0] | (sl[1] << 16), sl[2] | (sl[3] << 16), 0]
+                    if (pk.kind == L.OP_MDN and int(op["tc"][0]) and d == 1 and 2 <= pk.k <= 5
+                            and r.src == "sample" and not r.shared and not r.inject
+                            and not r.add_logw and not r.out_logp):
+                        flags |= L.F_MDNPLAIN
             if flags & L.F_LGFAST:
                 op["aux"][3] = op["n_off"]
                 if (r.src == "sample" and not r.shared and not r.inject and not r.store
