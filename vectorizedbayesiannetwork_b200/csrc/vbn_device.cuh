@@ -106,6 +106,15 @@ struct Lse {
       l += __expf(x - m);
     }
   }
+  __device__ __forceinline__ void merge(const Lse& o) {
+    if (o.m == -CUDART_INF_F) return;
+    if (o.m > m) {
+      l = l * __expf(m - o.m) + o.l;
+      m = o.m;
+    } else {
+      l += o.l * __expf(o.m - m);
+    }
+  }
   __device__ __forceinline__ float value() const { return m + logf(l); }
 };
 

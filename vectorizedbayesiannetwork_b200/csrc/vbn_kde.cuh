@@ -20,8 +20,85 @@ namespace vbn {
 constexpr int kKdeTile = 1024;  // stored points per shared-memory tile
 constexpr int kKdeThreads = 128;
 constexpr int kKdeQpt = 4;      // query rows per thread
-constexpr int kKdeChunk = 4;    // points per online-max step
+constexpr int kKdeChunk = 4;    // points per online-max step (two packed pairs)
 
+// ---- packed fp32x2 arithmetic (sm_100a: one FMA-pipe issue slot does two lanes' worth) ----------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// One online (max, sum) accumulator, two-level: `cur` (packed pair) collects the current tile,
+// `tot` the finished tiles, so the fp32 error grows with sqrt(tile) + sqrt(#tiles) instead of
+// sqrt(N) (200 000 sequential adds cost ~3e-5 relative, which fails the 1e-5 parity).
+struct KdeAcc {
+  float m, tot;
+  f32x2 cur;
+  __device__ __forceinline__ void init() {
+    m = -CUDART_INF_F;
+    tot = 0.0f;
+    cur = pack2(0.0f, 0.0f);
+  }
+  // v0, v1: four log2-domain terms (two packed pairs)
+  __device__ __forceinline__ void push4(f32x2 v0, f32x2 v1) {
+    float a, b, c, d;
+    unpack2(v0, a, b);
+    unpack2(v1, c, d);
+    const float mx = fmaxf(fmaxf(a, b), fmaxf(c, d));
+    if (mx > m) {
+      const float sc = ex2_approx(m - mx);  // exp2(-inf) = 0 on the first chunk
+      tot *= sc;
+      cur = mul2(cur, pack2(sc, sc));
+      m = mx;
+    }
+    const f32x2 mm = pack2(m, m);
+    unpack2(sub2(v0, mm), a, b);
+    unpack2(sub2(v1, mm), c, d);
+    cur = add2(cur, pack2(ex2_approx(a), ex2_approx(b)));
+    cur = add2(cur, pack2(ex2_approx(c), ex2_approx(d)));
+  }
+  __device__ __forceinline__ void end_tile() {
+    float a, b;
+    unpack2(cur, a, b);
+    tot += a + b;
+    cur = pack2(0.0f, 0.0f);
+  }
+  __device__ __forceinline__ float log2_value() const { return m + log2f(tot); }
+};
+
+// Shared-memory tile layout: dimension-major, [d][kKdeTile] floats, so a float2 load fetches the
+// same coordinate of two consecutive points (the two lanes of the packed math).  Tile tails are
+// filled with +inf parents / targets: their terms are exp2(-inf) = 0.
 template <int DP, int DX>
 __global__ void __launch_bounds__(kKdeThreads) kde_log_prob_kernel(
     const float* __restrict__ tp, const float* __restrict__ ty, int64_t n_points,
@@ -29,37 +106,53 @@ __global__ void __launch_bounds__(kKdeThreads) kde_log_prob_kernel(
     float hp2, float hy2, float const_y, float log_n, float* __restrict__ out) {
   // hp2 = 0.5*log2(e)/s_p^2, hy2 = 0.5*log2(e)/s_y^2  (log2 domain)
   constexpr int DPS = DP > 0 ? DP : 1;
-  __shared__ __align__(16) float s_p[2][kKdeTile * DPS];
-  __shared__ __align__(16) float s_y[2][kKdeTile * DX];
+  __shared__ __align__(16) float s_p[2][DPS * kKdeTile];
+  __shared__ __align__(16) float s_y[2][DX * kKdeTile];
 
   const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * kKdeThreads * kKdeQpt) + threadIdx.x;
-  float xp[kKdeQpt][DPS], xy[kKdeQpt][DX];
+  f32x2 xp[kKdeQpt][DPS], xy[kKdeQpt][DX];
 #pragma unroll
   for (int j = 0; j < kKdeQpt; ++j) {
     int64_t r = row0 + static_cast<int64_t>(j) * kKdeThreads;
     if (r >= n_rows) r = n_rows - 1;
 #pragma unroll
-    for (int d = 0; d < DP; ++d) xp[j][d] = __ldg(qp + r * DP + d);
+    for (int d = 0; d < DP; ++d) {
+      const float v = __ldg(qp + r * DP + d);
+      xp[j][d] = pack2(v, v);
+    }
 #pragma unroll
-    for (int d = 0; d < DX; ++d) xy[j][d] = __ldg(qx + r * DX + d);
+    for (int d = 0; d < DX; ++d) {
+      const float v = __ldg(qx + r * DX + d);
+      xy[j][d] = pack2(v, v);
+    }
   }
-  float ma[kKdeQpt], la[kKdeQpt], mc[kKdeQpt], lc[kKdeQpt];
+  KdeAcc den[kKdeQpt], num[kKdeQpt];
 #pragma unroll
   for (int j = 0; j < kKdeQpt; ++j) {
-    ma[j] = mc[j] = -CUDART_INF_F;
-    la[j] = lc[j] = 0.0f;
+    den[j].init();
+    num[j].init();
   }
+  const f32x2 nhp = pack2(-hp2, -hp2), nhy = pack2(-hy2, -hy2);
 
   const int64_t n_tiles = (n_points + kKdeTile - 1) / kKdeTile;
   auto stage = [&](int64_t t, int buf) {
     const int64_t base = t * kKdeTile;
-    const int64_t cnt = n_points - base < kKdeTile ? n_points - base : kKdeTile;
-    // stored points are padded by the host to a multiple of the tile with +inf-distance
-    // sentinels?  No: tails are handled by clamping the copy and masking in the math below.
-    for (int i = threadIdx.x; i < cnt * DP; i += kKdeThreads)
-      __pipeline_memcpy_async(&s_p[buf][i], tp + base * DP + i, sizeof(float));
-    for (int i = threadIdx.x; i < cnt * DX; i += kKdeThreads)
-      __pipeline_memcpy_async(&s_y[buf][i], ty + base * DX + i, sizeof(float));
+    const int cnt = static_cast<int>(n_points - base < kKdeTile ? n_points - base : kKdeTile);
+    for (int i = threadIdx.x; i < kKdeTile; i += kKdeThreads) {
+      if (i < cnt) {
+#pragma unroll
+        for (int d = 0; d < DP; ++d)
+          __pipeline_memcpy_async(&s_p[buf][d * kKdeTile + i], tp + (base + i) * DP + d, sizeof(float));
+#pragma unroll
+        for (int d = 0; d < DX; ++d)
+          __pipeline_memcpy_async(&s_y[buf][d * kKdeTile + i], ty + (base + i) * DX + d, sizeof(float));
+      } else {  // sentinel: infinitely far away
+#pragma unroll
+        for (int d = 0; d < DP; ++d) s_p[buf][d * kKdeTile + i] = CUDART_INF_F;
+#pragma unroll
+        for (int d = 0; d < DX; ++d) s_y[buf][d * kKdeTile + i] = CUDART_INF_F;
+      }
+    }
     __pipeline_commit();
   };
 
@@ -73,83 +166,50 @@ __global__ void __launch_bounds__(kKdeThreads) kde_log_prob_kernel(
       __pipeline_wait_prior(0);
     }
     __syncthreads();
-    const int64_t base = t * kKdeTile;
-    const int cnt = static_cast<int>(n_points - base < kKdeTile ? n_points - base : kKdeTile);
-    const int full = cnt & ~(kKdeChunk - 1);
-    for (int n0 = 0; n0 < full; n0 += kKdeChunk) {
-      float a[kKdeQpt][kKdeChunk], cc[kKdeQpt][kKdeChunk];
+#pragma unroll 2
+    for (int n0 = 0; n0 < kKdeTile; n0 += kKdeChunk) {
+      f32x2 a[kKdeQpt][2], cc[kKdeQpt][2];
 #pragma unroll
-      for (int i = 0; i < kKdeChunk; ++i) {
-        float pv[DPS], yv[DX];
+      for (int i = 0; i < 2; ++i) {
+        f32x2 pv[DPS], yv[DX];
 #pragma unroll
-        for (int d = 0; d < DP; ++d) pv[d] = s_p[buf][(n0 + i) * DP + d];
+        for (int d = 0; d < DP; ++d) pv[d] = *reinterpret_cast<const f32x2*>(&s_p[buf][d * kKdeTile + n0 + 2 * i]);
 #pragma unroll
-        for (int d = 0; d < DX; ++d) yv[d] = s_y[buf][(n0 + i) * DX + d];
+        for (int d = 0; d < DX; ++d) yv[d] = *reinterpret_cast<const f32x2*>(&s_y[buf][d * kKdeTile + n0 + 2 * i]);
 #pragma unroll
         for (int j = 0; j < kKdeQpt; ++j) {
-          float q1 = 0.0f, q2 = 0.0f;
+          f32x2 av = pack2(0.0f, 0.0f);
+          if (DP > 0) {
+            f32x2 df = sub2(xp[j][0], pv[0]);
+            f32x2 q1 = mul2(df, df);
 #pragma unroll
-          for (int d = 0; d < DP; ++d) {
-            const float df = xp[j][d] - pv[d];
-            q1 = fmaf(df, df, q1);
+            for (int d = 1; d < DP; ++d) {
+              df = sub2(xp[j][d], pv[d]);
+              q1 = fma2(df, df, q1);
+            }
+            av = mul2(q1, nhp);
           }
+          f32x2 df = sub2(xy[j][0], yv[0]);
+          f32x2 q2 = mul2(df, df);
 #pragma unroll
-          for (int d = 0; d < DX; ++d) {
-            const float df = xy[j][d] - yv[d];
-            q2 = fmaf(df, df, q2);
+          for (int d = 1; d < DX; ++d) {
+            df = sub2(xy[j][d], yv[d]);
+            q2 = fma2(df, df, q2);
           }
-          a[j][i] = -hp2 * q1;
-          cc[j][i] = fmaf(-hy2, q2, a[j][i]);
+          a[j][i] = av;
+          cc[j][i] = DP > 0 ? fma2(q2, nhy, av) : mul2(q2, nhy);
         }
       }
 #pragma unroll
       for (int j = 0; j < kKdeQpt; ++j) {
-        if (DP > 0) {
-          float mx = fmaxf(fmaxf(a[j][0], a[j][1]), fmaxf(a[j][2], a[j][3]));
-          if (mx > ma[j]) {
-            la[j] *= exp2f(ma[j] - mx);
-            ma[j] = mx;
-          }
-          la[j] += (exp2f(a[j][0] - ma[j]) + exp2f(a[j][1] - ma[j])) +
-                   (exp2f(a[j][2] - ma[j]) + exp2f(a[j][3] - ma[j]));
-        }
-        float mx = fmaxf(fmaxf(cc[j][0], cc[j][1]), fmaxf(cc[j][2], cc[j][3]));
-        if (mx > mc[j]) {
-          lc[j] *= exp2f(mc[j] - mx);
-          mc[j] = mx;
-        }
-        lc[j] += (exp2f(cc[j][0] - mc[j]) + exp2f(cc[j][1] - mc[j])) +
-                 (exp2f(cc[j][2] - mc[j]) + exp2f(cc[j][3] - mc[j]));
+        if (DP > 0) den[j].push4(a[j][0], a[j][1]);
+        num[j].push4(cc[j][0], cc[j][1]);
       }
     }
-    for (int n = full; n < cnt; ++n) {  // tail of the last tile
 #pragma unroll
-      for (int j = 0; j < kKdeQpt; ++j) {
-        float q1 = 0.0f, q2 = 0.0f;
-#pragma unroll
-        for (int d = 0; d < DP; ++d) {
-          const float df = xp[j][d] - s_p[buf][n * DP + d];
-          q1 = fmaf(df, df, q1);
-        }
-#pragma unroll
-        for (int d = 0; d < DX; ++d) {
-          const float df = xy[j][d] - s_y[buf][n * DX + d];
-          q2 = fmaf(df, df, q2);
-        }
-        const float av = -hp2 * q1, cv = fmaf(-hy2, q2, av);
-        if (DP > 0) {
-          if (av > ma[j]) {
-            la[j] *= exp2f(ma[j] - av);
-            ma[j] = av;
-          }
-          la[j] += exp2f(av - ma[j]);
-        }
-        if (cv > mc[j]) {
-          lc[j] *= exp2f(mc[j] - cv);
-          mc[j] = cv;
-        }
-        lc[j] += exp2f(cv - mc[j]);
-      }
+    for (int j = 0; j < kKdeQpt; ++j) {
+      den[j].end_tile();
+      num[j].end_tile();
     }
     __syncthreads();
   }
@@ -159,15 +219,8 @@ __global__ void __launch_bounds__(kKdeThreads) kde_log_prob_kernel(
   for (int j = 0; j < kKdeQpt; ++j) {
     const int64_t r = row0 + static_cast<int64_t>(j) * kKdeThreads;
     if (r < n_rows) {
-      const float num = (mc[j] + log2f(lc[j])) * kLn2;
-      float v;
-      if (DP > 0) {
-        const float den = (ma[j] + log2f(la[j])) * kLn2;
-        v = num - den + const_y;
-      } else {
-        v = num + const_y - log_n;
-      }
-      out[r] = v;
+      const float nv = num[j].log2_value() * kLn2;
+      out[r] = DP > 0 ? nv - den[j].log2_value() * kLn2 + const_y : nv + const_y - log_n;
     }
   }
 }

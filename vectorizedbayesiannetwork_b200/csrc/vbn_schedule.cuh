@@ -877,25 +877,35 @@ __device__ __forceinline__ void op_kde(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
     }
   }
   if (want_lp) {
+    // two-level logsumexp: blocks of 256 stored points are reduced on their own and then merged,
+    // so the fp32 summation error does not grow with sqrt(N) (matters from N ~ 1e5 on)
     Lse num[RPT], den[RPT];
 #pragma unroll
     for (int j = 0; j < RPT; ++j) { num[j].init(); den[j].init(); }
-    for (int n = 0; n < N; ++n)
+    for (int n0 = 0; n0 < N; n0 += 256) {
+      const int n1 = min(n0 + 256, N);
+      Lse bn[RPT], bd[RPT];
 #pragma unroll
-      for (int j = 0; j < RPT; ++j) {
-        float qp = 0.0f, qy = 0.0f;
-        for (int p = 0; p < Dp; ++p) {
-          const float df = c.slot(__ldg(par + p), j) - __ldg(tp + n * Dp + p);
-          qp = fmaf(df, df, qp);
+      for (int j = 0; j < RPT; ++j) { bn[j].init(); bd[j].init(); }
+      for (int n = n0; n < n1; ++n)
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+          float qp = 0.0f, qy = 0.0f;
+          for (int p = 0; p < Dp; ++p) {
+            const float df = c.slot(__ldg(par + p), j) - __ldg(tp + n * Dp + p);
+            qp = fmaf(df, df, qp);
+          }
+          for (int d = 0; d < D; ++d) {
+            const float df = c.slot(op.out_slot + d, j) - __ldg(ty + n * D + d);
+            qy = fmaf(df, df, qy);
+          }
+          const float a = -hp * qp;
+          bd[j].push(a);
+          bn[j].push(fmaf(-hy, qy, a));
         }
-        for (int d = 0; d < D; ++d) {
-          const float df = c.slot(op.out_slot + d, j) - __ldg(ty + n * D + d);
-          qy = fmaf(df, df, qy);
-        }
-        const float a = -hp * qp;
-        den[j].push(a);
-        num[j].push(fmaf(-hy, qy, a));
-      }
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) { num[j].merge(bn[j]); den[j].merge(bd[j]); }
+    }
     float lp[RPT];
 #pragma unroll
     for (int j = 0; j < RPT; ++j)
