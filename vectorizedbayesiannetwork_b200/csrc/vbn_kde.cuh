@@ -63,11 +63,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // sqrt(N) (200 000 sequential adds cost ~3e-5 relative, which fails the 1e-5 parity).
 struct KdeAcc {
   float m, tot;
-  f32x2 cur;
+  f32x2 cur, mm;  // mm = (m, m), kept packed so the hot path never rebuilds it
   __device__ __forceinline__ void init() {
     m = -CUDART_INF_F;
     tot = 0.0f;
     cur = pack2(0.0f, 0.0f);
+    mm = pack2(m, m);
   }
   // v0, v1: four log2-domain terms (two packed pairs)
   __device__ __forceinline__ void push4(f32x2 v0, f32x2 v1) {
@@ -80,8 +81,8 @@ struct KdeAcc {
       tot *= sc;
       cur = mul2(cur, pack2(sc, sc));
       m = mx;
+      mm = pack2(mx, mx);
     }
-    const f32x2 mm = pack2(m, m);
     unpack2(sub2(v0, mm), a, b);
     unpack2(sub2(v1, mm), c, d);
     cur = add2(cur, pack2(ex2_approx(a), ex2_approx(b)));
@@ -96,44 +97,51 @@ struct KdeAcc {
   __device__ __forceinline__ float log2_value() const { return m + log2f(tot); }
 };
 
+// Fast accumulator: every log2-domain term is <= 0 (it is minus a squared distance), so the sum
+// can be taken with a fixed shift m = 0 -- no running max, no rescale -- as long as the nearest
+// stored point keeps the sum above the fp32 underflow range.  Rows whose sums fall below 2^-100
+// (queries ~12 kernel widths away from every stored point) make the CTA redo the pass with KdeAcc.
+struct KdeFastAcc {
+  float tot;
+  f32x2 cur;
+  __device__ __forceinline__ void init() {
+    tot = 0.0f;
+    cur = pack2(0.0f, 0.0f);
+  }
+  __device__ __forceinline__ void push4(f32x2 v0, f32x2 v1) {
+    float a, b, c, d;
+    unpack2(v0, a, b);
+    unpack2(v1, c, d);
+    cur = add2(cur, pack2(ex2_approx(a), ex2_approx(b)));
+    cur = add2(cur, pack2(ex2_approx(c), ex2_approx(d)));
+  }
+  __device__ __forceinline__ void end_tile() {
+    float a, b;
+    unpack2(cur, a, b);
+    tot += a + b;
+    cur = pack2(0.0f, 0.0f);
+  }
+  __device__ __forceinline__ float log2_value() const { return log2f(tot); }
+  __device__ __forceinline__ bool underflowed() const { return !(tot > 7.888609e-31f); }  // 2^-100
+};
+
 // Shared-memory tile layout: dimension-major, [d][kKdeTile] floats, so a float2 load fetches the
 // same coordinate of two consecutive points (the two lanes of the packed math).  Tile tails are
 // filled with +inf parents / targets: their terms are exp2(-inf) = 0.
-template <int DP, int DX>
-__global__ void __launch_bounds__(kKdeThreads) kde_log_prob_kernel(
-    const float* __restrict__ tp, const float* __restrict__ ty, int64_t n_points,
-    const float* __restrict__ qp, const float* __restrict__ qx, int64_t n_rows,
-    float hp2, float hy2, float const_y, float log_n, float* __restrict__ out) {
-  // hp2 = 0.5*log2(e)/s_p^2, hy2 = 0.5*log2(e)/s_y^2  (log2 domain)
+template <int DP, int DX, class Acc>
+__device__ __forceinline__ void kde_pass(const float* __restrict__ tp, const float* __restrict__ ty,
+                                         int64_t n_points, float (*s_p)[(DP > 0 ? DP : 1) * kKdeTile],
+                                         float (*s_y)[DX * kKdeTile],
+                                         const f32x2 (&xp)[kKdeQpt][DP > 0 ? DP : 1],
+                                         const f32x2 (&xy)[kKdeQpt][DX], float hp2, float hy2,
+                                         Acc (&den)[kKdeQpt], Acc (&num)[kKdeQpt]) {
   constexpr int DPS = DP > 0 ? DP : 1;
-  __shared__ __align__(16) float s_p[2][DPS * kKdeTile];
-  __shared__ __align__(16) float s_y[2][DX * kKdeTile];
-
-  const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * kKdeThreads * kKdeQpt) + threadIdx.x;
-  f32x2 xp[kKdeQpt][DPS], xy[kKdeQpt][DX];
-#pragma unroll
-  for (int j = 0; j < kKdeQpt; ++j) {
-    int64_t r = row0 + static_cast<int64_t>(j) * kKdeThreads;
-    if (r >= n_rows) r = n_rows - 1;
-#pragma unroll
-    for (int d = 0; d < DP; ++d) {
-      const float v = __ldg(qp + r * DP + d);
-      xp[j][d] = pack2(v, v);
-    }
-#pragma unroll
-    for (int d = 0; d < DX; ++d) {
-      const float v = __ldg(qx + r * DX + d);
-      xy[j][d] = pack2(v, v);
-    }
-  }
-  KdeAcc den[kKdeQpt], num[kKdeQpt];
 #pragma unroll
   for (int j = 0; j < kKdeQpt; ++j) {
     den[j].init();
     num[j].init();
   }
   const f32x2 nhp = pack2(-hp2, -hp2), nhy = pack2(-hy2, -hy2);
-
   const int64_t n_tiles = (n_points + kKdeTile - 1) / kKdeTile;
   auto stage = [&](int64_t t, int buf) {
     const int64_t base = t * kKdeTile;
@@ -213,15 +221,61 @@ __global__ void __launch_bounds__(kKdeThreads) kde_log_prob_kernel(
     }
     __syncthreads();
   }
+}
 
+template <int DP, int DX>
+__global__ void __launch_bounds__(kKdeThreads) kde_log_prob_kernel(
+    const float* __restrict__ tp, const float* __restrict__ ty, int64_t n_points,
+    const float* __restrict__ qp, const float* __restrict__ qx, int64_t n_rows,
+    float hp2, float hy2, float const_y, float log_n, float* __restrict__ out) {
+  // hp2 = 0.5*log2(e)/s_p^2, hy2 = 0.5*log2(e)/s_y^2  (log2 domain)
+  constexpr int DPS = DP > 0 ? DP : 1;
+  __shared__ __align__(16) float s_p[2][DPS * kKdeTile];
+  __shared__ __align__(16) float s_y[2][DX * kKdeTile];
+
+  const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * kKdeThreads * kKdeQpt) + threadIdx.x;
+  f32x2 xp[kKdeQpt][DPS], xy[kKdeQpt][DX];
+#pragma unroll
+  for (int j = 0; j < kKdeQpt; ++j) {
+    int64_t r = row0 + static_cast<int64_t>(j) * kKdeThreads;
+    if (r >= n_rows) r = n_rows - 1;
+#pragma unroll
+    for (int d = 0; d < DPS; ++d) {
+      const float v = DP > 0 ? __ldg(qp + r * DP + d) : 0.0f;
+      xp[j][d] = pack2(v, v);
+    }
+#pragma unroll
+    for (int d = 0; d < DX; ++d) {
+      const float v = __ldg(qx + r * DX + d);
+      xy[j][d] = pack2(v, v);
+    }
+  }
   constexpr float kLn2 = 0.6931471805599453f;
+  float res[kKdeQpt];
+  bool redo = false;
+  {
+    KdeFastAcc den[kKdeQpt], num[kKdeQpt];
+    kde_pass<DP, DX>(tp, ty, n_points, s_p, s_y, xp, xy, hp2, hy2, den, num);
+#pragma unroll
+    for (int j = 0; j < kKdeQpt; ++j) {
+      const float nv = num[j].log2_value() * kLn2;
+      res[j] = DP > 0 ? nv - den[j].log2_value() * kLn2 + const_y : nv + const_y - log_n;
+      redo = redo || num[j].underflowed() || (DP > 0 && den[j].underflowed());
+    }
+  }
+  if (__syncthreads_or(redo ? 1 : 0)) {  // far-tail rows in this CTA: exact online-max pass
+    KdeAcc den[kKdeQpt], num[kKdeQpt];
+    kde_pass<DP, DX>(tp, ty, n_points, s_p, s_y, xp, xy, hp2, hy2, den, num);
+#pragma unroll
+    for (int j = 0; j < kKdeQpt; ++j) {
+      const float nv = num[j].log2_value() * kLn2;
+      res[j] = DP > 0 ? nv - den[j].log2_value() * kLn2 + const_y : nv + const_y - log_n;
+    }
+  }
 #pragma unroll
   for (int j = 0; j < kKdeQpt; ++j) {
     const int64_t r = row0 + static_cast<int64_t>(j) * kKdeThreads;
-    if (r < n_rows) {
-      const float nv = num[j].log2_value() * kLn2;
-      out[r] = DP > 0 ? nv - den[j].log2_value() * kLn2 + const_y : nv + const_y - log_n;
-    }
+    if (r < n_rows) out[r] = res[j];
   }
 }
 
