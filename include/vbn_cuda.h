@@ -42,6 +42,8 @@ extern "C" {
 #define VBN_OP_MDN 3    /* vbn/cpds/mdn.py:185-272                                         */
 #define VBN_OP_SNN 4    /* vbn/cpds/softmax_nn.py:581-759                                  */
 #define VBN_OP_KDE 5    /* vbn/cpds/kde.py:105-182                                         */
+#define VBN_OP_TAB 6     /* softmax_nn in discrete mode with all-discrete parents: log-density
+                            table per parent configuration, built by the plan compiler     */
 
 /* ---- op flags ------------------------------------------------------------------------ */
 #define VBN_SRC_MASK 0x3

@@ -541,6 +541,72 @@ class KDECPD(BaseCPD):
                 "min_scale": self.min_scale, "parents": self._parents, "targets": self._targets}
 
 
+# ------------------------------------------------------------------------------------------
+# discrete-parent lookup tables (VBN_OP_TAB)
+# ------------------------------------------------------------------------------------------
+_TABLE_CACHE: Dict[tuple, Packed] = {}
+TABLE_MAX_CONFIGS = 4096
+
+
+def _is_plain_discrete(cpd) -> bool:
+    return (isinstance(cpd, SoftmaxNNCPD) and cpd.output_dim == 1 and cpd._bins_ready
+            and bool(cpd._is_discrete.all()) and cpd.n_classes <= 8)
+
+
+def table_eligible(cpd, parent_cpds: Sequence[BaseCPD]) -> bool:
+    """A discrete-mode softmax_nn node (D = 1, <= 8 classes) whose parents are all such nodes: its
+    logits take one value per parent configuration."""
+    if not _is_plain_discrete(cpd) or not all(_is_plain_discrete(p) for p in parent_cpds):
+        return False
+    if len(parent_cpds) != cpd.input_dim:
+        return False
+    n_cfg = 1
+    for pc in parent_cpds:
+        n_cfg *= pc.n_classes
+    return n_cfg <= TABLE_MAX_CONFIGS
+
+
+def pack_table(cpd, parent_cpds: Sequence[BaseCPD], log_prob_fn) -> Packed:
+    """Builds the VBN_OP_TAB block: the node's own log-density for every (parent configuration, class),
+    evaluated by ``log_prob_fn(cpd, x[n,1], parents[n,Dp] | None) -> [n]`` -- the library's GPU path, so
+    the table holds exactly the numbers a per-row evaluation would produce."""
+    key = (cpd._uid, cpd._version, tuple((pc._uid, pc._version) for pc in parent_cpds))
+    hit = _TABLE_CACHE.get(key)
+    if hit is not None:
+        return hit
+    base = cpd.pack()
+    c = cpd.n_classes
+    cards = [pc.n_classes for pc in parent_cpds]
+    n_cfg = int(np.prod(cards)) if cards else 1
+    strides, acc = [], 1
+    for card in reversed(cards):
+        strides.append(acc)
+        acc *= card
+    strides = strides[::-1]
+    if cards:
+        grids = torch.cartesian_prod(*[pc._class_values[0] for pc in parent_cpds]).reshape(n_cfg, len(cards))
+    else:
+        grids = None
+    cols = []
+    for k in range(c):
+        x = cpd._class_values[0, k].repeat(n_cfg).reshape(n_cfg, 1)
+        cols.append(_f32(log_prob_fn(cpd, x, grids)).reshape(n_cfg))
+    logp = torch.stack(cols, dim=1)                       # [n_cfg, C]
+    cdf = torch.cumsum(torch.exp(logp.double()), dim=1).float()
+    head = [np.array([c, n_cfg, 0, 0], np.float32)]
+    for pc, card, stride in zip(parent_cpds, cards, strides):
+        head.append(np.concatenate([np.array([card, stride, 0, 0], np.float32),
+                                    _padded(_np(pc._class_values[0]), 8)]))
+    head += [_padded(_np(cpd._sample_values[0]), 8), _padded(_np(cpd._class_values[0]), 8), _np(cdf), _np(logp)]
+    params = np.concatenate(head)
+    pk = Packed(kind=L.OP_TAB, dim=1, n_par=len(cards), params=_padded(params, _pad4(params.size)), k=c,
+                n_normals=base.n_normals, n_uniforms=base.n_uniforms, scratch=0, heavy=False)
+    if len(_TABLE_CACHE) > 4096:
+        _TABLE_CACHE.clear()
+    _TABLE_CACHE[key] = pk
+    return pk
+
+
 CPD_CLASSES = {
     "linear_gaussian": LinearGaussianCPD,
     "gaussian_nn": GaussianNNCPD,

@@ -811,6 +811,81 @@ __device__ __forceinline__ void op_snn(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
 }
 
 // ---------------------------------------------------------------------------------------
+// VBN_OP_TAB: a softmax_nn node in discrete mode (softmax_nn.py:581-759, D = 1) whose parents are all
+// discrete too.  Its logits depend only on the parent configuration, so the plan compiler evaluates
+// the node's own log-density once per configuration (through this library's MLP path, i.e. the
+// same numbers the per-row evaluation produces) and the node becomes a table lookup.
+// params: {C, n_cfg, 0, 0}, per parent p < Dp: {card, stride, 0, 0, class_values[8]},
+//         sample_values[8], class_values[8], cdf[n_cfg][C] (running sums of exp(logp)),
+//         logp[n_cfg][C]
+// ---------------------------------------------------------------------------------------
+template <int RPT, int NT, class TC>
+__device__ __forceinline__ void op_tab(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
+  const float* P = c.a.params + op.param_off;
+  const int C = op.k, Dp = op.n_par;
+  const int n_cfg = static_cast<int>(__ldg(P + 1));
+  const float* pinfo = P + 4;
+  const float* sample_values = pinfo + 12 * Dp;
+  const float* class_values = sample_values + 8;
+  const float* cdf = class_values + 8;
+  const float* logp = cdf + n_cfg * C;
+  const int32_t* par = c.a.par_slots + op.par_off;
+  const bool sample = (op.flags & VBN_SRC_MASK) == VBN_SRC_SAMPLE;
+  const bool want_lp = (op.flags & (VBN_F_ADD_LOGW | VBN_F_OUT_LOGP)) != 0;
+
+  int cfg[RPT];
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) cfg[j] = 0;
+  for (int p = 0; p < Dp; ++p) {
+    const float* pi = pinfo + 12 * p;
+    const int card = static_cast<int>(__ldg(pi)), stride = static_cast<int>(__ldg(pi + 1));
+    const int ps = __ldg(par + p);
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const float v = c.slot(ps, j);
+      int ci = 0;  // a value outside the parent's class set is flagged where that parent is scored
+      for (int q = 1; q < card; ++q)
+        if (v == __ldg(pi + 4 + q)) ci = q;
+      cfg[j] += ci * stride;
+    }
+  }
+  if (sample) {
+    int pick[RPT];
+    if (!c.injected_index(op, 0, 1, pick)) {  // Categorical(logits).sample() (softmax_nn.py:651)
+      float u[RPT];
+      c.draw_uniform(op, op.u_off, 0, u);
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        const float* row = cdf + cfg[j] * C;
+        const float t = u[j] * __ldg(row + C - 1);
+        int k = 0;
+        for (int q = 0; q < C - 1; ++q) k += (t >= __ldg(row + q)) ? 1 : 0;
+        pick[j] = k;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < RPT; ++j)
+      c.slot(op.out_slot, j) = __ldg(sample_values + min(max(pick[j], 0), C - 1));
+  }
+  if (want_lp) {
+    float lp[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const float x = c.slot(op.out_slot, j);
+      int bin = -1;  // exact class match (softmax_nn.py:618-627)
+      for (int q = C - 1; q >= 0; --q)
+        if (x == __ldg(class_values + q)) bin = q;
+      if (bin < 0) {
+        if (c.rows.valid[j] && c.a.error_flag) atomicOr(c.a.error_flag, 1);
+        bin = 0;
+      }
+      lp[j] = __ldg(logp + cfg[j] * C + bin);
+    }
+    commit_logp(c, op, lp);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // VBN_OP_KDE: kde.py:105-182.
 // params: {hy, hp, const_y, noise_scale, log_n, 0,0,0}, parents[N][Dp] (pad4), targets[N][D]
 //   hy = 0.5/s_y^2, hp = 0.5/s_p^2  ->  log_k = -h*diff^2 + const
@@ -961,6 +1036,8 @@ __device__ __forceinline__ void run_ops(Ctx<RPT, NT, TC>& c) {
           dst[5] = __ldg(src + 5);  // w0..w3
           dst[6] = __ldg(src + 6);  // parent slots
         }
+      } else if (op.kind == VBN_OP_TAB) {
+        dst[3] = __ldg(src + 3);  // k = classes
       } else if (HEAVY && op.kind >= VBN_OP_GNN) {
         dst[3] = __ldg(src + 3);  // n_layers, act, n_out, k
         dst[6] = __ldg(src + 6);  // aux
@@ -977,6 +1054,7 @@ __device__ __forceinline__ void run_ops(Ctx<RPT, NT, TC>& c) {
       case VBN_OP_MDN: if (HEAVY) op_mdn(c, op); break;
       case VBN_OP_SNN: if (HEAVY) op_snn(c, op); break;
       case VBN_OP_KDE: if (HEAVY) op_kde(c, op); break;
+      case VBN_OP_TAB: op_tab(c, op); break;
       default: break;
     }
     store_value(c, op);

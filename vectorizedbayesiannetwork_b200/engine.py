@@ -258,6 +258,11 @@ def _cpd_plan(cpd: BaseCPD, device, *, mode: str, parents_kind: str, x_kind: str
     return plan
 
 
+def discrete_table_fn(cpd, x, parents):
+    """log p(x | parents) rows for plan.compile_schedule's table builder, through the GPU CPD path."""
+    return cpd_log_prob(cpd, x, parents).reshape(-1).detach().cpu()
+
+
 def _as_dev(t, device) -> torch.Tensor:
     return torch.as_tensor(t).detach().to(device=device, dtype=torch.float32)
 

@@ -76,7 +76,7 @@ class _ScheduleRunner:
             t = roles[query.target]
             t.out_logp = True
             t.density = True
-        prog = compile_schedule(topo, parents, cpds, roles)
+        prog = compile_schedule(topo, parents, cpds, roles, table_fn=E.discrete_table_fn)
         plan = E.DevicePlan(prog, vbn.device)
         if len(self._cache) > 64:
             self._cache.clear()

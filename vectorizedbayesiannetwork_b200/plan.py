@@ -16,7 +16,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 
 from . import _lib as L
-from .cpds import BaseCPD, Packed
+from .cpds import BaseCPD, Packed, pack_table, table_eligible
 
 
 @dataclass
@@ -58,9 +58,16 @@ def tensor_cores_enabled() -> bool:
     return os.environ.get("VBN_TC", "1") != "0"
 
 
+def tables_enabled() -> bool:
+    """VBN_TABLE=0 keeps discrete nodes on the per-row MLP path (A/B measurements); default on."""
+    return os.environ.get("VBN_TABLE", "1") != "0"
+
+
 def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpds: Dict[str, BaseCPD],
-                     roles: Dict[str, Role], use_tc: Optional[bool] = None) -> Program:
-    """``topo``: nodes to emit, in topological order (nodes absent from ``roles`` are skipped)."""
+                     roles: Dict[str, Role], use_tc: Optional[bool] = None, table_fn=None) -> Program:
+    """``topo``: nodes to emit, in topological order (nodes absent from ``roles`` are skipped).
+    ``table_fn(cpd, x, parents) -> log_prob``: lets discrete nodes with all-discrete parents be
+    compiled into lookup tables (VBN_OP_TAB); None keeps them on the MLP path."""
     if use_tc is None:
         use_tc = tensor_cores_enabled()
     any_tc = False
@@ -74,6 +81,14 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
         r = roles[n]
         evaluates = r.density and (r.src == "sample" or r.add_logw or r.out_logp)
         packed[n] = cpds[n].pack() if evaluates else None
+        if evaluates and table_fn is not None and tables_enabled():
+            plist = list(parents.get(n, ()))
+            # parents must carry class values: drawn discrete nodes, or evidence that is itself scored
+            # (an off-class evidence value then raises through that parent's own density)
+            ok = all(p in roles and roles[p].density and (roles[p].src == "sample" or roles[p].add_logw)
+                     for p in plist)
+            if ok and table_eligible(cpds[n], [cpds[p] for p in plist]):
+                packed[n] = pack_table(cpds[n], [cpds[p] for p in plist], table_fn)
         dims[n] = int(cpds[n].output_dim)
 
     # ---- liveness: last op that reads each node's value -------------------------------------
