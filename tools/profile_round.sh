@@ -1,0 +1,15 @@
+#!/bin/bash
+# Round profile capture (run under gpurun, one GPU): per-launch device times of one bench command per
+# workload, then one `--set full` capture of each dominant kernel.  Outputs land in gpurun_out/.
+set -u
+R=${1:-r01}
+declare -A ARGS=( [cfg5]="--queries-per-gpu 296" [cfg2]="--samples 250000" [cfg3]="--queries-per-gpu 1024" [cfg4]="--queries-per-gpu 303104" )
+declare -A KREG=( [cfg5]="schedule_tc" [cfg2]="schedule_kernel" [cfg3]="schedule_kernel" [cfg4]="kde_log_prob" )
+for w in cfg5 cfg2 cfg3 cfg4; do
+  CMD="python bench.py --workload $w --steps 2 --warmup 3 --no-cpu-baseline ${ARGS[$w]}"
+  $CMD > gpurun_out/${R}_plain_$w.json 2> gpurun_out/${R}_plain_$w.err &&
+  ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${R}_launches_$w.csv $CMD > gpurun_out/${R}_ncu_launches_$w.log 2>&1
+  $CMD > /dev/null 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:${KREG[$w]} -s 3 -c 1 -o gpurun_out/${R}_prof_$w $CMD > gpurun_out/${R}_ncu_full_$w.log 2>&1
+  tail -1 gpurun_out/${R}_ncu_full_$w.log
+done
