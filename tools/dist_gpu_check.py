@@ -23,7 +23,7 @@ def main():
     for name, spec, target, ev_nodes in (("lg_chain", S.lg_chain(12), "x5", ["x11"]),
                                          ("lg_mdn", S.random_dag_lg_mdn(40, seed=2), "n20", ["n38", "n39"])):
         g = torch.Generator().manual_seed(3)
-        B, Sn = 6, 4096
+        B, Sn = 2 * world + 2, 4096
         q = {"target": target, "evidence": {n: 0.5 * torch.randn(B, 1, generator=g) for n in ev_nodes}}
         model = V.VBN.from_spec(spec, device=dev)
         for method in ("likelihood_weighting", "importance_sampling"):
