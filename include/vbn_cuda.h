@@ -63,6 +63,8 @@ extern "C" {
 #define VBN_F_MDNPLAIN 0x200   /* MDN op, D = 1, 2 <= K <= 5, PAR4, tensor-core MLP, that is only
                                   drawn (Philox, per-row stream, no density): register-resident
                                   tail in the tcgen05 kernel; ignored by the FP32-pipe kernel   */
+#define VBN_F_OUT_PARAMS 0x400  /* write the conditional-distribution parameters of every row to
+                                  stores[store_idx] instead of drawing (CPDHandle.conditional)  */
 #define VBN_F_LGPLAIN 0x80     /* LGFAST op that is only drawn: Philox, per-row stream, no store,
                                   no density -- the kernel reads nothing but quads 0,4,5,6      */
 

@@ -354,3 +354,50 @@ def test_discrete_tables_reproduce_the_mlp_path(backend, monkeypatch):
     assert same > 0.999, same  # a pick can flip only when u sits within rounding of a CDF edge
     ok = ((out["0"][0] - out["1"][0]).abs() <= 1e-7 + 1e-4 * out["0"][0].abs()).float().mean().item()
     assert ok > 0.995, ok
+
+
+# ---- CPDHandle.conditional formats (vbn/core/cpd_handle.py:40-118, 348-402; tests/test_cpd_handle.py:61-88)
+def test_conditional_formats_match_the_parameter_heads(backend):
+    import os
+
+    blob = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mixed_relu.pt"),
+                      weights_only=False)
+    spec = blob["spec"]
+    model = V.VBN.from_spec(spec, device=backend.device)
+    g = torch.Generator().manual_seed(9)
+    seen = set()
+    for node in spec["nodes"]:
+        c = spec["cpds"][node]
+        h = model.get_cpd(node)
+        dp = c["input_dim"]
+        parents = torch.randn(5, dp, generator=g) if dp else None
+        out = h.conditional(parents)
+        seen.add(out["format"])
+        t = lambda key: torch.tensor(out[key])
+        if c["kind"] == "linear_gaussian":
+            loc, scale = O.lg_params(c, parents)
+            assert out["format"] == "normal_params"
+            torch.testing.assert_close(t("mean"), loc.reshape(t("mean").shape), rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(t("std"), scale.reshape(t("std").shape), rtol=1e-5, atol=1e-6)
+        elif c["kind"] == "gaussian_nn":
+            loc, scale = O.gnn_params(c, parents)
+            assert out["format"] == "normal_params"
+            torch.testing.assert_close(t("mean"), loc.reshape(t("mean").shape), rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(t("std"), scale.reshape(t("std").shape), rtol=1e-5, atol=1e-6)
+        elif c["kind"] == "mdn":
+            logits, loc, scale = O.mdn_params(c, parents)
+            assert out["format"] == "mixture_params"
+            w = torch.softmax(logits, dim=-1)
+            torch.testing.assert_close(t("weights"), w.reshape(t("weights").shape), rtol=2e-5, atol=1e-6)
+            torch.testing.assert_close(t("loc"), loc.reshape(t("loc").shape), rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(t("scale"), scale.reshape(t("scale").shape), rtol=1e-5, atol=1e-6)
+        elif c["kind"] == "softmax_nn":
+            b = 5 if dp else 1
+            probs = torch.softmax(O.snn_logits(c, parents, b, 1), dim=-1)
+            assert out["format"] == "categorical_probs" and out["k"] == c["n_classes"]
+            torch.testing.assert_close(t("probs"), probs.reshape(t("probs").shape), rtol=2e-5, atol=1e-6)
+        else:
+            assert out["format"] == "empirical_samples"
+        ms = h.conditional_mean_std(parents, n_samples=64)
+        assert torch.isfinite(ms["mean"]).all() and torch.isfinite(ms["std"]).all()
+    assert seen == {"normal_params", "mixture_params", "categorical_probs", "empirical_samples"}

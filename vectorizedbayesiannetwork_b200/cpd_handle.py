@@ -112,13 +112,30 @@ class CPDHandle:
                 "device": str(self.device), "is_fitted": True}
 
     def conditional(self, parents, *, n_samples: int = 1024) -> dict:
-        """vbn/core/cpd_handle.py:348-402.  Closed-form parameter formats (normal / mixture /
-        categorical) need the CPD's parameter head rather than draws; they are produced from GPU
-        draws/densities where a parameter read-out kernel is not yet wired."""
+        """vbn/core/cpd_handle.py:348-402: normal_params (linear_gaussian, gaussian_nn), mixture_params
+        (mdn), categorical_probs (softmax_nn) from the GPU parameter read-out (VBN_F_OUT_PARAMS);
+        empirical_samples for kde."""
         ptensor = self._parents_tensor(parents)
         base = {"node": self.node, "parents": self.parents, "cpd_name": self.cpd_name,
                 "cpd_type": self.cpd_type, "input_dim": self.input_dim, "output_dim": self.output_dim,
                 "conditioning": _to_serializable(ptensor)}
+        cpd, d = self._cpd, self.x_dim
+        if cpd.param_width() > 0:
+            out = cpd.params(ptensor).detach()  # [B, S, width] from the GPU read-out
+            if cpd.kind in ("linear_gaussian", "gaussian_nn"):
+                return {**base, "format": "normal_params", "mean": _to_serializable(out[..., :d]),
+                        "std": _to_serializable(out[..., d:])}
+            if cpd.kind == "mdn":
+                k = cpd.n_components
+                b, s_ = out.shape[0], out.shape[1]
+                return {**base, "format": "mixture_params", "weights": _to_serializable(out[..., :k]),
+                        "loc": _to_serializable(out[..., k:k + k * d].reshape(b, s_, k, d)),
+                        "scale": _to_serializable(out[..., k + k * d:].reshape(b, s_, k, d))}
+            if cpd.kind == "softmax_nn":
+                b, s_ = out.shape[0], out.shape[1]
+                return {**base, "format": "categorical_probs",
+                        "probs": _to_serializable(out.reshape(b, s_, d, cpd.n_classes)),
+                        "k": int(cpd.n_classes), "support": _to_serializable(cpd._sample_values)}
         samples = self._cpd.sample(ptensor, int(n_samples)).detach()
         return {**base, "format": "empirical_samples", "samples": _to_serializable(samples),
                 "mean": _to_serializable(samples.mean(dim=1)),

@@ -201,6 +201,15 @@ class BaseCPD:
     def to_spec(self) -> dict:  # pragma: no cover - abstract
         raise NotImplementedError
 
+    def param_width(self) -> int:
+        """Floats per row written by the parameter read-out (engine.cpd_params); 0 = none."""
+        return 0
+
+    def params(self, parents: Optional[torch.Tensor]) -> torch.Tensor:
+        from .engine import cpd_params
+
+        return cpd_params(self, parents)
+
 
 # ------------------------------------------------------------------------------------------
 class LinearGaussianCPD(BaseCPD):
@@ -217,6 +226,9 @@ class LinearGaussianCPD(BaseCPD):
 
     def _scale(self) -> torch.Tensor:
         return torch.sqrt(self._var.clamp(min=self.min_scale**2))  # linear_gaussian.py:163-165
+
+    def param_width(self) -> int:
+        return 2 * self.output_dim
 
     def _pack(self) -> Packed:
         scale = self._scale()
@@ -262,6 +274,9 @@ class GaussianNNCPD(BaseCPD):
             self.layers = None
         else:
             self.layers = [(_f32(w), _f32(b)) for w, b in layers]
+
+    def param_width(self) -> int:
+        return 2 * self.output_dim
 
     def _pack(self) -> Packed:
         d, dp = self.output_dim, self.input_dim
@@ -329,6 +344,9 @@ class MDNCPD(BaseCPD):
             self.layers = None
         else:
             self.layers = [(_f32(w), _f32(b)) for w, b in layers]
+
+    def param_width(self) -> int:
+        return self.n_components * (1 + 2 * self.output_dim)
 
     def _pack(self) -> Packed:
         k, d, dp = self.n_components, self.output_dim, self.input_dim
@@ -408,6 +426,9 @@ class SoftmaxNNCPD(BaseCPD):
             self.layers = None
         else:
             self.layers = [(_f32(w), _f32(b)) for w, b in layers]
+
+    def param_width(self) -> int:
+        return self.output_dim * self.n_classes
 
     def _ensure_bins_ready(self) -> None:
         if not self._bins_ready:  # softmax_nn.py:178-180

@@ -886,6 +886,79 @@ __device__ __forceinline__ void op_tab(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
 }
 
 // ---------------------------------------------------------------------------------------
+// VBN_F_OUT_PARAMS: write the op's conditional-distribution parameters for every row instead of
+// drawing it -- the numbers CPDHandle.conditional() reports (vbn/core/cpd_handle.py:40-118, 348-402):
+//   LG / GNN : loc[D], scale[D]                       ("normal_params")
+//   MDN      : softmax(logits)[K], loc[K][D], scale[K][D]   ("mixture_params"; unclamped softmax)
+//   SNN      : softmax(logits)[D][C]                  ("categorical_probs")
+// element i of row r goes to stores[store_idx] (r, i).
+// ---------------------------------------------------------------------------------------
+template <int RPT, int NT, class TC>
+__device__ __forceinline__ void op_params(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
+  const float* P = c.a.params + op.param_off;
+  const int D = op.dim, Dp = op.n_par;
+  const int32_t* par = c.a.par_slots + op.par_off;
+  const VbnView v = c.a.stores[op.store_idx];
+  auto put = [&](int i, int j, float x) {
+    if (c.rows.valid[j]) v.base[c.rows.r[j] * v.row_stride + i * v.dim_stride] = x;
+  };
+  if (op.kind == VBN_OP_LG) {
+    const float* W = P;
+    const float* bias = W + Dp * D;
+    const float* scale = bias + D;
+    for (int d = 0; d < D; ++d)
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        float loc = 0.0f;
+        for (int p = 0; p < Dp; ++p) loc = fmaf(c.slot(__ldg(par + p), j), __ldg(W + p * D + d), loc);
+        put(d, j, loc + __ldg(bias + d));
+        put(D + d, j, __ldg(scale + d));
+      }
+  } else if (op.kind == VBN_OP_GNN) {
+    const float* mean_y = P + 2 * Dp;
+    const float* std_y = mean_y + D;
+    const float min_scale = __ldg(std_y + D);
+    mlp_eval(c, op, P + pad4(2 * Dp + 2 * D + 1), P, par);
+    for (int d = 0; d < D; ++d)
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        const float sy = __ldg(std_y + d);
+        put(d, j, fmaf(c.scr(d, j), sy, __ldg(mean_y + d)));
+        put(D + d, j, (softplus20(c.scr(D + d, j)) + min_scale) * sy);
+      }
+  } else if (op.kind == VBN_OP_MDN) {
+    const int K = op.k;
+    const float min_scale = __ldg(P);
+    mlp_eval(c, op, P + 4, nullptr, par);
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      float mx = -CUDART_INF_F, se = 0.0f;
+      for (int k = 0; k < K; ++k) mx = fmaxf(mx, c.scr(k, j));
+      for (int k = 0; k < K; ++k) se += expf(c.scr(k, j) - mx);
+      for (int k = 0; k < K; ++k) put(k, j, __fdiv_rn(expf(c.scr(k, j) - mx), se));
+      for (int k = 0; k < K; ++k)
+        for (int d = 0; d < D; ++d) {
+          put(K + k * D + d, j, c.scr(K + k * 2 * D + d, j));
+          put(K + K * D + k * D + d, j, softplus20(c.scr(K + k * 2 * D + D + d, j)) + min_scale);
+        }
+    }
+  } else if (op.kind == VBN_OP_SNN) {
+    const int C = op.k;
+    const float temperature = __ldg(P + 2);
+    mlp_eval(c, op, P + pad4(4 + D * (C + 1) + 2 * D * C + D), nullptr, par);
+#pragma unroll
+    for (int j = 0; j < RPT; ++j)
+      for (int d = 0; d < D; ++d) {
+        float mx = -CUDART_INF_F, se = 0.0f;
+        const float it = (op.n_layers > 0 && temperature != 1.0f) ? temperature : 1.0f;
+        for (int k = 0; k < C; ++k) mx = fmaxf(mx, __fdiv_rn(c.scr(d * C + k, j), it));
+        for (int k = 0; k < C; ++k) se += expf(__fdiv_rn(c.scr(d * C + k, j), it) - mx);
+        for (int k = 0; k < C; ++k) put(d * C + k, j, __fdiv_rn(expf(__fdiv_rn(c.scr(d * C + k, j), it) - mx), se));
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // VBN_OP_KDE: kde.py:105-182.
 // params: {hy, hp, const_y, noise_scale, log_n, 0,0,0}, parents[N][Dp] (pad4), targets[N][D]
 //   hy = 0.5/s_y^2, hp = 0.5/s_p^2  ->  log_k = -h*diff^2 + const
@@ -1045,6 +1118,10 @@ __device__ __forceinline__ void run_ops(Ctx<RPT, NT, TC>& c) {
       }
     }
     c.gop = a.ops + i;
+    if (HEAVY && (op.flags & VBN_F_OUT_PARAMS)) {
+      op_params(c, op);
+      continue;
+    }
     load_fixed(c, op);
     switch (op.kind) {
       case VBN_OP_LG:

@@ -247,7 +247,9 @@ def _cpd_plan(cpd: BaseCPD, device, *, mode: str, parents_kind: str, x_kind: str
         parents["__x__"] = ["__parents__"]
     topo.append("__x__")
     cpds["__x__"] = cpd
-    if mode == "sample":
+    if mode == "params":
+        roles["__x__"] = Role(src="sample", store=True, out_params=True)
+    elif mode == "sample":
         roles["__x__"] = Role(src="sample", store=True, inject=inject)
     else:
         roles["__x__"] = Role(src=x_kind, out_logp=True)
@@ -297,6 +299,36 @@ def cpd_sample(cpd: BaseCPD, parents, n_samples: int, *, noise=None, seed=None) 
         plan.run(b, n_samples, fixed=fixed, inputs=inputs, stores=[out],
                  noise=[noise] if noise is not None else [],
                  seed=draw_seed() if seed is None else seed)
+    return out
+
+
+def cpd_params(cpd: BaseCPD, parents) -> torch.Tensor:
+    """Conditional-distribution parameters per row, [B, S, width] (S = 1 for 2-D parents):
+    LG / GNN loc[D], scale[D]; MDN weights[K], loc[K][D], scale[K][D]; softmax_nn probs[D][C]
+    (vbn/core/cpd_handle.py:40-118).  One launch of the schedule kernel with VBN_F_OUT_PARAMS."""
+    dev = require_cuda(cpd.device)
+    width = cpd.param_width()
+    if cpd.input_dim == 0:
+        b, s, pk, parents = 1, 1, "fixed_q", None
+    else:
+        if parents is None:
+            raise ValueError("parents cannot be None when input_dim > 0")
+        parents = _as_dev(parents, dev)
+        if parents.dim() not in (2, 3) or parents.shape[-1] != cpd.input_dim:
+            raise ValueError(f"Expected parents [B,{cpd.input_dim}] or [B,S,{cpd.input_dim}], got {tuple(parents.shape)}")
+        b = int(parents.shape[0])
+        s = 1 if parents.dim() == 2 else int(parents.shape[1])
+        pk = "fixed_q" if parents.dim() == 2 else "fixed_row"
+    plan = _cpd_plan(cpd, dev, mode="params", parents_kind=pk, x_kind="fixed_row", inject=False)
+    with torch.cuda.device(dev):
+        out = torch.empty(b, s, width, device=dev, dtype=torch.float32)
+        fixed, inputs = None, []
+        if parents is not None:
+            if pk == "fixed_q":
+                fixed = parents.t().contiguous()
+            else:
+                inputs = [parents.contiguous()]
+        plan.run(b, s, fixed=fixed, inputs=inputs, stores=[out])
     return out
 
 

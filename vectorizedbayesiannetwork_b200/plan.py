@@ -30,6 +30,7 @@ class Role:
     store: bool = False      # write the value to an output column
     inject: bool = False     # draws come from caller-supplied noise instead of Philox
     density: bool = True     # False: the node's CPD is never evaluated (do / plain clamp)
+    out_params: bool = False  # write the conditional-distribution parameters instead of drawing
 
 
 @dataclass
@@ -247,8 +248,11 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
                                     sl[0] | (sl[1] << 16), sl[2] | (sl[3] << 16), 0]
                     if (pk.kind == L.OP_MDN and int(op["tc"][0]) and d == 1 and 2 <= pk.k <= 5
                             and r.src == "sample" and not r.shared and not r.inject
-                            and not r.add_logw and not r.out_logp):
+                            and not r.add_logw and not r.out_logp and not r.out_params):
                         flags |= L.F_MDNPLAIN
+            if r.out_params:
+                flags |= L.F_OUT_PARAMS
+                heavy = True  # the read-out lives in the HEAVY kernels only
             if flags & L.F_LGFAST:
                 op["aux"][3] = op["n_off"]
                 if (r.src == "sample" and not r.shared and not r.inject and not r.store
