@@ -208,6 +208,19 @@ int32_t vbn_ess_below(const float* stats_dev, int64_t n_queries, float threshold
                       int32_t* flag_dev, void* stream);
 
 /*
+ * Posterior summary, VBN._posterior_stats (vbn/vbn.py:483-504): weights = pdf sanitised
+ * (nan/inf -> 0, clamp >= 0) and normalised over S (uniform 1/S when their sum <= eps);
+ * weighted mean / std per output dim and ESS = 1 / sum w^2.
+ *   pdf_dev [B,S], samples_dev [B,S,D] contiguous, D <= 8
+ *   partials_dev : [B][n_split][10] workspace
+ *   stats_dev    : [B][2+2D] = {sum of raw weights, ess, mean[D], std[D]}
+ * Four launches (two-pass moments like the reference).
+ */
+int32_t vbn_posterior_stats(const float* pdf_dev, const float* samples_dev, int64_t n_queries,
+                            int64_t n_samples, int32_t dim, int32_t n_split, float eps,
+                            float* partials_dev, float* stats_dev, void* stream);
+
+/*
  * KDE conditional log-density over M query rows against N stored points
  * (vbn/cpds/kde.py:111-149): out[m] = LSE_n(log_kp + log_ky) - LSE_n(log_kp)
  * (root, dp == 0: LSE_n(log_ky) - ln N).  Stored points / queries are row-major

@@ -97,6 +97,31 @@ int32_t vbn_ess_below(const float* st, int64_t B, float thr, int32_t* flag, void
   for (int64_t b = 0; b < B; ++b) if (st[b * 3 + 1] * st[b * 3 + 1] / st[b * 3 + 2] < thr) *flag |= 1;
   return 0;
 }
+int32_t vbn_posterior_stats(const float* pdf, const float* x, int64_t B, int64_t S, int32_t D, int32_t, float eps,
+                            float*, float* stats, void*) {
+  for (int64_t b = 0; b < B; ++b) {
+    float* st = stats + b * (2 + 2 * D);
+    double sw = 0, sw2 = 0;
+    std::vector<double> m(D, 0.0), v(D, 0.0);
+    auto wt = [&](int64_t i) { float w = pdf[b * S + i]; return (w == w && std::fabs(w) != INFINITY && w > 0) ? w : 0.0f; };
+    for (int64_t i = 0; i < S; ++i) sw += wt(i);
+    const bool uni = !(sw > eps);
+    const double den = uni ? (double)S : sw;
+    for (int64_t i = 0; i < S; ++i) {
+      const double w = uni ? 1.0 : wt(i);
+      sw2 += (w / den) * (w / den);
+      for (int d = 0; d < D; ++d) m[d] += w / den * x[(b * S + i) * D + d];
+    }
+    for (int64_t i = 0; i < S; ++i) {
+      const double w = uni ? 1.0 : wt(i);
+      for (int d = 0; d < D; ++d) { const double df = x[(b * S + i) * D + d] - m[d]; v[d] += w / den * df * df; }
+    }
+    st[0] = (float)sw; st[1] = (float)(1.0 / std::max(sw2, (double)eps));
+    for (int d = 0; d < D; ++d) { st[2 + d] = (float)m[d]; st[2 + D + d] = (float)std::sqrt(std::max(v[d], 0.0)); }
+  }
+  return 0;
+}
+
 int32_t vbn_kde_log_prob(const float* tp, const float* ty, int64_t N, int32_t dp, int32_t dx, const float* qp,
                          const float* qx, int64_t M, float bw, float pbw, float ms, float* out, void*) {
   const double sy = std::max((double)bw, 1e-3) + ms, sp = std::max((double)pbw, 1e-3) + ms;

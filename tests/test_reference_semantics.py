@@ -401,3 +401,43 @@ def test_conditional_formats_match_the_parameter_heads(backend):
         ms = h.conditional_mean_std(parents, n_samples=64)
         assert torch.isfinite(ms["mean"]).all() and torch.isfinite(ms["std"]).all()
     assert seen == {"normal_params", "mixture_params", "categorical_probs", "empirical_samples"}
+
+
+# ---- VBN._posterior_stats / infer_relative (vbn/vbn.py:483-568; tests/test_gaussian_exact_relative.py:40-57)
+def _ref_posterior_stats(pdf, samples, eps=1e-12):
+    weights = torch.nan_to_num(pdf, nan=0.0, posinf=0.0, neginf=0.0).clamp_min(0.0)
+    denom = weights.sum(dim=1, keepdim=True)
+    uniform = torch.full_like(weights, 1.0 / max(1, weights.shape[1]))
+    weights = torch.where(denom > eps, weights / denom.clamp_min(eps), uniform)
+    mean = (weights.unsqueeze(-1) * samples).sum(dim=1)
+    var = (weights.unsqueeze(-1) * (samples - mean.unsqueeze(1)) ** 2).sum(dim=1)
+    return mean, var.clamp_min(0.0).sqrt(), 1.0 / (weights**2).sum(dim=1).clamp_min(eps)
+
+
+def test_posterior_stats_match_the_reference_formula(backend):
+    g = torch.Generator().manual_seed(0)
+    pdf = torch.rand(6, 777, generator=g)
+    pdf[1, 5] = float("nan")
+    pdf[2, 7] = float("inf")
+    pdf[3] = 0.0  # degenerate query -> uniform weights
+    pdf[4, 10] = -3.0
+    samples = 3.0 + 2.0 * torch.randn(6, 777, 2, generator=g)
+    model = _chain(backend.device)
+    got = model._posterior_stats(pdf.to(backend.device), samples.to(backend.device))
+    mean, std, ess = _ref_posterior_stats(pdf.double(), samples.double())
+    torch.testing.assert_close(got["mean"].cpu().double(), mean, rtol=2e-5, atol=1e-5)
+    torch.testing.assert_close(got["std"].cpu().double(), std, rtol=2e-5, atol=1e-5)
+    torch.testing.assert_close(got["ess"].cpu().double(), ess, rtol=2e-5, atol=1e-4)
+    with pytest.raises(ValueError):
+        model._posterior_stats(pdf[0], samples)
+
+
+def test_infer_relative_direction(backend):
+    model = _chain(backend.device)
+    model.set_inference_method("likelihood_weighting", n_samples=4000)
+    out = model.infer_relative({"target": "x2", "evidence": {"x0": torch.tensor([[2.0], [3.0]])}})
+    assert out["target"] == "x2" and out["delta_mean"].shape == (2, 1)
+    assert bool((out["delta_mean"] > 0).all())  # slope-1 chain: raising x0 raises x2 (reference test: delta_mean > 0)
+    assert out["query_stats"]["effective_sample_size"].shape == (2,)
+    with pytest.raises(ValueError):
+        model.infer_relative({"target": "x2", "evidence": {}}, {"target": "x1", "evidence": {}})

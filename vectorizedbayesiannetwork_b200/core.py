@@ -343,6 +343,46 @@ class VBN:
         infer_batch_size(evidence, do)
         return Query(target=target, evidence=evidence, do=do)
 
+    # ----- posterior summaries (vbn/vbn.py:483-568) ------------------------------------------------
+    def _posterior_stats(self, pdf: torch.Tensor, samples: torch.Tensor, *, eps: float = 1e-12):
+        from .engine import posterior_stats
+
+        return posterior_stats(pdf, samples, eps)
+
+    posterior_stats = _posterior_stats
+
+    @staticmethod
+    def _broadcast_batch(a: torch.Tensor, b: torch.Tensor):
+        if a.shape[0] == b.shape[0]:
+            return a, b
+        if a.shape[0] == 1:
+            return a.expand(b.shape[0], *a.shape[1:]), b
+        if b.shape[0] == 1:
+            return a, b.expand(a.shape[0], *b.shape[1:])
+        raise ValueError("Query and reference batch sizes must match, unless one of them is 1.")
+
+    def infer_relative(self, query, reference_query=None, *, eps: float = 1e-12, **kwargs):
+        q = self._normalize_query(query)
+        if reference_query is None:
+            reference_query = Query(target=q.target, evidence={}, do={})
+        rq = self._normalize_query(reference_query)
+        if rq.target != q.target:
+            raise ValueError("query and reference_query must have the same target node.")
+        qs = self._posterior_stats(*self.infer_posterior(q, **kwargs), eps=eps)
+        rs = self._posterior_stats(*self.infer_posterior(rq, **kwargs), eps=eps)
+        qm, rm = self._broadcast_batch(qs["mean"], rs["mean"])
+        qsd, rsd = self._broadcast_batch(qs["std"], rs["std"])
+        qe, re_ = self._broadcast_batch(qs["ess"], rs["ess"])
+        dm, dsd = qm - rm, qsd - rsd
+        return {
+            "target": q.target,
+            "query_stats": {"mean": qm, "std": qsd, "effective_sample_size": qe},
+            "reference_stats": {"mean": rm, "std": rsd, "effective_sample_size": re_},
+            "delta_mean": dm, "delta_std": dsd,
+            "relative_mean_change": dm / rm.abs().clamp_min(eps),
+            "relative_std_change": dsd / rsd.abs().clamp_min(eps),
+        }
+
     # ----- CPD access (vbn/vbn.py:633-642) -------------------------------------------------------
     def cpd(self, node: str):
         from .cpd_handle import CPDHandle

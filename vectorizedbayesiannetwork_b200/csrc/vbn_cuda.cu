@@ -275,6 +275,27 @@ int32_t vbn_ess_below(const float* stats_dev, int64_t n_queries, float threshold
   return VBN_OK;
 }
 
+int32_t vbn_posterior_stats(const float* pdf_dev, const float* samples_dev, int64_t n_queries,
+                            int64_t n_samples, int32_t dim, int32_t n_split, float eps,
+                            float* partials_dev, float* stats_dev, void* stream) {
+  if (!pdf_dev || !samples_dev || !partials_dev || !stats_dev || n_queries <= 0 || n_samples <= 0 ||
+      dim <= 0 || dim > vbn::kStatsMaxDim || n_split <= 0)
+    return fail(VBN_E_INVALID, "bad argument to vbn_posterior_stats (dim must be 1..%d)", vbn::kStatsMaxDim);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dim3 grid(static_cast<unsigned>(n_queries), n_split);
+  const unsigned mg = static_cast<unsigned>((n_queries + 127) / 128);
+  vbn::posterior_partials_kernel<0><<<grid, 256, 0, st>>>(pdf_dev, samples_dev, n_samples, dim, n_split,
+                                                          stats_dev, eps, partials_dev);
+  vbn::posterior_merge_kernel<0><<<mg, 128, 0, st>>>(partials_dev, pdf_dev, samples_dev, n_queries, n_samples,
+                                                     dim, n_split, eps, stats_dev);
+  vbn::posterior_partials_kernel<1><<<grid, 256, 0, st>>>(pdf_dev, samples_dev, n_samples, dim, n_split,
+                                                          stats_dev, eps, partials_dev);
+  vbn::posterior_merge_kernel<1><<<mg, 128, 0, st>>>(partials_dev, pdf_dev, samples_dev, n_queries, n_samples,
+                                                     dim, n_split, eps, stats_dev);
+  CUDA_TRY(cudaGetLastError());
+  return VBN_OK;
+}
+
 int32_t vbn_kde_log_prob(const float* train_p_dev, const float* train_y_dev, int64_t n_points,
                          int32_t dp, int32_t dx, const float* query_p_dev,
                          const float* query_x_dev, int64_t n_rows, float bandwidth,

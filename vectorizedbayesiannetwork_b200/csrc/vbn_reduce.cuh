@@ -131,6 +131,122 @@ __global__ void ess_below_kernel(const float* __restrict__ stats, int64_t n_quer
   if (ess < threshold) atomicOr(flag, 1);
 }
 
+// ---------------------------------------------------------------------------------------
+// Posterior summary (VBN._posterior_stats, vbn/vbn.py:483-504): per query, weights = sanitised pdf
+// normalised over S (uniform when the sum is <= eps), mean / std of the weighted samples per
+// output dim, ESS = 1 / sum w^2.  Two passes like the reference (mean first, then the centred
+// second moment) so fp32 keeps its digits.  HBM-bound: pdf and samples are read twice.
+//   pass 0 partials per (query, split): {sum w, sum w^2, sum w x_d ...}
+//   pass 1 partials per (query, split): {sum w (x_d - mean_d)^2 ...}
+// ---------------------------------------------------------------------------------------
+constexpr int kStatsMaxDim = 8;
+
+__device__ __forceinline__ float sanitize_weight(float w) {
+  // nan_to_num(nan=0, posinf=0, neginf=0).clamp_min(0)
+  return (w == w && fabsf(w) != CUDART_INF_F && w > 0.0f) ? w : 0.0f;
+}
+
+__device__ __forceinline__ float block_sum256(float v, float* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  float t = lane < 8 ? sh[lane] : 0.0f;
+  if (warp == 0) {
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  return t;  // valid in warp 0
+}
+
+// grid (B, n_split), 256 threads.  PASS 0: sums; PASS 1: centred second moments (needs stats).
+template <int PASS>
+__global__ void __launch_bounds__(256) posterior_partials_kernel(
+    const float* __restrict__ pdf, const float* __restrict__ samples, int64_t n_samples, int dim,
+    int n_split, const float* __restrict__ stats, float eps, float* __restrict__ partials) {
+  __shared__ float sh[8];
+  const int64_t b = blockIdx.x;
+  const int sp = blockIdx.y;
+  const int64_t chunk = (n_samples + n_split - 1) / n_split;
+  const int64_t lo = sp * chunk;
+  const int64_t hi = lo + chunk < n_samples ? lo + chunk : n_samples;
+  const float* w = pdf + b * n_samples;
+  const float* x = samples + b * n_samples * dim;
+  const int width = PASS == 0 ? 2 + dim : dim;
+  float acc[2 + kStatsMaxDim];
+#pragma unroll
+  for (int i = 0; i < 2 + kStatsMaxDim; ++i) acc[i] = 0.0f;
+  float mean[kStatsMaxDim];
+  bool uniform = false;
+  if (PASS == 1) {
+    const float* st = stats + b * (2 + 2 * dim);  // {sum w, ess, mean[d], std[d]}
+    uniform = !(st[0] > eps);
+    for (int d = 0; d < dim; ++d) mean[d] = st[2 + d];
+  }
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const float wi = sanitize_weight(__ldg(w + i));
+    if (PASS == 0) {
+      acc[0] += wi;
+      acc[1] += wi * wi;
+      for (int d = 0; d < dim; ++d) {
+        const float xv = __ldg(x + i * dim + d);
+        acc[2 + d] += wi * xv;
+      }
+    } else {
+      const float wu = uniform ? 1.0f : wi;
+      for (int d = 0; d < dim; ++d) {
+        const float df = __ldg(x + i * dim + d) - mean[d];
+        acc[d] += wu * df * df;
+      }
+    }
+  }
+  for (int k = 0; k < width; ++k) {
+    const float t = block_sum256(acc[k], sh);
+    if (threadIdx.x == 0) partials[(b * n_split + sp) * (2 + kStatsMaxDim) + k] = t;
+  }
+}
+
+// plain sums of x for the uniform-weights fallback are folded in here: when sum w <= eps the
+// reference uses w = 1/S, so the mean is the plain sample mean; pass 0b recomputes it cheaply.
+// One thread per query.  PASS 0: partials -> stats {sum w, ess, mean[d], (std unset)};
+// PASS 1: partials -> std[d].
+template <int PASS>
+__global__ void posterior_merge_kernel(const float* __restrict__ partials, const float* __restrict__ pdf,
+                                       const float* __restrict__ samples, int64_t n_queries,
+                                       int64_t n_samples, int dim, int n_split, float eps,
+                                       float* __restrict__ stats) {
+  const int64_t b = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (b >= n_queries) return;
+  float* st = stats + b * (2 + 2 * dim);
+  float acc[2 + kStatsMaxDim];
+  for (int k = 0; k < 2 + kStatsMaxDim; ++k) acc[k] = 0.0f;
+  const int width = PASS == 0 ? 2 + dim : dim;
+  for (int i = 0; i < n_split; ++i)
+    for (int k = 0; k < width; ++k) acc[k] += partials[(b * n_split + i) * (2 + kStatsMaxDim) + k];
+  if (PASS == 0) {
+    const float sw = acc[0];
+    st[0] = sw;
+    if (sw > eps) {
+      const float den = fmaxf(sw, eps);
+      st[1] = __fdiv_rn(1.0f, fmaxf(__fdiv_rn(acc[1], den * den), eps));  // 1 / sum (w/den)^2
+      for (int d = 0; d < dim; ++d) st[2 + d] = __fdiv_rn(acc[2 + d], den);
+    } else {  // uniform weights 1/S (degenerate query): plain mean, ESS = S
+      st[1] = __fdiv_rn(1.0f, fmaxf(__fdiv_rn(1.0f, static_cast<float>(n_samples)), eps));
+      for (int d = 0; d < dim; ++d) {
+        float m = 0.0f;
+        for (int64_t i = 0; i < n_samples; ++i) m += samples[(b * n_samples + i) * dim + d];
+        st[2 + d] = __fdiv_rn(m, static_cast<float>(n_samples));
+      }
+    }
+  } else {
+    const float sw = st[0];
+    const float den = sw > eps ? fmaxf(sw, eps) : static_cast<float>(n_samples);
+    for (int d = 0; d < dim; ++d) st[2 + dim + d] = sqrtf(fmaxf(__fdiv_rn(acc[d], den), 0.0f));
+  }
+}
+
 __global__ void philox_fill_kernel(const uint32_t* __restrict__ ctr, int64_t n, uint32_t k0,
                                    uint32_t k1, uint32_t* __restrict__ out) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;

@@ -214,6 +214,30 @@ def normalize_weights(logw: torch.Tensor, stats: torch.Tensor, *, normalize: boo
     return w, ess
 
 
+def posterior_stats(pdf: torch.Tensor, samples: torch.Tensor, eps: float = 1e-12):
+    """VBN._posterior_stats (vbn/vbn.py:483-504) on the GPU: dict(mean [B,D], std [B,D], ess [B])."""
+    if pdf.dim() != 2:
+        raise ValueError(f"Expected pdf with shape [B,S], got {tuple(pdf.shape)}")
+    if samples.dim() != 3:
+        raise ValueError(f"Expected samples with shape [B,S,D], got {tuple(samples.shape)}")
+    if pdf.shape[0] != samples.shape[0] or pdf.shape[1] != samples.shape[1]:
+        raise ValueError("pdf and samples shapes are incompatible.")
+    lib = L.load()
+    dev = require_cuda(pdf.device)
+    b, s = pdf.shape
+    d = int(samples.shape[2])
+    pdf = pdf.to(device=dev, dtype=torch.float32).contiguous()
+    samples = samples.to(device=dev, dtype=torch.float32).contiguous()
+    split = pick_split(b, s)
+    with torch.cuda.device(dev):
+        partials = torch.empty(b, split, 10, device=dev, dtype=torch.float32)
+        stats = torch.empty(b, 2 + 2 * d, device=dev, dtype=torch.float32)
+        L.check(lib.vbn_posterior_stats(pdf.data_ptr(), samples.data_ptr(), b, s, d, split, float(eps),
+                                        partials.data_ptr(), stats.data_ptr(), _stream_ptr(dev)))
+        L.count_launch(4)
+    return {"mean": stats[:, 2:2 + d], "std": stats[:, 2 + d:2 + 2 * d], "ess": stats[:, 1]}
+
+
 def ess_below(stats: torch.Tensor, threshold: float) -> torch.Tensor:
     lib = L.load()
     dev = stats.device
