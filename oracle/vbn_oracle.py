@@ -504,6 +504,86 @@ def snn_log_prob(c, x, parents):
 
 
 # --------------------------------------------------------------------------------------
+# categorical_table  (vbn/cpds/categorical_table.py:12-21, 232-255, 359-417)  -- SURVEY 8f row 3
+# spec: counts [D, n_cfg, C] (smoothing already applied by fit), class_values [D, C],
+#       class_mask [D, C], parent_values [tensor per parent dim], parent_strides [int per parent dim]
+# --------------------------------------------------------------------------------------
+
+
+def ct_map_values(values: torch.Tensor, support: torch.Tensor) -> torch.Tensor:
+    support = support.contiguous()
+    values = values.contiguous()
+    idx = torch.searchsorted(support, values)  # :12-21
+    if torch.any(idx < 0) or torch.any(idx >= support.shape[0]):
+        raise ValueError("Found values outside support.")
+    if not torch.all(support[idx] == values):
+        raise ValueError("Found values outside support.")
+    return idx
+
+
+def ct_parents_to_index(c, parents: torch.Tensor) -> torch.Tensor:
+    if c["input_dim"] == 0:  # :232-245
+        return torch.zeros(parents.shape[0], dtype=torch.long)
+    idx = torch.zeros(parents.shape[0], dtype=torch.long)
+    for d, support in enumerate(c["parent_values"]):
+        idx = idx + ct_map_values(parents[:, d], support.to(dtype=parents.dtype)) * int(c["parent_strides"][d])
+    return idx
+
+
+def ct_logits(c, parents: Optional[torch.Tensor]) -> torch.Tensor:
+    counts = c["counts"]
+    d = c["output_dim"]
+    if parents is None:  # :371-378
+        probs = counts / counts.sum(dim=-1, keepdim=True).clamp_min(1e-12)
+        return torch.log(probs.clamp_min(1e-12)).view(1, 1, d, -1)
+    if parents.dim() == 2:  # :359-369
+        parents = parents.unsqueeze(1)
+    b, s, dp = parents.shape
+    parent_idx = ct_parents_to_index(c, parents.reshape(b * s, dp))
+    probs = counts[:, parent_idx, :]
+    probs = probs / probs.sum(dim=-1, keepdim=True).clamp_min(1e-12)
+    logits = torch.log(probs.clamp_min(1e-12))
+    return logits.permute(1, 0, 2).reshape(b, s, d, -1)
+
+
+def ct_sample(c, parents, n, noise, key):
+    d = c["output_dim"]
+    if c["input_dim"] == 0:  # :379-396
+        b = 1 if parents is None else parents.shape[0]
+        logits = ct_logits(c, None).expand(b, n, -1, -1)
+    else:
+        if parents is None:
+            raise ValueError("parents cannot be None when input_dim > 0")
+        logits = ct_logits(c, broadcast_samples(parents, n))
+    indices = noise.categorical_logits(key, logits)
+    values = c["class_values"].to(dtype=logits.dtype).view(1, 1, d, -1)
+    values = values.expand(indices.shape[0], indices.shape[1], -1, -1)
+    return values.gather(-1, indices.unsqueeze(-1)).squeeze(-1)
+
+
+def ct_log_prob(c, x, parents):
+    if x.dim() <= 2:  # :398-417
+        x = ensure_2d(x)
+    if x.dim() == 2:
+        x = x.unsqueeze(1)
+    d = c["output_dim"]
+    if c["input_dim"] == 0:
+        logits = ct_logits(c, None).expand(x.shape[0], x.shape[1], -1, -1)
+    else:
+        if parents is None:
+            raise ValueError("parents cannot be None when input_dim > 0")
+        logits = ct_logits(c, broadcast_samples(parents, x.shape[1]))
+    log_probs = torch.log_softmax(logits, dim=-1)
+    x_flat = x.reshape(-1, x.shape[-1])
+    targets = torch.zeros(x_flat.shape[0], d, dtype=torch.long)
+    for k in range(d):  # :246-255
+        support = c["class_values"][k][c["class_mask"][k]].to(dtype=x_flat.dtype)
+        targets[:, k] = ct_map_values(x_flat[:, k], support)
+    targets = targets.reshape(x.shape[0], x.shape[1], d)
+    return log_probs.gather(-1, targets.unsqueeze(-1)).squeeze(-1).sum(dim=-1)
+
+
+# --------------------------------------------------------------------------------------
 # kde  (vbn/cpds/kde.py:105-182)
 # --------------------------------------------------------------------------------------
 
@@ -576,6 +656,7 @@ _SAMPLE = {
     "mdn": mdn_sample,
     "softmax_nn": snn_sample,
     "kde": kde_sample,
+    "categorical_table": ct_sample,
 }
 _LOG_PROB = {
     "linear_gaussian": lg_log_prob,
@@ -583,6 +664,7 @@ _LOG_PROB = {
     "mdn": mdn_log_prob,
     "softmax_nn": snn_log_prob,
     "kde": kde_log_prob,
+    "categorical_table": ct_log_prob,
 }
 
 
@@ -934,6 +1016,11 @@ def cpd_spec_from_reference(cpd) -> dict:
                 "parent_bandwidth": float(cpd.parent_bandwidth), "min_scale": float(cpd.min_scale),
                 "parents": None if cpd._parents is None else g(cpd._parents),
                 "targets": None if cpd._targets is None else g(cpd._targets)}
+    if name == "CategoricalTableCPD":
+        return {**base, "kind": "categorical_table", "n_classes": int(cpd.n_classes),
+                "counts": g(cpd._counts), "class_values": g(cpd._class_values), "class_mask": g(cpd._class_mask),
+                "parent_values": [g(v) for v in (cpd._parent_values or [])],
+                "parent_strides": [int(v) for v in (cpd._parent_strides or [])]}
     raise ValueError(f"CPD type '{name}' is outside the hot-path scope")
 
 

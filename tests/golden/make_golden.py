@@ -67,7 +67,11 @@ def cpd_cases(model, spec, S=9, seed=3):
     for node, cpd in model.nodes.items():
         c = spec["cpds"][node]
         dp = c["input_dim"]
-        variants = [None] if dp == 0 else [torch.randn(4, dp), torch.randn(4, S, dp)]
+        if c["kind"] == "categorical_table" and dp:
+            pick = lambda *shape: torch.stack([v[torch.randint(0, v.numel(), shape)] for v in c["parent_values"]], dim=-1)
+            variants = [pick(4), pick(4, S)]
+        else:
+            variants = [None] if dp == 0 else [torch.randn(4, dp), torch.randn(4, S, dp)]
         for parents in variants:
             rec = O.RecordingNoise()
             torch.manual_seed(seed)
@@ -82,7 +86,34 @@ def cpd_cases(model, spec, S=9, seed=3):
     return out
 
 
+def table_files():
+    """categorical_table + discrete softmax_nn model; generated on its own so the
+    earlier fixtures stay byte-identical:  python tests/golden/make_golden.py table"""
+    torch.manual_seed(4321)
+    m = refmodels.table_model()
+    spec = O.spec_from_reference(m)
+    qs = [{"target": "rain", "evidence": {"slip": torch.tensor([[1.0], [0.0]]), "wet": torch.tensor([[2.0], [1.0]])}},
+          {"target": "slip", "evidence": {"season": torch.tensor([[3.0], [0.0], [1.0]])}},
+          {"target": "season", "evidence": {"slip": torch.tensor([[1.0]]), "sprinkler": torch.tensor([[0.0]])}},
+          {"target": "wet", "evidence": {}, "do": {"rain": torch.tensor([[1.0], [0.0]])}}]
+    cases = [run_case(m, spec, q, 64, meth, 17) for q in qs for meth in ("lw", "is", "mcm", "anc")]
+    return {"table": {"spec": spec, "cases": cases, "cpd_cases": cpd_cases(m, spec)}}
+
+
+def save(files):
+    total = 0
+    for name, blob in files.items():
+        path = os.path.join(HERE, f"{name}.pt")
+        torch.save(blob, path)
+        total += os.path.getsize(path)
+        print(f"{name}: {len(blob['cases'])} cases, {len(blob['cpd_cases'])} cpd cases, {os.path.getsize(path)/1024:.0f} KiB")
+    print(f"total {total/1024:.0f} KiB")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "table":
+        save(table_files())
+        return
     torch.manual_seed(1234)
     files = {}
 
@@ -145,13 +176,8 @@ def main():
     cases = [run_case(m, spec, q, 40, meth, 15) for q in qs for meth in ("lw", "is", "mcm", "anc")]
     files["kde"] = {"spec": spec, "cases": cases, "cpd_cases": cpd_cases(m, spec)}
 
-    total = 0
-    for name, blob in files.items():
-        path = os.path.join(HERE, f"{name}.pt")
-        torch.save(blob, path)
-        total += os.path.getsize(path)
-        print(f"{name}: {len(blob['cases'])} cases, {len(blob['cpd_cases'])} cpd cases, {os.path.getsize(path)/1024:.0f} KiB")
-    print(f"total {total/1024:.0f} KiB")
+    files.update(table_files())
+    save(files)
 
 
 if __name__ == "__main__":

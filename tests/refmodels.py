@@ -136,6 +136,33 @@ def discrete_model(rows=600, epochs=5, seed=0):
     return _fit(g, cpds, data)
 
 
+def table_model(rows=800, epochs=4, seed=0):
+    """Discrete BN mixing categorical_table and softmax_nn (discrete mode) nodes, incl. a 4-state node:
+    rain(ct,2) -> wet(ct,3) <- sprinkler(snn,2);  wet -> slip(snn,2);  season(ct,4) -> rain."""
+    import networkx as nx
+
+    gen = torch.Generator().manual_seed(seed)
+    g = nx.DiGraph()
+    g.add_edges_from([("season", "rain"), ("rain", "wet"), ("sprinkler", "wet"), ("wet", "slip")])
+    u = lambda: torch.rand(rows, generator=gen)
+    season = torch.randint(0, 4, (rows,), generator=gen).float()
+    rain = (u() < 0.15 + 0.15 * season).float()
+    spr = (u() < 0.5).float()
+    wet = torch.clamp(rain + spr + (u() < 0.2).float() - (u() < 0.2).float(), 0, 2)
+    slip = ((wet > 0) & (u() < 0.6)).float()
+    fit = {"epochs": epochs, "batch_size": 128}
+    cpds = {
+        "season": {"cpd": "categorical_table"},
+        "rain": {"cpd": "categorical_table", "alpha": 0.5},
+        "sprinkler": {"cpd": "softmax_nn", "n_classes": 2, "fit": fit},
+        "wet": {"cpd": "categorical_table", "alpha": 1.0, "alpha_mode": "total_mass", "prior": "global"},
+        "slip": {"cpd": "softmax_nn", "n_classes": 2, "fit": fit},
+    }
+    data = {"season": season[:, None], "rain": rain[:, None], "sprinkler": spr[:, None], "wet": wet[:, None],
+            "slip": slip[:, None]}
+    return _fit(g, cpds, data)
+
+
 def binned_model(within_bin="uniform", clip=False, rows=400, epochs=3, seed=0, dim=2):
     """softmax_nn in binned-continuous mode, root + child, D=dim."""
     import networkx as nx

@@ -110,6 +110,18 @@ def test_discrete_softmax_model():
         O.likelihood_weighting(spec, {"target": "rain", "evidence": {"wet": torch.tensor([[0.5]])}}, 8)
 
 
+def test_categorical_table_model():
+    """categorical_table (vbn/cpds/categorical_table.py) mixed with discrete softmax_nn nodes."""
+    model = refmodels.table_model()
+    spec = O.spec_from_reference(model)
+    q = {"target": "rain", "evidence": {"slip": torch.tensor([[1.0], [0.0]]), "wet": torch.tensor([[2.0], [1.0]])}}
+    _run_methods(model, spec, q, 64)
+    q = {"target": "slip", "evidence": {"season": torch.tensor([[3.0], [0.0], [1.0]])}}
+    _run_methods(model, spec, q, 64)
+    with pytest.raises(ValueError):  # parent value outside the table's support (categorical_table.py:12-21)
+        O.likelihood_weighting(spec, {"target": "slip", "evidence": {"rain": torch.tensor([[0.5]])}}, 8)
+
+
 @pytest.mark.parametrize("within_bin,clip", [("uniform", False), ("triangular", False),
                                              ("gaussian", False), ("uniform", True),
                                              ("triangular", True)])

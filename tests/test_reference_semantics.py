@@ -441,3 +441,25 @@ def test_infer_relative_direction(backend):
     assert out["query_stats"]["effective_sample_size"].shape == (2,)
     with pytest.raises(ValueError):
         model.infer_relative({"target": "x2", "evidence": {}}, {"target": "x1", "evidence": {}})
+
+
+# ---- categorical_table (vbn/cpds/categorical_table.py) ---------------------------
+def test_categorical_table_strict_support_and_conditional(backend):
+    import os
+
+    blob = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "table.pt"),
+                      weights_only=False)
+    spec = blob["spec"]
+    model = V.VBN.from_spec(spec, device=backend.device)
+    model.set_inference_method("likelihood_weighting", n_samples=16)
+    # "wet" is a categorical_table with parents (rain, sprinkler): an off-support rain value must raise
+    with pytest.raises(ValueError):
+        model.infer_posterior({"target": "slip", "do": {"rain": torch.tensor([[0.5]])}})
+    w, s = model.infer_posterior({"target": "slip", "do": {"rain": torch.tensor([[1.0]])}})
+    assert set(s.unique().tolist()) <= {0.0, 1.0}
+    h = model.get_cpd("wet")
+    out = h.conditional({"rain": torch.tensor([[1.0], [0.0]]), "sprinkler": torch.tensor([[0.0], [1.0]])})
+    assert out["format"] == "categorical_probs" and out["k"] == 3
+    probs = torch.tensor(out["probs"])
+    want = torch.softmax(O.ct_logits(spec["cpds"]["wet"], torch.tensor([[1.0, 0.0], [0.0, 1.0]])), dim=-1)
+    torch.testing.assert_close(probs, want.reshape(probs.shape), rtol=1e-5, atol=1e-7)

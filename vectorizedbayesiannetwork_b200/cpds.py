@@ -563,15 +563,111 @@ class KDECPD(BaseCPD):
 
 
 # ------------------------------------------------------------------------------------------
+class CategoricalTableCPD(BaseCPD):
+    """vbn/cpds/categorical_table.py:24-417: count table with Dirichlet smoothing.
+    Inference-time state only (counts already smoothed by the reference's fit).  D = 1 on the GPU path."""
+
+    kind = "categorical_table"
+
+    def __init__(self, input_dim, output_dim, *, counts, class_values, class_mask, parent_values=(),
+                 parent_strides=(), n_classes=None, device=None):
+        super().__init__(input_dim, output_dim, device)
+        self._counts = _f32(counts)
+        d = self.output_dim
+        self._class_values = _f32(class_values).reshape(d, -1)
+        self._sample_values = self._class_values
+        self._class_mask = torch.as_tensor(class_mask).detach().cpu().bool().reshape(d, -1)
+        self.n_classes = int(n_classes if n_classes is not None else self._class_values.shape[1])
+        self._parent_values = [_f32(v).reshape(-1) for v in parent_values]
+        self._parent_strides = [int(v) for v in parent_strides]
+        if len(self._parent_values) != self.input_dim:
+            raise ValueError("categorical_table needs one support vector per parent dim")
+
+    @property
+    def n_support(self) -> int:
+        return int(self._class_mask[0].sum())
+
+    def param_width(self) -> int:
+        return 0  # conditional() of a table is served on the host from the table itself
+
+    def logits_table(self) -> torch.Tensor:
+        """[n_cfg, C] log-probabilities: log_softmax(log(clamp(counts / sum, 1e-12)))  (:359-369, :413)."""
+        probs = self._counts[0] / self._counts[0].sum(dim=-1, keepdim=True).clamp_min(1e-12)
+        return torch.log_softmax(torch.log(probs.clamp_min(1e-12)), dim=-1)
+
+    def _pack(self) -> Packed:
+        if self.output_dim != 1:
+            raise ValueError("categorical_table with output_dim > 1 has no CUDA implementation yet")
+        if self.n_classes > TABLE_MAX_CLASSES or any(v.numel() > TABLE_MAX_CLASSES for v in self._parent_values):
+            raise ValueError(f"categorical_table supports at most {TABLE_MAX_CLASSES} classes per variable on the GPU")
+        if not bool(self._class_mask[0].all()):
+            # masked (padding) classes keep their clamp(1e-12) mass in the reference's softmax; they
+            # are kept as classes here too, but can never match an observed value
+            pass
+        logp = self.logits_table()
+        params = _tab_params(self.n_classes, logp, self._parent_values, self._parent_strides,
+                             self._class_values[0], torch.where(self._class_mask[0], self._class_values[0],
+                                                                torch.full_like(self._class_values[0], float("nan"))),
+                             strict=True)
+        return Packed(kind=L.OP_TAB, dim=1, n_par=self.input_dim, params=params, k=self.n_classes,
+                      n_normals=0, n_uniforms=1, scratch=0, heavy=False)
+
+    @classmethod
+    def from_spec(cls, c, device=None):
+        return cls(c["input_dim"], c["output_dim"], counts=c["counts"], class_values=c["class_values"],
+                   class_mask=c["class_mask"], parent_values=c.get("parent_values", ()),
+                   parent_strides=c.get("parent_strides", ()), n_classes=c.get("n_classes"), device=device)
+
+    @classmethod
+    def from_reference(cls, cpd, device=None):
+        return cls(cpd.input_dim, cpd.output_dim, counts=cpd._counts, class_values=cpd._class_values,
+                   class_mask=cpd._class_mask, parent_values=cpd._parent_values or (),
+                   parent_strides=cpd._parent_strides or (), n_classes=cpd.n_classes, device=device)
+
+    def to_spec(self):
+        return {"kind": self.kind, "input_dim": self.input_dim, "output_dim": self.output_dim,
+                "n_classes": self.n_classes, "counts": self._counts, "class_values": self._class_values,
+                "class_mask": self._class_mask, "parent_values": self._parent_values,
+                "parent_strides": self._parent_strides}
+
+
+# ------------------------------------------------------------------------------------------
 # discrete-parent lookup tables (VBN_OP_TAB)
 # ------------------------------------------------------------------------------------------
 _TABLE_CACHE: Dict[tuple, Packed] = {}
 TABLE_MAX_CONFIGS = 4096
 
 
+TABLE_MAX_CLASSES = 64
+
+
 def _is_plain_discrete(cpd) -> bool:
+    if isinstance(cpd, CategoricalTableCPD):
+        return cpd.output_dim == 1 and cpd.n_support <= TABLE_MAX_CLASSES
     return (isinstance(cpd, SoftmaxNNCPD) and cpd.output_dim == 1 and cpd._bins_ready
-            and bool(cpd._is_discrete.all()) and cpd.n_classes <= 8)
+            and bool(cpd._is_discrete.all()) and cpd.n_classes <= TABLE_MAX_CLASSES)
+
+
+def _support_of(cpd) -> torch.Tensor:
+    """Values a plain discrete node can take (sorted)."""
+    if isinstance(cpd, CategoricalTableCPD):
+        return cpd._class_values[0][cpd._class_mask[0]]
+    return cpd._class_values[0]
+
+
+def _tab_params(c: int, logp: torch.Tensor, parent_supports: Sequence[torch.Tensor], strides: Sequence[int],
+                sample_values: torch.Tensor, class_values: torch.Tensor, strict: bool) -> np.ndarray:
+    """VBN_OP_TAB parameter block (layout: csrc/vbn_schedule.cuh op_tab)."""
+    n_cfg = int(logp.shape[0])
+    widest = max([c] + [int(v.numel()) for v in parent_supports])
+    cpad = (widest + 7) & ~7
+    cdf = torch.cumsum(torch.exp(logp.double()), dim=1).float()
+    head = [np.array([c, n_cfg, cpad, 1.0 if strict else 0.0], np.float32)]
+    for sup, stride in zip(parent_supports, strides):
+        head.append(np.concatenate([np.array([int(sup.numel()), stride, 0, 0], np.float32), _padded(_np(sup), cpad)]))
+    head += [_padded(_np(sample_values), cpad), _padded(_np(class_values), cpad), _np(cdf), _np(logp)]
+    params = np.concatenate(head)
+    return _padded(params, _pad4(params.size))
 
 
 def table_eligible(cpd, parent_cpds: Sequence[BaseCPD]) -> bool:
@@ -581,9 +677,11 @@ def table_eligible(cpd, parent_cpds: Sequence[BaseCPD]) -> bool:
         return False
     if len(parent_cpds) != cpd.input_dim:
         return False
+    if not isinstance(cpd, SoftmaxNNCPD):
+        return False  # categorical_table nodes pack themselves
     n_cfg = 1
     for pc in parent_cpds:
-        n_cfg *= pc.n_classes
+        n_cfg *= int(_support_of(pc).numel())
     return n_cfg <= TABLE_MAX_CONFIGS
 
 
@@ -597,7 +695,8 @@ def pack_table(cpd, parent_cpds: Sequence[BaseCPD], log_prob_fn) -> Packed:
         return hit
     base = cpd.pack()
     c = cpd.n_classes
-    cards = [pc.n_classes for pc in parent_cpds]
+    supports = [_support_of(pc) for pc in parent_cpds]
+    cards = [int(v.numel()) for v in supports]
     n_cfg = int(np.prod(cards)) if cards else 1
     strides, acc = [], 1
     for card in reversed(cards):
@@ -605,7 +704,7 @@ def pack_table(cpd, parent_cpds: Sequence[BaseCPD], log_prob_fn) -> Packed:
         acc *= card
     strides = strides[::-1]
     if cards:
-        grids = torch.cartesian_prod(*[pc._class_values[0] for pc in parent_cpds]).reshape(n_cfg, len(cards))
+        grids = torch.cartesian_prod(*supports).reshape(n_cfg, len(cards))
     else:
         grids = None
     cols = []
@@ -613,14 +712,8 @@ def pack_table(cpd, parent_cpds: Sequence[BaseCPD], log_prob_fn) -> Packed:
         x = cpd._class_values[0, k].repeat(n_cfg).reshape(n_cfg, 1)
         cols.append(_f32(log_prob_fn(cpd, x, grids)).reshape(n_cfg))
     logp = torch.stack(cols, dim=1)                       # [n_cfg, C]
-    cdf = torch.cumsum(torch.exp(logp.double()), dim=1).float()
-    head = [np.array([c, n_cfg, 0, 0], np.float32)]
-    for pc, card, stride in zip(parent_cpds, cards, strides):
-        head.append(np.concatenate([np.array([card, stride, 0, 0], np.float32),
-                                    _padded(_np(pc._class_values[0]), 8)]))
-    head += [_padded(_np(cpd._sample_values[0]), 8), _padded(_np(cpd._class_values[0]), 8), _np(cdf), _np(logp)]
-    params = np.concatenate(head)
-    pk = Packed(kind=L.OP_TAB, dim=1, n_par=len(cards), params=_padded(params, _pad4(params.size)), k=c,
+    params = _tab_params(c, logp, supports, strides, cpd._sample_values[0], cpd._class_values[0], strict=False)
+    pk = Packed(kind=L.OP_TAB, dim=1, n_par=len(cards), params=params, k=c,
                 n_normals=base.n_normals, n_uniforms=base.n_uniforms, scratch=0, heavy=False)
     if len(_TABLE_CACHE) > 4096:
         _TABLE_CACHE.clear()
@@ -634,6 +727,7 @@ CPD_CLASSES = {
     "mdn": MDNCPD,
     "softmax_nn": SoftmaxNNCPD,
     "kde": KDECPD,
+    "categorical_table": CategoricalTableCPD,
 }
 
 _REFERENCE_CLASS_NAMES = {
@@ -642,6 +736,7 @@ _REFERENCE_CLASS_NAMES = {
     "MDNCPD": MDNCPD,
     "SoftmaxNNCPD": SoftmaxNNCPD,
     "KDECPD": KDECPD,
+    "CategoricalTableCPD": CategoricalTableCPD,
 }
 
 

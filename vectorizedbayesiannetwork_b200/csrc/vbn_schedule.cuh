@@ -815,19 +815,23 @@ __device__ __forceinline__ void op_snn(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
 // discrete too.  Its logits depend only on the parent configuration, so the plan compiler evaluates
 // the node's own log-density once per configuration (through this library's MLP path, i.e. the
 // same numbers the per-row evaluation produces) and the node becomes a table lookup.
-// params: {C, n_cfg, 0, 0}, per parent p < Dp: {card, stride, 0, 0, class_values[8]},
-//         sample_values[8], class_values[8], cdf[n_cfg][C] (running sums of exp(logp)),
+// The same op serves categorical_table CPDs (vbn/cpds/categorical_table.py:359-417), whose
+// parameters ARE such a table; those set `strict`: a parent value outside its support raises
+// (categorical_table.py:12-21), where a softmax_nn would have fed it to its MLP.
+// params: {C, n_cfg, cpad, strict}, per parent p < Dp: {card, stride, 0, 0, class_values[cpad]},
+//         sample_values[cpad], class_values[cpad], cdf[n_cfg][C] (running sums of exp(logp)),
 //         logp[n_cfg][C]
 // ---------------------------------------------------------------------------------------
 template <int RPT, int NT, class TC>
 __device__ __forceinline__ void op_tab(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
   const float* P = c.a.params + op.param_off;
   const int C = op.k, Dp = op.n_par;
-  const int n_cfg = static_cast<int>(__ldg(P + 1));
+  const int n_cfg = static_cast<int>(__ldg(P + 1)), cpad = static_cast<int>(__ldg(P + 2));
+  const bool strict = __ldg(P + 3) != 0.0f;
   const float* pinfo = P + 4;
-  const float* sample_values = pinfo + 12 * Dp;
-  const float* class_values = sample_values + 8;
-  const float* cdf = class_values + 8;
+  const float* sample_values = pinfo + (4 + cpad) * Dp;
+  const float* class_values = sample_values + cpad;
+  const float* cdf = class_values + cpad;
   const float* logp = cdf + n_cfg * C;
   const int32_t* par = c.a.par_slots + op.par_off;
   const bool sample = (op.flags & VBN_SRC_MASK) == VBN_SRC_SAMPLE;
@@ -837,15 +841,19 @@ __device__ __forceinline__ void op_tab(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
 #pragma unroll
   for (int j = 0; j < RPT; ++j) cfg[j] = 0;
   for (int p = 0; p < Dp; ++p) {
-    const float* pi = pinfo + 12 * p;
+    const float* pi = pinfo + (4 + cpad) * p;
     const int card = static_cast<int>(__ldg(pi)), stride = static_cast<int>(__ldg(pi + 1));
     const int ps = __ldg(par + p);
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
       const float v = c.slot(ps, j);
-      int ci = 0;  // a value outside the parent's class set is flagged where that parent is scored
-      for (int q = 1; q < card; ++q)
+      int ci = -1;
+      for (int q = 0; q < card; ++q)
         if (v == __ldg(pi + 4 + q)) ci = q;
+      if (ci < 0) {  // softmax_nn tables: flagged where that parent is itself scored
+        if (strict && c.rows.valid[j] && c.a.error_flag) atomicOr(c.a.error_flag, 1);
+        ci = 0;
+      }
       cfg[j] += ci * stride;
     }
   }
