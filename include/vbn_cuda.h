@@ -146,7 +146,9 @@ typedef struct VbnProgramDesc {
   const int32_t* tc_list_dev; /* [n_tc][2] {image float offset, image bytes} of every op with
                          tc[0] != 0, in schedule order (the weight ring's fetch list)       */
   int32_t n_tc;
-  int32_t reserved;
+  int32_t rows_per_thread; /* FP32-pipe kernel, schedules without MLP/KDE ops: 0 = default (4 rows
+                         per thread, best for drawn linear-Gaussian chains), 2 = table-lookup
+                         heavy schedules (fewer registers, more resident warps)             */
 } VbnProgramDesc;
 
 typedef struct VbnPlan VbnPlan;

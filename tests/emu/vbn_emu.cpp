@@ -47,7 +47,7 @@ int32_t vbn_run_forward(const VbnPlan* plan, const VbnRunDesc* run, void*) {
   a.logp_as_pdf = run->logp_as_pdf; a.n_queries = run->n_queries; a.n_samples = run->n_samples;
   a.n_rows = run->n_queries * run->n_samples;
   a.query_offset = (uint32_t)run->query_offset; a.sample_offset = (uint32_t)run->sample_offset;
-  a.key0 = (uint32_t)run->seed; a.key1 = (uint32_t)(run->seed >> 32); a.call_offset = (uint32_t)run->call_offset;
+  a.key0 = (uint32_t)run->seed; a.key1 = (uint32_t)(run->seed >> 32); a.call_offset = (uint32_t)run->call_offset; vbn::fill_round_keys(a);
   a.fixed = run->fixed_dev; a.inputs = run->inputs_dev; a.stores = run->stores_dev; a.noise = run->noise_dev;
   a.logw = run->logw_dev; a.logp = run->logp_dev; a.error_flag = run->error_flag_dev;
   if ((size_t)(a.n_slots + a.n_scratch) * 2 * 32 > sizeof(vbn::smem) / sizeof(float)) return VBN_E_CAPACITY;

@@ -56,7 +56,10 @@ const Shape kShapes[] = {
     make_shape<2, 128, true, 3>(),
     make_shape<1, 128, true, 3>(),
     make_shape<1, 64, true, 1>(),
+    make_shape<4, 256, false, 2>(),  // best on LG chains (cfg2: 64% of the level-SoA HBM model)
+    make_shape<4, 128, false, 4>(),
     make_shape<2, 256, false, 4>(),
+    make_shape<4, 128, false, 3>(),
     make_shape<2, 256, false, 3>(),
     make_shape<2, 256, false, 2>(),
     make_shape<1, 256, false, 4>(),
@@ -140,11 +143,12 @@ int32_t vbn_plan_create(const VbnProgramDesc* desc, VbnPlan** out_plan) {
     }
     // does not fit: fall through to the FFMA shapes (the ops keep their FFMA parameter blocks)
   }
-  const char* force = std::getenv("VBN_SHAPE");  // dev knob: force one launch shape by index
+  const char* force = desc->heavy ? nullptr : std::getenv("VBN_SHAPE");  // dev knob (light schedules): force a shape
   for (int i = 0; i < static_cast<int>(sizeof(kShapes) / sizeof(kShapes[0])); ++i) {
     const Shape& s = kShapes[i];
     if (s.heavy != (desc->heavy ? 1 : 0)) continue;
     if (force && std::atoi(force) != i) continue;
+    if (!force && !s.heavy && desc->rows_per_thread == 2 && s.rpt > 2) continue;
     const size_t bytes = per_row * s.rpt * s.nt;
     if (bytes > static_cast<size_t>(max_smem)) continue;
     CUDA_TRY(cudaFuncSetAttribute(s.fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -196,6 +200,7 @@ int32_t vbn_run_forward(const VbnPlan* plan, const VbnRunDesc* run, void* stream
   a.key0 = static_cast<uint32_t>(run->seed);
   a.key1 = static_cast<uint32_t>(run->seed >> 32);
   a.call_offset = static_cast<uint32_t>(run->call_offset);
+  vbn::fill_round_keys(a);
   a.fixed = run->fixed_dev;
   a.inputs = run->inputs_dev;
   a.stores = run->stores_dev;

@@ -36,6 +36,22 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
+// Same generator with the ten round keys supplied precomputed (host: key + i * Weyl).  Inlined
+// where `rk` is a kernel parameter, the keys become constant-bank operands of the LOP3s and the
+// twenty key-schedule adds disappear.
+__device__ __forceinline__ uint4 philox4x32_10_rk(uint4 c, const uint32_t (&rk)[20]) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint64_t p0 = static_cast<uint64_t>(M0) * c.x;
+    const uint64_t p1 = static_cast<uint64_t>(M1) * c.z;
+    const uint32_t hi0 = static_cast<uint32_t>(p0 >> 32), lo0 = static_cast<uint32_t>(p0);
+    const uint32_t hi1 = static_cast<uint32_t>(p1 >> 32), lo1 = static_cast<uint32_t>(p1);
+    c = make_uint4(hi1 ^ c.y ^ rk[2 * i], lo1, hi0 ^ c.w ^ rk[2 * i + 1], lo0);
+  }
+  return c;
+}
+
 // uint32 -> float in (0,1): 24 random bits, centred, never 0 or 1.
 __device__ __forceinline__ float u01(uint32_t x) {
   return (static_cast<float>(x >> 8) + 0.5f) * 5.9604644775390625e-8f;  // 2^-24
@@ -43,14 +59,32 @@ __device__ __forceinline__ float u01(uint32_t x) {
 
 // Two uniforms -> two standard normals (Box-Muller).  Fast intrinsics: these only shape the
 // generated noise (no parity requirement on generated bits, only on the law).
+#ifdef VBN_HOST_EMU
 __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
   const float u1 = u01(a);
-  const float u2 = u01(b) - 0.5f;  // angle in (-pi, pi): best range for sin/cos.approx
+  const float u2 = u01(b) - 0.5f;
   const float r = sqrtf(-2.0f * __logf(u1));
   float s, c;
   __sincosf(6.283185307179586f * u2, &s, &c);
   return make_float2(r * c, r * s);
 }
+#else
+// Device version, trimmed to the instruction count that matters for LG-only schedules (one normal
+// per row-node): mantissa-stuffing instead of int->float conversions, raw lg2 / sqrt approximations
+// (u1 >= 2^-24 is never denormal), angle produced by one FFMA.  ~15 instructions per pair.
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  const float f1 = __uint_as_float((a >> 9) | 0x3F800000u);  // [1, 2), 23 random bits
+  const float f2 = __uint_as_float((b >> 9) | 0x3F800000u);
+  const float u1 = f1 - 0.99999994f;                         // (0, 1): 2^-24 .. 1 - 2^-24
+  const float ang = fmaf(f2, 6.283185307179586f, -9.42477796076938f);  // 2 pi (f2 - 1.5) in [-pi, pi)
+  float l, r, s, c;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u1));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * -1.3862943611198906f));  // sqrt(-2 ln u1)
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(ang));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(ang));
+  return make_float2(r * c, r * s);
+}
+#endif
 
 __device__ __forceinline__ float4 normal4(uint4 w) {
   const float2 a = box_muller(w.x, w.y);

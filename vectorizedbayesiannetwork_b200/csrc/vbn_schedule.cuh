@@ -7,6 +7,8 @@
 //   monte_carlo_marginalization.py:39-92, vbn/sampling/ancestral.py:27-41
 // and the CPD bodies they call (cited at each op below).
 #pragma once
+#include <type_traits>
+
 #include "vbn_device.cuh"
 
 namespace vbn {
@@ -35,7 +37,15 @@ struct ScheduleArgs {
   int32_t* error_flag;
   const int2* tc_list;  // tensor-core kernel only: per tc op {image float offset, image bytes}
   int32_t n_tc;
+  uint32_t rk[20];      // Philox round keys: rk[2i] = key0 + i*0x9E3779B9, rk[2i+1] = key1 + i*0xBB67AE85
 };
+
+__host__ __device__ inline void fill_round_keys(ScheduleArgs& a) {
+  for (int i = 0; i < 10; ++i) {
+    a.rk[2 * i] = a.key0 + static_cast<uint32_t>(i) * 0x9E3779B9u;
+    a.rk[2 * i + 1] = a.key1 + static_cast<uint32_t>(i) * 0xBB67AE85u;
+  }
+}
 
 constexpr int kMaxGenericWidth = 128;  // widest layer the generic MLP path accepts
 
@@ -59,6 +69,13 @@ struct Rows {
 // Tensor-core hook: the tcgen05 kernel (vbn_schedule_tc.cuh) plugs its MLP evaluator in here.
 struct NoTc {
   static constexpr bool kEnabled = false;
+  static constexpr bool kInlineRng = false;
+};
+// LG / table-only schedules: the generator is the hot loop, so it is inlined with constant-bank
+// round keys instead of being called out of line.
+struct LightPolicy {
+  static constexpr bool kEnabled = false;
+  static constexpr bool kInlineRng = true;
 };
 
 template <int RPT, int NT, class TC = NoTc>
@@ -85,9 +102,11 @@ struct Ctx {
     return make_uint4(rows.gs[j], shared ? 0xFFFFFFFFu : rows.gb[j], block | (tag << 30), a.call_offset);
   }
   __device__ __forceinline__ float4 normals(int j, uint32_t block, uint32_t tag, bool shared) const {
+    if constexpr (TC::kInlineRng) return normal4(philox4x32_10_rk(counter(j, block, tag, shared), a.rk));
     return philox_normal4(counter(j, block, tag, shared), make_uint2(a.key0, a.key1));
   }
   __device__ __forceinline__ float4 uniforms(int j, uint32_t block, uint32_t tag, bool shared) const {
+    if constexpr (TC::kInlineRng) return uniform4(philox4x32_10_rk(counter(j, block, tag, shared), a.rk));
     return philox_uniform4(counter(j, block, tag, shared), make_uint2(a.key0, a.key1));
   }
 
@@ -1160,7 +1179,7 @@ template <int RPT, int NT, bool HEAVY, int MIN_BLOCKS>
 __global__ void __launch_bounds__(NT, MIN_BLOCKS) schedule_kernel(const ScheduleArgs a) {
   extern __shared__ __align__(16) float smem[];
   constexpr int ROWS = RPT * NT;
-  Ctx<RPT, NT> c(a, smem, threadIdx.x);
+  Ctx<RPT, NT, typename std::conditional<HEAVY, NoTc, LightPolicy>::type> c(a, smem, threadIdx.x);
   const int64_t n_tiles = (a.n_rows + ROWS - 1) / ROWS;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t base = tile * ROWS;

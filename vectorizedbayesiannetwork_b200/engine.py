@@ -66,7 +66,8 @@ class DevicePlan:
                 n_slots=program.n_slots, n_scratch=program.n_scratch,
                 heavy=1 if program.heavy else 0, tc=tc_warpgroups() if program.tc else 0,
                 tc_list_dev=self.tc_list.data_ptr() if program.tc else None,
-                n_tc=int(program.tc_list.shape[0]) if program.tc else 0, reserved=0,
+                n_tc=int(program.tc_list.shape[0]) if program.tc else 0,
+                rows_per_thread=2 if any(int(k) == L.OP_TAB for k in program.ops["kind"]) else 0,
             )
             handle = C.c_void_p()
             L.check(self.lib.vbn_plan_create(C.byref(desc), C.byref(handle)))
