@@ -210,6 +210,13 @@ int32_t vbn_ess_below(const float* stats_dev, int64_t n_queries, float threshold
                       int32_t* flag_dev, void* stream);
 
 /*
+ * gaussian_exact support grid (vbn/inference/gaussian_exact.py:166-183): loc_scale_dev [B][2];
+ * samples[b,s] = loc + scale * linspace(-stddevs, stddevs, S)[s], pdf[b,s] = N(samples; loc, scale).
+ */
+int32_t vbn_gaussian_grid(const float* loc_scale_dev, int64_t n_queries, int64_t n_samples, float stddevs,
+                          float min_scale, float* pdf_dev, float* samples_dev, void* stream);
+
+/*
  * Posterior summary, VBN._posterior_stats (vbn/vbn.py:483-504): weights = pdf sanitised
  * (nan/inf -> 0, clamp >= 0) and normalised over S (uniform 1/S when their sum <= eps);
  * weighted mean / std per output dim and ESS = 1 / sum w^2.

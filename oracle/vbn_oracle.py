@@ -787,6 +787,96 @@ def likelihood_weighting(spec, query, n_samples: int, noise=None, scope="lw", no
 
 
 # --------------------------------------------------------------------------------------
+# exact methods: closed form only when every parent of the target is fixed,
+# otherwise the configured fallback method runs (vbn/inference/gaussian_exact.py:134-183,
+# vbn/inference/categorical_exact.py:89-128)
+# --------------------------------------------------------------------------------------
+
+
+def _exact_parent_tensor(st: "_State", fixed, b: int):
+    pidx = st.parent_idx[st.target_idx]
+    if not all(fixed[p] is not None for p in pidx):
+        return False, None
+    if not pidx:
+        return True, None
+    return True, torch.cat([fixed[p].unsqueeze(1).expand(b, 1, -1) for p in pidx], dim=-1)
+
+
+def gaussian_exact(spec, query, n_samples: int, noise=None, stddevs: float = 4.0, min_scale: float = 1e-6,
+                   return_info: bool = False):
+    query = _norm_query(query)
+    n_samples = max(1, int(n_samples))
+    b = infer_batch_size(query["evidence"], query["do"])
+    st = _State(spec, query)
+    fixed = _fixed_values(query, st, torch.float32, clamp_obs=True)
+    t = st.target_idx
+    c = spec["cpds"][st.topo[t]]
+
+    def fallback():
+        out = likelihood_weighting(spec, query, n_samples, noise=noise)
+        return (*out, {"exact": False}) if return_info else out
+
+    if c["output_dim"] != 1:  # :146-147
+        return fallback()
+    if fixed[t] is not None:  # :149-153
+        out = (torch.ones(b, 1), fixed[t].unsqueeze(1).expand(b, 1, -1))
+        return (*out, {"exact": True}) if return_info else out
+    ok, parents = _exact_parent_tensor(st, fixed, b)
+    if not ok or c["kind"] not in ("linear_gaussian", "gaussian_nn"):  # :155-170 (_gaussian_params -> None)
+        return fallback()
+    loc, scale = (lg_params if c["kind"] == "linear_gaussian" else gnn_params)(c, parents)
+    loc = loc.reshape(-1, 1, 1) if loc.dim() < 3 else loc  # _to_3d (:52-64)
+    scale = scale.reshape(-1, 1, 1) if scale.dim() < 3 else scale
+    if loc.shape[0] == 1 and b > 1:
+        loc = loc.expand(b, -1, -1)
+    if scale.shape[0] == 1 and b > 1:
+        scale = scale.expand(b, -1, -1)
+    scale = torch.nan_to_num(scale, nan=min_scale, posinf=min_scale, neginf=min_scale).abs().clamp_min(min_scale)
+    loc, scale = loc[:, :1, :], scale[:, :1, :]
+    z = torch.linspace(-stddevs, stddevs, n_samples, dtype=torch.float32).view(1, n_samples, 1)  # :172-176
+    samples = loc + scale * z
+    log_pdf = -0.5 * (z**2 + 2.0 * torch.log(scale) + math.log(2.0 * math.pi)).sum(dim=-1)
+    out = (torch.exp(log_pdf), samples)
+    return (*out, {"exact": True}) if return_info else out
+
+
+def categorical_exact(spec, query, n_samples: int = 512, noise=None, return_info: bool = False):
+    query = _norm_query(query)
+    b = infer_batch_size(query["evidence"], query["do"])
+    st = _State(spec, query)
+    fixed = _fixed_values(query, st, torch.float32, clamp_obs=True)
+    t = st.target_idx
+    c = spec["cpds"][st.topo[t]]
+
+    def fallback():
+        out = likelihood_weighting(spec, query, n_samples, noise=noise)
+        return (*out, {"exact": False}) if return_info else out
+
+    if fixed[t] is not None:  # :101-104
+        out = (torch.ones(b, 1), fixed[t].unsqueeze(1).expand(b, 1, -1))
+        return (*out, {"exact": True}) if return_info else out
+    ok, parents = _exact_parent_tensor(st, fixed, b)
+    if not ok or c["kind"] not in ("softmax_nn", "categorical_table"):  # :106-121
+        return fallback()
+    if c["kind"] == "softmax_nn":
+        logits = snn_logits(c, parents, b, 1)  # includes the temperature and the root_ready branch (:48-71)
+        support = c["sample_values"][0]
+    else:
+        logits = ct_logits(c, parents)
+        support = c["class_values"][0]
+    probs = torch.softmax(logits, dim=-1)
+    if probs.dim() == 4:
+        probs = probs.reshape(probs.shape[0], -1, probs.shape[-1]) if parents is None else probs.squeeze(1)
+    if probs.dim() != 3 or probs.shape[1] != 1 or c["output_dim"] != 1:  # :77-80, :123-124
+        return fallback()
+    probs = probs[:, 0, :]
+    if probs.shape[0] == 1 and b > 1:
+        probs = probs.expand(b, -1)
+    out = (probs, support.to(dtype=probs.dtype).view(1, -1, 1).expand(b, -1, 1))
+    return (*out, {"exact": True}) if return_info else out
+
+
+# --------------------------------------------------------------------------------------
 # importance sampling (vbn/inference/importance_sampling.py:24-93)
 # --------------------------------------------------------------------------------------
 

@@ -97,6 +97,21 @@ int32_t vbn_ess_below(const float* st, int64_t B, float thr, int32_t* flag, void
   for (int64_t b = 0; b < B; ++b) if (st[b * 3 + 1] * st[b * 3 + 1] / st[b * 3 + 2] < thr) *flag |= 1;
   return 0;
 }
+int32_t vbn_gaussian_grid(const float* ls, int64_t B, int64_t S, float k, float min_scale, float* pdf, float* x, void*) {
+  const float step = S > 1 ? (k - (-k)) / (float)(S - 1) : 0.0f;
+  for (int64_t b = 0; b < B; ++b) {
+    float sc = ls[2 * b + 1];
+    if (!(sc == sc) || std::fabs(sc) == INFINITY) sc = min_scale;
+    sc = std::max(std::fabs(sc), min_scale);
+    for (int64_t s = 0; s < S; ++s) {
+      const float z = s < S / 2 ? -k + step * (float)s : k - step * (float)(S - 1 - s);
+      x[b * S + s] = ls[2 * b] + sc * z;
+      pdf[b * S + s] = std::exp(-0.5f * (z * z + 2.0f * std::log(sc) + 1.8378770664093453f));
+    }
+  }
+  return 0;
+}
+
 int32_t vbn_posterior_stats(const float* pdf, const float* x, int64_t B, int64_t S, int32_t D, int32_t, float eps,
                             float*, float* stats, void*) {
   for (int64_t b = 0; b < B; ++b) {

@@ -26,6 +26,8 @@ METHODS = {
     "lw": ("likelihood_weighting", O.likelihood_weighting),
     "is": ("importance_sampling", O.importance_sampling),
     "mcm": ("monte_carlo_marginalization", O.monte_carlo_marginalization),
+    "gexact": ("gaussian_exact", O.gaussian_exact),
+    "cexact": ("categorical_exact", O.categorical_exact),
 }
 
 
@@ -100,6 +102,35 @@ def table_files():
     return {"table": {"spec": spec, "cases": cases, "cpd_cases": cpd_cases(m, spec)}}
 
 
+def exact_files():
+    """gaussian_exact / categorical_exact, incl. their likelihood-weighting fallbacks:
+    python tests/golden/make_golden.py exact"""
+    torch.manual_seed(9876)
+    out = {}
+    m = refmodels.lg_chain_model(n_nodes=5)
+    spec = O.spec_from_reference(m)
+    ev = torch.tensor([[0.2], [1.0], [-0.7]])
+    qs = [{"target": "x3", "evidence": {"x2": ev}}, {"target": "x0", "evidence": {"x4": ev}},
+          {"target": "x1", "evidence": {"x4": ev}}, {"target": "x2", "evidence": {"x2": ev}},
+          {"target": "x4", "evidence": {}, "do": {"x3": ev}}]
+    out["exact_lg"] = {"spec": spec, "cases": [run_case(m, spec, q, 33, "gexact", 21) for q in qs], "cpd_cases": []}
+    m = refmodels.readme_model(n=300, epochs=2)
+    spec = O.spec_from_reference(m)
+    qs = [{"target": "feature_0", "evidence": {"feature_2": ev}},
+          {"target": "feature_2", "evidence": {"feature_0": ev, "feature_1": ev}}]
+    out["exact_gnn"] = {"spec": spec, "cases": [run_case(m, spec, q, 24, "gexact", 22) for q in qs], "cpd_cases": []}
+    m = refmodels.table_model()
+    spec = O.spec_from_reference(m)
+    qs = [{"target": "wet", "evidence": {"rain": torch.tensor([[1.0], [0.0]]), "sprinkler": torch.tensor([[0.0], [1.0]])}},
+          {"target": "slip", "evidence": {"wet": torch.tensor([[2.0], [0.0], [1.0]])}},
+          {"target": "season", "evidence": {"slip": torch.tensor([[1.0]])}},
+          {"target": "sprinkler", "evidence": {"slip": torch.tensor([[1.0], [0.0]])}},
+          {"target": "rain", "evidence": {"slip": torch.tensor([[1.0]])}},
+          {"target": "wet", "evidence": {"wet": torch.tensor([[2.0]])}}]
+    out["exact_cat"] = {"spec": spec, "cases": [run_case(m, spec, q, 40, "cexact", 23) for q in qs], "cpd_cases": []}
+    return out
+
+
 def save(files):
     total = 0
     for name, blob in files.items():
@@ -113,6 +144,9 @@ def save(files):
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "table":
         save(table_files())
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "exact":
+        save(exact_files())
         return
     torch.manual_seed(1234)
     files = {}
@@ -177,6 +211,7 @@ def main():
     files["kde"] = {"spec": spec, "cases": cases, "cpd_cases": cpd_cases(m, spec)}
 
     files.update(table_files())
+    files.update(exact_files())
     save(files)
 
 

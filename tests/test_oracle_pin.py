@@ -170,3 +170,45 @@ def test_record_replay_roundtrip():
     w1, s1 = O.importance_sampling(spec, q, 16, noise=rec)
     w2, s2 = O.importance_sampling(spec, q, 16, noise=O.ReplayNoise(rec.log))
     _eq(w1, w2), _eq(s1, s2)
+
+
+def _exact_eq(model, spec, method, q, S, oracle_fn, seed=3):
+    tq = {"target": q["target"], "evidence": q.get("evidence", {}), "do": q.get("do", {})}
+    model.set_inference_method(method, n_samples=S)
+    torch.manual_seed(seed)
+    rw, rs = model.infer_posterior(tq, n_samples=S)
+    torch.manual_seed(seed)
+    ow, os_ = oracle_fn(spec, tq, S)
+    _eq(rw, ow), _eq(rs, os_)
+
+
+def test_gaussian_exact_and_fallback():
+    """vbn/inference/gaussian_exact.py: closed form when the target's parents are fixed, LW otherwise."""
+    model = refmodels.lg_chain_model(n_nodes=5)
+    spec = O.spec_from_reference(model)
+    ev = torch.tensor([[0.2], [1.0], [-0.7]])
+    _exact_eq(model, spec, "gaussian_exact", {"target": "x3", "evidence": {"x2": ev}}, 31, O.gaussian_exact)
+    _exact_eq(model, spec, "gaussian_exact", {"target": "x0", "evidence": {"x4": ev}}, 31, O.gaussian_exact)  # root
+    _exact_eq(model, spec, "gaussian_exact", {"target": "x1", "evidence": {"x4": ev}}, 32, O.gaussian_exact)  # fallback
+    _exact_eq(model, spec, "gaussian_exact", {"target": "x2", "evidence": {"x2": ev}}, 9, O.gaussian_exact)   # fixed target
+    m2 = refmodels.readme_model(n=300, epochs=2)
+    s2 = O.spec_from_reference(m2)
+    _exact_eq(m2, s2, "gaussian_exact", {"target": "feature_0", "evidence": {"feature_2": ev}}, 17, O.gaussian_exact)  # gnn root
+    q = {"target": "feature_2", "evidence": {"feature_0": ev, "feature_1": ev}}
+    _exact_eq(m2, s2, "gaussian_exact", q, 16, O.gaussian_exact)  # mdn target -> fallback
+
+
+def test_categorical_exact_and_fallback():
+    """vbn/inference/categorical_exact.py."""
+    model = refmodels.table_model()
+    spec = O.spec_from_reference(model)
+    q = {"target": "wet", "evidence": {"rain": torch.tensor([[1.0], [0.0]]), "sprinkler": torch.tensor([[0.0], [1.0]])}}
+    _exact_eq(model, spec, "categorical_exact", q, 64, O.categorical_exact)   # categorical_table, parents fixed
+    q = {"target": "slip", "evidence": {"wet": torch.tensor([[2.0], [0.0], [1.0]])}}
+    _exact_eq(model, spec, "categorical_exact", q, 64, O.categorical_exact)   # softmax_nn, parents fixed
+    q = {"target": "season", "evidence": {"slip": torch.tensor([[1.0]])}}
+    _exact_eq(model, spec, "categorical_exact", q, 64, O.categorical_exact)   # root categorical_table
+    q = {"target": "sprinkler", "evidence": {"slip": torch.tensor([[1.0], [0.0]])}}
+    _exact_eq(model, spec, "categorical_exact", q, 64, O.categorical_exact)   # softmax_nn root (root_ready)
+    q = {"target": "rain", "evidence": {"slip": torch.tensor([[1.0]])}}
+    _exact_eq(model, spec, "categorical_exact", q, 48, O.categorical_exact)   # parent not fixed -> LW fallback

@@ -17,7 +17,8 @@ import vectorizedbayesiannetwork_b200 as V
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 FILES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, "*.pt")))
 RTOL, ATOL = 1e-5, 1e-6
-METHOD_NAMES = {"lw": "likelihood_weighting", "is": "importance_sampling", "mcm": "monte_carlo_marginalization"}
+METHOD_NAMES = {"lw": "likelihood_weighting", "is": "importance_sampling", "mcm": "monte_carlo_marginalization",
+                "gexact": "gaussian_exact", "cexact": "categorical_exact"}
 
 
 def _load(name):
@@ -58,8 +59,9 @@ def test_inference_methods_match_reference(backend, name):
         model.set_inference_method(METHOD_NAMES[method], n_samples=S)
         if method == "is":
             noise = {k: _dev_noise(v, backend.device) for k, v in inj.items()}
-        else:
-            noise = _dev_noise(inj.get(method, {}), backend.device)
+        else:  # the exact methods draw only through their likelihood-weighting fallback (scope "lw")
+            scope = "lw" if method in ("gexact", "cexact") else method
+            noise = _dev_noise(inj.get(scope, {}), backend.device)
         pdf, samples = model.infer_posterior(q, noise=noise)
         _close(samples, case["expect"]["samples"], tag + " samples")
         _close(pdf, case["expect"]["pdf"], tag + " pdf", rtol=5e-5)

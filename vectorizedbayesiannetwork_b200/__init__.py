@@ -11,8 +11,8 @@ from .cpd_handle import CPDHandle
 from .cpds import (BaseCPD, GaussianNNCPD, KDECPD, LinearGaussianCPD, MDNCPD, SoftmaxNNCPD,
                    cpd_from_spec, wrap_cpd)
 from .dist import Shard, auto_shard
-from .inference import (AncestralSampler, ImportanceSampling, LikelihoodWeighting,
-                        MonteCarloMarginalization)
+from .inference import (AncestralSampler, CategoricalExact, GaussianExact, ImportanceSampling,
+                        LikelihoodWeighting, MonteCarloMarginalization)
 from .install import install, uninstall
 
 __all__ = [
@@ -21,5 +21,6 @@ __all__ = [
     "BaseCPD", "LinearGaussianCPD", "GaussianNNCPD", "MDNCPD", "SoftmaxNNCPD", "KDECPD",
     "cpd_from_spec", "wrap_cpd",
     "ImportanceSampling", "LikelihoodWeighting", "MonteCarloMarginalization", "AncestralSampler",
+    "GaussianExact", "CategoricalExact",
     "Shard", "auto_shard", "install", "uninstall",
 ]

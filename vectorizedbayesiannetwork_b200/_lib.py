@@ -71,6 +71,8 @@ EXPORTS = {
     "vbn_weights_normalize": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
                                           C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vbn_ess_below": (C.c_int32, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]),
+    "vbn_gaussian_grid": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
     "vbn_posterior_stats": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                         C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vbn_kde_log_prob": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,

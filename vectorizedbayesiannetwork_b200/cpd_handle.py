@@ -121,19 +121,7 @@ class CPDHandle:
                 "conditioning": _to_serializable(ptensor)}
         cpd, d = self._cpd, self.x_dim
         if cpd.kind == "categorical_table":  # the CPD's parameters are the table: a host-side lookup
-            probs = torch.exp(cpd.logits_table())  # [n_cfg, C]
-            if ptensor is None:
-                rows = probs[:1].view(1, 1, 1, -1)
-            else:
-                p3 = ptensor.detach().cpu()
-                p3 = p3.unsqueeze(1) if p3.dim() == 2 else p3
-                idx = torch.zeros(p3.shape[:2], dtype=torch.long)
-                for k, (sup, stride) in enumerate(zip(cpd._parent_values, cpd._parent_strides)):
-                    pos = torch.searchsorted(sup, p3[..., k].contiguous()).clamp(max=sup.numel() - 1)
-                    if not bool((sup[pos] == p3[..., k]).all()):
-                        raise ValueError("Found values outside support.")  # categorical_table.py:12-21
-                    idx = idx + pos * stride
-                rows = probs[idx].unsqueeze(2)
+            rows = cpd.probs(ptensor)
             return {**base, "format": "categorical_probs", "probs": _to_serializable(rows),
                     "k": int(cpd.n_classes), "support": _to_serializable(cpd._sample_values)}
         if cpd.param_width() > 0:

@@ -595,6 +595,22 @@ class CategoricalTableCPD(BaseCPD):
         probs = self._counts[0] / self._counts[0].sum(dim=-1, keepdim=True).clamp_min(1e-12)
         return torch.log_softmax(torch.log(probs.clamp_min(1e-12)), dim=-1)
 
+    def probs(self, parents: Optional[torch.Tensor]) -> torch.Tensor:
+        """softmax(_logits_from_parents) rows [B, S, 1, C] (host lookup: the parameters ARE the table)."""
+        table = torch.exp(self.logits_table())
+        if parents is None or self.input_dim == 0:
+            return table[:1].view(1, 1, 1, -1)
+        p3 = torch.as_tensor(parents).detach().cpu().float()
+        p3 = p3.unsqueeze(1) if p3.dim() == 2 else p3
+        idx = torch.zeros(p3.shape[:2], dtype=torch.long)
+        for k, (sup, stride) in enumerate(zip(self._parent_values, self._parent_strides)):
+            col = p3[..., k].contiguous()
+            pos = torch.searchsorted(sup, col).clamp(max=sup.numel() - 1)
+            if not bool((sup[pos] == col).all()):
+                raise ValueError("Found values outside support.")  # categorical_table.py:12-21
+            idx = idx + pos * stride
+        return table[idx].unsqueeze(2)
+
     def _pack(self) -> Packed:
         if self.output_dim != 1:
             raise ValueError("categorical_table with output_dim > 1 has no CUDA implementation yet")

@@ -280,6 +280,18 @@ int32_t vbn_ess_below(const float* stats_dev, int64_t n_queries, float threshold
   return VBN_OK;
 }
 
+int32_t vbn_gaussian_grid(const float* loc_scale_dev, int64_t n_queries, int64_t n_samples, float stddevs,
+                          float min_scale, float* pdf_dev, float* samples_dev, void* stream) {
+  if (!loc_scale_dev || !pdf_dev || !samples_dev || n_queries <= 0 || n_samples <= 0)
+    return fail(VBN_E_INVALID, "bad argument to vbn_gaussian_grid");
+  const int64_t total = n_queries * n_samples;
+  const unsigned grid = static_cast<unsigned>(total / 256 + 1 < 148 * 8 ? total / 256 + 1 : 148 * 8);
+  vbn::gaussian_grid_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      loc_scale_dev, n_queries, n_samples, stddevs, min_scale, pdf_dev, samples_dev);
+  CUDA_TRY(cudaGetLastError());
+  return VBN_OK;
+}
+
 int32_t vbn_posterior_stats(const float* pdf_dev, const float* samples_dev, int64_t n_queries,
                             int64_t n_samples, int32_t dim, int32_t n_split, float eps,
                             float* partials_dev, float* stats_dev, void* stream) {

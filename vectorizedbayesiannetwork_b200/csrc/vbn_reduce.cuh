@@ -247,6 +247,30 @@ __global__ void posterior_merge_kernel(const float* __restrict__ partials, const
   }
 }
 
+// gaussian_exact grid (vbn/inference/gaussian_exact.py:166-183): per query b with Normal(loc_b, scale_b)
+//   z_s = linspace(-k, k, S)[s];  samples[b,s] = loc_b + scale_b * z_s;
+//   pdf[b,s] = exp(-0.5 * (z_s^2 + 2 ln scale_b + ln 2 pi))
+// scale is sanitised like the reference: nan/inf -> min_scale, abs, clamp_min(min_scale).
+__global__ void gaussian_grid_kernel(const float* __restrict__ loc_scale, int64_t n_queries, int64_t n_samples,
+                                     float stddevs, float min_scale, float* __restrict__ pdf,
+                                     float* __restrict__ samples) {
+  const int64_t total = n_queries * n_samples;
+  const float step = n_samples > 1 ? __fdiv_rn(stddevs - (-stddevs), static_cast<float>(n_samples - 1)) : 0.0f;
+  for (int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; r < total;
+       r += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t b = r / n_samples, s = r - b * n_samples;
+    const float loc = loc_scale[2 * b];
+    float sc = loc_scale[2 * b + 1];
+    if (!(sc == sc) || fabsf(sc) == CUDART_INF_F) sc = min_scale;
+    sc = fmaxf(fabsf(sc), min_scale);
+    // torch.linspace: start + step*i in the lower half, end - step*(S-1-i) in the upper half
+    const float z = s < n_samples / 2 ? fmaf(step, static_cast<float>(s), -stddevs)
+                                      : stddevs - step * static_cast<float>(n_samples - 1 - s);
+    samples[r] = loc + sc * z;
+    pdf[r] = expf(-0.5f * (z * z + 2.0f * logf(sc) + kLog2Pi));
+  }
+}
+
 __global__ void philox_fill_kernel(const uint32_t* __restrict__ ctr, int64_t n, uint32_t k0,
                                    uint32_t k1, uint32_t* __restrict__ out) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;

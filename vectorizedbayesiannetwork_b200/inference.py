@@ -254,6 +254,120 @@ class MonteCarloMarginalization:
         return out["logp"], out["stores"][target]
 
 
+def _exact_setup(vbn, query: Query):
+    """Common prologue of the exact methods (gaussian_exact.py:134-164, categorical_exact.py:89-118):
+    returns (b, target cpd, fixed target value | None, parents all fixed?, parent tensor [b,Dp] | None)."""
+    dev = _check_model(vbn)
+    b = infer_batch_size(query.evidence, query.do)
+    cpds = model_cpds(vbn)
+    target = query.target
+
+    def fixed(node):
+        if node in query.do:
+            return query.do[node].to(device=dev, dtype=torch.float32)
+        if node in query.evidence:
+            return clamp_evidence(query.evidence[node].to(device=dev, dtype=torch.float32))  # clamp_obs=True
+        return None
+
+    tval = fixed(target)
+    plist = list(vbn.dag.parents(target))
+    pvals = [fixed(p) for p in plist]
+    ok = all(v is not None for v in pvals)
+    ptensor = torch.cat(pvals, dim=-1) if (ok and plist) else None
+    return dev, b, cpds[target], tval, ok, ptensor
+
+
+class _ExactBase:
+    def _init_fallback(self, fallback, own_name: str, kwargs: dict):
+        self.fallback = str(fallback).strip().lower() if fallback is not None else "none"
+        self._fallback = None
+        if self.fallback != "none":
+            from .core import INFERENCE_REGISTRY
+
+            if self.fallback not in INFERENCE_REGISTRY:
+                raise ValueError(f"Unknown fallback inference '{fallback}'. Available: {list(INFERENCE_REGISTRY.keys())}")
+            if self.fallback == own_name:
+                raise ValueError(f"fallback cannot be '{own_name}'")
+            self._fallback = INFERENCE_REGISTRY[self.fallback](**kwargs)
+
+    def _fallback_infer(self, vbn, query, name: str, **kwargs):
+        if self._fallback is None:
+            raise RuntimeError(f"{name} cannot handle this query and has no fallback")
+        self._last_exact = False
+        return self._fallback.infer_posterior(vbn, query, **kwargs)
+
+
+@register_inference("gaussian_exact")
+class GaussianExact(_ExactBase):
+    """vbn/inference/gaussian_exact.py:14-183: Normal(loc, scale) of the target on a +-stddevs grid when all
+    its parents are fixed (loc/scale from the GPU parameter read-out, grid by vbn_gaussian_grid); the
+    fallback method otherwise."""
+
+    def __init__(self, n_samples: int = 200, stddevs: float = 4.0, min_scale: float = 1e-6,
+                 fallback: str = "likelihood_weighting", **kwargs) -> None:
+        self.n_samples = int(n_samples)
+        self.stddevs = float(stddevs)
+        self.min_scale = float(min_scale)
+        self._cache = {}
+        self._last_exact = False
+        fk = dict(kwargs)
+        fk.setdefault("n_samples", self.n_samples)
+        self._init_fallback(fallback, "gaussian_exact", fk)
+
+    def infer_posterior(self, vbn, query: Query, **kwargs):
+        from . import _lib as L
+
+        n_samples = max(1, int(kwargs.get("n_samples", self.n_samples)))
+        dev, b, cpd, tval, ok, ptensor = _exact_setup(vbn, query)
+        if cpd.output_dim != 1:
+            return self._fallback_infer(vbn, query, "gaussian_exact", **kwargs)
+        if tval is not None:
+            self._last_exact = True
+            return torch.ones(b, 1, device=dev), tval.unsqueeze(1).expand(b, 1, -1)
+        if not ok or cpd.kind not in ("linear_gaussian", "gaussian_nn"):
+            return self._fallback_infer(vbn, query, "gaussian_exact", **kwargs)
+        ls = cpd.params(ptensor).reshape(-1, 2)  # [b or 1, {loc, scale}]
+        if ls.shape[0] == 1 and b > 1:
+            ls = ls.expand(b, 2)
+        ls = ls.contiguous()
+        lib = L.load()
+        with torch.cuda.device(dev):
+            pdf = torch.empty(b, n_samples, device=dev, dtype=torch.float32)
+            samples = torch.empty(b, n_samples, 1, device=dev, dtype=torch.float32)
+            L.check(lib.vbn_gaussian_grid(ls.data_ptr(), b, n_samples, self.stddevs, self.min_scale,
+                                          pdf.data_ptr(), samples.data_ptr(), E._stream_ptr(dev)))
+            L.count_launch(1)
+        self._last_exact = True
+        return pdf, samples
+
+
+@register_inference("categorical_exact")
+class CategoricalExact(_ExactBase):
+    """vbn/inference/categorical_exact.py:14-128: class probabilities of a categorical target whose parents
+    are all fixed (softmax_nn through the GPU parameter read-out, categorical_table from its table)."""
+
+    def __init__(self, fallback: str = "likelihood_weighting", **kwargs) -> None:
+        self._last_exact = False
+        self._init_fallback(fallback, "categorical_exact", dict(kwargs))
+
+    def infer_posterior(self, vbn, query: Query, **kwargs):
+        dev, b, cpd, tval, ok, ptensor = _exact_setup(vbn, query)
+        if tval is not None:
+            self._last_exact = True
+            return torch.ones(b, 1, device=dev), tval.unsqueeze(1).expand(b, 1, -1)
+        if not ok or cpd.kind not in ("softmax_nn", "categorical_table") or cpd.output_dim != 1:
+            return self._fallback_infer(vbn, query, "categorical_exact", **kwargs)
+        if cpd.kind == "softmax_nn":
+            probs = cpd.params(ptensor).reshape(-1, cpd.n_classes)
+        else:
+            probs = cpd.probs(ptensor).reshape(-1, cpd.n_classes).to(dev)
+        if probs.shape[0] == 1 and b > 1:
+            probs = probs.expand(b, -1)
+        support = cpd._sample_values[0].to(device=dev, dtype=torch.float32)
+        self._last_exact = True
+        return probs, support.view(1, -1, 1).expand(b, -1, 1)
+
+
 @register_sampling("ancestral")
 class AncestralSampler:
     """vbn/sampling/ancestral.py:57-65."""

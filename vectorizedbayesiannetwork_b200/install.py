@@ -4,8 +4,8 @@ hot-path methods (vbn/core/registry.py:7-11) with the CUDA classes, so
 The registry decorator refuses duplicate keys (registry.py:18-20), hence plain dict assignment."""
 from __future__ import annotations
 
-from .inference import (AncestralSampler, ImportanceSampling, LikelihoodWeighting,
-                        MonteCarloMarginalization)
+from .inference import (AncestralSampler, CategoricalExact, GaussianExact, ImportanceSampling,
+                        LikelihoodWeighting, MonteCarloMarginalization)
 
 _ORIGINAL = {}
 
@@ -16,7 +16,8 @@ def install(vbn_module=None) -> None:
     reg = vbn_module.core.registry
     for key, cls in (("likelihood_weighting", LikelihoodWeighting),
                      ("importance_sampling", ImportanceSampling),
-                     ("monte_carlo_marginalization", MonteCarloMarginalization)):
+                     ("monte_carlo_marginalization", MonteCarloMarginalization),
+                     ("gaussian_exact", GaussianExact), ("categorical_exact", CategoricalExact)):
         _ORIGINAL.setdefault(("inference", key), reg.INFERENCE_REGISTRY.get(key))
         reg.INFERENCE_REGISTRY[key] = cls
     _ORIGINAL.setdefault(("sampling", "ancestral"), reg.SAMPLING_REGISTRY.get("ancestral"))
