@@ -168,7 +168,8 @@ typedef struct VbnRunDesc {
   float* logw_dev;         /* [B*S] log-weights, required if any op has VBN_F_ADD_LOGW      */
   float* logp_dev;         /* [B*S] log-density, required if any op has VBN_F_OUT_LOGP      */
   int32_t logp_as_pdf;     /* 1: write exp(logp) (MCM pdf, monte_carlo_marginalization.py:57,91) */
-  int32_t reserved;
+  int32_t logw_accumulate; /* 1: logw[r] += this run's log-weight (schedules run in segments,
+                              resampled_importance_sampling.py:69-100); 0: overwrite          */
   int32_t* error_flag_dev; /* set to 1 when a softmax_nn discrete value has no class
                               (softmax_nn.py:620-625 raises ValueError); may be NULL       */
 } VbnRunDesc;
@@ -208,6 +209,20 @@ int32_t vbn_weights_normalize(const float* logw_dev, const float* stats_dev, int
  * (importance_sampling.py:85-88) */
 int32_t vbn_ess_below(const float* stats_dev, int64_t n_queries, float threshold,
                       int32_t* flag_dev, void* stream);
+
+/*
+ * Resampling step of resampled_importance_sampling (vbn/inference/resampled_importance_sampling.py:33-41,
+ * torch.multinomial(weights, S, replacement=True) + row gather), three launches:
+ *   vbn_row_cdf          : cdf[b,s] = running sum of w[b,:]          (w need not be normalised)
+ *   vbn_resample_indices : idx[b,s] = first position with cdf > u * cdf[b,S-1], u from the row's Philox stream
+ *   vbn_gather_rows      : dst[c][b][s] = src[c][b][idx[b][s]] for n_cols live node columns ([n_cols][B][S] each)
+ */
+int32_t vbn_row_cdf(const float* w_dev, int64_t n_queries, int64_t n_samples, float* cdf_dev, void* stream);
+int32_t vbn_resample_indices(const float* cdf_dev, int64_t n_queries, int64_t n_samples, uint64_t seed,
+                             uint64_t call_offset, int64_t query_offset, int64_t sample_offset,
+                             int32_t* idx_dev, void* stream);
+int32_t vbn_gather_rows(const float* src_dev, float* dst_dev, const int32_t* idx_dev, int32_t n_cols,
+                        int64_t n_queries, int64_t n_samples, void* stream);
 
 /*
  * gaussian_exact support grid (vbn/inference/gaussian_exact.py:166-183): loc_scale_dev [B][2];

@@ -71,6 +71,10 @@ class TorchNoise:
         # torch.randint(0, n, (count,))  (kde.py:170)
         return torch.randint(0, n, (count,), device=device)
 
+    def resample(self, key, weights: torch.Tensor, n: int) -> torch.Tensor:
+        # torch.multinomial(weights, num_samples=n, replacement=True)  (resampled_importance_sampling.py:38)
+        return torch.multinomial(weights, num_samples=n, replacement=True)
+
 
 class RecordingNoise(TorchNoise):
     """TorchNoise that also stores every draw under its key (list per key, call order)."""
@@ -102,6 +106,9 @@ class RecordingNoise(TorchNoise):
 
     def randint(self, key, n, count, device):
         return self._rec(key + ("idx",), super().randint(key, n, count, device))
+
+    def resample(self, key, weights, n):
+        return self._rec(key + ("idx",), super().resample(key, weights, n))
 
 
 class ReplayNoise:
@@ -137,6 +144,9 @@ class ReplayNoise:
 
     def randint(self, key, n, count, device):
         return self._next(key + ("idx",)).reshape(count)
+
+    def resample(self, key, weights, n):
+        return self._next(key + ("idx",)).reshape(weights.shape[0], n).long()
 
 
 # --------------------------------------------------------------------------------------
@@ -783,6 +793,49 @@ def likelihood_weighting(spec, query, n_samples: int, noise=None, scope="lw", no
         w = torch.exp(lw).clamp_min(eps)
     if return_all:
         return w, target, samples, logw
+    return w, target
+
+
+# --------------------------------------------------------------------------------------
+# resampled importance sampling (vbn/inference/resampled_importance_sampling.py:13-105)
+# --------------------------------------------------------------------------------------
+
+
+def resampled_importance_sampling(spec, query, n_samples: int, noise=None, ess_threshold: float = 0.5,
+                                  resample: bool = True, clamp_obs: bool = True, return_info: bool = False):
+    query = _norm_query(query)
+    noise = noise or TorchNoise()
+    b = infer_batch_size(query["evidence"], query["do"])
+    st = _State(spec, query)
+    dtype = torch.float32
+    samples = torch.zeros(b, n_samples, st.total_dim, dtype=dtype)
+    logw = torch.zeros(b, n_samples, dtype=dtype)
+    fixed = _fixed_values(query, st, dtype, clamp_obs=clamp_obs)
+    threshold = max(1.0, ess_threshold * float(n_samples)) if ess_threshold <= 1.0 else float(ess_threshold)  # :62-65
+    resampled, last_ess = False, None
+    for idx, node in enumerate(st.topo):
+        c = spec["cpds"][node]
+        if fixed[idx] is not None:  # :72-91
+            value = fixed[idx].unsqueeze(1).expand(b, n_samples, -1)
+            samples[..., st.slices[idx]] = value
+            if st.evidence_mask[idx]:
+                logw = logw + cpd_log_prob(c, value, _gather_parents(samples, st, idx))
+                if resample:
+                    weights = torch.softmax(logw, dim=1)
+                    ess = 1.0 / (weights**2).sum(dim=1)
+                    last_ess = ess
+                    if torch.any(ess < threshold):
+                        w = torch.softmax(logw, dim=1)  # _resample :33-41
+                        pick = noise.resample(("ris", "__resample__"), w, n_samples)
+                        samples = samples[torch.arange(b).unsqueeze(1), pick]
+                        logw = torch.zeros_like(logw)
+                        resampled = True
+            continue
+        samples[..., st.slices[idx]] = cpd_sample(c, _gather_parents(samples, st, idx), n_samples, noise, ("ris", node))
+    w = torch.softmax(logw, dim=1)
+    target = samples[..., st.slices[st.target_idx]]
+    if return_info:
+        return w, target, {"resampled": resampled, "ess": last_ess}
     return w, target
 
 

@@ -44,7 +44,7 @@ int32_t vbn_run_forward(const VbnPlan* plan, const VbnRunDesc* run, void*) {
   std::memset(&a, 0, sizeof(a));
   a.ops = plan->desc.ops_dev; a.par_slots = plan->desc.par_slots_dev; a.params = plan->desc.params_dev;
   a.n_ops = plan->desc.n_ops; a.n_slots = plan->desc.n_slots; a.n_scratch = plan->desc.n_scratch;
-  a.logp_as_pdf = run->logp_as_pdf; a.n_queries = run->n_queries; a.n_samples = run->n_samples;
+  a.logp_as_pdf = run->logp_as_pdf; a.logw_accumulate = run->logw_accumulate; a.n_queries = run->n_queries; a.n_samples = run->n_samples;
   a.n_rows = run->n_queries * run->n_samples;
   a.query_offset = (uint32_t)run->query_offset; a.sample_offset = (uint32_t)run->sample_offset;
   a.key0 = (uint32_t)run->seed; a.key1 = (uint32_t)(run->seed >> 32); a.call_offset = (uint32_t)run->call_offset; vbn::fill_round_keys(a);
@@ -97,6 +97,29 @@ int32_t vbn_ess_below(const float* st, int64_t B, float thr, int32_t* flag, void
   for (int64_t b = 0; b < B; ++b) if (st[b * 3 + 1] * st[b * 3 + 1] / st[b * 3 + 2] < thr) *flag |= 1;
   return 0;
 }
+int32_t vbn_row_cdf(const float* w, int64_t B, int64_t S, float* cdf, void*) {
+  for (int64_t b = 0; b < B; ++b) { double run = 0; for (int64_t s = 0; s < S; ++s) { run += w[b * S + s]; cdf[b * S + s] = (float)run; } }
+  return 0;
+}
+int32_t vbn_resample_indices(const float* cdf, int64_t B, int64_t S, uint64_t seed, uint64_t call, int64_t qo, int64_t so,
+                             int32_t* idx, void*) {
+  for (int64_t b = 0; b < B; ++b) for (int64_t s = 0; s < S; ++s) {
+    const uint4 c = make_uint4((uint32_t)(so + s), (uint32_t)(qo + b), 0x7FFFFFFFu, (uint32_t)call);
+    const uint4 r = vbn::philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const float* row = cdf + b * S;
+    const float u = vbn::u01(r.x) * row[S - 1];
+    int64_t lo = 0, hi = S - 1;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (row[mid] > u) hi = mid; else lo = mid + 1; }
+    idx[b * S + s] = (int32_t)lo;
+  }
+  return 0;
+}
+int32_t vbn_gather_rows(const float* src, float* dst, const int32_t* idx, int32_t n_cols, int64_t B, int64_t S, void*) {
+  const int64_t rows = B * S;
+  for (int c = 0; c < n_cols; ++c) for (int64_t r = 0; r < rows; ++r) dst[c * rows + r] = src[c * rows + (r / S) * S + idx[r]];
+  return 0;
+}
+
 int32_t vbn_gaussian_grid(const float* ls, int64_t B, int64_t S, float k, float min_scale, float* pdf, float* x, void*) {
   const float step = S > 1 ? (k - (-k)) / (float)(S - 1) : 0.0f;
   for (int64_t b = 0; b < B; ++b) {

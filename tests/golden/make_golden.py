@@ -26,6 +26,7 @@ METHODS = {
     "lw": ("likelihood_weighting", O.likelihood_weighting),
     "is": ("importance_sampling", O.importance_sampling),
     "mcm": ("monte_carlo_marginalization", O.monte_carlo_marginalization),
+    "ris": ("resampled_importance_sampling", O.resampled_importance_sampling),
     "gexact": ("gaussian_exact", O.gaussian_exact),
     "cexact": ("categorical_exact", O.categorical_exact),
 }
@@ -53,7 +54,11 @@ def run_case(model, spec, query, S, method, seed):
         torch.manual_seed(seed)
         ref_w, ref_s = model.infer_posterior(q)
         torch.manual_seed(seed)
-        if method == "is":
+        if method == "ris":
+            ora_w, ora_s, inf = fn(spec, q, S, noise=rec, return_info=True)
+            info = {"resampled": bool(inf["resampled"])}
+            assert info["resampled"] == model._inference._last_resampled
+        elif method == "is":
             ora_w, ora_s, inf = fn(spec, q, S, noise=rec, return_info=True)
             info = {"fallback": bool(inf["fallback"]), "ess": inf["ess"]}
             assert info["fallback"] == model._inference._last_fallback
@@ -131,6 +136,29 @@ def exact_files():
     return out
 
 
+def ris_files():
+    """resampled_importance_sampling:  python tests/golden/make_golden.py ris"""
+    torch.manual_seed(2468)
+    out = {}
+    m = refmodels.lg_chain_model(n_nodes=6)
+    spec = O.spec_from_reference(m)
+    ev = torch.tensor([[0.2], [1.0], [-0.7]])
+    qs = [{"target": "x2", "evidence": {"x3": ev, "x5": ev * 2}}, {"target": "x5", "evidence": {"x1": ev}},
+          {"target": "x0", "evidence": {"x4": ev}, "do": {"x2": ev}}, {"target": "x3", "evidence": {}},
+          {"target": "x4", "evidence": {"x4": ev, "x1": ev}}]
+    out["ris_lg"] = {"spec": spec, "cases": [run_case(m, spec, q, 48, "ris", 31) for q in qs], "cpd_cases": []}
+    m = refmodels.mixed_model(epochs=1)
+    spec = O.spec_from_reference(m)
+    qs = [{"target": "e", "evidence": {"g": torch.randn(3, 2), "h": torch.randn(3, 1)}},
+          {"target": "a", "evidence": {"f": torch.randn(3, 1) ** 2, "c": torch.randn(3, 1)}, "do": {"d": torch.randn(3, 1)}}]
+    out["ris_mixed"] = {"spec": spec, "cases": [run_case(m, spec, q, 32, "ris", 32) for q in qs], "cpd_cases": []}
+    m = refmodels.table_model()
+    spec = O.spec_from_reference(m)
+    qs = [{"target": "season", "evidence": {"slip": torch.tensor([[1.0], [0.0]]), "wet": torch.tensor([[2.0], [1.0]])}}]
+    out["ris_table"] = {"spec": spec, "cases": [run_case(m, spec, q, 64, "ris", 33) for q in qs], "cpd_cases": []}
+    return out
+
+
 def save(files):
     total = 0
     for name, blob in files.items():
@@ -144,6 +172,9 @@ def save(files):
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "table":
         save(table_files())
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "ris":
+        save(ris_files())
         return
     if len(sys.argv) > 1 and sys.argv[1] == "exact":
         save(exact_files())
@@ -212,6 +243,7 @@ def main():
 
     files.update(table_files())
     files.update(exact_files())
+    files.update(ris_files())
     save(files)
 
 

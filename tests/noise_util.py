@@ -9,6 +9,9 @@ def to_injection(log, spec, n_samples: int):
     out = {}
     for key, lst in log.items():
         scope, node, kind = key
+        if node == "__resample__":  # resampled_importance_sampling: one [B, S] index tensor per resampling event
+            out.setdefault(scope, {})[node] = [x.to(torch.int32).reshape(-1, n_samples) for x in lst]
+            continue
         c = spec["cpds"][node]
         d = int(c["output_dim"])
         if kind in ("eps", "u"):

@@ -212,3 +212,30 @@ def test_categorical_exact_and_fallback():
     _exact_eq(model, spec, "categorical_exact", q, 64, O.categorical_exact)   # softmax_nn root (root_ready)
     q = {"target": "rain", "evidence": {"slip": torch.tensor([[1.0]])}}
     _exact_eq(model, spec, "categorical_exact", q, 48, O.categorical_exact)   # parent not fixed -> LW fallback
+
+
+def test_resampled_importance_sampling():
+    """vbn/inference/resampled_importance_sampling.py: ESS-triggered multinomial resampling after evidence nodes."""
+    model = refmodels.lg_chain_model(n_nodes=6)
+    spec = O.spec_from_reference(model)
+    ev = torch.tensor([[0.2], [1.0], [-0.7]])
+    for q in ({"target": "x2", "evidence": {"x3": ev, "x5": ev * 2}},       # resamples (sharp evidence)
+              {"target": "x5", "evidence": {"x1": ev}},                    # target after the cut
+              {"target": "x0", "evidence": {"x4": ev}, "do": {"x2": ev}}):
+        tq = {"target": q["target"], "evidence": q.get("evidence", {}), "do": q.get("do", {})}
+        model.set_inference_method("resampled_importance_sampling", n_samples=64)
+        torch.manual_seed(5)
+        rw, rs = model.infer_posterior(tq)
+        torch.manual_seed(5)
+        ow, os_, info = O.resampled_importance_sampling(spec, tq, 64, return_info=True)
+        _eq(rw, ow), _eq(rs, os_)
+        assert info["resampled"] == model._inference._last_resampled
+    mixed = refmodels.mixed_model(epochs=1)
+    mspec = O.spec_from_reference(mixed)
+    tq = {"target": "e", "evidence": {"g": torch.randn(3, 2), "h": torch.randn(3, 1)}, "do": {}}
+    mixed.set_inference_method("resampled_importance_sampling", n_samples=32)
+    torch.manual_seed(6)
+    rw, rs = mixed.infer_posterior(tq)
+    torch.manual_seed(6)
+    ow, os_ = O.resampled_importance_sampling(mspec, tq, 32)
+    _eq(rw, ow), _eq(rs, os_)

@@ -18,7 +18,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 FILES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, "*.pt")))
 RTOL, ATOL = 1e-5, 1e-6
 METHOD_NAMES = {"lw": "likelihood_weighting", "is": "importance_sampling", "mcm": "monte_carlo_marginalization",
-                "gexact": "gaussian_exact", "cexact": "categorical_exact"}
+                "gexact": "gaussian_exact", "cexact": "categorical_exact", "ris": "resampled_importance_sampling"}
 
 
 def _load(name):
@@ -38,7 +38,8 @@ def _close(got, want, what, rtol=RTOL, atol=ATOL):
 
 
 def _dev_noise(noise, device):
-    return {n: {k: t.to(device) for k, t in d.items()} for n, d in noise.items()}
+    return {n: ([t.to(device) for t in d] if isinstance(d, list) else {k: t.to(device) for k, t in d.items()})
+            for n, d in noise.items()}
 
 
 @pytest.mark.parametrize("name", FILES)
@@ -65,6 +66,8 @@ def test_inference_methods_match_reference(backend, name):
         pdf, samples = model.infer_posterior(q, noise=noise)
         _close(samples, case["expect"]["samples"], tag + " samples")
         _close(pdf, case["expect"]["pdf"], tag + " pdf", rtol=5e-5)
+        if method == "ris":
+            assert model._inference._last_resampled == case["info"]["resampled"], tag
         if method == "is":
             assert model._inference._last_fallback == case["info"]["fallback"], tag
             _close(model._inference._last_ess, case["info"]["ess"], tag + " ess", rtol=1e-4)

@@ -463,3 +463,30 @@ def test_categorical_table_strict_support_and_conditional(backend):
     probs = torch.tensor(out["probs"])
     want = torch.softmax(O.ct_logits(spec["cpds"]["wet"], torch.tensor([[1.0, 0.0], [0.0, 1.0]])), dim=-1)
     torch.testing.assert_close(probs, want.reshape(probs.shape), rtol=1e-5, atol=1e-7)
+
+
+# ---- resampled_importance_sampling (vbn/inference/resampled_importance_sampling.py) ----------------
+def test_resampled_importance_sampling_philox_path(backend):
+    spec = S.lg_chain(8)
+    model = V.VBN.from_spec(spec, device=backend.device)
+    n = 100_000 if backend.name == "cuda" else 6_000
+    ev = torch.tensor([[0.5], [3.0]])
+    model.set_inference_method("resampled_importance_sampling", n_samples=n)
+    w, s = model.infer_posterior({"target": "x3", "evidence": {"x5": ev, "x7": ev + 0.3}}, seed=8)
+    assert w.shape == (2, n) and s.shape == (2, n, 1)
+    assert model._inference._last_resampled is True and model._inference._last_ess.shape == (2,)
+    torch.testing.assert_close(w.sum(1).cpu(), torch.ones(2), rtol=1e-4, atol=1e-4)
+    wd, sd = w.double().cpu(), s[..., 0].double().cpu()
+    mean = (wd * sd).sum(1)
+    em, evar = O.lg_exact_posterior(spec, "x3", {"x5": ev, "x7": ev + 0.3})
+    # resampling adds Monte-Carlo noise of order sigma / sqrt(ESS at the resampling step) ~ sigma / sqrt(n/10)
+    assert bool(((mean - em).abs() < 8.0 * evar.sqrt() / (n / 10) ** 0.5).all()), (mean, em)
+    # resampling off: plain sequential importance sampling, never resamples
+    w2, _ = model.infer_posterior({"target": "x3", "evidence": {"x5": ev}}, seed=8, resample=False)
+    assert model._inference._last_resampled is False
+    torch.testing.assert_close(w2.sum(1).cpu(), torch.ones(2), rtol=1e-4, atol=1e-4)
+    # target after the last evidence node, and a fixed target
+    w3, s3 = model.infer_posterior({"target": "x7", "evidence": {"x2": ev}}, seed=8)
+    assert s3.shape == (2, n, 1) and torch.isfinite(s3).all()
+    w4, s4 = model.infer_posterior({"target": "x2", "evidence": {"x2": ev}}, seed=8)
+    assert bool((s4[0] == 0.5).all()) and bool((s4[1] == 3.0).all())

@@ -53,7 +53,7 @@ class RunDesc(C.Structure):
         ("fixed_dev", C.c_void_p), ("inputs_dev", C.c_void_p),
         ("stores_dev", C.c_void_p), ("noise_dev", C.c_void_p),
         ("logw_dev", C.c_void_p), ("logp_dev", C.c_void_p),
-        ("logp_as_pdf", C.c_int32), ("reserved", C.c_int32),
+        ("logp_as_pdf", C.c_int32), ("logw_accumulate", C.c_int32),
         ("error_flag_dev", C.c_void_p),
     ]
 
@@ -71,6 +71,10 @@ EXPORTS = {
     "vbn_weights_normalize": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
                                           C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vbn_ess_below": (C.c_int32, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]),
+    "vbn_row_cdf": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "vbn_resample_indices": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64, C.c_int64,
+                                         C.c_int64, C.c_void_p, C.c_void_p]),
+    "vbn_gather_rows": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p]),
     "vbn_gaussian_grid": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
     "vbn_posterior_stats": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,

@@ -128,7 +128,9 @@ int32_t vbn_plan_create(const VbnProgramDesc* desc, VbnPlan** out_plan) {
       const size_t bytes = vbn::tc::kCtrlBytes + static_cast<size_t>(nbuf) * vbn::tc::kWbufBytes +
                            per_row * threads;
       if (bytes > static_cast<size_t>(max_smem)) continue;
-      CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+      // the attribute is per FUNCTION, not per plan: always raise it to the device maximum so that plans with
+      // different footprints can coexist (a later, smaller plan must not lower the limit of an earlier one)
+      CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
       int occ = 0;
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, bytes));
       if (occ < 1) continue;
@@ -151,8 +153,7 @@ int32_t vbn_plan_create(const VbnProgramDesc* desc, VbnPlan** out_plan) {
     if (!force && !s.heavy && desc->rows_per_thread == 2 && s.rpt > 2) continue;
     const size_t bytes = per_row * s.rpt * s.nt;
     if (bytes > static_cast<size_t>(max_smem)) continue;
-    CUDA_TRY(cudaFuncSetAttribute(s.fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(bytes)));
+    CUDA_TRY(cudaFuncSetAttribute(s.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s.fn, s.nt, bytes));
     if (occ < 1) continue;
@@ -192,6 +193,7 @@ int32_t vbn_run_forward(const VbnPlan* plan, const VbnRunDesc* run, void* stream
   a.n_slots = plan->desc.n_slots;
   a.n_scratch = plan->desc.n_scratch;
   a.logp_as_pdf = run->logp_as_pdf;
+  a.logw_accumulate = run->logw_accumulate;
   a.n_queries = run->n_queries;
   a.n_samples = run->n_samples;
   a.n_rows = run->n_queries * run->n_samples;
@@ -276,6 +278,39 @@ int32_t vbn_ess_below(const float* stats_dev, int64_t n_queries, float threshold
   const unsigned grid = static_cast<unsigned>((n_queries + 255) / 256);
   vbn::ess_below_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(stats_dev, n_queries,
                                                                            threshold, flag_dev);
+  CUDA_TRY(cudaGetLastError());
+  return VBN_OK;
+}
+
+int32_t vbn_row_cdf(const float* w_dev, int64_t n_queries, int64_t n_samples, float* cdf_dev, void* stream) {
+  if (!w_dev || !cdf_dev || n_queries <= 0 || n_samples <= 0) return fail(VBN_E_INVALID, "bad argument to vbn_row_cdf");
+  vbn::row_cdf_kernel<<<static_cast<unsigned>(n_queries), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w_dev, n_samples, cdf_dev);
+  CUDA_TRY(cudaGetLastError());
+  return VBN_OK;
+}
+
+int32_t vbn_resample_indices(const float* cdf_dev, int64_t n_queries, int64_t n_samples, uint64_t seed,
+                             uint64_t call_offset, int64_t query_offset, int64_t sample_offset,
+                             int32_t* idx_dev, void* stream) {
+  if (!cdf_dev || !idx_dev || n_queries <= 0 || n_samples <= 0)
+    return fail(VBN_E_INVALID, "bad argument to vbn_resample_indices");
+  const int64_t rows = n_queries * n_samples;
+  vbn::resample_index_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      cdf_dev, n_queries, n_samples, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32),
+      static_cast<uint32_t>(call_offset), static_cast<uint32_t>(query_offset), static_cast<uint32_t>(sample_offset),
+      idx_dev);
+  CUDA_TRY(cudaGetLastError());
+  return VBN_OK;
+}
+
+int32_t vbn_gather_rows(const float* src_dev, float* dst_dev, const int32_t* idx_dev, int32_t n_cols,
+                        int64_t n_queries, int64_t n_samples, void* stream) {
+  if (!src_dev || !dst_dev || !idx_dev || n_cols <= 0 || n_queries <= 0 || n_samples <= 0)
+    return fail(VBN_E_INVALID, "bad argument to vbn_gather_rows");
+  const int64_t rows = n_queries * n_samples;
+  vbn::gather_rows_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src_dev, dst_dev, idx_dev, n_cols, n_queries, n_samples);
   CUDA_TRY(cudaGetLastError());
   return VBN_OK;
 }

@@ -247,6 +247,85 @@ __global__ void posterior_merge_kernel(const float* __restrict__ partials, const
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Resampling step of resampled_importance_sampling (resampled_importance_sampling.py:33-41):
+//   idx = torch.multinomial(softmax(logw), S, replacement=True); samples = samples[b, idx]
+// as three kernels: per-query inclusive CDF of the weights, inverse-CDF index draws (one Philox
+// uniform per output row + binary search), and a gather of the live node columns.
+// ---------------------------------------------------------------------------------------
+// grid B, 256 threads: cdf[b, s] = sum_{t <= s} w[b, t]; the running carry is kept in double
+__global__ void __launch_bounds__(256) row_cdf_kernel(const float* __restrict__ w, int64_t n_samples,
+                                                       float* __restrict__ cdf) {
+  __shared__ double warp_sums[8];
+  __shared__ double carry_sh;
+  const int64_t b = blockIdx.x;
+  const float* x = w + b * n_samples;
+  float* y = cdf + b * n_samples;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_sh = 0.0;
+  __syncthreads();
+  for (int64_t base = 0; base < n_samples; base += 1024) {
+    const int64_t i0 = base + threadIdx.x * 4;
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = i0 + k < n_samples ? x[i0 + k] : 0.0f;
+    double t = static_cast<double>(v[0]) + v[1] + v[2] + v[3];
+    double inc = t;  // inclusive scan of the per-thread sums across the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double n = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += n;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    double before = carry_sh;
+    for (int q = 0; q < warp; ++q) before += warp_sums[q];
+    double run = before + inc - t;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      run += v[k];
+      if (i0 + k < n_samples) y[i0 + k] = static_cast<float>(run);
+    }
+    __syncthreads();
+    if (threadIdx.x == 255) carry_sh = before + inc;
+    __syncthreads();
+  }
+}
+
+// one thread per output row (b, s): u ~ U(0, total_b) from the row's own Philox stream, then the
+// first position whose cumulative weight exceeds u
+__global__ void __launch_bounds__(256) resample_index_kernel(const float* __restrict__ cdf, int64_t n_queries,
+                                                              int64_t n_samples, uint32_t key0, uint32_t key1,
+                                                              uint32_t call_offset, uint32_t query_offset,
+                                                              uint32_t sample_offset, int32_t* __restrict__ idx) {
+  const int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (r >= n_queries * n_samples) return;
+  const int64_t b = r / n_samples, s = r - b * n_samples;
+  const uint4 c = make_uint4(sample_offset + static_cast<uint32_t>(s), query_offset + static_cast<uint32_t>(b),
+                             0x7FFFFFFFu, call_offset);  // stream tag 1 (uniform/row), block 0x3FFFFFFF: unused by ops
+  const uint4 rnd = philox4x32_10(c, make_uint2(key0, key1));
+  const float* row = cdf + b * n_samples;
+  const float u = u01(rnd.x) * row[n_samples - 1];
+  int64_t lo = 0, hi = n_samples - 1;  // invariant: answer in [lo, hi]
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (row[mid] > u) hi = mid; else lo = mid + 1;
+  }
+  idx[r] = static_cast<int32_t>(lo);
+}
+
+// dst[c][b][s] = src[c][b][idx[b][s]] for n_cols columns of B*S floats
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                           const int32_t* __restrict__ idx, int32_t n_cols,
+                                                           int64_t n_queries, int64_t n_samples) {
+  const int64_t rows = n_queries * n_samples;
+  const int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (r >= rows) return;
+  const int64_t b = r / n_samples;
+  const int64_t from = b * n_samples + idx[r];
+  for (int c = 0; c < n_cols; ++c) dst[c * rows + r] = __ldg(src + c * rows + from);
+}
+
 // gaussian_exact grid (vbn/inference/gaussian_exact.py:166-183): per query b with Normal(loc_b, scale_b)
 //   z_s = linspace(-k, k, S)[s];  samples[b,s] = loc_b + scale_b * z_s;
 //   pdf[b,s] = exp(-0.5 * (z_s^2 + 2 ln scale_b + ln 2 pi))

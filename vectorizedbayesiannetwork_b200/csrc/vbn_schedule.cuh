@@ -21,6 +21,7 @@ struct ScheduleArgs {
   int32_t n_slots;
   int32_t n_scratch;
   int32_t logp_as_pdf;
+  int32_t logw_accumulate;
   int64_t n_queries;  // B (local)
   int64_t n_samples;  // S (local)
   int64_t n_rows;     // B*S
@@ -1166,7 +1167,7 @@ __device__ __forceinline__ void run_ops(Ctx<RPT, NT, TC>& c) {
   if (a.logw) {
 #pragma unroll
     for (int j = 0; j < RPT; ++j)
-      if (c.rows.valid[j]) a.logw[c.rows.r[j]] = c.rows.logw[j];
+      if (c.rows.valid[j]) a.logw[c.rows.r[j]] = (a.logw_accumulate ? a.logw[c.rows.r[j]] : 0.0f) + c.rows.logw[j];
   }
   if (a.logp) {
 #pragma unroll

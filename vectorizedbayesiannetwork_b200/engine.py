@@ -103,7 +103,7 @@ class DevicePlan:
             noise: Sequence[Dict[str, torch.Tensor]] = (), logw: Optional[torch.Tensor] = None,
             logp: Optional[torch.Tensor] = None, logp_as_pdf: bool = False, seed: int = 0,
             call_offset: int = 0, query_offset: int = 0, sample_offset: int = 0,
-            error_flag: Optional[torch.Tensor] = None) -> None:
+            error_flag: Optional[torch.Tensor] = None, logw_accumulate: bool = False) -> None:
         p = self.program
         n_rows = int(n_queries) * int(n_samples)
         if len(inputs) != len(p.inputs) or len(stores) != len(p.stores) or len(noise) != len(p.noise):
@@ -145,7 +145,7 @@ class DevicePlan:
                 noise_dev=base + 24 * (n_in + n_st) if len(noise) else None,
                 logw_dev=logw.data_ptr() if logw is not None else None,
                 logp_dev=logp.data_ptr() if logp is not None else None,
-                logp_as_pdf=1 if logp_as_pdf else 0, reserved=0,
+                logp_as_pdf=1 if logp_as_pdf else 0, logw_accumulate=1 if logw_accumulate else 0,
                 error_flag_dev=error_flag.data_ptr() if error_flag is not None else None,
             )
             events = KERNEL_EVENTS
@@ -213,6 +213,36 @@ def normalize_weights(logw: torch.Tensor, stats: torch.Tensor, *, normalize: boo
                                           ess.data_ptr() if ess is not None else None, _stream_ptr(dev)))
         L.count_launch(1)
     return w, ess
+
+
+def resample_indices(weights: torch.Tensor, *, seed: int, call_offset: int, query_offset: int = 0) -> torch.Tensor:
+    """idx[b, :] ~ multinomial(weights[b], S, replacement=True) (resampled_importance_sampling.py:37-38):
+    per-query CDF + one Philox uniform and a binary search per output row.  int32 [B, S]."""
+    lib = L.load()
+    dev = weights.device
+    b, s = weights.shape
+    with torch.cuda.device(dev):
+        cdf = torch.empty(b, s, device=dev, dtype=torch.float32)
+        idx = torch.empty(b, s, device=dev, dtype=torch.int32)
+        sp = _stream_ptr(dev)
+        L.check(lib.vbn_row_cdf(weights.contiguous().data_ptr(), b, s, cdf.data_ptr(), sp))
+        L.check(lib.vbn_resample_indices(cdf.data_ptr(), b, s, int(seed) & (2**64 - 1), int(call_offset),
+                                         int(query_offset), 0, idx.data_ptr(), sp))
+        L.count_launch(2)
+    return idx
+
+
+def gather_rows(cols: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """cols [n_cols, B*S] (node columns, SoA) -> same shape with rows re-drawn: out[c][b,s] = cols[c][b, idx[b,s]]."""
+    lib = L.load()
+    dev = cols.device
+    b, s = idx.shape
+    with torch.cuda.device(dev):
+        out = torch.empty_like(cols)
+        L.check(lib.vbn_gather_rows(cols.data_ptr(), out.data_ptr(), idx.data_ptr(), int(cols.shape[0]), b, s,
+                                    _stream_ptr(dev)))
+        L.count_launch(1)
+    return out
 
 
 def posterior_stats(pdf: torch.Tensor, samples: torch.Tensor, eps: float = 1e-12):

@@ -254,6 +254,145 @@ class MonteCarloMarginalization:
         return out["logp"], out["stores"][target]
 
 
+@register_inference("resampled_importance_sampling")
+class ResampledImportanceSampling:
+    """vbn/inference/resampled_importance_sampling.py:13-105.
+
+    Resampling permutes rows inside a query, which the fused row-local schedule cannot do on chip, so
+    the schedule is cut after every evidence node: each segment is one fused launch that reads the live
+    node columns of the previous segments from HBM (SoA, per-row inputs) and writes the columns later
+    segments still need.  Between segments: ESS test (4-byte flag read, like IS), and when any query is
+    below the threshold, multinomial resampling of every live column (vbn_row_cdf /
+    vbn_resample_indices / vbn_gather_rows) and a reset of the log-weights."""
+
+    def __init__(self, n_samples: int = 512, ess_threshold: float = 0.5, resample: bool = True,
+                 clamp_obs: bool = True, **kwargs) -> None:
+        self.n_samples = int(n_samples)
+        self.ess_threshold = float(ess_threshold)
+        self.resample = bool(resample)
+        self.clamp_obs = bool(clamp_obs)
+        self._cache: Dict[tuple, list] = {}
+        self._last_ess: Optional[torch.Tensor] = None
+        self._last_resampled = False
+
+    # ---- segment compilation ------------------------------------------------------------------
+    def _segments(self, vbn, query: Query, inject: frozenset):
+        cpds = model_cpds(vbn)
+        fp = tuple((c._uid, c._version) for c in cpds.values())
+        key = (fp, query.target, tuple(sorted(query.evidence)), tuple(sorted(query.do)), tuple(sorted(inject)),
+               str(vbn.device))
+        hit = self._cache.get(key)
+        if hit is not None:
+            return hit
+        topo, parents = _topology(vbn)
+        pos = {n: i for i, n in enumerate(topo)}
+        fixed = set(query.evidence) | set(query.do)
+        evaluated = lambda n: n not in query.do  # drawn or scored: reads its parents
+        bounds, start = [], 0
+        for i, n in enumerate(topo):
+            if n in query.evidence:
+                bounds.append((start, i + 1, True))
+                start = i + 1
+        if start < len(topo):
+            bounds.append((start, len(topo), False))
+        segs = []
+        for lo, hi, ends_ev in bounds:
+            seg_nodes = topo[lo:hi]
+            needs = [p for n in seg_nodes if evaluated(n) for p in parents[n] if pos[p] < lo]
+            carried_in = sorted({p for p in needs if p not in fixed}, key=pos.get)
+            fixed_in = sorted({p for p in needs if p in fixed}, key=pos.get)
+            later = {p for n in topo[hi:] if evaluated(n) for p in parents[n]}
+            keep = lambda n: n not in fixed and (n in later or n == query.target)
+            roles: Dict[str, Role] = {}
+            for n in carried_in:
+                roles[n] = Role(src="fixed_row", density=False)
+            for n in fixed_in:
+                roles[n] = Role(src="fixed_q", density=False)
+            for n in seg_nodes:
+                if n in query.do:
+                    roles[n] = Role(src="fixed_q", density=False)
+                elif n in query.evidence:
+                    roles[n] = Role(src="fixed_q", add_logw=True)
+                else:
+                    roles[n] = Role(src="sample", shared=len(parents[n]) == 0, inject=n in inject, store=keep(n))
+            order = carried_in + fixed_in + seg_nodes
+            prog = compile_schedule(order, parents, cpds, roles, table_fn=E.discrete_table_fn)
+            segs.append({"plan": E.DevicePlan(prog, vbn.device), "ends_ev": ends_ev,
+                         "live_after": [n for n in topo[:hi] if keep(n)]})
+        if len(self._cache) > 64:
+            self._cache.clear()
+        self._cache[key] = segs
+        return segs
+
+    def infer_posterior(self, vbn, query: Query, **kwargs):
+        n_samples = int(kwargs.get("n_samples", self.n_samples))
+        ess_threshold = float(kwargs.get("ess_threshold", self.ess_threshold))
+        resample = bool(kwargs.get("resample", self.resample))
+        clamp_obs = bool(kwargs.get("clamp_obs", self.clamp_obs))
+        shard = kwargs.get("shard")
+        if shard is not None and shard.kind != "queries":
+            raise ValueError("resampled_importance_sampling shards queries only (resampling is per query)")
+        noise = kwargs.get("noise") or {}
+        picks = list(noise.get("__resample__", []))
+        seed = E.draw_seed() if kwargs.get("seed") is None else int(kwargs["seed"])
+        dev = _check_model(vbn)
+        b_full = infer_batch_size(query.evidence, query.do)
+        b, q_off = (b_full, 0) if shard is None else shard.local_queries(b_full)
+        s = n_samples
+        rows = b * s
+        threshold = max(1.0, ess_threshold * float(s)) if ess_threshold <= 1.0 else float(ess_threshold)
+        segs = self._segments(vbn, query, frozenset(k for k in noise if k != "__resample__"))
+        live: Dict[str, torch.Tensor] = {}  # node -> [D, B*S] column block
+        self._last_resampled = False
+        with torch.cuda.device(dev):
+            logw = torch.zeros(b, s, device=dev, dtype=torch.float32)
+            flag_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+            for k, seg in enumerate(segs):
+                plan = seg["plan"]
+                prog = plan.program
+                fixed = _ScheduleRunner.fixed_table(plan, query, b, clamp_obs=clamp_obs, shard=shard)
+                new = {n: torch.empty(prog.dims[n], rows, device=dev, dtype=torch.float32) for n in prog.stores}
+                plan.run(b, s, fixed=fixed, inputs=[live[n].t() for n in prog.inputs],
+                         stores=[new[n].t() for n in prog.stores], noise=[noise[n] for n in prog.noise],
+                         logw=logw if prog.needs_logw else None, logw_accumulate=True, seed=seed, call_offset=k,
+                         query_offset=q_off, error_flag=flag_dev)
+                live.update(new)
+                live = {n: live[n] for n in seg["live_after"]}
+                if seg["ends_ev"] and resample:
+                    stats = E.lse_stats(logw)
+                    w, ess = E.normalize_weights(logw, stats)
+                    self._last_ess = ess
+                    flag = E.ess_below(stats, threshold)
+                    if shard is not None and shard.world > 1:
+                        flag = shard.any_flag(flag)
+                    if int(flag.item()) != 0:
+                        if picks:
+                            idx = picks.pop(0).to(device=dev, dtype=torch.int32).reshape(b, s).contiguous()
+                        else:
+                            idx = E.resample_indices(w, seed=seed, call_offset=0x40000000 + k, query_offset=q_off)
+                        live = {n: E.gather_rows(t, idx) for n, t in live.items()}
+                        logw.zero_()
+                        self._last_resampled = True
+            cpds = model_cpds(vbn)
+            if any(c.kind in ("softmax_nn", "categorical_table") for c in cpds.values()) and int(flag_dev.item()) != 0:
+                raise ValueError("Found values outside discrete class set.")
+            stats = E.lse_stats(logw)
+            w, _ = E.normalize_weights(logw, stats)
+            t = query.target
+            if t in live:
+                d = live[t].shape[0]
+                samples = live[t].view(d, b, s).permute(1, 2, 0).contiguous()
+            else:  # the target is itself fixed
+                v = query.do[t] if t in query.do else query.evidence[t]
+                v = v.to(device=dev, dtype=torch.float32)
+                if clamp_obs and t in query.evidence:
+                    v = clamp_evidence(v)
+                if shard is not None:
+                    v = shard.slice_queries(v)
+                samples = v.unsqueeze(1).expand(b, s, -1)
+        return w, samples
+
+
 def _exact_setup(vbn, query: Query):
     """Common prologue of the exact methods (gaussian_exact.py:134-164, categorical_exact.py:89-118):
     returns (b, target cpd, fixed target value | None, parents all fixed?, parent tensor [b,Dp] | None)."""

@@ -5,7 +5,7 @@ The registry decorator refuses duplicate keys (registry.py:18-20), hence plain d
 from __future__ import annotations
 
 from .inference import (AncestralSampler, CategoricalExact, GaussianExact, ImportanceSampling,
-                        LikelihoodWeighting, MonteCarloMarginalization)
+                        LikelihoodWeighting, MonteCarloMarginalization, ResampledImportanceSampling)
 
 _ORIGINAL = {}
 
@@ -17,7 +17,8 @@ def install(vbn_module=None) -> None:
     for key, cls in (("likelihood_weighting", LikelihoodWeighting),
                      ("importance_sampling", ImportanceSampling),
                      ("monte_carlo_marginalization", MonteCarloMarginalization),
-                     ("gaussian_exact", GaussianExact), ("categorical_exact", CategoricalExact)):
+                     ("gaussian_exact", GaussianExact), ("categorical_exact", CategoricalExact),
+                     ("resampled_importance_sampling", ResampledImportanceSampling)):
         _ORIGINAL.setdefault(("inference", key), reg.INFERENCE_REGISTRY.get(key))
         reg.INFERENCE_REGISTRY[key] = cls
     _ORIGINAL.setdefault(("sampling", "ancestral"), reg.SAMPLING_REGISTRY.get("ancestral"))
