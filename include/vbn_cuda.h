@@ -225,6 +225,18 @@ int32_t vbn_gather_rows(const float* src_dev, float* dst_dev, const int32_t* idx
                         int64_t n_queries, int64_t n_samples, void* stream);
 
 /*
+ * rao_blackwellized_marginalization epilogues (vbn/inference/rao_blackwellized_marginalization.py:277-317):
+ *   vbn_weighted_sum          : out[b][k] = sum_s w[b,s] x[b,s,k]            (categorical marginal)
+ *   vbn_gaussian_mixture_grid : mixture of N(mu_s, sigma_s) weighted by w on a +-stddevs grid around the
+ *                               mixture mean; loc_scale_dev [B][S][2]; pdf_dev / grid_dev [B][n_out]
+ */
+int32_t vbn_weighted_sum(const float* w_dev, const float* x_dev, int64_t n_queries, int64_t n_samples,
+                         int32_t width, float* out_dev, void* stream);
+int32_t vbn_gaussian_mixture_grid(const float* w_dev, const float* loc_scale_dev, int64_t n_queries,
+                                  int64_t n_particles, int64_t n_out, float stddevs, float min_scale,
+                                  float* pdf_dev, float* grid_dev, void* stream);
+
+/*
  * gaussian_exact support grid (vbn/inference/gaussian_exact.py:166-183): loc_scale_dev [B][2];
  * samples[b,s] = loc + scale * linspace(-stddevs, stddevs, S)[s], pdf[b,s] = N(samples; loc, scale).
  */

@@ -840,6 +840,134 @@ def resampled_importance_sampling(spec, query, n_samples: int, noise=None, ess_t
 
 
 # --------------------------------------------------------------------------------------
+# rao_blackwellized_marginalization (vbn/inference/rao_blackwellized_marginalization.py:15-324)
+# --------------------------------------------------------------------------------------
+
+
+def _descendants(spec, node: str) -> set:
+    children: Dict[str, List[str]] = {n: [] for n in spec["nodes"]}
+    for n in spec["nodes"]:
+        for p in spec["parents"][n]:
+            children[p].append(n)
+    out, stack = set(), [node]
+    while stack:
+        for c in children[stack.pop()]:
+            if c not in out:
+                out.add(c)
+                stack.append(c)
+    return out
+
+
+def rb_normalized_weights(logw: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    logw = torch.nan_to_num(logw, nan=-1e30, posinf=1e30, neginf=-1e30)  # :68-77
+    logw = logw - logw.max(dim=1, keepdim=True).values
+    w = torch.exp(logw)
+    denom = w.sum(dim=1, keepdim=True)
+    uniform = torch.full_like(w, 1.0 / max(1, w.shape[1]))
+    return torch.where(denom > eps, w / denom.clamp_min(eps), uniform)
+
+
+def rao_blackwellized_marginalization(spec, query, n_samples: int, noise=None, n_particles: Optional[int] = None,
+                                      stddevs: float = 4.0, min_scale: float = 1e-6, return_info: bool = False):
+    query = _norm_query(query)
+    noise = noise or TorchNoise()
+    n_samples = max(1, int(n_samples))
+    n_particles = max(1, int(n_particles if n_particles is not None else n_samples))
+    b = infer_batch_size(query["evidence"], query["do"])
+    st = _State(spec, query)
+    t = st.target_idx
+    tnode = st.topo[t]
+
+    def fallback(reason):
+        out = likelihood_weighting(spec, query, n_samples, noise=noise)
+        return (*out, {"fallback": True, "reason": reason}) if return_info else out
+
+    def done(*out):
+        return (*out, {"fallback": False, "reason": None}) if return_info else out
+
+    desc = {st.topo.index(n) for n in _descendants(spec, tnode)}
+    if any(st.evidence_mask[i] or st.do_mask[i] for i in desc):  # :213-220
+        return fallback("target has observed/intervened descendants")
+    fixed = _fixed_values(query, st, torch.float32, clamp_obs=True)
+    if fixed[t] is not None:  # :223-227
+        return done(torch.ones(b, 1), fixed[t].unsqueeze(1).expand(b, 1, -1))
+    skip = set(desc) | {t}
+    samples = torch.zeros(b, n_particles, st.total_dim)
+    logw = torch.zeros(b, n_particles)
+    for idx, node in enumerate(st.topo):  # :237-256
+        if idx in skip:
+            continue
+        c = spec["cpds"][node]
+        parents = _gather_parents(samples, st, idx)
+        if fixed[idx] is not None:
+            value = fixed[idx].unsqueeze(1).expand(b, n_particles, -1)
+            samples[..., st.slices[idx]] = value
+            if st.evidence_mask[idx]:
+                logw = logw + cpd_log_prob(c, value, parents)
+            continue
+        samples[..., st.slices[idx]] = cpd_sample(c, parents, n_particles, noise, ("rb", node))
+    w = rb_normalized_weights(logw)
+    parents = _gather_parents(samples, st, t)
+    c = spec["cpds"][tnode]
+    if c["kind"] in ("softmax_nn", "categorical_table"):  # _target_categorical_probs :155-194
+        if c["kind"] == "softmax_nn":
+            if parents is None:
+                raw = c["root_log_probs"] if c["root_ready"] else c["logits"]
+                logits = (torch.log_softmax(raw, dim=-1) if c["root_ready"] else raw).view(1, 1, c["output_dim"], -1)
+                logits = logits.expand(b, 1, -1, -1)
+            else:
+                logits = snn_logits(c, parents, b, n_particles)
+            support = c["sample_values"][0]
+        else:
+            logits = ct_logits(c, parents)
+            if parents is None:
+                logits = logits.expand(b, 1, -1, -1)
+            support = c["class_values"][0]
+        probs = torch.softmax(logits, dim=-1)
+        if probs.dim() == 4 and probs.shape[2] == 1:
+            probs = probs[:, :, 0, :]
+        if probs.dim() == 3 and probs.shape[-1] == int(c["n_classes"]):
+            if probs.shape[1] != n_particles:
+                if probs.shape[1] != 1:
+                    return fallback("categorical conditional shape mismatch")
+                probs = probs.expand(-1, n_particles, -1)
+            marginal = (w.unsqueeze(-1) * probs).sum(dim=1)  # :277-279
+            return done(marginal, support.to(dtype=marginal.dtype).view(1, -1, 1).expand(b, -1, 1))
+    if c["kind"] in ("linear_gaussian", "gaussian_nn") and c["output_dim"] == 1:  # _target_gaussian_params :92-153
+        loc, scale = (lg_params if c["kind"] == "linear_gaussian" else gnn_params)(c, parents)
+        loc = loc.reshape(1, 1, -1) if loc.dim() == 1 else loc
+        scale = scale.reshape(1, 1, -1) if scale.dim() == 1 else scale
+        if loc.shape[0] == 1 and b > 1:
+            loc = loc.expand(b, -1, -1)
+        if scale.shape[0] == 1 and b > 1:
+            scale = scale.expand(b, -1, -1)
+        if scale.shape[1] == 1 and loc.shape[1] > 1:
+            scale = scale.expand(-1, loc.shape[1], -1)
+        scale = torch.nan_to_num(scale, nan=min_scale, posinf=min_scale, neginf=min_scale).abs().clamp_min(min_scale)
+        if loc.shape[1] != n_particles:
+            if loc.shape[1] != 1:
+                return fallback("gaussian conditional shape mismatch")
+            loc = loc.expand(-1, n_particles, -1)
+            scale = scale.expand(-1, n_particles, -1)
+        comp_var = scale.squeeze(-1) ** 2  # :296-317
+        comp_mean = loc.squeeze(-1)
+        mix_mean = (w * comp_mean).sum(dim=1)
+        second = (w * (comp_var + comp_mean**2)).sum(dim=1)
+        mix_std = (second - mix_mean**2).clamp_min(min_scale**2).sqrt()
+        z = torch.linspace(0.0, 1.0, n_samples).view(1, n_samples, 1)
+        lo = (mix_mean - stddevs * mix_std).view(b, 1, 1)
+        hi = (mix_mean + stddevs * mix_std).view(b, 1, 1)
+        grid = lo + (hi - lo) * z
+        x = grid.squeeze(-1).unsqueeze(1)
+        mu = loc.squeeze(-1).unsqueeze(-1)
+        sigma = scale.squeeze(-1).unsqueeze(-1).clamp_min(min_scale)
+        zn = (x - mu) / sigma
+        comp_pdf = torch.exp(-0.5 * zn**2) / (math.sqrt(2.0 * math.pi) * sigma)
+        return done((w.unsqueeze(-1) * comp_pdf).sum(dim=1), grid)
+    return fallback("unsupported target CPD for RB marginalization")
+
+
+# --------------------------------------------------------------------------------------
 # exact methods: closed form only when every parent of the target is fixed,
 # otherwise the configured fallback method runs (vbn/inference/gaussian_exact.py:134-183,
 # vbn/inference/categorical_exact.py:89-128)

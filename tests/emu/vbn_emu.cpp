@@ -120,6 +120,32 @@ int32_t vbn_gather_rows(const float* src, float* dst, const int32_t* idx, int32_
   return 0;
 }
 
+int32_t vbn_weighted_sum(const float* w, const float* x, int64_t B, int64_t S, int32_t K, float* out, void*) {
+  for (int64_t b = 0; b < B; ++b) for (int k = 0; k < K; ++k) {
+    double acc = 0; for (int64_t s = 0; s < S; ++s) acc += (double)w[b * S + s] * x[(b * S + s) * K + k];
+    out[b * K + k] = (float)acc;
+  }
+  return 0;
+}
+int32_t vbn_gaussian_mixture_grid(const float* w, const float* ls, int64_t B, int64_t S, int64_t N, float k, float min_scale,
+                                  float* pdf, float* grid, void*) {
+  for (int64_t b = 0; b < B; ++b) {
+    auto sg = [&](int64_t s) { float v = ls[(b * S + s) * 2 + 1]; if (!(v == v) || std::fabs(v) == INFINITY) v = min_scale; return std::max(std::fabs(v), min_scale); };
+    double m1 = 0, m2 = 0;
+    for (int64_t s = 0; s < S; ++s) { const double wi = w[b * S + s], mu = ls[(b * S + s) * 2], g = sg(s); m1 += wi * mu; m2 += wi * (g * g + mu * mu); }
+    const float mean = (float)m1, sd = std::sqrt(std::max((float)(m2 - m1 * m1), min_scale * min_scale));
+    const float lo = mean - k * sd, hi = mean + k * sd, step = N > 1 ? 1.0f / (float)(N - 1) : 0.0f;
+    for (int64_t j = 0; j < N; ++j) {
+      const float z = j < N / 2 ? step * (float)j : 1.0f - step * (float)(N - 1 - j);
+      const float x = lo + (hi - lo) * z;
+      double acc = 0;
+      for (int64_t s = 0; s < S; ++s) { const float g = sg(s); const float zn = (x - ls[(b * S + s) * 2]) / g; acc += (double)w[b * S + s] * std::exp(-0.5f * zn * zn) / (2.5066282746310002f * g); }
+      grid[b * N + j] = x; pdf[b * N + j] = (float)acc;
+    }
+  }
+  return 0;
+}
+
 int32_t vbn_gaussian_grid(const float* ls, int64_t B, int64_t S, float k, float min_scale, float* pdf, float* x, void*) {
   const float step = S > 1 ? (k - (-k)) / (float)(S - 1) : 0.0f;
   for (int64_t b = 0; b < B; ++b) {

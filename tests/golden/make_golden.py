@@ -27,6 +27,7 @@ METHODS = {
     "is": ("importance_sampling", O.importance_sampling),
     "mcm": ("monte_carlo_marginalization", O.monte_carlo_marginalization),
     "ris": ("resampled_importance_sampling", O.resampled_importance_sampling),
+    "rb": ("rao_blackwellized_marginalization", O.rao_blackwellized_marginalization),
     "gexact": ("gaussian_exact", O.gaussian_exact),
     "cexact": ("categorical_exact", O.categorical_exact),
 }
@@ -136,6 +137,32 @@ def exact_files():
     return out
 
 
+def rb_files():
+    """rao_blackwellized_marginalization:  python tests/golden/make_golden.py rb"""
+    torch.manual_seed(1357)
+    out = {}
+    ev = torch.tensor([[0.2], [1.0], [-0.7]])
+    m = refmodels.lg_chain_model(n_nodes=6)
+    spec = O.spec_from_reference(m)
+    qs = [{"target": "x5", "evidence": {"x1": ev}}, {"target": "x0", "evidence": {}},
+          {"target": "x2", "evidence": {"x4": ev}}, {"target": "x3", "evidence": {"x3": ev}},
+          {"target": "x4", "evidence": {"x1": ev}, "do": {"x2": ev}}]
+    out["rb_lg"] = {"spec": spec, "cases": [run_case(m, spec, q, 40, "rb", 41) for q in qs], "cpd_cases": []}
+    m = refmodels.table_model()
+    spec = O.spec_from_reference(m)
+    qs = [{"target": "slip", "evidence": {"season": torch.tensor([[3.0], [0.0], [1.0]])}},
+          {"target": "wet", "evidence": {"season": torch.tensor([[1.0], [2.0]])}},
+          {"target": "season", "evidence": {}}, {"target": "sprinkler", "evidence": {"season": torch.tensor([[1.0]])}}]
+    out["rb_table"] = {"spec": spec, "cases": [run_case(m, spec, q, 48, "rb", 42) for q in qs], "cpd_cases": []}
+    m = refmodels.mixed_model(epochs=1)
+    spec = O.spec_from_reference(m)
+    qs = [{"target": "e", "evidence": {"a": torch.randn(3, 1)}},      # gaussian_nn target, mdn/lg parents sampled
+          {"target": "c", "evidence": {"a": torch.randn(3, 1)}},      # mdn target -> fallback
+          {"target": "g", "evidence": {"a": torch.randn(3, 1)}}]      # 2-D target -> fallback
+    out["rb_mixed"] = {"spec": spec, "cases": [run_case(m, spec, q, 24, "rb", 43) for q in qs], "cpd_cases": []}
+    return out
+
+
 def ris_files():
     """resampled_importance_sampling:  python tests/golden/make_golden.py ris"""
     torch.manual_seed(2468)
@@ -172,6 +199,9 @@ def save(files):
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "table":
         save(table_files())
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "rb":
+        save(rb_files())
         return
     if len(sys.argv) > 1 and sys.argv[1] == "ris":
         save(ris_files())
@@ -244,6 +274,7 @@ def main():
     files.update(table_files())
     files.update(exact_files())
     files.update(ris_files())
+    files.update(rb_files())
     save(files)
 
 

@@ -239,3 +239,29 @@ def test_resampled_importance_sampling():
     torch.manual_seed(6)
     ow, os_ = O.resampled_importance_sampling(mspec, tq, 32)
     _eq(rw, ow), _eq(rs, os_)
+
+
+def test_rao_blackwellized_marginalization():
+    """vbn/inference/rao_blackwellized_marginalization.py: gaussian mixture grid, categorical marginal, fallbacks."""
+    ev = torch.tensor([[0.2], [1.0], [-0.7]])
+    model = refmodels.lg_chain_model(n_nodes=6)
+    spec = O.spec_from_reference(model)
+    for q, S in (({"target": "x5", "evidence": {"x1": ev}}, 33),                  # gaussian mixture over sampled parents
+                 ({"target": "x0", "evidence": {}, "do": {}}, 16),                # root target
+                 ({"target": "x2", "evidence": {"x4": ev}}, 24),                  # observed descendant -> fallback
+                 ({"target": "x3", "evidence": {"x3": ev}}, 8),                   # fixed target
+                 ({"target": "x4", "evidence": {"x1": ev}, "do": {"x2": ev}}, 20)):
+        _exact_eq(model, spec, "rao_blackwellized_marginalization", q, S, O.rao_blackwellized_marginalization)
+    m2 = refmodels.table_model()
+    s2 = O.spec_from_reference(m2)
+    for q in ({"target": "slip", "evidence": {"season": torch.tensor([[3.0], [0.0], [1.0]])}},   # softmax_nn target
+              {"target": "wet", "evidence": {"season": torch.tensor([[1.0], [2.0]])}},            # categorical_table target
+              {"target": "season", "evidence": {}},                                               # root categorical
+              {"target": "sprinkler", "evidence": {"season": torch.tensor([[1.0]])}}):            # softmax_nn root
+        _exact_eq(m2, s2, "rao_blackwellized_marginalization", q, 40, O.rao_blackwellized_marginalization)
+    m3 = refmodels.readme_model(n=300, epochs=2)
+    s3 = O.spec_from_reference(m3)
+    _exact_eq(m3, s3, "rao_blackwellized_marginalization", {"target": "feature_2", "evidence": {"feature_0": ev}}, 16,
+              O.rao_blackwellized_marginalization)  # mdn target -> unsupported -> fallback
+    _exact_eq(m3, s3, "rao_blackwellized_marginalization", {"target": "feature_0", "evidence": {}}, 16,
+              O.rao_blackwellized_marginalization)  # gaussian_nn root

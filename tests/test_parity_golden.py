@@ -18,7 +18,8 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 FILES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, "*.pt")))
 RTOL, ATOL = 1e-5, 1e-6
 METHOD_NAMES = {"lw": "likelihood_weighting", "is": "importance_sampling", "mcm": "monte_carlo_marginalization",
-                "gexact": "gaussian_exact", "cexact": "categorical_exact", "ris": "resampled_importance_sampling"}
+                "gexact": "gaussian_exact", "cexact": "categorical_exact", "ris": "resampled_importance_sampling",
+                "rb": "rao_blackwellized_marginalization"}
 
 
 def _load(name):
@@ -58,7 +59,7 @@ def test_inference_methods_match_reference(backend, name):
             _close(got, case["expect"]["samples"], tag + " samples")
             continue
         model.set_inference_method(METHOD_NAMES[method], n_samples=S)
-        if method == "is":
+        if method in ("is", "rb"):  # two passes with their own draws: {"is"|"rb": ..., "lw": fallback}
             noise = {k: _dev_noise(v, backend.device) for k, v in inj.items()}
         else:  # the exact methods draw only through their likelihood-weighting fallback (scope "lw")
             scope = "lw" if method in ("gexact", "cexact") else method

@@ -12,7 +12,8 @@ from .cpds import (BaseCPD, GaussianNNCPD, KDECPD, LinearGaussianCPD, MDNCPD, So
                    cpd_from_spec, wrap_cpd)
 from .dist import Shard, auto_shard
 from .inference import (AncestralSampler, CategoricalExact, GaussianExact, ImportanceSampling,
-                        LikelihoodWeighting, MonteCarloMarginalization, ResampledImportanceSampling)
+                        LikelihoodWeighting, MonteCarloMarginalization, RaoBlackwellizedMarginalization,
+                        ResampledImportanceSampling)
 from .install import install, uninstall
 
 __all__ = [
@@ -21,6 +22,6 @@ __all__ = [
     "BaseCPD", "LinearGaussianCPD", "GaussianNNCPD", "MDNCPD", "SoftmaxNNCPD", "KDECPD",
     "cpd_from_spec", "wrap_cpd",
     "ImportanceSampling", "LikelihoodWeighting", "MonteCarloMarginalization", "AncestralSampler",
-    "GaussianExact", "CategoricalExact", "ResampledImportanceSampling",
+    "GaussianExact", "CategoricalExact", "ResampledImportanceSampling", "RaoBlackwellizedMarginalization",
     "Shard", "auto_shard", "install", "uninstall",
 ]

@@ -588,7 +588,7 @@ class CategoricalTableCPD(BaseCPD):
         return int(self._class_mask[0].sum())
 
     def param_width(self) -> int:
-        return 0  # conditional() of a table is served on the host from the table itself
+        return self.n_classes  # probs[C] of the row's parent configuration (op_params, VBN_OP_TAB)
 
     def logits_table(self) -> torch.Tensor:
         """[n_cfg, C] log-probabilities: log_softmax(log(clamp(counts / sum, 1e-12)))  (:359-369, :413)."""

@@ -315,6 +315,27 @@ int32_t vbn_gather_rows(const float* src_dev, float* dst_dev, const int32_t* idx
   return VBN_OK;
 }
 
+int32_t vbn_weighted_sum(const float* w_dev, const float* x_dev, int64_t n_queries, int64_t n_samples,
+                         int32_t width, float* out_dev, void* stream) {
+  if (!w_dev || !x_dev || !out_dev || n_queries <= 0 || n_samples <= 0 || width <= 0)
+    return fail(VBN_E_INVALID, "bad argument to vbn_weighted_sum");
+  vbn::weighted_sum_kernel<<<static_cast<unsigned>(n_queries), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w_dev, x_dev, n_samples, width, out_dev);
+  CUDA_TRY(cudaGetLastError());
+  return VBN_OK;
+}
+
+int32_t vbn_gaussian_mixture_grid(const float* w_dev, const float* loc_scale_dev, int64_t n_queries,
+                                  int64_t n_particles, int64_t n_out, float stddevs, float min_scale,
+                                  float* pdf_dev, float* grid_dev, void* stream) {
+  if (!w_dev || !loc_scale_dev || !pdf_dev || !grid_dev || n_queries <= 0 || n_particles <= 0 || n_out <= 0)
+    return fail(VBN_E_INVALID, "bad argument to vbn_gaussian_mixture_grid");
+  vbn::gaussian_mixture_grid_kernel<<<static_cast<unsigned>(n_queries), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w_dev, loc_scale_dev, n_particles, n_out, stddevs, min_scale, pdf_dev, grid_dev);
+  CUDA_TRY(cudaGetLastError());
+  return VBN_OK;
+}
+
 int32_t vbn_gaussian_grid(const float* loc_scale_dev, int64_t n_queries, int64_t n_samples, float stddevs,
                           float min_scale, float* pdf_dev, float* samples_dev, void* stream) {
   if (!loc_scale_dev || !pdf_dev || !samples_dev || n_queries <= 0 || n_samples <= 0)

@@ -326,6 +326,70 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
   for (int c = 0; c < n_cols; ++c) dst[c * rows + r] = __ldg(src + c * rows + from);
 }
 
+// ---------------------------------------------------------------------------------------
+// rao_blackwellized_marginalization epilogues (rao_blackwellized_marginalization.py:277-317).
+// ---------------------------------------------------------------------------------------
+// out[b][k] = sum_s w[b,s] * x[b,s,k]   (categorical marginal; K <= 64).  grid B, 256 threads.
+__global__ void __launch_bounds__(256) weighted_sum_kernel(const float* __restrict__ w, const float* __restrict__ x,
+                                                            int64_t n_samples, int width, float* __restrict__ out) {
+  __shared__ float sh[8];
+  const int64_t b = blockIdx.x;
+  for (int k = 0; k < width; ++k) {
+    float acc = 0.0f;
+    for (int64_t s = threadIdx.x; s < n_samples; s += blockDim.x)
+      acc = fmaf(__ldg(w + b * n_samples + s), __ldg(x + (b * n_samples + s) * width + k), acc);
+    const float t = block_sum256(acc, sh);
+    if (threadIdx.x == 0) out[b * width + k] = t;
+  }
+}
+
+// Gaussian-mixture posterior on a grid: per query b, particles s with (w, mu, sigma):
+//   mix_mean = sum w mu; mix_std = sqrt(max(sum w (sigma^2 + mu^2) - mix_mean^2, min_scale^2))
+//   grid[b,j] = lo + (hi - lo) * linspace(0,1,S_out)[j], lo/hi = mix_mean -/+ stddevs * mix_std
+//   pdf[b,j] = sum_s w exp(-0.5 ((x - mu)/sigma)^2) / (sqrt(2 pi) sigma)
+// grid B, 256 threads; loc_scale [B][S][2]; sigma sanitised like the reference (:145-149, :311).
+__global__ void __launch_bounds__(256) gaussian_mixture_grid_kernel(
+    const float* __restrict__ w, const float* __restrict__ loc_scale, int64_t n_particles, int64_t n_out,
+    float stddevs, float min_scale, float* __restrict__ pdf, float* __restrict__ grid) {
+  __shared__ float sh[8];
+  __shared__ float moments[2];
+  const int64_t b = blockIdx.x;
+  const float* wb = w + b * n_particles;
+  const float* ls = loc_scale + b * n_particles * 2;
+  auto sigma_of = [&](int64_t s) {
+    float sc = __ldg(ls + 2 * s + 1);
+    if (!(sc == sc) || fabsf(sc) == CUDART_INF_F) sc = min_scale;
+    return fmaxf(fabsf(sc), min_scale);
+  };
+  float m1 = 0.0f, m2 = 0.0f;
+  for (int64_t s = threadIdx.x; s < n_particles; s += blockDim.x) {
+    const float wi = __ldg(wb + s), mu = __ldg(ls + 2 * s), sg = sigma_of(s);
+    m1 = fmaf(wi, mu, m1);
+    m2 = fmaf(wi, fmaf(sg, sg, mu * mu), m2);
+  }
+  const float t1 = block_sum256(m1, sh);
+  if (threadIdx.x == 0) moments[0] = t1;
+  const float t2 = block_sum256(m2, sh);
+  if (threadIdx.x == 0) moments[1] = t2;
+  __syncthreads();
+  const float mean = moments[0];
+  const float sd = sqrtf(fmaxf(moments[1] - mean * mean, min_scale * min_scale));
+  const float lo = mean - stddevs * sd, hi = mean + stddevs * sd;
+  const float step = n_out > 1 ? __fdiv_rn(1.0f, static_cast<float>(n_out - 1)) : 0.0f;
+  for (int64_t j = threadIdx.x; j < n_out; j += blockDim.x) {
+    const float z = j < n_out / 2 ? step * static_cast<float>(j) : 1.0f - step * static_cast<float>(n_out - 1 - j);
+    const float x = lo + (hi - lo) * z;
+    float acc = 0.0f;
+    for (int64_t s = 0; s < n_particles; ++s) {
+      const float sg = sigma_of(s);
+      const float zn = __fdiv_rn(x - __ldg(ls + 2 * s), sg);
+      acc = fmaf(__ldg(wb + s), __fdiv_rn(expf(-0.5f * zn * zn), 2.5066282746310002f * sg), acc);
+    }
+    grid[b * n_out + j] = x;
+    pdf[b * n_out + j] = acc;
+  }
+}
+
 // gaussian_exact grid (vbn/inference/gaussian_exact.py:166-183): per query b with Normal(loc_b, scale_b)
 //   z_s = linspace(-k, k, S)[s];  samples[b,s] = loc_b + scale_b * z_s;
 //   pdf[b,s] = exp(-0.5 * (z_s^2 + 2 ln scale_b + ln 2 pi))

@@ -970,6 +970,25 @@ __device__ __forceinline__ void op_params(Ctx<RPT, NT, TC>& c, const VbnOp& op) 
           put(K + K * D + k * D + d, j, softplus20(c.scr(K + k * 2 * D + D + d, j)) + min_scale);
         }
     }
+  } else if (op.kind == VBN_OP_TAB) {  // exp(logp[cfg][:]) of the row's parent configuration
+    const int C = op.k;
+    const int n_cfg = static_cast<int>(__ldg(P + 1)), cpad = static_cast<int>(__ldg(P + 2));
+    const float* pinfo = P + 4;
+    const float* logp = pinfo + (4 + cpad) * Dp + 2 * cpad + n_cfg * C;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      int cfg = 0;
+      for (int p = 0; p < Dp; ++p) {
+        const float* pi = pinfo + (4 + cpad) * p;
+        const int card = static_cast<int>(__ldg(pi)), stride = static_cast<int>(__ldg(pi + 1));
+        const float v = c.slot(__ldg(par + p), j);
+        int ci = 0;
+        for (int q = 1; q < card; ++q)
+          if (v == __ldg(pi + 4 + q)) ci = q;
+        cfg += ci * stride;
+      }
+      for (int k = 0; k < C; ++k) put(k, j, expf(__ldg(logp + cfg * C + k)));
+    }
   } else if (op.kind == VBN_OP_SNN) {
     const int C = op.k;
     const float temperature = __ldg(P + 2);

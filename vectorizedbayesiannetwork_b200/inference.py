@@ -62,7 +62,7 @@ class _ScheduleRunner:
             if n in query.do:
                 r = Role(src="fixed_q", density=False)
             elif n in query.evidence:
-                if mode in ("lw", "is"):
+                if mode in ("lw", "is", "rb"):
                     r = Role(src="fixed_q", add_logw=True)
                 else:
                     r = Role(src="fixed_q", density=False)
@@ -71,6 +71,8 @@ class _ScheduleRunner:
                 r = Role(src="sample", shared=shared, inject=n in inject)
             if n == query.target or store_all:
                 r.store = True
+            if mode == "rb" and n == query.target:
+                r = Role(src="sample", store=True, out_params=True)
             roles[n] = r
         if mode in ("mcm", "mcm_fast"):
             t = roles[query.target]
@@ -116,7 +118,7 @@ class _ScheduleRunner:
             s, s_off = shard.local_samples(s)
         with torch.cuda.device(dev):
             fixed = self.fixed_table(plan, query, b, clamp_obs=clamp_obs, shard=shard)
-            stores = {n: torch.empty(b, s, prog.dims[n], device=dev, dtype=torch.float32) for n in prog.stores}
+            stores = {n: torch.empty(b, s, prog.store_widths[n], device=dev, dtype=torch.float32) for n in prog.stores}
             logw = torch.empty(b, s, device=dev, dtype=torch.float32) if prog.needs_logw else None
             logp = torch.empty(b, s, device=dev, dtype=torch.float32) if prog.needs_logp else None
             flag = torch.zeros(1, device=dev, dtype=torch.int32)
@@ -391,6 +393,103 @@ class ResampledImportanceSampling:
                     v = shard.slice_queries(v)
                 samples = v.unsqueeze(1).expand(b, s, -1)
         return w, samples
+
+
+@register_inference("rao_blackwellized_marginalization")
+class RaoBlackwellizedMarginalization(object):
+    """vbn/inference/rao_blackwellized_marginalization.py:15-324: draw the non-descendants
+    of the target with likelihood weighting, then mix the target's conditional analytically over the
+    particles.  One fused launch draws the particles AND reads out the target's parameters per particle
+    (VBN_F_OUT_PARAMS); the mixture (categorical marginal / Gaussian mixture on a grid) is one more kernel."""
+
+    def __init__(self, n_samples: int = 200, n_particles: Optional[int] = None, stddevs: float = 4.0,
+                 min_scale: float = 1e-6, fallback: str = "likelihood_weighting", **kwargs) -> None:
+        self.n_samples = int(n_samples)
+        self.n_particles = int(n_particles) if n_particles is not None else self.n_samples
+        self.stddevs = float(stddevs)
+        self.min_scale = float(min_scale)
+        self._runner = _ScheduleRunner()
+        self._cache = self._runner._cache
+        self._last_fallback = False
+        self._last_reason = None
+        self.fallback = str(fallback).strip().lower() if fallback is not None else "none"
+        self._fallback = None
+        if self.fallback != "none":
+            from .core import INFERENCE_REGISTRY
+
+            if self.fallback not in INFERENCE_REGISTRY:
+                raise ValueError(f"Unknown fallback inference '{fallback}'. Available: {list(INFERENCE_REGISTRY.keys())}")
+            if self.fallback == "rao_blackwellized_marginalization":
+                raise ValueError("fallback cannot be 'rao_blackwellized_marginalization'")
+            fk = dict(kwargs)
+            fk.setdefault("n_samples", self.n_samples)
+            self._fallback = INFERENCE_REGISTRY[self.fallback](**fk)
+
+    def _fallback_infer(self, vbn, query, *, reason: str, **kwargs):
+        self._last_fallback = True
+        self._last_reason = reason
+        if self._fallback is None:
+            raise RuntimeError("rao_blackwellized_marginalization cannot handle this query and has no fallback")
+        if kwargs.get("noise") is not None:  # injected draws: {"rb": particle pass, "lw": fallback pass}
+            kwargs = dict(kwargs, noise=kwargs["noise"].get("lw"))
+        return self._fallback.infer_posterior(vbn, query, **kwargs)
+
+    def infer_posterior(self, vbn, query: Query, **kwargs):
+        from . import _lib as L
+
+        self._last_fallback, self._last_reason = False, None
+        n_samples = max(1, int(kwargs.get("n_samples", self.n_samples)))
+        n_particles = max(1, int(kwargs.get("n_particles", self.n_particles)))
+        dev = _check_model(vbn)
+        b = infer_batch_size(query.evidence, query.do)
+        topo, parents = _topology(vbn)
+        target = query.target
+        children: Dict[str, list] = {n: [] for n in topo}
+        for n in topo:
+            for p in parents[n]:
+                children[p].append(n)
+        desc, stack = set(), [target]
+        while stack:
+            for ch in children[stack.pop()]:
+                if ch not in desc:
+                    desc.add(ch)
+                    stack.append(ch)
+        fixed = set(query.evidence) | set(query.do)
+        if desc & fixed:
+            return self._fallback_infer(vbn, query, reason="target has observed/intervened descendants", **kwargs)
+        if target in fixed:
+            v = query.do[target] if target in query.do else clamp_evidence(query.evidence[target])
+            v = v.to(device=dev, dtype=torch.float32)
+            return torch.ones(b, 1, device=dev), v.unsqueeze(1).expand(b, 1, -1)
+        cpds = model_cpds(vbn)
+        tc = cpds[target]
+        categorical = tc.kind in ("softmax_nn", "categorical_table") and tc.output_dim == 1
+        gaussian = tc.kind in ("linear_gaussian", "gaussian_nn") and tc.output_dim == 1
+        if not (categorical or gaussian):
+            return self._fallback_infer(vbn, query, reason="unsupported target CPD for RB marginalization", **kwargs)
+        only = [n for n in topo if n not in desc]
+        out = self._runner.forward(vbn, query, n_particles, "rb", noise=(kwargs.get("noise") or {}).get("rb"),
+                                   seed=kwargs.get("seed"),
+                                   clamp_obs=True, only=only)
+        _raise_if_flagged(vbn, out)
+        w, _, _ = _weights(out)
+        params = out["stores"][target]  # [B, S, width] parameter read-out of the target per particle
+        lib = L.load()
+        with torch.cuda.device(dev):
+            sp = E._stream_ptr(dev)
+            if categorical:
+                k = int(tc.n_classes)
+                marginal = torch.empty(b, k, device=dev, dtype=torch.float32)
+                L.check(lib.vbn_weighted_sum(w.data_ptr(), params.data_ptr(), b, n_particles, k, marginal.data_ptr(), sp))
+                L.count_launch(1)
+                support = tc._sample_values[0].to(device=dev, dtype=torch.float32)
+                return marginal, support.view(1, -1, 1).expand(b, -1, 1)
+            pdf = torch.empty(b, n_samples, device=dev, dtype=torch.float32)
+            grid = torch.empty(b, n_samples, 1, device=dev, dtype=torch.float32)
+            L.check(lib.vbn_gaussian_mixture_grid(w.data_ptr(), params.data_ptr(), b, n_particles, n_samples,
+                                                  self.stddevs, self.min_scale, pdf.data_ptr(), grid.data_ptr(), sp))
+            L.count_launch(1)
+        return pdf, grid
 
 
 def _exact_setup(vbn, query: Query):

@@ -5,7 +5,8 @@ The registry decorator refuses duplicate keys (registry.py:18-20), hence plain d
 from __future__ import annotations
 
 from .inference import (AncestralSampler, CategoricalExact, GaussianExact, ImportanceSampling,
-                        LikelihoodWeighting, MonteCarloMarginalization, ResampledImportanceSampling)
+                        LikelihoodWeighting, MonteCarloMarginalization, RaoBlackwellizedMarginalization,
+                        ResampledImportanceSampling)
 
 _ORIGINAL = {}
 
@@ -18,7 +19,8 @@ def install(vbn_module=None) -> None:
                      ("importance_sampling", ImportanceSampling),
                      ("monte_carlo_marginalization", MonteCarloMarginalization),
                      ("gaussian_exact", GaussianExact), ("categorical_exact", CategoricalExact),
-                     ("resampled_importance_sampling", ResampledImportanceSampling)):
+                     ("resampled_importance_sampling", ResampledImportanceSampling),
+                     ("rao_blackwellized_marginalization", RaoBlackwellizedMarginalization)):
         _ORIGINAL.setdefault(("inference", key), reg.INFERENCE_REGISTRY.get(key))
         reg.INFERENCE_REGISTRY[key] = cls
     _ORIGINAL.setdefault(("sampling", "ancestral"), reg.SAMPLING_REGISTRY.get("ancestral"))

@@ -52,6 +52,7 @@ class Program:
     dims: Dict[str, int] = field(default_factory=dict)
     tc: bool = False                       # ops carry tensor-core MLP images -> tcgen05 kernel
     tc_list: Optional[np.ndarray] = None   # [n_tc, 2] int32 {image float offset, image bytes}, op order
+    store_widths: Dict[str, int] = field(default_factory=dict)  # floats per row of each store (dims, or read-out width)
 
 
 def tensor_cores_enabled() -> bool:
@@ -285,6 +286,7 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
         needs_logw=needs_logw,
         needs_logp=needs_logp,
         dims=dims,
+        store_widths={n: (int(cpds[n].param_width()) if roles[n].out_params else dims[n]) for n in stores},
         tc=any_tc,
         tc_list=np.asarray(tc_list, dtype=np.int32).reshape(-1, 2) if any_tc else None,
     )
