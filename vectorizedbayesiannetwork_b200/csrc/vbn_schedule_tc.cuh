@@ -171,6 +171,28 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
   hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
+// Two activations at once with packed fp32x2 arithmetic: c = p * 2^13 (exact), t = fl(p + c) rounds
+// p's low 13 bits away (round to nearest), hi = t - c (exact) is p with 11 significant bits -- a tf32
+// value -- and lo = p - hi exactly.  4 packed instructions per PAIR instead of 3 scalar ones per
+// element.  Written so that an FMA contraction of any mul+add pair cannot change a value (the classic
+// Veltkamp form t = p*(2^13+1); hi = t - (t - p) was contracted by ptxas and lost the split).
+__device__ __forceinline__ void split_tf32_x2(float a, float b, uint32_t& hi_a, uint32_t& hi_b, uint32_t& lo_a,
+                                              uint32_t& lo_b) {
+  unsigned long long p, c, t, hi, lo;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(a), "f"(b));
+  asm("{\n\t"
+      ".reg .b64 k;\n\t"
+      "mov.b64 k, {%5, %5};\n\t"
+      "mul.rn.f32x2 %0, %4, k;\n\t"
+      "add.rn.f32x2 %1, %4, %0;\n\t"
+      "sub.rn.f32x2 %2, %1, %0;\n\t"
+      "sub.rn.f32x2 %3, %4, %2;\n\t"
+      "}"
+      : "=&l"(c), "=&l"(t), "=&l"(hi), "=&l"(lo)
+      : "l"(p), "f"(8192.0f));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(hi_a), "=r"(hi_b) : "l"(hi));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo_a), "=r"(lo_b) : "l"(lo));
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -292,7 +314,9 @@ struct TcMlp {
       tmem_wait_ld();
       if (act == VBN_ACT_RELU) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) split_tf32(fmaxf(__uint_as_float(v[q]), 0.0f), hi[q], lo[q]);
+        for (int q = 0; q < 16; q += 2)
+          split_tf32_x2(fmaxf(__uint_as_float(v[q]), 0.0f), fmaxf(__uint_as_float(v[q + 1]), 0.0f), hi[q],
+                        hi[q + 1], lo[q], lo[q + 1]);
       } else {
 #pragma unroll
         for (int q = 0; q < 16; ++q) split_tf32(activate_slow(__uint_as_float(v[q]), act), hi[q], lo[q]);
