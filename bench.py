@@ -300,7 +300,10 @@ def run_kde(args, rank: int, local_rank: int, world: int) -> None:
         "roofline": {"bound": "mufu", "achieved": round(2 * pairs_per_s / 1e12, 4), "peak": round(mufu_peak / 1e12, 4),
                      "unit": "Tex2/s", "frac": round(2 * pairs_per_s / mufu_peak, 4), "traffic": None,
                      "peak_source": "16 MUFU/clk/SM x SMs x median SM clock during the run (SURVEY 8d: KDE is "
-                                    "exp-limited at small dims; 2 ex2 per (row, point) pair)",
+                                    "exp-limited at small dims; 2 exp2 per (row, point) pair)",
+                     "note": "achieved counts every exponential the algorithm needs; the kernel evaluates 1 in 4 of "
+                             "them with a degree-5 polynomial on the FMA pipe (FlashAttention-4 style), so the "
+                             "fraction of the MUFU-only ceiling can exceed 1",
                      "kernel": "vbn::kde_log_prob_kernel<1,1>"},
         "cpu_baseline": cpu,
     }

@@ -13,6 +13,8 @@
 #pragma once
 #include <cuda_pipeline.h>
 
+#include <cstdlib>
+
 #include "vbn_device.cuh"
 
 namespace vbn {
@@ -58,6 +60,34 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return r;
 }
 
+// exp2 of a packed pair on the FMA pipe instead of the MUFU (the FlashAttention-4 trick): the kernel is
+// bound by 16 MUFU lanes/clk/SM while the FMA pipe has issue slots to spare, so a fraction of the
+// exponentials is evaluated as 2^round(x) * p(x - round(x)) with a degree-5 polynomial on [-0.5, 0.5]
+// (max relative error 2.4e-7, the same 2 ulp as ex2.approx).  Arguments are <= 0; they are clamped at
+// -126 so the exponent arithmetic cannot wrap (such terms are ~1e-38, i.e. zero for every sum the fast
+// pass accepts).  12 instructions per pair of values.
+__device__ __forceinline__ f32x2 ex2_poly2(f32x2 x) {
+  float a, b;
+  unpack2(x, a, b);
+  const f32x2 xc = pack2(fmaxf(a, -126.0f), fmaxf(b, -126.0f));
+  const f32x2 magic = pack2(12582912.0f, 12582912.0f);  // 1.5 * 2^23: adding it rounds to an integer
+  const f32x2 t = add2(xc, magic);
+  const f32x2 f = sub2(xc, sub2(t, magic));
+  f32x2 p = pack2(0.0013390863314270973f, 0.0013390863314270973f);
+  p = fma2(p, f, pack2(0.009676031768321991f, 0.009676031768321991f));
+  p = fma2(p, f, pack2(0.055503569543361664f, 0.055503569543361664f));
+  p = fma2(p, f, pack2(0.2402210682630539f, 0.2402210682630539f));
+  p = fma2(p, f, pack2(0.6931471824645996f, 0.6931471824645996f));
+  p = fma2(p, f, pack2(1.0000001192092896f, 1.0000001192092896f));
+  float pa, pb, ta, tb;
+  unpack2(p, pa, pb);
+  unpack2(t, ta, tb);
+  // the low mantissa bits of t hold round(x): shifted into the exponent field they scale p by 2^round(x)
+  const float ra = __int_as_float(__float_as_int(pa) + (__float_as_int(ta) << 23));
+  const float rb = __int_as_float(__float_as_int(pb) + (__float_as_int(tb) << 23));
+  return pack2(ra, rb);
+}
+
 // One online (max, sum) accumulator, two-level: `cur` (packed pair) collects the current tile,
 // `tot` the finished tiles, so the fp32 error grows with sqrt(tile) + sqrt(#tiles) instead of
 // sqrt(N) (200 000 sequential adds cost ~3e-5 relative, which fails the 1e-5 parity).
@@ -101,6 +131,8 @@ struct KdeAcc {
 // can be taken with a fixed shift m = 0 -- no running max, no rescale -- as long as the nearest
 // stored point keeps the sum above the fp32 underflow range.  Rows whose sums fall below 2^-100
 // (queries ~12 kernel widths away from every stored point) make the CTA redo the pass with KdeAcc.
+// NPOLY of the two packed pairs of every push go through ex2_poly2, the rest through the MUFU.
+template <int NPOLY>
 struct KdeFastAcc {
   float tot;
   f32x2 cur;
@@ -112,8 +144,8 @@ struct KdeFastAcc {
     float a, b, c, d;
     unpack2(v0, a, b);
     unpack2(v1, c, d);
-    cur = add2(cur, pack2(ex2_approx(a), ex2_approx(b)));
-    cur = add2(cur, pack2(ex2_approx(c), ex2_approx(d)));
+    cur = add2(cur, NPOLY >= 2 ? ex2_poly2(v0) : pack2(ex2_approx(a), ex2_approx(b)));
+    cur = add2(cur, NPOLY >= 1 ? ex2_poly2(v1) : pack2(ex2_approx(c), ex2_approx(d)));
   }
   __device__ __forceinline__ void end_tile() {
     float a, b;
@@ -128,13 +160,13 @@ struct KdeFastAcc {
 // Shared-memory tile layout: dimension-major, [d][kKdeTile] floats, so a float2 load fetches the
 // same coordinate of two consecutive points (the two lanes of the packed math).  Tile tails are
 // filled with +inf parents / targets: their terms are exp2(-inf) = 0.
-template <int DP, int DX, class Acc>
+template <int DP, int DX, class Acc, class AccD>
 __device__ __forceinline__ void kde_pass(const float* __restrict__ tp, const float* __restrict__ ty,
                                          int64_t n_points, float (*s_p)[(DP > 0 ? DP : 1) * kKdeTile],
                                          float (*s_y)[DX * kKdeTile],
                                          const f32x2 (&xp)[kKdeQpt][DP > 0 ? DP : 1],
                                          const f32x2 (&xy)[kKdeQpt][DX], float hp2, float hy2,
-                                         Acc (&den)[kKdeQpt], Acc (&num)[kKdeQpt]) {
+                                         AccD (&den)[kKdeQpt], Acc (&num)[kKdeQpt]) {
   constexpr int DPS = DP > 0 ? DP : 1;
 #pragma unroll
   for (int j = 0; j < kKdeQpt; ++j) {
@@ -223,7 +255,9 @@ __device__ __forceinline__ void kde_pass(const float* __restrict__ tp, const flo
   }
 }
 
-template <int DP, int DX>
+// PN / PD: how many of the two value pairs per push the numerator / denominator accumulators evaluate
+// with the polynomial (0..2 each): (PN + PD) / 4 of all exponentials leave the MUFU.
+template <int DP, int DX, int PN, int PD>
 __global__ void __launch_bounds__(kKdeThreads) kde_log_prob_kernel(
     const float* __restrict__ tp, const float* __restrict__ ty, int64_t n_points,
     const float* __restrict__ qp, const float* __restrict__ qx, int64_t n_rows,
@@ -254,7 +288,8 @@ __global__ void __launch_bounds__(kKdeThreads) kde_log_prob_kernel(
   float res[kKdeQpt];
   bool redo = false;
   {
-    KdeFastAcc den[kKdeQpt], num[kKdeQpt];
+    KdeFastAcc<PD> den[kKdeQpt];
+    KdeFastAcc<PN> num[kKdeQpt];
     kde_pass<DP, DX>(tp, ty, n_points, s_p, s_y, xp, xy, hp2, hy2, den, num);
 #pragma unroll
     for (int j = 0; j < kKdeQpt; ++j) {
@@ -322,10 +357,19 @@ inline cudaError_t launch_kde_log_prob(const float* tp, const float* ty, int64_t
   const float log_n = static_cast<float>(log(static_cast<double>(n_points)));
   const int64_t per_cta = static_cast<int64_t>(kKdeThreads) * kKdeQpt;
   const unsigned grid = static_cast<unsigned>((n_rows + per_cta - 1) / per_cta);
+  // fraction of exponentials moved to the FMA pipe; VBN_KDE_POLY=0..4 overrides (dev knob)
+  const char* env = std::getenv("VBN_KDE_POLY");
+  const int poly = env ? std::atoi(env) : 1;
+#define VBN_KDE_LAUNCH(DP_, DX_, PN_, PD_)                                                      \
+  kde_log_prob_kernel<DP_, DX_, PN_, PD_><<<grid, kKdeThreads, 0, stream>>>(                    \
+      tp, ty, n_points, qp, qx, n_rows, hp2, hy2, const_y, log_n, out)
 #define VBN_KDE_CASE(DP_, DX_)                                                                  \
   if (dp == DP_ && dx == DX_) {                                                                 \
-    kde_log_prob_kernel<DP_, DX_><<<grid, kKdeThreads, 0, stream>>>(                            \
-        tp, ty, n_points, qp, qx, n_rows, hp2, hy2, const_y, log_n, out);                       \
+    if (poly <= 0) VBN_KDE_LAUNCH(DP_, DX_, 0, 0);                                              \
+    else if (poly == 1 || DP_ == 0) VBN_KDE_LAUNCH(DP_, DX_, 1, 0);                             \
+    else if (poly == 2) VBN_KDE_LAUNCH(DP_, DX_, 1, 1);                                         \
+    else if (poly == 3) VBN_KDE_LAUNCH(DP_, DX_, 2, 1);                                         \
+    else VBN_KDE_LAUNCH(DP_, DX_, 2, 2);                                                        \
     return cudaGetLastError();                                                                  \
   }
   VBN_KDE_CASE(0, 1)
@@ -335,6 +379,7 @@ inline cudaError_t launch_kde_log_prob(const float* tp, const float* ty, int64_t
   VBN_KDE_CASE(1, 2)
   VBN_KDE_CASE(2, 2)
 #undef VBN_KDE_CASE
+#undef VBN_KDE_LAUNCH
   const unsigned g2 = static_cast<unsigned>((n_rows + 127) / 128);
   kde_log_prob_generic_kernel<<<g2, 128, 0, stream>>>(tp, ty, n_points, dp, dx, qp, qx, n_rows, hp,
                                                       hy, const_y, log_n, out);
