@@ -286,6 +286,14 @@ def run_kde(args, rank: int, local_rank: int, world: int) -> None:
     cpu = None
     if not args.no_cpu_baseline:
         cpu = kde_cpu_baseline(n_points)
+    traffic = None
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("cfg4")
+        if cap:
+            traffic = {"bytes_per_launch": round(cap["dram_bytes"] * rows_rank / cap["rows"]),
+                       "source": f"ncu --set full capture at {cap['rows']} rows ({cap['file']}), scaled by rows"}
+    except Exception:
+        pass
     line = {
         "metric": "density_rows_per_sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -298,7 +306,7 @@ def run_kde(args, rank: int, local_rank: int, world: int) -> None:
                 "h2d_bytes_per_step": 8 * rows_rank, "d2h_bytes_per_step": 4 * rows_rank},
         "gpu_launches": launches, "clocks": clock_info,
         "roofline": {"bound": "mufu", "achieved": round(2 * pairs_per_s / 1e12, 4), "peak": round(mufu_peak / 1e12, 4),
-                     "unit": "Tex2/s", "frac": round(2 * pairs_per_s / mufu_peak, 4), "traffic": None,
+                     "unit": "Tex2/s", "frac": round(2 * pairs_per_s / mufu_peak, 4), "traffic": traffic,
                      "peak_source": "16 MUFU/clk/SM x SMs x median SM clock during the run (SURVEY 8d: KDE is "
                                     "exp-limited at small dims; 2 exp2 per (row, point) pair)",
                      "note": "achieved counts every exponential the algorithm needs; the kernel evaluates 1 in 4 of "

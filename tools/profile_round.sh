@@ -12,4 +12,7 @@ for w in cfg5 cfg2 cfg3 cfg4; do
   $CMD > /dev/null 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:${KREG[$w]} -s 3 -c 1 -o gpurun_out/${R}_prof_$w $CMD > gpurun_out/${R}_ncu_full_$w.log 2>&1
   tail -1 gpurun_out/${R}_ncu_full_$w.log
+  # gpurun brings back at most 64 MiB: keep the raw-metric export, drop the report (cfg5's is kept)
+  ncu -i gpurun_out/${R}_prof_$w.ncu-rep --page raw --csv > gpurun_out/${R}_prof_$w.raw.csv 2>/dev/null
+  if [ "$w" != "cfg5" ]; then rm -f gpurun_out/${R}_prof_$w.ncu-rep; fi
 done

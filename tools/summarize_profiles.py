@@ -56,9 +56,9 @@ for w in ("cfg5", "cfg2", "cfg3", "cfg4"):
             for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
                 lines.append(f"{t / tot * 100:6.2f}%  {t:10.3f} ms  x{n:<4d} {k}")
     # ---- full capture ------------------------------------------------------------------------
-    rp = os.path.join(GP, f"{R}_prof_{w}.ncu-rep")
+    rp = os.path.join(GP, f"{R}_prof_{w}.raw.csv")  # `ncu -i <rep> --page raw --csv`, exported on the GPU box
     if os.path.exists(rp):
-        raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        raw = open(rp).read()
         rows = list(csv.reader(raw.splitlines()))
         if len(rows) > 2:
             hdr, units, vals = rows[0], rows[1], rows[2]
