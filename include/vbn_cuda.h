@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define VBN_CUDA_ABI_VERSION 3
+#define VBN_CUDA_ABI_VERSION 4
 
 /* error codes */
 #define VBN_OK 0
@@ -65,6 +65,14 @@ extern "C" {
                                   tail in the tcgen05 kernel; ignored by the FP32-pipe kernel   */
 #define VBN_F_OUT_PARAMS 0x400  /* write the conditional-distribution parameters of every row to
                                   stores[store_idx] instead of drawing (CPDHandle.conditional)  */
+#define VBN_F_MDNROOT 0x800    /* MDN op without parents (mdn.py:190-196 root parameters), D = 1,
+                                  2 <= K <= 4, that is only drawn (Philox, per-row stream, no store,
+                                  no density).  Its mixture is the same for every row, so the plan
+                                  compiler evaluates it once: layer_dim[0..7], aux[0..3] hold the
+                                  float bits of {cumulative weights c_0..c_{K-2} of the clamped,
+                                  renormalised pi (mdn.py:227-228); then (loc_k, scale_k) for
+                                  k = 0..K-1, scale_k = softplus(raw_k) + min_scale}; tc[] =
+                                  {out_slot, n_off, u_off, K}.  The kernel reads quads 0,4,5,6,7  */
 #define VBN_F_LGPLAIN 0x80     /* LGFAST op that is only drawn: Philox, per-row stream, no store,
                                   no density -- the kernel reads nothing but quads 0,4,5,6      */
 

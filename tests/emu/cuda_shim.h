@@ -42,6 +42,7 @@ inline float __logf(float x) { return std::log(x); }
 inline float __expf(float x) { return std::exp(x); }
 inline void __sincosf(float x, float* s, float* c) { *s = std::sin(x); *c = std::cos(x); }
 inline float __fdiv_rn(float a, float b) { return a / b; }
+inline float __fdividef(float a, float b) { return a / b; }
 inline float fmaf_(float a, float b, float c) { return std::fma(a, b, c); }
 inline int atomicOr(int32_t* p, int v) { int o = *p; *p |= v; return o; }
 using std::min;

@@ -356,6 +356,31 @@ def test_discrete_tables_reproduce_the_mlp_path(backend, monkeypatch):
     assert ok > 0.995, ok
 
 
+# ---- parent-less MDN nodes precomputed by the plan compiler (VBN_F_MDNROOT) vs the per-row path ----
+def test_root_mdn_fast_path_reproduces_the_generic_path(backend, monkeypatch):
+    """mdn.py:190-196, 227-235: the root mixture is row-independent; with the same Philox seed the
+    op-embedded mixture must draw what the per-row evaluation draws."""
+    from vectorizedbayesiannetwork_b200 import _lib as L
+
+    spec = S.random_dag_lg_mdn(40, seed=5)
+    assert any(spec["cpds"][n]["kind"] == "mdn" and not spec["parents"][n] for n in spec["nodes"])
+    g = torch.Generator().manual_seed(2)
+    ev = {n: 0.3 * torch.randn(3, 1, generator=g) for n in spec["nodes"][-2:]}
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("VBN_MDNROOT", flag)
+        model = V.VBN.from_spec(spec, device=backend.device)
+        model.set_inference_method("importance_sampling", n_samples=700, ess_threshold=0.0)
+        w, s = model.infer_posterior({"target": "n20", "evidence": ev}, seed=9)
+        ops = next(iter(model._inference._runner._cache.values())).program.ops
+        out[flag] = (w.cpu(), s.cpu(), sum(1 for op in ops if int(op["flags"]) & L.F_MDNROOT))
+    assert out["0"][2] == 0 and out["1"][2] > 0
+    close = ((out["0"][1] - out["1"][1]).abs() <= 1e-6 + 1e-5 * out["0"][1].abs()).float().mean().item()
+    assert close > 0.995, close  # a pick can flip only when u sits within rounding of a CDF edge
+    ok = ((out["0"][0] - out["1"][0]).abs() <= 1e-7 + 1e-3 * out["0"][0].abs()).float().mean().item()
+    assert ok > 0.99, ok
+
+
 # ---- CPDHandle.conditional formats (vbn/core/cpd_handle.py:40-118, 348-402; tests/test_cpd_handle.py:61-88)
 def test_conditional_formats_match_the_parameter_heads(backend):
     import os

@@ -518,6 +518,52 @@ __device__ __forceinline__ void op_lg_plain(Ctx<RPT, NT, TC>& c, const VbnOp& op
   for (int j = 0; j < RPT; ++j) c.slot(op.aux[2], j) = fmaf(lane4(c.rows.ncache[j], lane), sc, loc[j] + b);
 }
 
+// VBN_F_MDNROOT: a parent-less MDN node (D = 1, K <= 4) that is simply drawn.  The mixture is the
+// same for every row, so the plan compiler has already evaluated pi = softmax(logits).clamp_min(1e-5)
+// / sum and scale_k = softplus(raw_k) + min_scale (mdn.py:190-196, 227-235); the op carries the
+// cumulative weights and the (loc, scale) pairs.  k ~ Categorical(pi) by inverse CDF on one uniform.
+template <int K, int RPT, int NT, class TC>
+__device__ __forceinline__ void mdn_root_k(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
+  float f[12];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = __int_as_float(op.layer_dim[i]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) f[8 + i] = __int_as_float(op.aux[i]);
+  const int out_slot = op.tc[0], n_off = op.tc[1], u_off = op.tc[2];
+  const int uq = u_off >> 2, ul = u_off & 3;
+  if (uq != c.rows.cur_uq) {
+    c.rows.cur_uq = uq;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) c.rows.ucache[j] = c.uniforms(j, uq, 1u, false);
+  }
+  const int nq = n_off >> 2, nl = n_off & 3;
+  if (nq != c.rows.cur_nq) {
+    c.rows.cur_nq = nq;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) c.rows.ncache[j] = c.normals(j, nq, 0u, false);
+  }
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    const float u = lane4(c.rows.ucache[j], ul);
+    float loc = f[K - 1 + 2 * (K - 1)], sc = f[K - 1 + 2 * (K - 1) + 1];
+#pragma unroll
+    for (int k = K - 2; k >= 0; --k)
+      if (u < f[k]) {
+        loc = f[K - 1 + 2 * k];
+        sc = f[K - 1 + 2 * k + 1];
+      }
+    c.slot(out_slot, j) = fmaf(lane4(c.rows.ncache[j], nl), sc, loc);
+  }
+}
+template <int RPT, int NT, class TC>
+__device__ __forceinline__ void op_mdn_root(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
+  switch (op.tc[3]) {
+    case 2: mdn_root_k<2>(c, op); break;
+    case 3: mdn_root_k<3>(c, op); break;
+    default: mdn_root_k<4>(c, op); break;
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // VBN_OP_GNN: gaussian_nn.py:215-288.
 // params: mean_x[Dp], std_x[Dp], mean_y[D], std_y[D], min_scale, pad4 ; then MLP block
@@ -1138,16 +1184,50 @@ __device__ __forceinline__ void run_ops(Ctx<RPT, NT, TC>& c) {
     VbnOp op;  // only the 16-byte quads this op kind reads are fetched (layer_dim: via c.gop)
     {
       const int4* src = reinterpret_cast<const int4*>(a.ops + i);
-      int4* dst = reinterpret_cast<int4*>(&op);
-      dst[0] = __ldg(src + 0);  // kind, flags, dim, n_par
-      if (op.flags & VBN_F_LGPLAIN) {
-        dst[4] = __ldg(src + 4);  // bias, scale, 2 ln scale, var
-        dst[5] = __ldg(src + 5);  // w0..w3
-        dst[6] = __ldg(src + 6);  // packed parent slots, out_slot, n_off
+      const int4 q0 = __ldg(src + 0);  // kind, flags, dim, n_par
+      // The plain ops get their own descriptor object: `op` below is indexed dynamically by the generic
+      // paths and therefore lives in local memory, which would cost the hot ops a store per quad.
+      if (q0.y & VBN_F_LGPLAIN) {
+        VbnOp lop;
+        int4* ld = reinterpret_cast<int4*>(&lop);
+        ld[0] = q0;
+        ld[4] = __ldg(src + 4);  // bias, scale, 2 ln scale, var
+        ld[5] = __ldg(src + 5);  // w0..w3
+        ld[6] = __ldg(src + 6);  // packed parent slots, out_slot, n_off
         c.gop = a.ops + i;
-        op_lg_plain(c, op);
+        op_lg_plain(c, lop);
         continue;
       }
+      if (HEAVY && (q0.y & VBN_F_MDNROOT)) {
+        VbnOp lop;
+        int4* ld = reinterpret_cast<int4*>(&lop);
+        ld[0] = q0;
+        ld[4] = __ldg(src + 4);  // cumulative weights, (loc, scale) pairs ...
+        ld[5] = __ldg(src + 5);
+        ld[6] = __ldg(src + 6);
+        ld[7] = __ldg(src + 7);  // out_slot, n_off, u_off, K
+        c.gop = a.ops + i;
+        op_mdn_root(c, lop);
+        continue;
+      }
+      if constexpr (TC::kEnabled) {
+        if (q0.y & VBN_F_MDNPLAIN) {  // drawn-only MDN node with a tensor-core MLP
+          VbnOp lop;
+          int4* ld = reinterpret_cast<int4*>(&lop);
+          ld[0] = q0;
+          ld[1] = __ldg(src + 1);  // out_slot
+          ld[2] = __ldg(src + 2);  // n_off, u_off
+          ld[3] = __ldg(src + 3);  // act, k
+          ld[6] = __ldg(src + 6);  // min_scale, packed parent slots
+          ld[7] = __ldg(src + 7);  // tensor-core image: K1, N3
+          c.gop = a.ops + i;
+          c.tc.mdn_plain(c, lop);
+          store_value(c, lop);  // a plain node may still be the stored target
+          continue;
+        }
+      }
+      int4* dst = reinterpret_cast<int4*>(&op);
+      dst[0] = q0;
       dst[1] = __ldg(src + 1);  // out_slot, par_off, param_off, fixed_col
       dst[2] = __ldg(src + 2);  // store_idx, noise_idx, n_off, u_off
       if (op.kind == VBN_OP_LG) {

@@ -233,12 +233,16 @@ struct TcMlp {
   const unsigned char* wbuf_ptr;
   uint32_t full_bar, empty_bar, mma_bar;  // full/empty: arrays of nbuf; mma_bar: this warpgroup's
   uint32_t w_iter;     // tensor-core MLPs consumed so far (ring position)
+  uint32_t w_buf;      // w_iter % nbuf, and (w_iter / nbuf) & 1 in bit 8: kept as running state (nbuf
+                       // is a runtime value; the division pair cost ~37 instructions per MLP)
   uint32_t mma_phase;  // parity of the next completion of mma_bar
   int nbuf;
   int wg, warp_in_wg, lane;
   // weight-ring producer (warp 0 only)
   bool producer;
   uint32_t p_iter;     // weight images issued so far
+  uint32_t p_buf;      // p_iter % nbuf | (((p_iter / nbuf) & 1) ^ 1) << 8   (running, like w_buf)
+  uint32_t p_idx;      // p_iter % n_tc
   uint32_t p_total;    // images this CTA will consume in total (n_iter * n_tc)
   const int2* tc_list; // per tensor-core op: {float offset of its image in params, bytes}
   const float* params;
@@ -249,17 +253,19 @@ struct TcMlp {
   // w_iter - nbuf, which never depends on this warp).  One elected lane.
   __device__ __forceinline__ void produce() {
     while (p_iter < p_total && p_iter < w_iter + static_cast<uint32_t>(nbuf)) {
-      const uint32_t buf = p_iter % static_cast<uint32_t>(nbuf);
-      const uint32_t ph = ((p_iter / static_cast<uint32_t>(nbuf)) & 1u) ^ 1u;
+      const uint32_t buf = p_buf & 0xFFu;
+      const uint32_t ph = p_buf >> 8;
       if (p_iter > w_iter) {
         if (!mbar_test(empty_bar + 8 * buf, ph)) break;
       } else {
         mbar_wait(empty_bar + 8 * buf, ph);
       }
-      const int2 e = __ldg(tc_list + (p_iter % n_tc));
+      const int2 e = __ldg(tc_list + p_idx);
       mbar_expect_tx(full_bar + 8 * buf, static_cast<uint32_t>(e.y));
       bulk_g2s(wbuf + buf * kWbufBytes, params + e.x, static_cast<uint32_t>(e.y), full_bar + 8 * buf);
       ++p_iter;
+      p_idx = p_idx + 1u == n_tc ? 0u : p_idx + 1u;
+      p_buf = buf + 1u == static_cast<uint32_t>(nbuf) ? ((ph ^ 1u) << 8) : p_buf + 1u;
     }
   }
 
@@ -338,8 +344,8 @@ struct TcMlp {
       if (elect_one()) produce();
       __syncwarp();
     }
-    const uint32_t buf = w_iter % static_cast<uint32_t>(nbuf);
-    const uint32_t ph = (w_iter / static_cast<uint32_t>(nbuf)) & 1u;
+    const uint32_t buf = w_buf & 0xFFu;
+    const uint32_t ph = w_buf >> 8;
     const uint32_t w1hi = wbuf + buf * kWbufBytes;
     const uint32_t w1lo = w1hi + kHidden * k1 * 4;
     const uint32_t w2hi = w1lo + kHidden * k1 * 4;
@@ -395,6 +401,7 @@ struct TcMlp {
     __syncwarp();
     if (lane == 0) mbar_arrive(empty_bar + 8 * buf);
     ++w_iter;
+    w_buf = buf + 1u == static_cast<uint32_t>(nbuf) ? ((ph ^ 1u) << 8) : w_buf + 1u;
   }
 
   // Generic consumer: outputs land in scratch rows 0..n_out-1 like the FFMA paths
@@ -424,19 +431,19 @@ struct TcMlp {
     float se = 0.0f;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      q[k] = expf(__uint_as_float(v[k]) - mx);
+      q[k] = __expf(__uint_as_float(v[k]) - mx);  // only places the CDF edges: 2^-21 relative is plenty
       se += q[k];
     }
     // pi = softmax.clamp_min(1e-5) / sum (mdn.py:227-228); k ~ Categorical(pi) by inverse CDF on
-    // the un-normalised clamped weights with u scaled by their sum
-    const float inv = __frcp_rn(se);
+    // un-normalised weights: e_k / se >= 1e-5  <=>  e_k >= 1e-5 se, so the clamp is applied to e_k
+    // itself and u is scaled by the clamped total -- no division (se >= 1: the max term is 1)
+    const float floor_e = 1e-5f * se;
     float tot = 0.0f;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      q[k] = fmaxf(q[k] * inv, 1e-5f);
+      q[k] = fmaxf(q[k], floor_e);
       tot += q[k];
     }
-    tot = fmaxf(tot, 1e-12f);
     const int uq = op.u_off >> 2;
     if (uq != c.rows.cur_uq) {
       c.rows.cur_uq = uq;
@@ -460,7 +467,7 @@ struct TcMlp {
       c.rows.ncache[0] = c.normals(0, nq, 0u, false);
     }
     const float eps = lane4(c.rows.ncache[0], op.n_off & 3);
-    const float sc = softplus20(raw) + __int_as_float(op.aux[0]);
+    const float sc = softplus20_fast(raw) + __int_as_float(op.aux[0]);
     c.slot(op.out_slot, 0) = fmaf(eps, sc, loc);
   }
 
@@ -493,7 +500,12 @@ __global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const S
   const uint32_t empty_bar = full_bar + 8 * kMaxBufs;
   const uint32_t mma_bar0 = empty_bar + 8 * kMaxBufs;
   const uint32_t wbuf = smem_base + kCtrlBytes;
-  float* slots = reinterpret_cast<float*>(smem_raw + kCtrlBytes + static_cast<size_t>(nbuf) * kWbufBytes);
+  // Word offset of this thread's column in the slot area.  Made opaque to the optimiser: at 128
+  // registers per thread ptxas otherwise REMATERIALISES it (S2R tid, nbuf * kWbufBytes, ...) at the top
+  // of every op of the walk instead of keeping -- or spilling -- one register.
+  int slot_word = (kCtrlBytes + nbuf * kWbufBytes) / 4 + tid;
+  asm volatile("" : "+r"(slot_word));
+  float* slots = reinterpret_cast<float*>(smem_raw) + slot_word;
 
   if (tid == 0) {
     for (int i = 0; i < kMaxBufs; ++i) {
@@ -513,7 +525,7 @@ __global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const S
   const int64_t per_round = static_cast<int64_t>(gridDim.x) * NWG;
   const int64_t n_iter = (n_tiles + per_round - 1) / per_round;  // same for every warpgroup: the ring needs it
 
-  Ctx<1, kThreads, TcMlp> c(a, slots, tid);
+  Ctx<1, kThreads, TcMlp> c(a, slots, 0);  // the thread index is already folded into `slots`
   const int wg = warp >> 2;
   const uint32_t col = tmem_base + static_cast<uint32_t>(wg * kColsPerWg);
   const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
@@ -529,6 +541,7 @@ __global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const S
   c.tc.empty_bar = empty_bar;
   c.tc.mma_bar = mma_bar0 + 8 * wg;
   c.tc.w_iter = 0;
+  c.tc.w_buf = 0;
   c.tc.mma_phase = 0;
   c.tc.nbuf = nbuf;
   c.tc.wg = wg;
@@ -536,6 +549,8 @@ __global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const S
   c.tc.lane = lane;
   c.tc.producer = warp == 0;
   c.tc.p_iter = 0;
+  c.tc.p_buf = 1u << 8;
+  c.tc.p_idx = 0;
   c.tc.p_total = static_cast<uint32_t>(n_iter) * static_cast<uint32_t>(a.n_tc);
   c.tc.tc_list = a.tc_list;
   c.tc.params = a.params;
@@ -543,6 +558,9 @@ __global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const S
   for (int64_t it = 0; it < n_iter; ++it) {
     const int64_t tile = (it * gridDim.x + blockIdx.x) * NWG + wg;
     bind_row(c, 0, tile * kWgThreads + (tid & (kWgThreads - 1)));
+    // same reason as slot_word: keep the Philox counter words as values, not as a recipe (the row
+    // index -> (query, sample) division chain was being re-executed per op)
+    asm volatile("" : "+r"(c.rows.gs[0]), "+r"(c.rows.gb[0]));
     run_ops<true>(c);
   }
   tc_fence_before();

@@ -14,6 +14,8 @@ import os
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
+import torch
+import torch.nn.functional as F
 
 from . import _lib as L
 from .cpds import BaseCPD, Packed, pack_table, table_eligible
@@ -63,6 +65,11 @@ def tensor_cores_enabled() -> bool:
 def tables_enabled() -> bool:
     """VBN_TABLE=0 keeps discrete nodes on the per-row MLP path (A/B measurements); default on."""
     return os.environ.get("VBN_TABLE", "1") != "0"
+
+
+def _roots_enabled() -> bool:
+    """VBN_MDNROOT=0 keeps parent-less MDN nodes on the generic per-row path (A/B + equivalence test)."""
+    return os.environ.get("VBN_MDNROOT", "1") != "0"
 
 
 def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpds: Dict[str, BaseCPD],
@@ -251,6 +258,25 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
                             and r.src == "sample" and not r.shared and not r.inject
                             and not r.add_logw and not r.out_logp and not r.out_params):
                         flags |= L.F_MDNPLAIN
+            if (_roots_enabled() and pk.kind == L.OP_MDN and pk.n_par == 0 and d == 1 and 2 <= pk.k <= 4
+                    and r.src == "sample" and not r.shared and not r.inject and not r.store
+                    and not r.add_logw and not r.out_logp and not r.out_params):
+                # parent-less MDN that is only drawn: the mixture is row-independent, evaluate it here
+                # (mdn.py:190-196 root parameters, 227-235 clamp / renormalise / softplus)
+                cpd = cpds[n]
+                pi = torch.softmax(cpd._logits.detach().float().cpu(), dim=0).clamp_min(1e-5)
+                pi = pi / pi.sum().clamp_min(1e-12)
+                cum = torch.cumsum(pi, dim=0)[: pk.k - 1]
+                loc = cpd._loc.detach().float().cpu().reshape(pk.k)
+                sc = F.softplus(cpd._log_scale.detach().float().cpu().reshape(pk.k)) + float(cpd.min_scale)
+                emb = np.zeros(12, np.float32)
+                emb[: pk.k - 1] = cum.numpy()
+                emb[pk.k - 1 : pk.k - 1 + 2 * pk.k : 2] = loc.numpy()
+                emb[pk.k : pk.k + 2 * pk.k : 2] = sc.numpy()
+                op["layer_dim"][:] = emb[:8].view(np.int32)
+                op["aux"][:] = emb[8:].view(np.int32)
+                op["tc"][:] = [slot_of[n], int(op["n_off"]), int(op["u_off"]), pk.k]
+                flags |= L.F_MDNROOT
             if r.out_params:
                 flags |= L.F_OUT_PARAMS
                 heavy = True  # the read-out lives in the HEAVY kernels only
