@@ -265,6 +265,17 @@ int32_t vbn_posterior_stats(const float* pdf_dev, const float* samples_dev, int6
                             float* partials_dev, float* stats_dev, void* stream);
 
 /*
+ * Weighted class histogram of a discrete target -- replaces the benchmark adapter's Python double
+ * loop _estimate_discrete_posterior(_batch) (benchmarking/models/vbn.py:202-242) and _normalize_probs
+ * (:116-121): probs[b][c] = sum_s w[b,s] [round_half_even(x[b,s]) == c and w finite], divided by the
+ * row total; uniform 1/K when the total is not finite or <= 0.  Sample (b, s) is read at
+ * samples_dev[(b*S + s) * sample_stride] (stride D picks dim 0 of a [B,S,D] tensor, like the
+ * reference's samples[:, :, 0]).  1 <= n_classes <= 256.  probs_dev: [B][n_classes].
+ */
+int32_t vbn_weighted_histogram(const float* samples_dev, const float* w_dev, int64_t n_queries, int64_t n_samples,
+                               int64_t sample_stride, int32_t n_classes, float* probs_dev, void* stream);
+
+/*
  * KDE conditional log-density over M query rows against N stored points
  * (vbn/cpds/kde.py:111-149): out[m] = LSE_n(log_kp + log_ky) - LSE_n(log_kp)
  * (root, dp == 0: LSE_n(log_ky) - ln N).  Stored points / queries are row-major

@@ -1189,6 +1189,83 @@ def monte_carlo_marginalization(spec, query, n_samples: int, noise=None):
 # --------------------------------------------------------------------------------------
 
 
+# ---------------------------------------------------------------------------------------------
+# Posterior summaries of the benchmark adapter, restated with numpy float64 like
+# the reference (benchmarking/models/vbn.py).
+# ---------------------------------------------------------------------------------------------
+def normalize_probs(hist):
+    """benchmarking/models/vbn.py:116-121."""
+    import numpy as np
+
+    arr = np.asarray(list(hist), dtype=float)
+    total = float(arr.sum())
+    if not math.isfinite(total) or total <= 0:
+        return (np.ones_like(arr) / len(arr)).tolist()
+    return (arr / total).tolist()
+
+
+def estimate_discrete_posterior_batch(samples: torch.Tensor, weights: torch.Tensor, k: int):
+    """benchmarking/models/vbn.py:202-242: per query, hist[round(x)] += w over finite weights with the
+    class in range; Python round() is round-half-to-even (= numpy rint); float64 accumulation."""
+    import numpy as np
+
+    if samples.dim() == 3:
+        samples = samples[:, :, 0]
+    if samples.dim() != 2:
+        raise ValueError(f"Expected samples with 2D shape, got {tuple(samples.shape)}")
+    if weights.dim() != 2:
+        raise ValueError(f"Expected weights with 2D shape, got {tuple(weights.shape)}")
+    if samples.shape[0] != weights.shape[0]:
+        raise ValueError("Samples/weights batch size mismatch")
+    out = []
+    for b in range(samples.shape[0]):
+        vals = samples[b].detach().cpu().numpy().reshape(-1).astype(float)
+        wts = weights[b].detach().cpu().numpy().reshape(-1).astype(float)
+        idx = np.rint(vals)
+        ok = np.isfinite(wts) & (idx >= 0) & (idx < k)
+        hist = np.zeros(int(k), dtype=float)
+        np.add.at(hist, idx[ok].astype(int), wts[ok])
+        out.append(normalize_probs(hist))
+    return out
+
+
+def continuous_from_samples(samples, weights=None) -> dict:
+    """benchmarking/models/vbn.py:365-423 (_extract_samples_1d + _continuous_from_samples)."""
+    import numpy as np
+
+    arr = np.asarray(samples.detach().cpu().numpy() if isinstance(samples, torch.Tensor) else samples)
+    if arr.ndim == 0:
+        arr = arr.reshape(1)
+    if arr.ndim == 3:
+        arr = arr.reshape(-1, arr.shape[-1])
+    if arr.ndim == 2:
+        if arr.shape[1] != 1:
+            raise ValueError("Multivariate continuous targets are unsupported")
+        arr = arr[:, 0]
+    vals = arr.astype(float)
+    if vals.size == 0:
+        raise ValueError("No samples returned for continuous target")
+    wts = None
+    if weights is not None:
+        w = np.asarray(weights.detach().cpu().numpy() if isinstance(weights, torch.Tensor) else weights).reshape(-1)
+        if w.size == vals.size and np.isfinite(w).any():
+            wts = w.astype(float)
+    mean = std = None
+    if wts is not None:
+        wts = np.clip(wts, 0.0, np.inf)
+        total = float(wts.sum())
+        if total > 0:
+            wts = wts / total
+            mean = float(np.sum(wts * vals))
+            std = math.sqrt(float(np.sum(wts * (vals - mean) ** 2)))
+    if mean is None:
+        mean, std = float(np.mean(vals)), float(np.std(vals, ddof=0))
+    keep = [float(x) for x in vals[: min(int(vals.size), 2048)]]
+    if math.isfinite(mean) and math.isfinite(std):
+        return {"format": "normal_params", "mean": mean, "std": std, "n_samples": int(vals.size), "samples": keep}
+    return {"format": "samples_1d", "samples": keep, "n_samples": int(vals.size)}
+
+
 def lg_exact_posterior(spec, target: str, evidence: Dict[str, torch.Tensor],
                        do: Optional[Dict[str, torch.Tensor]] = None):
     """Exact N(mean, var) of ``target`` given evidence for an all-linear_gaussian DAG with

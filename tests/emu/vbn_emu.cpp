@@ -127,6 +127,21 @@ int32_t vbn_weighted_sum(const float* w, const float* x, int64_t B, int64_t S, i
   }
   return 0;
 }
+int32_t vbn_weighted_histogram(const float* x, const float* w, int64_t B, int64_t S, int64_t stride, int32_t K, float* probs, void*) {
+  for (int64_t b = 0; b < B; ++b) {
+    std::vector<double> h(K, 0.0);
+    for (int64_t s = 0; s < S; ++s) {
+      const float wv = w[b * S + s], xv = x[(b * S + s) * stride];
+      if (!(wv == wv) || std::fabs(wv) == INFINITY || !(xv == xv) || !(std::fabs(xv) < 2.0e9f)) continue;
+      const long j = std::lrint(xv);  // round half to even (default rounding mode)
+      if (j >= 0 && j < K) h[j] += wv;
+    }
+    double tot = 0; for (double v : h) tot += v;
+    const bool uni = !(tot == tot) || std::fabs(tot) == INFINITY || tot <= 0;
+    for (int c = 0; c < K; ++c) probs[b * K + c] = uni ? 1.0f / K : (float)(h[c] / tot);
+  }
+  return 0;
+}
 int32_t vbn_gaussian_mixture_grid(const float* w, const float* ls, int64_t B, int64_t S, int64_t N, float k, float min_scale,
                                   float* pdf, float* grid, void*) {
   for (int64_t b = 0; b < B; ++b) {

@@ -186,6 +186,47 @@ def ris_files():
     return out
 
 
+def summaries_file():
+    """Posterior summaries of the benchmark adapter: inputs and the outputs of the
+    reference's own functions (benchmarking/models/vbn.py:202-242, 381-423):
+    python tests/golden/make_golden.py summaries"""
+    refmodels.import_reference()
+    from benchmarking.models import vbn as RB
+
+    g = torch.Generator().manual_seed(97531)
+    cases = []
+    for (b, s, k) in ((1, 7, 2), (3, 200, 4), (5, 1000, 3), (2, 513, 20), (4, 64, 37)):
+        x = torch.randint(-1, k + 1, (b, s), generator=g).float()  # some values outside the class set
+        x[:, ::11] += 0.5  # exact halves: Python round() goes to even
+        x[:, 1::13] += 0.25 * torch.randn(x[:, 1::13].shape, generator=g)
+        w = torch.rand(b, s, generator=g)
+        w = w / w.sum(1, keepdim=True)
+        if s > 20:
+            w[0, 3] = float("nan")
+            w[0, 5] = float("inf")
+        if b > 1:
+            w[1] = 0.0  # empty histogram -> uniform
+        probs = RB._estimate_discrete_posterior_batch(x.unsqueeze(-1), w, k)
+        assert probs == O.estimate_discrete_posterior_batch(x.unsqueeze(-1), w, k)
+        cases.append({"kind": "discrete", "samples": x.unsqueeze(-1), "weights": w, "k": k, "probs": torch.tensor(probs, dtype=torch.float64)})
+    model = RB.VBNBenchmarkModel.__new__(RB.VBNBenchmarkModel)
+    for (s, mode) in ((9, "w"), (400, "w"), (4096, "w"), (300, "none"), (300, "zero"), (50, "neg")):
+        x = 2.0 * torch.randn(1, s, 1, generator=g) + 0.7
+        w = torch.rand(1, s, generator=g)
+        if mode == "zero":
+            w = torch.zeros(1, s)
+        if mode == "neg":
+            w = w - 0.3  # negative weights are clipped at 0 (:396)
+        arg = None if mode == "none" else w
+        out = model._continuous_from_samples(x, weights=arg)
+        mine = O.continuous_from_samples(x, weights=arg)
+        assert out == mine, (out["mean"], mine["mean"])
+        cases.append({"kind": "continuous", "samples": x, "weights": arg, "out": out})
+    path = os.path.join(HERE, "summaries.pt")
+    torch.save({"cases": cases}, path)
+    print(f"summaries: {len(cases)} cases, {os.path.getsize(path)/1024:.0f} KiB")
+
+
 def save(files):
     total = 0
     for name, blob in files.items():
@@ -205,6 +246,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "ris":
         save(ris_files())
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "summaries":
+        summaries_file()
         return
     if len(sys.argv) > 1 and sys.argv[1] == "exact":
         save(exact_files())

@@ -265,3 +265,22 @@ def test_rao_blackwellized_marginalization():
               O.rao_blackwellized_marginalization)  # mdn target -> unsupported -> fallback
     _exact_eq(m3, s3, "rao_blackwellized_marginalization", {"target": "feature_0", "evidence": {}}, 16,
               O.rao_blackwellized_marginalization)  # gaussian_nn root
+
+
+def test_posterior_summaries_of_the_benchmark_adapter():
+    """benchmarking/models/vbn.py:116-121, 202-242, 365-423: float64-exact."""
+    refmodels.import_reference()
+    from benchmarking.models import vbn as RB
+
+    g = torch.Generator().manual_seed(31)
+    for (b, s, k) in ((1, 5, 2), (4, 333, 5), (2, 1200, 9)):
+        x = torch.randint(-2, k + 2, (b, s), generator=g).float() + 0.5 * torch.randint(0, 2, (b, s), generator=g)
+        w = torch.rand(b, s, generator=g)
+        w[0, 0] = float("nan")
+        assert RB._estimate_discrete_posterior_batch(x, w, k) == O.estimate_discrete_posterior_batch(x, w, k)
+        assert RB._estimate_discrete_posterior(x, w, k) == O.estimate_discrete_posterior_batch(x[:1], w[:1], k)[0]
+    model = RB.VBNBenchmarkModel.__new__(RB.VBNBenchmarkModel)
+    for s in (3, 500, 5000):
+        x = torch.randn(1, s, 1, generator=g)
+        for w in (None, torch.rand(1, s, generator=g), torch.zeros(1, s), torch.rand(1, s, generator=g) - 0.5):
+            assert model._continuous_from_samples(x, weights=w) == O.continuous_from_samples(x, weights=w)

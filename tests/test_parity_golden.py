@@ -15,7 +15,9 @@ from oracle import vbn_oracle as O
 import vectorizedbayesiannetwork_b200 as V
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-FILES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, "*.pt")))
+NOT_MODELS = {"summaries"}  # fixtures that are not (model, cases) files
+FILES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, "*.pt"))
+               if os.path.basename(p)[:-3] not in NOT_MODELS)
 RTOL, ATOL = 1e-5, 1e-6
 METHOD_NAMES = {"lw": "likelihood_weighting", "is": "importance_sampling", "mcm": "monte_carlo_marginalization",
                 "gexact": "gaussian_exact", "cexact": "categorical_exact", "ris": "resampled_importance_sampling",
@@ -91,3 +93,47 @@ def test_cpd_sample_log_prob_match_reference(backend, name):
         _close(cpd.log_prob(x, p_dev), case["log_prob"], tag + " log_prob", rtol=2e-5, atol=2e-6)
         p2 = p_dev if p_dev is None or p_dev.dim() == 2 else p_dev[:, :1]
         _close(cpd.log_prob(x[:, 0], p2), case["log_prob_2d"], tag + " log_prob 2d", rtol=2e-5, atol=2e-6)
+
+
+# ---- posterior summaries of the benchmark adapter ----------------------------------
+def test_posterior_summaries_match_reference(backend):
+    """benchmarking/models/vbn.py:202-242 (_estimate_discrete_posterior(_batch)) and :381-423
+    (_continuous_from_samples): outputs of the reference's own functions stored in summaries.pt."""
+    from vectorizedbayesiannetwork_b200 import summaries as SM
+
+    for i, c in enumerate(_load("summaries")["cases"]):
+        x = c["samples"].to(backend.device)
+        w = None if c["weights"] is None else c["weights"].to(backend.device)
+        if c["kind"] == "discrete":
+            got = torch.tensor(SM._estimate_discrete_posterior_batch(x, w, c["k"]), dtype=torch.float64)
+            _close(got, c["probs"], f"summaries[{i}] probs", rtol=1e-5, atol=1e-7)
+            assert got.shape == (x.shape[0], c["k"])
+            torch.testing.assert_close(got.sum(1), torch.ones(x.shape[0], dtype=torch.float64), rtol=0, atol=1e-5)
+            one = SM._estimate_discrete_posterior(x, w, c["k"])  # first query only (:207-212)
+            _close(torch.tensor(one, dtype=torch.float64), c["probs"][0], f"summaries[{i}] single", rtol=1e-5, atol=1e-7)
+            _close(torch.tensor(O.estimate_discrete_posterior_batch(c["samples"], c["weights"], c["k"]),
+                                dtype=torch.float64), c["probs"], f"summaries[{i}] oracle", rtol=0, atol=0)
+        else:
+            got = SM._continuous_from_samples(x, weights=w)
+            want = c["out"]
+            assert got["format"] == want["format"] == "normal_params" and got["n_samples"] == want["n_samples"]
+            assert abs(got["mean"] - want["mean"]) <= 1e-6 + 1e-5 * abs(want["mean"]), (i, got["mean"], want["mean"])
+            assert abs(got["std"] - want["std"]) <= 1e-6 + 1e-5 * abs(want["std"]), (i, got["std"], want["std"])
+            assert got["samples"] == want["samples"]
+            assert O.continuous_from_samples(c["samples"], weights=c["weights"]) == want
+
+
+def test_posterior_summaries_argument_errors(backend):
+    from vectorizedbayesiannetwork_b200 import summaries as SM
+
+    x, w = torch.zeros(2, 5, device=backend.device), torch.ones(2, 5, device=backend.device)
+    with pytest.raises(ValueError):  # :233-234
+        SM._estimate_discrete_posterior_batch(x[0], w, 3)
+    with pytest.raises(ValueError):  # :235-236
+        SM._estimate_discrete_posterior_batch(x, w[0], 3)
+    with pytest.raises(ValueError):  # :237-238
+        SM._estimate_discrete_posterior_batch(x, w[:1], 3)
+    with pytest.raises(ValueError):  # :376
+        SM._continuous_from_samples(torch.zeros(4, 2, device=backend.device))
+    probs = SM._estimate_discrete_posterior_batch(x, w, 3)  # every sample is class 0
+    assert probs == [[1.0, 0.0, 0.0], [1.0, 0.0, 0.0]]

@@ -75,6 +75,8 @@ EXPORTS = {
     "vbn_resample_indices": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64, C.c_int64,
                                          C.c_int64, C.c_void_p, C.c_void_p]),
     "vbn_gather_rows": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p]),
+    "vbn_weighted_histogram": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                                           C.c_void_p, C.c_void_p]),
     "vbn_weighted_sum": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "vbn_gaussian_mixture_grid": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_float,
                                               C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),

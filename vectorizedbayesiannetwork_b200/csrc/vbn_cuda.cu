@@ -325,6 +325,17 @@ int32_t vbn_weighted_sum(const float* w_dev, const float* x_dev, int64_t n_queri
   return VBN_OK;
 }
 
+int32_t vbn_weighted_histogram(const float* samples_dev, const float* w_dev, int64_t n_queries, int64_t n_samples,
+                               int64_t sample_stride, int32_t n_classes, float* probs_dev, void* stream) {
+  if (!samples_dev || !w_dev || !probs_dev || n_queries <= 0 || n_samples <= 0 || sample_stride <= 0 ||
+      n_classes <= 0 || n_classes > vbn::kHistMaxClasses)
+    return fail(VBN_E_INVALID, "bad argument to vbn_weighted_histogram (1 <= n_classes <= %d)", vbn::kHistMaxClasses);
+  vbn::weighted_histogram_kernel<<<static_cast<unsigned>(n_queries), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      samples_dev, w_dev, n_samples, sample_stride, n_classes, probs_dev);
+  CUDA_TRY(cudaGetLastError());
+  return VBN_OK;
+}
+
 int32_t vbn_gaussian_mixture_grid(const float* w_dev, const float* loc_scale_dev, int64_t n_queries,
                                   int64_t n_particles, int64_t n_out, float stddevs, float min_scale,
                                   float* pdf_dev, float* grid_dev, void* stream) {

@@ -327,6 +327,50 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------
+// Weighted class histogram of a discrete target: the benchmark adapter's Python double loop
+// _estimate_discrete_posterior(_batch) (benchmarking/models/vbn.py:202-242) + _normalize_probs (:116-121):
+//   hist[b][c] = sum_s w[b,s] [round_half_even(x[b,s]) == c, w finite];  probs = hist / sum(hist),
+//   uniform 1/K when the total is not finite or <= 0.
+// grid B, 256 threads, K <= kHistMaxClasses; classes are processed 16 at a time in register
+// accumulators (deterministic: no atomics), block-reduced by warp shuffles.
+// ---------------------------------------------------------------------------------------
+constexpr int kHistMaxClasses = 256;
+
+__global__ void __launch_bounds__(256) weighted_histogram_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                  int64_t n_samples, int64_t x_stride, int n_classes,
+                                                                  float* __restrict__ probs) {
+  __shared__ float sh[8];
+  __shared__ float hist[kHistMaxClasses];
+  const int64_t b = blockIdx.x;
+  for (int c0 = 0; c0 < n_classes; c0 += 16) {
+    float acc[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc[q] = 0.0f;
+    for (int64_t s = threadIdx.x; s < n_samples; s += blockDim.x) {
+      const float wv = __ldg(w + b * n_samples + s);
+      const float xv = __ldg(x + (b * n_samples + s) * x_stride);
+      const bool ok = wv == wv && fabsf(wv) != CUDART_INF_F && xv == xv && fabsf(xv) < 2.0e9f;
+      const int j = ok ? static_cast<int>(rintf(xv)) - c0 : -1;  // Python round(): half to even
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc[q] += j == q ? wv : 0.0f;
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const float t = block_sum256(acc[q], sh);
+      if (threadIdx.x == 0 && c0 + q < n_classes) hist[c0 + q] = t;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float total = 0.0f;
+    for (int c = 0; c < n_classes; ++c) total += hist[c];
+    const bool uniform = !(total == total) || fabsf(total) == CUDART_INF_F || total <= 0.0f;
+    for (int c = 0; c < n_classes; ++c)
+      probs[b * n_classes + c] = uniform ? __fdiv_rn(1.0f, static_cast<float>(n_classes)) : __fdiv_rn(hist[c], total);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // rao_blackwellized_marginalization epilogues (rao_blackwellized_marginalization.py:277-317).
 // ---------------------------------------------------------------------------------------
 // out[b][k] = sum_s w[b,s] * x[b,s,k]   (categorical marginal; K <= 64).  grid B, 256 threads.

@@ -269,6 +269,23 @@ def posterior_stats(pdf: torch.Tensor, samples: torch.Tensor, eps: float = 1e-12
     return {"mean": stats[:, 2:2 + d], "std": stats[:, 2 + d:2 + 2 * d], "ess": stats[:, 1]}
 
 
+def weighted_histogram(samples: torch.Tensor, weights: torch.Tensor, k: int) -> torch.Tensor:
+    """probs [B,k] of a discrete target from (samples [B,S] or [B,S,D], weights [B,S]): the GPU form of
+    _estimate_discrete_posterior_batch + _normalize_probs (benchmarking/models/vbn.py:116-121, 202-242)."""
+    lib = L.load()
+    dev = require_cuda(weights.device)
+    b, s = weights.shape
+    samples = samples.to(device=dev, dtype=torch.float32).contiguous()
+    weights = weights.to(device=dev, dtype=torch.float32).contiguous()
+    stride = int(samples.shape[2]) if samples.dim() == 3 else 1
+    with torch.cuda.device(dev):
+        probs = torch.empty(b, int(k), device=dev, dtype=torch.float32)
+        L.check(lib.vbn_weighted_histogram(samples.data_ptr(), weights.data_ptr(), b, s, stride, int(k),
+                                           probs.data_ptr(), _stream_ptr(dev)))
+        L.count_launch(1)
+    return probs
+
+
 def ess_below(stats: torch.Tensor, threshold: float) -> torch.Tensor:
     lib = L.load()
     dev = stats.device
