@@ -45,6 +45,9 @@ extern "C" {
 #define VBN_OP_TAB 6     /* softmax_nn in discrete mode with all-discrete parents: log-density
                             table per parent configuration, built by the plan compiler     */
 
+#define VBN_OP_RFF 7     /* vbn/cpds/rff_gaussian.py:131-146,185-206,254-291: random Fourier features,
+                            loc = (sqrt(2/F) cos(z W^T + b)) coef + bias, de-standardised; constant scale */
+
 /* ---- op flags ------------------------------------------------------------------------ */
 #define VBN_SRC_MASK 0x3
 #define VBN_SRC_SAMPLE 0x0     /* draw x ~ p(x | parents)                                    */

@@ -304,6 +304,68 @@ def gnn_log_prob(c, x, parents):
 
 
 # --------------------------------------------------------------------------------------
+# rff_gaussian  (vbn/cpds/rff_gaussian.py:131-146, 181-206, 254-291)  -- SURVEY 8f row 3
+# --------------------------------------------------------------------------------------
+
+
+def rff_scale(c) -> torch.Tensor:
+    return torch.sqrt(c["var"].clamp(min=float(c["min_scale"]) ** 2))  # :181-183
+
+
+def rff_features(c, parents: torch.Tensor) -> torch.Tensor:
+    z = (parents - c["mean_x"].view(1, -1)) / c["std_x"].view(1, -1)  # :131-136
+    proj = z @ c["rff_w"].t() + c["rff_b"]  # :144
+    return math.sqrt(2.0 / float(c["n_features"])) * torch.cos(proj)  # :145-146
+
+
+def rff_params(c, parents: Optional[torch.Tensor]):
+    if c["input_dim"] == 0:
+        return c["mean_y"], rff_scale(c)  # :188-191
+    if parents is None:
+        raise ValueError("parents cannot be None when input_dim > 0")
+    if parents.dim() == 2:
+        parents = parents.unsqueeze(1)
+    b, s, dp = parents.shape
+    feats = rff_features(c, parents.reshape(b * s, dp))
+    loc_norm = (feats @ c["coef"] + c["bias"]).reshape(b, s, c["output_dim"])  # :198-199
+    loc = loc_norm * c["std_y"].view(1, 1, -1) + c["mean_y"].view(1, 1, -1)
+    return loc, rff_scale(c).view(1, 1, -1).expand(b, s, -1)
+
+
+def _rff_check(c):
+    if not c["stats_ready"]:
+        raise RuntimeError("RFFGaussianCPD is not fitted yet.")  # :76-78
+
+
+def rff_sample(c, parents, n, noise, key):
+    _rff_check(c)
+    if c["input_dim"] == 0:
+        b = 1 if parents is None else parents.shape[0]
+        loc = c["mean_y"].view(1, 1, -1).expand(b, n, -1)
+        scale = rff_scale(c).view(1, 1, -1).expand(b, n, -1)
+    else:
+        if parents is None:
+            raise ValueError("parents cannot be None when input_dim > 0")
+        loc, scale = rff_params(c, broadcast_samples(parents, n))
+    eps = noise.normal(key, scale)  # torch.randn_like(scale)  (:266)
+    return loc + eps * scale
+
+
+def rff_log_prob(c, x, parents):
+    _rff_check(c)
+    x = _x3(x)
+    if c["input_dim"] == 0:
+        b, s, _ = x.shape
+        loc = c["mean_y"].view(1, 1, -1).expand(b, s, -1)
+        scale = rff_scale(c).view(1, 1, -1).expand(b, s, -1)
+    else:
+        if parents is None:
+            raise ValueError("parents cannot be None when input_dim > 0")
+        loc, scale = rff_params(c, broadcast_samples(parents, x.shape[1]))
+    return gaussian_logpdf_sum(x, loc, scale)  # :287-291
+
+
+# --------------------------------------------------------------------------------------
 # mdn  (vbn/cpds/mdn.py:185-272)
 # --------------------------------------------------------------------------------------
 
@@ -667,6 +729,7 @@ _SAMPLE = {
     "softmax_nn": snn_sample,
     "kde": kde_sample,
     "categorical_table": ct_sample,
+    "rff_gaussian": rff_sample,
 }
 _LOG_PROB = {
     "linear_gaussian": lg_log_prob,
@@ -675,7 +738,13 @@ _LOG_PROB = {
     "softmax_nn": snn_log_prob,
     "kde": kde_log_prob,
     "categorical_table": ct_log_prob,
+    "rff_gaussian": rff_log_prob,
 }
+
+
+# CPDs whose conditional is one Gaussian: read through _weight/_bias/_var or a callable _params by the
+# exact / Rao-Blackwellized methods and CPDHandle.conditional (cpd_handle.py:40-70)
+_GAUSSIAN_PARAMS = {"linear_gaussian": lg_params, "gaussian_nn": gnn_params, "rff_gaussian": rff_params}
 
 
 def cpd_sample(c, parents, n_samples: int, noise=None, key=("cpd",)):
@@ -933,8 +1002,8 @@ def rao_blackwellized_marginalization(spec, query, n_samples: int, noise=None, n
                 probs = probs.expand(-1, n_particles, -1)
             marginal = (w.unsqueeze(-1) * probs).sum(dim=1)  # :277-279
             return done(marginal, support.to(dtype=marginal.dtype).view(1, -1, 1).expand(b, -1, 1))
-    if c["kind"] in ("linear_gaussian", "gaussian_nn") and c["output_dim"] == 1:  # _target_gaussian_params :92-153
-        loc, scale = (lg_params if c["kind"] == "linear_gaussian" else gnn_params)(c, parents)
+    if c["kind"] in _GAUSSIAN_PARAMS and c["output_dim"] == 1:  # _target_gaussian_params :92-153
+        loc, scale = _GAUSSIAN_PARAMS[c["kind"]](c, parents)
         loc = loc.reshape(1, 1, -1) if loc.dim() == 1 else loc
         scale = scale.reshape(1, 1, -1) if scale.dim() == 1 else scale
         if loc.shape[0] == 1 and b > 1:
@@ -1003,9 +1072,9 @@ def gaussian_exact(spec, query, n_samples: int, noise=None, stddevs: float = 4.0
         out = (torch.ones(b, 1), fixed[t].unsqueeze(1).expand(b, 1, -1))
         return (*out, {"exact": True}) if return_info else out
     ok, parents = _exact_parent_tensor(st, fixed, b)
-    if not ok or c["kind"] not in ("linear_gaussian", "gaussian_nn"):  # :155-170 (_gaussian_params -> None)
+    if not ok or c["kind"] not in _GAUSSIAN_PARAMS:  # :155-170 (_gaussian_params -> None)
         return fallback()
-    loc, scale = (lg_params if c["kind"] == "linear_gaussian" else gnn_params)(c, parents)
+    loc, scale = _GAUSSIAN_PARAMS[c["kind"]](c, parents)
     loc = loc.reshape(-1, 1, 1) if loc.dim() < 3 else loc  # _to_3d (:52-64)
     scale = scale.reshape(-1, 1, 1) if scale.dim() < 3 else scale
     if loc.shape[0] == 1 and b > 1:
@@ -1335,6 +1404,11 @@ def cpd_spec_from_reference(cpd) -> dict:
         else:
             out["layers"] = _layers_of(cpd.net)
         return out
+    if name == "RFFGaussianCPD":
+        return {**base, "kind": "rff_gaussian", "min_scale": float(cpd.min_scale), "n_features": int(cpd.n_features),
+                "mean_x": g(cpd.mean_x), "std_x": g(cpd.std_x), "mean_y": g(cpd.mean_y), "std_y": g(cpd.std_y),
+                "rff_w": g(cpd._rff_w), "rff_b": g(cpd._rff_b), "coef": g(cpd._coef), "bias": g(cpd._bias),
+                "var": g(cpd._var), "stats_ready": bool(cpd._stats_ready.item())}
     if name == "MDNCPD":
         out = {**base, "kind": "mdn", "min_scale": float(cpd.min_scale),
                "activation": cpd.activation, "n_components": int(cpd.n_components)}

@@ -108,6 +108,22 @@ def table_files():
     return {"table": {"spec": spec, "cases": cases, "cpd_cases": cpd_cases(m, spec)}}
 
 
+def rff_files():
+    """rff_gaussian nodes:  python tests/golden/make_golden.py rff"""
+    torch.manual_seed(8642)
+    m = refmodels.rff_model()
+    spec = O.spec_from_reference(m)
+    ev = torch.tensor([[0.4], [-1.1], [2.0]])
+    qs = [{"target": "b", "evidence": {"d": ev}},
+          {"target": "c", "evidence": {"a": ev, "e": -ev}},
+          {"target": "a", "evidence": {"c": torch.randn(2, 2)}},
+          {"target": "d", "evidence": {}, "do": {"b": ev}}]
+    cases = [run_case(m, spec, q, 40, meth, 23) for q in qs for meth in ("lw", "is", "mcm", "anc")]
+    cases += [run_case(m, spec, {"target": "b", "evidence": {"a": ev, "e": 0.5 * ev}}, 21, meth, 5) for meth in ("gexact", "rb")]
+    cases += [run_case(m, spec, {"target": "d", "evidence": {"a": ev}}, 21, meth, 5) for meth in ("gexact", "rb")]
+    return {"rff": {"spec": spec, "cases": cases, "cpd_cases": cpd_cases(m, spec)}}
+
+
 def exact_files():
     """gaussian_exact / categorical_exact, incl. their likelihood-weighting fallbacks:
     python tests/golden/make_golden.py exact"""
@@ -246,6 +262,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "ris":
         save(ris_files())
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "rff":
+        save(rff_files())
         return
     if len(sys.argv) > 1 and sys.argv[1] == "summaries":
         summaries_file()

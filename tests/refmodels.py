@@ -163,6 +163,32 @@ def table_model(rows=800, epochs=4, seed=0):
     return _fit(g, cpds, data)
 
 
+def rff_model(rows=600, seed=0):
+    """rff_gaussian nodes (vbn/cpds/rff_gaussian.py) next to linear_gaussian ones, incl. a root and a 2-D node:
+    a(rff root) -> b(rff, 24 features) ; a, b -> c(rff, D=2, default 256 features) ; c -> d(lg) ; e(lg root) -> b."""
+    import networkx as nx
+
+    gen = torch.Generator().manual_seed(seed)
+    g = nx.DiGraph()
+    g.add_edges_from([("a", "b"), ("e", "b"), ("a", "c"), ("b", "c"), ("c", "d")])
+    rn = lambda *s: torch.randn(*s, generator=gen)
+    a = 0.3 + 1.2 * rn(rows, 1)
+    e = rn(rows, 1)
+    b = torch.sin(1.5 * a) - 0.4 * e + 0.2 * rn(rows, 1)
+    c = torch.cat([torch.cos(a) * b, a - b**2], dim=1) + 0.25 * rn(rows, 2)
+    d = c.sum(1, keepdim=True) * 0.5 + 0.3 * rn(rows, 1)
+    cpds = {
+        "a": {"cpd": "rff_gaussian"},
+        "e": {"cpd": "linear_gaussian"},
+        # ridge keeps sum|coef| ~ |loc|: with the default 1e-6 the fit is ill-conditioned (sum|coef| ~ 400 for an
+        # O(1) loc) and fp32 summation ORDER alone moves loc by 1e-5 relative -- in the reference as much as here
+        "b": {"cpd": "rff_gaussian", "n_features": 24, "lengthscale": 0.8, "ridge": 3e-2},
+        "c": {"cpd": "rff_gaussian", "ridge": 1e-1},
+        "d": {"cpd": "linear_gaussian"},
+    }
+    return _fit(g, cpds, {"a": a, "e": e, "b": b, "c": c, "d": d})
+
+
 def binned_model(within_bin="uniform", clip=False, rows=400, epochs=3, seed=0, dim=2):
     """softmax_nn in binned-continuous mode, root + child, D=dim."""
     import networkx as nx

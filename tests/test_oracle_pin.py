@@ -122,6 +122,29 @@ def test_categorical_table_model():
         O.likelihood_weighting(spec, {"target": "slip", "evidence": {"rain": torch.tensor([[0.5]])}}, 8)
 
 
+def test_rff_gaussian_model():
+    """rff_gaussian (vbn/cpds/rff_gaussian.py:131-146, 185-206, 254-291): root, 1-D and 2-D nodes."""
+    model = refmodels.rff_model()
+    spec = O.spec_from_reference(model)
+    ev = torch.tensor([[0.4], [-1.1], [2.0]])
+    _run_methods(model, spec, {"target": "b", "evidence": {"d": ev}}, 48)
+    _run_methods(model, spec, {"target": "c", "evidence": {"a": ev, "e": -ev}}, 48)
+    _run_methods(model, spec, {"target": "a", "evidence": {"c": torch.randn(2, 2)}}, 48)
+    for name in ("gaussian_exact", "rao_blackwellized_marginalization"):
+        fn = getattr(O, name)
+        _exact_eq(model, spec, name, {"target": "b", "evidence": {"a": ev, "e": ev * 0.5}}, 21, fn)  # parents fixed
+        _exact_eq(model, spec, name, {"target": "a", "evidence": {}}, 21, fn)                         # root
+        _exact_eq(model, spec, name, {"target": "d", "evidence": {"a": ev}}, 21, fn)
+    for node, cpd in model.nodes.items():
+        c = spec["cpds"][node]
+        parents = None if cpd.input_dim == 0 else torch.randn(4, cpd.input_dim)
+        torch.manual_seed(3)
+        rs = cpd.sample(parents, 6)
+        torch.manual_seed(3)
+        _eq(rs, O.cpd_sample(c, parents, 6))
+        _eq(cpd.log_prob(rs, parents), O.cpd_log_prob(c, rs, parents))
+
+
 @pytest.mark.parametrize("within_bin,clip", [("uniform", False), ("triangular", False),
                                              ("gaussian", False), ("uniform", True),
                                              ("triangular", True)])

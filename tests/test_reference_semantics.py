@@ -428,6 +428,35 @@ def test_conditional_formats_match_the_parameter_heads(backend):
     assert seen == {"normal_params", "mixture_params", "categorical_probs", "empirical_samples"}
 
 
+# ---- rff_gaussian (vbn/cpds/rff_gaussian.py) ---------------------------------------
+def test_rff_gaussian_conditional_and_unfitted(backend):
+    import os
+
+    spec = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rff.pt"),
+                      weights_only=False)["spec"]
+    model = V.VBN.from_spec(spec, device=backend.device)
+    g = torch.Generator().manual_seed(3)
+    for node in ("a", "b", "c"):
+        c = spec["cpds"][node]
+        parents = torch.randn(6, c["input_dim"], generator=g) if c["input_dim"] else None
+        out = model.get_cpd(node).conditional(parents)  # a callable _params -> "normal_params" (cpd_handle.py:59-66)
+        loc, scale = O.rff_params(c, parents)
+        assert out["format"] == "normal_params"
+        mean, std = torch.tensor(out["mean"]), torch.tensor(out["std"])
+        torch.testing.assert_close(mean, loc.reshape(mean.shape), rtol=1e-5, atol=4e-6)
+        torch.testing.assert_close(std, scale.expand(loc.shape).reshape(std.shape), rtol=1e-5, atol=1e-6)
+    # Philox path: the drawn column has the conditional's moments
+    cpd = V.cpd_from_spec(spec["cpds"]["b"], device=backend.device)
+    pa = torch.tensor([[0.3, -0.5]])
+    s = cpd.sample(pa, 20000, seed=5).cpu()
+    loc, scale = O.rff_params(spec["cpds"]["b"], pa)
+    assert abs(s.mean().item() - loc.item()) < 5 * scale.item() / 20000**0.5
+    assert abs(s.std().item() / scale.item() - 1.0) < 0.03
+    unfitted = dict(spec["cpds"]["b"], stats_ready=False)
+    with pytest.raises(RuntimeError):  # rff_gaussian.py:76-78
+        V.cpd_from_spec(unfitted, device=backend.device).sample(pa, 4)
+
+
 # ---- VBN._posterior_stats / infer_relative (vbn/vbn.py:483-568; tests/test_gaussian_exact_relative.py:40-57)
 def _ref_posterior_stats(pdf, samples, eps=1e-12):
     weights = torch.nan_to_num(pdf, nan=0.0, posinf=0.0, neginf=0.0).clamp_min(0.0)

@@ -126,7 +126,7 @@ class CPDHandle:
                     "k": int(cpd.n_classes), "support": _to_serializable(cpd._sample_values)}
         if cpd.param_width() > 0:
             out = cpd.params(ptensor).detach()  # [B, S, width] from the GPU read-out
-            if cpd.kind in ("linear_gaussian", "gaussian_nn"):
+            if cpd.kind in ("linear_gaussian", "gaussian_nn", "rff_gaussian"):
                 return {**base, "format": "normal_params", "mean": _to_serializable(out[..., :d]),
                         "std": _to_serializable(out[..., d:])}
             if cpd.kind == "mdn":

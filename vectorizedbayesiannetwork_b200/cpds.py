@@ -325,6 +325,77 @@ class GaussianNNCPD(BaseCPD):
 
 
 # ------------------------------------------------------------------------------------------
+class RFFGaussianCPD(BaseCPD):
+    """vbn/cpds/rff_gaussian.py:14-291: random-Fourier-feature ridge regression with a
+    constant Gaussian noise scale.  Inference-time state only (buffers of a fitted reference object)."""
+
+    kind = "rff_gaussian"
+
+    def __init__(self, input_dim, output_dim, *, n_features, rff_w=None, rff_b=None, coef=None, bias=None, var=None,
+                 mean_x=None, std_x=None, mean_y=None, std_y=None, min_scale: float = 1e-3, stats_ready: bool = True,
+                 device=None):
+        super().__init__(input_dim, output_dim, device)
+        d, dp, f = self.output_dim, self.input_dim, int(n_features)
+        self.n_features = f
+        self.min_scale = float(min_scale)
+        self._stats_ready = bool(stats_ready)
+        self.mean_x = _f32(mean_x if mean_x is not None else torch.zeros(dp)).reshape(dp)
+        self.std_x = _f32(std_x if std_x is not None else torch.ones(dp)).reshape(dp)
+        self.mean_y = _f32(mean_y if mean_y is not None else torch.zeros(d)).reshape(d)
+        self.std_y = _f32(std_y if std_y is not None else torch.ones(d)).reshape(d)
+        self._rff_w = _f32(rff_w if rff_w is not None else torch.zeros(f, dp)).reshape(f, dp)
+        self._rff_b = _f32(rff_b if rff_b is not None else torch.zeros(f)).reshape(f)
+        self._coef = _f32(coef if coef is not None else torch.zeros(f, d)).reshape(f, d)
+        self._bias = _f32(bias if bias is not None else torch.zeros(d)).reshape(d)
+        self._var = _f32(var if var is not None else torch.ones(d)).reshape(d)
+
+    def _scale(self) -> torch.Tensor:
+        return torch.sqrt(self._var.clamp(min=self.min_scale**2))  # rff_gaussian.py:181-183
+
+    def param_width(self) -> int:
+        return 2 * self.output_dim
+
+    def _pack(self) -> Packed:
+        if not self._stats_ready:  # rff_gaussian.py:76-78
+            raise RuntimeError("RFFGaussianCPD is not fitted yet.")
+        d, dp, f = self.output_dim, self.input_dim, self.n_features
+        scale = self._scale()
+        if dp == 0:
+            # root: Normal(mean_y, scale) (rff_gaussian.py:188-191, 256-259) -- linear_gaussian with Dp = 0
+            params = np.concatenate([_np(self.mean_y), _np(scale), _np(2 * torch.log(scale)), _np(scale**2)])
+            return Packed(kind=L.OP_LG, dim=d, n_par=0, params=params, n_normals=d)
+        head = np.array([f, math.sqrt(2.0 / float(f)), 0.0, 0.0], np.float32)
+        stats = _padded(np.concatenate([_np(self.mean_x), _np(self.std_x)]), _pad4(2 * dp))
+        tail = _padded(np.concatenate([_np(self._bias), _np(self.mean_y), _np(self.std_y), _np(scale),
+                                       _np(2 * torch.log(scale)), _np(scale**2)]), _pad4(6 * d))
+        wb = torch.cat([self._rff_w, self._rff_b.reshape(f, 1)], dim=1)  # per feature: w_f[Dp], b_f
+        params = np.concatenate([head, stats, tail, _np(wb), _np(self._coef)])
+        return Packed(kind=L.OP_RFF, dim=d, n_par=dp, params=_padded(params, _pad4(params.size)), n_normals=d,
+                      scratch=dp + d, heavy=True)
+
+    @classmethod
+    def from_spec(cls, c, device=None):
+        return cls(c["input_dim"], c["output_dim"], n_features=c["n_features"], rff_w=c["rff_w"], rff_b=c["rff_b"],
+                   coef=c["coef"], bias=c["bias"], var=c["var"], mean_x=c["mean_x"], std_x=c["std_x"],
+                   mean_y=c["mean_y"], std_y=c["std_y"], min_scale=c["min_scale"],
+                   stats_ready=c.get("stats_ready", True), device=device)
+
+    @classmethod
+    def from_reference(cls, cpd, device=None):
+        return cls(cpd.input_dim, cpd.output_dim, n_features=cpd.n_features, rff_w=cpd._rff_w, rff_b=cpd._rff_b,
+                   coef=cpd._coef, bias=cpd._bias, var=cpd._var, mean_x=cpd.mean_x, std_x=cpd.std_x,
+                   mean_y=cpd.mean_y, std_y=cpd.std_y, min_scale=cpd.min_scale,
+                   stats_ready=bool(cpd._stats_ready.item()), device=device)
+
+    def to_spec(self):
+        return {"kind": self.kind, "input_dim": self.input_dim, "output_dim": self.output_dim,
+                "n_features": self.n_features, "min_scale": self.min_scale, "mean_x": self.mean_x,
+                "std_x": self.std_x, "mean_y": self.mean_y, "std_y": self.std_y, "rff_w": self._rff_w,
+                "rff_b": self._rff_b, "coef": self._coef, "bias": self._bias, "var": self._var,
+                "stats_ready": self._stats_ready}
+
+
+# ------------------------------------------------------------------------------------------
 class MDNCPD(BaseCPD):
     """vbn/cpds/mdn.py:37-272."""
 
@@ -744,6 +815,7 @@ CPD_CLASSES = {
     "softmax_nn": SoftmaxNNCPD,
     "kde": KDECPD,
     "categorical_table": CategoricalTableCPD,
+    "rff_gaussian": RFFGaussianCPD,
 }
 
 _REFERENCE_CLASS_NAMES = {
@@ -753,6 +825,7 @@ _REFERENCE_CLASS_NAMES = {
     "SoftmaxNNCPD": SoftmaxNNCPD,
     "KDECPD": KDECPD,
     "CategoricalTableCPD": CategoricalTableCPD,
+    "RFFGaussianCPD": RFFGaussianCPD,
 }
 
 

@@ -1000,6 +1000,15 @@ __device__ __forceinline__ void op_params(Ctx<RPT, NT, TC>& c, const VbnOp& op) 
         put(d, j, fmaf(c.scr(d, j), sy, __ldg(mean_y + d)));
         put(D + d, j, (softplus20(c.scr(D + d, j)) + min_scale) * sy);
       }
+  } else if (op.kind == VBN_OP_RFF) {
+    const float* tail = P + 4 + pad4(2 * Dp);
+    rff_loc(c, op, P);
+    for (int d = 0; d < D; ++d)
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        put(d, j, c.scr(Dp + d, j));
+        put(D + d, j, __ldg(tail + 3 * D + d));
+      }
   } else if (op.kind == VBN_OP_MDN) {
     const int K = op.k;
     const float min_scale = __ldg(P);
@@ -1048,6 +1057,100 @@ __device__ __forceinline__ void op_params(Ctx<RPT, NT, TC>& c, const VbnOp& op) 
         for (int k = 0; k < C; ++k) se += expf(__fdiv_rn(c.scr(d * C + k, j), it) - mx);
         for (int k = 0; k < C; ++k) put(d * C + k, j, __fdiv_rn(expf(__fdiv_rn(c.scr(d * C + k, j), it) - mx), se));
       }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// VBN_OP_RFF: rff_gaussian.py:131-146 (_normalize_parents, _features), 185-206 (_params),
+// 254-291 (sample, log_prob).
+// params: {F, sqrt(2/F), 0, 0}, mean_x[Dp], std_x[Dp] (pad4), {bias, mean_y, std_y, scale,
+//         2 ln scale, var}[D] (pad4), then per feature f: w_f[Dp], b_f  (stride Dp+1), coef[F][D]
+// loc lands in scratch rows Dp..Dp+D-1 (rows 0..Dp-1 hold the standardised parents).
+// ---------------------------------------------------------------------------------------
+template <int RPT, int NT, class TC>
+__device__ __forceinline__ void rff_loc(Ctx<RPT, NT, TC>& c, const VbnOp& op, const float* P) {
+  const int D = op.dim, Dp = op.n_par;
+  const int F = static_cast<int>(__ldg(P));
+  const float phi = __ldg(P + 1);
+  const float* mean_x = P + 4;
+  const float* std_x = mean_x + Dp;
+  const float* tail = P + 4 + pad4(2 * Dp);
+  const float* wb = tail + pad4(6 * D);
+  const float* coef = wb + F * (Dp + 1);
+  const int32_t* par = c.a.par_slots + op.par_off;
+  for (int p = 0; p < Dp; ++p) {
+    const float m = __ldg(mean_x + p), sd = __ldg(std_x + p);
+    const int ps = __ldg(par + p);
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) c.scr(p, j) = __fdiv_rn(c.slot(ps, j) - m, sd);
+  }
+  for (int d0 = 0; d0 < D; d0 += 4) {
+    float acc[RPT][4];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[j][q] = 0.0f;
+    for (int f = 0; f < F; ++f) {
+      const float* w = wb + f * (Dp + 1);
+      float proj[RPT];
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) proj[j] = 0.0f;
+      for (int p = 0; p < Dp; ++p) {
+        const float wp = __ldg(w + p);
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) proj[j] = fmaf(c.scr(p, j), wp, proj[j]);
+      }
+      const float bf = __ldg(w + Dp);
+      float cf[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cf[q] = d0 + q < D ? __ldg(coef + f * D + d0 + q) : 0.0f;
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        const float ph = phi * cosf(proj[j] + bf);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[j][q] = fmaf(ph, cf[q], acc[j][q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (d0 + q < D) {
+        const int d = d0 + q;
+        const float b = __ldg(tail + d), my = __ldg(tail + D + d), sy = __ldg(tail + 2 * D + d);
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) c.scr(Dp + d, j) = fmaf(acc[j][q] + b, sy, my);
+      }
+  }
+}
+
+template <int RPT, int NT, class TC>
+__device__ __forceinline__ void op_rff(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
+  const float* P = c.a.params + op.param_off;
+  const int D = op.dim, Dp = op.n_par;
+  const float* tail = P + 4 + pad4(2 * Dp);
+  const bool sample = (op.flags & VBN_SRC_MASK) == VBN_SRC_SAMPLE;
+  const bool want_lp = (op.flags & (VBN_F_ADD_LOGW | VBN_F_OUT_LOGP)) != 0;
+  rff_loc(c, op, P);
+  if (sample) {
+    for (int d = 0; d < D; ++d) {
+      float eps[RPT];
+      c.draw_normal(op, op.n_off + d, d, eps);
+      const float sc = __ldg(tail + 3 * D + d);
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) c.slot(op.out_slot + d, j) = fmaf(eps[j], sc, c.scr(Dp + d, j));
+    }
+  }
+  if (want_lp) {
+    float acc[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) acc[j] = 0.0f;
+    for (int d = 0; d < D; ++d) {
+      const float t = __ldg(tail + 4 * D + d), v = __ldg(tail + 5 * D + d);
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) acc[j] += gauss_term(c.slot(op.out_slot + d, j), c.scr(Dp + d, j), v, t);
+    }
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) acc[j] *= -0.5f;
+    commit_logp(c, op, acc);
   }
 }
 
@@ -1258,6 +1361,7 @@ __device__ __forceinline__ void run_ops(Ctx<RPT, NT, TC>& c) {
       case VBN_OP_MDN: if (HEAVY) op_mdn(c, op); break;
       case VBN_OP_SNN: if (HEAVY) op_snn(c, op); break;
       case VBN_OP_KDE: if (HEAVY) op_kde(c, op); break;
+      case VBN_OP_RFF: if (HEAVY) op_rff(c, op); break;
       case VBN_OP_TAB: op_tab(c, op); break;
       default: break;
     }

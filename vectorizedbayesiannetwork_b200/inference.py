@@ -464,7 +464,7 @@ class RaoBlackwellizedMarginalization(object):
         cpds = model_cpds(vbn)
         tc = cpds[target]
         categorical = tc.kind in ("softmax_nn", "categorical_table") and tc.output_dim == 1
-        gaussian = tc.kind in ("linear_gaussian", "gaussian_nn") and tc.output_dim == 1
+        gaussian = tc.kind in ("linear_gaussian", "gaussian_nn", "rff_gaussian") and tc.output_dim == 1
         if not (categorical or gaussian):
             return self._fallback_infer(vbn, query, reason="unsupported target CPD for RB marginalization", **kwargs)
         only = [n for n in topo if n not in desc]
@@ -562,7 +562,7 @@ class GaussianExact(_ExactBase):
         if tval is not None:
             self._last_exact = True
             return torch.ones(b, 1, device=dev), tval.unsqueeze(1).expand(b, 1, -1)
-        if not ok or cpd.kind not in ("linear_gaussian", "gaussian_nn"):
+        if not ok or cpd.kind not in ("linear_gaussian", "gaussian_nn", "rff_gaussian"):
             return self._fallback_infer(vbn, query, "gaussian_exact", **kwargs)
         ls = cpd.params(ptensor).reshape(-1, 2)  # [b or 1, {loc, scale}]
         if ls.shape[0] == 1 and b > 1:
