@@ -656,6 +656,82 @@ def ct_log_prob(c, x, parents):
 
 
 # --------------------------------------------------------------------------------------
+# categorical_embedded_softmax  (vbn/cpds/categorical_embedded_softmax.py:36-46, 280-329, 469-511)
+# -- SURVEY 8f row 3.  spec: embeddings [tensor [card_d, E] per parent dim], layers, activation,
+#    logits [D, C] (root), class_values / class_mask [D, C], parent_values [tensor per parent dim]
+# --------------------------------------------------------------------------------------
+
+
+def ces_logits(c, parents: torch.Tensor) -> torch.Tensor:
+    if parents.dim() == 2:  # :316-329
+        parents = parents.unsqueeze(1)
+    b, s, dp = parents.shape
+    flat = parents.reshape(b * s, dp)
+    d = c["output_dim"]
+    if c["input_dim"] == 0:
+        logits = c["logits"].view(1, 1, d, -1).expand(b, s, -1, -1)
+    else:
+        idx = torch.zeros(flat.shape[0], c["input_dim"], dtype=torch.long)  # :280-293
+        for k, support in enumerate(c["parent_values"]):
+            idx[:, k] = ct_map_values(flat[:, k], support.to(dtype=flat.dtype))
+        feats = torch.cat([emb[idx[:, k]] for k, emb in enumerate(c["embeddings"])], dim=-1)  # :306-314
+        logits = mlp_forward(c["layers"], c["activation"], feats).reshape(b, s, d, -1)
+    return logits.masked_fill(~c["class_mask"].view(1, 1, d, -1), -1e9)
+
+
+def ces_logits_or_root(c, parents: Optional[torch.Tensor]) -> torch.Tensor:
+    """What the exact / Rao-Blackwellized methods read: cpd._logits for a root (no mask), else
+    _logits_from_parents (rao_blackwellized_marginalization.py:163-175, categorical_exact.py:48-71)."""
+    if parents is None:
+        return c["logits"].view(1, 1, c["output_dim"], -1)
+    return ces_logits(c, parents)
+
+
+def _ces_check(c):
+    if not c["stats_ready"]:
+        raise RuntimeError("CategoricalEmbeddedSoftmaxCPD is not fitted yet.")  # :136-138
+
+
+def ces_sample(c, parents, n, noise, key):
+    _ces_check(c)
+    d = c["output_dim"]
+    if c["input_dim"] == 0:  # :471-475 (root logits are NOT masked here)
+        b = 1 if parents is None else parents.shape[0]
+        logits = c["logits"].view(1, 1, d, -1).expand(b, n, -1, -1)
+    else:
+        if parents is None:
+            raise ValueError("parents cannot be None when input_dim > 0")
+        logits = ces_logits(c, broadcast_samples(parents, n))
+    indices = noise.categorical_logits(key, logits)
+    values = c["class_values"].to(dtype=logits.dtype).view(1, 1, d, -1)
+    values = values.expand(indices.shape[0], indices.shape[1], -1, -1)
+    return values.gather(-1, indices.unsqueeze(-1)).squeeze(-1)
+
+
+def ces_log_prob(c, x, parents):
+    _ces_check(c)
+    if x.dim() <= 2:  # :490-511
+        x = ensure_2d(x)
+    if x.dim() == 2:
+        x = x.unsqueeze(1)
+    d = c["output_dim"]
+    if c["input_dim"] == 0:
+        logits = c["logits"].view(1, 1, d, -1).expand(x.shape[0], x.shape[1], -1, -1)
+    else:
+        if parents is None:
+            raise ValueError("parents cannot be None when input_dim > 0")
+        logits = ces_logits(c, broadcast_samples(parents, x.shape[1]))
+    log_probs = torch.log_softmax(logits, dim=-1)
+    x_flat = x.reshape(-1, x.shape[-1])
+    targets = torch.zeros(x_flat.shape[0], d, dtype=torch.long)
+    for k in range(d):  # :295-304
+        support = c["class_values"][k][c["class_mask"][k]].to(dtype=x_flat.dtype)
+        targets[:, k] = ct_map_values(x_flat[:, k], support)
+    targets = targets.reshape(x.shape[0], x.shape[1], d)
+    return log_probs.gather(-1, targets.unsqueeze(-1)).squeeze(-1).sum(dim=-1)
+
+
+# --------------------------------------------------------------------------------------
 # kde  (vbn/cpds/kde.py:105-182)
 # --------------------------------------------------------------------------------------
 
@@ -730,6 +806,7 @@ _SAMPLE = {
     "kde": kde_sample,
     "categorical_table": ct_sample,
     "rff_gaussian": rff_sample,
+    "categorical_embedded_softmax": ces_sample,
 }
 _LOG_PROB = {
     "linear_gaussian": lg_log_prob,
@@ -739,12 +816,15 @@ _LOG_PROB = {
     "kde": kde_log_prob,
     "categorical_table": ct_log_prob,
     "rff_gaussian": rff_log_prob,
+    "categorical_embedded_softmax": ces_log_prob,
 }
 
 
 # CPDs whose conditional is one Gaussian: read through _weight/_bias/_var or a callable _params by the
 # exact / Rao-Blackwellized methods and CPDHandle.conditional (cpd_handle.py:40-70)
 _GAUSSIAN_PARAMS = {"linear_gaussian": lg_params, "gaussian_nn": gnn_params, "rff_gaussian": rff_params}
+# categorical CPDs over strictly discrete parents: logits of the row's parent configuration
+_TABLE_LOGITS = {"categorical_table": ct_logits, "categorical_embedded_softmax": ces_logits_or_root}
 
 
 def cpd_sample(c, parents, n_samples: int, noise=None, key=("cpd",)):
@@ -978,7 +1058,7 @@ def rao_blackwellized_marginalization(spec, query, n_samples: int, noise=None, n
     w = rb_normalized_weights(logw)
     parents = _gather_parents(samples, st, t)
     c = spec["cpds"][tnode]
-    if c["kind"] in ("softmax_nn", "categorical_table"):  # _target_categorical_probs :155-194
+    if c["kind"] in ("softmax_nn",) + tuple(_TABLE_LOGITS):  # _target_categorical_probs :155-194
         if c["kind"] == "softmax_nn":
             if parents is None:
                 raw = c["root_log_probs"] if c["root_ready"] else c["logits"]
@@ -988,7 +1068,7 @@ def rao_blackwellized_marginalization(spec, query, n_samples: int, noise=None, n
                 logits = snn_logits(c, parents, b, n_particles)
             support = c["sample_values"][0]
         else:
-            logits = ct_logits(c, parents)
+            logits = _TABLE_LOGITS[c["kind"]](c, parents)
             if parents is None:
                 logits = logits.expand(b, 1, -1, -1)
             support = c["class_values"][0]
@@ -1106,13 +1186,13 @@ def categorical_exact(spec, query, n_samples: int = 512, noise=None, return_info
         out = (torch.ones(b, 1), fixed[t].unsqueeze(1).expand(b, 1, -1))
         return (*out, {"exact": True}) if return_info else out
     ok, parents = _exact_parent_tensor(st, fixed, b)
-    if not ok or c["kind"] not in ("softmax_nn", "categorical_table"):  # :106-121
+    if not ok or c["kind"] not in ("softmax_nn",) + tuple(_TABLE_LOGITS):  # :106-121
         return fallback()
     if c["kind"] == "softmax_nn":
         logits = snn_logits(c, parents, b, 1)  # includes the temperature and the root_ready branch (:48-71)
         support = c["sample_values"][0]
     else:
-        logits = ct_logits(c, parents)
+        logits = _TABLE_LOGITS[c["kind"]](c, parents)
         support = c["class_values"][0]
     probs = torch.softmax(logits, dim=-1)
     if probs.dim() == 4:
@@ -1443,6 +1523,16 @@ def cpd_spec_from_reference(cpd) -> dict:
                 "counts": g(cpd._counts), "class_values": g(cpd._class_values), "class_mask": g(cpd._class_mask),
                 "parent_values": [g(v) for v in (cpd._parent_values or [])],
                 "parent_strides": [int(v) for v in (cpd._parent_strides or [])]}
+    if name == "CategoricalEmbeddedSoftmaxCPD":
+        root = cpd.input_dim == 0
+        return {**base, "kind": "categorical_embedded_softmax", "n_classes": int(cpd.n_classes),
+                "activation": cpd.activation, "stats_ready": bool(cpd._stats_ready.item()),
+                "class_values": g(cpd._class_values), "class_mask": g(cpd._class_mask),
+                "sample_values": g(cpd._sample_values),
+                "parent_values": [g(v) for v in (cpd._parent_values or [])],
+                "logits": g(cpd._logits) if root else None,
+                "embeddings": None if root else [g(e.weight) for e in cpd.embeddings],
+                "layers": None if root else _layers_of(cpd.net)}
     raise ValueError(f"CPD type '{name}' is outside the hot-path scope")
 
 

@@ -75,7 +75,7 @@ def cpd_cases(model, spec, S=9, seed=3):
     for node, cpd in model.nodes.items():
         c = spec["cpds"][node]
         dp = c["input_dim"]
-        if c["kind"] == "categorical_table" and dp:
+        if c["kind"] in ("categorical_table", "categorical_embedded_softmax") and dp:
             pick = lambda *shape: torch.stack([v[torch.randint(0, v.numel(), shape)] for v in c["parent_values"]], dim=-1)
             variants = [pick(4), pick(4, S)]
         else:
@@ -122,6 +122,24 @@ def rff_files():
     cases += [run_case(m, spec, {"target": "b", "evidence": {"a": ev, "e": 0.5 * ev}}, 21, meth, 5) for meth in ("gexact", "rb")]
     cases += [run_case(m, spec, {"target": "d", "evidence": {"a": ev}}, 21, meth, 5) for meth in ("gexact", "rb")]
     return {"rff": {"spec": spec, "cases": cases, "cpd_cases": cpd_cases(m, spec)}}
+
+
+def embedded_files():
+    """categorical_embedded_softmax nodes:  python tests/golden/make_golden.py embedded"""
+    torch.manual_seed(7531)
+    m = refmodels.embedded_model()
+    spec = O.spec_from_reference(m)
+    t = lambda *v: torch.tensor([[float(x)] for x in v])
+    qs = [{"target": "v", "evidence": {"z": t(1, 0)}},
+          {"target": "u", "evidence": {"y": t(2, 0, 1)}},
+          {"target": "y", "evidence": {"t": t(1)}, "do": {"u": t(2)}},
+          {"target": "z", "evidence": {"u": t(0, 1, 2), "t": t(1, 1, 0)}}]
+    cases = [run_case(m, spec, q, 64, meth, 29) for q in qs for meth in ("lw", "is", "mcm", "anc")]
+    for meth in ("cexact", "rb"):
+        cases.append(run_case(m, spec, {"target": "v", "evidence": {"u": t(0, 2), "t": t(1, 0)}}, 16, meth, 5))
+        cases.append(run_case(m, spec, {"target": "u", "evidence": {}}, 16, meth, 5))
+        cases.append(run_case(m, spec, {"target": "y", "evidence": {"t": t(1, 0)}}, 16, meth, 5))
+    return {"embedded": {"spec": spec, "cases": cases, "cpd_cases": cpd_cases(m, spec)}}
 
 
 def exact_files():
@@ -262,6 +280,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "ris":
         save(ris_files())
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "embedded":
+        save(embedded_files())
         return
     if len(sys.argv) > 1 and sys.argv[1] == "rff":
         save(rff_files())

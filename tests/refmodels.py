@@ -189,6 +189,33 @@ def rff_model(rows=600, seed=0):
     return _fit(g, cpds, {"a": a, "e": e, "b": b, "c": c, "d": d})
 
 
+def embedded_model(rows=700, epochs=4, seed=0):
+    """categorical_embedded_softmax nodes (vbn/cpds/categorical_embedded_softmax.py) in a discrete BN with a
+    categorical_table root and a discrete softmax_nn node:
+    u(ces root,3) -> v(ces,4) <- t(ct,2) ;  v -> y(ces, n_classes given) ; u -> y ; y -> z(snn,2)."""
+    import networkx as nx
+
+    gen = torch.Generator().manual_seed(seed)
+    g = nx.DiGraph()
+    g.add_edges_from([("u", "v"), ("t", "v"), ("v", "y"), ("u", "y"), ("y", "z")])
+    ri = lambda k: torch.randint(0, k, (rows,), generator=gen)
+    u = ri(3)
+    t = ri(2)
+    v = (u + 2 * t + (torch.rand(rows, generator=gen) < 0.25).long()) % 4
+    y = ((v + u) % 3 + (torch.rand(rows, generator=gen) < 0.2).long()) % 3
+    z = ((y > 0) & (torch.rand(rows, generator=gen) < 0.7)).long()
+    fit = {"epochs": epochs, "batch_size": 128}
+    cpds = {
+        "u": {"cpd": "categorical_embedded_softmax", "fit": fit},
+        "t": {"cpd": "categorical_table"},
+        "v": {"cpd": "categorical_embedded_softmax", "embedding_dim": 4, "hidden_dims": [16, 16], "fit": fit},
+        "y": {"cpd": "categorical_embedded_softmax", "n_classes": 3, "activation": "tanh", "fit": fit},
+        "z": {"cpd": "softmax_nn", "n_classes": 2, "fit": fit},
+    }
+    data = {k: x.float()[:, None] for k, x in {"u": u, "t": t, "v": v, "y": y, "z": z}.items()}
+    return _fit(g, cpds, data)
+
+
 def binned_model(within_bin="uniform", clip=False, rows=400, epochs=3, seed=0, dim=2):
     """softmax_nn in binned-continuous mode, root + child, D=dim."""
     import networkx as nx

@@ -122,6 +122,34 @@ def test_categorical_table_model():
         O.likelihood_weighting(spec, {"target": "slip", "evidence": {"rain": torch.tensor([[0.5]])}}, 8)
 
 
+def test_categorical_embedded_softmax_model():
+    """categorical_embedded_softmax (vbn/cpds/categorical_embedded_softmax.py:280-329, 469-511)."""
+    model = refmodels.embedded_model()
+    spec = O.spec_from_reference(model)
+    _run_methods(model, spec, {"target": "v", "evidence": {"z": torch.tensor([[1.0], [0.0]])}}, 64)
+    _run_methods(model, spec, {"target": "u", "evidence": {"y": torch.tensor([[2.0], [0.0], [1.0]])}}, 64)
+    _run_methods(model, spec, {"target": "y", "evidence": {"t": torch.tensor([[1.0]])}, "do": {"u": torch.tensor([[2.0]])}}, 64)
+    for name in ("categorical_exact", "rao_blackwellized_marginalization"):
+        fn = getattr(O, name)
+        _exact_eq(model, spec, name, {"target": "v", "evidence": {"u": torch.tensor([[0.0], [2.0]]), "t": torch.tensor([[1.0], [0.0]])}}, 16, fn)
+        _exact_eq(model, spec, name, {"target": "u", "evidence": {}}, 16, fn)  # root: unmasked _logits
+        _exact_eq(model, spec, name, {"target": "y", "evidence": {"t": torch.tensor([[1.0], [0.0]])}}, 16, fn)
+    with pytest.raises(ValueError):  # parent value outside the support (:36-46)
+        O.likelihood_weighting(spec, {"target": "y", "evidence": {"v": torch.tensor([[0.5]])}}, 8)
+    for node, cpd in model.nodes.items():
+        c = spec["cpds"][node]
+        if c["kind"] != "categorical_embedded_softmax":
+            continue
+        parents = None
+        if cpd.input_dim:
+            parents = torch.stack([v[torch.randint(0, v.numel(), (5,))] for v in cpd._parent_values], dim=1)
+        torch.manual_seed(3)
+        rs = cpd.sample(parents, 6)
+        torch.manual_seed(3)
+        _eq(rs, O.cpd_sample(c, parents, 6))
+        _eq(cpd.log_prob(rs, parents), O.cpd_log_prob(c, rs, parents))
+
+
 def test_rff_gaussian_model():
     """rff_gaussian (vbn/cpds/rff_gaussian.py:131-146, 185-206, 254-291): root, 1-D and 2-D nodes."""
     model = refmodels.rff_model()

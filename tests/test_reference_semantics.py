@@ -519,6 +519,33 @@ def test_categorical_table_strict_support_and_conditional(backend):
     torch.testing.assert_close(probs, want.reshape(probs.shape), rtol=1e-5, atol=1e-7)
 
 
+# ---- categorical_embedded_softmax (vbn/cpds/categorical_embedded_softmax.py) --------
+def test_categorical_embedded_softmax_strict_support_conditional_and_frequencies(backend):
+    import os
+
+    spec = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "embedded.pt"),
+                      weights_only=False)["spec"]
+    model = V.VBN.from_spec(spec, device=backend.device)
+    model.set_inference_method("likelihood_weighting", n_samples=16)
+    with pytest.raises(ValueError):  # "y" embeds (v, u): an off-support v must raise (:36-46)
+        model.infer_posterior({"target": "z", "do": {"v": torch.tensor([[0.5]])}})
+    pa = torch.tensor([[1.0, 0.0], [3.0, 2.0]])  # parents of y in DAG order
+    order = spec["parents"]["y"]
+    out = model.get_cpd("y").conditional({order[0]: pa[:, :1], order[1]: pa[:, 1:]})
+    assert out["format"] == "categorical_probs" and out["k"] == 3
+    probs = torch.tensor(out["probs"])
+    want = torch.softmax(O.ces_logits(spec["cpds"]["y"], pa), dim=-1)
+    torch.testing.assert_close(probs, want.reshape(probs.shape), rtol=2e-5, atol=1e-7)
+    # Philox path: class frequencies of a long draw follow the conditional
+    cpd = V.cpd_from_spec(spec["cpds"]["y"], device=backend.device)
+    s = cpd.sample(pa[:1], 30000, seed=3).cpu().reshape(-1)
+    freq = torch.stack([(s == float(k)).float().mean() for k in range(3)])
+    assert (freq - want[0].reshape(-1)).abs().max().item() < 0.015
+    unfitted = dict(spec["cpds"]["y"], stats_ready=False)
+    with pytest.raises(RuntimeError):  # :136-138
+        V.cpd_from_spec(unfitted, device=backend.device).sample(pa, 4)
+
+
 # ---- resampled_importance_sampling (vbn/inference/resampled_importance_sampling.py) ----------------
 def test_resampled_importance_sampling_philox_path(backend):
     spec = S.lg_chain(8)

@@ -8,7 +8,7 @@ libvbn_cuda.so."""
 from . import inference as _inference  # noqa: F401  (populates the registries)
 from .core import (INFERENCE_REGISTRY, SAMPLING_REGISTRY, ConfigItem, CPDOutput, Query, StaticDAG, VBN)
 from .cpd_handle import CPDHandle
-from .cpds import (BaseCPD, GaussianNNCPD, KDECPD, LinearGaussianCPD, MDNCPD, RFFGaussianCPD, SoftmaxNNCPD,
+from .cpds import (BaseCPD, CategoricalEmbeddedSoftmaxCPD, CategoricalTableCPD, GaussianNNCPD, KDECPD, LinearGaussianCPD, MDNCPD, RFFGaussianCPD, SoftmaxNNCPD,
                    cpd_from_spec, wrap_cpd)
 from .dist import Shard, auto_shard
 from .inference import (AncestralSampler, CategoricalExact, GaussianExact, ImportanceSampling,
@@ -19,7 +19,7 @@ from .install import install, uninstall
 __all__ = [
     "VBN", "Query", "CPDOutput", "StaticDAG", "ConfigItem", "CPDHandle",
     "INFERENCE_REGISTRY", "SAMPLING_REGISTRY",
-    "BaseCPD", "LinearGaussianCPD", "GaussianNNCPD", "MDNCPD", "SoftmaxNNCPD", "KDECPD", "RFFGaussianCPD",
+    "BaseCPD", "LinearGaussianCPD", "GaussianNNCPD", "MDNCPD", "SoftmaxNNCPD", "KDECPD", "RFFGaussianCPD", "CategoricalTableCPD", "CategoricalEmbeddedSoftmaxCPD",
     "cpd_from_spec", "wrap_cpd",
     "ImportanceSampling", "LikelihoodWeighting", "MonteCarloMarginalization", "AncestralSampler",
     "GaussianExact", "CategoricalExact", "ResampledImportanceSampling", "RaoBlackwellizedMarginalization",

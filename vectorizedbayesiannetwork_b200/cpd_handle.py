@@ -9,7 +9,7 @@ from typing import Optional
 import torch
 
 from .core import CPDOutput, ensure_2d, ensure_tensor
-from .cpds import wrap_cpd
+from .cpds import TABLE_KINDS, wrap_cpd
 
 
 def _to_serializable(obj, *, max_tensor_elems: int = 2048):
@@ -120,7 +120,7 @@ class CPDHandle:
                 "cpd_type": self.cpd_type, "input_dim": self.input_dim, "output_dim": self.output_dim,
                 "conditioning": _to_serializable(ptensor)}
         cpd, d = self._cpd, self.x_dim
-        if cpd.kind == "categorical_table":  # the CPD's parameters are the table: a host-side lookup
+        if cpd.kind in TABLE_KINDS:  # the CPD's parameters are the table: a host-side lookup
             rows = cpd.probs(ptensor)
             return {**base, "format": "categorical_probs", "probs": _to_serializable(rows),
                     "k": int(cpd.n_classes), "support": _to_serializable(cpd._sample_values)}

@@ -719,6 +719,117 @@ class CategoricalTableCPD(BaseCPD):
 
 
 # ------------------------------------------------------------------------------------------
+class CategoricalEmbeddedSoftmaxCPD(CategoricalTableCPD):
+    """vbn/cpds/categorical_embedded_softmax.py:49-511: a categorical CPD whose logits are
+    MLP(concat of per-parent embeddings).  Its parents are strictly discrete (:36-46, :280-293), so there is one
+    logit vector per parent configuration: the CPD compiles to the same lookup op as categorical_table
+    (VBN_OP_TAB, strict parent support).  The table is evaluated ONCE, through this library's GPU MLP path,
+    over all configurations; D = 1 on the GPU path."""
+
+    kind = "categorical_embedded_softmax"
+
+    def __init__(self, input_dim, output_dim, *, n_classes, class_values, class_mask, parent_values=(),
+                 embeddings=None, layers=None, logits=None, activation="relu", stats_ready: bool = True, device=None):
+        BaseCPD.__init__(self, input_dim, output_dim, device)
+        d = self.output_dim
+        self.n_classes = int(n_classes)
+        self.activation = str(activation)
+        self._stats_ready = bool(stats_ready)
+        self._class_values = _f32(class_values).reshape(d, -1)
+        self._sample_values = self._class_values  # categorical_embedded_softmax.py:357-360
+        self._class_mask = torch.as_tensor(class_mask).detach().cpu().bool().reshape(d, -1)
+        self._parent_values = [_f32(v).reshape(-1) for v in parent_values]
+        if len(self._parent_values) != self.input_dim:
+            raise ValueError("categorical_embedded_softmax needs one support vector per parent dim")
+        cards = [int(v.numel()) for v in self._parent_values]
+        strides, acc = [], 1
+        for card in reversed(cards):  # our own configuration index: last parent fastest
+            strides.append(acc)
+            acc *= card
+        self._parent_strides = strides[::-1]
+        if self.input_dim == 0:
+            self._logits = _f32(logits).reshape(d, -1)
+            self.embeddings, self.layers = None, None
+        else:
+            self._logits = None
+            self.embeddings = [_f32(e) for e in embeddings]
+            self.layers = [(_f32(w), _f32(b)) for w, b in layers]
+        self._table: Optional[torch.Tensor] = None
+
+    def invalidate(self) -> None:
+        super().invalidate()
+        self._table = None
+
+    def logits_table(self) -> torch.Tensor:
+        """[n_cfg, C] log-probabilities log_softmax(masked logits) of every parent configuration."""
+        if not self._stats_ready:  # :136-138
+            raise RuntimeError("CategoricalEmbeddedSoftmaxCPD is not fitted yet.")
+        if self._table is not None:
+            return self._table
+        if self.output_dim != 1:
+            raise ValueError("categorical_embedded_softmax with output_dim > 1 has no CUDA implementation yet")
+        c = self.n_classes
+        if self.input_dim == 0:
+            # root parameters (:471-475, :497-500): a [1, C] parameter transform, like categorical_table's counts
+            self._table = torch.log_softmax(self._logits[:1], dim=-1)
+            return self._table
+        if not bool(self._class_mask[0].all()):
+            raise ValueError("categorical_embedded_softmax with padded classes has no CUDA implementation yet")
+        cards = [int(v.numel()) for v in self._parent_values]
+        n_cfg = int(np.prod(cards))
+        if n_cfg > TABLE_MAX_CONFIGS:
+            raise ValueError(f"categorical_embedded_softmax: {n_cfg} parent configurations exceed {TABLE_MAX_CONFIGS}")
+        grid = torch.cartesian_prod(*[torch.arange(k) for k in cards]).reshape(n_cfg, len(cards))
+        feats = torch.cat([emb[grid[:, k]] for k, emb in enumerate(self.embeddings)], dim=-1)  # :306-314
+        # the MLP forward + log_softmax run on the GPU: a discrete-mode softmax_nn over the embedded features
+        # has exactly this density (softmax_nn.py:581-759 with temperature 1, discrete dims add no within-bin term)
+        ar = torch.arange(c, dtype=torch.float32).reshape(1, c)
+        net = SoftmaxNNCPD(feats.shape[1], 1, c, layers=self.layers, bin_edges=torch.arange(c + 1).float().reshape(1, -1) - 0.5,
+                           class_values=ar, sample_values=ar, is_discrete=torch.ones(1, dtype=torch.bool),
+                           activation=self.activation, device=self.device)
+        from .engine import cpd_log_prob
+
+        cols = [_f32(cpd_log_prob(net, torch.full((n_cfg, 1), float(k)), feats)).reshape(n_cfg) for k in range(c)]
+        self._table = torch.stack(cols, dim=1)
+        return self._table
+
+    def _pack(self) -> Packed:
+        logp = self.logits_table()
+        if self.n_classes > TABLE_MAX_CLASSES or any(v.numel() > TABLE_MAX_CLASSES for v in self._parent_values):
+            raise ValueError(f"categorical_embedded_softmax supports at most {TABLE_MAX_CLASSES} classes per variable on the GPU")
+        params = _tab_params(self.n_classes, logp, self._parent_values, self._parent_strides,
+                             self._class_values[0], torch.where(self._class_mask[0], self._class_values[0],
+                                                                torch.full_like(self._class_values[0], float("nan"))),
+                             strict=True)
+        return Packed(kind=L.OP_TAB, dim=1, n_par=self.input_dim, params=params, k=self.n_classes,
+                      n_normals=0, n_uniforms=1, scratch=0, heavy=False)
+
+    @classmethod
+    def from_spec(cls, c, device=None):
+        return cls(c["input_dim"], c["output_dim"], n_classes=c["n_classes"], class_values=c["class_values"],
+                   class_mask=c["class_mask"], parent_values=c.get("parent_values", ()),
+                   embeddings=c.get("embeddings"), layers=c.get("layers"), logits=c.get("logits"),
+                   activation=c.get("activation", "relu"), stats_ready=c.get("stats_ready", True), device=device)
+
+    @classmethod
+    def from_reference(cls, cpd, device=None):
+        root = cpd.input_dim == 0
+        return cls(cpd.input_dim, cpd.output_dim, n_classes=cpd.n_classes, class_values=cpd._class_values,
+                   class_mask=cpd._class_mask, parent_values=cpd._parent_values or (),
+                   embeddings=None if root else [e.weight for e in cpd.embeddings],
+                   layers=None if root else _layers_from_module(cpd.net),
+                   logits=cpd._logits if root else None, activation=cpd.activation,
+                   stats_ready=bool(cpd._stats_ready.item()), device=device)
+
+    def to_spec(self):
+        return {"kind": self.kind, "input_dim": self.input_dim, "output_dim": self.output_dim,
+                "n_classes": self.n_classes, "activation": self.activation, "stats_ready": self._stats_ready,
+                "class_values": self._class_values, "class_mask": self._class_mask,
+                "sample_values": self._sample_values, "parent_values": self._parent_values,
+                "logits": self._logits, "embeddings": self.embeddings, "layers": self.layers}
+
+
+# ------------------------------------------------------------------------------------------
 # discrete-parent lookup tables (VBN_OP_TAB)
 # ------------------------------------------------------------------------------------------
 _TABLE_CACHE: Dict[tuple, Packed] = {}
@@ -726,6 +837,7 @@ TABLE_MAX_CONFIGS = 4096
 
 
 TABLE_MAX_CLASSES = 64
+TABLE_KINDS = ("categorical_table", "categorical_embedded_softmax")  # CPDs whose parameters ARE a lookup table
 
 
 def _is_plain_discrete(cpd) -> bool:
@@ -816,6 +928,7 @@ CPD_CLASSES = {
     "kde": KDECPD,
     "categorical_table": CategoricalTableCPD,
     "rff_gaussian": RFFGaussianCPD,
+    "categorical_embedded_softmax": CategoricalEmbeddedSoftmaxCPD,
 }
 
 _REFERENCE_CLASS_NAMES = {
@@ -826,6 +939,7 @@ _REFERENCE_CLASS_NAMES = {
     "KDECPD": KDECPD,
     "CategoricalTableCPD": CategoricalTableCPD,
     "RFFGaussianCPD": RFFGaussianCPD,
+    "CategoricalEmbeddedSoftmaxCPD": CategoricalEmbeddedSoftmaxCPD,
 }
 
 

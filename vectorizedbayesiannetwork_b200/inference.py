@@ -18,6 +18,7 @@ import torch
 
 from . import engine as E
 from .core import (Query, infer_batch_size, model_cpds, register_inference, register_sampling)
+from .cpds import TABLE_KINDS
 from .dist import Shard, gather_stats
 from .plan import Role, compile_schedule
 
@@ -376,7 +377,7 @@ class ResampledImportanceSampling:
                         logw.zero_()
                         self._last_resampled = True
             cpds = model_cpds(vbn)
-            if any(c.kind in ("softmax_nn", "categorical_table") for c in cpds.values()) and int(flag_dev.item()) != 0:
+            if any(c.kind in ("softmax_nn",) + TABLE_KINDS for c in cpds.values()) and int(flag_dev.item()) != 0:
                 raise ValueError("Found values outside discrete class set.")
             stats = E.lse_stats(logw)
             w, _ = E.normalize_weights(logw, stats)
@@ -463,7 +464,7 @@ class RaoBlackwellizedMarginalization(object):
             return torch.ones(b, 1, device=dev), v.unsqueeze(1).expand(b, 1, -1)
         cpds = model_cpds(vbn)
         tc = cpds[target]
-        categorical = tc.kind in ("softmax_nn", "categorical_table") and tc.output_dim == 1
+        categorical = tc.kind in ("softmax_nn",) + TABLE_KINDS and tc.output_dim == 1
         gaussian = tc.kind in ("linear_gaussian", "gaussian_nn", "rff_gaussian") and tc.output_dim == 1
         if not (categorical or gaussian):
             return self._fallback_infer(vbn, query, reason="unsupported target CPD for RB marginalization", **kwargs)
@@ -593,7 +594,7 @@ class CategoricalExact(_ExactBase):
         if tval is not None:
             self._last_exact = True
             return torch.ones(b, 1, device=dev), tval.unsqueeze(1).expand(b, 1, -1)
-        if not ok or cpd.kind not in ("softmax_nn", "categorical_table") or cpd.output_dim != 1:
+        if not ok or cpd.kind not in ("softmax_nn",) + TABLE_KINDS or cpd.output_dim != 1:
             return self._fallback_infer(vbn, query, "categorical_exact", **kwargs)
         if cpd.kind == "softmax_nn":
             probs = cpd.params(ptensor).reshape(-1, cpd.n_classes)
