@@ -48,11 +48,21 @@ extern "C" {
 #define VBN_OP_RFF 7     /* vbn/cpds/rff_gaussian.py:131-146,185-206,254-291: random Fourier features,
                             loc = (sqrt(2/F) cos(z W^T + b)) coef + bias, de-standardised; constant scale */
 
+/* Gibbs sweeps (vbn/sampling/gibbs.py:38-82): candidates and their scores are ordinary CPD ops; these
+ * glue them together.  One row = one chain. */
+#define VBN_OP_TAKEW 8   /* slot[out_slot] = accumulated log-weight of the row; log-weight = 0          */
+#define VBN_OP_SELECT 9  /* draw c ~ softmax(slots aux[0] .. aux[0]+k-1) (gibbs.py:76-77), copy candidate
+                            c (slots aux[1] + c*dim ..) to out_slot; u from u_off or noise idx           */
+#define VBN_OP_JUMP 10   /* back to op aux[0] until the loop has run k times; layer_dim[0], [1] = Philox
+                            stream blocks (normal, uniform) one iteration consumes                      */
+
 /* ---- op flags ------------------------------------------------------------------------ */
 #define VBN_SRC_MASK 0x3
 #define VBN_SRC_SAMPLE 0x0     /* draw x ~ p(x | parents)                                    */
 #define VBN_SRC_FIXED_Q 0x1    /* x = fixed[fixed_col + d][b]   (evidence / do, per query)   */
 #define VBN_SRC_FIXED_ROW 0x2  /* x = inputs[fixed_col] element (r, d)  (per row, CPD API)   */
+#define VBN_SRC_SLOT 0x3       /* x = the value another op left in slots fixed_col .. (Gibbs: a child's
+                                  current state, scored under a candidate parent value)       */
 #define VBN_F_ADD_LOGW 0x4     /* logw[r] += log p(x | parents)  (evidence node)             */
 #define VBN_F_OUT_LOGP 0x8     /* logp[r]  = log p(x | parents)  (MCM target, CPD.log_prob)  */
 #define VBN_F_SHARED 0x10      /* draw is shared by all queries: noise keyed by s, not (b,s) */
@@ -119,6 +129,8 @@ typedef struct VbnOp {
   int32_t k;          /* MDN: components K; SNN: classes C; KDE: stored points N           */
   int32_t layer_dim[VBN_MAX_LAYERS]; /* widths after each Linear layer (last == n_out)      */
   int32_t aux[4];     /* SNN: {within_bin, clip, any_discrete, 0}                          */
+  /* injected draws only: tc[1] > 1 = this op replays member tc[2] of a group of tc[1] draws the reference
+     made in one call (Gibbs candidates); arrays inside a VBN_OP_JUMP loop carry a leading iteration axis */
   int32_t tc[4];      /* tensor-core MLP image (hidden dims [32,32], Dp <= 32, O <= 32), written by
                          the plan compiler: {1 if present, float offset of the image in the
                          parameter blob (16-byte aligned), K1 = Dp padded to 8, N3 = O padded to 16};

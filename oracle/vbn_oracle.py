@@ -1287,6 +1287,69 @@ def ancestral_sample(spec, query, n_samples: int, noise=None):
 
 
 # --------------------------------------------------------------------------------------
+# Gibbs sampler (vbn/sampling/gibbs.py:23-92) -- SURVEY 8f row 4
+# --------------------------------------------------------------------------------------
+
+
+def spec_children(spec) -> Dict[str, List[str]]:
+    """Children of every node in dag.edges() order (_core.py:84-93).  Specs written before the key existed
+    fall back to (child in node order, parent in parent order), which is networkx's order for DAGs built
+    with add_edges_from in that order."""
+    if "children" in spec:
+        return spec["children"]
+    out: Dict[str, List[str]] = {n: [] for n in spec["nodes"]}
+    for p in spec["nodes"]:
+        for c in spec["nodes"]:
+            if p in spec["parents"][c]:
+                out[p].append(c)
+    return out
+
+
+def gibbs_sample(spec, query, n_samples: int, noise=None, burn_in: int = 10, n_steps: int = 1,
+                 n_candidates: int = 8):
+    """One chain per query.  Per step and latent node: n_candidates proposals from the node's own CPD given the
+    current parents, scored by their own log-density plus the log-density of every child's current value with the
+    proposal substituted, one of them drawn by softmax (gibbs.py:38-82).  The target is collected every
+    max(n_steps, 1) steps after burn_in -- as views of the live state, so the returned [B, n, D] tensor holds the
+    chain's final target value n times (reference behaviour, reproduced)."""
+    query = _norm_query(query)
+    noise = noise or TorchNoise()
+    b = infer_batch_size(query["evidence"], query["do"])
+    current, st = ancestral_sample_tensor(spec, query, 1, noise, scope="gibbs_init")  # :32
+    fixed = _fixed_values(query, st, torch.float32, clamp_obs=False)
+    children = spec_children(spec)
+    latent = [i for i in range(len(st.topo)) if fixed[i] is None]
+    total_steps = int(burn_in) + int(n_samples) * max(int(n_steps), 1)
+    k = int(n_candidates)
+    collected = []
+    for step in range(total_steps):
+        for idx in latent:
+            node = st.topo[idx]
+            c = spec["cpds"][node]
+            parents = _gather_parents(current, st, idx)
+            if parents is not None and parents.shape[1] != k:
+                parents = parents.expand(b, k, -1)
+            cand = cpd_sample(c, parents, k, noise, ("gibbs", node))
+            score = cpd_log_prob(c, cand, parents)
+            for child in children[node]:
+                ci = st.node_to_idx[child]
+                cval = current[..., st.slices[ci]].expand(b, k, -1)
+                parts = [cand if p == idx else current[..., st.slices[p]].expand(b, k, -1) for p in st.parent_idx[ci]]
+                score = score + cpd_log_prob(spec["cpds"][child], cval, torch.cat(parts, dim=-1) if parts else None)
+            weights = torch.softmax(score, dim=1)
+            choice = noise.multinomial(("gibbs", node, "choice"), weights)
+            chosen = cand[torch.arange(b), choice]
+            current[..., st.slices[idx]] = chosen.unsqueeze(1)
+        if step >= burn_in and (step - burn_in) % max(int(n_steps), 1) == 0:
+            # QUIRK kept on purpose: the reference appends a VIEW of `current` (gibbs.py:83-87), which the later
+            # in-place updates keep rewriting -- every collected entry ends up equal to the FINAL state
+            collected.append(current[..., st.slices[st.target_idx]])
+    if not collected:
+        return current[..., st.slices[st.target_idx]]
+    return torch.cat(collected, dim=1)
+
+
+# --------------------------------------------------------------------------------------
 # monte-carlo marginalisation (vbn/inference/monte_carlo_marginalization.py:18-92)
 # --------------------------------------------------------------------------------------
 
@@ -1544,4 +1607,6 @@ def spec_from_reference(vbn) -> dict:
         "parents": {n: list(vbn.dag.parents(n)) for n in nodes},
         "topo": list(vbn.dag.topological_order()),
         "cpds": {n: cpd_spec_from_reference(vbn.nodes[n]) for n in nodes},
+        # children in dag.edges() order (what _core.py:84-93 iterates; only the Gibbs sampler reads it)
+        "children": {n: [c for p, c in vbn.dag.edges() if p == n] for n in nodes},
     }

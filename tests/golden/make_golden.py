@@ -142,6 +142,46 @@ def embedded_files():
     return {"embedded": {"spec": spec, "cases": cases, "cpd_cases": cpd_cases(m, spec)}}
 
 
+def gibbs_case(model, spec, query, n, seed, **kw):
+    q = {"target": query["target"], "evidence": query.get("evidence", {}), "do": query.get("do", {})}
+    model.set_sampling_method("gibbs", n_samples=n, **kw)
+    torch.manual_seed(seed)
+    ref = model.sample(q, n_samples=n).detach()
+    rec = O.RecordingNoise()
+    torch.manual_seed(seed)
+    ora = O.gibbs_sample(spec, q, n, noise=rec, **kw)
+    assert _same(ref, ora)
+    return {"query": q, "n": n, "kw": kw, "noise": log_to_strkeys(rec.log), "expect": ref}
+
+
+def gibbs_file():
+    """Gibbs sampler: chains recorded from the reference, per model kind:
+    python tests/golden/make_golden.py gibbs"""
+    torch.manual_seed(1593)
+    out = []
+    m = refmodels.readme_model(n=300, epochs=2)
+    spec = O.spec_from_reference(m)
+    cases = [gibbs_case(m, spec, {"target": "feature_2", "evidence": {"feature_0": torch.tensor([[0.3]]), "feature_1": torch.tensor([[-0.2]])}}, 12, 3),
+             gibbs_case(m, spec, {"target": "feature_0", "evidence": {"feature_2": torch.tensor([[0.1]])}}, 9, 4, burn_in=3, n_steps=2)]
+    out.append({"name": "readme", "spec": spec, "cases": cases})
+    m = refmodels.lg_chain_model(n_nodes=5)
+    spec = O.spec_from_reference(m)
+    cases = [gibbs_case(m, spec, {"target": "x2", "evidence": {"x4": torch.tensor([[0.7]])}}, 10, 5, burn_in=4),
+             gibbs_case(m, spec, {"target": "x3", "evidence": {"x0": torch.tensor([[0.2], [1.0], [-0.7]])}}, 6, 6, burn_in=2)]
+    out.append({"name": "lg_chain", "spec": spec, "cases": cases})
+    m = refmodels.mixed_model(rows=256, epochs=1)
+    spec = O.spec_from_reference(m)
+    out.append({"name": "mixed", "spec": spec,
+                "cases": [gibbs_case(m, spec, {"target": "e", "evidence": {"g": torch.tensor([[0.3, -0.2]])}}, 5, 7, burn_in=2)]})
+    m = refmodels.table_model(rows=300, epochs=1)
+    spec = O.spec_from_reference(m)
+    out.append({"name": "table", "spec": spec,
+                "cases": [gibbs_case(m, spec, {"target": "rain", "evidence": {"slip": torch.tensor([[1.0]])}}, 7, 8, burn_in=2)]})
+    path = os.path.join(HERE, "gibbs.pt")
+    torch.save({"models": out}, path)
+    print(f"gibbs: {sum(len(m['cases']) for m in out)} cases, {os.path.getsize(path)/1024:.0f} KiB")
+
+
 def exact_files():
     """gaussian_exact / categorical_exact, incl. their likelihood-weighting fallbacks:
     python tests/golden/make_golden.py exact"""
@@ -280,6 +320,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "ris":
         save(ris_files())
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "gibbs":
+        gibbs_file()
         return
     if len(sys.argv) > 1 and sys.argv[1] == "embedded":
         save(embedded_files())

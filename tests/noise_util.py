@@ -30,3 +30,24 @@ def log_to_strkeys(log):
 
 def log_from_strkeys(d):
     return {tuple(k.split("|")): v for k, v in d.items()}
+
+
+def gibbs_injection(log, spec):
+    """RecordingNoise log of oracle.gibbs_sample -> {"init": {node: {...}}, "cand": {node: {...}}, "choice": {node: {"idx"}}}.
+    "cand" arrays keep the reference's call shape with a leading sweep axis: [T, B, 8, D] (eps / u / softmax_nn idx) or
+    [T, B, 8] (idx); "choice" is [T, B]."""
+    out = {"init": {}, "cand": {}, "choice": {}}
+    for key, lst in log.items():
+        scope, node = key[0], key[1]
+        kind = key[-1]
+        dt = torch.float32 if kind in ("eps", "u") else torch.int32
+        if scope == "gibbs_init":
+            d = int(spec["cpds"][node]["output_dim"])
+            t = lst[0].to(dt)
+            t = t.reshape(-1, 1, d) if kind in ("eps", "u") or spec["cpds"][node]["kind"] == "softmax_nn" else t.reshape(-1, 1)
+            out["init"].setdefault(node, {})[kind] = t.contiguous()
+        elif len(key) == 4:  # ("gibbs", node, "choice", "idx")
+            out["choice"].setdefault(node, {})["idx"] = torch.stack([x.reshape(-1) for x in lst]).to(torch.int32).contiguous()
+        else:
+            out["cand"].setdefault(node, {})[kind] = torch.stack([x.reshape(-1) for x in lst]).to(dt).contiguous()
+    return out

@@ -335,3 +335,29 @@ def test_posterior_summaries_of_the_benchmark_adapter():
         x = torch.randn(1, s, 1, generator=g)
         for w in (None, torch.rand(1, s, generator=g), torch.zeros(1, s), torch.rand(1, s, generator=g) - 0.5):
             assert model._continuous_from_samples(x, weights=w) == O.continuous_from_samples(x, weights=w)
+
+
+def test_gibbs_sampler():
+    """vbn/sampling/gibbs.py:23-92: same torch seed -> the same chain, bit for bit."""
+    def run(model, spec, q, n, **kw):
+        model.set_sampling_method("gibbs", n_samples=n, **kw)
+        torch.manual_seed(21)
+        ref = model.sample(q, n_samples=n)
+        torch.manual_seed(21)
+        got = O.gibbs_sample(spec, {"target": q["target"], "evidence": q.get("evidence", {}), "do": q.get("do", {})}, n, **kw)
+        _eq(ref, got)
+
+    m = refmodels.readme_model(n=300, epochs=2)
+    spec = O.spec_from_reference(m)
+    run(m, spec, {"target": "feature_2", "evidence": {"feature_0": torch.tensor([[0.3]]), "feature_1": torch.tensor([[-0.2]])}}, 12)
+    run(m, spec, {"target": "feature_0", "evidence": {"feature_2": torch.tensor([[0.1]])}}, 9, burn_in=3, n_steps=2)
+    m = refmodels.lg_chain_model(n_nodes=5)
+    spec = O.spec_from_reference(m)
+    run(m, spec, {"target": "x2", "evidence": {"x4": torch.tensor([[0.7]])}}, 10, burn_in=4)
+    run(m, spec, {"target": "x3", "evidence": {"x0": torch.tensor([[0.2], [1.0], [-0.7]])}}, 6, burn_in=2)  # B = 3, no latent root
+    m = refmodels.mixed_model(rows=256, epochs=1)
+    spec = O.spec_from_reference(m)
+    run(m, spec, {"target": "e", "evidence": {"g": torch.tensor([[0.3, -0.2]])}}, 5, burn_in=2)
+    m = refmodels.table_model(rows=300, epochs=1)
+    spec = O.spec_from_reference(m)
+    run(m, spec, {"target": "rain", "evidence": {"slip": torch.tensor([[1.0]])}}, 7, burn_in=2)

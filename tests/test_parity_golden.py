@@ -9,13 +9,13 @@ import pytest
 import torch
 
 from backends import backend  # noqa: F401
-from noise_util import log_from_strkeys, to_injection
+from noise_util import gibbs_injection, log_from_strkeys, to_injection
 from oracle import vbn_oracle as O
 
 import vectorizedbayesiannetwork_b200 as V
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-NOT_MODELS = {"summaries"}  # fixtures that are not (model, cases) files
+NOT_MODELS = {"summaries", "gibbs"}  # fixtures that are not (model, cases) files
 FILES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, "*.pt"))
                if os.path.basename(p)[:-3] not in NOT_MODELS)
 RTOL, ATOL = 1e-5, 1e-6
@@ -154,3 +154,22 @@ def test_posterior_summaries_argument_errors(backend):
         SM._continuous_from_samples(torch.zeros(4, 2, device=backend.device))
     probs = SM._estimate_discrete_posterior_batch(x, w, 3)  # every sample is class 0
     assert probs == [[1.0, 0.0, 0.0], [1.0, 0.0, 0.0]]
+
+
+# ---- Gibbs sampler ---------------------------------------------------------------
+def test_gibbs_chains_match_reference(backend):
+    """vbn/sampling/gibbs.py:23-92: chains recorded from the reference (gibbs.pt), replayed with the reference's own
+    draws (initial ancestral state, 8 candidates per latent node and sweep, the selected candidate)."""
+    for m in _load("gibbs")["models"]:
+        spec = m["spec"]
+        model = V.VBN.from_spec(spec, device=backend.device)
+        atol = max(ATOL, _dot_floor(spec))
+        for i, case in enumerate(m["cases"]):
+            inj = gibbs_injection(log_from_strkeys(case["noise"]), spec)
+            noise = {scope: {n: {k: t.to(backend.device) for k, t in d.items()} for n, d in nodes.items()}
+                     for scope, nodes in inj.items()}
+            model.set_sampling_method("gibbs", n_samples=case["n"], **case["kw"])
+            got = model.sample(case["query"], n_samples=case["n"], noise=noise)
+            _close(got, case["expect"], f"gibbs:{m['name']}[{i}]", atol=atol)
+            # the reference returns the chain's final state n times (views of the live state, gibbs.py:83-91)
+            assert bool((got == got[:, :1]).all())

@@ -546,6 +546,34 @@ def test_categorical_embedded_softmax_strict_support_conditional_and_frequencies
         V.cpd_from_spec(unfitted, device=backend.device).sample(pa, 4)
 
 
+# ---- Gibbs sampler (vbn/sampling/gibbs.py; tests/test_sampling.py:46-56) -----------
+def test_gibbs_sampler_philox_path(backend):
+    model = _mixed(backend.device)
+    model.set_sampling_method("gibbs", n_samples=7, burn_in=3)
+    assert model._sampling.n_candidates == 8 and model._sampling.burn_in == 3 and model._sampling.n_steps == 1
+    ev = {"n11": torch.tensor([[0.2], [0.2], [-0.4]])}
+    s1 = model.sample({"target": "n5", "evidence": ev}, n_samples=7, seed=5)
+    assert s1.shape == (3, 7, 1) and torch.isfinite(s1).all() and not s1.requires_grad
+    assert bool((s1 == s1[:, :1]).all())  # final state repeated (views of the live state, gibbs.py:83-91)
+    s2 = model.sample({"target": "n5", "evidence": ev}, n_samples=7, seed=5)
+    assert torch.equal(s1, s2)
+    s3 = model.sample({"target": "n5", "evidence": ev}, n_samples=7, seed=6)
+    assert not torch.equal(s1, s3)
+    assert s1[0, 0, 0] != s1[1, 0, 0]  # same evidence, independent chains
+    # more sweeps move the chain: 1 step vs 40 steps from the same seed end in different states
+    model.set_sampling_method("gibbs", n_samples=40, burn_in=0)
+    s4 = model.sample({"target": "n5", "evidence": ev}, n_samples=40, seed=5)
+    assert s4.shape == (3, 40, 1) and not torch.equal(s4[:, :1], s1[:, :1])
+    # a fixed target is returned as given; a chain pulled by strong evidence follows it
+    chain = _chain(backend.device, n=3)
+    chain.set_sampling_method("gibbs", n_samples=2, burn_in=30)
+    hi = chain.sample({"target": "x1", "evidence": {"x2": torch.full((256, 1), 6.0)}}, n_samples=2, seed=1)[:, 0, 0]
+    lo = chain.sample({"target": "x1", "evidence": {"x2": torch.full((256, 1), -6.0)}}, n_samples=2, seed=1)[:, 0, 0]
+    assert hi.mean().item() > lo.mean().item() + 2.0
+    fx = chain.sample({"target": "x2", "evidence": {"x2": torch.tensor([[1.5]])}}, n_samples=2, seed=1)
+    assert torch.equal(fx.cpu(), torch.full((1, 2, 1), 1.5))
+
+
 # ---- resampled_importance_sampling (vbn/inference/resampled_importance_sampling.py) ----------------
 def test_resampled_importance_sampling_philox_path(backend):
     spec = S.lg_chain(8)

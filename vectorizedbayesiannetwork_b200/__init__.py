@@ -11,7 +11,7 @@ from .cpd_handle import CPDHandle
 from .cpds import (BaseCPD, CategoricalEmbeddedSoftmaxCPD, CategoricalTableCPD, GaussianNNCPD, KDECPD, LinearGaussianCPD, MDNCPD, RFFGaussianCPD, SoftmaxNNCPD,
                    cpd_from_spec, wrap_cpd)
 from .dist import Shard, auto_shard
-from .inference import (AncestralSampler, CategoricalExact, GaussianExact, ImportanceSampling,
+from .inference import (AncestralSampler, CategoricalExact, GaussianExact, GibbsSampler, ImportanceSampling,
                         LikelihoodWeighting, MonteCarloMarginalization, RaoBlackwellizedMarginalization,
                         ResampledImportanceSampling)
 from .install import install, uninstall
@@ -21,7 +21,7 @@ __all__ = [
     "INFERENCE_REGISTRY", "SAMPLING_REGISTRY",
     "BaseCPD", "LinearGaussianCPD", "GaussianNNCPD", "MDNCPD", "SoftmaxNNCPD", "KDECPD", "RFFGaussianCPD", "CategoricalTableCPD", "CategoricalEmbeddedSoftmaxCPD",
     "cpd_from_spec", "wrap_cpd",
-    "ImportanceSampling", "LikelihoodWeighting", "MonteCarloMarginalization", "AncestralSampler",
+    "ImportanceSampling", "LikelihoodWeighting", "MonteCarloMarginalization", "AncestralSampler", "GibbsSampler",
     "GaussianExact", "CategoricalExact", "ResampledImportanceSampling", "RaoBlackwellizedMarginalization",
     "Shard", "auto_shard", "install", "uninstall",
 ]

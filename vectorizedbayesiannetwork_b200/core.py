@@ -121,7 +121,8 @@ class StaticDAG:
     """Accepts a networkx.DiGraph (like the reference) or an explicit (nodes, parents) pair."""
 
     def __init__(self, graph=None, *, nodes: Optional[List[str]] = None,
-                 parents: Optional[Dict[str, List[str]]] = None, topo: Optional[List[str]] = None):
+                 parents: Optional[Dict[str, List[str]]] = None, topo: Optional[List[str]] = None,
+                 children: Optional[Dict[str, List[str]]] = None):
         if graph is not None:
             import networkx as nx
 
@@ -135,7 +136,10 @@ class StaticDAG:
         else:
             self._nodes = list(nodes)
             self._parents = {n: list(parents.get(n, [])) for n in self._nodes}
-            self._edges = [(p, n) for n in self._nodes for p in self._parents[n]]
+            if children is not None:  # dag.edges() order of the reference (what its Gibbs sampler iterates)
+                self._edges = [(p, c) for p in self._nodes for c in children.get(p, [])]
+            else:
+                self._edges = [(p, n) for p in self._nodes for n in self._nodes if p in self._parents[n]]
             self._topo = list(topo) if topo is not None else self._toposort()
             self.graph = None
 
@@ -228,7 +232,8 @@ class VBN:
     # ----- construction from fitted parameters (fit itself is out of scope) -----------------
     @classmethod
     def from_spec(cls, spec: dict, device=None, seed: Optional[int] = None) -> "VBN":
-        dag = StaticDAG(nodes=spec["nodes"], parents=spec["parents"], topo=spec.get("topo"))
+        dag = StaticDAG(nodes=spec["nodes"], parents=spec["parents"], topo=spec.get("topo"),
+                        children=spec.get("children"))
         model = cls(dag, seed=seed, device=device)
         model.nodes = {n: cpd_from_spec(spec["cpds"][n], model.device) for n in spec["nodes"]}
         return model
@@ -238,7 +243,8 @@ class VBN:
         """Snapshot of a fitted reference ``vbn.VBN`` (same DAG order, same parameters)."""
         nodes = list(ref_vbn.dag.nodes())
         dag = StaticDAG(nodes=nodes, parents={n: list(ref_vbn.dag.parents(n)) for n in nodes},
-                        topo=list(ref_vbn.dag.topological_order()))
+                        topo=list(ref_vbn.dag.topological_order()),
+                        children={n: [c for p, c in ref_vbn.dag.edges() if p == n] for n in nodes})
         model = cls(dag, device=device)
         model.nodes = {n: wrap_cpd(ref_vbn.nodes[n], model.device) for n in nodes}
         return model

@@ -62,6 +62,9 @@ struct Rows {
   bool valid[RPT];
   float logw[RPT];
   float logp[RPT];
+  // VBN_OP_JUMP loop state: iteration number, and the Philox stream blocks one iteration consumes
+  // (added to every stream block index so each iteration draws fresh numbers)
+  int loop_iter, loop_nq, loop_uq;
   // Philox stream caches (per-row keyed streams): block index + 4 values per row
   int cur_nq, cur_uq;
   float4 ncache[RPT], ucache[RPT];
@@ -111,16 +114,28 @@ struct Ctx {
     return philox_uniform4(counter(j, block, tag, shared), make_uint2(a.key0, a.key1));
   }
 
+  // Element of an injected array that belongs to row j: [Bn, S] entries of `width` values; inside a
+  // VBN_OP_JUMP loop the arrays gain a leading iteration axis, and an op may address one member of a
+  // group of draws the reference made in a single call (gop->tc[1] = group size, tc[2] = member:
+  // the Gibbs sampler's candidates, sampling/gibbs.py:54).  Test / replay path only.
+  __device__ __forceinline__ int64_t injected_row(int j, bool shared) const {
+    const int64_t per_iter = shared ? a.n_samples : a.n_rows;
+    int64_t r = static_cast<int64_t>(rows.loop_iter) * per_iter + (shared ? rows.ls[j] : rows.r[j]);
+    const int group = __ldg(&gop->tc[1]);
+    if (group > 1) r = r * group + __ldg(&gop->tc[2]);
+    return r;
+  }
+
   // normal number `index` of the op's stream, for all RPT rows
   __device__ __forceinline__ void draw_normal(const VbnOp& op, int index, int d, float (&out)[RPT]) {
     const bool shared = (op.flags & VBN_F_SHARED) != 0;
     if (op.noise_idx >= 0) {
       const float* eps = a.noise[op.noise_idx].eps;
 #pragma unroll
-      for (int j = 0; j < RPT; ++j)
-        out[j] = __ldg(eps + (shared ? rows.ls[j] : rows.r[j]) * op.dim + d);
+      for (int j = 0; j < RPT; ++j) out[j] = __ldg(eps + injected_row(j, shared) * op.dim + d);
       return;
     }
+    index += 4 * rows.loop_iter * rows.loop_nq;
     const int q = index >> 2, lane = index & 3;
     if (shared) {
 #pragma unroll
@@ -142,10 +157,10 @@ struct Ctx {
     if (op.noise_idx >= 0 && a.noise[op.noise_idx].u != nullptr) {
       const float* u = a.noise[op.noise_idx].u;
 #pragma unroll
-      for (int j = 0; j < RPT; ++j)
-        out[j] = __ldg(u + (shared ? rows.ls[j] : rows.r[j]) * op.dim + d);
+      for (int j = 0; j < RPT; ++j) out[j] = __ldg(u + injected_row(j, shared) * op.dim + d);
       return;
     }
+    index += 4 * rows.loop_iter * rows.loop_uq;
     const int q = index >> 2, lane = index & 3;
     if (shared) {
 #pragma unroll
@@ -168,8 +183,7 @@ struct Ctx {
     if (idx == nullptr) return false;
     const bool shared = (op.flags & VBN_F_SHARED) != 0;
 #pragma unroll
-    for (int j = 0; j < RPT; ++j)
-      out[j] = __ldg(idx + (shared ? rows.ls[j] : rows.r[j]) * width + d);
+    for (int j = 0; j < RPT; ++j) out[j] = __ldg(idx + injected_row(j, shared) * width + d);
     return true;
   }
 };
@@ -373,6 +387,11 @@ __device__ __forceinline__ void load_fixed(Ctx<RPT, NT, TC>& c, const VbnOp& op)
 #pragma unroll
       for (int j = 0; j < RPT; ++j)
         c.slot(op.out_slot + d, j) = __ldg(v.base + c.rows.r[j] * v.row_stride + d * v.dim_stride);
+  } else if (src == VBN_SRC_SLOT) {  // score the value another op left in slot fixed_col (Gibbs: a child's state)
+    if (op.fixed_col != op.out_slot)
+      for (int d = 0; d < op.dim; ++d)
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) c.slot(op.out_slot + d, j) = c.slot(op.fixed_col + d, j);
   }
 }
 
@@ -1261,6 +1280,55 @@ __device__ __forceinline__ void op_kde(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
 // ---------------------------------------------------------------------------------------
 // the kernels' shared body
 // ---------------------------------------------------------------------------------------
+// Gibbs sweeps (sampling/gibbs.py:38-82): candidate / score ops are ordinary CPD ops; these three
+// tie them together.
+//   VBN_OP_TAKEW : slot[out_slot] = accumulated log-weight of the row; log-weight = 0
+//   VBN_OP_SELECT: among k candidates (values in slots aux[1] + c*dim + d, scores in slots aux[0] + c),
+//                  draw c ~ softmax(scores) (gibbs.py:76-77) and copy its value to out_slot
+//   VBN_OP_JUMP  : back to op aux[0] until the loop has run k times; layer_dim[0..1] = Philox stream
+//                  blocks (normal, uniform) one iteration consumes
+// ---------------------------------------------------------------------------------------
+template <int RPT, int NT, class TC>
+__device__ __forceinline__ void op_takew(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    c.slot(op.out_slot, j) = c.rows.logw[j];
+    c.rows.logw[j] = 0.0f;
+  }
+}
+
+template <int RPT, int NT, class TC>
+__device__ __forceinline__ void op_select(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
+  const int K = __ldg(&c.gop->k), D = op.dim;  // read from the descriptor: the light kernels do not fetch quad 3
+  const int s_score = __ldg(&c.gop->aux[0]), s_cand = __ldg(&c.gop->aux[1]);
+  int pick[RPT];
+  if (!c.injected_index(op, 0, 1, pick)) {
+    float u[RPT];
+    c.draw_uniform(op, op.u_off, 0, u);
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      float mx = -CUDART_INF_F;
+      for (int k = 0; k < K; ++k) mx = fmaxf(mx, c.slot(s_score + k, j));
+      float tot = 0.0f;
+      for (int k = 0; k < K; ++k) tot += expf(c.slot(s_score + k, j) - mx);
+      const float t = u[j] * tot;
+      float cum = 0.0f;
+      pick[j] = K - 1;
+      for (int k = 0; k < K; ++k) {
+        const float before = cum;
+        cum += expf(c.slot(s_score + k, j) - mx);
+        if (t >= before && t < cum) { pick[j] = k; break; }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    const int k = min(max(pick[j], 0), K - 1);
+    for (int d = 0; d < D; ++d) c.slot(op.out_slot + d, j) = c.slot(s_cand + k * D + d, j);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // binds row j of the thread to local row index r (clamped into range; `valid` masks the stores)
 template <class C>
 __device__ __forceinline__ void bind_row(C& c, int j, int64_t r) {
@@ -1283,6 +1351,9 @@ __device__ __forceinline__ void run_ops(Ctx<RPT, NT, TC>& c) {
   const ScheduleArgs& a = c.a;
   c.rows.cur_nq = -1;
   c.rows.cur_uq = -1;
+  c.rows.loop_iter = 0;
+  c.rows.loop_nq = 0;
+  c.rows.loop_uq = 0;
   for (int i = 0; i < a.n_ops; ++i) {
     VbnOp op;  // only the 16-byte quads this op kind reads are fetched (layer_dim: via c.gop)
     {
@@ -1348,6 +1419,25 @@ __device__ __forceinline__ void run_ops(Ctx<RPT, NT, TC>& c) {
       }
     }
     c.gop = a.ops + i;
+    if (op.kind >= VBN_OP_TAKEW) {  // Gibbs glue ops (rare: one warp-uniform compare per generic op)
+      if (op.kind == VBN_OP_TAKEW) {
+        op_takew(c, op);
+      } else if (op.kind == VBN_OP_SELECT) {
+        op_select(c, op);
+        store_value(c, op);
+      } else if (op.kind == VBN_OP_JUMP) {
+        const int k = __ldg(&c.gop->k);
+        c.rows.loop_nq = __ldg(&c.gop->layer_dim[0]);
+        c.rows.loop_uq = __ldg(&c.gop->layer_dim[1]);
+        if (c.rows.loop_iter + 1 < k) {
+          ++c.rows.loop_iter;
+          c.rows.cur_nq = -1;
+          c.rows.cur_uq = -1;
+          i = __ldg(&c.gop->aux[0]) - 1;
+        }
+      }
+      continue;
+    }
     if (HEAVY && (op.flags & VBN_F_OUT_PARAMS)) {
       op_params(c, op);
       continue;

@@ -12,7 +12,7 @@ Extra keyword arguments understood by every method (all optional):
 """
 from __future__ import annotations
 
-from typing import Dict, Optional
+from typing import Dict, List, Optional
 
 import torch
 
@@ -20,7 +20,7 @@ from . import engine as E
 from .core import (Query, infer_batch_size, model_cpds, register_inference, register_sampling)
 from .cpds import TABLE_KINDS
 from .dist import Shard, gather_stats
-from .plan import Role, compile_schedule
+from .plan import Role, compile_gibbs, compile_schedule
 
 
 def _check_model(vbn) -> torch.device:
@@ -623,3 +623,62 @@ class AncestralSampler:
         out = self._runner.forward(vbn, q, n_samples, "anc", noise=kwargs.get("noise"),
                                    seed=kwargs.get("seed"), shard=kwargs.get("shard"), store_all=joint)
         return out["stores"] if joint else out["stores"][query.target]
+
+
+@register_sampling("gibbs")
+class GibbsSampler:
+    """vbn/sampling/gibbs.py:12-92.  One chain per query; the whole chain -- ancestral initial
+    state, burn_in + n_samples * max(n_steps, 1) sweeps of 8-candidate propose / score / select per latent node --
+    is ONE kernel launch (plan.compile_gibbs): a row is a chain, node values stay in shared memory.
+
+    Reference behaviour kept on purpose: the chain's states are collected as VIEWS of the live state tensor
+    (gibbs.py:83-91), so the returned [B, n_samples, D] tensor holds the FINAL target state n_samples times.
+    Deviation: with B > 1 and a latent root the reference raises IndexError (root candidates are [1, 8, D]);
+    here every chain draws its own root candidates."""
+
+    def __init__(self, n_samples: int = 200, burn_in: int = 10, n_steps: int = 1, **kwargs) -> None:
+        self.n_samples = int(n_samples)
+        self.burn_in = int(burn_in)
+        self.n_steps = int(n_steps)
+        self.n_candidates = 8
+        self._cache: Dict[tuple, E.DevicePlan] = {}
+
+    def _plan(self, vbn, query: Query, total_steps: int, inject: bool) -> E.DevicePlan:
+        cpds = model_cpds(vbn)
+        fp = tuple((c._uid, c._version) for c in cpds.values())
+        key = (fp, query.target, tuple(sorted(query.evidence)), tuple(sorted(query.do)), int(total_steps),
+               self.n_candidates, bool(inject), str(vbn.device))
+        plan = self._cache.get(key)
+        if plan is None:
+            topo, parents = _topology(vbn)
+            children: Dict[str, List[str]] = {n: [] for n in topo}
+            for p, c in vbn.dag.edges():
+                children[p].append(c)
+            prog = compile_gibbs(topo, parents, children, cpds, list(query.evidence) + list(query.do), query.target,
+                                 total_steps, self.n_candidates, inject=inject)
+            plan = E.DevicePlan(prog, vbn.device)
+            if len(self._cache) > 64:
+                self._cache.clear()
+            self._cache[key] = plan
+        return plan
+
+    def sample(self, vbn, query: Query, n_samples: Optional[int] = None, **kwargs):
+        n_samples = int(n_samples or self.n_samples)
+        dev = _check_model(vbn)
+        b = infer_batch_size(query.evidence, query.do)
+        total_steps = self.burn_in + n_samples * max(self.n_steps, 1)
+        noise = kwargs.get("noise")
+        plan = self._plan(vbn, query, total_steps, inject=noise is not None)
+        prog = plan.program
+        with torch.cuda.device(dev):
+            fixed = _ScheduleRunner.fixed_table(plan, query, b, clamp_obs=False, shard=None)
+            out = torch.empty(b, 1, prog.dims[query.target], device=dev, dtype=torch.float32)
+            flag = torch.zeros(1, device=dev, dtype=torch.int32)
+            arrays = [] if noise is None else [noise[kind][node] for kind, node in prog.noise_keys]
+            seed = kwargs.get("seed")
+            plan.run(b, 1, fixed=fixed, stores=[out], noise=arrays, seed=E.draw_seed() if seed is None else seed,
+                     error_flag=flag)
+            cpds = model_cpds(vbn)
+            if any(c.kind in ("softmax_nn",) + TABLE_KINDS for c in cpds.values()) and int(flag.item()) != 0:
+                raise ValueError("Found values outside discrete class set.")
+        return out.expand(b, n_samples, -1).contiguous()

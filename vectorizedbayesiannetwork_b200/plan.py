@@ -316,3 +316,150 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
         tc=any_tc,
         tc_list=np.asarray(tc_list, dtype=np.int32).reshape(-1, 2) if any_tc else None,
     )
+
+
+# ------------------------------------------------------------------------------------------------
+# Gibbs sampler (vbn/sampling/gibbs.py:23-92)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class GibbsProgram(Program):
+    """One launch runs the whole chain: ancestral initial state, then a VBN_OP_JUMP loop of sweeps.
+    noise_keys[i] names the injected array set of noise[i]: ("init", node) | ("cand", node) | ("choice", node)."""
+
+    noise_keys: List[tuple] = field(default_factory=list)
+    n_candidates: int = 8
+
+
+def compile_gibbs(topo: Sequence[str], parents: Dict[str, Sequence[str]], children: Dict[str, Sequence[str]],
+                  cpds: Dict[str, BaseCPD], fixed: Sequence[str], target: str, total_steps: int,
+                  n_candidates: int = 8, inject: bool = False) -> GibbsProgram:
+    """Schedule of the reference's Gibbs sampler, one ROW per chain (= per query):
+
+        init   : every node gets a permanent slot; fixed nodes are loaded from the per-query table, the others
+                 drawn ancestrally (gibbs.py:32, _ancestral_sample_tensor with one sample: roots shared)
+        sweep  : per latent node, per candidate c: the node's own CPD draws candidate c from the current parents
+                 and adds its log-density; every child's CPD scores the child's CURRENT value (VBN_SRC_SLOT)
+                 with the candidate substituted; VBN_OP_TAKEW moves the score to a slot.  VBN_OP_SELECT
+                 then draws one candidate by softmax and overwrites the node's slot (gibbs.py:41-82)
+        loop   : VBN_OP_JUMP repeats the sweep total_steps times with fresh Philox stream blocks
+        output : the target's final state (the reference returns it n_samples times, see oracle gibbs_sample)
+    """
+    k = int(n_candidates)
+    fixed = set(fixed)
+    order = list(topo)
+    dims = {n: int(cpds[n].output_dim) for n in order}
+    slot_of, nxt = {}, 0
+    for n in order:
+        slot_of[n] = nxt
+        nxt += dims[n]
+    dmax = max(dims.values())
+    s_score, s_cand, s_tmp = nxt, nxt + k, nxt + k + k * dmax
+    n_slots = s_tmp + dmax
+
+    blob: List[np.ndarray] = []
+    blob_len = 0
+    param_off: Dict[int, int] = {}
+    par_slots: List[int] = []
+    rows: List[dict] = []
+    noise_keys: List[tuple] = []
+    state = {"n_off": 0, "u_off": 0, "scratch": 0, "heavy": False, "n_fixed": 0}
+    fixed_cols: Dict[str, int] = {}
+
+    def params_of(pk: Packed) -> int:
+        nonlocal blob_len
+        key = id(pk)
+        if key not in param_off:
+            pad = (-blob_len) % 4
+            if pad:
+                blob.append(np.zeros(pad, np.float32))
+                blob_len += pad
+            param_off[key] = blob_len
+            blob.append(pk.params.astype(np.float32, copy=False))
+            blob_len += pk.params.size
+        return param_off[key]
+
+    def cpd_op(node: str, out_slot: int, par_of: Dict[str, int], flags: int, *, fixed_col: int = -1,
+               noise_key=None, member: int = 0, group: int = 0, draws: bool = False) -> dict:
+        pk = cpds[node].pack()
+        plist = list(parents.get(node, ()))
+        if sum(dims[p] for p in plist) != pk.n_par:
+            raise ValueError(f"node '{node}': CPD expects {pk.n_par} parent dims")
+        op = dict(kind=pk.kind, flags=flags, dim=dims[node], n_par=pk.n_par, out_slot=out_slot,
+                  par_off=len(par_slots), param_off=params_of(pk), fixed_col=fixed_col, store_idx=-1, noise_idx=-1,
+                  n_off=0, u_off=0, n_layers=pk.n_layers, act=pk.act, n_out=pk.n_out, k=pk.k,
+                  layer_dim=list(pk.layer_dim)[: L.MAX_LAYERS], aux=list(pk.aux), tc=[0, group, member, 0])
+        for p in plist:
+            par_slots.extend(range(par_of[p], par_of[p] + dims[p]))
+        if pk.n_layers == 3 and list(pk.layer_dim[:2]) == [32, 32]:
+            op["flags"] |= L.F_FAST32
+        if draws:
+            op["n_off"], op["u_off"] = state["n_off"], state["u_off"]
+            state["n_off"] += pk.n_normals
+            state["u_off"] += pk.n_uniforms
+            if inject and noise_key is not None:
+                if noise_key not in noise_keys:
+                    noise_keys.append(noise_key)
+                op["noise_idx"] = noise_keys.index(noise_key)
+        state["scratch"] = max(state["scratch"], pk.scratch)
+        state["heavy"] = state["heavy"] or pk.heavy
+        return op
+
+    def glue(kind: int, **kw) -> dict:
+        op = dict(kind=kind, flags=L.SRC_SAMPLE, dim=1, n_par=0, out_slot=0, par_off=0, param_off=0, fixed_col=-1,
+                  store_idx=-1, noise_idx=-1, n_off=0, u_off=0, n_layers=0, act=0, n_out=0, k=0, layer_dim=[],
+                  aux=[0, 0, 0, 0], tc=[0, 0, 0, 0])
+        op.update(kw)
+        return op
+
+    # ---- initial state ----------------------------------------------------------------------------
+    for n in order:
+        if n in fixed:
+            fixed_cols[n] = state["n_fixed"]
+            rows.append(glue(L.OP_NONE, flags=L.SRC_FIXED_Q, dim=dims[n], out_slot=slot_of[n], fixed_col=state["n_fixed"]))
+            state["n_fixed"] += dims[n]
+        else:
+            flags = L.SRC_SAMPLE | (L.F_SHARED if not parents.get(n) else 0)
+            rows.append(cpd_op(n, slot_of[n], slot_of, flags, noise_key=("init", n), draws=True))
+    # the loop's stream blocks start on a block boundary so that iteration t adds t * (blocks per sweep)
+    state["n_off"] = (state["n_off"] + 3) & ~3
+    state["u_off"] = (state["u_off"] + 3) & ~3
+    n0, u0 = state["n_off"], state["u_off"]
+    loop_start = len(rows)
+    latent = [n for n in order if n not in fixed]
+    for n in latent:
+        d = dims[n]
+        for c in range(k):
+            cand = s_cand + c * d
+            rows.append(cpd_op(n, cand, slot_of, L.SRC_SAMPLE | L.F_ADD_LOGW, noise_key=("cand", n), member=c,
+                               group=k, draws=True))
+            for ch in children.get(n, ()):
+                par_of = dict(slot_of)
+                par_of[n] = cand
+                rows.append(cpd_op(ch, s_tmp, par_of, L.SRC_SLOT | L.F_ADD_LOGW, fixed_col=slot_of[ch]))
+            rows.append(glue(L.OP_TAKEW, out_slot=s_score + c))
+        sel = glue(L.OP_SELECT, dim=d, out_slot=slot_of[n], k=k, aux=[s_score, s_cand, 0, 0], u_off=state["u_off"])
+        state["u_off"] += 1
+        if inject:
+            noise_keys.append(("choice", n))
+            sel["noise_idx"] = len(noise_keys) - 1
+        rows.append(sel)
+    nq = (state["n_off"] - n0 + 3) // 4
+    uq = (state["u_off"] - u0 + 3) // 4
+    if latent and total_steps > 1:
+        rows.append(glue(L.OP_JUMP, k=int(total_steps), aux=[loop_start, 0, 0, 0], layer_dim=[nq, uq]))
+    rows.append(glue(L.OP_NONE, dim=dims[target], out_slot=slot_of[target], store_idx=0))
+
+    ops = np.zeros(len(rows), dtype=L.OP_DTYPE)
+    for i, r in enumerate(rows):
+        for key, v in r.items():
+            if key in ("layer_dim", "aux", "tc"):
+                ops[i][key][: len(v)] = v
+            else:
+                ops[i][key] = v
+    params = np.concatenate(blob) if blob else np.zeros(4, np.float32)
+    return GibbsProgram(
+        ops=ops, par_slots=np.asarray(par_slots if par_slots else [0], dtype=np.int32), params=params,
+        n_slots=n_slots, n_scratch=int(state["scratch"]), heavy=bool(state["heavy"]), nodes=order,
+        fixed_cols=fixed_cols, n_fixed_cols=state["n_fixed"], inputs=[], stores=[target],
+        noise=[str(key) for key in noise_keys], needs_logw=False, needs_logp=False, dims=dims, tc=False, tc_list=None,
+        store_widths={target: dims[target]}, noise_keys=noise_keys, n_candidates=k)
