@@ -129,7 +129,7 @@ typedef struct VbnOp {
   int32_t k;          /* MDN: components K; SNN: classes C; KDE: stored points N           */
   int32_t layer_dim[VBN_MAX_LAYERS]; /* widths after each Linear layer (last == n_out)      */
   int32_t aux[4];     /* SNN: {within_bin, clip, any_discrete, 0}                          */
-  /* injected draws only: tc[1] > 1 = this op replays member tc[2] of a group of tc[1] draws the reference
+  /* injected draws only, ops without a tensor-core image (tc[0] == 0): tc[1] > 1 = this op replays member tc[2] of a group of tc[1] draws the reference
      made in one call (Gibbs candidates); arrays inside a VBN_OP_JUMP loop carry a leading iteration axis */
   int32_t tc[4];      /* tensor-core MLP image (hidden dims [32,32], Dp <= 32, O <= 32), written by
                          the plan compiler: {1 if present, float offset of the image in the

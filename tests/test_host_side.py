@@ -113,7 +113,7 @@ def test_registry_and_resolution_mirror_reference():
         V.INFERENCE_REGISTRY["gaussian_exact"](fallback="gaussian_exact")
     with pytest.raises(ValueError):
         V.INFERENCE_REGISTRY["categorical_exact"](fallback="no_such_method")
-    assert set(V.SAMPLING_REGISTRY) == {"ancestral"}
+    assert set(V.SAMPLING_REGISTRY) == {"ancestral", "gibbs"}
     from vectorizedbayesiannetwork_b200.core import register_inference
 
     with pytest.raises(ValueError):

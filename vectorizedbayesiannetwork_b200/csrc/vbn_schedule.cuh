@@ -121,7 +121,7 @@ struct Ctx {
   __device__ __forceinline__ int64_t injected_row(int j, bool shared) const {
     const int64_t per_iter = shared ? a.n_samples : a.n_rows;
     int64_t r = static_cast<int64_t>(rows.loop_iter) * per_iter + (shared ? rows.ls[j] : rows.r[j]);
-    const int group = __ldg(&gop->tc[1]);
+    const int group = __ldg(&gop->tc[0]) == 0 ? __ldg(&gop->tc[1]) : 0;  // tc[0] != 0: the fields describe a tensor-core image
     if (group > 1) r = r * group + __ldg(&gop->tc[2]);
     return r;
   }

@@ -4,7 +4,7 @@ hot-path methods (vbn/core/registry.py:7-11) with the CUDA classes, so
 The registry decorator refuses duplicate keys (registry.py:18-20), hence plain dict assignment."""
 from __future__ import annotations
 
-from .inference import (AncestralSampler, CategoricalExact, GaussianExact, ImportanceSampling,
+from .inference import (AncestralSampler, CategoricalExact, GaussianExact, GibbsSampler, ImportanceSampling,
                         LikelihoodWeighting, MonteCarloMarginalization, RaoBlackwellizedMarginalization,
                         ResampledImportanceSampling)
 
@@ -23,8 +23,9 @@ def install(vbn_module=None) -> None:
                      ("rao_blackwellized_marginalization", RaoBlackwellizedMarginalization)):
         _ORIGINAL.setdefault(("inference", key), reg.INFERENCE_REGISTRY.get(key))
         reg.INFERENCE_REGISTRY[key] = cls
-    _ORIGINAL.setdefault(("sampling", "ancestral"), reg.SAMPLING_REGISTRY.get("ancestral"))
-    reg.SAMPLING_REGISTRY["ancestral"] = AncestralSampler
+    for key, cls in (("ancestral", AncestralSampler), ("gibbs", GibbsSampler)):
+        _ORIGINAL.setdefault(("sampling", key), reg.SAMPLING_REGISTRY.get(key))
+        reg.SAMPLING_REGISTRY[key] = cls
 
 
 def uninstall(vbn_module=None) -> None:
