@@ -74,12 +74,14 @@ struct Rows {
 struct NoTc {
   static constexpr bool kEnabled = false;
   static constexpr bool kInlineRng = false;
+  static constexpr bool kLoops = true;  // carries the Gibbs glue ops (VBN_OP_TAKEW / SELECT / JUMP)
 };
 // LG / table-only schedules: the generator is the hot loop, so it is inlined with constant-bank
 // round keys instead of being called out of line.
 struct LightPolicy {
   static constexpr bool kEnabled = false;
   static constexpr bool kInlineRng = true;
+  static constexpr bool kLoops = false;  // the LG / table hot loops stay a plain counted walk
 };
 
 template <int RPT, int NT, class TC = NoTc>
@@ -119,6 +121,7 @@ struct Ctx {
   // group of draws the reference made in a single call (gop->tc[1] = group size, tc[2] = member:
   // the Gibbs sampler's candidates, sampling/gibbs.py:54).  Test / replay path only.
   __device__ __forceinline__ int64_t injected_row(int j, bool shared) const {
+    if constexpr (!TC::kLoops) return shared ? rows.ls[j] : rows.r[j];
     const int64_t per_iter = shared ? a.n_samples : a.n_rows;
     int64_t r = static_cast<int64_t>(rows.loop_iter) * per_iter + (shared ? rows.ls[j] : rows.r[j]);
     const int group = __ldg(&gop->tc[0]) == 0 ? __ldg(&gop->tc[1]) : 0;  // tc[0] != 0: the fields describe a tensor-core image
@@ -135,7 +138,7 @@ struct Ctx {
       for (int j = 0; j < RPT; ++j) out[j] = __ldg(eps + injected_row(j, shared) * op.dim + d);
       return;
     }
-    index += 4 * rows.loop_iter * rows.loop_nq;
+    if constexpr (TC::kLoops) index += 4 * rows.loop_iter * rows.loop_nq;
     const int q = index >> 2, lane = index & 3;
     if (shared) {
 #pragma unroll
@@ -160,7 +163,7 @@ struct Ctx {
       for (int j = 0; j < RPT; ++j) out[j] = __ldg(u + injected_row(j, shared) * op.dim + d);
       return;
     }
-    index += 4 * rows.loop_iter * rows.loop_uq;
+    if constexpr (TC::kLoops) index += 4 * rows.loop_iter * rows.loop_uq;
     const int q = index >> 2, lane = index & 3;
     if (shared) {
 #pragma unroll
@@ -1419,7 +1422,7 @@ __device__ __forceinline__ void run_ops(Ctx<RPT, NT, TC>& c) {
       }
     }
     c.gop = a.ops + i;
-    if (op.kind >= VBN_OP_TAKEW) {  // Gibbs glue ops (rare: one warp-uniform compare per generic op)
+    if (TC::kLoops && op.kind >= VBN_OP_TAKEW) {  // Gibbs glue ops: FFMA-pipe HEAVY kernels only (plan.compile_gibbs)
       if (op.kind == VBN_OP_TAKEW) {
         op_takew(c, op);
       } else if (op.kind == VBN_OP_SELECT) {

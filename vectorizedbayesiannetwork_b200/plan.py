@@ -459,7 +459,8 @@ def compile_gibbs(topo: Sequence[str], parents: Dict[str, Sequence[str]], childr
     params = np.concatenate(blob) if blob else np.zeros(4, np.float32)
     return GibbsProgram(
         ops=ops, par_slots=np.asarray(par_slots if par_slots else [0], dtype=np.int32), params=params,
-        n_slots=n_slots, n_scratch=int(state["scratch"]), heavy=bool(state["heavy"]), nodes=order,
+        n_slots=n_slots, n_scratch=int(state["scratch"]), heavy=True,  # the glue ops live in the HEAVY FFMA kernels only
+        nodes=order,
         fixed_cols=fixed_cols, n_fixed_cols=state["n_fixed"], inputs=[], stores=[target],
         noise=[str(key) for key in noise_keys], needs_logw=False, needs_logp=False, dims=dims, tc=False, tc_list=None,
         store_widths={target: dims[target]}, noise_keys=noise_keys, n_candidates=k)
