@@ -536,11 +536,17 @@ __global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const S
   c.tc.t_d = c.tc.m_d + lane_base;
   c.tc.t_ahi = c.tc.m_ahi + lane_base;
   c.tc.t_alo = c.tc.m_alo + lane_base;
+  c.tc.mma_bar = mma_bar0 + 8 * wg;
+  // same treatment for the per-thread TMEM / barrier addresses: values, not recipes in (tid, wg)
+  asm volatile("" : "+r"(c.tc.m_d), "+r"(c.tc.t_d), "+r"(c.tc.mma_bar));
+  c.tc.m_ahi = c.tc.m_d + (kColAhi - kColD);
+  c.tc.m_alo = c.tc.m_d + (kColAlo - kColD);
+  c.tc.t_ahi = c.tc.t_d + (kColAhi - kColD);
+  c.tc.t_alo = c.tc.t_d + (kColAlo - kColD);
   c.tc.wbuf = wbuf;
   c.tc.wbuf_ptr = smem_raw + kCtrlBytes;
   c.tc.full_bar = full_bar;
   c.tc.empty_bar = empty_bar;
-  c.tc.mma_bar = mma_bar0 + 8 * wg;
   c.tc.w_iter = 0;
   c.tc.w_buf = 0;
   c.tc.mma_phase = 0;
@@ -561,7 +567,9 @@ __global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const S
     bind_row(c, 0, tile * kWgThreads + (tid & (kWgThreads - 1)));
     // same reason as slot_word: keep the Philox counter words as values, not as a recipe (the row
     // index -> (query, sample) division chain was being re-executed per op)
-    asm volatile("" : "+r"(c.rows.gs[0]), "+r"(c.rows.gb[0]));
+    int row_ok = c.rows.valid[0] ? 1 : 0;
+    asm volatile("" : "+r"(c.rows.gs[0]), "+r"(c.rows.gb[0]), "+l"(c.rows.r[0]), "+r"(row_ok));
+    c.rows.valid[0] = row_ok != 0;
     run_ops<true>(c);
   }
   tc_fence_before();
