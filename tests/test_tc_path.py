@@ -38,7 +38,14 @@ def test_pack_mlp_tc_eligibility_and_size():
     ok = pack_mlp_tc(S.mlp_layers(g, 3, (32, 32), 9), 3)
     assert ok is not None
     blob, k1, n3 = ok
-    assert (k1, n3) == (8, 16) and blob.size * 4 == 4 * (2 * 32 * 8 + 2 * 32 * 32 + 2 * 16 * 32 + 64 + 16)
+    # every layer's K is extended by one 8-wide step that carries the bias (column K, then zeros)
+    assert (k1, n3) == (8, 16) and blob.size * 4 == 4 * 2 * (32 * (8 + 8) + 32 * (32 + 8) + 16 * (32 + 8))
+    layers = S.mlp_layers(torch.Generator().manual_seed(0), 3, (32, 32), 9)
+    w1hi = blob[: 32 * 16].reshape(4, 4, 8, 4).transpose(0, 2, 1, 3).reshape(32, 16)  # undo the core-matrix image
+    w1lo = blob[32 * 16: 2 * 32 * 16].reshape(4, 4, 8, 4).transpose(0, 2, 1, 3).reshape(32, 16)
+    torch.testing.assert_close(torch.from_numpy(w1hi + w1lo)[:, :3], layers[0][0], rtol=0, atol=1e-6)  # lo is itself rounded to tf32: 2^-21 relative
+    torch.testing.assert_close(torch.from_numpy(w1hi + w1lo)[:, 8], layers[0][1], rtol=0, atol=1e-6)
+    assert not (w1hi + w1lo)[:, 3:8].any() and not (w1hi + w1lo)[:, 9:].any()
     assert pack_mlp_tc(S.mlp_layers(g, 3, (16, 16), 9), 3) is None       # other hidden sizes: FFMA path
     assert pack_mlp_tc(S.mlp_layers(g, 40, (32, 32), 9), 40) is None     # too many parent dims
     assert pack_mlp_tc(S.mlp_layers(g, 3, (32, 32), 40), 3) is None      # too many outputs

@@ -118,8 +118,8 @@ def _core_matrix_image(w: np.ndarray) -> np.ndarray:
 
 def pack_mlp_tc(layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], input_dim: int):
     """Weight image for the tcgen05 kernel, or None when the MLP is not [Dp<=32 -> 32 -> 32 -> O<=32].
-    Layout (floats): W1hi, W1lo [32][K1]; W2hi, W2lo [32][32]; W3hi, W3lo [N3][32] (all core-matrix
-    images of nn.Linear's [out][in] = [N][K] K-major weight); b1[32], b2[32], b3[N3]."""
+    Layout (floats): W1hi, W1lo [32][K1+8]; W2hi, W2lo [32][40]; W3hi, W3lo [N3][40] -- core-matrix images of
+    nn.Linear's [out][in] = [N][K] K-major weight with the bias appended as column K (then 7 zero columns)."""
     if len(layers) != 3:
         return None
     (w1, b1), (w2, b2), (w3, b3) = [(_f32(w).numpy(), _f32(b).numpy()) for w, b in layers]
@@ -133,10 +133,14 @@ def pack_mlp_tc(layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], input_dim: 
     w3p = np.zeros((n3, 32), np.float32)
     w3p[:n_out] = w3
     chunks = []
-    for w in (w1p, w2, w3p):
-        hi, lo = _split_tf32(w)
+    for w, b in ((w1p, b1), (w2, b2), (w3p, _padded(b3, n3))):
+        # the bias rides in an extra K = 8 step: column K holds b, columns K+1..K+7 are zero; the kernel pairs it
+        # with a constant A block (1, 0, ..., 0) so the first MMA of a layer writes the bias into the accumulator
+        ext = np.zeros((w.shape[0], w.shape[1] + 8), np.float32)
+        ext[:, : w.shape[1]] = w
+        ext[:, w.shape[1]] = b
+        hi, lo = _split_tf32(ext)
         chunks += [_core_matrix_image(hi), _core_matrix_image(lo)]
-    chunks += [b1.astype(np.float32), b2.astype(np.float32), _padded(b3, n3)]
     return np.concatenate(chunks), k1, n3
 
 

@@ -34,13 +34,14 @@ constexpr int kTmemCols = 512;
 constexpr int kColsPerWg = 96;
 constexpr int kColD = 0, kColAhi = 32, kColAlo = 64;
 constexpr int kHidden = 32;
-constexpr int kWbufBytes = 25088;  // >= largest weight image (K1 = 32, N3 = 32: 24960 B)
+constexpr int kWbufBytes = 30720;  // largest weight image (K1 = 32, N3 = 32): 2 * 4 * 3 * 32 * 40 B
+constexpr int kBiasK = 8;          // every layer carries its bias as one extra K = 8 step (column K of the image)
 constexpr int kMaxBufs = 4;
 constexpr int kCtrlBytes = 128;    // tmem address + up to 13 mbarriers
 
-// bytes of one weight image: W1 hi/lo [32][K1], W2 hi/lo [32][32], W3 hi/lo [N3][32], b1, b2, b3
+// bytes of one weight image: W1 hi/lo [32][K1+8], W2 hi/lo [32][40], W3 hi/lo [N3][40] (bias = column K)
 __host__ __device__ __forceinline__ int blob_bytes(int k1, int n3) {
-  return 4 * (2 * kHidden * k1 + 2 * kHidden * kHidden + 2 * n3 * kHidden + 2 * kHidden + n3);
+  return 4 * 2 * (kHidden * (k1 + kBiasK) + kHidden * (kHidden + kBiasK) + n3 * (kHidden + kBiasK));
 }
 
 // ---- PTX wrappers -----------------------------------------------------------------------
@@ -205,18 +206,23 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// 3xTF32 layer: D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi over K (multiple of 8), N columns.
-// B images are [N][K] K-major core-matrix layouts (see pack_mlp_tc): LBO = 128, SBO = K*32.
-// KS = number of K = 8 steps (compile time so the issue sequence is straight-line code on the
-// uniform datapath); one step covers two core matrices = 256 B = 16 descriptor units.
+// 3xTF32 layer: D = bias + A_lo*B_hi + A_hi*B_lo + A_hi*B_hi over K (multiple of 8), N columns.
+// B images are [N][K+8] K-major core-matrix layouts (see pack_mlp_tc): LBO = 128, SBO = (K+8)*32; the last
+// K = 8 step of the image is the bias column.  It is multiplied by the constant A block `ones` = (1, 0, .., 0)
+// with accumulate = 0, so the layer needs no accumulator preload and its epilogue no bias add (the lo part of
+// 1.0 is zero: two MMAs).  KS = number of K = 8 steps of the weights proper (compile time so the issue
+// sequence is straight-line code on the uniform datapath); one step covers two core matrices = 256 B = 16
+// descriptor units.
 template <int KS>
-__device__ __forceinline__ void issue_layer(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+__device__ __forceinline__ void issue_layer(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t ones, uint32_t b_hi,
                                             uint32_t b_lo, int n) {
   const uint32_t idesc = make_idesc(n);
-  const uint32_t sbo = static_cast<uint32_t>(KS) * 256u;
+  const uint32_t sbo = static_cast<uint32_t>(KS + 1) * 256u;
   const uint64_t dhi = make_b_desc(b_hi, 128u, sbo), dlo = make_b_desc(b_lo, 128u, sbo);
+  mma_tf32_ts(d, ones, dhi + 16 * KS, idesc, 0u);  // D = bias_hi
+  mma_tf32_ts(d, ones, dlo + 16 * KS, idesc, 1u);  // D += bias_lo
 #pragma unroll
-  for (int s = 0; s < KS; ++s) mma_tf32_ts(d, a_lo + 8 * s, dhi + 16 * s, idesc, 1u);  // D holds the bias
+  for (int s = 0; s < KS; ++s) mma_tf32_ts(d, a_lo + 8 * s, dhi + 16 * s, idesc, 1u);
 #pragma unroll
   for (int s = 0; s < KS; ++s) mma_tf32_ts(d, a_hi + 8 * s, dlo + 16 * s, idesc, 1u);
 #pragma unroll
@@ -230,6 +236,7 @@ struct TcMlp {
   static constexpr bool kInlineRng = false;  // measured: inlining costs registers here (138.6 vs 135.5 ms on cfg5)
   uint32_t t_d, t_ahi, t_alo;  // TMEM addresses for this thread's warp (lane base folded in)
   uint32_t m_d, m_ahi, m_alo;  // same columns, lane 0: operands of the MMA
+  uint32_t m_ones;             // 8 columns shared by all warpgroups holding (1, 0, ..., 0): A operand of the bias step
   uint32_t wbuf;               // shared-space address of weight buffer 0
   const unsigned char* wbuf_ptr;
   uint32_t full_bar, empty_bar, mma_bar;  // full/empty: arrays of nbuf; mma_bar: this warpgroup's
@@ -280,10 +287,10 @@ struct TcMlp {
     if (warp_in_wg == 0) {  // warp-uniform: operands stay on the uniform datapath
       if (elect_one()) {
         switch (k) {
-          case 8: issue_layer<1>(m_d, m_ahi, m_alo, b_hi, b_lo, n); break;
-          case 16: issue_layer<2>(m_d, m_ahi, m_alo, b_hi, b_lo, n); break;
-          case 24: issue_layer<3>(m_d, m_ahi, m_alo, b_hi, b_lo, n); break;
-          default: issue_layer<4>(m_d, m_ahi, m_alo, b_hi, b_lo, n); break;
+          case 8: issue_layer<1>(m_d, m_ahi, m_alo, m_ones, b_hi, b_lo, n); break;
+          case 16: issue_layer<2>(m_d, m_ahi, m_alo, m_ones, b_hi, b_lo, n); break;
+          case 24: issue_layer<3>(m_d, m_ahi, m_alo, m_ones, b_hi, b_lo, n); break;
+          default: issue_layer<4>(m_d, m_ahi, m_alo, m_ones, b_hi, b_lo, n); break;
         }
         mma_commit(mma_bar);
       }
@@ -294,26 +301,8 @@ struct TcMlp {
     tc_fence_after();
   }
 
-  // D <- bias (identical for every row).  Every MMA of the layer then accumulates, so the
-  // epilogues carry no bias add.  Completion is covered by the tmem_wait_st() before the barrier.
-  __device__ __forceinline__ void preload_bias(const float* bias, int n) {
-    for (int o0 = 0; o0 < n; o0 += 16) {
-      uint32_t b[16];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 t = *reinterpret_cast<const float4*>(bias + o0 + 4 * q);
-        b[4 * q + 0] = __float_as_uint(t.x);
-        b[4 * q + 1] = __float_as_uint(t.y);
-        b[4 * q + 2] = __float_as_uint(t.z);
-        b[4 * q + 3] = __float_as_uint(t.w);
-      }
-      tmem_st16(t_d + o0, b);
-    }
-  }
-
-  // D (32 fp32 columns, bias included) -> activation -> 3xTF32 split -> A_hi / A_lo; then D <- the
-  // next layer's bias
-  __device__ __forceinline__ void hidden_epilogue(int act, const float* next_bias, int next_n) {
+  // D (32 fp32 columns, bias included) -> activation -> 3xTF32 split -> A_hi / A_lo
+  __device__ __forceinline__ void hidden_epilogue(int act) {
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       uint32_t v[16], hi[16], lo[16];
@@ -331,7 +320,6 @@ struct TcMlp {
       tmem_st16(t_ahi + 16 * half, hi);
       tmem_st16(t_alo + 16 * half, lo);
     }
-    preload_bias(next_bias, next_n);
     tmem_wait_st();
   }
 
@@ -348,12 +336,11 @@ struct TcMlp {
     const uint32_t buf = w_buf & 0xFFu;
     const uint32_t ph = w_buf >> 8;
     const uint32_t w1hi = wbuf + buf * kWbufBytes;
-    const uint32_t w1lo = w1hi + kHidden * k1 * 4;
-    const uint32_t w2hi = w1lo + kHidden * k1 * 4;
-    const uint32_t w2lo = w2hi + kHidden * kHidden * 4;
-    const uint32_t w3hi = w2lo + kHidden * kHidden * 4;
-    const uint32_t w3lo = w3hi + n3 * kHidden * 4;
-    const float* bias = reinterpret_cast<const float*>(wbuf_ptr + (w3lo + n3 * kHidden * 4 - wbuf));
+    const uint32_t w1lo = w1hi + kHidden * (k1 + kBiasK) * 4;
+    const uint32_t w2hi = w1lo + kHidden * (k1 + kBiasK) * 4;
+    const uint32_t w2lo = w2hi + kHidden * (kHidden + kBiasK) * 4;
+    const uint32_t w3hi = w2lo + kHidden * (kHidden + kBiasK) * 4;
+    const uint32_t w3lo = w3hi + n3 * (kHidden + kBiasK) * 4;
 
     // ---- inputs -> A (K1 columns, zero padded); gaussian_nn standardises them first
     if (op.flags & VBN_F_PAR4) {  // <= 4 parent dims, slots packed in aux[1..2]: K1 == 8
@@ -388,17 +375,16 @@ struct TcMlp {
         tmem_st8(t_alo + k0, lo);
       }
     }
-    mbar_wait(full_bar + 8 * buf, ph);  // weights + biases of this op have landed
-    preload_bias(bias, kHidden);
     tmem_wait_st();
+    mbar_wait(full_bar + 8 * buf, ph);  // weights + biases of this op have landed
 
     run_layer(w1hi, w1lo, k1, kHidden);
-    hidden_epilogue(op.act, bias + kHidden, kHidden);
+    hidden_epilogue(op.act);
     run_layer(w2hi, w2lo, kHidden, kHidden);
-    hidden_epilogue(op.act, bias + 2 * kHidden, n3);
+    hidden_epilogue(op.act);
     run_layer(w3hi, w3lo, kHidden, n3);
 
-    // this warp is done with the weight buffer (its MMAs completed, biases consumed)
+    // this warp is done with the weight buffer (its MMAs completed)
     __syncwarp();
     if (lane == 0) mbar_arrive(empty_bar + 8 * buf);
     ++w_iter;
@@ -492,7 +478,7 @@ struct TcMlp {
 template <int NWG>
 __global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const ScheduleArgs a, const int nbuf) {
   constexpr int kThreads = NWG * kWgThreads;
-  static_assert(NWG <= kMaxWg && NWG * kColsPerWg <= kTmemCols, "TMEM budget");
+  static_assert(NWG <= kMaxWg && NWG * kColsPerWg + kBiasK <= kTmemCols, "TMEM budget");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform for the compiler
@@ -526,6 +512,14 @@ __global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const S
   const int64_t per_round = static_cast<int64_t>(gridDim.x) * NWG;
   const int64_t n_iter = (n_tiles + per_round - 1) / per_round;  // same for every warpgroup: the ring needs it
 
+  {  // constant A block of the bias step: columns [NWG*96, NWG*96 + 8) of every lane = (1, 0, ..., 0)
+    const uint32_t ones[8] = {__float_as_uint(1.0f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    if (warp < 4) tmem_st8(tmem_base + NWG * kColsPerWg + (static_cast<uint32_t>(warp * 32) << 16), ones);
+    tmem_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
   Ctx<1, kThreads, TcMlp> c(a, slots, 0);  // the thread index is already folded into `slots`
   const int wg = warp >> 2;
   const uint32_t col = tmem_base + static_cast<uint32_t>(wg * kColsPerWg);
@@ -543,6 +537,7 @@ __global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const S
   c.tc.m_alo = c.tc.m_d + (kColAlo - kColD);
   c.tc.t_ahi = c.tc.t_d + (kColAhi - kColD);
   c.tc.t_alo = c.tc.t_d + (kColAlo - kColD);
+  c.tc.m_ones = tmem_base + NWG * kColsPerWg;
   c.tc.wbuf = wbuf;
   c.tc.wbuf_ptr = smem_raw + kCtrlBytes;
   c.tc.full_bar = full_bar;
