@@ -86,6 +86,13 @@ extern "C" {
                                   renormalised pi (mdn.py:227-228); then (loc_k, scale_k) for
                                   k = 0..K-1, scale_k = softplus(raw_k) + min_scale}; tc[] =
                                   {out_slot, n_off, u_off, K}.  The kernel reads quads 0,4,5,6,7  */
+#define VBN_F_TABPLAIN 0x1000   /* TAB op that is only drawn (Philox, no store, no density), <= 4 parents, every
+                                  parent's class values and its own sample values coded 0..k-1: the class index
+                                  IS the value, so the per-parent search and the value gather disappear.
+                                  layer_dim[p] = stride_p | card_p << 16 (p < 4), layer_dim[4] = float offset of
+                                  the cdf[n_cfg][C] table in the parameter blob, layer_dim[5] = C | strict << 16,
+                                  layer_dim[6] = out_slot, layer_dim[7] = u_off; aux[0..1] = packed parent slots.
+                                  The kernel reads quads 0,4,5,6                                            */
 #define VBN_F_LGPLAIN 0x80     /* LGFAST op that is only drawn: Philox, per-row stream, no store,
                                   no density -- the kernel reads nothing but quads 0,4,5,6      */
 

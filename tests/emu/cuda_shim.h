@@ -43,6 +43,7 @@ inline float __expf(float x) { return std::exp(x); }
 inline void __sincosf(float x, float* s, float* c) { *s = std::sin(x); *c = std::cos(x); }
 inline float __fdiv_rn(float a, float b) { return a / b; }
 inline float __fdividef(float a, float b) { return a / b; }
+inline int __float2int_rz(float x) { return (x != x || x >= 2147483648.0f || x < -2147483648.0f) ? 0 : static_cast<int>(x); }
 inline float fmaf_(float a, float b, float c) { return std::fma(a, b, c); }
 inline int atomicOr(int32_t* p, int v) { int o = *p; *p |= v; return o; }
 using std::min;

@@ -381,6 +381,26 @@ def test_root_mdn_fast_path_reproduces_the_generic_path(backend, monkeypatch):
     assert ok > 0.99, ok
 
 
+def test_plain_table_ops_reproduce_the_generic_lookup(backend, monkeypatch):
+    """VBN_F_TABPLAIN (class index = value, descriptor-embedded strides) vs the generic VBN_OP_TAB body on the same
+    Philox streams: identical draws and weights, bit for bit."""
+    from vectorizedbayesiannetwork_b200 import _lib as L
+
+    spec = S.alarm_softmax(seed=0)
+    g = torch.Generator().manual_seed(4)
+    ev = {n: torch.randint(0, S.ALARM[n][0], (6, 1), generator=g).float() for n in ("HRBP", "BP", "EXPCO2", "PRESS")}
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("VBN_TABPLAIN", flag)
+        model = V.VBN.from_spec(spec, device=backend.device)
+        model.set_inference_method("likelihood_weighting", n_samples=257)
+        w, s = model.infer_posterior({"target": "LVFAILURE", "evidence": ev}, seed=21)
+        ops = next(iter(model._inference._runner._cache.values())).program.ops
+        out[flag] = (w.cpu(), s.cpu(), sum(1 for op in ops if int(op["flags"]) & L.F_TABPLAIN))
+    assert out["0"][2] == 0 and out["1"][2] >= 30
+    assert torch.equal(out["0"][1], out["1"][1]) and torch.equal(out["0"][0], out["1"][0])
+
+
 # ---- CPDHandle.conditional formats (vbn/core/cpd_handle.py:40-118, 348-402; tests/test_cpd_handle.py:61-88)
 def test_conditional_formats_match_the_parameter_heads(backend):
     import os

@@ -140,15 +140,14 @@ struct Ctx {
     }
     if constexpr (TC::kLoops) index += 4 * rows.loop_iter * rows.loop_nq;
     const int q = index >> 2, lane = index & 3;
-    if (shared) {
+    // one cache serves both streams (key = block | shared << 30): shared draws are the roots of LW / MCM /
+    // ancestral passes, which sit next to each other at the head of the schedule, so four of them share one
+    // Philox call instead of paying one each
+    const int key = q | (shared ? 0x40000000 : 0);
+    if (key != rows.cur_nq) {
+      rows.cur_nq = key;
 #pragma unroll
-      for (int j = 0; j < RPT; ++j) out[j] = lane4(normals(j, q, 2u, true), lane);
-      return;
-    }
-    if (q != rows.cur_nq) {
-      rows.cur_nq = q;
-#pragma unroll
-      for (int j = 0; j < RPT; ++j) rows.ncache[j] = normals(j, q, 0u, false);
+      for (int j = 0; j < RPT; ++j) rows.ncache[j] = normals(j, q, shared ? 2u : 0u, shared);
     }
 #pragma unroll
     for (int j = 0; j < RPT; ++j) out[j] = lane4(rows.ncache[j], lane);
@@ -165,15 +164,11 @@ struct Ctx {
     }
     if constexpr (TC::kLoops) index += 4 * rows.loop_iter * rows.loop_uq;
     const int q = index >> 2, lane = index & 3;
-    if (shared) {
+    const int key = q | (shared ? 0x40000000 : 0);  // see draw_normal
+    if (key != rows.cur_uq) {
+      rows.cur_uq = key;
 #pragma unroll
-      for (int j = 0; j < RPT; ++j) out[j] = lane4(uniforms(j, q, 3u, true), lane);
-      return;
-    }
-    if (q != rows.cur_uq) {
-      rows.cur_uq = q;
-#pragma unroll
-      for (int j = 0; j < RPT; ++j) rows.ucache[j] = uniforms(j, q, 1u, false);
+      for (int j = 0; j < RPT; ++j) rows.ucache[j] = uniforms(j, q, shared ? 3u : 1u, shared);
     }
 #pragma unroll
     for (int j = 0; j < RPT; ++j) out[j] = lane4(rows.ucache[j], lane);
@@ -1082,6 +1077,54 @@ __device__ __forceinline__ void op_params(Ctx<RPT, NT, TC>& c, const VbnOp& op) 
   }
 }
 
+// VBN_F_TABPLAIN: a TAB op that is simply drawn and whose parents and own classes are coded 0..k-1, so the
+// class index is the value: no per-parent search, no value gather, no parameter-block header reads.
+// Everything but the cdf rows rides in quads 0,4,5,6.  This is the inner loop of ALARM-style discrete
+// networks (BASELINE cfg3: 33 of 37 ops).
+template <int RPT, int NT, class TC>
+__device__ __forceinline__ void op_tab_plain(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
+  const int Dp = op.n_par;
+  const int C = op.layer_dim[5] & 0xFFFF;
+  const bool strict = (op.layer_dim[5] >> 16) != 0;
+  const float* cdf = c.a.params + op.layer_dim[4];
+  int cfg[RPT];
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) cfg[j] = 0;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    if (p < Dp) {
+      const int ps = (op.aux[p >> 1] >> (16 * (p & 1))) & 0xFFFF;
+      const int stride = op.layer_dim[p] & 0xFFFF, card = op.layer_dim[p] >> 16;
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        const float v = c.slot(ps, j);
+        int ci = __float2int_rz(v);
+        if (static_cast<float>(ci) != v || static_cast<unsigned>(ci) >= static_cast<unsigned>(card)) {
+          if (strict && c.rows.valid[j] && c.a.error_flag) atomicOr(c.a.error_flag, 1);
+          ci = 0;
+        }
+        cfg[j] += ci * stride;
+      }
+    }
+  }
+  const bool shared = (op.flags & VBN_F_SHARED) != 0;
+  const int u_off = op.layer_dim[7], q = u_off >> 2, lane = u_off & 3;
+  const int key = q | (shared ? 0x40000000 : 0);
+  if (key != c.rows.cur_uq) {
+    c.rows.cur_uq = key;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) c.rows.ucache[j] = c.uniforms(j, q, shared ? 3u : 1u, shared);
+  }
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    const float* row = cdf + cfg[j] * C;
+    const float t = lane4(c.rows.ucache[j], lane) * __ldg(row + C - 1);
+    int k = 0;
+    for (int qq = 0; qq < C - 1; ++qq) k += (t >= __ldg(row + qq)) ? 1 : 0;
+    c.slot(op.layer_dim[6], j) = static_cast<float>(k);
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // VBN_OP_RFF: rff_gaussian.py:131-146 (_normalize_parents, _features), 185-206 (_params),
 // 254-291 (sample, log_prob).
@@ -1388,15 +1431,30 @@ __device__ __forceinline__ void run_ops(Ctx<RPT, NT, TC>& c) {
         int4* dst = reinterpret_cast<int4*>(&op);
         dst[0] = q0; dst[1] = q1; dst[2] = q2; dst[3] = q3; dst[4] = q4; dst[5] = q5; dst[6] = q6; dst[7] = q7;
       } else {
+      // quads 4-6 (what a plain LG op needs) are requested together with quad 0: one L1 round trip per op
+      const int4 q4 = __ldg(src + 4), q5 = __ldg(src + 5), q6 = __ldg(src + 6);
       if (q0.y & VBN_F_LGPLAIN) {
         VbnOp lop;
         int4* ld = reinterpret_cast<int4*>(&lop);
         ld[0] = q0;
-        ld[4] = __ldg(src + 4);  // bias, scale, 2 ln scale, var
-        ld[5] = __ldg(src + 5);  // w0..w3
-        ld[6] = __ldg(src + 6);  // packed parent slots, out_slot, n_off
+        ld[4] = q4;  // bias, scale, 2 ln scale, var
+        ld[5] = q5;  // w0..w3
+        ld[6] = q6;  // packed parent slots, out_slot, n_off
         c.gop = a.ops + i;
         op_lg_plain(c, lop);
+        continue;
+      }
+      // (only in the <= 2 rows-per-thread shapes, which is where schedules with table ops are placed: the
+      // 4-row linear-Gaussian shapes keep their loop body small; there the op takes the generic lookup)
+      if (RPT <= 2 && (q0.y & VBN_F_TABPLAIN)) {
+        VbnOp lop;
+        int4* ld = reinterpret_cast<int4*>(&lop);
+        ld[0] = q0;
+        ld[4] = q4;  // stride | card << 16 per parent
+        ld[5] = q5;  // cdf offset, C | strict << 16, out_slot, u_off
+        ld[6] = q6;  // packed parent slots
+        c.gop = a.ops + i;
+        op_tab_plain(c, lop);
         continue;
       }
       if (HEAVY && (q0.y & VBN_F_MDNROOT)) {

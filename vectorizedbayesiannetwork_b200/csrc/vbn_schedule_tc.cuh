@@ -301,25 +301,30 @@ struct TcMlp {
     tc_fence_after();
   }
 
-  // D (32 fp32 columns, bias included) -> activation -> 3xTF32 split -> A_hi / A_lo
-  __device__ __forceinline__ void hidden_epilogue(int act) {
+  // D (32 fp32 columns, bias included) -> activation -> 3xTF32 split -> A_hi / A_lo.
+  // Both halves of the accumulator row are requested before the first is processed, so the second
+  // TMEM read is in flight while the first half is split.
+  __device__ __forceinline__ void split_half(int act, const uint32_t (&v)[16], int half) {
+    uint32_t hi[16], lo[16];
+    if (act == VBN_ACT_RELU) {
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t v[16], hi[16], lo[16];
-      tmem_ld16(t_d + 16 * half, v);
-      tmem_wait_ld();
-      if (act == VBN_ACT_RELU) {
+      for (int q = 0; q < 16; q += 2)
+        split_tf32_x2(fmaxf(__uint_as_float(v[q]), 0.0f), fmaxf(__uint_as_float(v[q + 1]), 0.0f), hi[q],
+                      hi[q + 1], lo[q], lo[q + 1]);
+    } else {
 #pragma unroll
-        for (int q = 0; q < 16; q += 2)
-          split_tf32_x2(fmaxf(__uint_as_float(v[q]), 0.0f), fmaxf(__uint_as_float(v[q + 1]), 0.0f), hi[q],
-                        hi[q + 1], lo[q], lo[q + 1]);
-      } else {
-#pragma unroll
-        for (int q = 0; q < 16; ++q) split_tf32(activate_slow(__uint_as_float(v[q]), act), hi[q], lo[q]);
-      }
-      tmem_st16(t_ahi + 16 * half, hi);
-      tmem_st16(t_alo + 16 * half, lo);
+      for (int q = 0; q < 16; ++q) split_tf32(activate_slow(__uint_as_float(v[q]), act), hi[q], lo[q]);
     }
+    tmem_st16(t_ahi + 16 * half, hi);
+    tmem_st16(t_alo + 16 * half, lo);
+  }
+  __device__ __forceinline__ void hidden_epilogue(int act) {
+    uint32_t v0[16], v1[16];
+    tmem_ld16(t_d, v0);
+    tmem_ld16(t_d + 16, v1);
+    tmem_wait_ld();
+    split_half(act, v0, 0);
+    split_half(act, v1, 1);
     tmem_wait_st();
   }
 

@@ -72,6 +72,38 @@ def _roots_enabled() -> bool:
     return os.environ.get("VBN_MDNROOT", "1") != "0"
 
 
+def _tabplain_enabled() -> bool:
+    """VBN_TABPLAIN=0 keeps drawn table nodes on the generic lookup op (A/B + equivalence test)."""
+    return os.environ.get("VBN_TABPLAIN", "1") != "0"
+
+
+def _tab_plain_fields(pk: Packed, slots: Sequence[int], param_off: int, out_slot: int, u_off: int):
+    """VBN_F_TABPLAIN descriptor words (include/vbn_cuda.h) of a table op, or None when a parent's classes or
+    the node's own values are not coded 0..k-1.  Parses the VBN_OP_TAB block (cpds._tab_params)."""
+    P = pk.params
+    c, n_cfg, cpad, strict = int(P[0]), int(P[1]), int(P[2]), int(P[3] != 0)
+    words = [0] * 12
+    for p in range(pk.n_par):
+        pi = 4 + (4 + cpad) * p
+        card, stride = int(P[pi]), int(P[pi + 1])
+        if stride >= 65536 or card >= 32768 or not np.array_equal(P[pi + 4: pi + 4 + card], np.arange(card, dtype=np.float32)):
+            return None
+        words[p] = stride | (card << 16)
+    sv = 4 + (4 + cpad) * pk.n_par
+    if not np.array_equal(P[sv: sv + c], np.arange(c, dtype=np.float32)):
+        return None
+    if max(list(slots) + [out_slot]) >= 65536 or c >= 65536:
+        return None
+    words[4] = int(param_off) + sv + 2 * cpad       # cdf[n_cfg][C]
+    words[5] = c | (strict << 16)
+    words[6] = int(out_slot)
+    words[7] = int(u_off)
+    sl = list(slots) + [0] * (4 - len(slots))
+    words[8] = sl[0] | (sl[1] << 16)
+    words[9] = sl[2] | (sl[3] << 16)
+    return words
+
+
 def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpds: Dict[str, BaseCPD],
                      roles: Dict[str, Role], use_tc: Optional[bool] = None, table_fn=None) -> Program:
     """``topo``: nodes to emit, in topological order (nodes absent from ``roles`` are skipped).
@@ -277,6 +309,16 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
                 op["aux"][:] = emb[8:].view(np.int32)
                 op["tc"][:] = [slot_of[n], int(op["n_off"]), int(op["u_off"]), pk.k]
                 flags |= L.F_MDNROOT
+            if (_tabplain_enabled() and pk.kind == L.OP_TAB and d == 1 and pk.n_par <= 4 and r.src == "sample"
+                    and not r.inject and not r.store and not r.add_logw and not r.out_logp and not r.out_params):
+                # (the tensor-core kernel has no TABPLAIN branch: there the op runs the generic lookup, which
+                # reads none of the words rewritten here)
+                emb = _tab_plain_fields(pk, par_slots[len(par_slots) - pk.n_par:] if pk.n_par else [],
+                                        param_off[id(pk)], slot_of[n], int(op["u_off"]))
+                if emb is not None:
+                    op["layer_dim"][:] = emb[:8]
+                    op["aux"][:] = emb[8:]
+                    flags |= L.F_TABPLAIN
             if r.out_params:
                 flags |= L.F_OUT_PARAMS
                 heavy = True  # the read-out lives in the HEAVY kernels only
