@@ -1287,6 +1287,36 @@ def ancestral_sample(spec, query, n_samples: int, noise=None):
 
 
 # --------------------------------------------------------------------------------------
+# "lbp" (vbn/inference/lbp.py:11-70): a wrapper -- one IS / MCM pass, a damped re-normalisation of the
+# weights until the largest change is below tol, else a fresh IS pass
+# --------------------------------------------------------------------------------------
+
+
+def lbp(spec, query, n_samples: int, noise=None, n_iters: int = 10, damping: float = 0.5, tol: float = 1e-4,
+        fallback: str = "importance_sampling"):
+    eps = 1e-12
+    if fallback == "monte_carlo_marginalization":  # :43-47
+        pdf, target = monte_carlo_marginalization(spec, query, n_samples, noise)
+        weights = pdf / (pdf.sum(dim=-1, keepdim=True) + eps)
+    else:
+        weights, target = importance_sampling(spec, query, n_samples, noise)
+    converged = False
+    for _ in range(max(int(n_iters), 0)):  # :52-63
+        w_new = torch.clamp(weights, min=eps)
+        w_new = w_new / (w_new.sum(dim=-1, keepdim=True) + eps)
+        msg = damping * w_new + (1.0 - damping) * weights
+        msg = msg / (msg.sum(dim=-1, keepdim=True) + eps)
+        delta = (msg - weights).abs().max().item()
+        weights = msg
+        if delta < tol:
+            converged = True
+            break
+    if not converged:  # :65-66
+        return importance_sampling(spec, query, n_samples, noise)
+    return weights, target
+
+
+# --------------------------------------------------------------------------------------
 # Gibbs sampler (vbn/sampling/gibbs.py:23-92) -- SURVEY 8f row 4
 # --------------------------------------------------------------------------------------
 

@@ -106,7 +106,8 @@ def test_mlp_packing_layout():
 
 def test_registry_and_resolution_mirror_reference():
     assert set(V.INFERENCE_REGISTRY) == {"likelihood_weighting", "importance_sampling", "monte_carlo_marginalization",
-                                         "gaussian_exact", "categorical_exact", "resampled_importance_sampling", "rao_blackwellized_marginalization"}
+                                         "gaussian_exact", "categorical_exact", "resampled_importance_sampling", "rao_blackwellized_marginalization",
+                                         "lbp"}
     ge = V.INFERENCE_REGISTRY["gaussian_exact"](n_samples=31, fallback="likelihood_weighting")
     assert ge.n_samples == 31 and ge._fallback.n_samples == 31 and ge.stddevs == 4.0
     with pytest.raises(ValueError):

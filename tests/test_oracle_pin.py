@@ -361,3 +361,19 @@ def test_gibbs_sampler():
     m = refmodels.table_model(rows=300, epochs=1)
     spec = O.spec_from_reference(m)
     run(m, spec, {"target": "rain", "evidence": {"slip": torch.tensor([[1.0]])}}, 7, burn_in=2)
+
+
+def test_lbp_wrapper():
+    """vbn/inference/lbp.py:11-70 with both fallbacks, converged and not (tol = 0 forces the retry pass)."""
+    model = refmodels.lg_chain_model(n_nodes=5)
+    spec = O.spec_from_reference(model)
+    ev = torch.tensor([[0.2], [1.0], [-0.7]])
+    q = {"target": "x1", "evidence": {"x4": ev}, "do": {}}
+    for kw in ({}, {"fallback": "monte_carlo_marginalization"}, {"n_iters": 2, "damping": 0.9}):
+        model.set_inference_method("lbp", n_samples=40, **kw)
+        for call_kw in ({}, {"tol": 0.0}):
+            torch.manual_seed(8)
+            rw, rs = model.infer_posterior(q, **call_kw)
+            torch.manual_seed(8)
+            ow, os_ = O.lbp(spec, q, 40, **kw, **call_kw)
+            _eq(rw, ow), _eq(rs, os_)

@@ -566,6 +566,28 @@ def test_categorical_embedded_softmax_strict_support_conditional_and_frequencies
         V.cpd_from_spec(unfitted, device=backend.device).sample(pa, 4)
 
 
+# ---- "lbp" wrapper (vbn/inference/lbp.py; tests/test_inference.py:27-59) -----------------------------
+def test_lbp_wrapper_matches_its_definition(backend):
+    model = _chain(backend.device, n=4)
+    ev = {"x3": torch.tensor([[0.4], [-1.0]])}
+    q = {"target": "x1", "evidence": ev}
+    model.set_inference_method("importance_sampling", n_samples=300, ess_threshold=0.0)
+    w0, s0 = model.infer_posterior(q, seed=12)
+    model.set_inference_method("lbp", n_samples=300)
+    model._inference._is.ess_threshold = 0.0
+    w1, s1 = model.infer_posterior(q, seed=12)
+    assert w1.shape == (2, 300) and s1.shape == (2, 300, 1) and torch.equal(s0, s1)
+    # already-normalised weights are a fixed point of the damped update (lbp.py:52-63): converges at once
+    torch.testing.assert_close(w1, w0, rtol=1e-5, atol=1e-9)
+    with pytest.raises(ValueError):
+        V.INFERENCE_REGISTRY["lbp"](damping=1.5)
+    with pytest.raises(ValueError):
+        V.INFERENCE_REGISTRY["lbp"](fallback="likelihood_weighting")
+    model.set_inference_method("lbp", n_samples=64, fallback="monte_carlo_marginalization")
+    w2, s2 = model.infer_posterior(q, seed=3)
+    torch.testing.assert_close(w2.sum(1).cpu(), torch.ones(2), rtol=1e-4, atol=1e-5)
+
+
 # ---- Gibbs sampler (vbn/sampling/gibbs.py; tests/test_sampling.py:46-56) -----------
 def test_gibbs_sampler_philox_path(backend):
     model = _mixed(backend.device)

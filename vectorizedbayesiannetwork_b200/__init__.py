@@ -12,7 +12,7 @@ from .cpds import (BaseCPD, CategoricalEmbeddedSoftmaxCPD, CategoricalTableCPD, 
                    cpd_from_spec, wrap_cpd)
 from .dist import Shard, auto_shard
 from .inference import (AncestralSampler, CategoricalExact, GaussianExact, GibbsSampler, ImportanceSampling,
-                        LikelihoodWeighting, MonteCarloMarginalization, RaoBlackwellizedMarginalization,
+                        LikelihoodWeighting, LoopyBeliefPropagation, MonteCarloMarginalization, RaoBlackwellizedMarginalization,
                         ResampledImportanceSampling)
 from .install import install, uninstall
 
@@ -21,7 +21,7 @@ __all__ = [
     "INFERENCE_REGISTRY", "SAMPLING_REGISTRY",
     "BaseCPD", "LinearGaussianCPD", "GaussianNNCPD", "MDNCPD", "SoftmaxNNCPD", "KDECPD", "RFFGaussianCPD", "CategoricalTableCPD", "CategoricalEmbeddedSoftmaxCPD",
     "cpd_from_spec", "wrap_cpd",
-    "ImportanceSampling", "LikelihoodWeighting", "MonteCarloMarginalization", "AncestralSampler", "GibbsSampler",
+    "ImportanceSampling", "LikelihoodWeighting", "MonteCarloMarginalization", "AncestralSampler", "GibbsSampler", "LoopyBeliefPropagation",
     "GaussianExact", "CategoricalExact", "ResampledImportanceSampling", "RaoBlackwellizedMarginalization",
     "Shard", "auto_shard", "install", "uninstall",
 ]

@@ -5,7 +5,7 @@ The registry decorator refuses duplicate keys (registry.py:18-20), hence plain d
 from __future__ import annotations
 
 from .inference import (AncestralSampler, CategoricalExact, GaussianExact, GibbsSampler, ImportanceSampling,
-                        LikelihoodWeighting, MonteCarloMarginalization, RaoBlackwellizedMarginalization,
+                        LikelihoodWeighting, LoopyBeliefPropagation, MonteCarloMarginalization, RaoBlackwellizedMarginalization,
                         ResampledImportanceSampling)
 
 _ORIGINAL = {}
@@ -20,7 +20,8 @@ def install(vbn_module=None) -> None:
                      ("monte_carlo_marginalization", MonteCarloMarginalization),
                      ("gaussian_exact", GaussianExact), ("categorical_exact", CategoricalExact),
                      ("resampled_importance_sampling", ResampledImportanceSampling),
-                     ("rao_blackwellized_marginalization", RaoBlackwellizedMarginalization)):
+                     ("rao_blackwellized_marginalization", RaoBlackwellizedMarginalization),
+                     ("lbp", LoopyBeliefPropagation)):
         _ORIGINAL.setdefault(("inference", key), reg.INFERENCE_REGISTRY.get(key))
         reg.INFERENCE_REGISTRY[key] = cls
     for key, cls in (("ancestral", AncestralSampler), ("gibbs", GibbsSampler)):
