@@ -233,7 +233,7 @@ __device__ __forceinline__ void issue_layer(uint32_t d, uint32_t a_hi, uint32_t 
 struct TcMlp {
   static constexpr bool kEnabled = true;
   static constexpr bool kLoops = false;      // Gibbs programs never carry tensor-core images
-  static constexpr bool kInlineRng = false;  // measured: inlining costs registers here (138.6 vs 135.5 ms on cfg5)
+  static constexpr bool kInlineRng = true;   // inlined generator with constant-bank round keys: 80.4 -> 78.8 ms on cfg5 (it lost when registers were tighter)
   uint32_t t_d, t_ahi, t_alo;  // TMEM addresses for this thread's warp (lane base folded in)
   uint32_t m_d, m_ahi, m_alo;  // same columns, lane 0: operands of the MMA
   uint32_t m_ones;             // 8 columns shared by all warpgroups holding (1, 0, ..., 0): A operand of the bias step
