@@ -1118,9 +1118,25 @@ __device__ __forceinline__ void op_tab_plain(Ctx<RPT, NT, TC>& c, const VbnOp& o
 #pragma unroll
   for (int j = 0; j < RPT; ++j) {
     const float* row = cdf + cfg[j] * C;
-    const float t = lane4(c.rows.ucache[j], lane) * __ldg(row + C - 1);
+    const float u = lane4(c.rows.ucache[j], lane);
     int k = 0;
-    for (int qq = 0; qq < C - 1; ++qq) k += (t >= __ldg(row + qq)) ? 1 : 0;
+    // the common cardinalities get straight-line code: fixed-offset loads, no loop control
+    if (C == 2) {
+      const float c0 = __ldg(row), c1 = __ldg(row + 1);
+      k = (u * c1 >= c0) ? 1 : 0;
+    } else if (C == 3) {
+      const float c0 = __ldg(row), c1 = __ldg(row + 1), c2 = __ldg(row + 2);
+      const float t = u * c2;
+      k = ((t >= c0) ? 1 : 0) + ((t >= c1) ? 1 : 0);
+    } else if (C == 4) {
+      const float c0 = __ldg(row), c1 = __ldg(row + 1), c2 = __ldg(row + 2), c3 = __ldg(row + 3);
+      const float t = u * c3;
+      k = ((t >= c0) ? 1 : 0) + ((t >= c1) ? 1 : 0) + ((t >= c2) ? 1 : 0);
+    } else {
+      const float t = u * __ldg(row + C - 1);
+#pragma unroll 1
+      for (int qq = 0; qq < C - 1; ++qq) k += (t >= __ldg(row + qq)) ? 1 : 0;
+    }
     c.slot(op.layer_dim[6], j) = static_cast<float>(k);
   }
 }
@@ -1543,12 +1559,20 @@ template <int RPT, int NT, bool HEAVY, int MIN_BLOCKS>
 __global__ void __launch_bounds__(NT, MIN_BLOCKS) schedule_kernel(const ScheduleArgs a) {
   extern __shared__ __align__(16) float smem[];
   constexpr int ROWS = RPT * NT;
-  Ctx<RPT, NT, typename std::conditional<HEAVY, NoTc, LightPolicy>::type> c(a, smem, threadIdx.x);
+  // The thread index and the Philox counter words are made opaque to the optimiser (empty asm): otherwise ptxas
+  // rematerialises them -- S2R tid in front of every slot access, the row -> (query, sample) division chain in
+  // front of every generator refill -- instead of keeping one register each (same finding as in the tcgen05 kernel).
+  int tid = threadIdx.x;
+  asm volatile("" : "+r"(tid));
+  Ctx<RPT, NT, typename std::conditional<HEAVY, NoTc, LightPolicy>::type> c(a, smem + tid, 0);
   const int64_t n_tiles = (a.n_rows + ROWS - 1) / ROWS;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t base = tile * ROWS;
 #pragma unroll
-    for (int j = 0; j < RPT; ++j) bind_row(c, j, base + j * NT + threadIdx.x);
+    for (int j = 0; j < RPT; ++j) {
+      bind_row(c, j, base + j * NT + tid);
+      asm volatile("" : "+r"(c.rows.gs[j]), "+r"(c.rows.gb[j]));
+    }
     run_ops<HEAVY>(c);
   }
 }
