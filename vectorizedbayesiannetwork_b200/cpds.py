@@ -521,7 +521,10 @@ class SoftmaxNNCPD(BaseCPD):
         aux = [L.WITHIN_BIN[self.within_bin], int(self.within_bin_clip), int(bool(self._is_discrete.any())), 0]
         gaussian = self.within_bin == "gaussian"
         common = dict(kind=L.OP_SNN, dim=d, k=k, n_out=d * k, aux=aux, scratch=d * k, heavy=True,
-                      n_normals=d if gaussian else 0, n_uniforms=d if gaussian else 2 * d)
+                      # per row: D picks, plus D within-bin uniforms unless the law is gaussian (normals) or every dim is
+                      # discrete (no within-bin draw at all: keeps four consecutive discrete nodes on one Philox block)
+                      n_normals=d if gaussian else 0,
+                      n_uniforms=d if (gaussian or bool(self._is_discrete.all())) else 2 * d)
         if dp == 0:
             t = self.temperature
             if self._root_ready:  # softmax_nn.py:636-641

@@ -139,18 +139,47 @@ struct Ctx {
       return;
     }
     if constexpr (TC::kLoops) index += 4 * rows.loop_iter * rows.loop_nq;
+    cached_normal(shared, index, out);
+  }
+
+  // Value `index & 3` of stream block `index >> 2` for all RPT rows, through the 4-value block cache.
+  // One cache serves both streams (key = block | shared << 30).  Shared draws are the roots of LW / MCM /
+  // ancestral passes; the plan compiler moves them to the head of the schedule (plan.py), where four of them
+  // share one generator call.  A shared draw that arrives while the cache holds a per-row block (roots left
+  // interleaved in a large DAG) bypasses the cache instead of evicting it.
+  __device__ __forceinline__ void cached_normal(bool shared, int index, float (&out)[RPT]) {
     const int q = index >> 2, lane = index & 3;
-    // one cache serves both streams (key = block | shared << 30): shared draws are the roots of LW / MCM /
-    // ancestral passes, which sit next to each other at the head of the schedule, so four of them share one
-    // Philox call instead of paying one each
     const int key = q | (shared ? 0x40000000 : 0);
-    if (key != rows.cur_nq) {
-      rows.cur_nq = key;
+    if (key == rows.cur_nq) {
 #pragma unroll
-      for (int j = 0; j < RPT; ++j) rows.ncache[j] = normals(j, q, shared ? 2u : 0u, shared);
+      for (int j = 0; j < RPT; ++j) out[j] = lane4(rows.ncache[j], lane);
+      return;
     }
+    const bool keep = !shared || rows.cur_nq < 0 || (rows.cur_nq & 0x40000000) != 0;
 #pragma unroll
-    for (int j = 0; j < RPT; ++j) out[j] = lane4(rows.ncache[j], lane);
+    for (int j = 0; j < RPT; ++j) {
+      const float4 blk = normals(j, q, shared ? 2u : 0u, shared);
+      if (keep) rows.ncache[j] = blk;
+      out[j] = lane4(blk, lane);
+    }
+    if (keep) rows.cur_nq = key;
+  }
+  __device__ __forceinline__ void cached_uniform(bool shared, int index, float (&out)[RPT]) {
+    const int q = index >> 2, lane = index & 3;
+    const int key = q | (shared ? 0x40000000 : 0);
+    if (key == rows.cur_uq) {
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) out[j] = lane4(rows.ucache[j], lane);
+      return;
+    }
+    const bool keep = !shared || rows.cur_uq < 0 || (rows.cur_uq & 0x40000000) != 0;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const float4 blk = uniforms(j, q, shared ? 3u : 1u, shared);
+      if (keep) rows.ucache[j] = blk;
+      out[j] = lane4(blk, lane);
+    }
+    if (keep) rows.cur_uq = key;
   }
 
   // uniform number `index`; `slot_in_noise` selects which injected array element to use
@@ -163,15 +192,7 @@ struct Ctx {
       return;
     }
     if constexpr (TC::kLoops) index += 4 * rows.loop_iter * rows.loop_uq;
-    const int q = index >> 2, lane = index & 3;
-    const int key = q | (shared ? 0x40000000 : 0);  // see draw_normal
-    if (key != rows.cur_uq) {
-      rows.cur_uq = key;
-#pragma unroll
-      for (int j = 0; j < RPT; ++j) rows.ucache[j] = uniforms(j, q, shared ? 3u : 1u, shared);
-    }
-#pragma unroll
-    for (int j = 0; j < RPT; ++j) out[j] = lane4(rows.ucache[j], lane);
+    cached_uniform(shared, index, out);
   }
 
   // injected categorical pick (per row, per dim `d` of `width` dims); returns false if absent
@@ -1107,18 +1128,12 @@ __device__ __forceinline__ void op_tab_plain(Ctx<RPT, NT, TC>& c, const VbnOp& o
       }
     }
   }
-  const bool shared = (op.flags & VBN_F_SHARED) != 0;
-  const int u_off = op.layer_dim[7], q = u_off >> 2, lane = u_off & 3;
-  const int key = q | (shared ? 0x40000000 : 0);
-  if (key != c.rows.cur_uq) {
-    c.rows.cur_uq = key;
-#pragma unroll
-    for (int j = 0; j < RPT; ++j) c.rows.ucache[j] = c.uniforms(j, q, shared ? 3u : 1u, shared);
-  }
+  float uu[RPT];
+  c.cached_uniform((op.flags & VBN_F_SHARED) != 0, op.layer_dim[7], uu);
 #pragma unroll
   for (int j = 0; j < RPT; ++j) {
     const float* row = cdf + cfg[j] * C;
-    const float u = lane4(c.rows.ucache[j], lane);
+    const float u = uu[j];
     int k = 0;
     // the common cardinalities get straight-line code: fixed-offset loads, no loop control
     if (C == 2) {

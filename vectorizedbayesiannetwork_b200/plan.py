@@ -115,6 +115,13 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
     lg_fast_ops: List[int] = []
     tc_list: List[tuple] = []
     order = [n for n in topo if n in roles]
+    # Roots whose draw is shared by all queries (LW / MCM / ancestral passes) go first -- still a topological
+    # order -- so that consecutive shared draws are served from one generator block (csrc cached_uniform /
+    # cached_normal).  Bounded: every hoisted root stays live until its first reader, which costs a slot each.
+    hoist = [n for n in order if roles[n].src == "sample" and roles[n].shared and not parents.get(n)]
+    if 1 < len(hoist) <= 32:
+        hs = set(hoist)
+        order = hoist + [n for n in order if n not in hs]
     index = {n: i for i, n in enumerate(order)}
     packed: Dict[str, Optional[Packed]] = {}
     dims: Dict[str, int] = {}
