@@ -173,3 +173,23 @@ def test_gibbs_chains_match_reference(backend):
             _close(got, case["expect"], f"gibbs:{m['name']}[{i}]", atol=atol)
             # the reference returns the chain's final state n times (views of the live state, gibbs.py:83-91)
             assert bool((got == got[:, :1]).all())
+
+
+def test_gibbs_multidim_latent_matches_oracle(backend):
+    """A 2-D latent node with a child (rff model: a, b -> c[2] -> d): candidates, scores and the selected value are
+    D-wide.  The oracle (pinned to the reference) records its draws; the CUDA chain replays them."""
+    spec = _load("rff")["spec"]
+    model = V.VBN.from_spec(spec, device=backend.device)
+    # one query: with B > 1 and latent roots the reference (and the oracle) cannot run at all -- root candidates
+    # are [1, 8, D] there, see inference.GibbsSampler
+    q = {"target": "c", "evidence": {"d": torch.tensor([[0.4]])}, "do": {}}
+    rec = O.RecordingNoise()
+    torch.manual_seed(17)
+    want = O.gibbs_sample(spec, q, 5, noise=rec, burn_in=2, n_steps=2)
+    inj = gibbs_injection(rec.log, spec)
+    noise = {scope: {n: {k: t.to(backend.device) for k, t in d.items()} for n, d in nodes.items()}
+             for scope, nodes in inj.items()}
+    model.set_sampling_method("gibbs", n_samples=5, burn_in=2, n_steps=2)
+    got = model.sample(q, n_samples=5, noise=noise)
+    assert got.shape == (1, 5, 2)
+    _close(got, want, "gibbs 2-D latent", atol=max(ATOL, _dot_floor(spec)))

@@ -230,6 +230,7 @@ __device__ __forceinline__ void issue_layer(uint32_t d, uint32_t a_hi, uint32_t 
 }
 
 // Per-thread tensor-core state, plugged into Ctx as the TC policy.
+template <int NWG>
 struct TcMlp {
   static constexpr bool kEnabled = true;
   static constexpr bool kLoops = false;      // Gibbs programs never carry tensor-core images
@@ -319,12 +320,22 @@ struct TcMlp {
     tmem_st16(t_alo + 16 * half, lo);
   }
   __device__ __forceinline__ void hidden_epilogue(int act) {
-    uint32_t v0[16], v1[16];
-    tmem_ld16(t_d, v0);
-    tmem_ld16(t_d + 16, v1);
-    tmem_wait_ld();
-    split_half(act, v0, 0);
-    split_half(act, v1, 1);
+    if constexpr (NWG <= 4) {
+      uint32_t v0[16], v1[16];
+      tmem_ld16(t_d, v0);
+      tmem_ld16(t_d + 16, v1);
+      tmem_wait_ld();
+      split_half(act, v0, 0);
+      split_half(act, v1, 1);
+    } else {  // 5 warpgroups leave 96 registers per thread: one half at a time
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[16];
+        tmem_ld16(t_d + 16 * half, v);
+        tmem_wait_ld();
+        split_half(act, v, half);
+      }
+    }
     tmem_wait_st();
   }
 
@@ -525,7 +536,7 @@ __global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const S
     __syncthreads();
     tc_fence_after();
   }
-  Ctx<1, kThreads, TcMlp> c(a, slots, 0);  // the thread index is already folded into `slots`
+  Ctx<1, kThreads, TcMlp<NWG>> c(a, slots, 0);  // the thread index is already folded into `slots`
   const int wg = warp >> 2;
   const uint32_t col = tmem_base + static_cast<uint32_t>(wg * kColsPerWg);
   const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;

@@ -683,7 +683,7 @@ class GibbsSampler:
 
     Reference behaviour kept on purpose: the chain's states are collected as VIEWS of the live state tensor
     (gibbs.py:83-91), so the returned [B, n_samples, D] tensor holds the FINAL target state n_samples times.
-    Deviation: with B > 1 and a latent root the reference raises IndexError (root candidates are [1, 8, D]);
+    Deviation: with B > 1 and a latent root the reference raises (IndexError / a torch.cat size error: root candidates are [1, 8, D]);
     here every chain draws its own root candidates."""
 
     def __init__(self, n_samples: int = 200, burn_in: int = 10, n_steps: int = 1, **kwargs) -> None:
