@@ -42,8 +42,10 @@ extern "C" {
 #define VBN_OP_MDN 3    /* vbn/cpds/mdn.py:185-272                                         */
 #define VBN_OP_SNN 4    /* vbn/cpds/softmax_nn.py:581-759                                  */
 #define VBN_OP_KDE 5    /* vbn/cpds/kde.py:105-182                                         */
-#define VBN_OP_TAB 6     /* softmax_nn in discrete mode with all-discrete parents: log-density
-                            table per parent configuration, built by the plan compiler     */
+#define VBN_OP_TAB 6     /* log-density table per parent configuration: softmax_nn in discrete mode with
+                            all-discrete parents (table built by the plan compiler), categorical_table
+                            (vbn/cpds/categorical_table.py:359-417) and categorical_embedded_softmax
+                            (vbn/cpds/categorical_embedded_softmax.py:316-511), both with strict supports */
 
 #define VBN_OP_RFF 7     /* vbn/cpds/rff_gaussian.py:131-146,185-206,254-291: random Fourier features,
                             loc = (sqrt(2/F) cos(z W^T + b)) coef + bias, de-standardised; constant scale */
