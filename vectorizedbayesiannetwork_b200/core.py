@@ -87,6 +87,8 @@ def _default_config() -> SimpleNamespace:
 
 def ensure_tensor(x, device, dtype=torch.float32) -> torch.Tensor:
     if isinstance(x, torch.Tensor):
+        if x.dtype == dtype and x.device == device:  # the common case on the small-call latency path
+            return x
         return x.to(device=device, dtype=dtype)
     return torch.tensor(x, device=device, dtype=dtype)
 

@@ -14,8 +14,10 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional
 
+import numpy as np
 import torch
 
+from . import _lib as L
 from . import engine as E
 from .core import (Query, infer_batch_size, model_cpds, register_inference, register_sampling)
 from .cpds import TABLE_KINDS
@@ -94,7 +96,8 @@ class _ScheduleRunner:
         cols = []
         for n in prog.fixed_cols:  # insertion order == op order
             v = query.do[n] if n in query.do else query.evidence[n]
-            v = v.to(device=plan.device, dtype=torch.float32)
+            if v.dtype != torch.float32 or v.device != plan.device:
+                v = v.to(device=plan.device, dtype=torch.float32)
             if clamp_obs and n in query.evidence:
                 v = clamp_evidence(v)
             if shard is not None:
@@ -122,7 +125,11 @@ class _ScheduleRunner:
             stores = {n: torch.empty(b, s, prog.store_widths[n], device=dev, dtype=torch.float32) for n in prog.stores}
             logw = torch.empty(b, s, device=dev, dtype=torch.float32) if prog.needs_logw else None
             logp = torch.empty(b, s, device=dev, dtype=torch.float32) if prog.needs_logp else None
-            flag = torch.zeros(1, device=dev, dtype=torch.int32)
+            # the device error flag is only ever raised by discrete ops (softmax_nn classes, table supports)
+            needs_flag = getattr(prog, "_needs_flag", None)
+            if needs_flag is None:
+                needs_flag = prog._needs_flag = bool(np.isin(prog.ops["kind"], (L.OP_SNN, L.OP_TAB)).any())
+            flag = torch.zeros(1, device=dev, dtype=torch.int32) if needs_flag else None
             plan.run(b, s, fixed=fixed, stores=[stores[n] for n in prog.stores],
                      noise=[noise[n] for n in prog.noise], logw=logw, logp=logp,
                      logp_as_pdf=mode in ("mcm", "mcm_fast"),
@@ -134,7 +141,7 @@ class _ScheduleRunner:
 def _raise_if_flagged(vbn, out) -> None:
     cpds = model_cpds(vbn)
     if any(c.kind == "softmax_nn" and bool(c._is_discrete.any()) for c in cpds.values()):
-        if int(out["flag"].item()) != 0:
+        if out["flag"] is not None and int(out["flag"].item()) != 0:
             raise ValueError("Found values outside discrete class set.")  # softmax_nn.py:623-625
 
 
