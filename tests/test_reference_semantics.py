@@ -477,6 +477,34 @@ def test_rff_gaussian_conditional_and_unfitted(backend):
         V.cpd_from_spec(unfitted, device=backend.device).sample(pa, 4)
 
 
+# ---- CPDHandle bookkeeping surface (vbn/core/cpd_handle.py:130-193, 276-346; tests/test_cpd_handle.py) ----
+def test_cpd_handle_summary_state_and_clone(backend):
+    import os
+
+    spec = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mixed_relu.pt"),
+                      weights_only=False)["spec"]
+    model = V.VBN.from_spec(spec, device=backend.device)
+    for node in spec["nodes"]:
+        h = model.get_cpd(node)
+        s = h.summary()
+        assert s["node"] == node and s["is_fitted"] is True and s["cpd_name"] == spec["cpds"][node]["kind"]
+        assert s["input_dim"] == spec["cpds"][node]["input_dim"] and s["output_dim"] == spec["cpds"][node]["output_dim"]
+        assert h.name == node and h.parents == spec["parents"][node] and h.x_dim == h.output_dim
+        sd = h.state_dict()
+        assert sd and all(isinstance(v, torch.Tensor) for v in sd.values())
+        cfg = h.export_config()
+        assert cfg["node"] == node and cfg["cpd_name"] == h.cpd_name and isinstance(cfg["init_kwargs"], dict)
+        clone = h.clone_cpd()
+        assert clone is not h.cpd and type(clone) is type(h.cpd)
+        pa = torch.randn(3, h.input_dim) if h.input_dim else None
+        a = h.cpd.sample(pa, 5, seed=4)
+        b = clone.sample(pa, 5, seed=4)
+        assert torch.equal(a, b)  # same parameters, same Philox stream
+    unfitted = dict(spec["cpds"]["f"], bins_ready=False)  # softmax_nn before fit (softmax_nn.py:178-183)
+    model.nodes["f"] = V.cpd_from_spec(unfitted, device=backend.device)
+    assert model.get_cpd("f").is_fitted is False and model.get_cpd("f").summary()["is_fitted"] is False
+
+
 # ---- VBN._posterior_stats / infer_relative (vbn/vbn.py:483-568; tests/test_gaussian_exact_relative.py:40-57)
 def _ref_posterior_stats(pdf, samples, eps=1e-12):
     weights = torch.nan_to_num(pdf, nan=0.0, posinf=0.0, neginf=0.0).clamp_min(0.0)

@@ -106,10 +106,61 @@ class CPDHandle:
         out = self._cpd.forward(self._parents_tensor(parents), int(n_samples))
         return CPDOutput(samples=out.samples.detach(), log_prob=out.log_prob.detach(), pdf=out.pdf.detach())
 
+    @property
+    def is_fitted(self) -> bool:
+        """vbn/core/cpd_handle.py:154-171: the fitted flags the reference probes (`_targets`, `_bins_ready`,
+        `_stats_ready`), else "has parameters" -- which holds for every parameter holder here."""
+        for flag in ("_targets", "_bins_ready", "_stats_ready"):
+            if hasattr(self._cpd, flag):
+                value = getattr(self._cpd, flag)
+                if isinstance(value, torch.Tensor):
+                    value = value.numel() > 0 if value.dim() > 0 else bool(value.item())
+                if value is not None and bool(value):
+                    return True
+                if flag != "_targets":
+                    return False
+        return True
+
+    def state_dict(self) -> dict:
+        """vbn/core/cpd_handle.py:308-311: the tensors of the CPD's spec (what the packed device blob is built from)."""
+        out = {}
+
+        def walk(prefix, v):
+            if isinstance(v, torch.Tensor):
+                out[prefix] = v
+            elif isinstance(v, (list, tuple)):
+                for i, x in enumerate(v):
+                    walk(f"{prefix}.{i}", x)
+
+        for k, v in self._cpd.to_spec().items():
+            walk(k, v)
+        return out
+
+    def export_config(self) -> dict:
+        """vbn/core/cpd_handle.py:288-306: the non-tensor part of the spec plays the role of init_kwargs."""
+        spec = self._cpd.to_spec()
+        init = {k: v for k, v in spec.items() if not isinstance(v, (torch.Tensor, list, tuple)) and k != "kind"}
+        return {"node": self.node, "parents": self.parents, "cpd_name": self.cpd_name, "cpd_type": self.cpd_type,
+                "init_kwargs": _to_serializable(init), "extra_state": None}
+
+    def clone_cpd(self, detach: bool = True):
+        """vbn/core/cpd_handle.py:313-346: an independent copy of the CPD (parameters cloned; nothing here tracks
+        gradients, so ``detach`` has nothing left to do)."""
+        from .cpds import cpd_from_spec
+
+        def cp(v):
+            if isinstance(v, torch.Tensor):
+                return v.detach().clone()
+            if isinstance(v, (list, tuple)):
+                return type(v)(cp(x) for x in v)
+            return v
+
+        return cpd_from_spec({k: cp(v) for k, v in self._cpd.to_spec().items()}, device=self._cpd.device)
+
     def summary(self) -> dict:
         return {"node": self.node, "parents": self.parents, "cpd_name": self.cpd_name,
                 "cpd_type": self.cpd_type, "input_dim": self.input_dim, "output_dim": self.output_dim,
-                "device": str(self.device), "is_fitted": True}
+                "device": str(self.device), "is_fitted": self.is_fitted}
 
     def conditional(self, parents, *, n_samples: int = 1024) -> dict:
         """vbn/core/cpd_handle.py:348-402: normal_params (linear_gaussian, gaussian_nn), mixture_params
