@@ -251,6 +251,16 @@ class VBN:
         model.nodes = {n: wrap_cpd(ref_vbn.nodes[n], model.device) for n in nodes}
         return model
 
+    def to_device(self, device) -> None:
+        """vbn/vbn.py:621-631: move the model to another CUDA device.  The CPD objects only hold host-side
+        parameters; their packed blobs and cached plans are per device, so they are dropped and rebuilt lazily."""
+        from .engine import require_cuda
+
+        self.device = require_cuda(device)
+        for cpd in self.nodes.values():
+            cpd.device = self.device
+            cpd.invalidate()
+
     def set_cpd(self, node: str, cpd: BaseCPD) -> None:
         if node not in self.dag.nodes():
             raise ValueError(f"Unknown node '{node}'.")
