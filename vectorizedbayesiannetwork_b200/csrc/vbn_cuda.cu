@@ -82,6 +82,9 @@ struct VbnPlan {
   int shape;       // index into kShapes
   int blocks_per_sm;
   size_t smem_bytes;
+  int small_shape;      // smallest-CTA shape of the same family (-1: none): used when a run has too few rows to give
+  int small_blocks;     // every SM a CTA of the preferred shape (Gibbs chains, CPD-handle calls, small batches)
+  size_t small_smem;
   int tc;          // 0, or warpgroups per CTA of vbn::tc::schedule_tc_kernel<NWG>
   int tc_nbuf;     // weight-ring depth of the tensor-core kernel
 };
@@ -112,6 +115,7 @@ int32_t vbn_plan_create(const VbnProgramDesc* desc, VbnPlan** out_plan) {
   int max_smem = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
   p->shape = -1;
+  p->small_shape = -1;
   p->tc = 0;
   p->tc_nbuf = 0;
   const size_t per_row = static_cast<size_t>(desc->n_slots + desc->n_scratch) * sizeof(float);
@@ -161,6 +165,22 @@ int32_t vbn_plan_create(const VbnProgramDesc* desc, VbnPlan** out_plan) {
     p->blocks_per_sm = occ;
     p->smem_bytes = bytes;
     break;
+  }
+  if (p->shape >= 0 && !force) {
+    const int n_shapes = static_cast<int>(sizeof(kShapes) / sizeof(kShapes[0]));
+    for (int i = n_shapes - 1; i > p->shape; --i) {  // fewest rows per CTA first
+      const Shape& s = kShapes[i];
+      if (s.heavy != (desc->heavy ? 1 : 0) || s.rpt * s.nt >= kShapes[p->shape].rpt * kShapes[p->shape].nt) continue;
+      const size_t bytes = per_row * s.rpt * s.nt;
+      CUDA_TRY(cudaFuncSetAttribute(s.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      int occ = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s.fn, s.nt, bytes));
+      if (occ < 1) continue;
+      p->small_shape = i;
+      p->small_blocks = occ;
+      p->small_smem = bytes;
+      break;
+    }
   }
   if (p->shape < 0) {
     delete p;
@@ -224,9 +244,21 @@ int32_t vbn_run_forward(const VbnPlan* plan, const VbnRunDesc* run, void* stream
   }
   const int64_t rows_per_cta = static_cast<int64_t>(s.rpt) * s.nt;
   const int64_t n_tiles = (a.n_rows + rows_per_cta - 1) / rows_per_cta;
+  void* args[] = {&a};
+  if (n_tiles < plan->num_sms && plan->small_shape >= 0) {
+    // fewer tiles than SMs: spread the rows over more, smaller CTAs (a 4096-chain Gibbs run is 16 CTAs of the
+    // preferred heavy shape, 64 of the small one)
+    const Shape& q = kShapes[plan->small_shape];
+    const int64_t rows_small = static_cast<int64_t>(q.rpt) * q.nt;
+    const int64_t tiles_small = (a.n_rows + rows_small - 1) / rows_small;
+    const int64_t resident_small = static_cast<int64_t>(plan->num_sms) * plan->small_blocks;
+    const unsigned grid_small = static_cast<unsigned>(tiles_small < resident_small ? tiles_small : resident_small);
+    CUDA_TRY(cudaLaunchKernel(q.fn, dim3(grid_small), dim3(q.nt), args, plan->small_smem,
+                              static_cast<cudaStream_t>(stream)));
+    return VBN_OK;
+  }
   const int64_t resident = static_cast<int64_t>(plan->num_sms) * plan->blocks_per_sm;
   const unsigned grid = static_cast<unsigned>(n_tiles < resident ? n_tiles : resident);
-  void* args[] = {&a};
   CUDA_TRY(cudaLaunchKernel(s.fn, dim3(grid), dim3(s.nt), args, plan->smem_bytes,
                             static_cast<cudaStream_t>(stream)));
   return VBN_OK;
