@@ -318,6 +318,44 @@ def test_cfg5_block_properties():
 
 
 @pytest.mark.gpu
+def test_cfg3_full_size_posterior_matches_oracle_estimate():
+    """BASELINE cfg3 at full size (ALARM, 4096 queries x 16 384 samples, likelihood weighting), summarised on the
+    device by the class histogram (benchmarking/models/vbn.py:202-242).  Size-independent properties, plus the
+    posterior of the first queries against the oracle's own likelihood-weighting estimate (independent draws):
+    the two Monte-Carlo estimates must agree within their combined standard error."""
+    from vectorizedbayesiannetwork_b200 import summaries as SM
+
+    dev = torch.device("cuda", 0)
+    spec = S.alarm_softmax(seed=0)
+    g = torch.Generator().manual_seed(11)
+    ev = {n: torch.randint(0, S.ALARM[n][0], (4096, 1), generator=g).float() for n in ("HRBP", "BP", "EXPCO2", "PRESS")}
+    model = V.VBN.from_spec(spec, device=dev)
+    model.set_inference_method("likelihood_weighting", n_samples=16384)
+    w, x = model.infer_posterior({"target": "LVFAILURE", "evidence": ev}, seed=3)
+    assert w.shape == (4096, 16384) and x.shape == (4096, 16384, 1)
+    assert bool(((x == 0) | (x == 1)).all()) and torch.isfinite(w).all() and bool((w >= 0).all())
+    k = S.ALARM["LVFAILURE"][0]
+    probs = SM.estimate_discrete_posterior_tensor(x, w, k)
+    torch.testing.assert_close(probs.sum(1).cpu(), torch.ones(4096), rtol=0, atol=1e-5)
+    # the histogram kernel against a torch reduction over the same tensors
+    wn = w / w.sum(1, keepdim=True)
+    want1 = (wn * (x[..., 0] == 1)).sum(1)
+    torch.testing.assert_close(probs[:, 1], want1, rtol=1e-4, atol=1e-6)
+    ess = (1.0 / (wn**2).sum(1)).cpu()
+    for b in range(3):
+        q = {"target": "LVFAILURE", "evidence": {n: v[b:b + 1] for n, v in ev.items()}, "do": {}}
+        torch.manual_seed(100 + b)
+        ow, ox = O.likelihood_weighting(spec, q, 16384)
+        op = O.estimate_discrete_posterior_batch(ox, ow, k)[0][1]
+        on = ow / ow.sum(1, keepdim=True)
+        oess = float(1.0 / (on**2).sum())
+        pg = float(probs[b, 1])
+        pm = 0.5 * (pg + op)
+        se = (pm * (1 - pm) * (1.0 / float(ess[b]) + 1.0 / oess)) ** 0.5
+        assert abs(pg - op) < 5.0 * se + 1e-3, (b, pg, op, se)
+
+
+@pytest.mark.gpu
 def test_cfg4_size_spot_check():
     dev = torch.device("cuda", 0)
     spec = S.kde_pair(200_000)
