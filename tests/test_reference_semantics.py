@@ -318,6 +318,34 @@ def test_cfg5_block_properties():
 
 
 @pytest.mark.gpu
+def test_cfg5_posterior_mean_matches_oracle_estimate():
+    """BASELINE cfg5 (1000-node LG + MDN DAG, importance sampling, tcgen05 kernel with every fast path on): the
+    self-normalised posterior mean of the target for a few queries against the oracle's own importance-sampling
+    estimate (independent draws) within the combined Monte-Carlo standard error."""
+    dev = torch.device("cuda", 0)
+    spec = S.random_dag_lg_mdn(1000, seed=0)
+    g = torch.Generator().manual_seed(1)
+    ev = {n: 0.3 * torch.randn(3, 1, generator=g) for n in spec["nodes"][-5:]}
+    model = V.VBN.from_spec(spec, device=dev)
+    model.set_inference_method("importance_sampling", n_samples=65536, ess_threshold=0.0)
+    w, x = model.infer_posterior({"target": "n500", "evidence": ev}, seed=9)
+    w, x = w.double().cpu(), x[..., 0].double().cpu()
+    mean = (w * x).sum(1)
+    var = (w * (x - mean[:, None]) ** 2).sum(1)
+    ess = 1.0 / (w**2).sum(1)
+    for b in range(3):
+        q = {"target": "n500", "evidence": {n: v[b:b + 1] for n, v in ev.items()}, "do": {}}
+        torch.manual_seed(50 + b)
+        ow, ox = O.importance_sampling(spec, q, 8192, ess_threshold=0.0)
+        ow, ox = ow.double()[0], ox[0, :, 0].double()
+        om = float((ow * ox).sum())
+        ovar = float((ow * (ox - om) ** 2).sum())
+        oess = float(1.0 / (ow**2).sum())
+        se = (float(var[b]) / float(ess[b]) + ovar / oess) ** 0.5
+        assert abs(float(mean[b]) - om) < 5.0 * se + 1e-3, (b, float(mean[b]), om, se, float(ess[b]), oess)
+
+
+@pytest.mark.gpu
 def test_cfg3_full_size_posterior_matches_oracle_estimate():
     """BASELINE cfg3 at full size (ALARM, 4096 queries x 16 384 samples, likelihood weighting), summarised on the
     device by the class histogram (benchmarking/models/vbn.py:202-242).  Size-independent properties, plus the
