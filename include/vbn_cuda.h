@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define VBN_CUDA_ABI_VERSION 4
+#define VBN_CUDA_ABI_VERSION 5
 
 /* error codes */
 #define VBN_OK 0
@@ -142,7 +142,9 @@ typedef struct VbnOp {
      made in one call (Gibbs candidates); arrays inside a VBN_OP_JUMP loop carry a leading iteration axis */
   int32_t tc[4];      /* tensor-core MLP image (hidden dims [32,32], Dp <= 32, O <= 32), written by
                          the plan compiler: {1 if present, float offset of the image in the
-                         parameter blob (16-byte aligned), K1 = Dp padded to 8, N3 = O padded to 16};
+                         parameter blob (16-byte aligned), K1 = Dp padded to 8 -- or 0: first layer on the
+                         FP32 pipe from the plain W1^T[4][32], b1[32] block at the head of the image (GNN /
+                         MDN ops with VBN_F_PAR4 only) --, N3 = O padded to 16};
                          image layout: see csrc/vbn_schedule_tc.cuh and cpds.py pack_mlp_tc        */
 } VbnOp;
 
@@ -173,8 +175,9 @@ typedef struct VbnProgramDesc {
   int32_t n_slots;    /* value slots a row needs at once (after liveness analysis)         */
   int32_t n_scratch;  /* per-row scratch floats (max MLP output width over the program)    */
   int32_t heavy;      /* 1 if the program contains MLP / KDE ops (picks the launch shape)  */
-  int32_t tc;         /* 0: FP32-pipe kernel; 4 or 5: tcgen05 kernel with that many 128-row
-                         warpgroups per CTA (ops carry tensor-core MLP images)              */
+  int32_t tc;         /* 0: FP32-pipe kernel; else the tcgen05 kernel (ops carry tensor-core MLP images) with
+                         (tc & 0xFF) warpgroups per CTA, each owning (tc >> 8, 0 = 1) 128-row tiles:
+                         4 | 1 << 8 or 2 | 2 << 8                                          */
   const int32_t* tc_list_dev; /* [n_tc][2] {image float offset, image bytes} of every op with
                          tc[0] != 0, in schedule order (the weight ring's fetch list)       */
   int32_t n_tc;

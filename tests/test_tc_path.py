@@ -46,6 +46,15 @@ def test_pack_mlp_tc_eligibility_and_size():
     torch.testing.assert_close(torch.from_numpy(w1hi + w1lo)[:, :3], layers[0][0], rtol=0, atol=1e-6)  # lo is itself rounded to tf32: 2^-21 relative
     torch.testing.assert_close(torch.from_numpy(w1hi + w1lo)[:, 8], layers[0][1], rtol=0, atol=1e-6)
     assert not (w1hi + w1lo)[:, 3:8].any() and not (w1hi + w1lo)[:, 9:].any()
+    # gaussian_nn / mdn nodes with <= 4 parent dims: first layer on the FP32 pipe -> plain W1^T[4][32], b1[32] block
+    blob2, k1b, n3b = pack_mlp_tc(layers, 3, l1_fma=True)
+    assert (k1b, n3b) == (0, 16) and blob2.size * 4 == 640 + 4 * 2 * (32 * 40 + 16 * 40)
+    plain = blob2[:160].reshape(5, 32)
+    torch.testing.assert_close(torch.from_numpy(plain[:3]), layers[0][0].t(), rtol=0, atol=0)
+    torch.testing.assert_close(torch.from_numpy(plain[4]), layers[0][1], rtol=0, atol=0)
+    assert not plain[3].any()
+    np.testing.assert_array_equal(blob2[160:], blob[2 * 32 * 16:])       # the W2 / W3 images are the same
+    assert pack_mlp_tc(S.mlp_layers(g, 5, (32, 32), 9), 5, l1_fma=True)[1] == 8   # > 4 parent dims: MMA first layer
     assert pack_mlp_tc(S.mlp_layers(g, 3, (16, 16), 9), 3) is None       # other hidden sizes: FFMA path
     assert pack_mlp_tc(S.mlp_layers(g, 40, (32, 32), 9), 40) is None     # too many parent dims
     assert pack_mlp_tc(S.mlp_layers(g, 3, (32, 32), 40), 3) is None      # too many outputs
@@ -61,7 +70,7 @@ def test_plan_marks_tensor_core_ops(monkeypatch):
         want = spec["cpds"][n]["kind"] == "mdn" and spec["cpds"][n]["input_dim"] > 0
         assert bool(op["tc"][0]) == want
         if want:
-            assert op["tc"][1] % 4 == 0 and op["tc"][2] == 8 and op["tc"][3] == 16
+            assert op["tc"][1] % 4 == 0 and op["tc"][2] == 0 and op["tc"][3] == 16  # K1 = 0: first layer on the FP32 pipe
     assert not compile_schedule(spec["topo"], spec["parents"], cpds, roles, use_tc=False).tc
 
 

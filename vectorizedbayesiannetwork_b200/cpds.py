@@ -8,6 +8,7 @@ parameters come from a fitted reference model (``from_reference``), from a spec 
 from __future__ import annotations
 
 import itertools
+import os
 import math
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -116,10 +117,13 @@ def _core_matrix_image(w: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray(w.reshape(n // 8, 8, k // 4, 4).transpose(0, 2, 1, 3)).reshape(-1)
 
 
-def pack_mlp_tc(layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], input_dim: int):
+def pack_mlp_tc(layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], input_dim: int, l1_fma: bool = False):
     """Weight image for the tcgen05 kernel, or None when the MLP is not [Dp<=32 -> 32 -> 32 -> O<=32].
     Layout (floats): W1hi, W1lo [32][K1+8]; W2hi, W2lo [32][40]; W3hi, W3lo [N3][40] -- core-matrix images of
-    nn.Linear's [out][in] = [N][K] K-major weight with the bias appended as column K (then 7 zero columns)."""
+    nn.Linear's [out][in] = [N][K] K-major weight with the bias appended as column K (then 7 zero columns).
+    ``l1_fma`` (gaussian_nn / mdn nodes, whose ops carry their parent slots in the descriptor) and Dp <= 4: the first
+    layer runs on the FP32 pipe, so the W1 images are replaced by the plain block W1^T[4][32] (rows >= Dp zero),
+    b1[32], and K1 is reported as 0 (csrc/vbn_schedule_tc.cuh hidden1_fma)."""
     if len(layers) != 3:
         return None
     (w1, b1), (w2, b2), (w3, b3) = [(_f32(w).numpy(), _f32(b).numpy()) for w, b in layers]
@@ -133,7 +137,15 @@ def pack_mlp_tc(layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], input_dim: 
     w3p = np.zeros((n3, 32), np.float32)
     w3p[:n_out] = w3
     chunks = []
-    for w, b in ((w1p, b1), (w2, b2), (w3p, _padded(b3, n3))):
+    mma_layers = [(w1p, b1), (w2, b2), (w3p, _padded(b3, n3))]
+    if l1_fma and dp <= 4:
+        plain = np.zeros((5, 32), np.float32)
+        plain[:dp] = w1.T
+        plain[4] = b1
+        chunks.append(plain.reshape(-1))
+        mma_layers = mma_layers[1:]
+        k1 = 0
+    for w, b in mma_layers:
         # the bias rides in an extra K = 8 step: column K holds b, columns K+1..K+7 are zero; the kernel pairs it
         # with a constant A block (1, 0, ..., 0) so the first MMA of a layer writes the bias into the accumulator
         ext = np.zeros((w.shape[0], w.shape[1] + 8), np.float32)
@@ -149,7 +161,7 @@ def _layers_from_module(net) -> List[Tuple[torch.Tensor, torch.Tensor]]:
 
 
 def _with_tc(pk: Packed, layers, input_dim: int) -> Packed:
-    img = pack_mlp_tc(layers, input_dim)
+    img = pack_mlp_tc(layers, input_dim, l1_fma=pk.kind in (L.OP_GNN, L.OP_MDN) and os.environ.get("VBN_TC_L1FMA", "1") != "0")
     if img is not None:
         pk.tc_blob, pk.tc_k1, pk.tc_n3 = img
     return pk

@@ -7,13 +7,15 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <new>
 
 #include "vbn_cuda.h"
 #include "vbn_kde.cuh"
 #include "vbn_reduce.cuh"
+#include "vbn_launch.h"
 #include "vbn_schedule.cuh"
-#include "vbn_schedule_tc.cuh"
+#include "vbn_tc_layout.h"
 
 static_assert(sizeof(VbnOp) == 128, "VbnOp must be 128 bytes");
 static_assert(sizeof(VbnView) == 24, "VbnView layout");
@@ -40,37 +42,32 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 
 // ---- launch shapes of the schedule kernel -------------------------------------------------
+// The kernels themselves are instantiated in vbn_k_heavy.cu / vbn_k_light4.cu / vbn_k_light2.cu / vbn_k_tc.cu
+// (separate translation units, compiled in parallel); entry points are looked up through vbn_launch.h.
 struct Shape {
   int rpt, nt, heavy, min_blocks;
-  const void* fn;
 };
-
-template <int RPT, int NT, bool HEAVY, int MB>
-constexpr Shape make_shape() {
-  return Shape{RPT, NT, HEAVY ? 1 : 0, MB,
-               reinterpret_cast<const void*>(&vbn::schedule_kernel<RPT, NT, HEAVY, MB>)};
-}
 
 // preferred first; later entries hold fewer rows per CTA (capacity fallbacks)
 const Shape kShapes[] = {
-    make_shape<2, 128, true, 3>(),
-    make_shape<1, 128, true, 3>(),
-    make_shape<1, 64, true, 1>(),
-    make_shape<4, 256, false, 2>(),  // best on LG chains (cfg2: 64% of the level-SoA HBM model)
-    make_shape<4, 128, false, 4>(),
-    make_shape<2, 256, false, 4>(),
-    make_shape<4, 128, false, 3>(),
-    make_shape<2, 256, false, 3>(),
-    make_shape<2, 256, false, 2>(),
-    make_shape<1, 256, false, 4>(),
-    make_shape<1, 256, false, 6>(),
-    make_shape<1, 128, false, 4>(),
-    make_shape<1, 64, false, 1>(),
+    {2, 128, 1, 3},
+    {1, 128, 1, 3},
+    {1, 64, 1, 1},
+    {4, 256, 0, 2},  // best on LG chains (cfg2: 64% of the level-SoA HBM model)
+    {4, 128, 0, 4},
+    {2, 256, 0, 4},
+    {4, 128, 0, 3},
+    {2, 256, 0, 3},
+    {2, 256, 0, 2},
+    {1, 256, 0, 4},
+    {1, 256, 0, 6},
+    {1, 128, 0, 4},
+    {1, 64, 0, 1},
 };
+constexpr int kNumShapes = static_cast<int>(sizeof(kShapes) / sizeof(kShapes[0]));
 
-const void* tc_kernel(int nwg) {
-  return nwg == 5 ? reinterpret_cast<const void*>(&vbn::tc::schedule_tc_kernel<5>)
-                  : reinterpret_cast<const void*>(&vbn::tc::schedule_tc_kernel<4>);
+const void* shape_fn(const Shape& s) {
+  return s.heavy ? vbn::heavy_kernel_ptr(s.rpt, s.nt, s.min_blocks) : vbn::light_kernel_ptr(s.rpt, s.nt, s.min_blocks);
 }
 
 }  // namespace
@@ -85,7 +82,8 @@ struct VbnPlan {
   int small_shape;      // smallest-CTA shape of the same family (-1: none): used when a run has too few rows to give
   int small_blocks;     // every SM a CTA of the preferred shape (Gibbs chains, CPD-handle calls, small batches)
   size_t small_smem;
-  int tc;          // 0, or warpgroups per CTA of vbn::tc::schedule_tc_kernel<NWG>
+  int tc;          // 0, or warpgroups per CTA of vbn::tc::schedule_tc_kernel<NWG, RPT>
+  int tc_rpt;      // 128-row tiles per warpgroup
   int tc_nbuf;     // weight-ring depth of the tensor-core kernel
 };
 
@@ -107,7 +105,8 @@ int32_t vbn_plan_create(const VbnProgramDesc* desc, VbnPlan** out_plan) {
   if (!desc || !out_plan) return fail(VBN_E_INVALID, "NULL argument");
   if (desc->n_ops <= 0 || !desc->ops_dev) return fail(VBN_E_INVALID, "empty program");
   if (desc->n_slots <= 0 || desc->n_scratch < 0) return fail(VBN_E_INVALID, "bad slot counts");
-  VbnPlan* p = new (std::nothrow) VbnPlan();
+  std::unique_ptr<VbnPlan> holder(new (std::nothrow) VbnPlan());  // released to the caller only on success
+  VbnPlan* p = holder.get();
   if (!p) return fail(VBN_E_INVALID, "out of host memory");
   p->desc = *desc;
   CUDA_TRY(cudaGetDevice(&p->device));
@@ -117,20 +116,23 @@ int32_t vbn_plan_create(const VbnProgramDesc* desc, VbnPlan** out_plan) {
   p->shape = -1;
   p->small_shape = -1;
   p->tc = 0;
+  p->tc_rpt = 1;
   p->tc_nbuf = 0;
   const size_t per_row = static_cast<size_t>(desc->n_slots + desc->n_scratch) * sizeof(float);
   if (desc->tc) {
     // tensor-core kernel: 512 rows per CTA, one CTA per SM, deepest weight ring that fits
     if (!desc->tc_list_dev || desc->n_tc <= 0) {
-      delete p;
       return fail(VBN_E_INVALID, "tc program without a tc_list");
     }
-    const int nwg = desc->tc == 5 ? 5 : 4;
-    const void* fn = tc_kernel(nwg);
+    const int nwg = desc->tc & 0xFF, rpt = (desc->tc >> 8) > 0 ? (desc->tc >> 8) : 1;
+    const void* fn = vbn::tc::tc_kernel_ptr(nwg, rpt);
+    if (!fn) {
+      return fail(VBN_E_INVALID, "no tensor-core kernel with %d warpgroups x %d tiles", nwg, rpt);
+    }
     const int threads = nwg * vbn::tc::kWgThreads;
     for (int nbuf = vbn::tc::kMaxBufs; nbuf >= 2 && !p->tc; --nbuf) {
       const size_t bytes = vbn::tc::kCtrlBytes + static_cast<size_t>(nbuf) * vbn::tc::kWbufBytes +
-                           per_row * threads;
+                           per_row * threads * rpt;
       if (bytes > static_cast<size_t>(max_smem)) continue;
       // the attribute is per FUNCTION, not per plan: always raise it to the device maximum so that plans with
       // different footprints can coexist (a later, smaller plan must not lower the limit of an earlier one)
@@ -139,27 +141,28 @@ int32_t vbn_plan_create(const VbnProgramDesc* desc, VbnPlan** out_plan) {
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, bytes));
       if (occ < 1) continue;
       p->tc = nwg;
+      p->tc_rpt = rpt;
       p->tc_nbuf = nbuf;
       p->blocks_per_sm = 1;
       p->smem_bytes = bytes;
     }
     if (p->tc) {
-      *out_plan = p;
+      *out_plan = holder.release();
       return VBN_OK;
     }
     // does not fit: fall through to the FFMA shapes (the ops keep their FFMA parameter blocks)
   }
   const char* force = desc->heavy ? nullptr : std::getenv("VBN_SHAPE");  // dev knob (light schedules): force a shape
-  for (int i = 0; i < static_cast<int>(sizeof(kShapes) / sizeof(kShapes[0])); ++i) {
+  for (int i = 0; i < kNumShapes; ++i) {
     const Shape& s = kShapes[i];
     if (s.heavy != (desc->heavy ? 1 : 0)) continue;
     if (force && std::atoi(force) != i) continue;
     if (!force && !s.heavy && desc->rows_per_thread == 2 && s.rpt > 2) continue;
     const size_t bytes = per_row * s.rpt * s.nt;
     if (bytes > static_cast<size_t>(max_smem)) continue;
-    CUDA_TRY(cudaFuncSetAttribute(s.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(shape_fn(s), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     int occ = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s.fn, s.nt, bytes));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, shape_fn(s), s.nt, bytes));
     if (occ < 1) continue;
     p->shape = i;
     p->blocks_per_sm = occ;
@@ -167,14 +170,13 @@ int32_t vbn_plan_create(const VbnProgramDesc* desc, VbnPlan** out_plan) {
     break;
   }
   if (p->shape >= 0 && !force) {
-    const int n_shapes = static_cast<int>(sizeof(kShapes) / sizeof(kShapes[0]));
-    for (int i = n_shapes - 1; i > p->shape; --i) {  // fewest rows per CTA first
+    for (int i = kNumShapes - 1; i > p->shape; --i) {  // fewest rows per CTA first
       const Shape& s = kShapes[i];
       if (s.heavy != (desc->heavy ? 1 : 0) || s.rpt * s.nt >= kShapes[p->shape].rpt * kShapes[p->shape].nt) continue;
       const size_t bytes = per_row * s.rpt * s.nt;
-      CUDA_TRY(cudaFuncSetAttribute(s.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      CUDA_TRY(cudaFuncSetAttribute(shape_fn(s), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
       int occ = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s.fn, s.nt, bytes));
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, shape_fn(s), s.nt, bytes));
       if (occ < 1) continue;
       p->small_shape = i;
       p->small_blocks = occ;
@@ -183,13 +185,12 @@ int32_t vbn_plan_create(const VbnProgramDesc* desc, VbnPlan** out_plan) {
     }
   }
   if (p->shape < 0) {
-    delete p;
     return fail(VBN_E_CAPACITY,
                 "schedule needs %d value slots + %d scratch floats per row: exceeds %d bytes of "
                 "shared memory even at 64 rows per CTA",
                 desc->n_slots, desc->n_scratch, max_smem);
   }
-  *out_plan = p;
+  *out_plan = holder.release();
   return VBN_OK;
 }
 
@@ -203,6 +204,7 @@ int32_t vbn_run_forward_launches(const VbnPlan* plan) { return plan ? 1 : 0; }
 int32_t vbn_run_forward(const VbnPlan* plan, const VbnRunDesc* run, void* stream) {
   if (!plan || !run) return fail(VBN_E_INVALID, "NULL argument");
   if (run->n_queries <= 0 || run->n_samples <= 0) return fail(VBN_E_INVALID, "empty run");
+  if (!plan->tc && plan->shape < 0) return fail(VBN_E_INVALID, "plan has no launch shape");
   const Shape& s = kShapes[plan->shape < 0 ? 0 : plan->shape];
   vbn::ScheduleArgs a;
   std::memset(&a, 0, sizeof(a));
@@ -232,13 +234,14 @@ int32_t vbn_run_forward(const VbnPlan* plan, const VbnRunDesc* run, void* stream
   a.error_flag = run->error_flag_dev;
   if (plan->tc) {
     const int threads = plan->tc * vbn::tc::kWgThreads;
-    const int64_t n_tiles = (a.n_rows + threads - 1) / threads;
+    const int64_t rows_per_cta = static_cast<int64_t>(threads) * plan->tc_rpt;
+    const int64_t n_tiles = (a.n_rows + rows_per_cta - 1) / rows_per_cta;
     const unsigned grid = static_cast<unsigned>(n_tiles < plan->num_sms ? n_tiles : plan->num_sms);
     int nbuf = plan->tc_nbuf;
     a.tc_list = reinterpret_cast<const int2*>(plan->desc.tc_list_dev);
     a.n_tc = plan->desc.n_tc;
     void* targs[] = {&a, &nbuf};
-    CUDA_TRY(cudaLaunchKernel(tc_kernel(plan->tc), dim3(grid), dim3(threads), targs, plan->smem_bytes,
+    CUDA_TRY(cudaLaunchKernel(vbn::tc::tc_kernel_ptr(plan->tc, plan->tc_rpt), dim3(grid), dim3(threads), targs, plan->smem_bytes,
                               static_cast<cudaStream_t>(stream)));
     return VBN_OK;
   }
@@ -253,13 +256,13 @@ int32_t vbn_run_forward(const VbnPlan* plan, const VbnRunDesc* run, void* stream
     const int64_t tiles_small = (a.n_rows + rows_small - 1) / rows_small;
     const int64_t resident_small = static_cast<int64_t>(plan->num_sms) * plan->small_blocks;
     const unsigned grid_small = static_cast<unsigned>(tiles_small < resident_small ? tiles_small : resident_small);
-    CUDA_TRY(cudaLaunchKernel(q.fn, dim3(grid_small), dim3(q.nt), args, plan->small_smem,
+    CUDA_TRY(cudaLaunchKernel(shape_fn(q), dim3(grid_small), dim3(q.nt), args, plan->small_smem,
                               static_cast<cudaStream_t>(stream)));
     return VBN_OK;
   }
   const int64_t resident = static_cast<int64_t>(plan->num_sms) * plan->blocks_per_sm;
   const unsigned grid = static_cast<unsigned>(n_tiles < resident ? n_tiles : resident);
-  CUDA_TRY(cudaLaunchKernel(s.fn, dim3(grid), dim3(s.nt), args, plan->smem_bytes,
+  CUDA_TRY(cudaLaunchKernel(shape_fn(s), dim3(grid), dim3(s.nt), args, plan->smem_bytes,
                             static_cast<cudaStream_t>(stream)));
   return VBN_OK;
 }
@@ -446,8 +449,9 @@ int32_t vbn_fma_peak(int32_t mode, int32_t iters, int32_t n_blocks, float* scrat
 
 int32_t vbn_tf32_peak(int32_t iters, int32_t n_blocks, float* scratch_dev, void* stream) {
   if (!scratch_dev || iters <= 0 || n_blocks <= 0) return fail(VBN_E_INVALID, "bad argument");
-  vbn::tc::tf32_peak_kernel<<<n_blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(iters, scratch_dev);
-  CUDA_TRY(cudaGetLastError());
+  void* args[] = {&iters, &scratch_dev};
+  CUDA_TRY(cudaLaunchKernel(vbn::tc::tf32_peak_kernel_ptr(), dim3(n_blocks), dim3(128), args, 0,
+                            static_cast<cudaStream_t>(stream)));
   return VBN_OK;
 }
 

@@ -98,8 +98,8 @@ __device__ __forceinline__ float4 uniform4(uint4 w) {
 
 // Out-of-line Philox + transform: the schedule kernels call these from many op bodies; keeping one
 // copy keeps the hot loop inside the instruction cache.
-__device__ __noinline__ float4 philox_normal4(uint4 c, uint2 k) { return normal4(philox4x32_10(c, k)); }
-__device__ __noinline__ float4 philox_uniform4(uint4 c, uint2 k) { return uniform4(philox4x32_10(c, k)); }
+static __device__ __noinline__ float4 philox_normal4(uint4 c, uint2 k) { return normal4(philox4x32_10(c, k)); }
+static __device__ __noinline__ float4 philox_uniform4(uint4 c, uint2 k) { return uniform4(philox4x32_10(c, k)); }
 
 __device__ __forceinline__ float lane4(const float4& v, int lane) {
   return lane == 0 ? v.x : (lane == 1 ? v.y : (lane == 2 ? v.z : v.w));
@@ -130,7 +130,7 @@ __device__ __forceinline__ float softplus20_fast(float x) {
   return fmaf(2.0f * s, p, fmaxf(x, 0.0f));
 }
 
-__device__ __noinline__ float activate_slow(float x, int act) {
+static __device__ __noinline__ float activate_slow(float x, int act) {
   switch (act) {
     case VBN_ACT_TANH: return tanhf(x);
     case VBN_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));  // nn.GELU (erf)

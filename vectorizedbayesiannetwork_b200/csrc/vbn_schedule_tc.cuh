@@ -1,48 +1,36 @@
 // Tensor-core variant of the fused schedule kernel (sm_100a: tcgen05 + TMEM + bulk async copy).
 //
-// Same schedule walk as schedule_kernel (vbn_schedule.cuh), but the three dense contractions of
-// every [Dp -> 32 -> 32 -> O] MLP CPD (gaussian_nn.py:16-34 _build_mlp, evaluated at
-// gaussian_nn.py:235, mdn.py:199, softmax_nn.py:585) run on the 5th-gen tensor cores:
+// Same schedule walk as schedule_kernel (vbn_schedule.cuh), but the dense contractions of every
+// [Dp -> 32 -> 32 -> O] MLP CPD (gaussian_nn.py:16-34 _build_mlp, evaluated at gaussian_nn.py:235, mdn.py:199,
+// softmax_nn.py:585) run on the 5th-gen tensor cores:
 //
-//   * one CTA = NWG warpgroups (NWG x 128 rows; NWG = 4 or 5), one CTA per SM, persistent;
-//   * a row is a TMEM lane: thread t of a warpgroup owns row t of its 128-row tile for the whole
-//     DAG walk, so MLP inputs/outputs move registers <-> TMEM with tcgen05.st / tcgen05.ld
-//     (32x32b shapes) and never touch shared memory or HBM;
-//   * activations are the A operand, read by tcgen05.mma straight from TMEM; the weights are the
-//     B operand, K-major core-matrix images prepacked by the host (cpds.py pack_mlp_tc) and
-//     streamed L2 -> shared memory with cp.async.bulk through a ring of mbarrier-guarded buffers;
-//     one elected lane of warp 0 tops the ring up (non-blocking look-ahead) each time it enters an
-//     MLP, so no warp -- and no register allocation -- is spent on a dedicated producer;
+//   * one CTA = NWG warpgroups, one CTA per SM, persistent; every warpgroup owns RPT 128-row tiles
+//     (<4,1> or <2,2>: 512 rows per CTA pass either way);
+//   * a row is a TMEM lane: thread t of a warpgroup owns row t of each of its tiles for the whole DAG walk, so
+//     hidden activations move registers <-> TMEM with tcgen05.st / tcgen05.ld (32x32b shapes) and never touch
+//     shared memory or HBM;
+//   * activations are the A operand, read by tcgen05.mma straight from TMEM; the weights are the B operand,
+//     K-major core-matrix images prepacked by the host (cpds.py pack_mlp_tc) and streamed L2 -> shared memory
+//     with cp.async.bulk through a ring of mbarrier-guarded buffers; one elected lane of one warp tops the ring
+//     up (non-blocking look-ahead) each time it enters an MLP, so no warp -- and no register allocation -- is
+//     spent on a dedicated producer;
+//   * a first layer with <= 4 inputs (K would be padded 2 -> 8 for 64 useful MACs per row) runs as 16 Dp packed
+//     FMAs per row straight from a plain copy of W1 / b1 at the head of the image: one MMA round trip less;
 //   * fp32 parity (1e-5) rules out plain TF32, so every product is the error-compensated
 //     3xTF32 split  a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  (hi = RN-to-tf32, lo = exact
 //     remainder), accumulated in fp32 in TMEM: ~2^-21 relative per product;
-//   * each warpgroup issues its own MMAs (one elected thread) and waits on its own mbarrier
-//     (tcgen05.commit), so the four row tiles of a CTA drift freely and hide each other's
-//     MMA / TMEM latency; the only CTA-wide coupling is the weight ring.
+//   * each warpgroup issues its own MMAs (one elected thread of warp `wg & 3`, so the issuing warps of a CTA
+//     sit on different SM sub-partitions) and waits on per-tile mbarriers (tcgen05.commit); tiles drift freely
+//     and hide each other's MMA / TMEM latency; the only CTA-wide coupling is the weight ring.
 //
-// TMEM map (512 columns allocated, 96 per warpgroup): D fp32 accumulator [0,32) | A_hi [32,64) |
-// A_lo [64,96).
+// TMEM map (512 columns allocated, 96 per tile): D fp32 accumulator [0,32) | A_hi [32,64) | A_lo [64,96); then the
+// 8-column constant block (1, 0, ..., 0) of the bias step.
 #pragma once
 #include "vbn_schedule.cuh"
+#include "vbn_tc_layout.h"
 
 namespace vbn {
 namespace tc {
-
-constexpr int kWgThreads = 128;
-constexpr int kMaxWg = 5;
-constexpr int kTmemCols = 512;
-constexpr int kColsPerWg = 96;
-constexpr int kColD = 0, kColAhi = 32, kColAlo = 64;
-constexpr int kHidden = 32;
-constexpr int kWbufBytes = 30720;  // largest weight image (K1 = 32, N3 = 32): 2 * 4 * 3 * 32 * 40 B
-constexpr int kBiasK = 8;          // every layer carries its bias as one extra K = 8 step (column K of the image)
-constexpr int kMaxBufs = 4;
-constexpr int kCtrlBytes = 128;    // tmem address + up to 13 mbarriers
-
-// bytes of one weight image: W1 hi/lo [32][K1+8], W2 hi/lo [32][40], W3 hi/lo [N3][40] (bias = column K)
-__host__ __device__ __forceinline__ int blob_bytes(int k1, int n3) {
-  return 4 * 2 * (kHidden * (k1 + kBiasK) + kHidden * (kHidden + kBiasK) + n3 * (kHidden + kBiasK));
-}
 
 // ---- PTX wrappers -----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -89,6 +77,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+// 16 bytes of shared memory (warp-uniform address: one broadcast wavefront) as two packed f32x2 operands
+__device__ __forceinline__ void lds_f32x4_as_x2(uint32_t addr, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
 }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -230,24 +222,30 @@ __device__ __forceinline__ void issue_layer(uint32_t d, uint32_t a_hi, uint32_t 
 }
 
 // Per-thread tensor-core state, plugged into Ctx as the TC policy.
-template <int NWG>
+// NWG warpgroups per CTA, RPT 128-row tiles per warpgroup (thread t of a warpgroup owns row t of each of its
+// tiles: TMEM lane t of RPT column regions).  <4,1>: four tiles drift against each other (thread-level
+// parallelism hides the MMA round trips); <2,2>: each thread interleaves two rows -- tile 1's MMAs run while
+// tile 0's accumulator is split, and the per-op control flow, descriptor fetch and weight loads are paid once
+// for two rows.
+template <int NWG, int RPT>
 struct TcMlp {
   static constexpr bool kEnabled = true;
   static constexpr bool kLoops = false;      // Gibbs programs never carry tensor-core images
-  static constexpr bool kInlineRng = true;   // inlined generator with constant-bank round keys: 80.4 -> 78.8 ms on cfg5 (it lost when registers were tighter)
-  uint32_t t_d, t_ahi, t_alo;  // TMEM addresses for this thread's warp (lane base folded in)
-  uint32_t m_d, m_ahi, m_alo;  // same columns, lane 0: operands of the MMA
-  uint32_t m_ones;             // 8 columns shared by all warpgroups holding (1, 0, ..., 0): A operand of the bias step
-  uint32_t wbuf;               // shared-space address of weight buffer 0
-  const unsigned char* wbuf_ptr;
-  uint32_t full_bar, empty_bar, mma_bar;  // full/empty: arrays of nbuf; mma_bar: this warpgroup's
+  static constexpr bool kInlineRng = true;   // inlined generator with constant-bank round keys
+  uint32_t t_d;        // TMEM address of tile 0's accumulator for this thread's warp (lane base folded in); tile j
+                       // adds j * kColsPerTile, A_hi / A_lo add kColAhi / kColAlo
+  uint32_t m_d;        // same columns, lane 0: operand of the MMA
+  uint32_t m_ones;     // 8 columns shared by all warpgroups holding (1, 0, ..., 0): A operand of the bias step
+  uint32_t wbuf;       // shared-space address of weight buffer 0
+  uint32_t full_bar, empty_bar, mma_bar;  // full/empty: arrays of nbuf; mma_bar: this warpgroup's (RPT of them)
   uint32_t w_iter;     // tensor-core MLPs consumed so far (ring position)
-  uint32_t w_buf;      // w_iter % nbuf, and (w_iter / nbuf) & 1 in bit 8: kept as running state (nbuf
-                       // is a runtime value; the division pair cost ~37 instructions per MLP)
-  uint32_t mma_phase;  // parity of the next completion of mma_bar
+  uint32_t w_buf;      // w_iter % nbuf, and (w_iter / nbuf) & 1 in bit 8: kept as running state
+  uint32_t mma_phase;  // parity of the next completion of the mma barriers (all tiles of a thread move together)
   int nbuf;
-  int wg, warp_in_wg, lane;
-  // weight-ring producer (warp 0 only)
+  int wg, lane;
+  bool issuer;         // this warp issues its warpgroup's MMAs: warp (wg & 3) of the warpgroup, so that the
+                       // issuing warps of a CTA sit on four different SM sub-partitions (warp id mod 4)
+  // weight-ring producer (one warp of the CTA)
   bool producer;
   uint32_t p_iter;     // weight images issued so far
   uint32_t p_buf;      // p_iter % nbuf | (((p_iter / nbuf) & 1) ^ 1) << 8   (running, like w_buf)
@@ -256,6 +254,9 @@ struct TcMlp {
   const int2* tc_list; // per tensor-core op: {float offset of its image in params, bytes}
   const float* params;
   uint32_t n_tc;
+
+  __device__ __forceinline__ uint32_t td(int j) const { return t_d + static_cast<uint32_t>(j * kColsPerTile); }
+  __device__ __forceinline__ uint32_t md(int j) const { return m_d + static_cast<uint32_t>(j * kColsPerTile); }
 
   // Issues every image whose ring slot is free, up to nbuf ahead of this warp; blocks only for the
   // image of the op this warp is about to run (its slot frees once the slowest warp has left op
@@ -280,127 +281,188 @@ struct TcMlp {
 
   __device__ __forceinline__ void wg_sync() const { named_bar_sync(1 + wg, kWgThreads); }
 
-  // all 128 threads of the warpgroup: publish TMEM writes, elect, issue, wait for completion
-  __device__ __forceinline__ void run_layer(uint32_t b_hi, uint32_t b_lo, int k, int n) {
+  // All 128 threads of the warpgroup: make this thread's TMEM stores visible to the tensor core, meet, and let
+  // the issuing warp queue one layer for tiles [j0, j1) -- each tile commits to its own mbarrier.
+  __device__ __forceinline__ void publish_and_issue(int j0, int j1, uint32_t b_hi, uint32_t b_lo, int k, int n) {
+    tmem_wait_st();
     tc_fence_before();
     wg_sync();
-    tc_fence_after();
-    if (warp_in_wg == 0) {  // warp-uniform: operands stay on the uniform datapath
+    if (issuer) {  // warp-uniform: operands stay on the uniform datapath
+      tc_fence_after();
       if (elect_one()) {
-        switch (k) {
-          case 8: issue_layer<1>(m_d, m_ahi, m_alo, m_ones, b_hi, b_lo, n); break;
-          case 16: issue_layer<2>(m_d, m_ahi, m_alo, m_ones, b_hi, b_lo, n); break;
-          case 24: issue_layer<3>(m_d, m_ahi, m_alo, m_ones, b_hi, b_lo, n); break;
-          default: issue_layer<4>(m_d, m_ahi, m_alo, m_ones, b_hi, b_lo, n); break;
+        for (int j = j0; j < j1; ++j) {
+          const uint32_t d = md(j);
+          switch (k) {
+            case 8: issue_layer<1>(d, d + kColAhi, d + kColAlo, m_ones, b_hi, b_lo, n); break;
+            case 16: issue_layer<2>(d, d + kColAhi, d + kColAlo, m_ones, b_hi, b_lo, n); break;
+            case 24: issue_layer<3>(d, d + kColAhi, d + kColAlo, m_ones, b_hi, b_lo, n); break;
+            default: issue_layer<4>(d, d + kColAhi, d + kColAlo, m_ones, b_hi, b_lo, n); break;
+          }
+          mma_commit(mma_bar + 8 * j);
         }
-        mma_commit(mma_bar);
       }
       __syncwarp();
     }
-    mbar_wait(mma_bar, mma_phase);
-    mma_phase ^= 1u;
+  }
+  // the layer queued last for tile j has completed: its accumulator may be read, its A operand overwritten
+  __device__ __forceinline__ void await(int j) const {
+    mbar_wait(mma_bar + 8 * j, mma_phase);
     tc_fence_after();
   }
 
-  // D (32 fp32 columns, bias included) -> activation -> 3xTF32 split -> A_hi / A_lo.
-  // Both halves of the accumulator row are requested before the first is processed, so the second
-  // TMEM read is in flight while the first half is split.
-  __device__ __forceinline__ void split_half(int act, const uint32_t (&v)[16], int half) {
+  // 32 activations (already through the activation function) -> 3xTF32 split -> A_hi / A_lo of tile j
+  __device__ __forceinline__ void split_store(int j, int half, const float (&h)[16], bool relu_pending) {
     uint32_t hi[16], lo[16];
-    if (act == VBN_ACT_RELU) {
+    if (relu_pending) {
 #pragma unroll
       for (int q = 0; q < 16; q += 2)
-        split_tf32_x2(fmaxf(__uint_as_float(v[q]), 0.0f), fmaxf(__uint_as_float(v[q + 1]), 0.0f), hi[q],
-                      hi[q + 1], lo[q], lo[q + 1]);
+        split_tf32_x2(fmaxf(h[q], 0.0f), fmaxf(h[q + 1], 0.0f), hi[q], hi[q + 1], lo[q], lo[q + 1]);
     } else {
 #pragma unroll
-      for (int q = 0; q < 16; ++q) split_tf32(activate_slow(__uint_as_float(v[q]), act), hi[q], lo[q]);
+      for (int q = 0; q < 16; q += 2) split_tf32_x2(h[q], h[q + 1], hi[q], hi[q + 1], lo[q], lo[q + 1]);
     }
-    tmem_st16(t_ahi + 16 * half, hi);
-    tmem_st16(t_alo + 16 * half, lo);
+    tmem_st16(td(j) + kColAhi + 16 * half, hi);
+    tmem_st16(td(j) + kColAlo + 16 * half, lo);
   }
-  __device__ __forceinline__ void hidden_epilogue(int act) {
-    if constexpr (NWG <= 4) {
-      uint32_t v0[16], v1[16];
-      tmem_ld16(t_d, v0);
-      tmem_ld16(t_d + 16, v1);
-      tmem_wait_ld();
-      split_half(act, v0, 0);
-      split_half(act, v1, 1);
-    } else {  // 5 warpgroups leave 96 registers per thread: one half at a time
+  __device__ __forceinline__ void act_split_store(int j, int half, int act, const uint32_t (&v)[16]) {
+    float h[16];
+    if (act == VBN_ACT_RELU) {
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t v[16];
-        tmem_ld16(t_d + 16 * half, v);
-        tmem_wait_ld();
-        split_half(act, v, half);
-      }
+      for (int q = 0; q < 16; ++q) h[q] = __uint_as_float(v[q]);
+      split_store(j, half, h, true);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) h[q] = activate_slow(__uint_as_float(v[q]), act);
+      split_store(j, half, h, false);
     }
-    tmem_wait_st();
+  }
+  // D of tile j (32 fp32 columns, bias included) -> activation -> split -> A.  Both halves of the accumulator
+  // row are requested before the first is processed, so the second TMEM read is in flight meanwhile.
+  __device__ __forceinline__ void hidden_epilogue(int j, int act) {
+    uint32_t v0[16], v1[16];
+    tmem_ld16(td(j), v0);
+    tmem_ld16(td(j) + 16, v1);
+    tmem_wait_ld();
+    act_split_store(j, 0, act, v0);
+    act_split_store(j, 1, act, v1);
   }
 
-  // The three layers of the op's MLP for this thread's row.  On return D holds the N3 outputs
-  // (bias included) and the weight buffer has been released.
+  // First layer on the FP32 pipe (<= 4 parent dims: 16 Dp packed FMAs per row).  `l1` = shared-space address of
+  // the plain block at the head of the weight image: W1^T[4][32] (rows >= Dp zero), b1[32].  The MMA route
+  // (K padded 2 -> 8: 5 MMAs, an input split, two TMEM stores, a commit / wait round trip and a 32-column TMEM
+  // read) only pays from Dp > 4.
   template <class C>
-  __device__ __forceinline__ void layers(C& c, const VbnOp& op, const float* norm, const int32_t* par) {
-    const int k1 = op.tc[2], n3 = op.tc[3];
+  __device__ __forceinline__ void hidden1_fma(C& c, const VbnOp& op, const float* norm, int j, uint32_t l1) {
     const int dp = op.n_par;
+    unsigned long long h[16];  // 32 pre-activations as f32x2 pairs
+#pragma unroll
+    for (int q = 0; q < 8; ++q) lds_f32x4_as_x2(l1 + 4 * (4 * kHidden + 4 * q), h[2 * q], h[2 * q + 1]);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      if (p < dp) {
+        float z = c.slot((op.aux[1 + (p >> 1)] >> (16 * (p & 1))) & 0xFFFF, j);
+        if (norm) z = __fdiv_rn(z - __ldg(norm + p), __ldg(norm + dp + p));
+        unsigned long long zz;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(zz) : "f"(z));
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          unsigned long long w0, w1;
+          lds_f32x4_as_x2(l1 + 4 * (p * kHidden + 4 * q), w0, w1);
+          asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(h[2 * q]) : "l"(w0), "l"(zz));
+          asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(h[2 * q + 1]) : "l"(w1), "l"(zz));
+        }
+      }
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float f[16];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(f[2 * q]), "=f"(f[2 * q + 1]) : "l"(h[8 * half + q]));
+      if (op.act == VBN_ACT_RELU) {
+        split_store(j, half, f, true);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) f[q] = activate_slow(f[q], op.act);
+        split_store(j, half, f, false);
+      }
+    }
+  }
+
+  // Inputs of tile j -> A (K1 columns, zero padded) for a first layer on the tensor core; gaussian_nn
+  // standardises them first.
+  template <class C>
+  __device__ __forceinline__ void inputs_to_a(C& c, const VbnOp& op, const float* norm, const int32_t* par, int j,
+                                              int k1) {
+    const int dp = op.n_par;
+    for (int k0 = 0; k0 < k1; k0 += 8) {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int p = k0 + q;
+        float z = 0.0f;
+        if (p < dp) {
+          z = c.slot(__ldg(par + p), j);
+          if (norm) z = __fdiv_rn(z - __ldg(norm + p), __ldg(norm + dp + p));
+        }
+        split_tf32(z, hi[q], lo[q]);
+      }
+      tmem_st8(td(j) + kColAhi + k0, hi);
+      tmem_st8(td(j) + kColAlo + k0, lo);
+    }
+  }
+
+  // Everything of the op's MLP up to and including the issue of its last layer, for all RPT tiles.  The caller
+  // then does independent work (generator refills), await(j) per tile -- D of tile j holds the N3 outputs, bias
+  // included -- and layers_end().
+  template <class C>
+  __device__ __forceinline__ void layers_begin(C& c, const VbnOp& op, const float* norm, const int32_t* par) {
+    const int k1 = op.tc[2], n3 = op.tc[3];
     if (producer) {  // warp-uniform
       if (elect_one()) produce();
       __syncwarp();
     }
     const uint32_t buf = w_buf & 0xFFu;
     const uint32_t ph = w_buf >> 8;
-    const uint32_t w1hi = wbuf + buf * kWbufBytes;
-    const uint32_t w1lo = w1hi + kHidden * (k1 + kBiasK) * 4;
-    const uint32_t w2hi = w1lo + kHidden * (k1 + kBiasK) * 4;
+    const uint32_t img = wbuf + buf * kWbufBytes;
+    // image: k1 == 0: L1 plain block (640 B) | W2hi W2lo | W3hi W3lo ; else W1hi W1lo | W2hi W2lo | W3hi W3lo
+    const uint32_t w1_bytes = k1 == 0 ? kL1PlainBytes / 2 : kHidden * (k1 + kBiasK) * 4;  // per half
+    const uint32_t w2hi = img + 2 * w1_bytes;
     const uint32_t w2lo = w2hi + kHidden * (kHidden + kBiasK) * 4;
     const uint32_t w3hi = w2lo + kHidden * (kHidden + kBiasK) * 4;
     const uint32_t w3lo = w3hi + n3 * (kHidden + kBiasK) * 4;
 
-    // ---- inputs -> A (K1 columns, zero padded); gaussian_nn standardises them first
-    if (op.flags & VBN_F_PAR4) {  // <= 4 parent dims, slots packed in aux[1..2]: K1 == 8
-      uint32_t hi[8], lo[8];
+    if (k1 == 0) {
+      mbar_wait(full_bar + 8 * buf, ph);  // this layer reads its weights from the image itself
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float z = 0.0f;
-        if (q < dp) {
-          z = c.slot((op.aux[1 + (q >> 1)] >> (16 * (q & 1))) & 0xFFFF, 0);
-          if (norm) z = __fdiv_rn(z - __ldg(norm + q), __ldg(norm + dp + q));
-        }
-        split_tf32(z, hi[q], lo[q]);
-      }
-#pragma unroll
-      for (int q = 4; q < 8; ++q) hi[q] = lo[q] = 0u;
-      tmem_st8(t_ahi, hi);
-      tmem_st8(t_alo, lo);
+      for (int j = 0; j < RPT; ++j) hidden1_fma(c, op, norm, j, img);
     } else {
-      for (int k0 = 0; k0 < k1; k0 += 8) {
-        uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int p = k0 + q;
-          float z = 0.0f;
-          if (p < dp) {
-            z = c.slot(__ldg(par + p), 0);
-            if (norm) z = __fdiv_rn(z - __ldg(norm + p), __ldg(norm + dp + p));
-          }
-          split_tf32(z, hi[q], lo[q]);
-        }
-        tmem_st8(t_ahi + k0, hi);
-        tmem_st8(t_alo + k0, lo);
+      for (int j = 0; j < RPT; ++j) inputs_to_a(c, op, norm, par, j, k1);
+      mbar_wait(full_bar + 8 * buf, ph);
+      publish_and_issue(0, RPT, img, img + w1_bytes, k1, kHidden);
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        await(j);
+        hidden_epilogue(j, op.act);
       }
+      mma_phase ^= 1u;
     }
-    tmem_wait_st();
-    mbar_wait(full_bar + 8 * buf, ph);  // weights + biases of this op have landed
-
-    run_layer(w1hi, w1lo, k1, kHidden);
-    hidden_epilogue(op.act);
-    run_layer(w2hi, w2lo, kHidden, kHidden);
-    hidden_epilogue(op.act);
-    run_layer(w3hi, w3lo, kHidden, n3);
-
-    // this warp is done with the weight buffer (its MMAs completed)
+    publish_and_issue(0, RPT, w2hi, w2lo, kHidden, kHidden);
+    // tile j's accumulator is split while the other tiles' MMAs run; its last layer is queued at once
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      await(j);
+      hidden_epilogue(j, op.act);
+      publish_and_issue(j, j + 1, w3hi, w3lo, kHidden, n3);
+    }
+    mma_phase ^= 1u;
+  }
+  __device__ __forceinline__ void layers_end() {
+    mma_phase ^= 1u;
+    // this warp is done with the weight buffer (every MMA it waited for has completed)
+    const uint32_t buf = w_buf & 0xFFu;
+    const uint32_t ph = w_buf >> 8;
     __syncwarp();
     if (lane == 0) mbar_arrive(empty_bar + 8 * buf);
     ++w_iter;
@@ -411,22 +473,27 @@ struct TcMlp {
   // (mlp_fast32 / mlp_generic), for op_gnn / op_mdn / op_snn to pick up.
   template <class C>
   __device__ __forceinline__ void mlp(C& c, const VbnOp& op, const float* norm, const int32_t* par) {
-    layers(c, op, norm, par);
+    layers_begin(c, op, norm, par);
     const int n3 = op.tc[3], n_out = op.n_out;
-    for (int o0 = 0; o0 < n3; o0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(t_d + o0, v);
-      tmem_wait_ld();
 #pragma unroll
-      for (int q = 0; q < 16; ++q)
-        if (o0 + q < n_out) c.scr(o0 + q, 0) = __uint_as_float(v[q]);
+    for (int j = 0; j < RPT; ++j) {
+      await(j);
+      for (int o0 = 0; o0 < n3; o0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(td(j) + o0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          if (o0 + q < n_out) c.scr(o0 + q, j) = __uint_as_float(v[q]);
+      }
     }
+    layers_end();
   }
 
   // VBN_F_MDNPLAIN: an MDN node (D = 1, K <= 5 components, <= 4 parent dims) that is only drawn
   // (mdn.py:209-235).  MLP outputs stay in registers: logits[K], then per component (loc, raw scale).
   template <int K, class C>
-  __device__ __forceinline__ void mdn_tail(C& c, const VbnOp& op, const uint32_t (&v)[16]) {
+  __device__ __forceinline__ void mdn_tail(C& c, const VbnOp& op, const uint32_t (&v)[16], int j) {
     float q[K];
     float mx = __uint_as_float(v[0]);
 #pragma unroll
@@ -447,12 +514,7 @@ struct TcMlp {
       q[k] = fmaxf(q[k], floor_e);
       tot += q[k];
     }
-    const int uq = op.u_off >> 2;
-    if (uq != c.rows.cur_uq) {
-      c.rows.cur_uq = uq;
-      c.rows.ucache[0] = c.uniforms(0, uq, 1u, false);
-    }
-    const float u = lane4(c.rows.ucache[0], op.u_off & 3) * tot;
+    const float u = lane4(c.rows.ucache[j], op.u_off & 3) * tot;
     float cum = 0.0f;
     float loc = __uint_as_float(v[K + 2 * (K - 1)]), raw = __uint_as_float(v[K + 2 * (K - 1) + 1]);
 #pragma unroll
@@ -464,37 +526,51 @@ struct TcMlp {
         raw = __uint_as_float(v[K + 2 * k + 1]);
       }
     }
-    const int nq = op.n_off >> 2;
-    if (nq != c.rows.cur_nq) {
-      c.rows.cur_nq = nq;
-      c.rows.ncache[0] = c.normals(0, nq, 0u, false);
-    }
-    const float eps = lane4(c.rows.ncache[0], op.n_off & 3);
+    const float eps = lane4(c.rows.ncache[j], op.n_off & 3);
     const float sc = softplus20_fast(raw) + __int_as_float(op.aux[0]);
-    c.slot(op.out_slot, 0) = fmaf(eps, sc, loc);
+    c.slot(op.out_slot, j) = fmaf(eps, sc, loc);
   }
 
   template <class C>
   __device__ __forceinline__ void mdn_plain(C& c, const VbnOp& op) {
-    layers(c, op, nullptr, nullptr);
-    uint32_t v[16];
-    tmem_ld16(t_d, v);
-    tmem_wait_ld();
-    switch (op.k) {
-      case 2: mdn_tail<2>(c, op, v); break;
-      case 3: mdn_tail<3>(c, op, v); break;
-      case 4: mdn_tail<4>(c, op, v); break;
-      default: mdn_tail<5>(c, op, v); break;
+    layers_begin(c, op, nullptr, nullptr);
+    // generator refills run in the shadow of the last layer's MMAs
+    const int uq = op.u_off >> 2;
+    if (uq != c.rows.cur_uq) {
+      c.rows.cur_uq = uq;
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) c.rows.ucache[j] = c.uniforms(j, uq, 1u, false);
     }
+    const int nq = op.n_off >> 2;
+    if (nq != c.rows.cur_nq) {
+      c.rows.cur_nq = nq;
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) c.rows.ncache[j] = c.normals(j, nq, 0u, false);
+    }
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      await(j);
+      uint32_t v[16];
+      tmem_ld16(td(j), v);
+      tmem_wait_ld();
+      switch (op.k) {
+        case 2: mdn_tail<2>(c, op, v, j); break;
+        case 3: mdn_tail<3>(c, op, v, j); break;
+        case 4: mdn_tail<4>(c, op, v, j); break;
+        default: mdn_tail<5>(c, op, v, j); break;
+      }
+    }
+    layers_end();
   }
 };
 
-// The kernel.  grid <= #SMs (one CTA per SM), NWG * 128 threads.
+// The kernel.  grid <= #SMs (one CTA per SM), NWG * 128 threads, NWG * RPT * 128 rows per pass.
 // dynamic smem: [ctrl 128 B][nbuf weight buffers][slots + scratch: (n_slots+n_scratch) x ROWS floats]
-template <int NWG>
+template <int NWG, int RPT>
 __global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const ScheduleArgs a, const int nbuf) {
   constexpr int kThreads = NWG * kWgThreads;
-  static_assert(NWG <= kMaxWg && NWG * kColsPerWg + kBiasK <= kTmemCols, "TMEM budget");
+  constexpr int kTiles = NWG * RPT;
+  static_assert(kTiles <= kMaxTiles && kTiles * kColsPerTile + kBiasK <= kTmemCols, "TMEM budget");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform for the compiler
@@ -515,7 +591,7 @@ __global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const S
       mbar_init(full_bar + 8 * i, 1);               // the producer lane's arrive.expect_tx
       mbar_init(empty_bar + 8 * i, kThreads / 32);  // one arrive per warp
     }
-    for (int g = 0; g < NWG; ++g) mbar_init(mma_bar0 + 8 * g, 1);  // tcgen05.commit
+    for (int g = 0; g < kTiles; ++g) mbar_init(mma_bar0 + 8 * g, 1);  // tcgen05.commit
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(smem_base, kTmemCols);
@@ -525,37 +601,28 @@ __global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const S
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem_raw), 0);
 
   const int64_t n_tiles = (a.n_rows + kWgThreads - 1) / kWgThreads;
-  const int64_t per_round = static_cast<int64_t>(gridDim.x) * NWG;
+  const int64_t per_round = static_cast<int64_t>(gridDim.x) * kTiles;
   const int64_t n_iter = (n_tiles + per_round - 1) / per_round;  // same for every warpgroup: the ring needs it
 
-  {  // constant A block of the bias step: columns [NWG*96, NWG*96 + 8) of every lane = (1, 0, ..., 0)
+  {  // constant A block of the bias step: columns [kTiles*96, kTiles*96 + 8) of every lane = (1, 0, ..., 0)
     const uint32_t ones[8] = {__float_as_uint(1.0f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-    if (warp < 4) tmem_st8(tmem_base + NWG * kColsPerWg + (static_cast<uint32_t>(warp * 32) << 16), ones);
+    if (warp < 4) tmem_st8(tmem_base + kTiles * kColsPerTile + (static_cast<uint32_t>(warp * 32) << 16), ones);
     tmem_wait_st();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
   }
-  Ctx<1, kThreads, TcMlp<NWG>> c(a, slots, 0);  // the thread index is already folded into `slots`
+  Ctx<RPT, kThreads, TcMlp<NWG, RPT>> c(a, slots, 0);  // the thread index is already folded into `slots`
   const int wg = warp >> 2;
-  const uint32_t col = tmem_base + static_cast<uint32_t>(wg * kColsPerWg);
+  const uint32_t col = tmem_base + static_cast<uint32_t>(wg * RPT * kColsPerTile);
   const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
   c.tc.m_d = col + kColD;
-  c.tc.m_ahi = col + kColAhi;
-  c.tc.m_alo = col + kColAlo;
   c.tc.t_d = c.tc.m_d + lane_base;
-  c.tc.t_ahi = c.tc.m_ahi + lane_base;
-  c.tc.t_alo = c.tc.m_alo + lane_base;
-  c.tc.mma_bar = mma_bar0 + 8 * wg;
+  c.tc.mma_bar = mma_bar0 + 8 * wg * RPT;
   // same treatment for the per-thread TMEM / barrier addresses: values, not recipes in (tid, wg)
   asm volatile("" : "+r"(c.tc.m_d), "+r"(c.tc.t_d), "+r"(c.tc.mma_bar));
-  c.tc.m_ahi = c.tc.m_d + (kColAhi - kColD);
-  c.tc.m_alo = c.tc.m_d + (kColAlo - kColD);
-  c.tc.t_ahi = c.tc.t_d + (kColAhi - kColD);
-  c.tc.t_alo = c.tc.t_d + (kColAlo - kColD);
-  c.tc.m_ones = tmem_base + NWG * kColsPerWg;
+  c.tc.m_ones = tmem_base + kTiles * kColsPerTile;
   c.tc.wbuf = wbuf;
-  c.tc.wbuf_ptr = smem_raw + kCtrlBytes;
   c.tc.full_bar = full_bar;
   c.tc.empty_bar = empty_bar;
   c.tc.w_iter = 0;
@@ -563,9 +630,9 @@ __global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const S
   c.tc.mma_phase = 0;
   c.tc.nbuf = nbuf;
   c.tc.wg = wg;
-  c.tc.warp_in_wg = warp & 3;
   c.tc.lane = lane;
-  c.tc.producer = warp == 0;
+  c.tc.issuer = (warp & 3) == (wg & 3);
+  c.tc.producer = warp == (NWG > 1 ? 6 : 2);  // a warp that issues no MMAs (warpgroup 1's issuer is its warp 1 = CTA warp 5)
   c.tc.p_iter = 0;
   c.tc.p_buf = 1u << 8;
   c.tc.p_idx = 0;
@@ -574,63 +641,21 @@ __global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const S
   c.tc.params = a.params;
   c.tc.n_tc = static_cast<uint32_t>(a.n_tc);
   for (int64_t it = 0; it < n_iter; ++it) {
-    const int64_t tile = (it * gridDim.x + blockIdx.x) * NWG + wg;
-    bind_row(c, 0, tile * kWgThreads + (tid & (kWgThreads - 1)));
-    // same reason as slot_word: keep the Philox counter words as values, not as a recipe (the row
-    // index -> (query, sample) division chain was being re-executed per op)
-    int row_ok = c.rows.valid[0] ? 1 : 0;
-    asm volatile("" : "+r"(c.rows.gs[0]), "+r"(c.rows.gb[0]), "+l"(c.rows.r[0]), "+r"(row_ok));
-    c.rows.valid[0] = row_ok != 0;
+    const int64_t base = (it * gridDim.x + blockIdx.x) * static_cast<int64_t>(kThreads * RPT);
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      bind_row(c, j, base + j * kThreads + tid);
+      // same reason as slot_word: keep the Philox counter words as values, not as a recipe (the row
+      // index -> (query, sample) division chain was being re-executed per op)
+      int row_ok = c.rows.valid[j] ? 1 : 0;
+      asm volatile("" : "+r"(c.rows.gs[j]), "+r"(c.rows.gb[j]), "+l"(c.rows.r[j]), "+r"(row_ok));
+      c.rows.valid[j] = row_ok != 0;
+    }
     run_ops<true>(c);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
-}
-
-// Bench-only probe: dense tcgen05 kind::tf32 throughput of this GPU (the denominator of the
-// tensor roofline; MEASURED_PEAKS.json only has the bf16 figure).  One CTA per SM, one thread issues
-// `iters` back-to-back M=128, N=256, K=8 MMAs (A in TMEM, B a zeroed 8 KB shared-memory tile).
-// flops = 2 * 128 * 256 * 8 * iters * gridDim.x.
-__global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters, float* __restrict__ out) {
-  __shared__ __align__(128) float b_tile[256 * 8];
-  __shared__ __align__(8) unsigned long long bar;
-  __shared__ uint32_t tmem_slot;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  for (int i = tid; i < 256 * 8; i += 128) b_tile[i] = 0.0f;
-  if (tid == 0) {
-    mbar_init(smem_u32(&bar), 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), kTmemCols);
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // b_tile stores -> tensor-core reads
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
-  {  // zero the A operand (columns 256..263) so the accumulation stays finite
-    uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    tmem_st8(tmem + 256 + (static_cast<uint32_t>(warp * 32) << 16), z);
-    tmem_wait_st();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (tid == 0) {
-    const uint64_t bd = make_b_desc(smem_u32(b_tile), 128u, 256u);
-    const uint32_t idesc = make_idesc(256);
-    for (int i = 0; i < iters; ++i) mma_tf32_ts(tmem, tmem + 256, bd, idesc, i > 0 ? 1u : 0u);
-    mma_commit(smem_u32(&bar));
-  }
-  mbar_wait(smem_u32(&bar), 0);
-  tc_fence_after();
-  uint32_t v[16];
-  tmem_ld16(tmem + (static_cast<uint32_t>(warp * 32) << 16), v);
-  tmem_wait_ld();
-  if (__uint_as_float(v[0]) == 123.456f) out[0] = 1.0f;  // keep the chain observable
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, kTmemCols);
 }
 
 }  // namespace tc

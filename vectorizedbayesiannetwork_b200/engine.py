@@ -17,10 +17,11 @@ from .plan import Program, Role, compile_schedule
 KERNEL_EVENTS = None  # set to a list by bench.py to time every schedule-kernel launch
 
 
-def tc_warpgroups() -> int:
-    """128-row warpgroups per CTA of the tensor-core kernel (VBN_TC_WG=4|5)."""
-    n = int(os.environ.get("VBN_TC_WG", "4"))
-    return n if n in (4, 5) else 4
+def tc_shape() -> int:
+    """Geometry of the tensor-core kernel as VbnProgramDesc.tc = warpgroups | tiles per warpgroup << 8
+    (VBN_TC_SHAPE=4x1|2x2; default 4x1: four 128-row warpgroups with one tile each)."""
+    nwg, rpt = {"4x1": (4, 1), "2x2": (2, 2)}.get(os.environ.get("VBN_TC_SHAPE", "4x1"), (4, 1))
+    return nwg | (rpt << 8)
 
 
 def require_cuda(device=None) -> torch.device:
@@ -64,7 +65,7 @@ class DevicePlan:
                 par_slots_dev=self.par_slots.data_ptr(), n_par_slots=int(self.par_slots.numel()),
                 params_dev=self.params.data_ptr(), n_params=int(self.params.numel()),
                 n_slots=program.n_slots, n_scratch=program.n_scratch,
-                heavy=1 if program.heavy else 0, tc=tc_warpgroups() if program.tc else 0,
+                heavy=1 if program.heavy else 0, tc=tc_shape() if program.tc else 0,
                 tc_list_dev=self.tc_list.data_ptr() if program.tc else None,
                 n_tc=int(program.tc_list.shape[0]) if program.tc else 0,
                 rows_per_thread=2 if any(int(k) == L.OP_TAB for k in program.ops["kind"]) else 0,

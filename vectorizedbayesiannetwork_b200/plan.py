@@ -297,6 +297,9 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
                             and r.src == "sample" and not r.shared and not r.inject
                             and not r.add_logw and not r.out_logp and not r.out_params):
                         flags |= L.F_MDNPLAIN
+            if int(op["tc"][0]) and int(op["tc"][2]) == 0 and not (flags & L.F_PAR4):
+                # the FP32-pipe first layer reads its parent slots from the descriptor (cpds.pack_mlp_tc l1_fma)
+                raise ValueError(f"node '{n}': tensor-core image without first-layer MMA needs packed parent slots")
             if (_roots_enabled() and pk.kind == L.OP_MDN and pk.n_par == 0 and d == 1 and 2 <= pk.k <= 4
                     and r.src == "sample" and not r.shared and not r.inject and not r.store
                     and not r.add_logw and not r.out_logp and not r.out_params):
