@@ -317,6 +317,18 @@ int32_t vbn_kde_log_prob(const float* train_p_dev, const float* train_y_dev, int
 int32_t vbn_philox_fill(const uint32_t* ctr_dev, int64_t n, uint32_t key0, uint32_t key1,
                         uint32_t* out_dev, void* stream);
 
+/* Replay hook: the random draws vbn_run_forward makes for a run with the same (seed, call_offset, offsets), through
+ * the same inlined generator as the hot kernels (csrc/vbn_schedule.cuh Ctx::normals / uniforms: Philox4x32-10 on
+ * counter (global sample, global query | 0xFFFFFFFF when shared, block | tag << 30, call_offset), Box-Muller / u01).
+ * kind 0: normals, 1: uniforms, 2: raw generator words (uint32 bit patterns).  Value i of an op's stream
+ * (VbnOp.n_off / u_off + dim) is element i & 3 of block i >> 2.  out_dev: [4 * n_blocks][Bn][S] floats for blocks
+ * block_lo .. block_lo + n_blocks - 1, Bn = n_queries (per-row streams) or 1 (shared != 0: the streams of
+ * VBN_F_SHARED ops).  Tests regenerate a run's noise with it and replay it through the CPU oracle; the words are
+ * checked against the oracle's numpy Philox (Random123 known answers). */
+int32_t vbn_stream_draws(uint64_t seed, uint64_t call_offset, int32_t kind, int32_t shared, int32_t block_lo,
+                         int32_t n_blocks, int64_t n_queries, int64_t n_samples, int64_t query_offset,
+                         int64_t sample_offset, float* out_dev, void* stream);
+
 /* Bench-only probe of the FP32 FMA pipe (the MLP layers' roofline denominator): n_blocks x 256
  * threads each run 16*iters FMAs.  mode 0 = scalar FFMA, 1 = packed fma.rn.f32x2.
  * flops = 2 * 16 * iters * 256 * n_blocks.  scratch_dev: >= 1 float. */

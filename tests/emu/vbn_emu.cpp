@@ -218,6 +218,22 @@ int32_t vbn_kde_log_prob(const float* tp, const float* ty, int64_t N, int32_t dp
   }
   return 0;
 }
+int32_t vbn_stream_draws(uint64_t seed, uint64_t call, int32_t kind, int32_t shared, int32_t block_lo, int32_t n_blocks,
+                         int64_t B, int64_t S, int64_t qo, int64_t so, float* out, void*) {
+  vbn::ScheduleArgs keys; keys.key0 = (uint32_t)seed; keys.key1 = (uint32_t)(seed >> 32); vbn::fill_round_keys(keys);
+  const int64_t bn = shared ? 1 : B, per_block = bn * S;
+  const uint32_t tag = (kind == 1 ? 1u : 0u) + (shared ? 2u : 0u);
+  for (int64_t blk = 0; blk < n_blocks; ++blk) for (int64_t b = 0; b < bn; ++b) for (int64_t s = 0; s < S; ++s) {
+    const uint4 c = make_uint4((uint32_t)(so + s), shared ? 0xFFFFFFFFu : (uint32_t)(qo + b), (uint32_t)(block_lo + blk) | (tag << 30), (uint32_t)call);
+    const uint4 w = vbn::philox4x32_10_rk(c, keys.rk);
+    float v[4];
+    if (kind == 0) { const float4 n = vbn::normal4(w); v[0] = n.x; v[1] = n.y; v[2] = n.z; v[3] = n.w; }
+    else if (kind == 1) { const float4 u = vbn::uniform4(w); v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w; }
+    else { std::memcpy(v, &w, 16); }
+    for (int i = 0; i < 4; ++i) out[(4 * blk + i) * per_block + b * S + s] = v[i];
+  }
+  return 0;
+}
 int32_t vbn_fma_peak(int32_t, int32_t, int32_t, float*, void*) { return 0; }
 int32_t vbn_tf32_peak(int32_t, int32_t, float*, void*) { return 0; }
 int32_t vbn_philox_fill(const uint32_t* ctr, int64_t n, uint32_t k0, uint32_t k1, uint32_t* out, void*) {

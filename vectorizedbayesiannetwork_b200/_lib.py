@@ -22,6 +22,7 @@ ACT = {"relu": 0, "tanh": 1, "gelu": 2, "elu": 3}
 WITHIN_BIN = {"uniform": 0, "triangular": 1, "gaussian": 2}
 MAX_LAYERS = 8
 MAX_GENERIC_WIDTH = 128
+TC_WBUF_BYTES = 30720  # one slot of the tensor-core kernel's weight ring (csrc/vbn_tc_layout.h kWbufBytes)
 
 OP_DTYPE = np.dtype(
     [
@@ -91,6 +92,8 @@ EXPORTS = {
     "vbn_fma_peak": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "vbn_tf32_peak": (C.c_int32, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "vbn_philox_fill": (C.c_int32, [C.c_void_p, C.c_int64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "vbn_stream_draws": (C.c_int32, [C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
+                                     C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

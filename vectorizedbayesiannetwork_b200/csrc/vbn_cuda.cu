@@ -440,6 +440,34 @@ int32_t vbn_philox_fill(const uint32_t* ctr_dev, int64_t n, uint32_t key0, uint3
   return VBN_OK;
 }
 
+int32_t vbn_stream_draws(uint64_t seed, uint64_t call_offset, int32_t kind, int32_t shared, int32_t block_lo,
+                         int32_t n_blocks, int64_t n_queries, int64_t n_samples, int64_t query_offset,
+                         int64_t sample_offset, float* out_dev, void* stream) {
+  if (!out_dev || kind < 0 || kind > 2 || block_lo < 0 || n_blocks <= 0 || n_queries <= 0 || n_samples <= 0)
+    return fail(VBN_E_INVALID, "bad argument to vbn_stream_draws");
+  vbn::ScheduleArgs keys;
+  keys.key0 = static_cast<uint32_t>(seed);
+  keys.key1 = static_cast<uint32_t>(seed >> 32);
+  vbn::fill_round_keys(keys);
+  vbn::StreamDrawArgs a;
+  std::memcpy(a.rk, keys.rk, sizeof(a.rk));
+  a.call_offset = static_cast<uint32_t>(call_offset);
+  a.query_offset = static_cast<uint32_t>(query_offset);
+  a.sample_offset = static_cast<uint32_t>(sample_offset);
+  a.kind = kind;
+  a.shared = shared ? 1 : 0;
+  a.block_lo = block_lo;
+  a.n_blocks = n_blocks;
+  a.n_queries = n_queries;
+  a.n_samples = n_samples;
+  const int64_t total = (shared ? 1 : n_queries) * n_samples * n_blocks;
+  const int64_t want = (total + 255) / 256;
+  const unsigned grid = static_cast<unsigned>(want < 148 * 16 ? want : 148 * 16);
+  vbn::stream_draws_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, out_dev);
+  CUDA_TRY(cudaGetLastError());
+  return VBN_OK;
+}
+
 int32_t vbn_fma_peak(int32_t mode, int32_t iters, int32_t n_blocks, float* scratch_dev, void* stream) {
   if (!scratch_dev || iters <= 0 || n_blocks <= 0) return fail(VBN_E_INVALID, "bad argument");
   vbn::fma_peak_kernel<<<n_blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(mode, iters, scratch_dev);

@@ -470,6 +470,46 @@ __global__ void philox_fill_kernel(const uint32_t* __restrict__ ctr, int64_t n, 
   out[4 * i + 3] = r.w;
 }
 
+// The draws the schedule kernels make, exported for replay checks (tests regenerate a run's noise and feed it to
+// the CPU oracle).  Same code path as Ctx::normals / Ctx::uniforms with the inlined generator: counter
+// (global sample, global query | 0xFFFFFFFF when shared, block | tag << 30, call offset), round keys as kernel
+// parameters, normal4 / uniform4.  out[(4 * blk + i) * Bn * S + b * S + s], Bn = 1 for the shared streams.
+// kind 0: normals, 1: uniforms, 2: raw generator words (bit patterns), tags as in vbn_schedule.cuh.
+struct StreamDrawArgs {
+  uint32_t rk[20];
+  uint32_t call_offset, query_offset, sample_offset;
+  int32_t kind, shared, block_lo, n_blocks;
+  int64_t n_queries, n_samples;
+};
+__global__ void __launch_bounds__(256) stream_draws_kernel(const StreamDrawArgs a, float* __restrict__ out) {
+  const int64_t bn = a.shared ? 1 : a.n_queries;
+  const int64_t per_block = bn * a.n_samples;
+  const int64_t total = per_block * a.n_blocks;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t blk = i / per_block, r = i - blk * per_block;
+    const int64_t b = r / a.n_samples, s = r - b * a.n_samples;
+    const uint32_t tag = (a.kind == 1 ? 1u : 0u) + (a.shared ? 2u : 0u);
+    const uint4 c = make_uint4(a.sample_offset + static_cast<uint32_t>(s),
+                               a.shared ? 0xFFFFFFFFu : a.query_offset + static_cast<uint32_t>(b),
+                               static_cast<uint32_t>(a.block_lo + blk) | (tag << 30), a.call_offset);
+    const uint4 w = philox4x32_10_rk(c, a.rk);
+    float4 v;
+    if (a.kind == 0) {
+      v = normal4(w);
+    } else if (a.kind == 1) {
+      v = uniform4(w);
+    } else {
+      v = make_float4(__uint_as_float(w.x), __uint_as_float(w.y), __uint_as_float(w.z), __uint_as_float(w.w));
+    }
+    float* o = out + (4 * blk) * per_block + r;
+    o[0] = v.x;
+    o[per_block] = v.y;
+    o[2 * per_block] = v.z;
+    o[3 * per_block] = v.w;
+  }
+}
+
 }  // namespace vbn
 
 // FP32 FMA peak probe (bench only): the MLP layers run on the FFMA pipe in fp32 (1e-5 parity

@@ -1435,34 +1435,41 @@ __device__ __forceinline__ void run_ops(Ctx<RPT, NT, TC>& c) {
     VbnOp op;  // only the 16-byte quads this op kind reads are fetched (layer_dim: via c.gop)
     {
       const int4* src = reinterpret_cast<const int4*>(a.ops + i);
-      const int4 q0 = __ldg(src + 0);  // kind, flags, dim, n_par
       // The plain ops get their own descriptor object: `op` below is indexed dynamically by the generic
       // paths and therefore lives in local memory, which would cost the hot ops a store per quad.
       if constexpr (TC::kEnabled) {
         // Tensor-core kernel: the whole 128-byte descriptor is requested in ONE round of independent loads.
         // Fetching the kind-specific quads only after the flag test made every op pay two dependent L1
         // round trips (~125 + ~210 cycles measured: 17 % of the kernel's stall samples).
-        const int4 q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3), q4 = __ldg(src + 4);
-        const int4 q5 = __ldg(src + 5), q6 = __ldg(src + 6), q7 = __ldg(src + 7);
+        // Ops that follow an MLP op are served from the descriptor tail of its weight image in shared memory.
+        const int4* dsc = c.tc.op_in_ring(i) ? c.tc.ring_ptr(i) : src;
+        const int4 q0 = dsc[0];  // kind, flags, dim, n_par -- decides which other quads the op reads (a second
+                                 // round trip, ~30 cycles from shared memory; loading all eight up front costs 32
+                                 // registers at the top of every op)
         if (q0.y & (VBN_F_LGPLAIN | VBN_F_MDNROOT | VBN_F_MDNPLAIN)) {
           VbnOp lop;
           int4* ld = reinterpret_cast<int4*>(&lop);
-          ld[0] = q0; ld[1] = q1; ld[2] = q2; ld[3] = q3; ld[4] = q4; ld[5] = q5; ld[6] = q6; ld[7] = q7;
+          ld[0] = q0;
           c.gop = a.ops + i;
           if (q0.y & VBN_F_LGPLAIN) {
+            ld[4] = dsc[4]; ld[5] = dsc[5]; ld[6] = dsc[6];
             op_lg_plain(c, lop);
           } else if (q0.y & VBN_F_MDNROOT) {
+            ld[4] = dsc[4]; ld[5] = dsc[5]; ld[6] = dsc[6]; ld[7] = dsc[7];
             op_mdn_root(c, lop);
           } else {
+            ld[1] = dsc[1]; ld[2] = dsc[2]; ld[3] = dsc[3]; ld[5] = dsc[5]; ld[6] = dsc[6]; ld[7] = dsc[7];
             c.tc.mdn_plain(c, lop);
             store_value(c, lop);  // a plain node may still be the stored target
           }
           continue;
         }
+        const int4 q1 = dsc[1], q2 = dsc[2], q3 = dsc[3], q4 = dsc[4], q5 = dsc[5], q6 = dsc[6], q7 = dsc[7];
         int4* dst = reinterpret_cast<int4*>(&op);
         dst[0] = q0; dst[1] = q1; dst[2] = q2; dst[3] = q3; dst[4] = q4; dst[5] = q5; dst[6] = q6; dst[7] = q7;
       } else {
       // quads 4-6 (what a plain LG op needs) are requested together with quad 0: one L1 round trip per op
+      const int4 q0 = __ldg(src + 0);  // kind, flags, dim, n_par
       const int4 q4 = __ldg(src + 4), q5 = __ldg(src + 5), q6 = __ldg(src + 6);
       if (q0.y & VBN_F_LGPLAIN) {
         VbnOp lop;

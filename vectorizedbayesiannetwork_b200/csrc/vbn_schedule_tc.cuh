@@ -82,6 +82,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void lds_f32x4_as_x2(uint32_t addr, unsigned long long& a, unsigned long long& b) {
   asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -232,54 +240,87 @@ struct TcMlp {
   static constexpr bool kEnabled = true;
   static constexpr bool kLoops = false;      // Gibbs programs never carry tensor-core images
   static constexpr bool kInlineRng = true;   // inlined generator with constant-bank round keys
+  // Per-thread state is kept to a handful of OPAQUE values (see "values, not recipes" in the kernel): everything
+  // else is an immediate offset from them, and the weight-ring producer's counters live in shared memory (one
+  // lane touches them once per MLP) instead of a register in every thread.
   uint32_t t_d;        // TMEM address of tile 0's accumulator for this thread's warp (lane base folded in); tile j
                        // adds j * kColsPerTile, A_hi / A_lo add kColAhi / kColAlo
-  uint32_t m_d;        // same columns, lane 0: operand of the MMA
-  uint32_t m_ones;     // 8 columns shared by all warpgroups holding (1, 0, ..., 0): A operand of the bias step
-  uint32_t wbuf;       // shared-space address of weight buffer 0
-  uint32_t full_bar, empty_bar, mma_bar;  // full/empty: arrays of nbuf; mma_bar: this warpgroup's (RPT of them)
-  uint32_t w_iter;     // tensor-core MLPs consumed so far (ring position)
-  uint32_t w_buf;      // w_iter % nbuf, and (w_iter / nbuf) & 1 in bit 8: kept as running state
+  uint32_t tm;         // TMEM base of the CTA's allocation
+  uint32_t ctl;        // shared-space address of the control block: barriers at fixed offsets, weight ring behind it
+  uint32_t role;       // wg | issuer << 8 | producer << 9 | (lane == 0) << 10 | (a ring slot is still held) << 11
+  uint32_t seg_org;    // descriptor tail of the ring slot held: shared-space address of op i = seg_org + 128 i ...
+  uint32_t seg;        // ... for seg_first <= i < seg_first + seg_cnt; seg = seg_first | seg_cnt << 16
+  uint32_t w_buf;      // ring slot of the next MLP (w_iter % nbuf), and (w_iter / nbuf) & 1 in bit 8: running state
   uint32_t mma_phase;  // parity of the next completion of the mma barriers (all tiles of a thread move together)
-  int nbuf;
-  int wg, lane;
-  bool issuer;         // this warp issues its warpgroup's MMAs: warp (wg & 3) of the warpgroup, so that the
-                       // issuing warps of a CTA sit on four different SM sub-partitions (warp id mod 4)
-  // weight-ring producer (one warp of the CTA)
-  bool producer;
-  uint32_t p_iter;     // weight images issued so far
-  uint32_t p_buf;      // p_iter % nbuf | (((p_iter / nbuf) & 1) ^ 1) << 8   (running, like w_buf)
-  uint32_t p_idx;      // p_iter % n_tc
-  uint32_t p_total;    // images this CTA will consume in total (n_iter * n_tc)
-  const int2* tc_list; // per tensor-core op: {float offset of its image in params, bytes}
-  const float* params;
-  uint32_t n_tc;
+  uint32_t nbuf;
+
+  static constexpr uint32_t kFull = 16, kEmpty = kFull + 8 * kMaxBufs, kMma = kEmpty + 8 * kMaxBufs;
+  static constexpr uint32_t kProd = kMma + 8 * kMaxTiles;  // producer words: p_iter, p_buf, p_idx, p_total, w_iter
+  static_assert(kProd + 20 <= kCtrlBytes, "control block");
 
   __device__ __forceinline__ uint32_t td(int j) const { return t_d + static_cast<uint32_t>(j * kColsPerTile); }
-  __device__ __forceinline__ uint32_t md(int j) const { return m_d + static_cast<uint32_t>(j * kColsPerTile); }
+  __device__ __forceinline__ uint32_t wg() const { return role & 0xFFu; }
+  __device__ __forceinline__ uint32_t md(int j) const { return tm + (wg() * RPT + j) * kColsPerTile; }
+  __device__ __forceinline__ uint32_t m_ones() const { return tm + NWG * RPT * kColsPerTile; }
+  __device__ __forceinline__ uint32_t wbuf(uint32_t buf) const { return ctl + kCtrlBytes + buf * kWbufBytes; }
+  __device__ __forceinline__ uint32_t full_bar(uint32_t buf) const { return ctl + kFull + 8 * buf; }
+  __device__ __forceinline__ uint32_t empty_bar(uint32_t buf) const { return ctl + kEmpty + 8 * buf; }
+  __device__ __forceinline__ uint32_t mma_bar(int j) const { return ctl + kMma + 8 * (wg() * RPT + j); }
+  // Descriptor of op i: from the tail of the weight image this warp still holds (cpds / plan.py: copies of the ops
+  // that follow an MLP op ride behind its weights), else from global memory.
+  __device__ __forceinline__ bool op_in_ring(int i) const {
+    return static_cast<uint32_t>(i) - (seg & 0xFFFFu) < (seg >> 16);
+  }
+  // generic-space address of op i's copy in the ring slot (one load path for both sources: no register shuffling
+  // at the join)
+  __device__ __forceinline__ const int4* ring_ptr(int i) const {
+    return reinterpret_cast<const int4*>(__cvta_shared_to_generic(seg_org + 128u * static_cast<uint32_t>(i)));
+  }
+  // gives the ring slot of the previous MLP back (its tail has been consumed) -- called when the next MLP starts and
+  // at the end of the walk
+  __device__ __forceinline__ void release_held() {
+    if (role & 0x800u) {
+      const uint32_t buf = w_buf & 0xFFu;
+      const uint32_t ph = w_buf >> 8;
+      __syncwarp();
+      if (role & 0x400u) mbar_arrive(empty_bar(buf));
+      w_buf = buf + 1u == nbuf ? ((ph ^ 1u) << 8) : w_buf + 1u;
+      role &= ~0x800u;
+      seg = 0u;
+    }
+  }
+  __device__ __forceinline__ bool issuer() const { return (role & 0x100u) != 0; }
+  __device__ __forceinline__ bool producer() const { return (role & 0x200u) != 0; }
 
   // Issues every image whose ring slot is free, up to nbuf ahead of this warp; blocks only for the
   // image of the op this warp is about to run (its slot frees once the slowest warp has left op
-  // w_iter - nbuf, which never depends on this warp).  One elected lane.
-  __device__ __forceinline__ void produce() {
-    while (p_iter < p_total && p_iter < w_iter + static_cast<uint32_t>(nbuf)) {
+  // w_iter - nbuf, which never depends on this warp).  One elected lane; its counters live in shared memory.
+  __device__ __forceinline__ void produce(const ScheduleArgs& a) {
+    const uint32_t st = ctl + kProd;
+    uint32_t p_iter = lds_u32(st), p_buf = lds_u32(st + 4), p_idx = lds_u32(st + 8);
+    const uint32_t p_total = lds_u32(st + 12), w_iter = lds_u32(st + 16);
+    while (p_iter < p_total && p_iter < w_iter + nbuf) {
       const uint32_t buf = p_buf & 0xFFu;
       const uint32_t ph = p_buf >> 8;
       if (p_iter > w_iter) {
-        if (!mbar_test(empty_bar + 8 * buf, ph)) break;
+        if (!mbar_test(empty_bar(buf), ph)) break;
       } else {
-        mbar_wait(empty_bar + 8 * buf, ph);
+        mbar_wait(empty_bar(buf), ph);
       }
-      const int2 e = __ldg(tc_list + p_idx);
-      mbar_expect_tx(full_bar + 8 * buf, static_cast<uint32_t>(e.y));
-      bulk_g2s(wbuf + buf * kWbufBytes, params + e.x, static_cast<uint32_t>(e.y), full_bar + 8 * buf);
+      const int2 e = __ldg(a.tc_list + p_idx);
+      mbar_expect_tx(full_bar(buf), static_cast<uint32_t>(e.y));
+      bulk_g2s(wbuf(buf), a.params + e.x, static_cast<uint32_t>(e.y), full_bar(buf));
       ++p_iter;
-      p_idx = p_idx + 1u == n_tc ? 0u : p_idx + 1u;
-      p_buf = buf + 1u == static_cast<uint32_t>(nbuf) ? ((ph ^ 1u) << 8) : p_buf + 1u;
+      p_idx = p_idx + 1u == static_cast<uint32_t>(a.n_tc) ? 0u : p_idx + 1u;
+      p_buf = buf + 1u == nbuf ? ((ph ^ 1u) << 8) : p_buf + 1u;
     }
+    sts_u32(st, p_iter);
+    sts_u32(st + 4, p_buf);
+    sts_u32(st + 8, p_idx);
+    sts_u32(st + 16, w_iter + 1u);  // this warp is entering MLP number w_iter
   }
 
-  __device__ __forceinline__ void wg_sync() const { named_bar_sync(1 + wg, kWgThreads); }
+  __device__ __forceinline__ void wg_sync() const { named_bar_sync(1 + wg(), kWgThreads); }
 
   // All 128 threads of the warpgroup: make this thread's TMEM stores visible to the tensor core, meet, and let
   // the issuing warp queue one layer for tiles [j0, j1) -- each tile commits to its own mbarrier.
@@ -287,18 +328,18 @@ struct TcMlp {
     tmem_wait_st();
     tc_fence_before();
     wg_sync();
-    if (issuer) {  // warp-uniform: operands stay on the uniform datapath
+    if (issuer()) {  // warp-uniform: operands stay on the uniform datapath
       tc_fence_after();
       if (elect_one()) {
         for (int j = j0; j < j1; ++j) {
           const uint32_t d = md(j);
           switch (k) {
-            case 8: issue_layer<1>(d, d + kColAhi, d + kColAlo, m_ones, b_hi, b_lo, n); break;
-            case 16: issue_layer<2>(d, d + kColAhi, d + kColAlo, m_ones, b_hi, b_lo, n); break;
-            case 24: issue_layer<3>(d, d + kColAhi, d + kColAlo, m_ones, b_hi, b_lo, n); break;
-            default: issue_layer<4>(d, d + kColAhi, d + kColAlo, m_ones, b_hi, b_lo, n); break;
+            case 8: issue_layer<1>(d, d + kColAhi, d + kColAlo, m_ones(), b_hi, b_lo, n); break;
+            case 16: issue_layer<2>(d, d + kColAhi, d + kColAlo, m_ones(), b_hi, b_lo, n); break;
+            case 24: issue_layer<3>(d, d + kColAhi, d + kColAlo, m_ones(), b_hi, b_lo, n); break;
+            default: issue_layer<4>(d, d + kColAhi, d + kColAlo, m_ones(), b_hi, b_lo, n); break;
           }
-          mma_commit(mma_bar + 8 * j);
+          mma_commit(mma_bar(j));
         }
       }
       __syncwarp();
@@ -306,71 +347,75 @@ struct TcMlp {
   }
   // the layer queued last for tile j has completed: its accumulator may be read, its A operand overwritten
   __device__ __forceinline__ void await(int j) const {
-    mbar_wait(mma_bar + 8 * j, mma_phase);
+    mbar_wait(mma_bar(j), mma_phase);
     tc_fence_after();
   }
 
-  // 32 activations (already through the activation function) -> 3xTF32 split -> A_hi / A_lo of tile j
-  __device__ __forceinline__ void split_store(int j, int half, const float (&h)[16], bool relu_pending) {
+  // 16 activations -> 3xTF32 split -> columns [16 half, 16 half + 16) of A_hi / A_lo of tile j.
+  // RELU: the values are pre-activations and the activation is ReLU (applied here).
+  template <bool RELU>
+  __device__ __forceinline__ void split_store(int j, int half, const float (&h)[16]) {
     uint32_t hi[16], lo[16];
-    if (relu_pending) {
 #pragma unroll
-      for (int q = 0; q < 16; q += 2)
+    for (int q = 0; q < 16; q += 2) {
+      if constexpr (RELU) {
         split_tf32_x2(fmaxf(h[q], 0.0f), fmaxf(h[q + 1], 0.0f), hi[q], hi[q + 1], lo[q], lo[q + 1]);
-    } else {
-#pragma unroll
-      for (int q = 0; q < 16; q += 2) split_tf32_x2(h[q], h[q + 1], hi[q], hi[q + 1], lo[q], lo[q + 1]);
+      } else {
+        split_tf32_x2(h[q], h[q + 1], hi[q], hi[q + 1], lo[q], lo[q + 1]);
+      }
     }
     tmem_st16(td(j) + kColAhi + 16 * half, hi);
     tmem_st16(td(j) + kColAlo + 16 * half, lo);
   }
-  __device__ __forceinline__ void act_split_store(int j, int half, int act, const uint32_t (&v)[16]) {
-    float h[16];
-    if (act == VBN_ACT_RELU) {
-#pragma unroll
-      for (int q = 0; q < 16; ++q) h[q] = __uint_as_float(v[q]);
-      split_store(j, half, h, true);
+  // ACT >= 0: compile-time activation (the hot path is ReLU); ACT < 0: `act` decides at run time
+  template <int ACT>
+  __device__ __forceinline__ void act_split_store(int j, int half, int act, float (&h)[16]) {
+    if (ACT == VBN_ACT_RELU || (ACT < 0 && act == VBN_ACT_RELU)) {
+      split_store<true>(j, half, h);
     } else {
 #pragma unroll
-      for (int q = 0; q < 16; ++q) h[q] = activate_slow(__uint_as_float(v[q]), act);
-      split_store(j, half, h, false);
+      for (int q = 0; q < 16; ++q) h[q] = activate_slow(h[q], act);
+      split_store<false>(j, half, h);
     }
   }
   // D of tile j (32 fp32 columns, bias included) -> activation -> split -> A.  Both halves of the accumulator
   // row are requested before the first is processed, so the second TMEM read is in flight meanwhile.
+  template <int ACT>
   __device__ __forceinline__ void hidden_epilogue(int j, int act) {
     uint32_t v0[16], v1[16];
     tmem_ld16(td(j), v0);
     tmem_ld16(td(j) + 16, v1);
     tmem_wait_ld();
-    act_split_store(j, 0, act, v0);
-    act_split_store(j, 1, act, v1);
+    float h[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) h[q] = __uint_as_float(v0[q]);
+    act_split_store<ACT>(j, 0, act, h);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) h[q] = __uint_as_float(v1[q]);
+    act_split_store<ACT>(j, 1, act, h);
   }
 
   // First layer on the FP32 pipe (<= 4 parent dims: 16 Dp packed FMAs per row).  `l1` = shared-space address of
   // the plain block at the head of the weight image: W1^T[4][32] (rows >= Dp zero), b1[32].  The MMA route
   // (K padded 2 -> 8: 5 MMAs, an input split, two TMEM stores, a commit / wait round trip and a 32-column TMEM
-  // read) only pays from Dp > 4.
-  template <class C>
+  // read) only pays from Dp > 4.  DP: compile-time parent count, so the body is straight-line code.
+  template <int DP, int ACT, class C>
   __device__ __forceinline__ void hidden1_fma(C& c, const VbnOp& op, const float* norm, int j, uint32_t l1) {
-    const int dp = op.n_par;
     unsigned long long h[16];  // 32 pre-activations as f32x2 pairs
 #pragma unroll
     for (int q = 0; q < 8; ++q) lds_f32x4_as_x2(l1 + 4 * (4 * kHidden + 4 * q), h[2 * q], h[2 * q + 1]);
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      if (p < dp) {
-        float z = c.slot((op.aux[1 + (p >> 1)] >> (16 * (p & 1))) & 0xFFFF, j);
-        if (norm) z = __fdiv_rn(z - __ldg(norm + p), __ldg(norm + dp + p));
-        unsigned long long zz;
-        asm("mov.b64 %0, {%1, %1};" : "=l"(zz) : "f"(z));
+    for (int p = 0; p < DP; ++p) {
+      float z = c.slot((op.aux[1 + (p >> 1)] >> (16 * (p & 1))) & 0xFFFF, j);
+      if (norm) z = __fdiv_rn(z - __ldg(norm + p), __ldg(norm + DP + p));
+      unsigned long long zz;
+      asm("mov.b64 %0, {%1, %1};" : "=l"(zz) : "f"(z));
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          unsigned long long w0, w1;
-          lds_f32x4_as_x2(l1 + 4 * (p * kHidden + 4 * q), w0, w1);
-          asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(h[2 * q]) : "l"(w0), "l"(zz));
-          asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(h[2 * q + 1]) : "l"(w1), "l"(zz));
-        }
+      for (int q = 0; q < 8; ++q) {
+        unsigned long long w0, w1;
+        lds_f32x4_as_x2(l1 + 4 * (p * kHidden + 4 * q), w0, w1);
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(h[2 * q]) : "l"(w0), "l"(zz));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(h[2 * q + 1]) : "l"(w1), "l"(zz));
       }
     }
 #pragma unroll
@@ -379,13 +424,16 @@ struct TcMlp {
 #pragma unroll
       for (int q = 0; q < 8; ++q)
         asm("mov.b64 {%0, %1}, %2;" : "=f"(f[2 * q]), "=f"(f[2 * q + 1]) : "l"(h[8 * half + q]));
-      if (op.act == VBN_ACT_RELU) {
-        split_store(j, half, f, true);
-      } else {
-#pragma unroll
-        for (int q = 0; q < 16; ++q) f[q] = activate_slow(f[q], op.act);
-        split_store(j, half, f, false);
-      }
+      act_split_store<ACT>(j, half, op.act, f);
+    }
+  }
+  template <int ACT, class C>
+  __device__ __forceinline__ void hidden1_fma_any(C& c, const VbnOp& op, const float* norm, int j, uint32_t l1) {
+    switch (op.n_par) {
+      case 1: hidden1_fma<1, ACT>(c, op, norm, j, l1); break;
+      case 2: hidden1_fma<2, ACT>(c, op, norm, j, l1); break;
+      case 3: hidden1_fma<3, ACT>(c, op, norm, j, l1); break;
+      default: hidden1_fma<4, ACT>(c, op, norm, j, l1); break;
     }
   }
 
@@ -395,6 +443,24 @@ struct TcMlp {
   __device__ __forceinline__ void inputs_to_a(C& c, const VbnOp& op, const float* norm, const int32_t* par, int j,
                                               int k1) {
     const int dp = op.n_par;
+    if (op.flags & VBN_F_PAR4) {  // <= 4 parent dims, slots packed in aux[1..2]: K1 == 8 (static field indices only:
+                                  // a dynamically indexed descriptor would be demoted to local memory)
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float z = 0.0f;
+        if (q < dp) {
+          z = c.slot((op.aux[1 + (q >> 1)] >> (16 * (q & 1))) & 0xFFFF, j);
+          if (norm) z = __fdiv_rn(z - __ldg(norm + q), __ldg(norm + dp + q));
+        }
+        split_tf32(z, hi[q], lo[q]);
+      }
+#pragma unroll
+      for (int q = 4; q < 8; ++q) hi[q] = lo[q] = 0u;
+      tmem_st8(td(j) + kColAhi, hi);
+      tmem_st8(td(j) + kColAlo, lo);
+      return;
+    }
     for (int k0 = 0; k0 < k1; k0 += 8) {
       uint32_t hi[8], lo[8];
 #pragma unroll
@@ -412,68 +478,88 @@ struct TcMlp {
     }
   }
 
-  // Everything of the op's MLP up to and including the issue of its last layer, for all RPT tiles.  The caller
-  // then does independent work (generator refills), await(j) per tile -- D of tile j holds the N3 outputs, bias
-  // included -- and layers_end().
-  template <class C>
-  __device__ __forceinline__ void layers_begin(C& c, const VbnOp& op, const float* norm, const int32_t* par) {
-    const int k1 = op.tc[2], n3 = op.tc[3];
-    if (producer) {  // warp-uniform
-      if (elect_one()) produce();
+  // The MLP of one op for all RPT tiles, in two stages so that the caller can put independent work into the
+  // shadow of the MMAs:
+  //   stage_a : first layer (FP32 pipe, or MMA round trip), hidden layer queued              -> shadow 1
+  //   stage_b : per tile: wait, split the hidden layer's accumulator, queue the last layer   -> shadow 2
+  //   await(j) per tile -- D of tile j then holds the N3 outputs, bias included -- and layers_end().
+  // FAST (the drawn-only MDN hot path): first layer on the FP32 pipe, ReLU, all decided at compile time.
+  template <bool FAST, class C>
+  __device__ __forceinline__ void stage_a(C& c, const VbnOp& op, const float* norm, const int32_t* par) {
+    const int k1 = FAST ? 0 : op.tc[2];
+    release_held();
+    if (producer()) {  // warp-uniform
+      if (elect_one()) produce(c.a);
       __syncwarp();
     }
     const uint32_t buf = w_buf & 0xFFu;
     const uint32_t ph = w_buf >> 8;
-    const uint32_t img = wbuf + buf * kWbufBytes;
+    const uint32_t img = wbuf(buf);
     // image: k1 == 0: L1 plain block (640 B) | W2hi W2lo | W3hi W3lo ; else W1hi W1lo | W2hi W2lo | W3hi W3lo
     const uint32_t w1_bytes = k1 == 0 ? kL1PlainBytes / 2 : kHidden * (k1 + kBiasK) * 4;  // per half
     const uint32_t w2hi = img + 2 * w1_bytes;
     const uint32_t w2lo = w2hi + kHidden * (kHidden + kBiasK) * 4;
-    const uint32_t w3hi = w2lo + kHidden * (kHidden + kBiasK) * 4;
-    const uint32_t w3lo = w3hi + n3 * (kHidden + kBiasK) * 4;
-
     if (k1 == 0) {
-      mbar_wait(full_bar + 8 * buf, ph);  // this layer reads its weights from the image itself
+      mbar_wait(full_bar(buf), ph);  // this layer reads its weights from the image itself
 #pragma unroll
-      for (int j = 0; j < RPT; ++j) hidden1_fma(c, op, norm, j, img);
+      for (int j = 0; j < RPT; ++j) {
+        if constexpr (FAST) {
+          hidden1_fma_any<VBN_ACT_RELU>(c, op, norm, j, img);
+        } else {
+          hidden1_fma_any<-1>(c, op, norm, j, img);
+        }
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < RPT; ++j) inputs_to_a(c, op, norm, par, j, k1);
-      mbar_wait(full_bar + 8 * buf, ph);
+      mbar_wait(full_bar(buf), ph);
       publish_and_issue(0, RPT, img, img + w1_bytes, k1, kHidden);
 #pragma unroll
       for (int j = 0; j < RPT; ++j) {
         await(j);
-        hidden_epilogue(j, op.act);
+        hidden_epilogue<-1>(j, op.act);
       }
       mma_phase ^= 1u;
     }
     publish_and_issue(0, RPT, w2hi, w2lo, kHidden, kHidden);
+  }
+  template <bool FAST, class C>
+  __device__ __forceinline__ void stage_b(C& c, const VbnOp& op) {
+    const int k1 = FAST ? 0 : op.tc[2], n3 = op.tc[3];
+    const uint32_t w1_bytes = k1 == 0 ? kL1PlainBytes / 2 : kHidden * (k1 + kBiasK) * 4;
+    const uint32_t w3hi = wbuf(w_buf & 0xFFu) + 2 * w1_bytes + 2 * kHidden * (kHidden + kBiasK) * 4;
+    const uint32_t w3lo = w3hi + n3 * (kHidden + kBiasK) * 4;
     // tile j's accumulator is split while the other tiles' MMAs run; its last layer is queued at once
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
       await(j);
-      hidden_epilogue(j, op.act);
+      if constexpr (FAST) {
+        hidden_epilogue<VBN_ACT_RELU>(j, VBN_ACT_RELU);
+      } else {
+        hidden_epilogue<-1>(j, op.act);
+      }
       publish_and_issue(j, j + 1, w3hi, w3lo, kHidden, n3);
     }
     mma_phase ^= 1u;
   }
-  __device__ __forceinline__ void layers_end() {
+  // `op_index` = position of the MLP op in the schedule, `n_tail` = descriptors behind its weights in the image.
+  // The ring slot stays held until the next MLP starts (release_held): the ops in between read their descriptors
+  // from it.
+  __device__ __forceinline__ void layers_end(const VbnOp& op, int op_index) {
     mma_phase ^= 1u;
-    // this warp is done with the weight buffer (every MMA it waited for has completed)
-    const uint32_t buf = w_buf & 0xFFu;
-    const uint32_t ph = w_buf >> 8;
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty_bar + 8 * buf);
-    ++w_iter;
-    w_buf = buf + 1u == static_cast<uint32_t>(nbuf) ? ((ph ^ 1u) << 8) : w_buf + 1u;
+    const int k1 = op.tc[2], n3 = op.tc[3];
+    const uint32_t n_tail = static_cast<uint32_t>(op.layer_dim[7]);
+    role |= 0x800u;
+    seg = static_cast<uint32_t>(op_index + 1) | (n_tail << 16);
+    seg_org = wbuf(w_buf & 0xFFu) + static_cast<uint32_t>(blob_bytes(k1, n3)) - 128u * static_cast<uint32_t>(op_index + 1);
   }
 
   // Generic consumer: outputs land in scratch rows 0..n_out-1 like the FFMA paths
   // (mlp_fast32 / mlp_generic), for op_gnn / op_mdn / op_snn to pick up.
   template <class C>
   __device__ __forceinline__ void mlp(C& c, const VbnOp& op, const float* norm, const int32_t* par) {
-    layers_begin(c, op, norm, par);
+    stage_a<false>(c, op, norm, par);
+    stage_b<false>(c, op);
     const int n3 = op.tc[3], n_out = op.n_out;
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
@@ -487,7 +573,7 @@ struct TcMlp {
           if (o0 + q < n_out) c.scr(o0 + q, j) = __uint_as_float(v[q]);
       }
     }
-    layers_end();
+    layers_end(op, static_cast<int>(c.gop - c.a.ops));
   }
 
   // VBN_F_MDNPLAIN: an MDN node (D = 1, K <= 5 components, <= 4 parent dims) that is only drawn
@@ -531,21 +617,25 @@ struct TcMlp {
     c.slot(op.out_slot, j) = fmaf(eps, sc, loc);
   }
 
-  template <class C>
-  __device__ __forceinline__ void mdn_plain(C& c, const VbnOp& op) {
-    layers_begin(c, op, nullptr, nullptr);
-    // generator refills run in the shadow of the last layer's MMAs
-    const int uq = op.u_off >> 2;
-    if (uq != c.rows.cur_uq) {
-      c.rows.cur_uq = uq;
+  template <bool FAST, class C>
+  __device__ __forceinline__ void mdn_plain_body(C& c, const VbnOp& op) {
+    stage_a<FAST>(c, op, nullptr, nullptr);
+    {  // shadow of the hidden layer's MMAs: refill the uniform cache
+      const int uq = op.u_off >> 2;
+      if (uq != c.rows.cur_uq) {
+        c.rows.cur_uq = uq;
 #pragma unroll
-      for (int j = 0; j < RPT; ++j) c.rows.ucache[j] = c.uniforms(j, uq, 1u, false);
+        for (int j = 0; j < RPT; ++j) c.rows.ucache[j] = c.uniforms(j, uq, 1u, false);
+      }
     }
-    const int nq = op.n_off >> 2;
-    if (nq != c.rows.cur_nq) {
-      c.rows.cur_nq = nq;
+    stage_b<FAST>(c, op);
+    {  // shadow of the last layer's MMAs: refill the normal cache
+      const int nq = op.n_off >> 2;
+      if (nq != c.rows.cur_nq) {
+        c.rows.cur_nq = nq;
 #pragma unroll
-      for (int j = 0; j < RPT; ++j) c.rows.ncache[j] = c.normals(j, nq, 0u, false);
+        for (int j = 0; j < RPT; ++j) c.rows.ncache[j] = c.normals(j, nq, 0u, false);
+      }
     }
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
@@ -553,32 +643,43 @@ struct TcMlp {
       uint32_t v[16];
       tmem_ld16(td(j), v);
       tmem_wait_ld();
-      switch (op.k) {
-        case 2: mdn_tail<2>(c, op, v, j); break;
-        case 3: mdn_tail<3>(c, op, v, j); break;
-        case 4: mdn_tail<4>(c, op, v, j); break;
-        default: mdn_tail<5>(c, op, v, j); break;
+      if constexpr (FAST) {
+        mdn_tail<3>(c, op, v, j);
+      } else {
+        switch (op.k) {
+          case 2: mdn_tail<2>(c, op, v, j); break;
+          case 3: mdn_tail<3>(c, op, v, j); break;
+          case 4: mdn_tail<4>(c, op, v, j); break;
+          default: mdn_tail<5>(c, op, v, j); break;
+        }
       }
     }
-    layers_end();
+    layers_end(op, static_cast<int>(c.gop - c.a.ops));
+  }
+  template <class C>
+  __device__ __forceinline__ void mdn_plain(C& c, const VbnOp& op) {
+    // the reference's defaults (mdn.py: n_components = 3 is what BASELINE cfg5 uses, ReLU, first layer on the FP32
+    // pipe) get a body with every one of those choices made at compile time
+    if (op.k == 3 && op.act == VBN_ACT_RELU && op.tc[2] == 0) {
+      mdn_plain_body<true>(c, op);
+    } else {
+      mdn_plain_body<false>(c, op);
+    }
   }
 };
 
 // The kernel.  grid <= #SMs (one CTA per SM), NWG * 128 threads, NWG * RPT * 128 rows per pass.
-// dynamic smem: [ctrl 128 B][nbuf weight buffers][slots + scratch: (n_slots+n_scratch) x ROWS floats]
+// dynamic smem: [ctrl][nbuf weight buffers][slots + scratch: (n_slots+n_scratch) x ROWS floats]
 template <int NWG, int RPT>
 __global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const ScheduleArgs a, const int nbuf) {
   constexpr int kThreads = NWG * kWgThreads;
   constexpr int kTiles = NWG * RPT;
+  using Tc = TcMlp<NWG, RPT>;
   static_assert(kTiles <= kMaxTiles && kTiles * kColsPerTile + kBiasK <= kTmemCols, "TMEM budget");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform for the compiler
   const uint32_t smem_base = smem_u32(smem_raw);
-  const uint32_t full_bar = smem_base + 16;
-  const uint32_t empty_bar = full_bar + 8 * kMaxBufs;
-  const uint32_t mma_bar0 = empty_bar + 8 * kMaxBufs;
-  const uint32_t wbuf = smem_base + kCtrlBytes;
   // Word offset of this thread's column in the slot area.  Made opaque to the optimiser: at 128
   // registers per thread ptxas otherwise REMATERIALISES it (S2R tid, nbuf * kWbufBytes, ...) at the top
   // of every op of the walk instead of keeping -- or spilling -- one register.
@@ -586,23 +687,28 @@ __global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const S
   asm volatile("" : "+r"(slot_word));
   float* slots = reinterpret_cast<float*>(smem_raw) + slot_word;
 
+  const int64_t n_tiles = (a.n_rows + kWgThreads - 1) / kWgThreads;
+  const int64_t per_round = static_cast<int64_t>(gridDim.x) * kTiles;
+  const int64_t n_iter = (n_tiles + per_round - 1) / per_round;  // same for every warpgroup: the ring needs it
+
   if (tid == 0) {
     for (int i = 0; i < kMaxBufs; ++i) {
-      mbar_init(full_bar + 8 * i, 1);               // the producer lane's arrive.expect_tx
-      mbar_init(empty_bar + 8 * i, kThreads / 32);  // one arrive per warp
+      mbar_init(smem_base + Tc::kFull + 8 * i, 1);               // the producer lane's arrive.expect_tx
+      mbar_init(smem_base + Tc::kEmpty + 8 * i, kThreads / 32);  // one arrive per warp
     }
-    for (int g = 0; g < kTiles; ++g) mbar_init(mma_bar0 + 8 * g, 1);  // tcgen05.commit
+    for (int g = 0; g < kTiles; ++g) mbar_init(smem_base + Tc::kMma + 8 * g, 1);  // tcgen05.commit
     fence_mbar_init();
+    sts_u32(smem_base + Tc::kProd, 0u);                // p_iter
+    sts_u32(smem_base + Tc::kProd + 4, 1u << 8);       // p_buf
+    sts_u32(smem_base + Tc::kProd + 8, 0u);            // p_idx
+    sts_u32(smem_base + Tc::kProd + 12, static_cast<uint32_t>(n_iter) * static_cast<uint32_t>(a.n_tc));  // p_total
+    sts_u32(smem_base + Tc::kProd + 16, 0u);           // w_iter of the producer warp
   }
   if (warp == 0) tmem_alloc(smem_base, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem_raw), 0);
-
-  const int64_t n_tiles = (a.n_rows + kWgThreads - 1) / kWgThreads;
-  const int64_t per_round = static_cast<int64_t>(gridDim.x) * kTiles;
-  const int64_t n_iter = (n_tiles + per_round - 1) / per_round;  // same for every warpgroup: the ring needs it
 
   {  // constant A block of the bias step: columns [kTiles*96, kTiles*96 + 8) of every lane = (1, 0, ..., 0)
     const uint32_t ones[8] = {__float_as_uint(1.0f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
@@ -612,34 +718,21 @@ __global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const S
     __syncthreads();
     tc_fence_after();
   }
-  Ctx<RPT, kThreads, TcMlp<NWG, RPT>> c(a, slots, 0);  // the thread index is already folded into `slots`
+  Ctx<RPT, kThreads, Tc> c(a, slots, 0);  // the thread index is already folded into `slots`
   const int wg = warp >> 2;
-  const uint32_t col = tmem_base + static_cast<uint32_t>(wg * RPT * kColsPerTile);
-  const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-  c.tc.m_d = col + kColD;
-  c.tc.t_d = c.tc.m_d + lane_base;
-  c.tc.mma_bar = mma_bar0 + 8 * wg * RPT;
-  // same treatment for the per-thread TMEM / barrier addresses: values, not recipes in (tid, wg)
-  asm volatile("" : "+r"(c.tc.m_d), "+r"(c.tc.t_d), "+r"(c.tc.mma_bar));
-  c.tc.m_ones = tmem_base + kTiles * kColsPerTile;
-  c.tc.wbuf = wbuf;
-  c.tc.full_bar = full_bar;
-  c.tc.empty_bar = empty_bar;
-  c.tc.w_iter = 0;
+  c.tc.t_d = tmem_base + static_cast<uint32_t>(wg * RPT * kColsPerTile) + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  c.tc.tm = tmem_base;
+  c.tc.ctl = smem_base;
+  // the issuing warp of warpgroup g is its warp 0; the ring producer is a warp that issues no MMAs
+  c.tc.role = static_cast<uint32_t>(wg) | ((warp & 3) == 0 ? 0x100u : 0u) | (warp == 6 ? 0x200u : 0u) |
+              (lane == 0 ? 0x400u : 0u);
   c.tc.w_buf = 0;
+  c.tc.seg = 0;
+  c.tc.seg_org = 0;
   c.tc.mma_phase = 0;
-  c.tc.nbuf = nbuf;
-  c.tc.wg = wg;
-  c.tc.lane = lane;
-  c.tc.issuer = (warp & 3) == (wg & 3);
-  c.tc.producer = warp == (NWG > 1 ? 6 : 2);  // a warp that issues no MMAs (warpgroup 1's issuer is its warp 1 = CTA warp 5)
-  c.tc.p_iter = 0;
-  c.tc.p_buf = 1u << 8;
-  c.tc.p_idx = 0;
-  c.tc.p_total = static_cast<uint32_t>(n_iter) * static_cast<uint32_t>(a.n_tc);
-  c.tc.tc_list = a.tc_list;
-  c.tc.params = a.params;
-  c.tc.n_tc = static_cast<uint32_t>(a.n_tc);
+  c.tc.nbuf = static_cast<uint32_t>(nbuf);
+  // values, not recipes in (tid, wg, nbuf): one register each for the whole walk
+  asm volatile("" : "+r"(c.tc.t_d), "+r"(c.tc.tm), "+r"(c.tc.ctl), "+r"(c.tc.role), "+r"(c.tc.nbuf));
   for (int64_t it = 0; it < n_iter; ++it) {
     const int64_t base = (it * gridDim.x + blockIdx.x) * static_cast<int64_t>(kThreads * RPT);
 #pragma unroll
@@ -652,6 +745,7 @@ __global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const S
       c.rows.valid[j] = row_ok != 0;
     }
     run_ops<true>(c);
+    c.tc.release_held();  // the last MLP's ring slot (the ops behind it read their descriptors from its tail)
   }
   tc_fence_before();
   __syncthreads();

@@ -72,6 +72,11 @@ def _roots_enabled() -> bool:
     return os.environ.get("VBN_MDNROOT", "1") != "0"
 
 
+def _tails_enabled() -> bool:
+    """VBN_TC_TAILS=0: the tensor-core kernel fetches every op descriptor from global memory (A/B measurements)."""
+    return os.environ.get("VBN_TC_TAILS", "1") != "0"
+
+
 def _tabplain_enabled() -> bool:
     """VBN_TABPLAIN=0 keeps drawn table nodes on the generic lookup op (A/B + equivalence test)."""
     return os.environ.get("VBN_TABPLAIN", "1") != "0"
@@ -114,6 +119,7 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
     any_tc = False
     lg_fast_ops: List[int] = []
     tc_list: List[tuple] = []
+    tc_ops: List[tuple] = []  # (op index, weight image) of every op with a tensor-core image
     order = [n for n in topo if n in roles]
     # Roots whose draw is shared by all queries (LW / MCM / ancestral passes) go first -- still a topological
     # order -- so that consecutive shared draws are served from one generator block (csrc cached_uniform /
@@ -236,17 +242,10 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
                 blob_len += pk.params.size
             op["param_off"] = param_off[key]
             if use_tc and pk.tc_blob is not None:
-                tkey = ("tc", id(pk))
-                if tkey not in param_off:
-                    pad = (-blob_len) % 4  # the bulk copy needs a 16-byte aligned source
-                    if pad:
-                        blob.append(np.zeros(pad, np.float32))
-                        blob_len += pad
-                    param_off[tkey] = blob_len
-                    blob.append(pk.tc_blob.astype(np.float32, copy=False))
-                    blob_len += pk.tc_blob.size
-                op["tc"][:] = [1, param_off[tkey], pk.tc_k1, pk.tc_n3]
-                tc_list.append((param_off[tkey], 4 * int(pk.tc_blob.size)))
+                # the image itself (weights + the descriptors of the ops that follow, see below) is placed
+                # once the whole op table is known
+                op["tc"][:] = [1, 0, pk.tc_k1, pk.tc_n3]
+                tc_ops.append((i, pk.tc_blob.astype(np.float32, copy=False)))
                 any_tc = True
             op["n_layers"] = pk.n_layers
             op["act"] = pk.act
@@ -345,6 +344,32 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
             for j in range(s, s + dims[gone]):
                 occupied[j] = False
 
+    if tc_ops:
+        # Weight-ring images: [weights][tail], tail = verbatim copies of the descriptors of the ops that follow the
+        # MLP op, up to and including the next MLP op.  The image is in shared memory long before the warps get
+        # there, so the kernel reads those descriptors from the ring buffer instead of L2 (the 128-byte records do not
+        # stay in the small L1 left beside ~180 KB of shared memory).  layer_dim[7] of the MLP op = records in its tail.
+        tail_of = []
+        for k, (i, w) in enumerate(tc_ops):
+            nxt = tc_ops[k + 1][0] if k + 1 < len(tc_ops) else len(order) - 1
+            room = (L.TC_WBUF_BYTES - 4 * int(w.size)) // 128
+            n_tail = max(0, min(nxt - i, room)) if (_tails_enabled() and len(order) < 65536) else 0
+            tail_of.append(n_tail)
+            ops[i]["layer_dim"][7] = n_tail
+        offs = []
+        for (i, w), n_tail in zip(tc_ops, tail_of):  # offsets first: a tail may hold the NEXT MLP op's descriptor
+            pad = (-blob_len) % 4  # the bulk copy needs a 16-byte aligned source
+            blob_len += pad
+            offs.append((blob_len, pad))
+            ops[i]["tc"][1] = blob_len
+            blob_len += int(w.size) + 32 * n_tail
+        for (i, w), n_tail, (off, pad) in zip(tc_ops, tail_of, offs):
+            if pad:
+                blob.append(np.zeros(pad, np.float32))
+            blob.append(w)
+            if n_tail:
+                blob.append(np.frombuffer(ops[i + 1: i + 1 + n_tail].tobytes(), dtype=np.float32))
+            tc_list.append((off, 4 * int(w.size) + 128 * n_tail))
     params = np.concatenate(blob) if blob else np.zeros(4, np.float32)
     if params.size == 0:
         params = np.zeros(4, np.float32)
