@@ -181,6 +181,8 @@ typedef struct VbnProgramDesc {
   const int32_t* tc_list_dev; /* [n_tc][2] {image float offset, image bytes} of every op with
                          tc[0] != 0, in schedule order (the weight ring's fetch list)       */
   int32_t n_tc;
+  int32_t tc_image_bytes;  /* largest {image bytes} of tc_list (one slot of the kernel's weight ring), 0 = the
+                         format's maximum (30720)                                           */
   int32_t rows_per_thread; /* FP32-pipe kernel, schedules without MLP/KDE ops: 0 = default (4 rows
                          per thread, best for drawn linear-Gaussian chains), 2 = table-lookup
                          heavy schedules (fewer registers, more resident warps)             */

@@ -315,6 +315,18 @@ def test_cfg5_block_properties():
     wb, sb = model.infer_posterior({"target": "n500", "evidence": sub}, seed=4,
                                    shard=None)
     assert wa.shape == (96, 4096) and wb.shape == (32, 4096)
+    # ... provided the block is run with its global query offset (dist.Shard does exactly this): per-row Philox
+    # streams are keyed by the GLOBAL (query, sample) index
+    runner = model._inference._runner
+    subq = V.core.Query(target="n500", evidence={k: v.to(dev) for k, v in sub.items()}, do={})
+    plan = runner.plan_for(model, subq, "is")
+    logw = torch.empty(32, 4096, device=dev)
+    sc = torch.empty(32, 4096, 1, device=dev)
+    fixed = runner.fixed_table(plan, subq, 32, clamp_obs=False, shard=None)
+    plan.run(32, 4096, fixed=fixed, stores=[sc], logw=logw, seed=4, query_offset=32)
+    wc = torch.softmax(logw, dim=1)
+    assert torch.equal(sc, sa[32:64])
+    torch.testing.assert_close(wc, wa[32:64], rtol=2e-5, atol=1e-9)  # same log-weights; softmax by torch here
 
 
 @pytest.mark.gpu
@@ -631,6 +643,36 @@ def test_categorical_table_strict_support_and_conditional(backend):
     probs = torch.tensor(out["probs"])
     want = torch.softmax(O.ct_logits(spec["cpds"]["wet"], torch.tensor([[1.0, 0.0], [0.0, 1.0]])), dim=-1)
     torch.testing.assert_close(probs, want.reshape(probs.shape), rtol=1e-5, atol=1e-7)
+
+
+def test_table_only_model_raises_on_off_support_values(backend):
+    """A model made of categorical_table CPDs only (no softmax_nn anywhere): off-support evidence or parent values
+    must raise in every method and in the CPD handle, with the reference's wording (categorical_table.py:12-21).
+    The device flags them and carries on with class 0, so forgetting to read the flag would return a wrong posterior."""
+    import os
+
+    full = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "table.pt"),
+                      weights_only=False)["spec"]
+    keep = ["season", "rain"]  # season -> rain, both categorical_table
+    spec = {"nodes": keep, "topo": keep, "parents": {n: [p for p in full["parents"][n] if p in keep] for n in keep},
+            "cpds": {n: full["cpds"][n] for n in keep}}
+    assert {c["kind"] for c in spec["cpds"].values()} == {"categorical_table"}
+    model = V.VBN.from_spec(spec, device=backend.device)
+    good = {"target": "season", "evidence": {"rain": torch.tensor([[1.0], [0.0]])}}
+    bad_ev = {"target": "season", "evidence": {"rain": torch.tensor([[1.0], [0.5]])}}   # evidence value off support
+    bad_pa = {"target": "rain", "do": {"season": torch.tensor([[7.0]])}}                # parent value off support
+    for method in ("likelihood_weighting", "importance_sampling", "monte_carlo_marginalization"):
+        model.set_inference_method(method, n_samples=32)
+        model.infer_posterior(good)
+        for q in ((bad_ev, bad_pa) if method != "monte_carlo_marginalization" else (bad_pa,)):
+            with pytest.raises(ValueError, match="outside support"):
+                model.infer_posterior(q)
+    h = model.get_cpd("rain")
+    h.log_prob(torch.tensor([[1.0]]), {"season": torch.tensor([[2.0]])})
+    with pytest.raises(ValueError, match="outside support"):
+        h.log_prob(torch.tensor([[0.5]]), {"season": torch.tensor([[2.0]])})
+    with pytest.raises(ValueError, match="outside support"):
+        h.log_prob(torch.tensor([[1.0]]), {"season": torch.tensor([[9.0]])})
 
 
 # ---- categorical_embedded_softmax (vbn/cpds/categorical_embedded_softmax.py; SURVEY 8f row 3) --------

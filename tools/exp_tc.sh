@@ -27,6 +27,6 @@ if [ "${TESTS:-1}" = "1" ]; then
 fi
 for v in ${VARIANTS:-"4x1:0 2x2:0"}; do
   shape=${v%%:*}; dbg=${v##*:}
-  run_bench ${shape}_d${dbg} VBN_TC_SHAPE=$shape VBN_TC_DBG=$dbg
+  run_bench ${shape}_d${dbg} VBN_TC_SHAPE=$shape VBN_TC_TUNE=$dbg
 done
 for v in ${PROFS:-"4x1"}; do prof $v VBN_TC_SHAPE=$v; done

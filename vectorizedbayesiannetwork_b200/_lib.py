@@ -43,7 +43,8 @@ class ProgramDesc(C.Structure):
         ("params_dev", C.c_void_p), ("n_params", C.c_int64),
         ("n_slots", C.c_int32), ("n_scratch", C.c_int32),
         ("heavy", C.c_int32), ("tc", C.c_int32),
-        ("tc_list_dev", C.c_void_p), ("n_tc", C.c_int32), ("rows_per_thread", C.c_int32),
+        ("tc_list_dev", C.c_void_p), ("n_tc", C.c_int32), ("tc_image_bytes", C.c_int32),
+        ("rows_per_thread", C.c_int32),
     ]
 
 

@@ -85,6 +85,7 @@ struct VbnPlan {
   int tc;          // 0, or warpgroups per CTA of vbn::tc::schedule_tc_kernel<NWG, RPT>
   int tc_rpt;      // 128-row tiles per warpgroup
   int tc_nbuf;     // weight-ring depth of the tensor-core kernel
+  int tc_slot_bytes;  // size of one ring slot
 };
 
 extern "C" {
@@ -130,9 +131,12 @@ int32_t vbn_plan_create(const VbnProgramDesc* desc, VbnPlan** out_plan) {
       return fail(VBN_E_INVALID, "no tensor-core kernel with %d warpgroups x %d tiles", nwg, rpt);
     }
     const int threads = nwg * vbn::tc::kWgThreads;
+    // ring slot = the program's largest image (weights + descriptor tail), 128-byte granular; deepest ring that fits
+    int slot = desc->tc_image_bytes > 0 ? (desc->tc_image_bytes + 127) & ~127 : vbn::tc::kWbufBytes;
+    if (slot > vbn::tc::kWbufBytes) return fail(VBN_E_INVALID, "tc_image_bytes %d exceeds %d", slot, vbn::tc::kWbufBytes);
+    p->tc_slot_bytes = slot;
     for (int nbuf = vbn::tc::kMaxBufs; nbuf >= 2 && !p->tc; --nbuf) {
-      const size_t bytes = vbn::tc::kCtrlBytes + static_cast<size_t>(nbuf) * vbn::tc::kWbufBytes +
-                           per_row * threads * rpt;
+      const size_t bytes = vbn::tc::kCtrlBytes + static_cast<size_t>(nbuf) * slot + per_row * threads * rpt;
       if (bytes > static_cast<size_t>(max_smem)) continue;
       // the attribute is per FUNCTION, not per plan: always raise it to the device maximum so that plans with
       // different footprints can coexist (a later, smaller plan must not lower the limit of an earlier one)
@@ -240,7 +244,10 @@ int32_t vbn_run_forward(const VbnPlan* plan, const VbnRunDesc* run, void* stream
     int nbuf = plan->tc_nbuf;
     a.tc_list = reinterpret_cast<const int2*>(plan->desc.tc_list_dev);
     a.n_tc = plan->desc.n_tc;
-    void* targs[] = {&a, &nbuf};
+    int slot_bytes = plan->tc_slot_bytes;
+    const char* tune_env = std::getenv("VBN_TC_TUNE");  // dev knob: bit 0 = issuing warps on different SM sub-partitions
+    int tune = tune_env ? std::atoi(tune_env) : 0;
+    void* targs[] = {&a, &nbuf, &slot_bytes, &tune};
     CUDA_TRY(cudaLaunchKernel(vbn::tc::tc_kernel_ptr(plan->tc, plan->tc_rpt), dim3(grid), dim3(threads), targs, plan->smem_bytes,
                               static_cast<cudaStream_t>(stream)));
     return VBN_OK;

@@ -102,7 +102,10 @@ static __device__ __noinline__ float4 philox_normal4(uint4 c, uint2 k) { return 
 static __device__ __noinline__ float4 philox_uniform4(uint4 c, uint2 k) { return uniform4(philox4x32_10(c, k)); }
 
 __device__ __forceinline__ float lane4(const float4& v, int lane) {
-  return lane == 0 ? v.x : (lane == 1 ? v.y : (lane == 2 ? v.z : v.w));
+  // two levels of selects on the two index bits (the chained comparison form compiled to branches)
+  const float lo = (lane & 1) ? v.y : v.x;
+  const float hi = (lane & 1) ? v.w : v.z;
+  return (lane & 2) ? hi : lo;
 }
 
 // ---------------------------------------------------------------------------------------

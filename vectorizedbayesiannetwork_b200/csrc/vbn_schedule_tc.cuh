@@ -253,6 +253,7 @@ struct TcMlp {
   uint32_t w_buf;      // ring slot of the next MLP (w_iter % nbuf), and (w_iter / nbuf) & 1 in bit 8: running state
   uint32_t mma_phase;  // parity of the next completion of the mma barriers (all tiles of a thread move together)
   uint32_t nbuf;
+  uint32_t slot_bytes; // size of one ring slot
 
   static constexpr uint32_t kFull = 16, kEmpty = kFull + 8 * kMaxBufs, kMma = kEmpty + 8 * kMaxBufs;
   static constexpr uint32_t kProd = kMma + 8 * kMaxTiles;  // producer words: p_iter, p_buf, p_idx, p_total, w_iter
@@ -262,7 +263,7 @@ struct TcMlp {
   __device__ __forceinline__ uint32_t wg() const { return role & 0xFFu; }
   __device__ __forceinline__ uint32_t md(int j) const { return tm + (wg() * RPT + j) * kColsPerTile; }
   __device__ __forceinline__ uint32_t m_ones() const { return tm + NWG * RPT * kColsPerTile; }
-  __device__ __forceinline__ uint32_t wbuf(uint32_t buf) const { return ctl + kCtrlBytes + buf * kWbufBytes; }
+  __device__ __forceinline__ uint32_t wbuf(uint32_t buf) const { return ctl + kCtrlBytes + buf * slot_bytes; }
   __device__ __forceinline__ uint32_t full_bar(uint32_t buf) const { return ctl + kFull + 8 * buf; }
   __device__ __forceinline__ uint32_t empty_bar(uint32_t buf) const { return ctl + kEmpty + 8 * buf; }
   __device__ __forceinline__ uint32_t mma_bar(int j) const { return ctl + kMma + 8 * (wg() * RPT + j); }
@@ -274,6 +275,8 @@ struct TcMlp {
   // generic-space address of op i's copy in the ring slot (one load path for both sources: no register shuffling
   // at the join)
   __device__ __forceinline__ const int4* ring_ptr(int i) const {
+    // (keeping the window's high word in a register of its own instead of the S2R this costs was measured slower:
+    // one more live value at 128 registers per thread means more spill traffic)
     return reinterpret_cast<const int4*>(__cvta_shared_to_generic(seg_org + 128u * static_cast<uint32_t>(i)));
   }
   // gives the ring slot of the previous MLP back (its tail has been consumed) -- called when the next MLP starts and
@@ -671,7 +674,7 @@ struct TcMlp {
 // The kernel.  grid <= #SMs (one CTA per SM), NWG * 128 threads, NWG * RPT * 128 rows per pass.
 // dynamic smem: [ctrl][nbuf weight buffers][slots + scratch: (n_slots+n_scratch) x ROWS floats]
 template <int NWG, int RPT>
-__global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const ScheduleArgs a, const int nbuf) {
+__global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const ScheduleArgs a, const int nbuf, const int slot_bytes, const int tune) {
   constexpr int kThreads = NWG * kWgThreads;
   constexpr int kTiles = NWG * RPT;
   using Tc = TcMlp<NWG, RPT>;
@@ -683,7 +686,7 @@ __global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const S
   // Word offset of this thread's column in the slot area.  Made opaque to the optimiser: at 128
   // registers per thread ptxas otherwise REMATERIALISES it (S2R tid, nbuf * kWbufBytes, ...) at the top
   // of every op of the walk instead of keeping -- or spilling -- one register.
-  int slot_word = (kCtrlBytes + nbuf * kWbufBytes) / 4 + tid;
+  int slot_word = (kCtrlBytes + nbuf * slot_bytes) / 4 + tid;
   asm volatile("" : "+r"(slot_word));
   float* slots = reinterpret_cast<float*>(smem_raw) + slot_word;
 
@@ -724,13 +727,15 @@ __global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const S
   c.tc.tm = tmem_base;
   c.tc.ctl = smem_base;
   // the issuing warp of warpgroup g is its warp 0; the ring producer is a warp that issues no MMAs
-  c.tc.role = static_cast<uint32_t>(wg) | ((warp & 3) == 0 ? 0x100u : 0u) | (warp == 6 ? 0x200u : 0u) |
+  c.tc.role = static_cast<uint32_t>(wg) | ((warp & 3) == ((tune & 1) ? (wg & 3) : 0) ? 0x100u : 0u) |
+              (warp == ((tune & 2) ? 3 : 6) ? 0x200u : 0u) |
               (lane == 0 ? 0x400u : 0u);
   c.tc.w_buf = 0;
   c.tc.seg = 0;
   c.tc.seg_org = 0;
   c.tc.mma_phase = 0;
   c.tc.nbuf = static_cast<uint32_t>(nbuf);
+  c.tc.slot_bytes = static_cast<uint32_t>(slot_bytes);  // a kernel parameter: stays a constant-bank operand
   // values, not recipes in (tid, wg, nbuf): one register each for the whole walk
   asm volatile("" : "+r"(c.tc.t_d), "+r"(c.tc.tm), "+r"(c.tc.ctl), "+r"(c.tc.role), "+r"(c.tc.nbuf));
   for (int64_t it = 0; it < n_iter; ++it) {

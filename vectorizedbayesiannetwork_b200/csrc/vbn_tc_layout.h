@@ -17,10 +17,11 @@ constexpr int kTmemCols = 512;
 constexpr int kColsPerTile = 96;
 constexpr int kColD = 0, kColAhi = 32, kColAlo = 64;
 constexpr int kHidden = 32;
-constexpr int kWbufBytes = 30720;  // largest weight image (K1 = 32, N3 = 32): 2 * 4 * 3 * 32 * 40 B
+constexpr int kWbufBytes = 30720;  // largest weight image (K1 = 32, N3 = 32): 2 * 4 * 3 * 32 * 40 B; the ring's slot size is
+                                   // the largest image of the PROGRAM (weights + descriptor tail), rounded up to 128 B
 constexpr int kBiasK = 8;          // every MMA layer carries its bias as one extra K = 8 step (column K of the image)
 constexpr int kL1PlainBytes = 640; // first layer on the FP32 pipe (Dp <= 4): W1^T[4][32], b1[32] fp32
-constexpr int kMaxBufs = 4;
+constexpr int kMaxBufs = 8;
 constexpr int kCtrlBytes = 256;    // tmem address, up to 13 mbarriers, the ring producer's counters
 
 // bytes of one weight image.  k1 > 0: W1 hi/lo [32][K1+8], W2 hi/lo [32][40], W3 hi/lo [N3][40] (bias = column K);

@@ -68,6 +68,7 @@ class DevicePlan:
                 heavy=1 if program.heavy else 0, tc=tc_shape() if program.tc else 0,
                 tc_list_dev=self.tc_list.data_ptr() if program.tc else None,
                 n_tc=int(program.tc_list.shape[0]) if program.tc else 0,
+                tc_image_bytes=int(program.tc_list[:, 1].max()) if program.tc else 0,
                 rows_per_thread=2 if any(int(k) == L.OP_TAB for k in program.ops["kind"]) else 0,
             )
             handle = C.c_void_p()
@@ -159,6 +160,26 @@ class DevicePlan:
                 events.append((e0, e1))
             L.count_launch(1)
         # `table` / `keep` are stream-ordered torch allocations: safe to drop after the launch
+
+
+def stream_draws(kind: str, n_values: int, n_queries: int, n_samples: int, *, seed: int, shared: bool = False,
+                 call_offset: int = 0, query_offset: int = 0, sample_offset: int = 0, device=None) -> torch.Tensor:
+    """Replay hook (vbn_stream_draws): the first ``n_values`` normals / uniforms / raw generator words of every row's
+    stream for a run with this (seed, call_offset, offsets), through the same generator code as the schedule
+    kernels.  kind: "normal" | "uniform" | "bits".  Returns [ceil4(n_values), Bn, S] (float32; int32 bit patterns
+    for "bits"), Bn = 1 for the shared streams (roots of LW / MCM / ancestral passes)."""
+    lib = L.load()
+    dev = require_cuda(device)
+    n_blocks = max(1, (int(n_values) + 3) // 4)
+    bn = 1 if shared else int(n_queries)
+    with torch.cuda.device(dev):
+        out = torch.empty(4 * n_blocks, bn, int(n_samples), device=dev, dtype=torch.float32)
+        L.check(lib.vbn_stream_draws(int(seed) & (2**64 - 1), int(call_offset),
+                                     {"normal": 0, "uniform": 1, "bits": 2}[kind], 1 if shared else 0, 0, n_blocks,
+                                     int(n_queries), int(n_samples), int(query_offset), int(sample_offset),
+                                     out.data_ptr(), _stream_ptr(dev)))
+        L.count_launch(1)
+    return out.view(torch.int32) if kind == "bits" else out
 
 
 # --------------------------------------------------------------------------------------------
@@ -459,8 +480,11 @@ def cpd_log_prob(cpd: BaseCPD, x, parents) -> torch.Tensor:
             inputs.append(x.contiguous())
         fixed = torch.cat(cols, dim=0).contiguous() if cols else None
         plan.run(b, s, fixed=fixed, inputs=inputs, logp=out, error_flag=flag)
-        if cpd.kind == "softmax_nn" and bool(cpd._is_discrete.any()) and int(flag.item()) != 0:
-            raise ValueError("Found values outside discrete class set.")  # softmax_nn.py:623-625
+        # only VBN_OP_SNN / VBN_OP_TAB ops ever raise the flag: softmax_nn class sets (softmax_nn.py:623-625) and the
+        # strict supports of the table kinds (categorical_table.py:12-21)
+        if bool(np.isin(plan.program.ops["kind"], (L.OP_SNN, L.OP_TAB)).any()) and int(flag.item()) != 0:
+            raise ValueError("Found values outside discrete class set." if cpd.kind == "softmax_nn"
+                             else "Found values outside support.")
     return out
 
 

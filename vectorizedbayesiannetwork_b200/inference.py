@@ -138,11 +138,21 @@ class _ScheduleRunner:
         return {"logw": logw, "logp": logp, "stores": stores, "plan": plan, "b": b, "s": s, "flag": flag}
 
 
+def _flag_message(cpds) -> str:
+    """The reference's wording for an off-support value: categorical_table / categorical_embedded_softmax raise
+    'Found values outside support.' (categorical_table.py:12-21), softmax_nn 'Found values outside discrete class
+    set.' (softmax_nn.py:623-625)."""
+    kinds = {c.kind for c in cpds}
+    if kinds & set(TABLE_KINDS) and "softmax_nn" not in kinds:
+        return "Found values outside support."
+    return "Found values outside discrete class set."
+
+
 def _raise_if_flagged(vbn, out) -> None:
-    cpds = model_cpds(vbn)
-    if any(c.kind == "softmax_nn" and bool(c._is_discrete.any()) for c in cpds.values()):
-        if out["flag"] is not None and int(out["flag"].item()) != 0:
-            raise ValueError("Found values outside discrete class set.")  # softmax_nn.py:623-625
+    """The device error flag exists exactly when the schedule holds an op that can raise it (VBN_OP_SNN / VBN_OP_TAB:
+    softmax_nn class sets, strict supports of the table kinds); a non-zero flag is the reference's ValueError."""
+    if out["flag"] is not None and int(out["flag"].item()) != 0:
+        raise ValueError(_flag_message(model_cpds(vbn).values()))
 
 
 def _weights(out, *, normalize=True, eps=1e-12, shard: Optional[Shard] = None):
@@ -385,7 +395,7 @@ class ResampledImportanceSampling:
                         self._last_resampled = True
             cpds = model_cpds(vbn)
             if any(c.kind in ("softmax_nn",) + TABLE_KINDS for c in cpds.values()) and int(flag_dev.item()) != 0:
-                raise ValueError("Found values outside discrete class set.")
+                raise ValueError(_flag_message(cpds.values()))
             stats = E.lse_stats(logw)
             w, _ = E.normalize_weights(logw, stats)
             t = query.target
@@ -737,5 +747,5 @@ class GibbsSampler:
                      error_flag=flag)
             cpds = model_cpds(vbn)
             if any(c.kind in ("softmax_nn",) + TABLE_KINDS for c in cpds.values()) and int(flag.item()) != 0:
-                raise ValueError("Found values outside discrete class set.")
+                raise ValueError(_flag_message(cpds.values()))
         return out.expand(b, n_samples, -1).contiguous()
