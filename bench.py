@@ -1,23 +1,31 @@
 #!/usr/bin/env python
 """Benchmark of the posterior-inference hot path (BASELINE.json metric: posterior samples/sec).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg5|cfg2|cfg3] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg5|cfg2|cfg3|cfg4] [--impl reference]
 
 A *step* is one ``infer_posterior`` call (importance sampling, with its likelihood-weighting
 fallback when ESS is low -- exactly the reference semantics) over one batch of synthetic queries.
-Default workload = BASELINE config 5 (1000-node random DAG, linear_gaussian + mdn CPDs,
-10 000 queries x 4096 samples sharded over 8 GPUs): every rank owns 1250 queries x 4096 samples,
-so the job at N GPUs is 1250*N queries ("weak" scaling; N=8 is the configuration as stated).
 
-One JSON line is printed by rank 0.  ``value`` = device-timed throughput with the evidence already
-resident in HBM; ``e2e`` = the same metric through the public API with HOST evidence buffers and
-the (weights, samples) result copied back to pinned host memory inside the timed region.
-``--impl reference`` times the CPU restatement of the reference (oracle/, pinned bit-for-bit to
-the reference in tests/test_oracle_pin.py) on this box's host cores.
+Default workload = BASELINE config 5 (1000-node random DAG, linear_gaussian + mdn CPDs, 10 000 queries x 4096
+samples).  At N = 1 the whole configuration runs on the one GPU; at N > 1 every rank owns 1250 queries x 4096 samples
+("weak" scaling over queries, no data-path collective; N = 8 is the configuration as stated).
+
+One JSON line is printed by rank 0.  ``value`` = device-timed throughput with the evidence already resident in HBM;
+``e2e`` = the same metric through the public API with HOST evidence buffers and the (weights, samples) result copied
+back to pinned host memory inside the timed region; ``e2e_summary`` = the same with the posterior summarised on the
+device (``summary=True``: weighted mean / std / ESS per query, nothing of size [B, S] crosses PCIe).
+At N = 1 the line also carries ``others``: short runs of cfg2 / cfg3 / cfg4 with their own roofline, e2e and clocks.
+Under torchrun (N > 1) it also carries ``strong_scaling``: BASELINE cfg2 (64 queries x 1M samples, samples sharded,
+the one path with a data-path collective) on 1 GPU and on N GPUs.
+
+``--impl reference`` times the UNMODIFIED reference package (``baseline/_ref``; oracle/reference_arm.py loads the same
+parameters into the reference's own CPD classes) through its public API on this box's host cores; if the package is
+absent it falls back to the oracle port (bit-identical arithmetic, tests/test_oracle_pin.py) and says so.
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -33,15 +41,15 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 WORKLOADS = {
-    # name: (description, per-rank queries, samples, method)
+    # name: (description, queries at N = 1, queries per rank at N > 1, samples, method)
     "cfg5": ("cfg5: 1000-node random DAG, even=linear_gaussian odd=mdn(K=3,[32,32]), importance_sampling, "
-             "evidence on last 5 nodes, target n500", 1250, 4096, "importance_sampling"),
+             "evidence on last 5 nodes, target n500", 10_000, 1250, 4096, "importance_sampling"),
     "cfg2": ("cfg2: 50-node linear_gaussian chain, importance_sampling, evidence x49, target x25",
-             64, 1_000_000, "importance_sampling"),
-    "cfg4": ("cfg4: kde CPD p->y with 200k stored points, CPDHandle.log_prob over 1M query rows", 1_000_000, 1,
-             "kde_log_prob"),
+             64, 64, 1_000_000, "importance_sampling"),
+    "cfg4": ("cfg4: kde CPD p->y with 200k stored points, CPDHandle.log_prob over 1M query rows",
+             1_000_000, 1_000_000, 1, "kde_log_prob"),
     "cfg3": ("cfg3: ALARM (37 nodes) softmax_nn discrete CPDs, likelihood_weighting, 4 evidence nodes, "
-             "target LVFAILURE", 4096, 16384, "likelihood_weighting"),
+             "target LVFAILURE", 4096, 4096, 16384, "likelihood_weighting"),
 }
 
 
@@ -119,6 +127,7 @@ class ClockSampler:
             self._thread.start()
         except Exception:
             self._nvml = None
+        return self
 
     def _loop(self):
         N = self._nvml
@@ -142,7 +151,12 @@ class ClockSampler:
                 pass
             self._stop.wait(0.05)
 
-    def stop(self) -> dict:
+    def mark(self):
+        """Keep only the samples taken from now on (start of a timed region)."""
+        self.sm.clear()
+        self.reasons.clear()
+
+    def read(self) -> dict:
         if self._nvml is None:
             try:
                 out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
@@ -151,14 +165,22 @@ class ClockSampler:
                 return {"sm_mhz": a, "sm_max_mhz": b, "reasons": [], "samples": 1, "source": "nvidia-smi after the run"}
             except Exception:
                 return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
-        self._stop.set()
-        self._thread.join(timeout=2)
         return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.sm_max,
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "NVML, 50 ms period"}
+
+    def stop(self):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+
+
+_PEAKS = {}
 
 
 def measure_fma_peak(dev) -> dict:
     """Measured FP32 FMA peak (TFLOP/s) of this GPU with our probe kernel: scalar FFMA and FFMA2."""
+    if "fma" in _PEAKS:
+        return _PEAKS["fma"]
     from vectorizedbayesiannetwork_b200 import _lib as L
 
     lib = L.load()
@@ -179,11 +201,14 @@ def measure_fma_peak(dev) -> dict:
                 ms = e0.elapsed_time(e1)
                 best = max(best, 2.0 * 16 * iters * 256 * blocks / (ms * 1e-3) / 1e12)
             out[name] = round(best, 2)
+    _PEAKS["fma"] = out
     return out
 
 
 def measure_tf32_peak(dev) -> float:
     """Measured dense tcgen05 kind::tf32 peak (TFLOP/s) with our probe kernel (one CTA per SM)."""
+    if "tf32" in _PEAKS:
+        return _PEAKS["tf32"]
     from vectorizedbayesiannetwork_b200 import _lib as L
 
     lib = L.load()
@@ -201,338 +226,171 @@ def measure_tf32_peak(dev) -> float:
             e1.record()
             torch.cuda.synchronize()
             best = max(best, 2.0 * 128 * 256 * 8 * iters * sms / (e0.elapsed_time(e1) * 1e-3) / 1e12)
-    return round(best, 1)
+    _PEAKS["tf32"] = round(best, 1)
+    return _PEAKS["tf32"]
 
 
-def kde_inputs(n_rows: int):
-    g = torch.Generator().manual_seed(1)
-    return torch.randn(n_rows, 1, generator=g), torch.randn(n_rows, 1, generator=g)
+def _captures() -> dict:
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        return {}
 
 
-def run_kde(args, rank: int, local_rank: int, world: int) -> None:
-    """cfg4: conditional KDE density over query rows (rows sharded across ranks, no collective)."""
-    import torch.distributed as dist
+def _traffic(workload: str, rows: int):
+    cap = _captures().get(workload)
+    if not cap:
+        return None, None
+    t = {"bytes_per_launch": round(cap["dram_bytes"] * rows / cap["rows"]),
+         "source": f"ncu --set full capture at {cap['rows']} rows ({cap['file']}), scaled by rows"}
+    issue = None
+    if "issue_active_pct" in cap:
+        issue = {"issue_active_pct": cap["issue_active_pct"], "inst_per_row": cap.get("inst_per_row"),
+                 "source": f"same capture ({cap['file']}): smsp__issue_active.avg.pct_of_peak_sustained_active"}
+    return t, issue
 
-    import vectorizedbayesiannetwork_b200 as V
-    from vectorizedbayesiannetwork_b200 import _lib as L
-    from vectorizedbayesiannetwork_b200 import synthetic as S
 
-    desc, rows_rank, _, method = WORKLOADS["cfg4"]
-    if args.queries_per_gpu:
-        rows_rank = args.queries_per_gpu
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    n_points = args.samples or 200_000
-    spec = S.kde_pair(n_points)
-    model = V.VBN.from_spec(spec, device=dev)
-    handle = model.get_cpd("y")
-    x_h, p_h = kde_inputs(rows_rank * world)
-    x_h, p_h = x_h[rank * rows_rank:(rank + 1) * rows_rank], p_h[rank * rows_rank:(rank + 1) * rows_rank]
-    x_d, p_d = x_h.to(dev), p_h.to(dev)
-    x_p, p_p = x_h.pin_memory(), p_h.pin_memory()
-    out_h = torch.empty(rows_rank, 1).pin_memory()
-    args.warmup = max(args.warmup, 3)
+class Dist:
+    def __init__(self, rank, local_rank, world):
+        self.rank, self.local_rank, self.world = rank, local_rank, world
+        self.dev = torch.device("cuda", local_rank)
 
-    def barrier():
+    def barrier(self):
         torch.cuda.synchronize()
-        if world > 1:
+        if self.world > 1:
+            import torch.distributed as dist
+
             dist.barrier()
 
-    for _ in range(args.warmup):
-        handle.log_prob(x_d, p_d)
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-    l0 = L.launch_count()
-    barrier()
-    ev = []
-    for _ in range(args.steps):  # inputs (8 MB) + stored points (1.6 MB) are L2-sized; the kernel is MUFU bound
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        handle.log_prob(x_d, p_d)
-        e1.record()
-        ev.append((e0, e1))
-    barrier()
-    launches = L.launch_count() - l0
-    clock_info = clocks.stop() if rank == 0 else None
-    tot = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], device=dev, dtype=torch.float64)
-    ev2 = []
-    for _ in range(args.steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        lp = handle.log_prob(x_p.to(dev, non_blocking=True), p_p.to(dev, non_blocking=True))
-        out_h.copy_(lp, non_blocking=True)
-        e1.record()
-        ev2.append((e0, e1))
-    barrier()
-    tot2 = torch.tensor([sum(a.elapsed_time(b) for a, b in ev2)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot2, op=dist.ReduceOp.MAX)
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    sec = float(tot.item()) * 1e-3
-    rows_total = rows_rank * world
-    value = rows_total * args.steps / sec
-    pairs_per_s = rows_rank * n_points * args.steps / sec  # per GPU
-    sm_mhz = (clock_info or {}).get("sm_mhz") or 1965.0
-    sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    mufu_peak = 16 * sms * sm_mhz * 1e6  # ex2/s
-    cpu = None
-    if not args.no_cpu_baseline:
-        cpu = kde_cpu_baseline(n_points)
-    traffic = None
-    try:
-        cap = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("cfg4")
-        if cap:
-            traffic = {"bytes_per_launch": round(cap["dram_bytes"] * rows_rank / cap["rows"]),
-                       "source": f"ncu --set full capture at {cap['rows']} rows ({cap['file']}), scaled by rows"}
-    except Exception:
-        pass
-    line = {
-        "metric": "density_rows_per_sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "method": method, "rows_per_gpu": rows_rank, "rows_total": rows_total,
-                   "stored_points": n_points, "sharding": "rows" if world > 1 else "none",
-                   "l2": "working set (9.6 MB) is L2 resident by nature; kernel is MUFU bound, no flush needed"},
-        "pair_evals_per_sec_per_gpu": pairs_per_s,
-        "e2e": {"value": rows_total * args.steps / (float(tot2.item()) * 1e-3), "unit": "rows/s",
-                "h2d_bytes_per_step": 8 * rows_rank, "d2h_bytes_per_step": 4 * rows_rank},
-        "gpu_launches": launches, "clocks": clock_info,
-        "roofline": {"bound": "mufu", "achieved": round(2 * pairs_per_s / 1e12, 4), "peak": round(mufu_peak / 1e12, 4),
-                     "unit": "Tex2/s", "frac": round(2 * pairs_per_s / mufu_peak, 4), "traffic": traffic,
-                     "peak_source": "16 MUFU/clk/SM x SMs x median SM clock during the run (SURVEY 8d: KDE is "
-                                    "exp-limited at small dims; 2 exp2 per (row, point) pair)",
-                     "note": "achieved counts every exponential the algorithm needs; the kernel evaluates 1 in 4 of "
-                             "them with a degree-5 polynomial on the FMA pipe (FlashAttention-4 style), so the "
-                             "fraction of the MUFU-only ceiling can exceed 1",
-                     "kernel": "vbn::kde_log_prob_kernel<1,1>"},
-        "cpu_baseline": cpu,
-    }
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    def max_ms(self, ms: float) -> float:
+        t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
 
-def kde_cpu_baseline(n_points: int, rows: int = 2048) -> dict:
-    from oracle import vbn_oracle as O
-    from vectorizedbayesiannetwork_b200 import synthetic as S
-
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    c = S.kde_pair(n_points)["cpds"]["y"]
-    x, p = kde_inputs(rows)
-    O.kde_log_prob(c, x[:512], p[:512])
-    t0 = time.perf_counter()
-    O.kde_log_prob(c, x, p)
-    dt = time.perf_counter() - t0
-    return {"value": rows / dt, "unit": "rows/s", "cores": cores, "kind": "port",
-            "sample": f"{rows} query rows x {n_points} stored points (cost is linear in rows)"}
-
-
-def run_reference(args, rank: int, world: int) -> None:
-    """CPU arm: the oracle port of the reference on the host cores, bounded sample per step."""
-    if rank != 0:
-        return
-    from oracle import vbn_oracle as O
-
-    if args.workload == "cfg4":
-        n_points = args.samples or 200_000
-        rows = 2048
-        best = None
-        for _ in range(max(args.steps, 1)):
-            b = kde_cpu_baseline(n_points, rows)
-            best = b if best is None or b["value"] > best["value"] else best
-        line = {"impl": "reference", "metric": "density_rows_per_sec", "value": best["value"], "unit": "rows/s",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": 1, "ms_per_step": rows / best["value"] * 1e3,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOADS["cfg4"][0], "sample": best["sample"]}, "cpu_baseline": best,
-                "e2e": {"value": best["value"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
-        return
-
-    desc, b_rank, s, method = WORKLOADS[args.workload]
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    sample_q = {"cfg5": 4, "cfg2": 2, "cfg3": 64}[args.workload]
-    sample_s = {"cfg5": 4096, "cfg2": 65536, "cfg3": 4096}[args.workload]
-    spec, target, evidence = build_workload(args.workload, sample_q)
-    q = {"target": target, "evidence": evidence, "do": {}}
-    fn = O.importance_sampling if method == "importance_sampling" else O.likelihood_weighting
-    torch.manual_seed(0)
-    for _ in range(max(args.warmup, 1)):
-        fn(spec, q, sample_s)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        fn(spec, q, sample_s)
-    dt = time.perf_counter() - t0
-    value = sample_q * sample_s * args.steps / dt
-    sample = f"{sample_q} queries x {sample_s} samples per step (bounded sample of the workload; cost is linear in rows)"
-    line = {
-        "impl": "reference", "metric": "posterior_samples_per_sec", "value": value, "unit": "samples/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1),
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "method": method, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "queries_per_sec": sample_q * args.steps / dt,
-    }
-    print(json.dumps(line), flush=True)
-
-
-def main() -> None:
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--queries-per-gpu", type=int, default=None)
-    ap.add_argument("--samples", type=int, default=None)
-    ap.add_argument("--shard", default="queries", choices=["queries", "samples"],
-                    help="multi-GPU split: queries (weak scaling, no data-path collective) or samples "
-                         "(strong scaling of a fixed B x S job; per-query (m,l,q) all-gather over NCCL)")
-    args = ap.parse_args()
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
-    if args.workload == "cfg4":
-        assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-        run_kde(args, rank, local_rank, world)
-        return
-
-    import torch.distributed as dist
-
+# ------------------------------------------------------------------------------------------------------------
+# one inference workload (cfg5 / cfg2 / cfg3), device-timed + end to end
+# ------------------------------------------------------------------------------------------------------------
+def run_inference(name: str, d: Dist, *, steps: int, warmup: int, shard_kind: str = "queries", queries=None,
+                  samples=None, clocks: ClockSampler = None, active_world=None) -> dict:
+    """Times ``steps`` infer_posterior calls of workload ``name``.  ``active_world``: 1 = only rank 0 works (the
+    1-GPU leg of the strong-scaling pair under torchrun); None = all ranks."""
     import vectorizedbayesiannetwork_b200 as V
     from vectorizedbayesiannetwork_b200 import _lib as L
     from vectorizedbayesiannetwork_b200 import engine as E
 
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    args.warmup = max(args.warmup, 3)
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    L.load()
-
-    desc, b_rank, s, method = WORKLOADS[args.workload]
-    if args.queries_per_gpu:
-        b_rank = args.queries_per_gpu
-    if args.samples:
-        s = args.samples
-    by_samples = args.shard == "samples" and world > 1
-    b_total = b_rank if by_samples else b_rank * world
-    spec, target, evidence_host = build_workload(args.workload, b_total)
-    shard = V.Shard(args.shard, rank, world) if world > 1 else None
-    model = V.VBN.from_spec(spec, device=dev)
-    model.set_inference_method(method, n_samples=s)
-    evidence_dev = {k: v.to(dev) for k, v in evidence_host.items()}
-    evidence_pinned = {k: v.pin_memory() for k, v in evidence_host.items()}
-    q_dev = {"target": target, "evidence": evidence_dev}
-    kw = {"shard": shard} if shard is not None else {}
-
-    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # > 126 MB L2
-
-    def barrier():
+    desc, b_one, b_rank, s, method = WORKLOADS[name]
+    world = d.world if active_world is None else active_world
+    working = d.rank < world
+    if queries:
+        b_one = b_rank = queries
+    if samples:
+        s = samples
+    by_samples = shard_kind == "samples" and world > 1
+    b_total = b_one if (world == 1 or by_samples) else b_rank * world
+    b_local = b_total if (world == 1 or by_samples) else b_rank
+    dev = d.dev
+    warmup = max(warmup, 3)
+    out = None
+    if working:
+        spec, target, evidence_host = build_workload(name, b_total)
+        shard = V.Shard(shard_kind, d.rank, world) if world > 1 else None
+        model = V.VBN.from_spec(spec, device=dev)
+        model.set_inference_method(method, n_samples=s)
+        evidence_dev = {k: v.to(dev) for k, v in evidence_host.items()}
+        evidence_pinned = {k: v.pin_memory() for k, v in evidence_host.items()}
+        q_dev = {"target": target, "evidence": evidence_dev}
+        kw = {"shard": shard} if shard is not None else {}
+        flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # > 126 MB L2
+        for _ in range(warmup):
+            # keep the previous result alive like the timed loop does, so the caching allocator reaches its steady
+            # state before timing starts -- a cudaMalloc of a 256 MB block inside a timed step costs tens of ms
+            w, smp = model.infer_posterior(q_dev, **kw)
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-
-    # ---- warm-up (also compiles / uploads the schedule); the NVML sampler starts first so that its
-    # initialisation cannot land inside a timed step
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-    for _ in range(args.warmup):
-        # keep the previous result alive like the timed loop does, so the caching allocator reaches its
-        # steady state (two live result sets) before timing starts -- a cudaMalloc of a 256 MB block
-        # inside a timed step costs tens of ms
-        w, smp = model.infer_posterior(q_dev, **kw)
-    torch.cuda.synchronize()
-
-    # ---- device-resident timed region ------------------------------------------------------
-    import gc
-
     gc.collect()
     gc.disable()  # no collector pauses inside the timed steps
-    E.KERNEL_EVENTS = []
-    launches0 = L.launch_count()
-    barrier()
-    clocks.sm.clear()  # keep only samples taken during the timed region
-    step_events = []
-    fallbacks = 0
-    for _ in range(args.steps):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        w, smp = model.infer_posterior(q_dev, **kw)
-        e1.record()
-        step_events.append((e0, e1))
-        fallbacks += int(bool(getattr(model._inference, "_last_fallback", False)))
-    barrier()
-    launches = L.launch_count() - launches0
-    clock_info = clocks.stop() if rank == 0 else None
-    step_ms = [a.elapsed_time(b) for a, b in step_events]
-    total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_s = float(total_ms.item()) * 1e-3
-    kernel_ms = [a.elapsed_time(b) for a, b in E.KERNEL_EVENTS]
-    E.KERNEL_EVENTS = None
-    value = b_total * s * args.steps / total_s
+    step_ms, kernel_ms, fallbacks, launches = [], [], 0, 0
+    if working:
+        E.KERNEL_EVENTS = []
+        launches0 = L.launch_count()
+    d.barrier()
+    if clocks is not None:
+        clocks.mark()
+    if working:
+        events = []
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            w, smp = model.infer_posterior(q_dev, **kw)
+            e1.record()
+            events.append((e0, e1))
+            fallbacks += int(bool(getattr(model._inference, "_last_fallback", False)))
+    d.barrier()
+    clock_info = clocks.read() if clocks is not None else None
+    if working:
+        launches = L.launch_count() - launches0
+        step_ms = [a.elapsed_time(b) for a, b in events]
+        kernel_ms = [a.elapsed_time(b) for a, b in E.KERNEL_EVENTS]
+        E.KERNEL_EVENTS = None
+    total_ms = d.max_ms(sum(step_ms))
 
-    # ---- end-to-end: host evidence in, host (weights, samples) out --------------------------
-    s_rank = shard.local_samples(s)[0] if by_samples else s
-    out_w = torch.empty(b_rank, s_rank, dtype=torch.float32).pin_memory()
-    out_s = torch.empty(b_rank, s_rank, 1, dtype=torch.float32).pin_memory()
-    h2d = sum(v.numel() * 4 for v in evidence_pinned.values())
-    d2h = out_w.numel() * 4 + out_s.numel() * 4
+    # ---- end to end: host evidence in, host result out -------------------------------------------------
+    e2e_ms = {"full": 0.0, "summary": 0.0}
+    h2d = d2h = d2h_summary = 0
+    if working:
+        s_local = shard.local_samples(s)[0] if by_samples else s
+        out_w = torch.empty(b_local, s_local, dtype=torch.float32).pin_memory()
+        out_s = torch.empty(b_local, s_local, 1, dtype=torch.float32).pin_memory()
+        out_sum = torch.empty(b_local, 3, dtype=torch.float32).pin_memory()
+        h2d = sum(v.numel() * 4 for v in evidence_pinned.values())
+        d2h = out_w.numel() * 4 + out_s.numel() * 4
+        d2h_summary = out_sum.numel() * 4
 
-    def e2e_step():
-        ev = {k: v.to(dev, non_blocking=True) for k, v in evidence_pinned.items()}
-        w_, s_ = model.infer_posterior({"target": target, "evidence": ev}, **kw)
-        out_w.copy_(w_, non_blocking=True)
-        out_s.copy_(s_, non_blocking=True)
+        def e2e_full():
+            ev = {k: v.to(dev, non_blocking=True) for k, v in evidence_pinned.items()}
+            w_, s_ = model.infer_posterior({"target": target, "evidence": ev}, **kw)
+            out_w.copy_(w_, non_blocking=True)
+            out_s.copy_(s_, non_blocking=True)
 
-    e2e_step()
-    barrier()
-    e2e_events = []
-    for _ in range(args.steps):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        e2e_step()
-        e1.record()
-        e2e_events.append((e0, e1))
-    barrier()
-    e2e_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in e2e_events)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = b_total * s * args.steps / (float(e2e_ms.item()) * 1e-3)
+        def e2e_summary():
+            ev = {k: v.to(dev, non_blocking=True) for k, v in evidence_pinned.items()}
+            st = model.infer_posterior({"target": target, "evidence": ev}, summary=True, **kw)
+            out_sum[:, 0:1].copy_(st["mean"], non_blocking=True)
+            out_sum[:, 1:2].copy_(st["std"], non_blocking=True)
+            out_sum[:, 2].copy_(st["ess"], non_blocking=True)
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        legs = {"full": e2e_full, "summary": e2e_summary}
+    for leg in ("full", "summary"):
+        if working:
+            legs[leg]()
+        d.barrier()
+        ms = 0.0
+        if working:
+            ev_ = []
+            for _ in range(steps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                legs[leg]()
+                e1.record()
+                ev_.append((e0, e1))
+            torch.cuda.synchronize()
+            ms = sum(a.elapsed_time(b) for a, b in ev_)
+        d.barrier()
+        e2e_ms[leg] = d.max_ms(ms)
+    gc.enable()
+    if d.rank != 0:
+        return None
 
-    # ---- roofline of the dominant kernel (the fused schedule kernel) -------------------------
+    total_s = total_ms * 1e-3
+    value = b_total * s * steps / total_s
     plan = next(iter(model._inference._runner._cache.values()))
     work = algorithmic_work(plan.program)
-    rows = b_rank * s_rank
+    rows = b_local * s_local
     k_avg_ms = sum(kernel_ms) / max(len(kernel_ms), 1)
     peaks = measure_fma_peak(dev)
     measured = {}
@@ -541,15 +399,7 @@ def main() -> None:
     except Exception:
         pass
     hbm_peak = measured.get("hbm_gbs", 6650.0)
-    heavy = plan.program.heavy
-    traffic = None
-    try:  # DRAM bytes of the dominant kernel from the committed ncu capture, scaled to this launch's rows
-        cap = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload)
-        if cap:
-            traffic = {"bytes_per_launch": round(cap["dram_bytes"] * rows / cap["rows"]),
-                       "source": f"ncu --set full capture at {cap['rows']} rows ({cap['file']}), scaled by rows"}
-    except Exception:
-        pass
+    traffic, issue = _traffic(name, rows)
     if plan.program.tc:
         achieved = work["flops_per_row"] * rows / (k_avg_ms * 1e-3) / 1e12
         tf32_peak = measure_tf32_peak(dev)
@@ -562,7 +412,7 @@ def main() -> None:
                             "is bound by the per-row epilogue instruction issue, not by the tensor pipe",
                     "fp32_fma_peak_tflops": max(peaks.values()),
                     "frac_of_fp32_fma_peak": round(achieved / max(peaks.values()), 4)}
-    elif heavy:
+    elif plan.program.heavy:
         achieved = work["flops_per_row"] * rows / (k_avg_ms * 1e-3) / 1e12
         peak = max(peaks.values())
         roofline = {"bound": "fp32_fma", "achieved": round(achieved, 3), "peak": peak, "unit": "TFLOP/s",
@@ -575,40 +425,355 @@ def main() -> None:
         roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
                     "frac": round(achieved / hbm_peak, 4), "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if measured else "fallback 6650",
-                    "note": "algorithmic bytes = SURVEY 8(d) per-level SoA formula; the fused kernel keeps node "
-                            "columns in shared memory, so real DRAM traffic is only the stored columns"}
-    roofline.update({"kernel": "vbn::tc::schedule_tc_kernel" if plan.program.tc else "vbn::schedule_kernel", "kernel_ms_avg": round(k_avg_ms, 4),
-                     "kernel_launches_timed": len(kernel_ms), "rows_per_launch": rows,
-                     "flops_per_row": work["flops_per_row"], "level_bytes_per_row": work["level_bytes_per_row"],
-                     "kernel_share_of_step": round(sum(kernel_ms) / sum(step_ms), 4)})
-
-    cpu = None
-    if not args.no_cpu_baseline:
-        try:
-            proc = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload",
-                                   args.workload, "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
-                                  timeout=900, env={k: v for k, v in os.environ.items()
-                                                    if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
-            cpu = json.loads(proc.stdout.strip().splitlines()[-1])["cpu_baseline"]
-        except Exception as exc:  # keep the bench line even if the CPU leg fails
-            cpu = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
-
-    line = {
+                    "note": "algorithmic bytes = SURVEY 8(d) per-level SoA formula, an EQUIVALENCE: the fused kernel "
+                            "keeps node columns in shared memory, so real DRAM traffic is only the stored columns and "
+                            "the kernel is instruction-issue bound (see `issue`)"}
+    if issue:
+        roofline["issue"] = issue
+    roofline.update({"kernel": "vbn::tc::schedule_tc_kernel" if plan.program.tc else "vbn::schedule_kernel",
+                     "kernel_ms_avg": round(k_avg_ms, 4), "kernel_launches_timed": len(kernel_ms),
+                     "rows_per_launch": rows, "flops_per_row": work["flops_per_row"],
+                     "level_bytes_per_row": work["level_bytes_per_row"],
+                     "kernel_share_of_step": round(sum(kernel_ms) / max(sum(step_ms), 1e-9), 4)})
+    jobs = b_total * s * steps
+    return {
         "metric": "posterior_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_s / args.steps * 1e3,
+        "steps": steps, "warmup": warmup, "ms_per_step": total_s / steps * 1e3,
         "higher_is_better": True, "scaling": "strong" if by_samples else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "method": method, "queries_per_gpu": b_rank, "queries_total": b_total,
-                   "samples_per_query": s, "sharding": args.shard if world > 1 else "none",
+        "config": {"workload": desc, "method": method, "queries_per_gpu": b_local, "queries_total": b_total,
+                   "samples_per_query": s, "sharding": shard_kind if world > 1 else "none",
                    "l2": "256 MB buffer rewritten between timed steps (L2 flush)",
-                   "is_fallback_steps": fallbacks, "weights": "random-init (nn.Linear default), seeded"},
-        "queries_per_sec": b_total * args.steps / total_s,
+                   "is_fallback_steps": fallbacks, "weights": "random-init (nn.Linear default), seeded; the "
+                   "reference arm loads the same tensors into the reference's own CPD classes"},
+        "queries_per_sec": b_total * steps / total_s,
         "step_ms": [round(x, 3) for x in step_ms], "kernel_ms": [round(x, 3) for x in kernel_ms],
-        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": launches, "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": jobs / (e2e_ms["full"] * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h},
+        "e2e_summary": {"value": jobs / (e2e_ms["summary"] * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h_summary,
+                        "what": "infer_posterior(..., summary=True): weighted mean / std / ESS per query reduced on "
+                                "the device (VBN._posterior_stats semantics); nothing of size [B,S] leaves the GPU"},
+        "gpu_launches": launches, "clocks": clock_info, "roofline": roofline,
     }
+
+
+# ------------------------------------------------------------------------------------------------------------
+# cfg4: KDE conditional density
+# ------------------------------------------------------------------------------------------------------------
+def kde_inputs(n_rows: int):
+    g = torch.Generator().manual_seed(1)
+    return torch.randn(n_rows, 1, generator=g), torch.randn(n_rows, 1, generator=g)
+
+
+def run_kde(d: Dist, *, steps: int, warmup: int, rows=None, n_points=None, clocks: ClockSampler = None) -> dict:
+    """cfg4: conditional KDE density over query rows (rows sharded across ranks, no collective)."""
+    import vectorizedbayesiannetwork_b200 as V
+    from vectorizedbayesiannetwork_b200 import _lib as L
+    from vectorizedbayesiannetwork_b200 import synthetic as S
+
+    desc, rows_one, rows_rank, _, method = WORKLOADS["cfg4"]
+    rows_rank = rows or (rows_one if d.world == 1 else rows_rank)
+    dev, rank, world = d.dev, d.rank, d.world
+    n_points = n_points or 200_000
+    spec = S.kde_pair(n_points)
+    model = V.VBN.from_spec(spec, device=dev)
+    handle = model.get_cpd("y")
+    x_h, p_h = kde_inputs(rows_rank * world)
+    x_h, p_h = x_h[rank * rows_rank:(rank + 1) * rows_rank], p_h[rank * rows_rank:(rank + 1) * rows_rank]
+    x_d, p_d = x_h.to(dev), p_h.to(dev)
+    x_p, p_p = x_h.pin_memory(), p_h.pin_memory()
+    out_h = torch.empty(rows_rank, 1).pin_memory()
+    warmup = max(warmup, 3)
+    for _ in range(warmup):
+        handle.log_prob(x_d, p_d)
+    l0 = L.launch_count()
+    d.barrier()
+    if clocks is not None:
+        clocks.mark()
+    ev = []
+    for _ in range(steps):  # inputs (8 MB) + stored points (1.6 MB) are L2-sized; the kernel is MUFU bound
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        handle.log_prob(x_d, p_d)
+        e1.record()
+        ev.append((e0, e1))
+    d.barrier()
+    launches = L.launch_count() - l0
+    clock_info = clocks.read() if clocks is not None else None
+    tot = d.max_ms(sum(a.elapsed_time(b) for a, b in ev))
+    ev2 = []
+    for _ in range(steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lp = handle.log_prob(x_p.to(dev, non_blocking=True), p_p.to(dev, non_blocking=True))
+        out_h.copy_(lp, non_blocking=True)
+        e1.record()
+        ev2.append((e0, e1))
+    d.barrier()
+    tot2 = d.max_ms(sum(a.elapsed_time(b) for a, b in ev2))
+    if rank != 0:
+        return None
+    sec = tot * 1e-3
+    rows_total = rows_rank * world
+    value = rows_total * steps / sec
+    pairs_per_s = rows_rank * n_points * steps / sec  # per GPU
+    sm_mhz = (clock_info or {}).get("sm_mhz") or 1965.0
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    mufu_peak = 16 * sms * sm_mhz * 1e6  # ex2/s
+    traffic, _ = _traffic("cfg4", rows_rank)
+    return {
+        "metric": "density_rows_per_sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": sec / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "method": method, "rows_per_gpu": rows_rank, "rows_total": rows_total,
+                   "stored_points": n_points, "sharding": "rows" if world > 1 else "none",
+                   "l2": "working set (9.6 MB) is L2 resident by nature; kernel is MUFU bound, no flush needed"},
+        "pair_evals_per_sec_per_gpu": pairs_per_s,
+        "e2e": {"value": rows_total * steps / (tot2 * 1e-3), "unit": "rows/s",
+                "h2d_bytes_per_step": 8 * rows_rank, "d2h_bytes_per_step": 4 * rows_rank},
+        "gpu_launches": launches, "clocks": clock_info,
+        "roofline": {"bound": "mufu", "achieved": round(2 * pairs_per_s / 1e12, 4), "peak": round(mufu_peak / 1e12, 4),
+                     "unit": "Tex2/s", "frac": round(2 * pairs_per_s / mufu_peak, 4), "traffic": traffic,
+                     "peak_source": "16 MUFU/clk/SM x SMs x median SM clock during the run (SURVEY 8d: KDE is "
+                                    "exp-limited at small dims; 2 exp2 per (row, point) pair)",
+                     "note": "achieved counts every exponential the algorithm needs; the kernel evaluates 1 in 4 of "
+                             "them with a degree-5 polynomial on the FMA pipe (FlashAttention-4 style), so the "
+                             "fraction of the MUFU-only ceiling can exceed 1",
+                     "kernel": "vbn::kde_log_prob_kernel<1,1>"},
+    }
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the reference arm (CPU)
+# ------------------------------------------------------------------------------------------------------------
+def _cpu_model() -> str:
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args, rank: int) -> None:
+    """CPU arm on the box's host cores: the unmodified reference package (baseline/_ref) through its own public API,
+    parameters = the same tensors the B200 arm uses; the oracle port only if the package is missing.  A step is a
+    bounded sample of the workload (cost is linear in queries: two sample sizes are timed first to show it), sized
+    so that the whole --steps K --warmup W run ends within a couple of minutes."""
+    if rank != 0:
+        return
+    from oracle import reference_arm as R
+    from oracle import vbn_oracle as O
+    from vectorizedbayesiannetwork_b200 import synthetic as S
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    have_ref = R.reference_path() is not None
+    kind = "reference" if have_ref else "port"
+    steps, warmup = max(args.steps, 1), max(args.warmup, 1)
+    budget_s = 100.0
+
+    if args.workload == "cfg4":
+        n_points = args.samples or 200_000
+        spec = S.kde_pair(n_points)
+        if have_ref:
+            handle = R.reference_from_spec(spec).get_cpd("y")
+            fn = lambda x, p: handle.log_prob(x, {"p": p})
+        else:
+            fn = lambda x, p: O.kde_log_prob(spec["cpds"]["y"], x, p)
+        unit, metric, per = "rows/s", "density_rows_per_sec", 1
+
+        def timed(n):
+            x, p = kde_inputs(n)
+            t0 = time.perf_counter()
+            fn(x, p)
+            return time.perf_counter() - t0
+
+        sizes = (512, 2048)
+        sample_of = lambda n: f"{n} query rows x {n_points} stored points"
+        method, desc = "kde_log_prob", WORKLOADS["cfg4"][0]
+        cap = 8192
+    else:
+        desc, _, _, s_full, method = WORKLOADS[args.workload]
+        sample_s = args.samples or {"cfg5": 4096, "cfg2": 65536, "cfg3": 4096}[args.workload]
+        sizes = {"cfg5": (4, 16), "cfg2": (2, 8), "cfg3": (32, 128)}[args.workload]
+        cap = sizes[1]
+        spec, target, _ = build_workload(args.workload, 1)
+        if have_ref:
+            model = R.reference_from_spec(spec)
+            model.set_inference_method(method, n_samples=sample_s)
+            fn = lambda q: model.infer_posterior(q)
+        else:
+            ofn = O.importance_sampling if method == "importance_sampling" else O.likelihood_weighting
+            fn = lambda q: ofn(spec, q, sample_s)
+        unit, metric, per = "samples/s", "posterior_samples_per_sec", sample_s
+
+        def timed(n):
+            _, tgt, ev = build_workload(args.workload, n)
+            q = {"target": tgt, "evidence": ev}
+            t0 = time.perf_counter()
+            fn(q)
+            return time.perf_counter() - t0
+
+        sample_of = lambda n: f"{n} queries x {sample_s} samples"
+
+    torch.manual_seed(0)
+    timed(sizes[0])  # first call: allocator / thread-pool warm-up
+    t_small, t_big = timed(sizes[0]), timed(sizes[1])
+    per_unit = t_big / sizes[1]
+    n_step = int(max(sizes[0] // 2 or 1, min(cap, budget_s / (steps + warmup) / per_unit)))
+    for _ in range(warmup):
+        timed(n_step)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        timed(n_step)
+    dt = time.perf_counter() - t0
+    value = n_step * per * steps / dt
+    sample = (f"{sample_of(n_step)} per step (bounded sample of the workload; cost is linear in queries: "
+              f"{sample_of(sizes[0])} took {t_small:.2f} s, {sample_of(sizes[1])} took {t_big:.2f} s = "
+              f"{t_big / t_small:.2f}x for {sizes[1] / sizes[0]:.0f}x the queries)")
+    line = {
+        "impl": "reference", "metric": metric, "value": value, "unit": unit,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt / steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "method": method, "sample": sample,
+                   "reference": ("unmodified vbn 0.3.0 from baseline/_ref, VBN(device='cpu'), parameters loaded into "
+                                 "the reference's own CPD classes (oracle/reference_arm.py)") if have_ref else
+                                "oracle port (reference package not found on this box)",
+                   "cpu": _cpu_model(), "threads": cores},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": kind, "sample": sample,
+                         "linearity": {"sizes": list(sizes), "seconds": [round(t_small, 3), round(t_big, 3)]}},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    if per != 1:
+        line["queries_per_sec"] = n_step * steps / dt
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(workload: str) -> dict:
+    """The reference arm in a child process (its torch thread pool must not fight this process's)."""
+    try:
+        proc = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload",
+                               workload, "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
+                              timeout=900, env={k: v for k, v in os.environ.items()
+                                                if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+        return json.loads(proc.stdout.strip().splitlines()[-1])["cpu_baseline"]
+    except Exception as exc:  # keep the bench line even if the CPU leg fails
+        return {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "reference",
+                "sample": f"failed: {exc}"}
+
+
+def secondary_cuda_reference(dev, n_queries: int = 4) -> dict:
+    """Optional, labelled extra: the unmodified reference with device='cuda' (torch eager) on
+    this B200, cfg5, a few queries (its cost is linear in queries: a Python loop over nodes and query rows)."""
+    try:
+        from oracle import reference_arm as R
+
+        if R.reference_path() is None:
+            return {"unavailable": "reference package not on this box"}
+        spec, target, ev = build_workload("cfg5", n_queries)
+        model = R.reference_from_spec(spec, device=dev)
+        model.set_inference_method("importance_sampling", n_samples=4096)
+        q = {"target": target, "evidence": {k: v.to(dev) for k, v in ev.items()}}
+        model.infer_posterior(q)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        model.infer_posterior(q)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        return {"what": "unmodified reference, VBN(device='cuda'), torch eager on one B200 (secondary, not the target)",
+                "value": n_queries * 4096 / dt, "unit": "samples/s",
+                "sample": f"{n_queries} queries x 4096 samples, wall clock around one infer_posterior call"}
+    except Exception as exc:
+        return {"unavailable": f"{type(exc).__name__}: {exc}"}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the cfg2 / cfg3 / cfg4 side runs of the default line")
+    ap.add_argument("--queries-per-gpu", type=int, default=None)
+    ap.add_argument("--samples", type=int, default=None)
+    ap.add_argument("--shard", default="queries", choices=["queries", "samples"],
+                    help="multi-GPU split: queries (weak scaling, no data-path collective) or samples "
+                         "(strong scaling of a fixed B x S job; per-query (m,l,q) all-gather over NCCL)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    from vectorizedbayesiannetwork_b200 import _lib as L
+
+    d = Dist(rank, local_rank, world)
+    torch.cuda.set_device(d.dev)
     if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=d.dev)
+    L.load()
+    clocks = ClockSampler(local_rank).start() if rank == 0 else None  # started before any timed region
+
+    default_line = args.workload == "cfg5" and not args.queries_per_gpu and not args.samples and args.shard == "queries"
+    if args.workload == "cfg4":
+        line = run_kde(d, steps=args.steps, warmup=args.warmup, rows=args.queries_per_gpu, n_points=args.samples,
+                       clocks=clocks)
+    else:
+        line = run_inference(args.workload, d, steps=args.steps, warmup=args.warmup, shard_kind=args.shard,
+                             queries=args.queries_per_gpu, samples=args.samples, clocks=clocks)
+
+    others, strong = None, None
+    if default_line and not args.no_others:
+        if world == 1:
+            # the other BASELINE workloads, short runs in the same process: driver-visible numbers for all four
+            others = {}
+            for name in ("cfg2", "cfg3"):
+                others[name] = run_inference(name, d, steps=3, warmup=3, clocks=clocks)
+            others["cfg4"] = run_kde(d, steps=3, warmup=3, clocks=clocks)
+        else:
+            # strong scaling of the one path with a data-path collective: cfg2 (64 x 1M), samples sharded
+            one = run_inference("cfg2", d, steps=5, warmup=3, clocks=clocks, active_world=1)
+            many = run_inference("cfg2", d, steps=5, warmup=3, shard_kind="samples", clocks=clocks)
+            if rank == 0:
+                strong = {"workload": WORKLOADS["cfg2"][0], "sharding": "samples", "n_gpus": world,
+                          "collective": "one all_gather of [B, 3 + moments] floats per pass (NCCL)",
+                          "ms_per_step_1gpu": one["ms_per_step"], "ms_per_step": many["ms_per_step"],
+                          "value_1gpu": one["value"], "value": many["value"],
+                          "speedup": one["ms_per_step"] / many["ms_per_step"],
+                          "efficiency": one["ms_per_step"] / many["ms_per_step"] / world,
+                          "kernel_share_of_step": many["roofline"]["kernel_share_of_step"],
+                          "gpu_launches": many["gpu_launches"], "is_fallback_steps": many["config"]["is_fallback_steps"],
+                          "clocks": many["clocks"]}
+    if rank == 0:
+        if others is not None:
+            for name, o in others.items():
+                if not args.no_cpu_baseline:
+                    o["cpu_baseline"] = cpu_baseline(name)
+            line["others"] = others
+        if strong is not None:
+            line["strong_scaling"] = strong
+        line["cpu_baseline"] = None if args.no_cpu_baseline else cpu_baseline(args.workload)
+        if default_line and world == 1 and not args.no_cpu_baseline:
+            line["secondary_baseline"] = secondary_cuda_reference(d.dev)
+        print(json.dumps(line), flush=True)
+    if clocks is not None:
+        clocks.stop()
+    if world > 1:
+        import torch.distributed as dist
+
         dist.destroy_process_group()
 
 

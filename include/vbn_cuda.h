@@ -209,6 +209,17 @@ typedef struct VbnRunDesc {
                               resampled_importance_sampling.py:69-100); 0: overwrite          */
   int32_t* error_flag_dev; /* set to 1 when a softmax_nn discrete value has no class
                               (softmax_nn.py:620-625 raises ValueError); may be NULL       */
+  /* Fused weight reduction (optional): the kernel folds every run of rows of one query inside a warp's 32
+   * consecutive rows into one 16-float record {m = max logw, l = sum e, q = sum e^2, x0, sum e (x - x0),
+   * sum e (x - x0)^2, rows, -, sum e [x == k] for k < 8}, e = exp(logw - m), at
+   * seg_dev[(b * seg_per_query + (r / 32 - b S / 32)) * 16]; vbn_segment_merge folds a query's records.  This is the
+   * first pass of torch.softmax(log_weights, 1) (importance_sampling.py:82-84, likelihood_weighting.py:75-80) and,
+   * with seg_slot >= 0, the sums of VBN._posterior_stats (vbn/vbn.py:495-503) / the benchmark adapter's class
+   * histogram (benchmarking/models/vbn.py:202-242) without a [B, S] tensor ever reaching HBM.                  */
+  float* seg_dev;          /* [B][seg_per_query][16], NULL = off                              */
+  int32_t seg_per_query;   /* >= ceil(S / 32) + 1                                             */
+  int32_t seg_slot;        /* value slot whose weighted moments are accumulated (D = 1), -1 = log-weights only */
+  int32_t seg_classes;     /* 0, or 1..8: also the weighted histogram of that value over classes 0..k-1 */
 } VbnRunDesc;
 
 int32_t vbn_cuda_abi_version(void);
@@ -242,6 +253,16 @@ int32_t vbn_lse_merge(const float* partials_dev, int64_t n_queries, int32_t n_sp
 int32_t vbn_weights_normalize(const float* logw_dev, const float* stats_dev, int64_t n_queries,
                               int64_t n_samples, int32_t normalize, float eps, float* w_dev,
                               float* ess_dev, void* stream);
+/*
+ * Folds the records written through VbnRunDesc.seg_dev: merged_dev [B][16] = {m, l, q, weighted mean, 0,
+ * M2 = sum e (x - mean)^2, rows, ess = l^2 / q, class sums[8]} (itself a valid record), stats_dev [B][3] = {m, l, q}
+ * for vbn_weights_normalize (either may be NULL); with ess_threshold > 0 and flag_dev != NULL also the IS -> LW
+ * fallback test any(ess < threshold) (importance_sampling.py:85-88).  n_samples > 0: records follow the kernel's
+ * geometry (query b owns ((b+1) S - 1)/32 - b S/32 + 1 of its n_per_query slots); n_samples == 0: all n_per_query
+ * records of every query are valid -- the cross-GPU merge of all-gathered merged records (samples sharded).
+ */
+int32_t vbn_segment_merge(const float* records_dev, int64_t n_queries, int64_t n_samples, int32_t n_per_query,
+                          float ess_threshold, float* merged_dev, float* stats_dev, int32_t* flag_dev, void* stream);
 /* any(ess < threshold) -> *flag_dev (int32), the IS->LW fallback test
  * (importance_sampling.py:85-88) */
 int32_t vbn_ess_below(const float* stats_dev, int64_t n_queries, float threshold,

@@ -50,6 +50,7 @@ int32_t vbn_run_forward(const VbnPlan* plan, const VbnRunDesc* run, void*) {
   a.key0 = (uint32_t)run->seed; a.key1 = (uint32_t)(run->seed >> 32); a.call_offset = (uint32_t)run->call_offset; vbn::fill_round_keys(a);
   a.fixed = run->fixed_dev; a.inputs = run->inputs_dev; a.stores = run->stores_dev; a.noise = run->noise_dev;
   a.logw = run->logw_dev; a.logp = run->logp_dev; a.error_flag = run->error_flag_dev;
+  a.seg = run->seg_dev; a.seg_per_query = run->seg_per_query; a.seg_slot = run->seg_slot; a.seg_classes = run->seg_classes;
   if ((size_t)(a.n_slots + a.n_scratch) * 2 * 32 > sizeof(vbn::smem) / sizeof(float)) return VBN_E_CAPACITY;
   if (plan->desc.heavy) run_kernel<2, 32, true>(a); else run_kernel<2, 32, false>(a);
   return 0;
@@ -90,6 +91,33 @@ int32_t vbn_weights_normalize(const float* x, const float* st, int64_t B, int64_
       w[b * S + i] = norm ? e / l : std::max(e, eps);
     }
     if (ess) ess[b] = l * l / q;
+  }
+  return 0;
+}
+int32_t vbn_segment_merge(const float* rec, int64_t B, int64_t S, int32_t P, float thr, float* merged, float* stats,
+                          int32_t* flag, void*) {
+  for (int64_t b = 0; b < B; ++b) {
+    const int64_t count = S > 0 ? (((b + 1) * S - 1) >> 5) - ((b * S) >> 5) + 1 : P;
+    double m = -CUDART_INF_F, l = 0, q = 0, mean = 0, m2 = 0, n = 0, h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t i = 0; i < count; ++i) {
+      const float* r = rec + (b * P + i) * 16;
+      if (r[6] == 0.0f) continue;
+      const double rl = r[1], rmean = rl > 0 ? r[3] + r[4] / rl : r[3], rm2 = rl > 0 ? std::max(0.0, r[5] - (double)r[4] * r[4] / rl) : 0.0;
+      if (n == 0) { m = r[0]; l = rl; q = r[2]; mean = rmean; m2 = rm2; n = r[6]; for (int k = 0; k < 8; ++k) h[k] = r[8 + k]; continue; }
+      const double mm = std::max(m, (double)r[0]);
+      const double sa = m > -CUDART_INF_F ? std::exp(m - mm) : 0.0, sb = r[0] > -CUDART_INF_F ? std::exp(r[0] - mm) : 0.0;
+      const double la = l * sa, lb = rl * sb, lt = la + lb, d = rmean - mean, fb = lt > 0 ? lb / lt : 0.0;
+      mean += d * fb; m2 = m2 * sa + rm2 * sb + d * d * la * fb; q = q * sa * sa + r[2] * sb * sb; l = lt; m = mm; n += r[6];
+      for (int k = 0; k < 8; ++k) h[k] = h[k] * sa + r[8 + k] * sb;
+    }
+    const double ess = l * l / q;  // 0/0 = NaN for an all -inf query, like torch.softmax
+    if (merged) {
+      float* o = merged + b * 16;
+      o[0] = (float)m; o[1] = (float)l; o[2] = (float)q; o[3] = (float)mean; o[4] = 0; o[5] = (float)m2; o[6] = (float)n; o[7] = (float)ess;
+      for (int k = 0; k < 8; ++k) o[8 + k] = (float)h[k];
+    }
+    if (stats) { stats[b * 3] = (float)m; stats[b * 3 + 1] = (float)l; stats[b * 3 + 2] = (float)q; }
+    if (flag && thr > 0 && ess < thr) *flag |= 1;
   }
   return 0;
 }

@@ -777,3 +777,71 @@ def test_resampled_importance_sampling_philox_path(backend):
     assert s3.shape == (2, n, 1) and torch.isfinite(s3).all()
     w4, s4 = model.infer_posterior({"target": "x2", "evidence": {"x2": ev}}, seed=8)
     assert bool((s4[0] == 0.5).all()) and bool((s4[1] == 3.0).all())
+
+
+# ---- fused weight reduction / summary path (the summaries as an epilogue of the weight pass) ------
+def test_summary_path_matches_posterior_stats_of_the_materialised_result(backend):
+    """infer_posterior(..., summary=True): the schedule kernel accumulates the weighted moments of the target next to
+    the softmax statistics (no [B, S] tensor is materialised); the result must equal VBN._posterior_stats
+    (vbn/vbn.py:495-504) of the ordinary (weights, samples) result on the same draws."""
+    model = _chain(backend.device, n=6)
+    q = {"target": "x2", "evidence": {"x5": torch.tensor([[1.0], [2.5], [-0.5]])}}
+    for method, s in (("likelihood_weighting", 1000), ("importance_sampling", 333), ("likelihood_weighting", 37)):
+        model.set_inference_method(method, n_samples=s)
+        if method == "importance_sampling":
+            model._inference.ess_threshold = 0.0  # keep the IS pass (no fallback) so both calls share the draws
+        w, x = model.infer_posterior(q, seed=21)
+        ref = O_posterior_stats(w.cpu(), x.cpu())
+        got = model.infer_posterior(q, seed=21, summary=True)
+        assert set(got) >= {"mean", "std", "ess"} and got["mean"].shape == (3, 1) and got["ess"].shape == (3,)
+        torch.testing.assert_close(got["mean"].cpu(), ref["mean"], rtol=2e-5, atol=2e-6)
+        torch.testing.assert_close(got["std"].cpu(), ref["std"], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(got["ess"].cpu(), ref["ess"], rtol=1e-4, atol=1e-3)
+
+
+def O_posterior_stats(pdf, samples, eps=1e-12):
+    weights = torch.nan_to_num(pdf, nan=0.0, posinf=0.0, neginf=0.0).clamp_min(0.0)
+    denom = weights.sum(dim=1, keepdim=True)
+    weights = torch.where(denom > eps, weights / denom.clamp_min(eps), torch.full_like(weights, 1.0 / weights.shape[1]))
+    mean = (weights.unsqueeze(-1) * samples).sum(dim=1)
+    var = (weights.unsqueeze(-1) * (samples - mean.unsqueeze(1)) ** 2).sum(dim=1)
+    return {"mean": mean, "std": var.clamp_min(0.0).sqrt(), "ess": 1.0 / (weights ** 2).sum(dim=1).clamp_min(eps)}
+
+
+def test_summary_path_class_histogram(backend):
+    """summary={"classes": k}: the weighted class histogram of a discrete target (the benchmark adapter's
+    _estimate_discrete_posterior_batch, benchmarking/models/vbn.py:202-242) from the same records."""
+    spec = S.alarm_softmax(seed=0)
+    model = V.VBN.from_spec(spec, device=backend.device)
+    g = torch.Generator().manual_seed(2)
+    ev = {n: torch.randint(0, S.ALARM[n][0], (4, 1), generator=g).float() for n in ("HRBP", "BP")}
+    q = {"target": "VENTLUNG", "evidence": ev}
+    model.set_inference_method("likelihood_weighting", n_samples=500)
+    w, x = model.infer_posterior(q, seed=8)
+    got = model.infer_posterior(q, seed=8, summary={"classes": 4})
+    import numpy as np
+
+    want = np.stack(O.estimate_discrete_posterior_batch(x.cpu()[..., 0], w.cpu(), 4))
+    torch.testing.assert_close(got["probs"].cpu(), torch.as_tensor(want, dtype=torch.float32), rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(got["probs"].sum(1).cpu(), torch.ones(4), rtol=1e-5, atol=1e-5)
+
+
+def test_minus_inf_log_weights_follow_softmax(backend):
+    """Rows whose log-weight is -inf get weight 0 when the query has any finite row (torch.softmax), whatever their
+    position; a query with no finite row gets NaN weights and NaN ESS (and therefore no IS fallback), exactly like
+    torch.softmax / 1 / sum w^2 in the reference (importance_sampling.py:82-88)."""
+    from vectorizedbayesiannetwork_b200 import engine as E
+
+    dev = backend.device
+    logw = torch.randn(3, 70)
+    logw[0, 0] = float("-inf")          # first element of a row
+    logw[0, 40:45] = float("-inf")
+    logw[1, :] = float("-inf")          # nothing finite
+    lw = logw.to(dev)
+    stats = E.lse_stats(lw)
+    w, ess = E.normalize_weights(lw, stats)
+    want = torch.softmax(logw, dim=1)
+    torch.testing.assert_close(w.cpu()[[0, 2]], want[[0, 2]], rtol=2e-5, atol=1e-9)
+    assert bool((w.cpu()[0, 40:45] == 0).all()) and w.cpu()[0, 0] == 0
+    assert bool(torch.isnan(w.cpu()[1]).all()) and bool(torch.isnan(ess.cpu()[1]))
+    torch.testing.assert_close(ess.cpu()[[0, 2]], 1.0 / (want[[0, 2]] ** 2).sum(1), rtol=1e-4, atol=1e-4)

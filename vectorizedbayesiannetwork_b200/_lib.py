@@ -58,6 +58,7 @@ class RunDesc(C.Structure):
         ("logw_dev", C.c_void_p), ("logp_dev", C.c_void_p),
         ("logp_as_pdf", C.c_int32), ("logw_accumulate", C.c_int32),
         ("error_flag_dev", C.c_void_p),
+        ("seg_dev", C.c_void_p), ("seg_per_query", C.c_int32), ("seg_slot", C.c_int32), ("seg_classes", C.c_int32),
     ]
 
 
@@ -73,6 +74,8 @@ EXPORTS = {
     "vbn_lse_merge": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "vbn_weights_normalize": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
                                           C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vbn_segment_merge": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
     "vbn_ess_below": (C.c_int32, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]),
     "vbn_row_cdf": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "vbn_resample_indices": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64, C.c_int64,

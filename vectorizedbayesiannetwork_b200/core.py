@@ -322,7 +322,10 @@ class VBN:
         if self._inference is None:
             raise RuntimeError("Call set_inference_method(...) before infer_posterior().")
         q = self._normalize_query(query)
-        pdf, samples = self._inference.infer_posterior(self, q, **kwargs)
+        out = self._inference.infer_posterior(self, q, **kwargs)
+        if isinstance(out, dict):  # summary=True (extension): per-query posterior summary reduced on the device
+            return {k: v.detach() for k, v in out.items()}
+        pdf, samples = out
         return pdf.detach(), samples.detach()
 
     def sample(self, query, n_samples: int = 200, **kwargs):

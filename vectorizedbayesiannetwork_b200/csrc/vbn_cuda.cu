@@ -236,6 +236,15 @@ int32_t vbn_run_forward(const VbnPlan* plan, const VbnRunDesc* run, void* stream
   a.logw = run->logw_dev;
   a.logp = run->logp_dev;
   a.error_flag = run->error_flag_dev;
+  a.seg = run->seg_dev;
+  a.seg_per_query = run->seg_per_query;
+  a.seg_slot = run->seg_slot;
+  a.seg_classes = run->seg_classes;
+  if (a.seg) {
+    if (a.seg_per_query < (a.n_samples + 31) / 32 + 1) return fail(VBN_E_INVALID, "seg_per_query too small");
+    if (a.seg_slot >= plan->desc.n_slots || a.seg_classes < 0 || a.seg_classes > 8)
+      return fail(VBN_E_INVALID, "bad seg_slot / seg_classes");
+  }
   if (plan->tc) {
     const int threads = plan->tc * vbn::tc::kWgThreads;
     const int64_t rows_per_cta = static_cast<int64_t>(threads) * plan->tc_rpt;
@@ -310,6 +319,16 @@ int32_t vbn_weights_normalize(const float* logw_dev, const float* stats_dev, int
   const unsigned grid = static_cast<unsigned>(want < cap ? (want > 0 ? want : 1) : cap);
   vbn::weights_normalize_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       logw_dev, stats_dev, n_queries, n_samples, normalize, eps, w_dev, ess_dev);
+  CUDA_TRY(cudaGetLastError());
+  return VBN_OK;
+}
+
+int32_t vbn_segment_merge(const float* records_dev, int64_t n_queries, int64_t n_samples, int32_t n_per_query,
+                          float ess_threshold, float* merged_dev, float* stats_dev, int32_t* flag_dev, void* stream) {
+  if (!records_dev || n_queries <= 0 || n_samples < 0 || n_per_query <= 0 || (!merged_dev && !stats_dev))
+    return fail(VBN_E_INVALID, "bad argument to vbn_segment_merge");
+  vbn::segment_merge_kernel<<<static_cast<unsigned>(n_queries), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      records_dev, n_samples, n_per_query, ess_threshold, merged_dev, stats_dev, flag_dev);
   CUDA_TRY(cudaGetLastError());
   return VBN_OK;
 }

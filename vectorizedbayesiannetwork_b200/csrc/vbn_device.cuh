@@ -155,6 +155,7 @@ struct Lse {
   float m, l;
   __device__ __forceinline__ void init() { m = -CUDART_INF_F; l = 0.0f; }
   __device__ __forceinline__ void push(float x) {
+    if (x == -CUDART_INF_F) return;  // contributes exp(-inf) = 0; the update below would form exp(-inf - -inf) = NaN
     if (x > m) {
       l = l * __expf(m - x) + 1.0f;
       m = x;

@@ -21,6 +21,7 @@ __device__ __forceinline__ Mlq mlq_merge(Mlq a, Mlq b) {
 }
 
 __device__ __forceinline__ void mlq_push(Mlq& s, float x) {
+  if (x == -CUDART_INF_F) return;  // weight 0 (torch.softmax gives such rows 0); exp(-inf - -inf) would be NaN
   if (x > s.m) {
     const float e = __expf(s.m - x);  // exp(-inf)=0 on the first element
     s.l = s.l * e + 1.0f;
@@ -103,6 +104,102 @@ __global__ void lse_merge_kernel(const float* __restrict__ partials, int64_t n_q
   stats[b * 3 + 0] = s.m;
   stats[b * 3 + 1] = s.l;
   stats[b * 3 + 2] = s.q;
+}
+
+// ---------------------------------------------------------------------------------------
+// Merge of the per-warp records the schedule kernels emit (emit_segments, vbn_schedule.cuh): one 128-thread block per
+// query folds its records into one -- (m, l, q) for the softmax / ESS, weighted mean and M2 = sum e (x - mean)^2 by
+// the pairwise (Chan) update so no E[x^2] - E[x]^2 cancellation, class sums -- and optionally raises the batch-global
+// IS -> LW fallback flag (importance_sampling.py:85-88: any ESS below the threshold).
+//   records [B][P][16]; n_samples > 0: query b owns records 0 .. ((b+1) S - 1)/32 - b S / 32 (the kernel's geometry);
+//   n_samples == 0: all P records are valid (cross-rank merge of all-gathered merged records).
+//   merged [B][16] = {m, l, q, mean, 0, M2, rows, ess, class sums[8]} (a valid record itself: x0 = mean, sx = 0);
+//   stats [B][3] = {m, l, q} for vbn_weights_normalize (either output may be NULL).
+// ---------------------------------------------------------------------------------------
+struct SegAcc {
+  float m, l, q, mean, m2, n;
+  float h[8];
+};
+__device__ __forceinline__ void seg_merge(SegAcc& a, const SegAcc& b) {
+  if (b.n == 0.0f) return;
+  if (a.n == 0.0f) { a = b; return; }
+  const float m = fmaxf(a.m, b.m);
+  const float sa = a.m > -CUDART_INF_F ? __expf(a.m - m) : 0.0f, sb = b.m > -CUDART_INF_F ? __expf(b.m - m) : 0.0f;
+  const float la = a.l * sa, lb = b.l * sb, l = la + lb;
+  const float d = b.mean - a.mean;
+  const float fb = l > 0.0f ? __fdiv_rn(lb, l) : 0.0f;
+  a.mean = fmaf(d, fb, a.mean);
+  a.m2 = a.m2 * sa + b.m2 * sb + d * d * la * fb;
+  a.q = a.q * sa * sa + b.q * sb * sb;
+  a.l = l;
+  a.m = m;
+  a.n += b.n;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a.h[k] = a.h[k] * sa + b.h[k] * sb;
+}
+__device__ __forceinline__ SegAcc seg_shfl(const SegAcc& a, int o) {
+  SegAcc r;
+  r.m = __shfl_xor_sync(0xffffffffu, a.m, o);
+  r.l = __shfl_xor_sync(0xffffffffu, a.l, o);
+  r.q = __shfl_xor_sync(0xffffffffu, a.q, o);
+  r.mean = __shfl_xor_sync(0xffffffffu, a.mean, o);
+  r.m2 = __shfl_xor_sync(0xffffffffu, a.m2, o);
+  r.n = __shfl_xor_sync(0xffffffffu, a.n, o);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) r.h[k] = __shfl_xor_sync(0xffffffffu, a.h[k], o);
+  return r;
+}
+__global__ void __launch_bounds__(128) segment_merge_kernel(const float* __restrict__ records, int64_t n_samples,
+                                                            int n_per_query, float ess_threshold,
+                                                            float* __restrict__ merged, float* __restrict__ stats,
+                                                            int32_t* __restrict__ flag) {
+  const int64_t b = blockIdx.x;
+  int count = n_per_query;
+  if (n_samples > 0) count = static_cast<int>((((b + 1) * n_samples - 1) >> 5) - ((b * n_samples) >> 5) + 1);
+  SegAcc acc;
+  acc.m = -CUDART_INF_F; acc.l = acc.q = acc.mean = acc.m2 = acc.n = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc.h[k] = 0.0f;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    const float4* r = reinterpret_cast<const float4*>(records + (b * n_per_query + i) * 16);
+    const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3);
+    SegAcc s;
+    s.m = r0.x; s.l = r0.y; s.q = r0.z; s.n = r1.z;
+    // record -> (mean, M2): mean = x0 + sx / l, M2 = sxx - sx^2 / l
+    const float inv = s.l > 0.0f ? __fdiv_rn(1.0f, s.l) : 0.0f;
+    s.mean = fmaf(r1.x, inv, r0.w);
+    s.m2 = fmaxf(r1.y - r1.x * r1.x * inv, 0.0f);
+    s.h[0] = r2.x; s.h[1] = r2.y; s.h[2] = r2.z; s.h[3] = r2.w; s.h[4] = r3.x; s.h[5] = r3.y; s.h[6] = r3.z; s.h[7] = r3.w;
+    seg_merge(acc, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const SegAcc other = seg_shfl(acc, o);
+    seg_merge(acc, other);
+  }
+  __shared__ SegAcc sh[4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) sh[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 4; ++w) seg_merge(acc, sh[w]);
+    // a query whose log-weights are all -inf has l = q = 0: ESS = 0/0 = NaN and NaN weights, like torch.softmax of
+    // such a row (and NaN < threshold is false: no fallback, importance_sampling.py:85)
+    const float ess = __fdiv_rn(acc.l * acc.l, acc.q);
+    if (merged) {
+      float4* o = reinterpret_cast<float4*>(merged + b * 16);
+      o[0] = make_float4(acc.m, acc.l, acc.q, acc.mean);
+      o[1] = make_float4(0.0f, acc.m2, acc.n, ess);
+      o[2] = make_float4(acc.h[0], acc.h[1], acc.h[2], acc.h[3]);
+      o[3] = make_float4(acc.h[4], acc.h[5], acc.h[6], acc.h[7]);
+    }
+    if (stats) {
+      stats[b * 3 + 0] = acc.m;
+      stats[b * 3 + 1] = acc.l;
+      stats[b * 3 + 2] = acc.q;
+    }
+    if (flag && ess_threshold > 0.0f && ess < ess_threshold) atomicOr(flag, 1);
+  }
 }
 
 __global__ void __launch_bounds__(256) weights_normalize_kernel(

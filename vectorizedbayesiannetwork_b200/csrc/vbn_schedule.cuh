@@ -38,6 +38,11 @@ struct ScheduleArgs {
   int32_t* error_flag;
   const int2* tc_list;  // tensor-core kernel only: per tc op {image float offset, image bytes}
   int32_t n_tc;
+  // fused weight reduction (emit_segments): per-warp partial records [n_queries][seg_per_query][kSegWords]
+  float* seg;
+  int32_t seg_per_query;
+  int32_t seg_slot;     // slot of the value whose weighted moments are accumulated (D = 1), -1: log-weights only
+  int32_t seg_classes;  // 1..8: also the weighted class histogram of that value (classes coded 0..k-1)
   uint32_t rk[20];      // Philox round keys: rk[2i] = key0 + i*0x9E3779B9, rk[2i+1] = key1 + i*0xBB67AE85
 };
 
@@ -1406,6 +1411,91 @@ __device__ __forceinline__ void op_select(Ctx<RPT, NT, TC>& c, const VbnOp& op) 
 }
 
 // ---------------------------------------------------------------------------------------
+// Fused weight reduction (replaces the first pass of torch.softmax(log_weights, 1) -- importance_sampling.py:82-84,
+// likelihood_weighting.py:75-80 -- and, when a value slot is given, the sums behind VBN._posterior_stats,
+// vbn/vbn.py:495-503, and the benchmark adapter's class histogram, benchmarking/models/vbn.py:202-242).
+// The 32 lanes of a warp hold 32 consecutive rows; every run of rows of one query inside them becomes one record
+//   [0] m = max logw   [1] l = sum e   [2] q = sum e^2   [3] x0   [4] sum e (x - x0)   [5] sum e (x - x0)^2
+//   [6] rows   [7] -   [8..15] sum e [x == k]          with e = exp(logw - m)
+// at seg[(b * seg_per_query + (r / 32 - b S / 32)) * kSegWords]; vbn_segment_merge folds a query's records.
+// ---------------------------------------------------------------------------------------
+constexpr int kSegWords = 16;
+
+template <int RPT, int NT, class TC>
+__device__ __forceinline__ void emit_segments(Ctx<RPT, NT, TC>& c) {
+  const ScheduleArgs& a = c.a;
+  const bool moments = a.seg_slot >= 0;
+  const int classes = a.seg_classes;
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    const float lw = c.rows.logw[j];
+    const float x = moments ? c.slot(a.seg_slot, j) : 0.0f;
+    const int64_t b = c.rows.lb[j];
+    const int64_t seg_index = (c.rows.r[j] >> 5) - ((b * a.n_samples) >> 5);
+    float* rec = a.seg + (b * a.seg_per_query + seg_index) * kSegWords;
+#ifdef VBN_HOST_EMU
+    // host emulation: threads run one after another, so each row is merged into its (zero-initialised) record
+    if (!c.rows.valid[j]) continue;
+    if (rec[6] == 0.0f) {
+      rec[0] = lw; rec[1] = lw > -CUDART_INF_F ? 1.0f : 0.0f; rec[2] = rec[1]; rec[3] = x; rec[4] = 0.0f; rec[5] = 0.0f;
+      for (int k = 0; k < 8; ++k) rec[8 + k] = (k < classes && x == static_cast<float>(k)) ? rec[1] : 0.0f;
+    } else {
+      const float m = fmaxf(rec[0], lw);
+      const float so = rec[0] > -CUDART_INF_F ? expf(rec[0] - m) : 0.0f, e = lw > -CUDART_INF_F ? expf(lw - m) : 0.0f;
+      const float dx = x - rec[3];
+      rec[0] = m; rec[1] = rec[1] * so + e; rec[2] = rec[2] * so * so + e * e;
+      rec[4] = rec[4] * so + e * dx; rec[5] = rec[5] * so + e * dx * dx;
+      for (int k = 0; k < classes; ++k) rec[8 + k] = rec[8 + k] * so + (x == static_cast<float>(k) ? e : 0.0f);
+    }
+    rec[6] += 1.0f;
+#else
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    unsigned todo = __ballot_sync(full, c.rows.valid[j]);
+    while (todo) {  // one pass per query present among the warp's rows (one, unless S is small or a query ends here)
+      const int leader = __ffs(todo) - 1;
+      const int64_t b0 = __shfl_sync(full, b, leader);
+      const bool mine = c.rows.valid[j] && b == b0;
+      todo &= ~__ballot_sync(full, mine);
+      float m = mine ? lw : -CUDART_INF_F;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(full, m, o));
+      const float e = (mine && lw > -CUDART_INF_F) ? __expf(lw - m) : 0.0f;
+      const float x0 = __shfl_sync(full, x, leader);
+      const float dx = x - x0;
+      float l = e, q = e * e, sx = e * dx, sxx = e * dx * dx, n = mine ? 1.0f : 0.0f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        l += __shfl_xor_sync(full, l, o);
+        q += __shfl_xor_sync(full, q, o);
+        n += __shfl_xor_sync(full, n, o);
+      }
+      if (moments) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          sx += __shfl_xor_sync(full, sx, o);
+          sxx += __shfl_xor_sync(full, sxx, o);
+        }
+      }
+      float h = 0.0f;  // lane k ends up with class k's sum
+      for (int k = 0; k < classes; ++k) {
+        float hk = (x == static_cast<float>(k)) ? e : 0.0f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) hk += __shfl_xor_sync(full, hk, o);
+        if (lane == k) h = hk;
+      }
+      float* r0 = reinterpret_cast<float*>(__shfl_sync(full, reinterpret_cast<unsigned long long>(rec), leader));
+      if (lane == leader) {
+        reinterpret_cast<float4*>(r0)[0] = make_float4(m, l, q, x0);
+        reinterpret_cast<float4*>(r0)[1] = make_float4(sx, sxx, n, 0.0f);
+      }
+      if (lane < 8) r0[8 + lane] = h;
+    }
+#endif
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // binds row j of the thread to local row index r (clamped into range; `valid` masks the stores)
 template <class C>
 __device__ __forceinline__ void bind_row(C& c, int j, int64_t r) {
@@ -1575,6 +1665,7 @@ __device__ __forceinline__ void run_ops(Ctx<RPT, NT, TC>& c) {
     for (int j = 0; j < RPT; ++j)
       if (c.rows.valid[j]) a.logp[c.rows.r[j]] = a.logp_as_pdf ? expf(c.rows.logp[j]) : c.rows.logp[j];
   }
+  if (a.seg) emit_segments(c);
 }
 
 template <int RPT, int NT, bool HEAVY, int MIN_BLOCKS>

@@ -67,15 +67,17 @@ class Shard:
 
 
 def gather_stats(stats: torch.Tensor, shard: Shard) -> torch.Tensor:
-    """All-gather per-rank (m, l, q) triples: [B,3] -> [B, world, 3].  Payload is B*12 bytes per
-    rank -- latency bound on NVLink; the merge itself is the CUDA kernel vbn_lse_merge."""
+    """All-gather per-rank per-query records ([B, k]: (m, l, q) triples or the 16-float merged records of
+    vbn_segment_merge) -> [B, world, k].  Payload is 4 k B bytes per rank -- latency bound on NVLink: one collective
+    into one preallocated tensor; the merge itself is a CUDA kernel (vbn_segment_merge / vbn_lse_merge)."""
     if shard.world == 1:
         return stats.unsqueeze(1)
     import torch.distributed as dist
 
-    parts = [torch.empty_like(stats) for _ in range(shard.world)]
-    dist.all_gather(parts, stats.contiguous(), group=shard.group)
-    return torch.stack(parts, dim=1).contiguous()
+    b = stats.shape[0]
+    out = torch.empty((shard.world * b,) + tuple(stats.shape[1:]), device=stats.device, dtype=stats.dtype)
+    dist.all_gather_into_tensor(out, stats.contiguous(), group=shard.group)  # rank-major concatenation along dim 0
+    return out.view((shard.world, b) + tuple(stats.shape[1:])).transpose(0, 1).contiguous()
 
 
 def auto_shard(n_queries: int, rank: int, world: int, group=None) -> Optional[Shard]:

@@ -74,6 +74,7 @@ class DevicePlan:
             handle = C.c_void_p()
             L.check(self.lib.vbn_plan_create(C.byref(desc), C.byref(handle)))
             self.handle = handle
+            self._tables: Dict[tuple, torch.Tensor] = {}
 
     def __del__(self):
         try:
@@ -105,15 +106,23 @@ class DevicePlan:
             noise: Sequence[Dict[str, torch.Tensor]] = (), logw: Optional[torch.Tensor] = None,
             logp: Optional[torch.Tensor] = None, logp_as_pdf: bool = False, seed: int = 0,
             call_offset: int = 0, query_offset: int = 0, sample_offset: int = 0,
-            error_flag: Optional[torch.Tensor] = None, logw_accumulate: bool = False) -> None:
+            error_flag: Optional[torch.Tensor] = None, logw_accumulate: bool = False,
+            seg: Optional[torch.Tensor] = None, seg_slot: int = -1, seg_classes: int = 0) -> None:
+        """``seg``: [B, P, 16] float32 record buffer (zero-filled, P >= ceil(S/32) + 1) -> the kernel also emits the
+        per-warp partial records of the fused weight reduction (VbnRunDesc.seg_dev); with it the log-weight buffer is
+        optional."""
         p = self.program
         n_rows = int(n_queries) * int(n_samples)
         if len(inputs) != len(p.inputs) or len(stores) != len(p.stores) or len(noise) != len(p.noise):
             raise ValueError("inputs/stores/noise do not match the compiled schedule")
         if p.n_fixed_cols and (fixed is None or tuple(fixed.shape) != (p.n_fixed_cols, n_queries)):
             raise ValueError(f"fixed table must be [{p.n_fixed_cols}, {n_queries}]")
-        if p.needs_logw and logw is None:
+        if p.needs_logw and logw is None and seg is None:
             raise ValueError("schedule accumulates log-weights: logw buffer required")
+        if seg is not None and (seg.dtype != torch.float32 or seg.dim() != 3 or seg.shape[0] != n_queries
+                                or seg.shape[1] < (int(n_samples) + 31) // 32 + 1 or seg.shape[2] != 16
+                                or not seg.is_contiguous()):
+            raise ValueError("seg must be a contiguous float32 [B, >= ceil(S/32)+1, 16] tensor")
         if p.needs_logp and logp is None:
             raise ValueError("schedule evaluates a density: logp buffer required")
         rows: List[List[int]] = []
@@ -134,7 +143,16 @@ class DevicePlan:
                     ent.append(t.data_ptr())
             rows.append(ent)
         with torch.cuda.device(self.device):
-            table = torch.tensor(rows if rows else [[0, 0, 0]], dtype=torch.int64).to(self.device)
+            # The view table (pointers + strides of this call's tensors) lives on the device.  The caching allocator
+            # hands a steady-state caller the same blocks call after call, so the table of a few recent calls is kept:
+            # no pageable host->device copy on the per-call path (it is immutable once uploaded).
+            key = tuple(tuple(r) for r in rows)
+            table = self._tables.get(key)
+            if table is None:
+                table = torch.tensor(rows if rows else [[0, 0, 0]], dtype=torch.int64).to(self.device)
+                if len(self._tables) >= 16:
+                    self._tables.pop(next(iter(self._tables)))
+                self._tables[key] = table
             base = table.data_ptr()
             n_in, n_st = len(inputs), len(stores)
             run = L.RunDesc(
@@ -149,6 +167,9 @@ class DevicePlan:
                 logp_dev=logp.data_ptr() if logp is not None else None,
                 logp_as_pdf=1 if logp_as_pdf else 0, logw_accumulate=1 if logw_accumulate else 0,
                 error_flag_dev=error_flag.data_ptr() if error_flag is not None else None,
+                seg_dev=seg.data_ptr() if seg is not None else None,
+                seg_per_query=int(seg.shape[1]) if seg is not None else 0,
+                seg_slot=int(seg_slot), seg_classes=int(seg_classes),
             )
             events = KERNEL_EVENTS
             if events is not None:  # bench.py: CUDA events on the launching stream around the kernel
@@ -208,6 +229,30 @@ def lse_stats(logw: torch.Tensor) -> torch.Tensor:
         L.check(lib.vbn_lse_merge(partials.data_ptr(), b, split, stats.data_ptr(), sp))
         L.count_launch(2)
     return stats
+
+
+def segment_records(n_queries: int, n_samples: int, device) -> torch.Tensor:
+    """Record buffer for DevicePlan.run(seg=...): [B, ceil(S/32) + 1, 16].  The CUDA kernels write every record the
+    merge reads; the host-emulation test build accumulates row by row and needs it zero-filled."""
+    alloc = torch.zeros if torch.device(device).type == "cpu" else torch.empty
+    return alloc(int(n_queries), (int(n_samples) + 31) // 32 + 1, 16, device=device, dtype=torch.float32)
+
+
+def segment_merge(records: torch.Tensor, n_samples: int, *, ess_threshold: float = 0.0, want_flag: bool = False):
+    """Folds per-warp (n_samples > 0) or per-rank (n_samples == 0) records: returns (merged [B,16], stats [B,3],
+    flag int32[1] or None).  merged = {m, l, q, mean, 0, M2, rows, ess, class sums[8]} (vbn_segment_merge)."""
+    lib = L.load()
+    dev = records.device
+    b, p, _ = records.shape
+    with torch.cuda.device(dev):
+        merged = torch.empty(b, 16, device=dev, dtype=torch.float32)
+        stats = torch.empty(b, 3, device=dev, dtype=torch.float32)
+        flag = torch.zeros(1, device=dev, dtype=torch.int32) if want_flag else None
+        L.check(lib.vbn_segment_merge(records.data_ptr(), b, int(n_samples), p, float(ess_threshold),
+                                      merged.data_ptr(), stats.data_ptr(),
+                                      flag.data_ptr() if flag is not None else None, _stream_ptr(dev)))
+        L.count_launch(1)
+    return merged, stats, flag
 
 
 def merge_stats(gathered: torch.Tensor) -> torch.Tensor:

@@ -49,11 +49,12 @@ class _ScheduleRunner:
         self._cache: Dict[tuple, E.DevicePlan] = {}
 
     def plan_for(self, vbn, query: Query, mode: str, *, inject=frozenset(), store_all=False,
-                 only=None) -> E.DevicePlan:
+                 only=None, summary: bool = False) -> E.DevicePlan:
         cpds = model_cpds(vbn)
         fp = tuple((c._uid, c._version) for c in cpds.values())
         key = (fp, mode, query.target, tuple(sorted(query.evidence)), tuple(sorted(query.do)),
-               tuple(sorted(inject)), bool(store_all), None if only is None else tuple(only), str(vbn.device))
+               tuple(sorted(inject)), bool(store_all), None if only is None else tuple(only), str(vbn.device),
+               bool(summary))
         plan = self._cache.get(key)
         if plan is not None:
             return plan
@@ -72,7 +73,7 @@ class _ScheduleRunner:
             else:
                 shared = mode != "is" and len(parents[n]) == 0 and mode != "mcm_fast"
                 r = Role(src="sample", shared=shared, inject=n in inject)
-            if n == query.target or store_all:
+            if (n == query.target and not summary) or store_all:
                 r.store = True
             if mode == "rb" and n == query.target:
                 r = Role(src="sample", store=True, out_params=True)
@@ -81,7 +82,8 @@ class _ScheduleRunner:
             t = roles[query.target]
             t.out_logp = True
             t.density = True
-        prog = compile_schedule(topo, parents, cpds, roles, table_fn=E.discrete_table_fn)
+        prog = compile_schedule(topo, parents, cpds, roles, table_fn=E.discrete_table_fn,
+                                keep_live=query.target if summary else None)
         plan = E.DevicePlan(prog, vbn.device)
         if len(self._cache) > 64:
             self._cache.clear()
@@ -109,11 +111,15 @@ class _ScheduleRunner:
 
     def forward(self, vbn, query: Query, n_samples: int, mode: str, *, noise=None, seed=None,
                 shard: Optional[Shard] = None, clamp_obs: bool = False, store_all: bool = False,
-                only=None, n_queries: Optional[int] = None):
-        """Runs one pass.  Returns dict(logw, logp, stores={node: [B,S,D]}, plan, b, s)."""
+                only=None, n_queries: Optional[int] = None, summary: bool = False, classes: int = 0):
+        """Runs one pass.  Returns dict(logw, logp, stores={node: [B,S,D]}, seg, plan, b, s).
+        Weighted passes (``lw`` / ``is``) also emit the per-warp records of the fused weight reduction (``seg``);
+        ``summary``: the target is not stored and no log-weight buffer exists -- its weighted moments (and, with
+        ``classes`` in 1..8, its class histogram) are accumulated into the records instead."""
         dev = _check_model(vbn)
         noise = noise or {}
-        plan = self.plan_for(vbn, query, mode, inject=frozenset(noise), store_all=store_all, only=only)
+        plan = self.plan_for(vbn, query, mode, inject=frozenset(noise), store_all=store_all, only=only,
+                             summary=summary)
         prog = plan.program
         b_full = infer_batch_size(query.evidence, query.do) if n_queries is None else n_queries
         b, s, q_off, s_off = b_full, int(n_samples), 0, 0
@@ -123,8 +129,9 @@ class _ScheduleRunner:
         with torch.cuda.device(dev):
             fixed = self.fixed_table(plan, query, b, clamp_obs=clamp_obs, shard=shard)
             stores = {n: torch.empty(b, s, prog.store_widths[n], device=dev, dtype=torch.float32) for n in prog.stores}
-            logw = torch.empty(b, s, device=dev, dtype=torch.float32) if prog.needs_logw else None
+            logw = torch.empty(b, s, device=dev, dtype=torch.float32) if prog.needs_logw and not summary else None
             logp = torch.empty(b, s, device=dev, dtype=torch.float32) if prog.needs_logp else None
+            seg = E.segment_records(b, s, dev) if mode in ("lw", "is", "rb") else None
             # the device error flag is only ever raised by discrete ops (softmax_nn classes, table supports)
             needs_flag = getattr(prog, "_needs_flag", None)
             if needs_flag is None:
@@ -134,8 +141,10 @@ class _ScheduleRunner:
                      noise=[noise[n] for n in prog.noise], logw=logw, logp=logp,
                      logp_as_pdf=mode in ("mcm", "mcm_fast"),
                      seed=E.draw_seed() if seed is None else seed,
-                     query_offset=q_off, sample_offset=s_off, error_flag=flag)
-        return {"logw": logw, "logp": logp, "stores": stores, "plan": plan, "b": b, "s": s, "flag": flag}
+                     query_offset=q_off, sample_offset=s_off, error_flag=flag,
+                     seg=seg, seg_slot=prog.keep_slot if summary else -1, seg_classes=classes if summary else 0)
+        return {"logw": logw, "logp": logp, "stores": stores, "plan": plan, "b": b, "s": s, "flag": flag, "seg": seg,
+                "dev": dev}
 
 
 def _flag_message(cpds) -> str:
@@ -155,19 +164,59 @@ def _raise_if_flagged(vbn, out) -> None:
         raise ValueError(_flag_message(model_cpds(vbn).values()))
 
 
-def _weights(out, *, normalize=True, eps=1e-12, shard: Optional[Shard] = None):
+def _reduce(out, *, shard: Optional[Shard] = None, ess_threshold: float = 0.0):
+    """Per-query reduction of a weighted pass from the records the kernel emitted: returns (merged [B,16], stats
+    [B,3], flag or None) -- see engine.segment_merge.  With the samples sharded over ranks the per-rank merged records
+    are all-gathered (64 B per query) and folded once more; the fallback flag is raised from the GLOBAL ESS."""
+    sharded = shard is not None and shard.kind == "samples" and shard.world > 1
+    want_flag = ess_threshold > 0.0
+    merged, stats, flag = E.segment_merge(out["seg"], out["s"], ess_threshold=0.0 if sharded else ess_threshold,
+                                          want_flag=want_flag and not sharded)
+    if sharded:
+        merged, stats, flag = E.segment_merge(gather_stats(merged, shard), 0, ess_threshold=ess_threshold,
+                                              want_flag=want_flag)
+    return merged, stats, flag
+
+
+def _weights(out, *, normalize=True, eps=1e-12, shard: Optional[Shard] = None, ess_threshold: float = 0.0):
     """softmax over samples (+ESS) from a pass's log-weights; merges across ranks when the
-    samples are sharded."""
+    samples are sharded.  Returns (w, ess, stats, flag)."""
     b, s = out["b"], out["s"]
     logw = out["logw"]
     if logw is None:  # no evidence with a density: uniform weights, like softmax of zeros
-        dev = next(iter(out["stores"].values())).device
-        logw = torch.zeros(b, s, device=dev, dtype=torch.float32)
-    stats = E.lse_stats(logw)
-    if shard is not None and shard.kind == "samples" and shard.world > 1:
-        stats = E.merge_stats(gather_stats(stats, shard))
-    w, ess = E.normalize_weights(logw, stats, normalize=normalize, eps=eps)
-    return w, ess, stats
+        logw = torch.zeros(b, s, device=out["dev"], dtype=torch.float32)
+    merged, stats, flag = _reduce(out, shard=shard, ess_threshold=ess_threshold)
+    w, _ = E.normalize_weights(logw, stats, normalize=normalize, eps=eps, want_ess=False)
+    return w, merged[:, 7], stats, flag
+
+
+def _summary(merged: torch.Tensor, classes: int = 0) -> Dict[str, torch.Tensor]:
+    """VBN._posterior_stats (vbn/vbn.py:495-504) of a one-dimensional target from a merged record: weighted mean,
+    std = sqrt(sum w (x - mean)^2), ESS = 1 / sum w^2; ``probs`` [B, classes] when a class histogram was asked for
+    (benchmarking/models/vbn.py:202-242)."""
+    l = merged[:, 1].clamp_min(1e-30)
+    out = {"mean": merged[:, 3:4], "std": (merged[:, 5:6] / l.unsqueeze(1)).clamp_min(0.0).sqrt(), "ess": merged[:, 7]}
+    if classes:
+        out["probs"] = merged[:, 8:8 + classes] / l.unsqueeze(1)
+    return out
+
+
+def _summary_args(vbn, query: Query, kwargs):
+    """(fused?, classes) for ``summary=True``: the kernel-side accumulation covers one-dimensional targets and up to 8
+    classes; anything else is summarised from the materialised tensors (still on the device)."""
+    want = kwargs.get("summary")
+    if not want:
+        return False, 0
+    classes = int(want.get("classes", 0)) if isinstance(want, dict) else 0
+    cpd = model_cpds(vbn)[query.target]
+    return int(cpd.output_dim) == 1 and 0 <= classes <= 8 and not kwargs.get("noise"), classes
+
+
+def _summary_from_tensors(w: torch.Tensor, samples: torch.Tensor, classes: int) -> Dict[str, torch.Tensor]:
+    st = E.posterior_stats(w, samples)
+    if classes:
+        st["probs"] = E.weighted_histogram(samples, w, classes)
+    return st
 
 
 @register_inference("likelihood_weighting")
@@ -186,10 +235,16 @@ class LikelihoodWeighting:
         normalize = bool(kwargs.get("normalize", self.normalize))
         eps = float(kwargs.get("eps", self.eps))
         shard = kwargs.get("shard")
+        fused, classes = _summary_args(vbn, query, kwargs)
         out = self._runner.forward(vbn, query, n_samples, "lw", noise=kwargs.get("noise"),
-                                   seed=kwargs.get("seed"), shard=shard, clamp_obs=True)
+                                   seed=kwargs.get("seed"), shard=shard, clamp_obs=True, summary=fused,
+                                   classes=classes)
         _raise_if_flagged(vbn, out)
-        w, _, _ = _weights(out, normalize=normalize, eps=eps, shard=shard)
+        if fused:  # summary=True: per-query posterior summary, nothing of size [B, S] is materialised
+            return _summary(_reduce(out, shard=shard)[0], classes)
+        w, _, _, _ = _weights(out, normalize=normalize, eps=eps, shard=shard)
+        if kwargs.get("summary"):
+            return _summary_from_tensors(w, out["stores"][query.target], classes)
         return w, out["stores"][query.target]
 
 
@@ -212,21 +267,30 @@ class ImportanceSampling:
         shard = kwargs.get("shard")
         noise = kwargs.get("noise") or {}
         seed = kwargs.get("seed")
-        out = self._runner.forward(vbn, query, n_samples, "is", noise=noise.get("is"), seed=seed, shard=shard)
+        fused, classes = _summary_args(vbn, query, kwargs)
+        out = self._runner.forward(vbn, query, n_samples, "is", noise=noise.get("is"), seed=seed, shard=shard,
+                                   summary=fused, classes=classes)
         _raise_if_flagged(vbn, out)
-        w, ess, stats = _weights(out, shard=shard)
-        self._last_ess = ess
         threshold = max(1.0, self.ess_threshold * float(n_samples))
-        flag = E.ess_below(stats, threshold)
+        # the softmax statistics, the ESS and the fallback test any(ESS < threshold) come out of ONE merge launch
+        merged, stats, flag = _reduce(out, shard=shard, ess_threshold=threshold)
+        self._last_ess = merged[:, 7]
         if shard is not None and shard.kind == "queries" and shard.world > 1:
             flag = shard.any_flag(flag)  # the fallback is batch-global (importance_sampling.py:85-88)
-        if int(flag.item()) != 0:
+        if int(flag.item()) != 0:  # the one device -> host read of the pass
             self._last_fallback = True
-            lw_kwargs = {"n_samples": n_samples, "shard": shard, "noise": noise.get("lw")}
+            lw_kwargs = {"n_samples": n_samples, "shard": shard, "noise": noise.get("lw"),
+                         "summary": kwargs.get("summary")}
             if seed is not None:
                 lw_kwargs["seed"] = seed + 1
             return self._lw.infer_posterior(vbn, query, **lw_kwargs)
         self._last_fallback = False
+        if fused:
+            return _summary(merged, classes)
+        logw = out["logw"] if out["logw"] is not None else torch.zeros(out["b"], out["s"], device=out["dev"])
+        w, _ = E.normalize_weights(logw, stats, want_ess=False)
+        if kwargs.get("summary"):
+            return _summary_from_tensors(w, out["stores"][query.target], classes)
         return w, out["stores"][query.target]
 
 
@@ -490,7 +554,7 @@ class RaoBlackwellizedMarginalization(object):
                                    seed=kwargs.get("seed"),
                                    clamp_obs=True, only=only)
         _raise_if_flagged(vbn, out)
-        w, _, _ = _weights(out)
+        w, _, _, _ = _weights(out)
         params = out["stores"][target]  # [B, S, width] parameter read-out of the target per particle
         lib = L.load()
         with torch.cuda.device(dev):

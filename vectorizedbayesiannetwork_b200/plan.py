@@ -55,6 +55,7 @@ class Program:
     tc: bool = False                       # ops carry tensor-core MLP images -> tcgen05 kernel
     tc_list: Optional[np.ndarray] = None   # [n_tc, 2] int32 {image float offset, image bytes}, op order
     store_widths: Dict[str, int] = field(default_factory=dict)  # floats per row of each store (dims, or read-out width)
+    keep_slot: int = -1                    # slot of the node kept live to the end of the walk (fused summaries), -1 none
 
 
 def tensor_cores_enabled() -> bool:
@@ -110,10 +111,13 @@ def _tab_plain_fields(pk: Packed, slots: Sequence[int], param_off: int, out_slot
 
 
 def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpds: Dict[str, BaseCPD],
-                     roles: Dict[str, Role], use_tc: Optional[bool] = None, table_fn=None) -> Program:
+                     roles: Dict[str, Role], use_tc: Optional[bool] = None, table_fn=None,
+                     keep_live: Optional[str] = None) -> Program:
     """``topo``: nodes to emit, in topological order (nodes absent from ``roles`` are skipped).
     ``table_fn(cpd, x, parents) -> log_prob``: lets discrete nodes with all-discrete parents be
-    compiled into lookup tables (VBN_OP_TAB); None keeps them on the MLP path."""
+    compiled into lookup tables (VBN_OP_TAB); None keeps them on the MLP path.
+    ``keep_live``: a node whose value slot must survive to the end of the walk (the kernel's fused summary reads
+    it there: VbnRunDesc.seg_slot)."""
     if use_tc is None:
         use_tc = tensor_cores_enabled()
     any_tc = False
@@ -154,6 +158,9 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
             if p not in index:
                 raise ValueError(f"node '{n}' is evaluated but its parent '{p}' is not in the schedule")
             last_use[p] = max(last_use[p], index[n])
+
+    if keep_live is not None:
+        last_use[keep_live] = len(order)  # never released
 
     # ---- slot allocation (first fit, D consecutive slots per node) --------------------------
     occupied: List[bool] = []
@@ -390,6 +397,7 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
         needs_logp=needs_logp,
         dims=dims,
         store_widths={n: (int(cpds[n].param_width()) if roles[n].out_params else dims[n]) for n in stores},
+        keep_slot=slot_of[keep_live] if keep_live is not None else -1,
         tc=any_tc,
         tc_list=np.asarray(tc_list, dtype=np.int32).reshape(-1, 2) if any_tc else None,
     )
