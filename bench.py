@@ -149,7 +149,7 @@ class ClockSampler:
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.02)
 
     def mark(self):
         """Keep only the samples taken from now on (start of a timed region)."""
@@ -166,7 +166,7 @@ class ClockSampler:
             except Exception:
                 return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
         return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.sm_max,
-                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "NVML, 50 ms period"}
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "NVML, 20 ms period"}
 
     def stop(self):
         if self._thread is not None:
@@ -745,8 +745,8 @@ def main() -> None:
             others["cfg4"] = run_kde(d, steps=3, warmup=3, clocks=clocks)
         else:
             # strong scaling of the one path with a data-path collective: cfg2 (64 x 1M), samples sharded
-            one = run_inference("cfg2", d, steps=5, warmup=3, clocks=clocks, active_world=1)
-            many = run_inference("cfg2", d, steps=5, warmup=3, shard_kind="samples", clocks=clocks)
+            one = run_inference("cfg2", d, steps=20, warmup=3, clocks=clocks, active_world=1)
+            many = run_inference("cfg2", d, steps=20, warmup=3, shard_kind="samples", clocks=clocks)
             if rank == 0:
                 strong = {"workload": WORKLOADS["cfg2"][0], "sharding": "samples", "n_gpus": world,
                           "collective": "one all_gather of [B, 3 + moments] floats per pass (NCCL)",

@@ -53,6 +53,17 @@ def main():
                     print(f"{name:9s} {method:22s} shard={kind:8s} world={world} fallback={fb} "
                           f"{'OK' if flag.item() else 'MISMATCH'}", flush=True)
                 ok = ok and bool(flag.item())
+            # the fused summary (no [B,S] tensor): sample-sharded ranks merge their per-query records over NCCL
+            st1 = model.infer_posterior(q, seed=77, summary=True)
+            sh = V.Shard("samples", rank, world)
+            st = model.infer_posterior(q, seed=77, shard=sh, summary=True)
+            good = all(torch.allclose(st[k], st1[k], rtol=1e-4, atol=1e-5) for k in ("mean", "std", "ess"))
+            flag = torch.tensor([int(good)], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if rank == 0:
+                print(f"{name:9s} {method:22s} summary shard=samples world={world} {'OK' if flag.item() else 'MISMATCH'}",
+                      flush=True)
+            ok = ok and bool(flag.item())
     dist.destroy_process_group()
     if not ok:
         sys.exit(1)

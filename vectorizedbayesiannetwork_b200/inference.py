@@ -90,11 +90,26 @@ class _ScheduleRunner:
         self._cache[key] = plan
         return plan
 
-    @staticmethod
-    def fixed_table(plan: E.DevicePlan, query: Query, b: int, *, clamp_obs: bool, shard: Optional[Shard]):
+    def fixed_table(self, plan: E.DevicePlan, query: Query, b: int, *, clamp_obs: bool, shard: Optional[Shard]):
+        """[n_fixed_cols][B] table of the per-query evidence / do values (prepare_fixed_values, _core.py:117-135).
+        The last table is kept: a caller that repeats a query with the same (unmodified) tensors -- the steady state
+        of a serving loop -- pays no clamp / concatenate launches again."""
         prog = plan.program
         if not prog.n_fixed_cols:
             return None
+        src = [query.do[n] if n in query.do else query.evidence[n] for n in prog.fixed_cols]
+        key = (id(plan), b, bool(clamp_obs), None if shard is None else (shard.kind, shard.rank, shard.world),
+               tuple((id(v), v._version, v.data_ptr()) for v in src))
+        hit = getattr(self, "_fixed_cache", None)
+        if hit is not None and hit[0] == key:
+            return hit[2]
+        table = self._build_fixed_table(plan, query, b, clamp_obs=clamp_obs, shard=shard)
+        self._fixed_cache = (key, src, table)  # `src` keeps the ids alive
+        return table
+
+    @staticmethod
+    def _build_fixed_table(plan: E.DevicePlan, query: Query, b: int, *, clamp_obs: bool, shard: Optional[Shard]):
+        prog = plan.program
         cols = []
         for n in prog.fixed_cols:  # insertion order == op order
             v = query.do[n] if n in query.do else query.evidence[n]
@@ -434,7 +449,7 @@ class ResampledImportanceSampling:
             for k, seg in enumerate(segs):
                 plan = seg["plan"]
                 prog = plan.program
-                fixed = _ScheduleRunner.fixed_table(plan, query, b, clamp_obs=clamp_obs, shard=shard)
+                fixed = _ScheduleRunner._build_fixed_table(plan, query, b, clamp_obs=clamp_obs, shard=shard) if plan.program.n_fixed_cols else None
                 new = {n: torch.empty(prog.dims[n], rows, device=dev, dtype=torch.float32) for n in prog.stores}
                 plan.run(b, s, fixed=fixed, inputs=[live[n].t() for n in prog.inputs],
                          stores=[new[n].t() for n in prog.stores], noise=[noise[n] for n in prog.noise],
@@ -802,7 +817,7 @@ class GibbsSampler:
         plan = self._plan(vbn, query, total_steps, inject=noise is not None)
         prog = plan.program
         with torch.cuda.device(dev):
-            fixed = _ScheduleRunner.fixed_table(plan, query, b, clamp_obs=False, shard=None)
+            fixed = _ScheduleRunner._build_fixed_table(plan, query, b, clamp_obs=False, shard=None) if plan.program.n_fixed_cols else None
             out = torch.empty(b, 1, prog.dims[query.target], device=dev, dtype=torch.float32)
             flag = torch.zeros(1, device=dev, dtype=torch.int32)
             arrays = [] if noise is None else [noise[kind][node] for kind, node in prog.noise_keys]
