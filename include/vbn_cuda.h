@@ -88,12 +88,15 @@ extern "C" {
                                   renormalised pi (mdn.py:227-228); then (loc_k, scale_k) for
                                   k = 0..K-1, scale_k = softplus(raw_k) + min_scale}; tc[] =
                                   {out_slot, n_off, u_off, K}.  The kernel reads quads 0,4,5,6,7  */
-#define VBN_F_TABPLAIN 0x1000   /* TAB op that is only drawn (Philox, no store, no density), <= 4 parents, every
-                                  parent's class values and its own sample values coded 0..k-1: the class index
-                                  IS the value, so the per-parent search and the value gather disappear.
-                                  layer_dim[p] = stride_p | card_p << 16 (p < 4), layer_dim[4] = float offset of
-                                  the cdf[n_cfg][C] table in the parameter blob, layer_dim[5] = C | strict << 16,
-                                  layer_dim[6] = out_slot, layer_dim[7] = u_off; aux[0..1] = packed parent slots.
+#define VBN_F_TABPLAIN 0x1000   /* TAB op with <= 4 parents and <= 4 classes, every parent's class values and its own
+                                  coded 0..k-1 (the class index IS the value: no per-parent search, no value gather),
+                                  either only drawn (VBN_SRC_SAMPLE: Philox, no store, no density) or only scored
+                                  (VBN_SRC_FIXED_Q | VBN_F_ADD_LOGW: an evidence node).
+                                  layer_dim[p] = stride_p | card_p << 16 (p < 4); layer_dim[4] = float offset in the
+                                  parameter blob of the 128-bit-row table the op reads -- drawn: cdf4[n_cfg][4] =
+                                  {c_0 .. c_{C-2}, +inf .., total}, scored: logp4[n_cfg][4] --; layer_dim[5] =
+                                  C | strict << 16; layer_dim[6] = out_slot; layer_dim[7] = u_off (drawn) or the
+                                  fixed[][B] row (scored); aux[0..1] = packed parent slots.
                                   The kernel reads quads 0,4,5,6                                            */
 #define VBN_F_LGPLAIN 0x80     /* LGFAST op that is only drawn: Philox, per-row stream, no store,
                                   no density -- the kernel reads nothing but quads 0,4,5,6      */

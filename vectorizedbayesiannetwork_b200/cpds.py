@@ -885,7 +885,18 @@ def _tab_params(c: int, logp: torch.Tensor, parent_supports: Sequence[torch.Tens
         head.append(np.concatenate([np.array([int(sup.numel()), stride, 0, 0], np.float32), _padded(_np(sup), cpad)]))
     head += [_padded(_np(sample_values), cpad), _padded(_np(class_values), cpad), _np(cdf), _np(logp)]
     params = np.concatenate(head)
-    return _padded(params, _pad4(params.size))
+    params = _padded(params, _pad4(params.size))
+    if c <= 4:
+        # 128-bit rows for the plain table op (csrc op_tab_plain): cdf4 = {c_0 .. c_{C-2}, +inf .., total} and logp4
+        # (class k in lane k), each [n_cfg][4], behind the block (plan._tab_plain_fields derives the offsets)
+        cdf_np = cdf.detach().cpu().numpy().astype(np.float32).reshape(n_cfg, c)
+        cdf4 = np.full((n_cfg, 4), np.inf, np.float32)
+        cdf4[:, : c - 1] = cdf_np[:, : c - 1]
+        cdf4[:, 3] = cdf_np[:, c - 1]
+        logp4 = np.zeros((n_cfg, 4), np.float32)
+        logp4[:, :c] = logp.detach().cpu().numpy().astype(np.float32).reshape(n_cfg, c)
+        params = np.concatenate([params, cdf4.reshape(-1), logp4.reshape(-1)])
+    return params
 
 
 def table_eligible(cpd, parent_cpds: Sequence[BaseCPD]) -> bool:

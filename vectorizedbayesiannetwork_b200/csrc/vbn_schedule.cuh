@@ -1103,16 +1103,20 @@ __device__ __forceinline__ void op_params(Ctx<RPT, NT, TC>& c, const VbnOp& op) 
   }
 }
 
-// VBN_F_TABPLAIN: a TAB op that is simply drawn and whose parents and own classes are coded 0..k-1, so the
-// class index is the value: no per-parent search, no value gather, no parameter-block header reads.
-// Everything but the cdf rows rides in quads 0,4,5,6.  This is the inner loop of ALARM-style discrete
-// networks (BASELINE cfg3: 33 of 37 ops).
+// VBN_F_TABPLAIN: a TAB op with <= 4 parents and <= 4 classes whose parents' and own classes are coded 0..k-1, so
+// the class index IS the value: no per-parent search, no value gather, no parameter-block header reads.  Two uses:
+//   drawn   (VBN_SRC_SAMPLE, no store / density): k = #{q < C-1 : u * total >= cdf_q}    -- one 128-bit row load of
+//           the padded table cdf4[n_cfg] = {c_0, .., c_{C-2}, +inf.., total}
+//   scored  (VBN_SRC_FIXED_Q | VBN_F_ADD_LOGW: an evidence node): logw += logp4[cfg][class of the fixed value]
+// Everything else rides in quads 0,4,5,6.  The body is one short straight-line block for every parent / class
+// count (BASELINE cfg3: 37 of 37 ALARM ops): the per-count variants of the first version made the hot loop spill out
+// of the instruction cache (a quarter of the stall samples were instruction fetch).
 template <int RPT, int NT, class TC>
 __device__ __forceinline__ void op_tab_plain(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
   const int Dp = op.n_par;
   const int C = op.layer_dim[5] & 0xFFFF;
   const bool strict = (op.layer_dim[5] >> 16) != 0;
-  const float* cdf = c.a.params + op.layer_dim[4];
+  const float4* tab = reinterpret_cast<const float4*>(c.a.params + op.layer_dim[4]);
   int cfg[RPT];
 #pragma unroll
   for (int j = 0; j < RPT; ++j) cfg[j] = 0;
@@ -1124,40 +1128,37 @@ __device__ __forceinline__ void op_tab_plain(Ctx<RPT, NT, TC>& c, const VbnOp& o
 #pragma unroll
       for (int j = 0; j < RPT; ++j) {
         const float v = c.slot(ps, j);
-        int ci = __float2int_rz(v);
-        if (static_cast<float>(ci) != v || static_cast<unsigned>(ci) >= static_cast<unsigned>(card)) {
-          if (strict && c.rows.valid[j] && c.a.error_flag) atomicOr(c.a.error_flag, 1);
-          ci = 0;
-        }
-        cfg[j] += ci * stride;
+        const int ci = __float2int_rz(v);
+        const bool ok = static_cast<float>(ci) == v && static_cast<unsigned>(ci) < static_cast<unsigned>(card);
+        if (!ok && strict && c.rows.valid[j] && c.a.error_flag) atomicOr(c.a.error_flag, 1);
+        cfg[j] += (ok ? ci : 0) * stride;
       }
     }
   }
-  float uu[RPT];
-  c.cached_uniform((op.flags & VBN_F_SHARED) != 0, op.layer_dim[7], uu);
+  const int out_slot = op.layer_dim[6];
+  if ((op.flags & VBN_SRC_MASK) == VBN_SRC_SAMPLE) {
+    float uu[RPT];
+    c.cached_uniform((op.flags & VBN_F_SHARED) != 0, op.layer_dim[7], uu);
 #pragma unroll
-  for (int j = 0; j < RPT; ++j) {
-    const float* row = cdf + cfg[j] * C;
-    const float u = uu[j];
-    int k = 0;
-    // the common cardinalities get straight-line code: fixed-offset loads, no loop control
-    if (C == 2) {
-      const float c0 = __ldg(row), c1 = __ldg(row + 1);
-      k = (u * c1 >= c0) ? 1 : 0;
-    } else if (C == 3) {
-      const float c0 = __ldg(row), c1 = __ldg(row + 1), c2 = __ldg(row + 2);
-      const float t = u * c2;
-      k = ((t >= c0) ? 1 : 0) + ((t >= c1) ? 1 : 0);
-    } else if (C == 4) {
-      const float c0 = __ldg(row), c1 = __ldg(row + 1), c2 = __ldg(row + 2), c3 = __ldg(row + 3);
-      const float t = u * c3;
-      k = ((t >= c0) ? 1 : 0) + ((t >= c1) ? 1 : 0) + ((t >= c2) ? 1 : 0);
-    } else {
-      const float t = u * __ldg(row + C - 1);
-#pragma unroll 1
-      for (int qq = 0; qq < C - 1; ++qq) k += (t >= __ldg(row + qq)) ? 1 : 0;
+    for (int j = 0; j < RPT; ++j) {
+      const float4 r = __ldg(tab + cfg[j]);
+      const float t = uu[j] * r.w;
+      const int k = ((t >= r.x) ? 1 : 0) + ((t >= r.y) ? 1 : 0) + ((t >= r.z) ? 1 : 0);
+      c.slot(out_slot, j) = static_cast<float>(k);
     }
-    c.slot(op.layer_dim[6], j) = static_cast<float>(k);
+  } else {  // evidence: the per-query value is its own class index (softmax_nn.py:618-627 exact class match)
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const float x = __ldg(c.a.fixed + static_cast<int64_t>(op.layer_dim[7]) * c.a.n_queries + c.rows.lb[j]);
+      c.slot(out_slot, j) = x;
+      const int ci = __float2int_rz(x);
+      const bool ok = static_cast<float>(ci) == x && static_cast<unsigned>(ci) < static_cast<unsigned>(C);
+      if (!ok && c.rows.valid[j] && c.a.error_flag) atomicOr(c.a.error_flag, 1);
+      const float4 r = __ldg(tab + cfg[j]);
+      const int b = ok ? ci : 0;
+      const float lo = (b & 1) ? r.y : r.x, hi = (b & 1) ? r.w : r.z;
+      c.rows.logw[j] += (b & 2) ? hi : lo;
+    }
   }
 }
 
@@ -1574,12 +1575,12 @@ __device__ __forceinline__ void run_ops(Ctx<RPT, NT, TC>& c) {
       }
       // (only in the <= 2 rows-per-thread shapes, which is where schedules with table ops are placed: the
       // 4-row linear-Gaussian shapes keep their loop body small; there the op takes the generic lookup)
-      if (RPT <= 2 && (q0.y & VBN_F_TABPLAIN)) {
+      if (q0.y & VBN_F_TABPLAIN) {
         VbnOp lop;
         int4* ld = reinterpret_cast<int4*>(&lop);
         ld[0] = q0;
         ld[4] = q4;  // stride | card << 16 per parent
-        ld[5] = q5;  // cdf offset, C | strict << 16, out_slot, u_off
+        ld[5] = q5;  // table offset, C | strict << 16, out_slot, u_off (drawn) / fixed_col (scored)
         ld[6] = q6;  // packed parent slots
         c.gop = a.ops + i;
         op_tab_plain(c, lop);

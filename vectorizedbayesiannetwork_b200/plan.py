@@ -83,11 +83,14 @@ def _tabplain_enabled() -> bool:
     return os.environ.get("VBN_TABPLAIN", "1") != "0"
 
 
-def _tab_plain_fields(pk: Packed, slots: Sequence[int], param_off: int, out_slot: int, u_off: int):
-    """VBN_F_TABPLAIN descriptor words (include/vbn_cuda.h) of a table op, or None when a parent's classes or
-    the node's own values are not coded 0..k-1.  Parses the VBN_OP_TAB block (cpds._tab_params)."""
+def _tab_plain_fields(pk: Packed, slots: Sequence[int], param_off: int, out_slot: int, last_word: int, scored: bool):
+    """VBN_F_TABPLAIN descriptor words (include/vbn_cuda.h) of a table op, or None when it has more than 4 classes or
+    a parent's classes / the node's own values are not coded 0..k-1.  Parses the VBN_OP_TAB block (cpds._tab_params).
+    ``last_word``: u_off of a drawn op, fixed_col of a scored (evidence) one."""
     P = pk.params
     c, n_cfg, cpad, strict = int(P[0]), int(P[1]), int(P[2]), int(P[3] != 0)
+    if c > 4:
+        return None
     words = [0] * 12
     for p in range(pk.n_par):
         pi = 4 + (4 + cpad) * p
@@ -98,12 +101,15 @@ def _tab_plain_fields(pk: Packed, slots: Sequence[int], param_off: int, out_slot
     sv = 4 + (4 + cpad) * pk.n_par
     if not np.array_equal(P[sv: sv + c], np.arange(c, dtype=np.float32)):
         return None
-    if max(list(slots) + [out_slot]) >= 65536 or c >= 65536:
+    if scored and not np.array_equal(P[sv + cpad: sv + cpad + c], np.arange(c, dtype=np.float32)):
+        return None  # class values (what an evidence value is matched against) must be 0..k-1 too
+    if max(list(slots) + [out_slot]) >= 65536:
         return None
-    words[4] = int(param_off) + sv + 2 * cpad       # cdf[n_cfg][C]
+    tab4 = (sv + 2 * cpad + 2 * n_cfg * c + 3) & ~3          # cdf4[n_cfg][4], then logp4[n_cfg][4]
+    words[4] = int(param_off) + tab4 + (4 * n_cfg if scored else 0)
     words[5] = c | (strict << 16)
     words[6] = int(out_slot)
-    words[7] = int(u_off)
+    words[7] = int(last_word)
     sl = list(slots) + [0] * (4 - len(slots))
     words[8] = sl[0] | (sl[1] << 16)
     words[9] = sl[2] | (sl[3] << 16)
@@ -325,12 +331,15 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
                 op["aux"][:] = emb[8:].view(np.int32)
                 op["tc"][:] = [slot_of[n], int(op["n_off"]), int(op["u_off"]), pk.k]
                 flags |= L.F_MDNROOT
-            if (_tabplain_enabled() and pk.kind == L.OP_TAB and d == 1 and pk.n_par <= 4 and r.src == "sample"
-                    and not r.inject and not r.store and not r.add_logw and not r.out_logp and not r.out_params):
+            drawn_plain = (r.src == "sample" and not r.inject and not r.store and not r.add_logw and not r.out_logp)
+            scored_plain = (r.src == "fixed_q" and r.add_logw and not r.store and not r.out_logp)
+            if (_tabplain_enabled() and pk.kind == L.OP_TAB and d == 1 and pk.n_par <= 4 and not r.out_params
+                    and (drawn_plain or scored_plain)):
                 # (the tensor-core kernel has no TABPLAIN branch: there the op runs the generic lookup, which
                 # reads none of the words rewritten here)
                 emb = _tab_plain_fields(pk, par_slots[len(par_slots) - pk.n_par:] if pk.n_par else [],
-                                        param_off[id(pk)], slot_of[n], int(op["u_off"]))
+                                        param_off[id(pk)], slot_of[n],
+                                        int(op["u_off"]) if drawn_plain else int(op["fixed_col"]), scored_plain)
                 if emb is not None:
                     op["layer_dim"][:] = emb[:8]
                     op["aux"][:] = emb[8:]
