@@ -339,6 +339,22 @@ int32_t vbn_kde_log_prob(const float* train_p_dev, const float* train_y_dev, int
                          const float* query_x_dev, int64_t n_rows, float bandwidth,
                          float parent_bandwidth, float min_scale, float* out_dev, void* stream);
 
+/*
+ * The same density with the pairwise |x - y|^2 term on the tensor cores (tcgen05.mma kind::tf32, three-piece
+ * operand split = fp32-exact products, streaming logsumexp in the epilogue): pays from dp + dx ~ 8, where the
+ * FP32-pipe kernel is bound by the distance arithmetic instead of the two exponentials per pair.
+ * workspace_dev: vbn_kde_tc_workspace_bytes() bytes (the stored points re-packed as augmented K-major tiles on every
+ * call; 0 bytes = these dims are not covered, use vbn_kde_log_prob).  center_dev: dp + dx floats (parents then
+ * targets) subtracted from both clouds, normally the stored points' mean, or NULL.  The GEMM form holds numbers of
+ * size h |x - center|^2 in fp32 accumulators: rows beyond 40 (log2 units) -- and rows whose sums underflow -- are
+ * recomputed with direct differences by a scalar pass, so accuracy never depends on the data, only speed does.
+ */
+int32_t vbn_kde_tc_workspace_bytes(int64_t n_points, int32_t dp, int32_t dx, int64_t* out_bytes);
+int32_t vbn_kde_log_prob_tc(const float* train_p_dev, const float* train_y_dev, int64_t n_points, int32_t dp,
+                            int32_t dx, const float* query_p_dev, const float* query_x_dev, int64_t n_rows,
+                            float bandwidth, float parent_bandwidth, float min_scale, const float* center_dev,
+                            void* workspace_dev, float* out_dev, void* stream);
+
 /* Philox4x32-10 known-answer hook: out[i] = philox(ctr[i], key) for n counters (uint32 x4). */
 int32_t vbn_philox_fill(const uint32_t* ctr_dev, int64_t n, uint32_t key0, uint32_t key1,
                         uint32_t* out_dev, void* stream);

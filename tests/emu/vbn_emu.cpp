@@ -262,6 +262,9 @@ int32_t vbn_stream_draws(uint64_t seed, uint64_t call, int32_t kind, int32_t sha
   }
   return 0;
 }
+int32_t vbn_kde_tc_workspace_bytes(int64_t, int32_t, int32_t, int64_t* out) { *out = 0; return 0; }  // not covered here
+int32_t vbn_kde_log_prob_tc(const float*, const float*, int64_t, int32_t, int32_t, const float*, const float*, int64_t,
+                            float, float, float, const float*, void*, float*, void*) { return VBN_E_CAPACITY; }
 int32_t vbn_fma_peak(int32_t, int32_t, int32_t, float*, void*) { return 0; }
 int32_t vbn_tf32_peak(int32_t, int32_t, float*, void*) { return 0; }
 int32_t vbn_philox_fill(const uint32_t* ctr, int64_t n, uint32_t k0, uint32_t k1, uint32_t* out, void*) {

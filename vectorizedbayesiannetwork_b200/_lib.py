@@ -95,6 +95,10 @@ EXPORTS = {
                                      C.c_float, C.c_void_p, C.c_void_p]),
     "vbn_fma_peak": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "vbn_tf32_peak": (C.c_int32, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "vbn_kde_tc_workspace_bytes": (C.c_int32, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
+    "vbn_kde_log_prob_tc": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                        C.c_int64, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]),
     "vbn_philox_fill": (C.c_int32, [C.c_void_p, C.c_int64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "vbn_stream_draws": (C.c_int32, [C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                                      C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),

@@ -23,7 +23,7 @@ def sources():
     """One translation unit per kernel family (compiled in parallel): the C ABI + reduction / KDE kernels, the
     FP32-pipe schedule kernels (heavy, light 4-row, light 1-2-row shapes) and the tcgen05 schedule kernels."""
     return [os.path.join(CSRC, f) for f in ("vbn_cuda.cu", "vbn_k_heavy.cu", "vbn_k_light4.cu", "vbn_k_light2.cu",
-                                            "vbn_k_tc.cu")]
+                                            "vbn_k_tc.cu", "vbn_k_kde_tc.cu")]
 
 
 def _deps():
@@ -49,7 +49,7 @@ def _obj_stale(src: str, obj: str) -> bool:
     for f in os.listdir(CSRC):
         if not f.endswith((".cuh", ".h")):
             continue
-        if f == "vbn_schedule_tc.cuh" and name != "vbn_k_tc.cu":
+        if f == "vbn_schedule_tc.cuh" and name not in ("vbn_k_tc.cu", "vbn_k_kde_tc.cu"):
             continue  # only the tcgen05 unit includes it
         if f in ("vbn_kde.cuh", "vbn_reduce.cuh") and name != "vbn_cuda.cu":
             continue

@@ -456,6 +456,27 @@ int32_t vbn_kde_log_prob(const float* train_p_dev, const float* train_y_dev, int
              : fail(VBN_E_CUDA, "kde launch failed: %s", cudaGetErrorString(cudaGetLastError()));
 }
 
+int32_t vbn_kde_tc_workspace_bytes(int64_t n_points, int32_t dp, int32_t dx, int64_t* out_bytes) {
+  if (!out_bytes || n_points <= 0 || dx <= 0 || dp < 0) return fail(VBN_E_INVALID, "bad argument");
+  *out_bytes = vbn::kde_tc_supported(dp, dx) ? static_cast<int64_t>(vbn::kde_tc_workspace_bytes(n_points, dp, dx)) : 0;
+  return VBN_OK;
+}
+
+int32_t vbn_kde_log_prob_tc(const float* train_p_dev, const float* train_y_dev, int64_t n_points, int32_t dp,
+                            int32_t dx, const float* query_p_dev, const float* query_x_dev, int64_t n_rows,
+                            float bandwidth, float parent_bandwidth, float min_scale, const float* center_dev,
+                            void* workspace_dev, float* out_dev, void* stream) {
+  if (!train_y_dev || !query_x_dev || !out_dev || !workspace_dev || n_points <= 0 || n_rows <= 0 || dx <= 0 || dp < 0)
+    return fail(VBN_E_INVALID, "bad argument to vbn_kde_log_prob_tc");
+  if (dp > 0 && (!train_p_dev || !query_p_dev)) return fail(VBN_E_INVALID, "parent arrays required when dp > 0");
+  if (!vbn::kde_tc_supported(dp, dx)) return fail(VBN_E_CAPACITY, "dims (%d, %d) exceed the tensor-core KDE kernel", dp, dx);
+  const cudaError_t e = vbn::launch_kde_log_prob_tc(train_p_dev, train_y_dev, n_points, dp, dx, query_p_dev, query_x_dev,
+                                                    n_rows, bandwidth, parent_bandwidth, min_scale, center_dev,
+                                                    static_cast<float*>(workspace_dev), out_dev,
+                                                    static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? VBN_OK : fail(VBN_E_CUDA, "kde tensor-core launch failed: %s", cudaGetErrorString(e));
+}
+
 int32_t vbn_philox_fill(const uint32_t* ctr_dev, int64_t n, uint32_t key0, uint32_t key1,
                         uint32_t* out_dev, void* stream) {
   if (!ctr_dev || !out_dev || n <= 0) return fail(VBN_E_INVALID, "bad argument");

@@ -1124,14 +1124,19 @@ __device__ __forceinline__ void op_tab_plain(Ctx<RPT, NT, TC>& c, const VbnOp& o
   for (int p = 0; p < 4; ++p) {
     if (p < Dp) {
       const int ps = (op.aux[p >> 1] >> (16 * (p & 1))) & 0xFFFF;
-      const int stride = op.layer_dim[p] & 0xFFFF, card = op.layer_dim[p] >> 16;
+      const int stride = op.layer_dim[p] & 0xFFFF, card = (op.layer_dim[p] >> 16) & 0x7FFF;
+      if (op.layer_dim[p] < 0) {  // bit 31: the parent is drawn by a plain table op of this schedule -- always a valid index
 #pragma unroll
-      for (int j = 0; j < RPT; ++j) {
-        const float v = c.slot(ps, j);
-        const int ci = __float2int_rz(v);
-        const bool ok = static_cast<float>(ci) == v && static_cast<unsigned>(ci) < static_cast<unsigned>(card);
-        if (!ok && strict && c.rows.valid[j] && c.a.error_flag) atomicOr(c.a.error_flag, 1);
-        cfg[j] += (ok ? ci : 0) * stride;
+        for (int j = 0; j < RPT; ++j) cfg[j] += __float2int_rz(c.slot(ps, j)) * stride;
+      } else {
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+          const float v = c.slot(ps, j);
+          const int ci = __float2int_rz(v);
+          const bool ok = static_cast<float>(ci) == v && static_cast<unsigned>(ci) < static_cast<unsigned>(card);
+          if (!ok && strict && c.rows.valid[j] && c.a.error_flag) atomicOr(c.a.error_flag, 1);
+          cfg[j] += (ok ? ci : 0) * stride;
+        }
       }
     }
   }

@@ -69,7 +69,8 @@ class DevicePlan:
                 tc_list_dev=self.tc_list.data_ptr() if program.tc else None,
                 n_tc=int(program.tc_list.shape[0]) if program.tc else 0,
                 tc_image_bytes=int(program.tc_list[:, 1].max()) if program.tc else 0,
-                rows_per_thread=2 if any(int(k) == L.OP_TAB for k in program.ops["kind"]) else 0,
+                rows_per_thread=int(os.environ.get("VBN_ROWS_PER_THREAD", "0")),  # 0: 4 rows per thread (measured best
+                # for chains and, since the plain table op became one compact body, for table schedules too)
             )
             handle = C.c_void_p()
             L.check(self.lib.vbn_plan_create(C.byref(desc), C.byref(handle)))
@@ -554,6 +555,27 @@ def _kde_log_prob_bulk(cpd: KDECPD, x, parents, b: int, s: int, dev) -> torch.Te
         if parents.dim() == 2:
             parents = parents.unsqueeze(1)
         qp = parents.expand(b, s, cpd.input_dim).reshape(b * s, cpd.input_dim).contiguous()
+    # Dp + Dx >= 8: the pairwise distance term goes to the tensor cores (VBN_KDE_TC=0/1 forces either kernel)
+    want_tc = os.environ.get("VBN_KDE_TC", "1" if cpd.input_dim + cpd.output_dim >= 8 else "0") == "1"
+    if want_tc:
+        nbytes = C.c_int64(0)
+        L.check(lib.vbn_kde_tc_workspace_bytes(int(ty.shape[0]), cpd.input_dim, cpd.output_dim, C.byref(nbytes)))
+        if nbytes.value > 0:
+            with torch.cuda.device(dev):
+                ws = getattr(cpd, "_tc_workspace", None)
+                if ws is None or ws.device != dev or ws.numel() * 4 < nbytes.value:
+                    ws = cpd._tc_workspace = torch.empty((nbytes.value + 3) // 4, device=dev, dtype=torch.float32)
+                    # both clouds are centred on the stored points' mean (smaller numbers in the fp32 accumulators)
+                    parts = ([tp.mean(dim=0)] if cpd.input_dim else []) + [ty.mean(dim=0)]
+                    cpd._tc_center = torch.cat(parts).contiguous()
+                out = torch.empty(b * s, device=dev, dtype=torch.float32)
+                L.check(lib.vbn_kde_log_prob_tc(
+                    tp.data_ptr() if cpd.input_dim else None, ty.data_ptr(), int(ty.shape[0]), cpd.input_dim,
+                    cpd.output_dim, qp.data_ptr() if qp is not None else None, qx.data_ptr(), b * s,
+                    cpd.bandwidth, cpd.parent_bandwidth, cpd.min_scale, cpd._tc_center.data_ptr(), ws.data_ptr(),
+                    out.data_ptr(), _stream_ptr(dev)))
+                L.count_launch(3)
+            return out.reshape(b, s)
     with torch.cuda.device(dev):
         out = torch.empty(b * s, device=dev, dtype=torch.float32)
         L.check(lib.vbn_kde_log_prob(

@@ -83,7 +83,8 @@ def _tabplain_enabled() -> bool:
     return os.environ.get("VBN_TABPLAIN", "1") != "0"
 
 
-def _tab_plain_fields(pk: Packed, slots: Sequence[int], param_off: int, out_slot: int, last_word: int, scored: bool):
+def _tab_plain_fields(pk: Packed, slots: Sequence[int], param_off: int, out_slot: int, last_word: int, scored: bool,
+                      trusted: Sequence[bool] = ()):
     """VBN_F_TABPLAIN descriptor words (include/vbn_cuda.h) of a table op, or None when it has more than 4 classes or
     a parent's classes / the node's own values are not coded 0..k-1.  Parses the VBN_OP_TAB block (cpds._tab_params).
     ``last_word``: u_off of a drawn op, fixed_col of a scored (evidence) one."""
@@ -98,6 +99,8 @@ def _tab_plain_fields(pk: Packed, slots: Sequence[int], param_off: int, out_slot
         if stride >= 65536 or card >= 32768 or not np.array_equal(P[pi + 4: pi + 4 + card], np.arange(card, dtype=np.float32)):
             return None
         words[p] = stride | (card << 16)
+        if p < len(trusted) and trusted[p]:
+            words[p] -= 1 << 31  # bit 31 (as a signed word): value is always a valid class index, no range check
     sv = 4 + (4 + cpad) * pk.n_par
     if not np.array_equal(P[sv: sv + c], np.arange(c, dtype=np.float32)):
         return None
@@ -130,6 +133,7 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
     lg_fast_ops: List[int] = []
     tc_list: List[tuple] = []
     tc_ops: List[tuple] = []  # (op index, weight image) of every op with a tensor-core image
+    plain_drawn: set = set()  # nodes drawn by VBN_F_TABPLAIN ops
     order = [n for n in topo if n in roles]
     # Roots whose draw is shared by all queries (LW / MCM / ancestral passes) go first -- still a topological
     # order -- so that consecutive shared draws are served from one generator block (csrc cached_uniform /
@@ -339,11 +343,14 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
                 # reads none of the words rewritten here)
                 emb = _tab_plain_fields(pk, par_slots[len(par_slots) - pk.n_par:] if pk.n_par else [],
                                         param_off[id(pk)], slot_of[n],
-                                        int(op["u_off"]) if drawn_plain else int(op["fixed_col"]), scored_plain)
+                                        int(op["u_off"]) if drawn_plain else int(op["fixed_col"]), scored_plain,
+                                        trusted=[p in plain_drawn and dims[p] == 1 for p in plist])
                 if emb is not None:
                     op["layer_dim"][:] = emb[:8]
                     op["aux"][:] = emb[8:]
                     flags |= L.F_TABPLAIN
+                    if drawn_plain:
+                        plain_drawn.add(n)  # its slot always holds a class index 0..k-1 produced by the kernel itself
             if r.out_params:
                 flags |= L.F_OUT_PARAMS
                 heavy = True  # the read-out lives in the HEAVY kernels only
