@@ -248,13 +248,15 @@ def test_ragged_row_counts_cover_tile_tails(backend):
 
 
 def test_registry_install_is_a_drop_in_for_the_reference(backend):
-    import refmodels
+    """The live drop-in: the UNMODIFIED reference package (baseline/_ref on the GPU box, /root/reference in the build
+    container), its own VBN facade and CPD modules on ``backend.device``, with this library's classes swapped into
+    its registries."""
+    from oracle import reference_arm as R
 
-    if not refmodels.have_reference():
-        pytest.skip("/root/reference not present")
-    vbn = refmodels.import_reference()
-    ref = refmodels.lg_chain_model(n_nodes=4, rows=256)
-    ref.device = backend.device  # the CUDA classes read vbn.device for placement
+    vbn = R.load_reference()
+    if vbn is None:
+        pytest.skip("reference package not present (baseline/_ref, /root/reference)")
+    ref = R.reference_from_spec(S.lg_chain(4), device=backend.device)
     V.install(vbn)
     try:
         assert vbn.core.registry.INFERENCE_REGISTRY["importance_sampling"] is V.ImportanceSampling

@@ -9,7 +9,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-R = sys.argv[1] if len(sys.argv) > 1 else "r01"
+R = sys.argv[1] if len(sys.argv) > 1 else "r02"
 OUT = os.path.join(ROOT, "profiles")
 GP = os.path.join(ROOT, "gpurun_out")
 KEYS = [
@@ -77,6 +77,11 @@ for w in ("cfg5", "cfg2", "cfg3", "cfg4"):
                 db = to_bytes(vals[hdr.index("dram__bytes_read.sum")], units[hdr.index("dram__bytes_read.sum")]) + \
                     to_bytes(vals[hdr.index("dram__bytes_write.sum")], units[hdr.index("dram__bytes_write.sum")])
                 traffic[w] = {"rows": int(rows_launch), "dram_bytes": db, "file": f"profiles/{R}_ncu_{w}.txt"}
+                ia = "smsp__issue_active.avg.pct_of_peak_sustained_active"
+                if ia in hdr:
+                    traffic[w]["issue_active_pct"] = round(float(vals[hdr.index(ia)]), 2)
+                    traffic[w]["inst_per_row"] = round(
+                        float(vals[hdr.index("smsp__inst_executed.sum")].replace(",", "")) * 32 / int(rows_launch), 1)
                 lines.append(f"rows in the captured launch = {rows_launch}; dram bytes read+write = {db:.0f}")
             except Exception as exc:  # noqa: BLE001
                 lines.append(f"(traffic not derived: {exc})")

@@ -36,18 +36,16 @@ class Shard:
     def local_queries(self, b: int) -> Tuple[int, int]:
         if self.kind != "queries":
             return int(b), 0
-        cnt, off = block_bounds(b, self.rank, self.world)
-        if cnt == 0:
-            raise ValueError(f"rank {self.rank} got no queries (B={b} < world={self.world}); shard samples instead")
-        return cnt, off
+        if b < self.world:  # the same test on EVERY rank: nobody walks into a collective the others never reach
+            raise ValueError(f"B={b} queries cannot be sharded over {self.world} ranks; shard samples instead")
+        return block_bounds(b, self.rank, self.world)
 
     def local_samples(self, s: int) -> Tuple[int, int]:
         if self.kind != "samples":
             return int(s), 0
-        cnt, off = block_bounds(s, self.rank, self.world)
-        if cnt == 0:
-            raise ValueError(f"rank {self.rank} got no samples (S={s} < world={self.world})")
-        return cnt, off
+        if s < self.world:  # raised on every rank alike
+            raise ValueError(f"S={s} samples cannot be sharded over {self.world} ranks")
+        return block_bounds(s, self.rank, self.world)
 
     def slice_queries(self, v: torch.Tensor) -> torch.Tensor:
         if self.kind != "queries":
@@ -64,6 +62,19 @@ class Shard:
         out = flag.clone()
         dist.all_reduce(out, op=dist.ReduceOp.MAX, group=self.group)
         return out
+
+
+def shared_seed(seed: int, shard: Optional[Shard], device) -> int:
+    """Rank 0's freshly drawn Philox key for every rank of a sharded call: the ranks' rows are pieces of ONE draw set
+    (counters carry global (query, sample) indices; roots are shared across query shards), so they must share the key
+    even when the caller did not pass ``seed=``."""
+    if shard is None or shard.world == 1:
+        return seed
+    import torch.distributed as dist
+
+    t = torch.tensor([seed], dtype=torch.int64, device=device)
+    dist.broadcast(t, src=0, group=shard.group)
+    return int(t.item())
 
 
 def gather_stats(stats: torch.Tensor, shard: Shard) -> torch.Tensor:

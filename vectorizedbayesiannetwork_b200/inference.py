@@ -21,7 +21,7 @@ from . import _lib as L
 from . import engine as E
 from .core import (Query, infer_batch_size, model_cpds, register_inference, register_sampling)
 from .cpds import TABLE_KINDS
-from .dist import Shard, gather_stats
+from .dist import Shard, gather_stats, shared_seed
 from .plan import Role, compile_gibbs, compile_schedule
 
 
@@ -155,7 +155,7 @@ class _ScheduleRunner:
             plan.run(b, s, fixed=fixed, stores=[stores[n] for n in prog.stores],
                      noise=[noise[n] for n in prog.noise], logw=logw, logp=logp,
                      logp_as_pdf=mode in ("mcm", "mcm_fast"),
-                     seed=E.draw_seed() if seed is None else seed,
+                     seed=shared_seed(E.draw_seed(), shard, dev) if seed is None else seed,
                      query_offset=q_off, sample_offset=s_off, error_flag=flag,
                      seg=seg, seg_slot=prog.keep_slot if summary else -1, seg_classes=classes if summary else 0)
         return {"logw": logw, "logp": logp, "stores": stores, "plan": plan, "b": b, "s": s, "flag": flag, "seg": seg,
