@@ -847,3 +847,25 @@ def test_minus_inf_log_weights_follow_softmax(backend):
     assert bool((w.cpu()[0, 40:45] == 0).all()) and w.cpu()[0, 0] == 0
     assert bool(torch.isnan(w.cpu()[1]).all()) and bool(torch.isnan(ess.cpu()[1]))
     torch.testing.assert_close(ess.cpu()[[0, 2]], 1.0 / (want[[0, 2]] ** 2).sum(1), rtol=1e-4, atol=1e-4)
+
+
+def test_barren_node_pruning_is_exact(backend):
+    """prune=True drops unobserved nodes without an observed / queried descendant from the schedule; the emitted
+    nodes keep their place in the random streams, so weights and samples equal the full walk's BIT FOR BIT."""
+    cases = [(S.random_dag_lg_mdn(60, seed=4), "n30", ["n57", "n58", "n59"], None),
+             (S.alarm_softmax(seed=0), "LVFAILURE", ["HRBP", "BP"], S.ALARM)]
+    for spec, target, ev_nodes, cards in cases:
+        model = V.VBN.from_spec(spec, device=backend.device)
+        g = torch.Generator().manual_seed(6)
+        ev = {n: (torch.randint(0, cards[n][0], (3, 1), generator=g).float() if cards else 0.3 * torch.randn(3, 1, generator=g))
+              for n in ev_nodes}
+        q = {"target": target, "evidence": ev}
+        for method in ("likelihood_weighting", "importance_sampling", "monte_carlo_marginalization"):
+            model.set_inference_method(method, n_samples=257)
+            w0, s0 = model.infer_posterior(q, seed=5)
+            w1, s1 = model.infer_posterior(q, seed=5, prune=True)
+            assert torch.equal(s0, s1) and torch.equal(w0, w1), (target, method)
+            if method != "monte_carlo_marginalization":  # (its one-CPD fast path has nothing to prune)
+                runner = model._inference._runner
+                n_ops = sorted(len(p.program.ops) for p in runner._cache.values())
+                assert n_ops[0] < n_ops[-1], n_ops  # the pruned schedule really is shorter

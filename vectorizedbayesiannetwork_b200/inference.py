@@ -48,13 +48,32 @@ class _ScheduleRunner:
     def __init__(self) -> None:
         self._cache: Dict[tuple, E.DevicePlan] = {}
 
+    @staticmethod
+    def barren_nodes(topo, parents, query: Query, mode: str) -> set:
+        """Nodes whose value cannot reach the result: not the target, not scored evidence, and no directed path to
+        either (the classic barren-node rule).  ``do`` nodes -- and, in the unweighted modes, evidence nodes -- are
+        clamped, so nothing is needed upstream of them."""
+        scored = set(query.evidence) if mode in ("lw", "is") else set()
+        need = {query.target} | scored
+        cut = set(query.do) | (set(query.evidence) - scored)
+        stack = [n for n in need if n not in cut or n in scored]
+        while stack:
+            n = stack.pop()
+            if n in cut and n not in scored:
+                continue
+            for p in parents[n]:
+                if p not in need:
+                    need.add(p)
+                    stack.append(p)
+        return set(topo) - need
+
     def plan_for(self, vbn, query: Query, mode: str, *, inject=frozenset(), store_all=False,
-                 only=None, summary: bool = False) -> E.DevicePlan:
+                 only=None, summary: bool = False, prune: bool = False) -> E.DevicePlan:
         cpds = model_cpds(vbn)
         fp = tuple((c._uid, c._version) for c in cpds.values())
         key = (fp, mode, query.target, tuple(sorted(query.evidence)), tuple(sorted(query.do)),
                tuple(sorted(inject)), bool(store_all), None if only is None else tuple(only), str(vbn.device),
-               bool(summary))
+               bool(summary), bool(prune))
         plan = self._cache.get(key)
         if plan is not None:
             return plan
@@ -82,8 +101,10 @@ class _ScheduleRunner:
             t = roles[query.target]
             t.out_logp = True
             t.density = True
+        barren = (self.barren_nodes(topo, parents, query, mode)
+                  if prune and mode in ("lw", "is", "mcm") and only is None and not store_all else ())
         prog = compile_schedule(topo, parents, cpds, roles, table_fn=E.discrete_table_fn,
-                                keep_live=query.target if summary else None)
+                                keep_live=query.target if summary else None, barren=barren)
         plan = E.DevicePlan(prog, vbn.device)
         if len(self._cache) > 64:
             self._cache.clear()
@@ -126,7 +147,8 @@ class _ScheduleRunner:
 
     def forward(self, vbn, query: Query, n_samples: int, mode: str, *, noise=None, seed=None,
                 shard: Optional[Shard] = None, clamp_obs: bool = False, store_all: bool = False,
-                only=None, n_queries: Optional[int] = None, summary: bool = False, classes: int = 0):
+                only=None, n_queries: Optional[int] = None, summary: bool = False, classes: int = 0,
+                prune: bool = False):
         """Runs one pass.  Returns dict(logw, logp, stores={node: [B,S,D]}, seg, plan, b, s).
         Weighted passes (``lw`` / ``is``) also emit the per-warp records of the fused weight reduction (``seg``);
         ``summary``: the target is not stored and no log-weight buffer exists -- its weighted moments (and, with
@@ -134,7 +156,7 @@ class _ScheduleRunner:
         dev = _check_model(vbn)
         noise = noise or {}
         plan = self.plan_for(vbn, query, mode, inject=frozenset(noise), store_all=store_all, only=only,
-                             summary=summary)
+                             summary=summary, prune=prune)
         prog = plan.program
         b_full = infer_batch_size(query.evidence, query.do) if n_queries is None else n_queries
         b, s, q_off, s_off = b_full, int(n_samples), 0, 0
@@ -160,6 +182,15 @@ class _ScheduleRunner:
                      seg=seg, seg_slot=prog.keep_slot if summary else -1, seg_classes=classes if summary else 0)
         return {"logw": logw, "logp": logp, "stores": stores, "plan": plan, "b": b, "s": s, "flag": flag, "seg": seg,
                 "dev": dev}
+
+
+def _prune(kwargs) -> bool:
+    """``prune=True`` (or VBN_PRUNE=1): barren nodes are left out of the schedule.  Off by default: the schedule then
+    walks every node like the reference's loops do.  Either way the result is the same bit for bit."""
+    import os
+
+    v = kwargs.get("prune")
+    return bool(v) if v is not None else os.environ.get("VBN_PRUNE", "0") == "1"
 
 
 def _flag_message(cpds) -> str:
@@ -253,7 +284,7 @@ class LikelihoodWeighting:
         fused, classes = _summary_args(vbn, query, kwargs)
         out = self._runner.forward(vbn, query, n_samples, "lw", noise=kwargs.get("noise"),
                                    seed=kwargs.get("seed"), shard=shard, clamp_obs=True, summary=fused,
-                                   classes=classes)
+                                   classes=classes, prune=_prune(kwargs))
         _raise_if_flagged(vbn, out)
         if fused:  # summary=True: per-query posterior summary, nothing of size [B, S] is materialised
             return _summary(_reduce(out, shard=shard)[0], classes)
@@ -284,7 +315,7 @@ class ImportanceSampling:
         seed = kwargs.get("seed")
         fused, classes = _summary_args(vbn, query, kwargs)
         out = self._runner.forward(vbn, query, n_samples, "is", noise=noise.get("is"), seed=seed, shard=shard,
-                                   summary=fused, classes=classes)
+                                   summary=fused, classes=classes, prune=_prune(kwargs))
         _raise_if_flagged(vbn, out)
         threshold = max(1.0, self.ess_threshold * float(n_samples))
         # the softmax statistics, the ESS and the fallback test any(ESS < threshold) come out of ONE merge launch
@@ -295,7 +326,7 @@ class ImportanceSampling:
         if int(flag.item()) != 0:  # the one device -> host read of the pass
             self._last_fallback = True
             lw_kwargs = {"n_samples": n_samples, "shard": shard, "noise": noise.get("lw"),
-                         "summary": kwargs.get("summary")}
+                         "summary": kwargs.get("summary"), "prune": kwargs.get("prune")}
             if seed is not None:
                 lw_kwargs["seed"] = seed + 1
             return self._lw.infer_posterior(vbn, query, **lw_kwargs)
@@ -348,7 +379,7 @@ class MonteCarloMarginalization:
             return out["logp"], out["stores"][target]
 
         out = self._runner.forward(vbn, query, n_samples, "mcm", noise=kwargs.get("noise"),
-                                   seed=kwargs.get("seed"), shard=shard)  # :60-92
+                                   seed=kwargs.get("seed"), shard=shard, prune=_prune(kwargs))  # :60-92
         _raise_if_flagged(vbn, out)
         return out["logp"], out["stores"][target]
 

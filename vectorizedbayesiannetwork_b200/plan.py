@@ -121,12 +121,15 @@ def _tab_plain_fields(pk: Packed, slots: Sequence[int], param_off: int, out_slot
 
 def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpds: Dict[str, BaseCPD],
                      roles: Dict[str, Role], use_tc: Optional[bool] = None, table_fn=None,
-                     keep_live: Optional[str] = None) -> Program:
+                     keep_live: Optional[str] = None, barren: Sequence[str] = ()) -> Program:
     """``topo``: nodes to emit, in topological order (nodes absent from ``roles`` are skipped).
     ``table_fn(cpd, x, parents) -> log_prob``: lets discrete nodes with all-discrete parents be
     compiled into lookup tables (VBN_OP_TAB); None keeps them on the MLP path.
     ``keep_live``: a node whose value slot must survive to the end of the walk (the kernel's fused summary reads
-    it there: VbnRunDesc.seg_slot)."""
+    it there: VbnRunDesc.seg_slot).
+    ``barren``: nodes (with roles, like every other) whose ops are NOT emitted: unobserved nodes without an observed
+    or queried descendant cannot influence the weights or the target.  They keep their place in the random streams, so
+    the emitted nodes draw exactly what they draw in the full schedule (pruned and full runs agree bit for bit)."""
     if use_tc is None:
         use_tc = tensor_cores_enabled()
     any_tc = False
@@ -142,6 +145,18 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
     if 1 < len(hoist) <= 32:
         hs = set(hoist)
         order = hoist + [n for n in order if n not in hs]
+    # stream positions are those of the FULL schedule (barren nodes included)
+    stream_base: Dict[str, tuple] = {}
+    n_acc = u_acc = 0
+    for n in order:
+        if roles[n].density and roles[n].src == "sample":
+            pk0 = cpds[n].pack()
+            stream_base[n] = (n_acc, u_acc)
+            n_acc += pk0.n_normals
+            u_acc += pk0.n_uniforms
+    if barren:
+        drop = set(barren)
+        order = [n for n in order if n not in drop]
     index = {n: i for i, n in enumerate(order)}
     packed: Dict[str, Optional[Packed]] = {}
     dims: Dict[str, int] = {}
@@ -206,8 +221,6 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
     inputs: List[str] = []
     stores: List[str] = []
     noise: List[str] = []
-    n_off = 0
-    u_off = 0
     n_scratch = 0
     heavy = False
     needs_logw = False
@@ -296,10 +309,7 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
             if r.src == "sample":
                 if r.shared:
                     flags |= L.F_SHARED
-                op["n_off"] = n_off
-                op["u_off"] = u_off
-                n_off += pk.n_normals
-                u_off += pk.n_uniforms
+                op["n_off"], op["u_off"] = stream_base[n]
                 if r.inject:
                     op["noise_idx"] = len(noise)
                     noise.append(n)
