@@ -186,6 +186,8 @@ typedef struct VbnProgramDesc {
   int32_t n_tc;
   int32_t tc_image_bytes;  /* largest {image bytes} of tc_list (one slot of the kernel's weight ring), 0 = the
                          format's maximum (30720)                                           */
+  int32_t has_tables;      /* 1 if the program contains VBN_OP_TAB ops (FP32-pipe kernels without MLP ops come in a
+                         variant without the table op bodies for linear-Gaussian-only schedules)           */
   int32_t rows_per_thread; /* FP32-pipe kernel, schedules without MLP/KDE ops: 0 = default (4 rows
                          per thread, best for drawn linear-Gaussian chains), 2 = table-lookup
                          heavy schedules (fewer registers, more resident warps)             */

@@ -30,7 +30,7 @@ def test_library_exports_every_header_symbol():
 
 def test_struct_layouts_match_header():
     assert L.OP_DTYPE.itemsize == 128
-    assert C.sizeof(L.ProgramDesc) == 88
+    assert C.sizeof(L.ProgramDesc) == 88  # (has_tables fills the former padding)
     assert C.sizeof(L.RunDesc) == 136
     assert L.RunDesc.logw_dev.offset == 80 and L.RunDesc.error_flag_dev.offset == 104
 

@@ -44,7 +44,7 @@ class ProgramDesc(C.Structure):
         ("n_slots", C.c_int32), ("n_scratch", C.c_int32),
         ("heavy", C.c_int32), ("tc", C.c_int32),
         ("tc_list_dev", C.c_void_p), ("n_tc", C.c_int32), ("tc_image_bytes", C.c_int32),
-        ("rows_per_thread", C.c_int32),
+        ("has_tables", C.c_int32), ("rows_per_thread", C.c_int32),
     ]
 
 

@@ -66,8 +66,9 @@ const Shape kShapes[] = {
 };
 constexpr int kNumShapes = static_cast<int>(sizeof(kShapes) / sizeof(kShapes[0]));
 
-const void* shape_fn(const Shape& s) {
-  return s.heavy ? vbn::heavy_kernel_ptr(s.rpt, s.nt, s.min_blocks) : vbn::light_kernel_ptr(s.rpt, s.nt, s.min_blocks);
+const void* shape_fn(const Shape& s, bool tab) {
+  return s.heavy ? vbn::heavy_kernel_ptr(s.rpt, s.nt, s.min_blocks)
+                 : vbn::light_kernel_ptr(s.rpt, s.nt, s.min_blocks, tab);
 }
 
 }  // namespace
@@ -82,6 +83,7 @@ struct VbnPlan {
   int small_shape;      // smallest-CTA shape of the same family (-1: none): used when a run has too few rows to give
   int small_blocks;     // every SM a CTA of the preferred shape (Gibbs chains, CPD-handle calls, small batches)
   size_t small_smem;
+  int tab;         // light schedules: the kernel variant with the table-lookup op bodies
   int tc;          // 0, or warpgroups per CTA of vbn::tc::schedule_tc_kernel<NWG, RPT>
   int tc_rpt;      // 128-row tiles per warpgroup
   int tc_nbuf;     // weight-ring depth of the tensor-core kernel
@@ -156,6 +158,8 @@ int32_t vbn_plan_create(const VbnProgramDesc* desc, VbnPlan** out_plan) {
     }
     // does not fit: fall through to the FFMA shapes (the ops keep their FFMA parameter blocks)
   }
+  const bool tab = desc->has_tables != 0;
+  p->tab = tab ? 1 : 0;
   const char* force = desc->heavy ? nullptr : std::getenv("VBN_SHAPE");  // dev knob (light schedules): force a shape
   for (int i = 0; i < kNumShapes; ++i) {
     const Shape& s = kShapes[i];
@@ -164,9 +168,9 @@ int32_t vbn_plan_create(const VbnProgramDesc* desc, VbnPlan** out_plan) {
     if (!force && !s.heavy && desc->rows_per_thread == 2 && s.rpt > 2) continue;
     const size_t bytes = per_row * s.rpt * s.nt;
     if (bytes > static_cast<size_t>(max_smem)) continue;
-    CUDA_TRY(cudaFuncSetAttribute(shape_fn(s), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(shape_fn(s, tab), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     int occ = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, shape_fn(s), s.nt, bytes));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, shape_fn(s, tab), s.nt, bytes));
     if (occ < 1) continue;
     p->shape = i;
     p->blocks_per_sm = occ;
@@ -178,9 +182,9 @@ int32_t vbn_plan_create(const VbnProgramDesc* desc, VbnPlan** out_plan) {
       const Shape& s = kShapes[i];
       if (s.heavy != (desc->heavy ? 1 : 0) || s.rpt * s.nt >= kShapes[p->shape].rpt * kShapes[p->shape].nt) continue;
       const size_t bytes = per_row * s.rpt * s.nt;
-      CUDA_TRY(cudaFuncSetAttribute(shape_fn(s), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      CUDA_TRY(cudaFuncSetAttribute(shape_fn(s, tab), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
       int occ = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, shape_fn(s), s.nt, bytes));
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, shape_fn(s, tab), s.nt, bytes));
       if (occ < 1) continue;
       p->small_shape = i;
       p->small_blocks = occ;
@@ -263,6 +267,7 @@ int32_t vbn_run_forward(const VbnPlan* plan, const VbnRunDesc* run, void* stream
   }
   const int64_t rows_per_cta = static_cast<int64_t>(s.rpt) * s.nt;
   const int64_t n_tiles = (a.n_rows + rows_per_cta - 1) / rows_per_cta;
+  const bool tab = plan->tab != 0;
   void* args[] = {&a};
   if (n_tiles < plan->num_sms && plan->small_shape >= 0) {
     // fewer tiles than SMs: spread the rows over more, smaller CTAs (a 4096-chain Gibbs run is 16 CTAs of the
@@ -272,13 +277,13 @@ int32_t vbn_run_forward(const VbnPlan* plan, const VbnRunDesc* run, void* stream
     const int64_t tiles_small = (a.n_rows + rows_small - 1) / rows_small;
     const int64_t resident_small = static_cast<int64_t>(plan->num_sms) * plan->small_blocks;
     const unsigned grid_small = static_cast<unsigned>(tiles_small < resident_small ? tiles_small : resident_small);
-    CUDA_TRY(cudaLaunchKernel(shape_fn(q), dim3(grid_small), dim3(q.nt), args, plan->small_smem,
+    CUDA_TRY(cudaLaunchKernel(shape_fn(q, tab), dim3(grid_small), dim3(q.nt), args, plan->small_smem,
                               static_cast<cudaStream_t>(stream)));
     return VBN_OK;
   }
   const int64_t resident = static_cast<int64_t>(plan->num_sms) * plan->blocks_per_sm;
   const unsigned grid = static_cast<unsigned>(n_tiles < resident ? n_tiles : resident);
-  CUDA_TRY(cudaLaunchKernel(shape_fn(s), dim3(grid), dim3(s.nt), args, plan->smem_bytes,
+  CUDA_TRY(cudaLaunchKernel(shape_fn(s, tab), dim3(grid), dim3(s.nt), args, plan->smem_bytes,
                             static_cast<cudaStream_t>(stream)));
   return VBN_OK;
 }

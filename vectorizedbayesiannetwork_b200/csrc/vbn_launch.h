@@ -9,9 +9,10 @@ namespace vbn {
 
 // &schedule_kernel<rpt, nt, heavy, min_blocks>, or nullptr when that shape is not instantiated
 const void* heavy_kernel_ptr(int rpt, int nt, int min_blocks);
-const void* light_kernel_ptr(int rpt, int nt, int min_blocks);   // dispatches to the two light TUs
-const void* light4_kernel_ptr(int rpt, int nt, int min_blocks);  // 4 rows per thread
-const void* light2_kernel_ptr(int rpt, int nt, int min_blocks);  // 1-2 rows per thread
+// tab: the schedule holds table-lookup ops (the kernels without their bodies serve linear-Gaussian-only schedules)
+const void* light_kernel_ptr(int rpt, int nt, int min_blocks, bool tab);   // dispatches to the two light TUs
+const void* light4_kernel_ptr(int rpt, int nt, int min_blocks, bool tab);  // 4 rows per thread
+const void* light2_kernel_ptr(int rpt, int nt, int min_blocks, bool tab);  // 1-2 rows per thread
 
 // tcgen05 KDE kernel (vbn_k_kde_tc.cu): bytes of the packed-point workspace, whether (dp, dx) fits, the launch
 size_t kde_tc_workspace_bytes(int64_t n_points, int dp, int dx);

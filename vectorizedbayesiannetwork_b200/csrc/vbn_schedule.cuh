@@ -80,14 +80,20 @@ struct NoTc {
   static constexpr bool kEnabled = false;
   static constexpr bool kInlineRng = false;
   static constexpr bool kLoops = true;  // carries the Gibbs glue ops (VBN_OP_TAKEW / SELECT / JUMP)
+  static constexpr bool kTab = true;    // carries the table-lookup op bodies
 };
 // LG / table-only schedules: the generator is the hot loop, so it is inlined with constant-bank
 // round keys instead of being called out of line.
-struct LightPolicy {
+// TAB = false: linear-Gaussian-only schedules get a kernel without the table op bodies (a chain's hot loop then has
+// nothing but the plain LG op in it: BASELINE cfg2 lost 9 % when the table code moved into the same kernel).
+template <bool TAB>
+struct LightPolicyT {
   static constexpr bool kEnabled = false;
   static constexpr bool kInlineRng = true;
   static constexpr bool kLoops = false;  // the LG / table hot loops stay a plain counted walk
+  static constexpr bool kTab = TAB;
 };
+using LightPolicy = LightPolicyT<true>;
 
 template <int RPT, int NT, class TC = NoTc>
 struct Ctx {
@@ -1580,7 +1586,7 @@ __device__ __forceinline__ void run_ops(Ctx<RPT, NT, TC>& c) {
       }
       // (only in the <= 2 rows-per-thread shapes, which is where schedules with table ops are placed: the
       // 4-row linear-Gaussian shapes keep their loop body small; there the op takes the generic lookup)
-      if (q0.y & VBN_F_TABPLAIN) {
+      if (TC::kTab && (q0.y & VBN_F_TABPLAIN)) {
         VbnOp lop;
         int4* ld = reinterpret_cast<int4*>(&lop);
         ld[0] = q0;
@@ -1656,7 +1662,7 @@ __device__ __forceinline__ void run_ops(Ctx<RPT, NT, TC>& c) {
       case VBN_OP_SNN: if (HEAVY) op_snn(c, op); break;
       case VBN_OP_KDE: if (HEAVY) op_kde(c, op); break;
       case VBN_OP_RFF: if (HEAVY) op_rff(c, op); break;
-      case VBN_OP_TAB: op_tab(c, op); break;
+      case VBN_OP_TAB: if (TC::kTab) op_tab(c, op); break;
       default: break;
     }
     store_value(c, op);
@@ -1674,7 +1680,7 @@ __device__ __forceinline__ void run_ops(Ctx<RPT, NT, TC>& c) {
   if (a.seg) emit_segments(c);
 }
 
-template <int RPT, int NT, bool HEAVY, int MIN_BLOCKS>
+template <int RPT, int NT, bool HEAVY, int MIN_BLOCKS, bool TAB = true>
 __global__ void __launch_bounds__(NT, MIN_BLOCKS) schedule_kernel(const ScheduleArgs a) {
   extern __shared__ __align__(16) float smem[];
   constexpr int ROWS = RPT * NT;
@@ -1683,7 +1689,7 @@ __global__ void __launch_bounds__(NT, MIN_BLOCKS) schedule_kernel(const Schedule
   // front of every generator refill -- instead of keeping one register each (same finding as in the tcgen05 kernel).
   int tid = threadIdx.x;
   asm volatile("" : "+r"(tid));
-  Ctx<RPT, NT, typename std::conditional<HEAVY, NoTc, LightPolicy>::type> c(a, smem + tid, 0);
+  Ctx<RPT, NT, typename std::conditional<HEAVY, NoTc, LightPolicyT<TAB>>::type> c(a, smem + tid, 0);
   const int64_t n_tiles = (a.n_rows + ROWS - 1) / ROWS;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t base = tile * ROWS;

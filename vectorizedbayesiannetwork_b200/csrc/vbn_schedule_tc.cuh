@@ -240,6 +240,7 @@ struct TcMlp {
   static constexpr bool kEnabled = true;
   static constexpr bool kLoops = false;      // Gibbs programs never carry tensor-core images
   static constexpr bool kInlineRng = true;   // inlined generator with constant-bank round keys
+  static constexpr bool kTab = true;
   // Per-thread state is kept to a handful of OPAQUE values (see "values, not recipes" in the kernel): everything
   // else is an immediate offset from them, and the weight-ring producer's counters live in shared memory (one
   // lane touches them once per MLP) instead of a register in every thread.

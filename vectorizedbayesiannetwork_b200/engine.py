@@ -69,6 +69,7 @@ class DevicePlan:
                 tc_list_dev=self.tc_list.data_ptr() if program.tc else None,
                 n_tc=int(program.tc_list.shape[0]) if program.tc else 0,
                 tc_image_bytes=int(program.tc_list[:, 1].max()) if program.tc else 0,
+                has_tables=1 if any(int(k) == L.OP_TAB for k in program.ops["kind"]) else 0,
                 rows_per_thread=int(os.environ.get("VBN_ROWS_PER_THREAD", "0")),  # 0: 4 rows per thread (measured best
                 # for chains and, since the plain table op became one compact body, for table schedules too)
             )
