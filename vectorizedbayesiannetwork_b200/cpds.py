@@ -117,13 +117,17 @@ def _core_matrix_image(w: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray(w.reshape(n // 8, 8, k // 4, 4).transpose(0, 2, 1, 3)).reshape(-1)
 
 
-def pack_mlp_tc(layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], input_dim: int, l1_fma: bool = False):
+def pack_mlp_tc(layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], input_dim: int, l1_fma: bool = False,
+                relu2: bool = False):
     """Weight image for the tcgen05 kernel, or None when the MLP is not [Dp<=32 -> 32 -> 32 -> O<=32].
     Layout (floats): W1hi, W1lo [32][K1+8]; W2hi, W2lo [32][40]; W3hi, W3lo [N3][40] -- core-matrix images of
     nn.Linear's [out][in] = [N][K] K-major weight with the bias appended as column K (then 7 zero columns).
     ``l1_fma`` (gaussian_nn / mdn nodes, whose ops carry their parent slots in the descriptor) and Dp <= 4: the first
     layer runs on the FP32 pipe, so the W1 images are replaced by the plain block W1^T[4][32] (rows >= Dp zero),
-    b1[32], and K1 is reported as 0 (csrc/vbn_schedule_tc.cuh hidden1_fma)."""
+    b1[32], and K1 is reported as 0 (csrc/vbn_schedule_tc.cuh hidden1_fma).
+    ``relu2`` (ReLU MLPs): the kernel stores 2 relu(h) = h + |h| as the hidden activations (one packed add instead of
+    two max), so W2 and W3 -- not the biases -- are halved here: an exact power-of-two scaling on both sides, every
+    product and the accumulator are bit-identical to relu(h) * w."""
     if len(layers) != 3:
         return None
     (w1, b1), (w2, b2), (w3, b3) = [(_f32(w).numpy(), _f32(b).numpy()) for w, b in layers]
@@ -137,7 +141,8 @@ def pack_mlp_tc(layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], input_dim: 
     w3p = np.zeros((n3, 32), np.float32)
     w3p[:n_out] = w3
     chunks = []
-    mma_layers = [(w1p, b1), (w2, b2), (w3p, _padded(b3, n3))]
+    half = np.float32(0.5 if relu2 else 1.0)
+    mma_layers = [(w1p, b1), (w2 * half, b2), (w3p * half, _padded(b3, n3))]
     if l1_fma and dp <= 4:
         plain = np.zeros((5, 32), np.float32)
         plain[:dp] = w1.T
@@ -161,7 +166,8 @@ def _layers_from_module(net) -> List[Tuple[torch.Tensor, torch.Tensor]]:
 
 
 def _with_tc(pk: Packed, layers, input_dim: int) -> Packed:
-    img = pack_mlp_tc(layers, input_dim, l1_fma=pk.kind in (L.OP_GNN, L.OP_MDN) and os.environ.get("VBN_TC_L1FMA", "1") != "0")
+    img = pack_mlp_tc(layers, input_dim, l1_fma=pk.kind in (L.OP_GNN, L.OP_MDN) and os.environ.get("VBN_TC_L1FMA", "1") != "0",
+                      relu2=pk.act == L.ACT["relu"])
     if img is not None:
         pk.tc_blob, pk.tc_k1, pk.tc_n3 = img
     return pk

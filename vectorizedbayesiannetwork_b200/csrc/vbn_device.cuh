@@ -118,8 +118,19 @@ __device__ __forceinline__ float softplus20(float x) { return x > 20.0f ? x : lo
 // ~1e-7 relative.  softplus(x) = max(x, 0) + log1p(e), e = exp(-|x|) in (0, 1];
 // log1p(e) = 2 atanh(s), s = e / (2 + e) <= 1/3, odd series to s^15 (next term < 2e-9 relative).
 // For x > 20 the series term is < 2.1e-9, i.e. the result is x in fp32, as with the threshold form.
+// 2^x, flush-to-zero form: one multiply-free MUFU (the default form brackets it with a range test and two
+// predicated multiplies for results below 2^-126, which the callers here clamp or add to >= 1 anyway)
+__device__ __forceinline__ float ex2_ftz(float x) {
+#ifdef VBN_HOST_EMU
+  return exp2f(x);
+#else
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+#endif
+}
 __device__ __forceinline__ float softplus20_fast(float x) {
-  const float e = __expf(-fabsf(x));
+  const float e = ex2_ftz(fabsf(x) * -1.4426950408889634f);
   const float s = __fdividef(e, 2.0f + e);
   const float z = s * s;
   float p = 1.0f / 15.0f;

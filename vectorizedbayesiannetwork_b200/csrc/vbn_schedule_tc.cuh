@@ -93,6 +93,9 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -191,6 +194,29 @@ __device__ __forceinline__ void split_tf32_x2(float a, float b, uint32_t& hi_a, 
       "}"
       : "=&l"(c), "=&l"(t), "=&l"(hi), "=&l"(lo)
       : "l"(p), "f"(8192.0f));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(hi_a), "=r"(hi_b) : "l"(hi));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo_a), "=r"(lo_b) : "l"(lo));
+}
+// ReLU + split of two pre-activations: q = p + |p| = 2 relu(p) is ONE packed add (the |.| is an operand
+// modifier of FADD2) instead of two FMNMX; the factor 2 is exact and the host halves the weights of the layer that
+// consumes these activations (cpds.pack_mlp_tc relu2), so every product -- and the accumulator -- is bit-identical
+// to relu(p) * w.  NaN pre-activations stay NaN (torch.relu semantics; fmaxf would have returned 0).
+__device__ __forceinline__ void split_relu2_tf32_x2(float a, float b, uint32_t& hi_a, uint32_t& hi_b, uint32_t& lo_a,
+                                                    uint32_t& lo_b) {
+  unsigned long long p, m, q, c, t, hi, lo;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(a), "f"(b));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(m) : "f"(fabsf(a)), "f"(fabsf(b)));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(q) : "l"(p), "l"(m));
+  asm("{\n\t"
+      ".reg .b64 k;\n\t"
+      "mov.b64 k, {%5, %5};\n\t"
+      "mul.rn.f32x2 %0, %4, k;\n\t"
+      "add.rn.f32x2 %1, %4, %0;\n\t"
+      "sub.rn.f32x2 %2, %1, %0;\n\t"
+      "sub.rn.f32x2 %3, %4, %2;\n\t"
+      "}"
+      : "=&l"(c), "=&l"(t), "=&l"(hi), "=&l"(lo)
+      : "l"(q), "f"(8192.0f));
   asm("mov.b64 {%0, %1}, %2;" : "=r"(hi_a), "=r"(hi_b) : "l"(hi));
   asm("mov.b64 {%0, %1}, %2;" : "=r"(lo_a), "=r"(lo_b) : "l"(lo));
 }
@@ -331,8 +357,18 @@ struct TcMlp {
   __device__ __forceinline__ void publish_and_issue(int j0, int j1, uint32_t b_hi, uint32_t b_lo, int k, int n) {
     tmem_wait_st();
     tc_fence_before();
-    wg_sync();
-    if (issuer()) {  // warp-uniform: operands stay on the uniform datapath
+    if (!issuer()) {
+      // Only the issuing warp has to see all 128 rows published.  With one tile per warpgroup the other warps just
+      // check in: they cannot reach the next check-in before this layer's MMAs -- which the issuing warp queues
+      // after its own bar.sync -- have completed.  With two tiles a warp can publish tile 1 while the issuing warp
+      // still waits for tile 0's check-ins, so there everybody waits.
+      if constexpr (RPT == 1) {
+        named_bar_arrive(1 + wg(), kWgThreads);
+      } else {
+        wg_sync();
+      }
+    } else {  // warp-uniform: operands stay on the uniform datapath
+      wg_sync();
       tc_fence_after();
       if (elect_one()) {
         for (int j = j0; j < j1; ++j) {
@@ -356,14 +392,15 @@ struct TcMlp {
   }
 
   // 16 activations -> 3xTF32 split -> columns [16 half, 16 half + 16) of A_hi / A_lo of tile j.
-  // RELU: the values are pre-activations and the activation is ReLU (applied here).
+  // RELU: the values are pre-activations and the activation is ReLU (applied here, as 2 relu: the next layer's
+  // weights are halved in the image).
   template <bool RELU>
   __device__ __forceinline__ void split_store(int j, int half, const float (&h)[16]) {
     uint32_t hi[16], lo[16];
 #pragma unroll
     for (int q = 0; q < 16; q += 2) {
       if constexpr (RELU) {
-        split_tf32_x2(fmaxf(h[q], 0.0f), fmaxf(h[q + 1], 0.0f), hi[q], hi[q + 1], lo[q], lo[q + 1]);
+        split_relu2_tf32_x2(h[q], h[q + 1], hi[q], hi[q + 1], lo[q], lo[q + 1]);
       } else {
         split_tf32_x2(h[q], h[q + 1], hi[q], hi[q + 1], lo[q], lo[q + 1]);
       }
@@ -591,7 +628,8 @@ struct TcMlp {
     float se = 0.0f;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      q[k] = __expf(__uint_as_float(v[k]) - mx);  // only places the CDF edges: 2^-21 relative is plenty
+      q[k] = ex2_ftz((__uint_as_float(v[k]) - mx) * 1.4426950408889634f);  // only places the CDF edges: 2^-21
+                                                                             // relative is plenty; arguments <= 0
       se += q[k];
     }
     // pi = softmax.clamp_min(1e-5) / sum (mdn.py:227-228); k ~ Categorical(pi) by inverse CDF on
