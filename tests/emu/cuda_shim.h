@@ -49,3 +49,4 @@ inline int atomicOr(int32_t* p, int v) { int o = *p; *p |= v; return o; }
 using std::min;
 using std::max;
 inline float __int_as_float(int32_t v) { float f; std::memcpy(&f, &v, 4); return f; }
+inline int32_t __float_as_int(float f) { int32_t v; std::memcpy(&v, &f, 4); return v; }

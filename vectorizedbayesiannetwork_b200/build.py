@@ -67,6 +67,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     base = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC]
     if verbose:
         base += ["-Xptxas", "-v"]
+    base += os.environ.get("VBN_NVCC_EXTRA", "").split()  # dev experiments (-D switches)
 
     def compile_one(src: str) -> str:
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
