@@ -31,3 +31,15 @@ except Exception as e:
 PY
 )"
 done
+for sh in ${SHAPES:-}; do
+  VBN_TC_SHAPE=$sh timeout 600 python bench.py --workload cfg5 --steps 5 --warmup 3 --no-cpu-baseline --no-others --queries-per-gpu 1250 > $O/${TAG}_s$sh.json 2> $O/${TAG}_s$sh.err
+  echo "shape=$sh rc=$? $(python - <<PY
+import json
+try:
+    d=json.loads(open('$O/${TAG}_s$sh.json').read().strip().splitlines()[-1])
+    print('ms/step', round(d['ms_per_step'],2), 'kernel_ms', d['roofline']['kernel_ms_avg'], 'value', '%.3e'%d['value'])
+except Exception as e:
+    print('no line', e)
+PY
+)"
+done
