@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from vectorizedbayesiannetwork_b200.dist import Shard, gather_stats
+from vectorizedbayesiannetwork_b200.dist import Shard, gather_stats, shared_seed
 
 
 def _free_port() -> int:
@@ -47,7 +47,11 @@ def _worker(rank, world, port, logw, out):
         b_loc, b_off = shq.local_queries(B)
         flag = torch.tensor([int(bool((ess[b_off: b_off + b_loc] < 0.1 * S).any()))], dtype=torch.int32)
         flag = shq.any_flag(flag)
-        out[rank] = (s_off, w_local, ess, int(flag.item()), shq.slice_queries(logw).shape[0])
+        # calls without seed=: every rank must key Philox identically although each seeds torch on its own; the key
+        # is agreed once per group, later calls derive theirs without a collective
+        torch.manual_seed(1000 + rank)
+        seeds = [shared_seed(int(torch.randint(0, 2**31 - 1, (1,)).item()), sh, "cpu") for _ in range(3)]
+        out[rank] = (s_off, w_local, ess, int(flag.item()), shq.slice_queries(logw).shape[0], seeds)
     finally:
         dist.destroy_process_group()
 
@@ -65,7 +69,8 @@ def test_sample_sharded_merge_matches_single_process():
     want_flag = int(bool((ess < 0.1 * S).any()))
     got = torch.zeros_like(w)
     for r in range(world):
-        s_off, w_local, ess_r, flag, b_loc = out[r]
+        s_off, w_local, ess_r, flag, b_loc, seeds = out[r]
+        assert seeds == out[0][5] and len(set(seeds)) == 3
         got[:, s_off: s_off + w_local.shape[1]] = w_local
         torch.testing.assert_close(ess_r, ess, rtol=1e-5, atol=1e-6)
         assert flag == want_flag  # identical on every rank
