@@ -54,7 +54,9 @@ __device__ __forceinline__ uint4 philox4x32_10_rk(uint4 c, const uint32_t (&rk)[
 
 // uint32 -> float in (0,1): 24 random bits, centred, never 0 or 1.
 __device__ __forceinline__ float u01(uint32_t x) {
-  return (static_cast<float>(x >> 8) + 0.5f) * 5.9604644775390625e-8f;  // 2^-24
+  // (N + 0.5) 2^-24 with N = x >> 8: one FMA -- N 2^-24 + 2^-25 is rounded once, exactly like N + 0.5 (scaling by a
+  // power of two commutes with the rounding), so the bits are those of the two-step form
+  return fmaf(static_cast<float>(x >> 8), 5.9604644775390625e-8f, 2.98023223876953125e-8f);
 }
 
 // Two uniforms -> two standard normals (Box-Muller).  Fast intrinsics: these only shape the

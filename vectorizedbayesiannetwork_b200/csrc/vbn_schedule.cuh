@@ -1154,8 +1154,9 @@ __device__ __forceinline__ void op_tab_plain(Ctx<RPT, NT, TC>& c, const VbnOp& o
     for (int j = 0; j < RPT; ++j) {
       const float4 r = __ldg(tab + cfg[j]);
       const float t = uu[j] * r.w;
-      const int k = ((t >= r.x) ? 1 : 0) + ((t >= r.y) ? 1 : 0) + ((t >= r.z) ? 1 : 0);
-      c.slot(out_slot, j) = static_cast<float>(k);
+      // class index as a float straight from the three compares (FSET.BF gives 1.0 / 0.0): no integer sum, no
+      // int -> float conversion
+      c.slot(out_slot, j) = ((t >= r.x) ? 1.0f : 0.0f) + ((t >= r.y) ? 1.0f : 0.0f) + ((t >= r.z) ? 1.0f : 0.0f);
     }
   } else {  // evidence: the per-query value is its own class index (softmax_nn.py:618-627 exact class match)
 #pragma unroll
@@ -1524,6 +1525,33 @@ __device__ __forceinline__ void bind_row(C& c, int j, int64_t r) {
   c.rows.logp[j] = 0.0f;
 }
 
+// row j of the thread = its row j-1 + STEP, for n_samples >= STEP: the (query, sample) pair moves by at most one query,
+// so no division is needed (the 64-bit one costs ~100 instructions per row: 13 % of a 37-op walk at 4 rows per thread)
+template <int STEP, class C>
+__device__ __forceinline__ void bind_next_row(C& c, int j) {
+  const ScheduleArgs& a = c.a;
+  const int64_t r = c.rows.r[j - 1] + STEP;  // (row j-1 is only clamped when it is itself out of range)
+  c.rows.valid[j] = c.rows.valid[j - 1] && r < a.n_rows;
+  if (c.rows.valid[j]) {
+    int64_t b = c.rows.lb[j - 1], s = c.rows.ls[j - 1] + STEP;
+    if (s >= a.n_samples) {
+      s -= a.n_samples;
+      ++b;
+    }
+    c.rows.r[j] = r;
+    c.rows.lb[j] = b;
+    c.rows.ls[j] = s;
+  } else {  // clamp to the last row, like bind_row
+    c.rows.r[j] = a.n_rows - 1;
+    c.rows.lb[j] = a.n_queries - 1;
+    c.rows.ls[j] = a.n_samples - 1;
+  }
+  c.rows.gb[j] = a.query_offset + static_cast<uint32_t>(c.rows.lb[j]);
+  c.rows.gs[j] = a.sample_offset + static_cast<uint32_t>(c.rows.ls[j]);
+  c.rows.logw[j] = 0.0f;
+  c.rows.logp[j] = 0.0f;
+}
+
 // walks every op of the schedule for the rows bound to this thread, then writes logw / logp
 template <bool HEAVY, int RPT, int NT, class TC>
 __device__ __forceinline__ void run_ops(Ctx<RPT, NT, TC>& c) {
@@ -1695,7 +1723,11 @@ __global__ void __launch_bounds__(NT, MIN_BLOCKS) schedule_kernel(const Schedule
     const int64_t base = tile * ROWS;
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
-      bind_row(c, j, base + j * NT + tid);
+      if (j == 0 || a.n_samples < NT) {
+        bind_row(c, j, base + j * NT + tid);  // 64-bit division: row -> (query, sample)
+      } else {
+        bind_next_row<NT>(c, j);              // row j = row j-1 + NT < one query further: a compare instead
+      }
       asm volatile("" : "+r"(c.rows.gs[j]), "+r"(c.rows.gb[j]));
     }
     run_ops<HEAVY>(c);
