@@ -770,7 +770,7 @@ def main() -> None:
             # the other BASELINE workloads, short runs in the same process: driver-visible numbers for all four
             others = {}
             for name in ("cfg2", "cfg3"):
-                others[name] = run_inference(name, d, steps=3, warmup=3, clocks=clocks)
+                others[name] = run_inference(name, d, steps=8, warmup=4, clocks=clocks)  # (~13 / ~7 ms steps)
             others["cfg4"] = run_kde(d, steps=3, warmup=3, clocks=clocks)
         else:
             # strong scaling of the one path with a data-path collective: cfg2 (64 x 1M), samples sharded
