@@ -1572,7 +1572,7 @@ __device__ __forceinline__ void run_ops(Ctx<RPT, NT, TC>& c) {
         // Fetching the kind-specific quads only after the flag test made every op pay two dependent L1
         // round trips (~125 + ~210 cycles measured: 17 % of the kernel's stall samples).
         // Ops that follow an MLP op are served from the descriptor tail of its weight image in shared memory.
-        const int4* dsc = c.tc.op_in_ring(i) ? c.tc.ring_ptr(i) : src;
+        const int4* dsc = c.tc.next_desc();
         const int4 q0 = dsc[0];  // kind, flags, dim, n_par -- decides which other quads the op reads (a second
                                  // round trip, ~30 cycles from shared memory; loading all eight up front costs 32
                                  // registers at the top of every op)

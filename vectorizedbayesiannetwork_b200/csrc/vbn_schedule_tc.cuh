@@ -275,8 +275,8 @@ struct TcMlp {
   uint32_t tm;         // TMEM base of the CTA's allocation
   uint32_t ctl;        // shared-space address of the control block: barriers at fixed offsets, weight ring behind it
   uint32_t role;       // wg | issuer << 8 | producer << 9 | (lane == 0) << 10 | (a ring slot is still held) << 11
-  uint32_t seg_org;    // descriptor tail of the ring slot held: shared-space address of op i = seg_org + 128 i ...
-  uint32_t seg;        // ... for seg_first <= i < seg_first + seg_cnt; seg = seg_first | seg_cnt << 16
+  const int4* dptr;    // descriptor of the NEXT op of the walk (generic address): runs through the global op list, or
+                       // through the descriptor tail of the ring slot held (re-pointed once per MLP, in layers_end)
   uint32_t w_buf;      // ring slot of the next MLP (w_iter % nbuf), and (w_iter / nbuf) & 1 in bit 8: running state
   uint32_t mma_phase;  // parity of the next completion of the mma barriers (all tiles of a thread move together)
   uint32_t nbuf;
@@ -294,17 +294,14 @@ struct TcMlp {
   __device__ __forceinline__ uint32_t full_bar(uint32_t buf) const { return ctl + kFull + 8 * buf; }
   __device__ __forceinline__ uint32_t empty_bar(uint32_t buf) const { return ctl + kEmpty + 8 * buf; }
   __device__ __forceinline__ uint32_t mma_bar(int j) const { return ctl + kMma + 8 * (wg() * RPT + j); }
-  // Descriptor of op i: from the tail of the weight image this warp still holds (cpds / plan.py: copies of the ops
-  // that follow an MLP op ride behind its weights), else from global memory.
-  __device__ __forceinline__ bool op_in_ring(int i) const {
-    return static_cast<uint32_t>(i) - (seg & 0xFFFFu) < (seg >> 16);
-  }
-  // generic-space address of op i's copy in the ring slot (one load path for both sources: no register shuffling
-  // at the join)
-  __device__ __forceinline__ const int4* ring_ptr(int i) const {
-    // (keeping the window's high word in a register of its own instead of the S2R this costs was measured slower:
-    // one more live value at 128 registers per thread means more spill traffic)
-    return reinterpret_cast<const int4*>(__cvta_shared_to_generic(seg_org + 128u * static_cast<uint32_t>(i)));
+  // Descriptor of the next op, and step.  One running generic pointer serves both sources -- the global op list and
+  // the copies that ride behind an MLP op's weights in the ring slot (plan.py: all ops up to and including the next
+  // MLP op, or none) -- so an op costs one 64-bit add instead of a range test, a shared-window lookup (S2R) and an
+  // address build.
+  __device__ __forceinline__ const int4* next_desc() {
+    const int4* d = dptr;
+    dptr = d + 8;
+    return d;
   }
   // gives the ring slot of the previous MLP back (its tail has been consumed) -- called when the next MLP starts and
   // at the end of the walk
@@ -316,7 +313,6 @@ struct TcMlp {
       if (role & 0x400u) mbar_arrive(empty_bar(buf));
       w_buf = buf + 1u == nbuf ? ((ph ^ 1u) << 8) : w_buf + 1u;
       role &= ~0x800u;
-      seg = 0u;
     }
   }
   __device__ __forceinline__ bool issuer() const { return (role & 0x100u) != 0; }
@@ -583,16 +579,19 @@ struct TcMlp {
     }
     mma_phase ^= 1u;
   }
-  // `op_index` = position of the MLP op in the schedule, `n_tail` = descriptors behind its weights in the image.
+  // `gop` = the MLP op in the global op list; layer_dim[7] = descriptors behind its weights in the image.
   // The ring slot stays held until the next MLP starts (release_held): the ops in between read their descriptors
   // from it.
-  __device__ __forceinline__ void layers_end(const VbnOp& op, int op_index) {
+  __device__ __forceinline__ void layers_end(const VbnOp& op, const VbnOp* gop) {
     mma_phase ^= 1u;
     const int k1 = op.tc[2], n3 = op.tc[3];
-    const uint32_t n_tail = static_cast<uint32_t>(op.layer_dim[7]);
     role |= 0x800u;
-    seg = static_cast<uint32_t>(op_index + 1) | (n_tail << 16);
-    seg_org = wbuf(w_buf & 0xFFu) + static_cast<uint32_t>(blob_bytes(k1, n3)) - 128u * static_cast<uint32_t>(op_index + 1);
+    if (op.layer_dim[7] != 0) {  // the ops up to and including the next MLP op ride behind the weights
+      dptr = reinterpret_cast<const int4*>(
+          __cvta_shared_to_generic(wbuf(w_buf & 0xFFu) + static_cast<uint32_t>(blob_bytes(k1, n3))));
+    } else {
+      dptr = reinterpret_cast<const int4*>(gop + 1);
+    }
   }
 
   // Generic consumer: outputs land in scratch rows 0..n_out-1 like the FFMA paths
@@ -614,7 +613,7 @@ struct TcMlp {
           if (o0 + q < n_out) c.scr(o0 + q, j) = __uint_as_float(v[q]);
       }
     }
-    layers_end(op, static_cast<int>(c.gop - c.a.ops));
+    layers_end(op, c.gop);
   }
 
   // VBN_F_MDNPLAIN: an MDN node (D = 1, K <= 5 components, <= 4 parent dims) that is only drawn
@@ -696,7 +695,7 @@ struct TcMlp {
         }
       }
     }
-    layers_end(op, static_cast<int>(c.gop - c.a.ops));
+    layers_end(op, c.gop);
   }
   template <class C>
   __device__ __forceinline__ void mdn_plain(C& c, const VbnOp& op) {
@@ -770,8 +769,7 @@ __global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const S
               (warp == ((tune & 2) ? 3 : 6) ? 0x200u : 0u) |
               (lane == 0 ? 0x400u : 0u);
   c.tc.w_buf = 0;
-  c.tc.seg = 0;
-  c.tc.seg_org = 0;
+  c.tc.dptr = nullptr;
   c.tc.mma_phase = 0;
   c.tc.nbuf = static_cast<uint32_t>(nbuf);
   c.tc.slot_bytes = static_cast<uint32_t>(slot_bytes);  // a kernel parameter: stays a constant-bank operand
@@ -788,6 +786,7 @@ __global__ void __launch_bounds__(NWG* kWgThreads, 1) schedule_tc_kernel(const S
       asm volatile("" : "+r"(c.rows.gs[j]), "+r"(c.rows.gb[j]), "+l"(c.rows.r[j]), "+r"(row_ok));
       c.rows.valid[j] = row_ok != 0;
     }
+    c.tc.dptr = reinterpret_cast<const int4*>(a.ops);
     run_ops<true>(c);
     c.tc.release_held();  // the last MLP's ring slot (the ops behind it read their descriptors from its tail)
   }

@@ -386,7 +386,8 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
         for k, (i, w) in enumerate(tc_ops):
             nxt = tc_ops[k + 1][0] if k + 1 < len(tc_ops) else len(order) - 1
             room = (L.TC_WBUF_BYTES - 4 * int(w.size)) // 128
-            n_tail = max(0, min(nxt - i, room)) if (_tails_enabled() and len(order) < 65536) else 0
+            # all or nothing: the kernel walks one running descriptor pointer, re-pointed once per MLP op
+            n_tail = (nxt - i) if (_tails_enabled() and 0 < nxt - i <= room) else 0
             tail_of.append(n_tail)
             ops[i]["layer_dim"][7] = n_tail
         offs = []
