@@ -99,7 +99,9 @@ extern "C" {
                                   fixed[][B] row (scored); aux[0..1] = packed parent slots.
                                   The kernel reads quads 0,4,5,6                                            */
 #define VBN_F_LGPLAIN 0x80     /* LGFAST op that is only drawn: Philox, per-row stream, no store,
-                                  no density -- the kernel reads nothing but quads 0,4,5,6      */
+                                  no density -- the kernel reads nothing but quads 0,4,5,6.  Its parent
+                                  slots are one word each: aux[0], aux[1], layer_dim[2], layer_dim[3]
+                                  (2 ln scale / var are only read by scored ops)                */
 
 /* activations of the MLP CPDs (gaussian_nn.py:16-34) */
 #define VBN_ACT_RELU 0

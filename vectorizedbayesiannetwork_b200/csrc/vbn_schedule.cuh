@@ -539,7 +539,9 @@ __device__ __forceinline__ void op_lg_fast(Ctx<RPT, NT, TC>& c, const VbnOp& op)
 }
 
 // VBN_F_LGPLAIN: an LGFAST op that is simply drawn (Philox, per-row stream, no store, no density).
-// Everything it needs is in quads 0, 4, 5, 6: aux[] = {parent slots 0|1<<16, 2|3<<16, out_slot, n_off}.
+// Everything it needs is in quads 0, 4, 5, 6: aux[] = {parent slot 0, parent slot 1, out_slot, n_off}, parent slots 2
+// and 3 in layer_dim[2..3] (where a scored LG op keeps 2 ln scale and the variance): one word per slot, so a parent's
+// shared-memory address is one shift-add instead of extract + scale + add.
 // This is the inner loop of linear-Gaussian chains (BASELINE cfg2) and of the LG half of cfg5.
 template <int RPT, int NT, class TC>
 __device__ __forceinline__ void op_lg_plain(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
@@ -551,7 +553,7 @@ __device__ __forceinline__ void op_lg_plain(Ctx<RPT, NT, TC>& c, const VbnOp& op
   for (int p = 0; p < 4; ++p) {
     if (p < Dp) {
       const float w = __int_as_float(op.layer_dim[4 + p]);
-      const int ps = (op.aux[p >> 1] >> (16 * (p & 1))) & 0xFFFF;
+      const int ps = p < 2 ? op.aux[p] : op.layer_dim[p];
 #pragma unroll
       for (int j = 0; j < RPT; ++j) loc[j] = fmaf(c.slot(ps, j), w, loc[j]);
     }

@@ -443,6 +443,8 @@ struct TcMlp {
     for (int q = 0; q < 8; ++q) lds_f32x4_as_x2(l1 + 4 * (4 * kHidden + 4 * q), h[2 * q], h[2 * q + 1]);
 #pragma unroll
     for (int p = 0; p < DP; ++p) {
+      // (one word per parent slot, as op_lg_plain reads them, was measured slower here: 3 more live descriptor words
+      // at 128 registers per thread doubled the spill traffic, cfg5 66.0 -> 68.9 ms)
       float z = c.slot((op.aux[1 + (p >> 1)] >> (16 * (p & 1))) & 0xFFFF, j);
       if (norm) z = __fdiv_rn(z - __ldg(norm + p), __ldg(norm + DP + p));
       unsigned long long zz;

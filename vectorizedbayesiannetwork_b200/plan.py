@@ -369,6 +369,11 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
                 if (r.src == "sample" and not r.shared and not r.inject and not r.store
                         and not r.add_logw and not r.out_logp):
                     flags |= L.F_LGPLAIN
+                    # op_lg_plain reads one word per parent slot: 0, 1 in aux[0..1], 2, 3 in layer_dim[2..3]
+                    # (2 ln scale / var: only a scored op needs them)
+                    a0, a1 = int(op["aux"][0]), int(op["aux"][1])
+                    op["aux"][0], op["aux"][1] = a0 & 0xFFFF, (a0 >> 16) & 0xFFFF
+                    op["layer_dim"][2], op["layer_dim"][3] = a1 & 0xFFFF, (a1 >> 16) & 0xFFFF
             op["flags"] = flags
             n_scratch = max(n_scratch, pk.scratch)
             heavy = heavy or pk.heavy
