@@ -98,6 +98,8 @@ extern "C" {
                                   C | strict << 16; layer_dim[6] = out_slot; layer_dim[7] = u_off (drawn) or the
                                   fixed[][B] row (scored); aux[0..1] = packed parent slots.
                                   The kernel reads quads 0,4,5,6                                            */
+#define VBN_F_MDNFAST 0x2000   /* MDNPLAIN op with K = 3, ReLU and the first layer on the FP32 pipe (tc[2] == 0): the
+                                  tcgen05 kernel reads quads 0,2,6,7 only; tc[1] = out_slot | tail count << 16         */
 #define VBN_F_LGPLAIN 0x80     /* LGFAST op that is only drawn: Philox, per-row stream, no store,
                                   no density -- the kernel reads nothing but quads 0,4,5,6.  Its parent
                                   slots are one word each: aux[0], aux[1], layer_dim[2], layer_dim[3]

@@ -8,6 +8,7 @@ import pytest
 import torch
 
 import vectorizedbayesiannetwork_b200 as V
+from vectorizedbayesiannetwork_b200 import _lib as L
 from vectorizedbayesiannetwork_b200 import synthetic as S
 from vectorizedbayesiannetwork_b200.cpds import _core_matrix_image, _split_tf32, pack_mlp_tc
 from vectorizedbayesiannetwork_b200.plan import Role, compile_schedule
@@ -70,7 +71,13 @@ def test_plan_marks_tensor_core_ops(monkeypatch):
         want = spec["cpds"][n]["kind"] == "mdn" and spec["cpds"][n]["input_dim"] > 0
         assert bool(op["tc"][0]) == want
         if want:
-            assert op["tc"][1] % 4 == 0 and op["tc"][2] == 0 and op["tc"][3] == 16  # K1 = 0: first layer on the FP32 pipe
+            assert op["tc"][2] == 0 and op["tc"][3] == 16  # K1 = 0: first layer on the FP32 pipe
+            if op["flags"] & L.F_MDNFAST:  # short descriptor: out_slot | tail count << 16 ride in tc[1]
+                assert op["tc"][1] & 0xFFFF == op["out_slot"] and op["tc"][1] >> 16 == op["layer_dim"][7]
+            else:
+                assert op["tc"][1] % 4 == 0
+    assert all(off % 4 == 0 for off, _ in prog.tc_list)
+    assert any(op["flags"] & L.F_MDNFAST for op in prog.ops)
     assert not compile_schedule(spec["topo"], spec["parents"], cpds, roles, use_tc=False).tc
 
 

@@ -17,7 +17,7 @@ OP_NONE, OP_LG, OP_GNN, OP_MDN, OP_SNN, OP_KDE, OP_TAB, OP_RFF = 0, 1, 2, 3, 4, 
 OP_TAKEW, OP_SELECT, OP_JUMP = 8, 9, 10
 SRC_SAMPLE, SRC_FIXED_Q, SRC_FIXED_ROW, SRC_SLOT = 0, 1, 2, 3
 F_ADD_LOGW, F_OUT_LOGP, F_SHARED, F_FAST32, F_LGFAST, F_LGPLAIN = 0x4, 0x8, 0x10, 0x20, 0x40, 0x80
-F_PAR4, F_MDNPLAIN, F_OUT_PARAMS, F_MDNROOT, F_TABPLAIN = 0x100, 0x200, 0x400, 0x800, 0x1000
+F_PAR4, F_MDNPLAIN, F_OUT_PARAMS, F_MDNROOT, F_TABPLAIN, F_MDNFAST = 0x100, 0x200, 0x400, 0x800, 0x1000, 0x2000
 ACT = {"relu": 0, "tanh": 1, "gelu": 2, "elu": 3}
 WITHIN_BIN = {"uniform": 0, "triangular": 1, "gaussian": 2}
 MAX_LAYERS = 8

@@ -668,12 +668,7 @@ __device__ __forceinline__ void op_gnn(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
 // ---------------------------------------------------------------------------------------
 template <int RPT, int NT, class TC>
 __device__ __forceinline__ void op_mdn(Ctx<RPT, NT, TC>& c, const VbnOp& op) {
-  if constexpr (TC::kEnabled) {
-    if (op.flags & VBN_F_MDNPLAIN) {  // drawn-only node with a tensor-core MLP: register-resident tail
-      c.tc.mdn_plain(c, op);
-      return;
-    }
-  }
+  // (VBN_F_MDNPLAIN ops of the tensor-core kernel never get here: run_ops hands them to TcMlp::mdn_plain_body)
   const float* P = c.a.params + op.param_off;
   const int D = op.dim, K = op.k;
   const float min_scale = __ldg(P);
@@ -1589,9 +1584,17 @@ __device__ __forceinline__ void run_ops(Ctx<RPT, NT, TC>& c) {
           } else if (q0.y & VBN_F_MDNROOT) {
             ld[4] = dsc[4]; ld[5] = dsc[5]; ld[6] = dsc[6]; ld[7] = dsc[7];
             op_mdn_root(c, lop);
+          } else if (q0.y & VBN_F_MDNFAST) {
+            // the reference's default MDN (K = 3, ReLU, first layer on the FP32 pipe): three quads instead of six --
+            // out_slot and the tail count ride in tc[1], which the kernel does not read otherwise
+            ld[2] = dsc[2]; ld[6] = dsc[6]; ld[7] = dsc[7];
+            lop.out_slot = lop.tc[1] & 0xFFFF;
+            lop.layer_dim[7] = static_cast<int>(static_cast<uint32_t>(lop.tc[1]) >> 16);
+            c.tc.template mdn_plain_body<true>(c, lop);
+            store_value(c, lop);
           } else {
             ld[1] = dsc[1]; ld[2] = dsc[2]; ld[3] = dsc[3]; ld[5] = dsc[5]; ld[6] = dsc[6]; ld[7] = dsc[7];
-            c.tc.mdn_plain(c, lop);
+            c.tc.template mdn_plain_body<false>(c, lop);
             store_value(c, lop);  // a plain node may still be the stored target
           }
           continue;

@@ -699,16 +699,9 @@ struct TcMlp {
     }
     layers_end(op, c.gop);
   }
-  template <class C>
-  __device__ __forceinline__ void mdn_plain(C& c, const VbnOp& op) {
-    // the reference's defaults (mdn.py: n_components = 3 is what BASELINE cfg5 uses, ReLU, first layer on the FP32
-    // pipe) get a body with every one of those choices made at compile time
-    if (op.k == 3 && op.act == VBN_ACT_RELU && op.tc[2] == 0) {
-      mdn_plain_body<true>(c, op);
-    } else {
-      mdn_plain_body<false>(c, op);
-    }
-  }
+  // mdn_plain_body<true>: the reference's defaults (mdn.py: n_components = 3 is what BASELINE cfg5 uses, ReLU, first
+  // layer on the FP32 pipe) get a body with every one of those choices made at compile time; the plan compiler marks
+  // those ops VBN_F_MDNFAST (run_ops fetches a shorter descriptor for them).
 };
 
 // The kernel.  grid <= #SMs (one CTA per SM), NWG * 128 threads, NWG * RPT * 128 rows per pass.

@@ -323,6 +323,9 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
                             and r.src == "sample" and not r.shared and not r.inject
                             and not r.add_logw and not r.out_logp and not r.out_params):
                         flags |= L.F_MDNPLAIN
+                        if (pk.k == 3 and int(op["act"]) == L.ACT["relu"] and int(op["tc"][2]) == 0
+                                and slot_of[n] < 65536):
+                            flags |= L.F_MDNFAST
             if int(op["tc"][0]) and int(op["tc"][2]) == 0 and not (flags & L.F_PAR4):
                 # the FP32-pipe first layer reads its parent slots from the descriptor (cpds.pack_mlp_tc l1_fma)
                 raise ValueError(f"node '{n}': tensor-core image without first-layer MMA needs packed parent slots")
@@ -395,12 +398,15 @@ def compile_schedule(topo: Sequence[str], parents: Dict[str, Sequence[str]], cpd
             n_tail = (nxt - i) if (_tails_enabled() and 0 < nxt - i <= room) else 0
             tail_of.append(n_tail)
             ops[i]["layer_dim"][7] = n_tail
+            if int(ops[i]["flags"]) & L.F_MDNFAST:  # short descriptor fetch: out_slot and the tail count in tc[1]
+                ops[i]["tc"][1] = int(ops[i]["out_slot"]) | (n_tail << 16)
         offs = []
         for (i, w), n_tail in zip(tc_ops, tail_of):  # offsets first: a tail may hold the NEXT MLP op's descriptor
             pad = (-blob_len) % 4  # the bulk copy needs a 16-byte aligned source
             blob_len += pad
             offs.append((blob_len, pad))
-            ops[i]["tc"][1] = blob_len
+            if not int(ops[i]["flags"]) & L.F_MDNFAST:  # (informative: the kernel takes image offsets from tc_list)
+                ops[i]["tc"][1] = blob_len
             blob_len += int(w.size) + 32 * n_tail
         for (i, w), n_tail, (off, pad) in zip(tc_ops, tail_of, offs):
             if pad:
