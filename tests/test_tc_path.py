@@ -109,3 +109,37 @@ def test_tensor_core_kernel_matches_ffma_kernel(monkeypatch, n_queries, n_sample
     torch.testing.assert_close(w1.sum(1), torch.ones(n_queries), rtol=1e-4, atol=1e-4)
     badw = ((w1 - w0).abs() > 1e-7 + 2e-4 * w0.abs()).float().mean().item()
     assert badw < 1e-3, f"fraction of mismatching weights {badw}"
+
+
+@pytest.mark.gpu
+def test_long_runs_between_mlp_ops_leave_the_descriptor_tail(monkeypatch):
+    """MLP ops followed by more ops than a ring slot can carry get no descriptor tail (plan.py: all or nothing): the
+    walk's running descriptor pointer then continues in the global op list and returns to a ring slot at the next
+    MLP op with a tail (TcMlp::layers_end, both branches)."""
+    import random
+    dev = torch.device("cuda", 0)
+    rng, gen = random.Random(7), torch.Generator().manual_seed(7)
+    names = [f"n{i}" for i in range(400)]
+    parents, cpds = {}, {}
+    for i, name in enumerate(names):
+        ps = sorted(rng.sample(range(max(0, i - 20), i), min(rng.randint(1, 3), i))) if i else []
+        parents[name] = [names[p] for p in ps]
+        cpds[name] = S.mdn_cpd(gen, len(ps)) if i in (5, 200, 390) else S.lg_cpd(gen, len(ps))
+    spec = {"nodes": names, "parents": parents, "topo": list(names), "cpds": cpds}
+    g = torch.Generator().manual_seed(5)
+    q = {"target": "n395", "evidence": {n: 0.3 * torch.randn(4, 1, generator=g) for n in names[-2:]}}
+    monkeypatch.setenv("VBN_TC", "0")
+    w0, s0, tc0 = _run(spec, q, "likelihood_weighting", 1024, 99, dev)
+    monkeypatch.setenv("VBN_TC", "1")
+    model = V.VBN.from_spec(spec, device=dev)
+    model.set_inference_method("likelihood_weighting", n_samples=1024)
+    w1, s1 = model.infer_posterior(q, seed=99)
+    prog = next(iter(model._inference._runner._cache.values())).program
+    tails = [int(op["layer_dim"][7]) for op in prog.ops if op["tc"][0]]
+    assert prog.tc and not tc0 and tails[:2] == [0, 0] and tails[2] > 0, tails
+    w1, s1 = w1.cpu(), s1.cpu()
+    assert torch.isfinite(s1).all() and torch.isfinite(w1).all()
+    bad = ((s1 - s0).abs() > 1e-5 + 1e-5 * s0.abs()).float().mean().item()
+    assert bad < 1e-4, f"fraction of mismatching samples {bad}"
+    badw = ((w1 - w0).abs() > 1e-7 + 2e-4 * w0.abs()).float().mean().item()
+    assert badw < 1e-3, f"fraction of mismatching weights {badw}"
