@@ -27,7 +27,9 @@
 extern "C" {
 #endif
 
-#define VBN_CUDA_ABI_VERSION 5
+/* 6: descriptor layout of VBN_F_LGPLAIN ops (one word per parent slot), VBN_F_MDNFAST, all-or-nothing descriptor
+   tails of tensor-core images -- a library and a plan compiler of different versions must not be mixed */
+#define VBN_CUDA_ABI_VERSION 6
 
 /* error codes */
 #define VBN_OK 0

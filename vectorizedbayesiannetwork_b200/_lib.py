@@ -10,7 +10,7 @@ import numpy as np
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libvbn_cuda.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # op kinds / flags (keep in sync with include/vbn_cuda.h)
 OP_NONE, OP_LG, OP_GNN, OP_MDN, OP_SNN, OP_KDE, OP_TAB, OP_RFF = 0, 1, 2, 3, 4, 5, 6, 7
