@@ -28,6 +28,45 @@ def test_library_exports_every_header_symbol():
     assert lib.vbn_cuda_abi_version() == L.ABI_VERSION
 
 
+def test_stale_library_is_refused(monkeypatch):
+    """A library built from another revision of the descriptor layout must not be used: load() compares
+    vbn_cuda_abi_version() with the Python side's ABI_VERSION and raises (no silent mis-read of new descriptors)."""
+    header = open(os.path.join(ROOT, "include", "vbn_cuda.h")).read()
+    assert int(re.search(r"#define VBN_CUDA_ABI_VERSION (\d+)", header).group(1)) == L.ABI_VERSION
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "ABI_VERSION", L.ABI_VERSION + 1)
+    with pytest.raises(L.VbnCudaError, match="ABI version mismatch"):
+        L.load()
+
+
+def test_descriptor_tails_are_all_or_nothing():
+    """plan.py: an MLP op carries the descriptors of ALL ops up to and including the next MLP op in its weight image,
+    or none (the tcgen05 kernel walks one running descriptor pointer, re-pointed once per MLP op)."""
+    import random
+    from vectorizedbayesiannetwork_b200 import synthetic as S
+    from vectorizedbayesiannetwork_b200.plan import Role, compile_schedule
+    import vectorizedbayesiannetwork_b200 as V
+    rng, gen = random.Random(7), torch.Generator().manual_seed(7)
+    names = [f"n{i}" for i in range(300)]
+    parents, cpds = {}, {}
+    mlp_at = (5, 9, 150, 290)
+    for i, name in enumerate(names):
+        ps = sorted(rng.sample(range(max(0, i - 20), i), min(rng.randint(1, 3), i))) if i else []
+        parents[name] = [names[p] for p in ps]
+        cpds[name] = S.mdn_cpd(gen, len(ps)) if i in mlp_at else S.lg_cpd(gen, len(ps))
+    built = {n: V.cpd_from_spec(c, device="cpu") for n, c in cpds.items()}
+    prog = compile_schedule(names, parents, built, {n: Role() for n in names}, use_tc=True)
+    tc_idx = [i for i, op in enumerate(prog.ops) if op["tc"][0]]
+    assert [prog.nodes[i] for i in tc_idx] == [f"n{i}" for i in mlp_at]
+    tails = [int(prog.ops[i]["layer_dim"][7]) for i in tc_idx]
+    assert tails == [4, 0, 0, 9], tails  # 9 -> 150 and 150 -> 290 do not fit a ring slot: no tail at all
+    for (off, nbytes), i, t in zip(prog.tc_list, tc_idx, tails):
+        assert nbytes % 128 == 0 or t == 0
+        if t:  # the tail is a verbatim copy of the following descriptors
+            tail = prog.params[off + nbytes // 4 - 32 * t: off + nbytes // 4]
+            np.testing.assert_array_equal(tail.view(np.int32), prog.ops[i + 1: i + 1 + t].view(np.int32).ravel())
+
+
 def test_struct_layouts_match_header():
     assert L.OP_DTYPE.itemsize == 128
     assert C.sizeof(L.ProgramDesc) == 88  # (has_tables fills the former padding)
