@@ -1722,7 +1722,15 @@ __global__ void __launch_bounds__(NT, MIN_BLOCKS) schedule_kernel(const Schedule
   // front of every generator refill -- instead of keeping one register each (same finding as in the tcgen05 kernel).
   int tid = threadIdx.x;
   asm volatile("" : "+r"(tid));
-  Ctx<RPT, NT, typename std::conditional<HEAVY, NoTc, LightPolicyT<TAB>>::type> c(a, smem + tid, 0);
+  // The thread's column of the slot area as ONE opaque pointer that is still known to point to shared memory:
+  // otherwise ptxas rebuilds the address of every slot access from the shared-window base (S2UR CgaCtaId, UMOV,
+  // ULEA) plus the thread index -- five instructions at the head of each parent read instead of one multiply-add.
+  float* col = smem + tid;
+#ifdef __CUDA_ARCH__
+  asm volatile("" : "+l"(col));
+  __builtin_assume(__isShared(col));
+#endif
+  Ctx<RPT, NT, typename std::conditional<HEAVY, NoTc, LightPolicyT<TAB>>::type> c(a, col, 0);
   const int64_t n_tiles = (a.n_rows + ROWS - 1) / ROWS;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t base = tile * ROWS;
