@@ -98,7 +98,7 @@ extern "C" {
                                   parameter blob of the 128-bit-row table the op reads -- drawn: cdf4[n_cfg][4] =
                                   {c_0 .. c_{C-2}, +inf .., total}, scored: logp4[n_cfg][4] --; layer_dim[5] =
                                   C | strict << 16; layer_dim[6] = out_slot; layer_dim[7] = u_off (drawn) or the
-                                  fixed[][B] row (scored); aux[0..1] = packed parent slots.
+                                  fixed[][B] row (scored); aux[0..3] = parent slots, one word each.
                                   The kernel reads quads 0,4,5,6                                            */
 #define VBN_F_MDNFAST 0x2000   /* MDNPLAIN op with K = 3, ReLU and the first layer on the FP32 pipe (tc[2] == 0): the
                                   tcgen05 kernel reads quads 0,2,6,7 only; tc[1] = out_slot | tail count << 16         */

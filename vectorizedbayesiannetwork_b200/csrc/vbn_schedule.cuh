@@ -1126,7 +1126,7 @@ __device__ __forceinline__ void op_tab_plain(Ctx<RPT, NT, TC>& c, const VbnOp& o
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
     if (p < Dp) {
-      const int ps = (op.aux[p >> 1] >> (16 * (p & 1))) & 0xFFFF;
+      const int ps = op.aux[p];
       const int stride = op.layer_dim[p] & 0xFFFF, card = (op.layer_dim[p] >> 16) & 0x7FFF;
       if (op.layer_dim[p] < 0) {  // bit 31: the parent is drawn by a plain table op of this schedule -- always a valid index
 #pragma unroll

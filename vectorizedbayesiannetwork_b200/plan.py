@@ -114,8 +114,7 @@ def _tab_plain_fields(pk: Packed, slots: Sequence[int], param_off: int, out_slot
     words[6] = int(out_slot)
     words[7] = int(last_word)
     sl = list(slots) + [0] * (4 - len(slots))
-    words[8] = sl[0] | (sl[1] << 16)
-    words[9] = sl[2] | (sl[3] << 16)
+    words[8:12] = [int(x) for x in sl]  # one word per parent slot (a slot address is then one multiply-add)
     return words
 
 
