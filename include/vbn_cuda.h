@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-/* 6: descriptor layout of VBN_F_LGPLAIN ops (one word per parent slot), VBN_F_MDNFAST, all-or-nothing descriptor
+/* 6: descriptor layout of VBN_F_LGPLAIN / VBN_F_TABPLAIN ops (one word per parent slot), VBN_F_MDNFAST, all-or-nothing descriptor
    tails of tensor-core images -- a library and a plan compiler of different versions must not be mixed */
 #define VBN_CUDA_ABI_VERSION 6
 
